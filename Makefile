@@ -1,0 +1,29 @@
+# Builds hybvio_b200/libhybvio_b200.so (sm_100a only) and the test oracles.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+CSRC := hybvio_b200/csrc
+OBJ := build/obj
+LIB := hybvio_b200/libhybvio_b200.so
+CU := $(wildcard $(CSRC)/*.cu)
+OBJS := $(patsubst $(CSRC)/%.cu,$(OBJ)/%.o,$(CU))
+
+all: $(LIB) oracle
+
+$(OBJ)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/hybvio_b200.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) $(if $(filter lk,$*),--fmad=false,) -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; false)
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker --version-script=$(CSRC)/exports.map
+
+oracle: oracle/libhv_oracle.so
+oracle/libhv_oracle.so: $(wildcard oracle/*.c)
+	gcc -O2 -ffp-contract=off -fPIC -shared -o $@ $^ -lm
+
+ref:
+	$(MAKE) -C oracle/ref_build -f Makefile.lk -j8
+
+clean:
+	rm -rf build $(LIB) oracle/libhv_oracle.so
+.PHONY: all oracle ref clean

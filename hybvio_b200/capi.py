@@ -1,0 +1,237 @@
+"""ctypes binding of libhybvio_b200.so (include/hybvio_b200.h).
+
+Harness-side plumbing only: tests/ and bench.py drive the C ABI through this module exactly the way the
+reference-side C++ adapters (hybvio_b200/host/) do. There is no CPU fallback: a missing library or a missing
+GPU raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhybvio_b200.so")
+
+c_int, c_double, c_void_p, c_size_t = ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t
+
+
+class HvError(RuntimeError):
+    pass
+
+
+class EkfParams(ctypes.Structure):
+    _fields_ = [
+        ("camera_trail_length", c_int), ("hybrid_map_size", c_int),
+        ("noise_scale", c_double), ("gravity", c_double),
+        ("noise_initial_pos", c_double), ("noise_initial_vel", c_double), ("noise_initial_ori", c_double),
+        ("noise_initial_bga", c_double), ("noise_initial_baa", c_double), ("noise_initial_bat", c_double),
+        ("noise_initial_sft", c_double),
+        ("noise_initial_pos_trail", c_double), ("noise_initial_ori_trail", c_double),
+        ("noise_process_acc", c_double), ("noise_process_gyro", c_double),
+        ("noise_process_baa", c_double), ("noise_process_baa_rev", c_double),
+        ("noise_process_bga", c_double), ("noise_process_bga_rev", c_double),
+        ("augment_r", c_double), ("init_zupt_r", c_double), ("rotation_zupt_r", c_double),
+    ]
+
+
+class LkJob(ctypes.Structure):
+    _fields_ = [("prev", c_void_p), ("next", c_void_p), ("d_prev_xy", c_void_p), ("d_next_xy", c_void_p),
+                ("d_status", c_void_p), ("d_track_status", c_void_p), ("n", c_int), ("use_initial", c_int)]
+
+
+_lib = None
+
+
+def load():
+    """Loads the CUDA library; fails loudly when it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make` (nvcc, sm_100a). hybvio_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.hv_version.restype = ctypes.c_char_p
+    lib.hv_last_error.restype = ctypes.c_char_p
+    lib.hv_ctx_stream.restype = c_void_p
+    lib.hv_ctx_stream.argtypes = [c_void_p]
+    lib.hv_ctx_launch_count.restype = ctypes.c_longlong
+    lib.hv_ctx_launch_count.argtypes = [c_void_p]
+    lib.hv_ctx_create.argtypes = [c_int, ctypes.POINTER(c_void_p)]
+    lib.hv_ctx_create_on_stream.argtypes = [c_int, c_void_p, ctypes.POINTER(c_void_p)]
+    lib.hv_ctx_destroy.argtypes = [c_void_p]
+    lib.hv_ctx_sync.argtypes = [c_void_p]
+    lib.hv_pyr_create.argtypes = [c_void_p, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]
+    lib.hv_pyr_release.argtypes = [c_void_p]
+    lib.hv_pyr_levels.argtypes = [c_void_p]
+    lib.hv_pyr_level_size.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    lib.hv_pyr_build.argtypes = [c_void_p, c_void_p, c_size_t]
+    lib.hv_pyr_build_batch.argtypes = [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t), c_int, c_int]
+    lib.hv_pyr_download_level.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
+    lib.hv_pyr_download_level_padded.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
+    lib.hv_lk_track.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double]
+    lib.hv_lk_track_device.argtypes = lib.hv_lk_track.argtypes
+    lib.hv_lk_track_batch_device.argtypes = [c_void_p, ctypes.POINTER(LkJob), c_int, c_int, c_double, c_double]
+    _bind_ekf(lib)
+    _lib = lib
+    return lib
+
+
+def _bind_ekf(lib):
+    if not hasattr(lib, "hv_ekf_create"):
+        return
+    dp = ctypes.POINTER(c_double)
+    lib.hv_ekf_default_params.argtypes = [ctypes.POINTER(EkfParams)]
+    lib.hv_ekf_default_params.restype = None
+    lib.hv_ekf_create.argtypes = [c_void_p, ctypes.POINTER(EkfParams), ctypes.POINTER(c_void_p)]
+    lib.hv_ekf_destroy.argtypes = [c_void_p]
+    lib.hv_ekf_clone.argtypes = [c_void_p, ctypes.POINTER(c_void_p)]
+    for name in ("hv_ekf_state_dim", "hv_ekf_pose_count", "hv_ekf_was_stationary", "hv_ekf_unaugment", "hv_ekf_symmetrize",
+                 "hv_ekf_condition_on_last_pose", "hv_ekf_lock_biases", "hv_ekf_update_zupt_initialization"):
+        getattr(lib, name).argtypes = [c_void_p]
+    lib.hv_ekf_platform_time.argtypes = [c_void_p]
+    lib.hv_ekf_platform_time.restype = c_double
+    lib.hv_ekf_history_time.argtypes = [c_void_p, c_int]
+    lib.hv_ekf_history_time.restype = c_double
+    lib.hv_ekf_set_first_sample_time.argtypes = [c_void_p, c_double]
+    lib.hv_ekf_upload.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.hv_ekf_download.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.hv_ekf_download_inertial.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.hv_ekf_set_inertial_state.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.hv_ekf_set_process_noise.argtypes = [c_void_p, c_void_p]
+    lib.hv_ekf_get_dydx.argtypes = [c_void_p, c_void_p]
+    lib.hv_ekf_initialize_orientation.argtypes = [c_void_p, c_void_p]
+    lib.hv_ekf_predict.argtypes = [c_void_p, c_double, c_void_p, c_void_p]
+    lib.hv_ekf_update_zupt.argtypes = [c_void_p, c_double]
+    lib.hv_ekf_update_zrupt.argtypes = [c_void_p, c_void_p]
+    lib.hv_ekf_update_pseudo_velocity.argtypes = [c_void_p, c_double, c_double]
+    lib.hv_ekf_update_position.argtypes = [c_void_p, c_void_p, c_double]
+    lib.hv_ekf_update_zero_height.argtypes = [c_void_p, c_double]
+    lib.hv_ekf_update_orientation.argtypes = [c_void_p, c_void_p, c_double]
+    lib.hv_ekf_visual_check.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double,
+                                        ctypes.POINTER(c_int), dp]
+    lib.hv_ekf_visual_update.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double]
+    lib.hv_ekf_visual_check_update.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double,
+                                               ctypes.POINTER(c_int), dp, c_void_p]
+    lib.hv_ekf_visual_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p]
+    lib.hv_ekf_augment.argtypes = [c_void_p, c_int]
+    lib.hv_ekf_normalize_quaternions.argtypes = [c_void_p, c_int]
+    lib.hv_ekf_translate_to.argtypes = [c_void_p, c_void_p]
+    lib.hv_ekf_transform_to.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
+    lib.hv_ekf_insert_map_point.argtypes = [c_void_p, c_int, c_void_p]
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise HvError(f"{what} failed with hv_status {rc}: {load().hv_last_error().decode()}")
+
+
+def _ptr(a):
+    """Address of a numpy array / torch tensor / raw int."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()   # torch tensor
+
+
+class Context:
+    """hv_ctx: one CUDA stream's worth of tracker + EKF work (the reference's Session, src/odometry/backend.cpp)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        h = c_void_p()
+        if stream is None:
+            check(self.lib.hv_ctx_create(device, ctypes.byref(h)), "hv_ctx_create")
+        else:
+            check(self.lib.hv_ctx_create_on_stream(device, c_void_p(stream), ctypes.byref(h)), "hv_ctx_create_on_stream")
+        self.h = h
+        self.device = device
+
+    def sync(self):
+        check(self.lib.hv_ctx_sync(self.h), "hv_ctx_sync")
+
+    @property
+    def stream(self):
+        return self.lib.hv_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return self.lib.hv_ctx_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.hv_ctx_destroy(self.h)
+            self.h = None
+
+    # ---- tracker::ImagePyramid::Factory::compute
+    def pyramid(self, width, height, win=31, max_level=3):
+        return Pyramid(self, width, height, win, max_level)
+
+    def build_pyramids(self, pyrs, images, device=False):
+        """One launch for several images (stereo pair). images: numpy (host) or torch tensors (host pinned / device)."""
+        n = len(pyrs)
+        P = (c_void_p * n)(*[p.h for p in pyrs])
+        G = (c_void_p * n)(*[_ptr(im) for im in images])
+        S = (c_size_t * n)(*[_stride0(im) for im in images])
+        check(self.lib.hv_pyr_build_batch(P, G, S, n, 1 if device else 0), "hv_pyr_build_batch")
+
+    # ---- tracker::OpticalFlow::compute
+    def lk_track(self, prev, nxt, prev_xy, next_xy=None, max_iter=20, eps=0.03, min_eig=1e-3):
+        """Host-buffer LK. Returns (next_xy float32 (n,2), status uint8 (n,), track_status int32 (n,))."""
+        prev_xy = np.ascontiguousarray(prev_xy, dtype=np.float32)
+        n = prev_xy.shape[0]
+        use_initial = next_xy is not None
+        out = np.ascontiguousarray(next_xy, dtype=np.float32).copy() if use_initial else np.zeros((n, 2), np.float32)
+        status = np.zeros(n, np.uint8)
+        ts = np.zeros(n, np.int32)
+        check(self.lib.hv_lk_track(self.h, prev.h, nxt.h, _ptr(prev_xy), _ptr(out), _ptr(status), _ptr(ts), n,
+                                   1 if use_initial else 0, max_iter, eps, min_eig), "hv_lk_track")
+        return out, status, ts
+
+    def lk_track_device(self, prev, nxt, d_prev, d_next, d_status, d_ts, n, use_initial, max_iter=20, eps=0.03, min_eig=1e-3):
+        check(self.lib.hv_lk_track_device(self.h, prev.h, nxt.h, _ptr(d_prev), _ptr(d_next), _ptr(d_status), _ptr(d_ts), n,
+                                          1 if use_initial else 0, max_iter, eps, min_eig), "hv_lk_track_device")
+
+
+def _stride0(im):
+    if isinstance(im, np.ndarray):
+        return im.strides[0]
+    return im.stride(0) * im.element_size()
+
+
+class Pyramid:
+    """hv_pyr: tracker::ImagePyramid (src/tracker/image_pyramid.hpp:18-42)."""
+
+    def __init__(self, ctx, width, height, win, max_level):
+        self.ctx, self.lib = ctx, ctx.lib
+        h = c_void_p()
+        check(self.lib.hv_pyr_create(ctx.h, width, height, win, max_level, ctypes.byref(h)), "hv_pyr_create")
+        self.h = h
+        self.win = win
+        self.levels = self.lib.hv_pyr_levels(h)
+
+    def level_size(self, level):
+        w, h = c_int(), c_int()
+        check(self.lib.hv_pyr_level_size(self.h, level, ctypes.byref(w), ctypes.byref(h)), "hv_pyr_level_size")
+        return w.value, h.value
+
+    def build(self, gray):
+        assert gray.dtype == np.uint8 and gray.ndim == 2
+        check(self.lib.hv_pyr_build(self.h, _ptr(gray), gray.strides[0]), "hv_pyr_build")
+
+    def download(self, level, padded=False):
+        w, h = self.level_size(level)
+        if padded:
+            w, h = w + 2 * self.win, h + 2 * self.win
+        g = np.zeros((h, w), np.uint8)
+        d = np.zeros((h, w, 2), np.int16)
+        fn = self.lib.hv_pyr_download_level_padded if padded else self.lib.hv_pyr_download_level
+        check(fn(self.h, level, _ptr(g), _ptr(d)), "hv_pyr_download_level")
+        return g, d
+
+    def release(self):
+        if self.h:
+            self.lib.hv_pyr_release(self.h)
+            self.h = None

@@ -1,0 +1,327 @@
+// hybvio_b200/csrc/capi.cu -- C ABI (include/hybvio_b200.h): context, image pyramid, Lucas-Kanade.
+// The EKF entry points live in ekf_capi.cu.
+#include "capi_internal.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+static thread_local char g_err[512] = "";
+
+void hv_set_error(const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+
+extern "C" {
+
+const char* hv_version(void) { return "hybvio_b200 0.1 (sm_100a)"; }
+const char* hv_last_error(void) { return g_err; }
+
+int hv_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int ctx_create(int device, cudaStream_t stream, bool own, hv_ctx** out)
+{
+    if (!out) { hv_set_error("hv_ctx_create: out is NULL"); return HV_ERR_INVALID; }
+    *out = nullptr;
+    int n = hv_device_count();
+    if (n <= 0 || device < 0 || device >= n) {
+        hv_set_error("hv_ctx_create: no CUDA device %d (found %d). hybvio_b200 has no CPU fallback.", device, n);
+        return HV_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    HV_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        hv_set_error("hv_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return HV_ERR_NO_DEVICE;
+    }
+    HV_CUDA(cudaSetDevice(device));
+    hv_ctx* c = new hv_ctx;
+    c->device = device;
+    if (own) { HV_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
+    else c->stream = stream;
+    HV_CUDA(cudaMalloc(&c->d_table, sizeof(HvPyrDesc) * HV_TABLE_CAPACITY));
+    HV_CUDA(cudaMemset(c->d_table, 0, sizeof(HvPyrDesc) * HV_TABLE_CAPACITY));
+    for (int i = HV_TABLE_CAPACITY - 1; i >= 0; --i) c->freeSlots.push_back(i);
+    *out = c;
+    return HV_OK;
+}
+
+int hv_ctx_create(int device, hv_ctx** out) { return ctx_create(device, nullptr, true, out); }
+int hv_ctx_create_on_stream(int device, void* s, hv_ctx** out) { return ctx_create(device, (cudaStream_t)s, false, out); }
+
+int hv_ctx_destroy(hv_ctx* c)
+{
+    if (!c) return HV_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->d_table) cudaFree(c->d_table);
+    if (c->d_stage) cudaFree(c->d_stage);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_ekfStage) cudaFree(c->d_ekfStage);
+    if (c->h_ekfStage) cudaFreeHost(c->h_ekfStage);
+    if (c->ownStream) cudaStreamDestroy(c->stream);
+    delete c;
+    return HV_OK;
+}
+
+int hv_ctx_sync(hv_ctx* c)
+{
+    if (!c) { hv_set_error("hv_ctx_sync: NULL ctx"); return HV_ERR_INVALID; }
+    HV_CUDA(cudaStreamSynchronize(c->stream));
+    return HV_OK;
+}
+void* hv_ctx_stream(hv_ctx* c) { return c ? (void*)c->stream : nullptr; }
+long long hv_ctx_launch_count(hv_ctx* c) { return c ? c->launches : 0; }
+
+} // extern "C"
+
+int hv_ctx_reserve_stage(hv_ctx* c, size_t bytes)
+{
+    if (bytes <= c->stageBytes) return HV_OK;
+    HV_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d_stage) cudaFree(c->d_stage);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->d_stage = nullptr; c->h_stage = nullptr; c->stageBytes = 0;
+    size_t cap = 4096; while (cap < bytes) cap *= 2;
+    HV_CUDA(cudaMalloc(&c->d_stage, cap));
+    HV_CUDA(cudaMallocHost(&c->h_stage, cap));
+    c->stageBytes = cap;
+    return HV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pyramid
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+int hv_pyr_create(hv_ctx* c, int w, int h, int win, int maxLevel, hv_pyr** out)
+{
+    if (!c || !out || w <= 0 || h <= 0 || win <= 2 || maxLevel < 0) {
+        hv_set_error("hv_pyr_create: invalid argument (w=%d h=%d win=%d maxLevel=%d)", w, h, win, maxLevel);
+        return HV_ERR_INVALID;
+    }
+    if (maxLevel > HV_MAX_LEVELS - 1) {
+        hv_set_error("hv_pyr_create: maxLevel %d > %d unsupported", maxLevel, HV_MAX_LEVELS - 1);
+        return HV_ERR_UNSUPPORTED;
+    }
+    if (c->freeSlots.empty()) { hv_set_error("hv_pyr_create: more than %d live pyramids", HV_TABLE_CAPACITY); return HV_ERR_OOM; }
+    HV_CUDA(cudaSetDevice(c->device));
+    hv_pyr* p = new hv_pyr;
+    p->ctx = c; p->w = w; p->h = h; p->win = win;
+    // level geometry (OCV/video/src/lkpyramid.cpp:776-816)
+    int lw = w, lh = h, nl = 0;
+    size_t off = 0, goff[HV_MAX_LEVELS], doff[HV_MAX_LEVELS];
+    memset(&p->desc, 0, sizeof(p->desc));
+    for (int level = 0; level <= maxLevel; ++level) {
+        HvLevel& L = p->desc.lv[level];
+        L.w = lw; L.h = lh;
+        L.gpitch = (int)align_up((size_t)lw, 128);
+        L.dpitch = (int)align_up((size_t)lw, 32);
+        goff[level] = off; off = align_up(off + (size_t)L.gpitch * lh, 256);
+        doff[level] = off; off = align_up(off + (size_t)L.dpitch * lh * sizeof(short2), 256);
+        nl = level + 1;
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+        if (lw <= win || lh <= win) break;
+    }
+    p->nlevels = nl; p->desc.nlevels = nl; p->desc.win = win;
+    p->bytes = off;
+    cudaError_t e = cudaMalloc(&p->d_mem, off);
+    if (e != cudaSuccess) { delete p; hv_set_error("hv_pyr_create: cudaMalloc(%zu) failed: %s", off, cudaGetErrorString(e)); return HV_ERR_OOM; }
+    HV_CUDA(cudaMemsetAsync(p->d_mem, 0, off, c->stream));
+    for (int level = 0; level < nl; ++level) {
+        p->desc.lv[level].gray = (uint8_t*)p->d_mem + goff[level];
+        p->desc.lv[level].deriv = (short2*)((uint8_t*)p->d_mem + doff[level]);
+    }
+    p->slot = c->freeSlots.back(); c->freeSlots.pop_back();
+    HV_CUDA(cudaMemcpyAsync(c->d_table + p->slot, &p->desc, sizeof(HvPyrDesc), cudaMemcpyHostToDevice, c->stream));
+    HV_CUDA(cudaStreamSynchronize(c->stream));   // desc is on the stack-owned object; creation is rare
+    *out = p;
+    return HV_OK;
+}
+
+int hv_pyr_release(hv_pyr* p)
+{
+    if (!p) return HV_OK;
+    hv_ctx* c = p->ctx;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (p->d_mem) cudaFree(p->d_mem);
+    c->freeSlots.push_back(p->slot);
+    delete p;
+    return HV_OK;
+}
+
+int hv_pyr_levels(const hv_pyr* p) { return p ? p->nlevels : HV_ERR_INVALID; }
+
+int hv_pyr_level_size(const hv_pyr* p, int level, int* w, int* h)
+{
+    if (!p || level < 0 || level >= p->nlevels) { hv_set_error("hv_pyr_level_size: bad level"); return HV_ERR_INVALID; }
+    if (w) *w = p->desc.lv[level].w;
+    if (h) *h = p->desc.lv[level].h;
+    return HV_OK;
+}
+
+int hv_pyr_build_batch(hv_pyr* const* pyrs, const uint8_t* const* gray, const size_t* strides, int n, int srcIsDevice)
+{
+    if (!pyrs || !gray || !strides || n <= 0) { hv_set_error("hv_pyr_build_batch: invalid argument"); return HV_ERR_INVALID; }
+    hv_ctx* c = pyrs[0] ? pyrs[0]->ctx : nullptr;
+    if (!c) { hv_set_error("hv_pyr_build_batch: NULL pyramid"); return HV_ERR_INVALID; }
+    HV_CUDA(cudaSetDevice(c->device));
+    std::vector<unsigned short> idx(n);
+    int maxNl = 0;
+    for (int i = 0; i < n; i++) {
+        hv_pyr* p = pyrs[i];
+        if (!p || p->ctx != c || p->w != pyrs[0]->w || p->h != pyrs[0]->h || !gray[i] || strides[i] < (size_t)p->w) {
+            hv_set_error("hv_pyr_build_batch: pyramid %d invalid / different context or size", i);
+            return HV_ERR_INVALID;
+        }
+        const HvLevel& L0 = p->desc.lv[0];
+        // the frame lands directly in the level-0 buffer: level 0 of the pyramid IS the input image
+        HV_CUDA(cudaMemcpy2DAsync(L0.gray, L0.gpitch, gray[i], strides[i], (size_t)p->w, (size_t)p->h,
+                                  srcIsDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+        idx[i] = (unsigned short)p->slot;
+        if (p->nlevels > maxNl) maxNl = p->nlevels;
+    }
+    HV_CUDA(hv_launch_pyr_fused(c->d_table, idx.data(), n, pyrs[0]->w, pyrs[0]->h, maxNl, c->stream));
+    c->launches += (n + 59) / 60;
+    return HV_OK;
+}
+
+int hv_pyr_build(hv_pyr* p, const uint8_t* gray, size_t stride)
+{
+    return hv_pyr_build_batch(&p, &gray, &stride, 1, 0);
+}
+
+int hv_pyr_download_level(hv_pyr* p, int level, uint8_t* gray, int16_t* deriv)
+{
+    if (!p || level < 0 || level >= p->nlevels) { hv_set_error("hv_pyr_download_level: bad level"); return HV_ERR_INVALID; }
+    hv_ctx* c = p->ctx;
+    HV_CUDA(cudaSetDevice(c->device));
+    const HvLevel& L = p->desc.lv[level];
+    if (gray) HV_CUDA(cudaMemcpy2DAsync(gray, L.w, L.gray, L.gpitch, L.w, L.h, cudaMemcpyDeviceToHost, c->stream));
+    if (deriv) HV_CUDA(cudaMemcpy2DAsync(deriv, (size_t)L.w * 4, L.deriv, (size_t)L.dpitch * 4, (size_t)L.w * 4, L.h,
+                                         cudaMemcpyDeviceToHost, c->stream));
+    HV_CUDA(cudaStreamSynchronize(c->stream));
+    return HV_OK;
+}
+
+int hv_pyr_download_level_padded(hv_pyr* p, int level, uint8_t* gray, int16_t* deriv)
+{
+    if (!p || level < 0 || level >= p->nlevels) { hv_set_error("hv_pyr_download_level_padded: bad level"); return HV_ERR_INVALID; }
+    const HvLevel& L = p->desc.lv[level];
+    const int win = p->win, W = L.w + 2 * win, H = L.h + 2 * win;
+    std::vector<uint8_t> g((size_t)L.w * L.h);
+    std::vector<int16_t> d((size_t)L.w * L.h * 2);
+    int rc = hv_pyr_download_level(p, level, gray ? g.data() : nullptr, deriv ? d.data() : nullptr);
+    if (rc != HV_OK) return rc;
+    // border exactly as the reference materialises it: gray REFLECT_101, gradient CONSTANT 0 (lkpyramid.cpp:761-808)
+    for (int y = 0; y < H; y++) {
+        const int sy = hv_reflect101(y - win, L.h);
+        const bool rowIn = (unsigned)(y - win) < (unsigned)L.h;
+        for (int x = 0; x < W; x++) {
+            const int sx = hv_reflect101(x - win, L.w);
+            const bool in = rowIn && (unsigned)(x - win) < (unsigned)L.w;
+            if (gray) gray[(size_t)y * W + x] = g[(size_t)sy * L.w + sx];
+            if (deriv) {
+                deriv[((size_t)y * W + x) * 2] = in ? d[((size_t)sy * L.w + sx) * 2] : 0;
+                deriv[((size_t)y * W + x) * 2 + 1] = in ? d[((size_t)sy * L.w + sx) * 2 + 1] : 0;
+            }
+        }
+    }
+    return HV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ LK
+static int lk_fill(LkLaunch& L, hv_ctx* c, int maxLevel, int maxIter, double eps, double minEig)
+{
+    // criteria clamp of SparsePyrLKOpticalFlowImpl::calc (lkpyramid.cpp:1361-1369)
+    L.table = c->d_table;
+    L.maxLevel = maxLevel;
+    L.maxIter = maxIter < 0 ? 0 : (maxIter > 100 ? 100 : maxIter);
+    double e = eps < 0. ? 0. : (eps > 10. ? 10. : eps);
+    L.eps2 = e * e;
+    L.minEig = (float)minEig;
+    return HV_OK;
+}
+
+static int lk_check_pair(const char* who, hv_ctx* c, hv_pyr* a, hv_pyr* b)
+{
+    if (!a || !b || a->ctx != c || b->ctx != c) { hv_set_error("%s: pyramid NULL or from another context", who); return HV_ERR_INVALID; }
+    if (a->w != b->w || a->h != b->h || a->win != b->win) { hv_set_error("%s: pyramids differ in size/window", who); return HV_ERR_INVALID; }
+    return HV_OK;
+}
+
+int hv_lk_track_batch_device(hv_ctx* c, const hv_lk_job* jobs, int njobs, int maxIter, double eps, double minEig)
+{
+    if (!c || !jobs || njobs < 0) { hv_set_error("hv_lk_track_batch_device: invalid argument"); return HV_ERR_INVALID; }
+    HV_CUDA(cudaSetDevice(c->device));
+    for (int base = 0; base < njobs; base += LK_MAX_JOBS) {
+        LkLaunch L;
+        int cnt = njobs - base < LK_MAX_JOBS ? njobs - base : LK_MAX_JOBS;
+        int win = 0, maxLevel = HV_MAX_LEVELS;
+        for (int i = 0; i < cnt; i++) {
+            const hv_lk_job& j = jobs[base + i];
+            int rc = lk_check_pair("hv_lk_track_batch_device", c, j.prev, j.next);
+            if (rc != HV_OK) return rc;
+            if (j.n < 0 || (j.n > 0 && (!j.d_prev_xy || !j.d_next_xy || !j.d_status))) {
+                hv_set_error("hv_lk_track_batch_device: job %d has NULL buffers", base + i); return HV_ERR_INVALID;
+            }
+            if (win && win != j.prev->win) { hv_set_error("hv_lk_track_batch_device: mixed window sizes"); return HV_ERR_INVALID; }
+            win = j.prev->win;
+            LkJob& d = L.jobs[i];
+            d.prevIdx = j.prev->slot; d.nextIdx = j.next->slot; d.n = j.n; d.useInitial = j.use_initial;
+            d.prevPts = (const float2*)j.d_prev_xy; d.nextPts = (float2*)j.d_next_xy;
+            d.status = j.d_status; d.trackStatus = j.d_track_status;
+        }
+        L.njobs = cnt;
+        lk_fill(L, c, maxLevel, maxIter, eps, minEig);
+        cudaError_t e = hv_launch_lk(L, win, c->stream);
+        if (e == cudaErrorInvalidValue) { hv_set_error("hv_lk_track: window size %d unsupported (supported: 11, 15, 21, 31)", win); return HV_ERR_UNSUPPORTED; }
+        HV_CUDA(e);
+        c->launches += 1;
+    }
+    return HV_OK;
+}
+
+int hv_lk_track_device(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* dPrev, float* dNext, uint8_t* dStatus,
+                       int32_t* dTs, int n, int useInitial, int maxIter, double eps, double minEig)
+{
+    if (n == 0) return HV_OK;
+    hv_lk_job j; j.prev = prev; j.next = next; j.d_prev_xy = dPrev; j.d_next_xy = dNext; j.d_status = dStatus;
+    j.d_track_status = dTs; j.n = n; j.use_initial = useInitial;
+    return hv_lk_track_batch_device(c, &j, 1, maxIter, eps, minEig);
+}
+
+int hv_lk_track(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* prevXY, float* nextXY, uint8_t* status,
+                int32_t* trackStatus, int n, int useInitial, int maxIter, double eps, double minEig)
+{
+    if (!c || n < 0 || (n > 0 && (!prevXY || !nextXY))) { hv_set_error("hv_lk_track: invalid argument"); return HV_ERR_INVALID; }
+    int rc = lk_check_pair("hv_lk_track", c, prev, next);
+    if (rc != HV_OK) return rc;
+    if (n == 0) return HV_OK;   // optical_flow.cpp:41-44: empty input, empty output
+    HV_CUDA(cudaSetDevice(c->device));
+    // staging block: [prev 8n | next 8n | trackStatus 4n | status n]
+    const size_t oPrev = 0, oNext = 8 * (size_t)n, oTs = 16 * (size_t)n, oSt = 20 * (size_t)n, total = 21 * (size_t)n;
+    rc = hv_ctx_reserve_stage(c, total);
+    if (rc != HV_OK) return rc;
+    uint8_t* hs = (uint8_t*)c->h_stage; uint8_t* ds = (uint8_t*)c->d_stage;
+    memcpy(hs + oPrev, prevXY, 8 * (size_t)n);
+    if (useInitial) memcpy(hs + oNext, nextXY, 8 * (size_t)n);
+    HV_CUDA(cudaMemcpyAsync(ds, hs, useInitial ? 16 * (size_t)n : 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    rc = hv_lk_track_device(c, prev, next, (const float*)(ds + oPrev), (float*)(ds + oNext), ds + oSt, (int32_t*)(ds + oTs),
+                            n, useInitial, maxIter, eps, minEig);
+    if (rc != HV_OK) return rc;
+    HV_CUDA(cudaMemcpyAsync(hs + oNext, ds + oNext, total - oNext, cudaMemcpyDeviceToHost, c->stream));
+    HV_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(nextXY, hs + oNext, 8 * (size_t)n);
+    if (trackStatus) memcpy(trackStatus, hs + oTs, 4 * (size_t)n);
+    if (status) memcpy(status, hs + oSt, (size_t)n);
+    return HV_OK;
+}
+
+} // extern "C"

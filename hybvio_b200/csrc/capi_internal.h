@@ -1,0 +1,46 @@
+// hybvio_b200/csrc/capi_internal.h -- host-side objects behind the opaque C handles.
+#pragma once
+#include "hv_common.cuh"
+#include "../../include/hybvio_b200.h"
+#include <vector>
+#include <string>
+
+#define HV_TABLE_CAPACITY 1024   // pyramids per context
+
+void hv_set_error(const char* fmt, ...);
+#define HV_CUDA(call)                                                                           \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            hv_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return e_ == cudaErrorMemoryAllocation ? HV_ERR_OOM : HV_ERR_CUDA;                  \
+        }                                                                                       \
+    } while (0)
+
+struct hv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    HvPyrDesc* d_table = nullptr;
+    std::vector<int> freeSlots;
+    long long launches = 0;
+    // LK staging (host-buffer API): one pinned block + one device block, grown on demand
+    void* h_stage = nullptr; void* d_stage = nullptr; size_t stageBytes = 0;
+    // EKF staging
+    void* h_ekfStage = nullptr; void* d_ekfStage = nullptr; size_t ekfStageBytes = 0;
+};
+
+struct hv_pyr {
+    hv_ctx* ctx = nullptr;
+    int slot = -1;
+    int w = 0, h = 0, win = 0, nlevels = 0;
+    void* d_mem = nullptr;
+    size_t bytes = 0;
+    HvPyrDesc desc;
+};
+
+int hv_ctx_reserve_stage(hv_ctx* ctx, size_t bytes);
+
+// kernels (pyramid.cu, lk.cu)
+cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* idx, int n, int w0, int h0, int maxNlevels,
+                                cudaStream_t stream);

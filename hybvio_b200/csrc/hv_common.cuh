@@ -1,0 +1,63 @@
+// hybvio_b200 -- shared device-side types for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define HV_MAX_LEVELS 6      // pyrLKMaxLevel <= 5 (HybVIO default 3, codegen/parameter_definitions.c:334-344)
+#define HV_PYR_TILE 64       // level-0 tile edge of the fused pyramid kernel; must be divisible by 2^maxLevel
+
+// One pyramid level in HBM. Levels are stored UNPADDED (the reference pads every level by winSize on all
+// sides, OCV/video/src/lkpyramid.cpp:761-808; here the reflect-101 / zero border is applied by index
+// arithmetic in the LK kernel instead, which saves 0.79 MB of writes per 752x480 image).
+struct HvLevel {
+    uint8_t* gray;    // w x h, row pitch gpitch bytes (multiple of 128)
+    short2*  deriv;   // w x h (Ix, Iy) Scharr x32, row pitch dpitch elements (multiple of 32 => 128 B)
+    int w, h;
+    int gpitch;
+    int dpitch;
+};
+
+struct HvPyrDesc {
+    HvLevel lv[HV_MAX_LEVELS];
+    int nlevels;
+    int win;
+};
+
+// BORDER_REFLECT_101 (OCV/core/src/copy.cpp:1136-1181)
+__host__ __device__ __forceinline__ int hv_reflect101(int p, int len)
+{
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        if (p < 0) p = -p;
+        else p = 2 * len - 2 - p;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+// ---- Lucas-Kanade launch description (lk.cu)
+#define LK_WARPS_PER_CTA 4
+#define LK_MAX_JOBS 8
+
+struct LkJob {
+    int prevIdx, nextIdx;       // pyramid descriptor indices
+    int n;                      // number of features
+    int useInitial;             // OPTFLOW_USE_INITIAL_FLOW
+    const float2* prevPts;      // device
+    float2* nextPts;            // device; in: initial guess (if useInitial), out: end point
+    uint8_t* status;            // device; OpenCV status 1 = ok, 0 = failed
+    int32_t* trackStatus;       // device, optional; tracker::Feature::Status (src/tracker/track.hpp:9-20)
+};
+
+struct LkLaunch {
+    const HvPyrDesc* table;
+    LkJob jobs[LK_MAX_JOBS];
+    int njobs;
+    int maxLevel;
+    int maxIter;                // already clamped to [0,100]
+    double eps2;                // already clamped and squared
+    float minEig;
+};
+
+
+cudaError_t hv_launch_lk(const LkLaunch& L, int win, cudaStream_t stream);

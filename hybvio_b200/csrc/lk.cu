@@ -1,0 +1,226 @@
+// hybvio_b200/csrc/lk.cu -- pyramidal Lucas-Kanade tracker for sm_100a, one warp per feature, all levels in
+// one launch. Compile with --fmad=false (the reference x86 build has no FMA; every fp32 op rounds separately).
+//
+// Replaces, for tracker::OpticalFlow::compute (src/tracker/optical_flow.cpp:10-59, 78-102), the reference's
+//   SparsePyrLKOpticalFlowImpl::calc   OCV/video/src/lkpyramid.cpp:1236-1401  (level loop, criteria clamp)
+//   LKTrackerInvoker::operator()       OCV/video/src/lkpyramid.cpp:183-724    (patch, 2x2 system, iterations)
+// and the HybVIO status mapping of optical_flow.cpp:52-58.
+//
+// Mapping to the hardware
+//   * lane x of the warp owns window column x (win <= 31, lane `win` carries the +1 bilinear column); the
+//     31x31 I / (Ix,Iy) patch lives in registers (2 x 31 regs per lane) for the whole level.
+//   * window rows are fetched as one coalesced 32-byte (gray) / 128-byte (gradient) warp load per row, all
+//     rows issued back to back (32 independent loads in flight per lane) so a patch or an iteration costs
+//     about one L2 round trip; the x+1 neighbour comes from __shfl_down, not from a second load.
+//   * pyramid levels are stored unpadded; the reference's 31-px REFLECT_101 (gray) / zero (gradient) padding
+//     (lkpyramid.cpp:761-808) is reproduced by per-lane column / per-row index reflection.
+//   * fixed-point sample arithmetic (W_BITS 14, DESCALE 9 / 14) is integer and bit-exact with the reference.
+//   * the 2x2 normal equations: per-lane int32 partial sums of the exact integer products (31 products per lane
+//     cannot overflow), reduced across the warp with redux.sync on 16-bit halves into an exact int64 total,
+//     rounded to fp32 ONCE. The reference accumulates the same products in fp32 SSE lanes
+//     (lkpyramid.cpp:317-350, 556-562); the exact sum differs from it by <= ~1e-6 relative, which is what
+//     the 1e-3 px end-point tolerance absorbs. The result is independent of reduction order => deterministic.
+//   * all scalar float steps (D, minEig, delta, stop tests) are evaluated redundantly by every lane with
+//     explicit round-to-nearest intrinsics, in the reference's operation order.
+#include "hv_common.cuh"
+#include <float.h>
+
+__device__ __forceinline__ int cv_floor(float v)
+{
+    // cvFloor (OCV/core/include/opencv2/core/fast_math.hpp:340-352) with the x86 out-of-range result
+    if (!(fabsf(v) < 2147483648.f)) return INT_MIN;
+    return __float2int_rd(v);
+}
+
+__device__ __forceinline__ long long warp_sum_exact(int v)
+{
+    // v = hi * 65536 + lo, lo in [0, 65535]; both partial sums fit int32 for 32 lanes
+    int lo = v & 0xffff, hi = v >> 16;
+    int slo = __reduce_add_sync(0xffffffffu, lo);
+    int shi = __reduce_add_sync(0xffffffffu, hi);
+    return (long long)shi * 65536 + (long long)slo;
+}
+
+__device__ __forceinline__ void bilin_weights(float a, float b, int& w00, int& w01, int& w10, int& w11)
+{
+    // lkpyramid.cpp:232-239; cvRound(float) = round-half-even
+    const float oa = __fsub_rn(1.f, a), ob = __fsub_rn(1.f, b);
+    w00 = __float2int_rn(__fmul_rn(__fmul_rn(oa, ob), 16384.f));
+    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, ob), 16384.f));
+    w10 = __float2int_rn(__fmul_rn(__fmul_rn(oa, b), 16384.f));
+    w11 = 16384 - w00 - w01 - w10;
+}
+
+template <int WIN>
+__global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32) hv_lk_kernel(LkLaunch L)
+{
+    const LkJob& job = L.jobs[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int f = blockIdx.x * LK_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (f >= job.n) return;
+
+    const HvPyrDesc& PI = L.table[job.prevIdx];
+    const HvPyrDesc& PJ = L.table[job.nextIdx];
+    int maxLevel = min(L.maxLevel, min(PI.nlevels, PJ.nlevels) - 1);
+
+    const float halfWin = (float)(WIN - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const int col = min(lane, WIN);            // lanes above WIN duplicate the last column (results unused)
+
+    const float2 prevPt = job.prevPts[f];
+    float2 outPt = job.useInitial ? job.nextPts[f] : prevPt;
+    int status = 1;
+
+    int Ipat[WIN];      // I patch column, x32 fixed point (lkpyramid.cpp:441)
+    int dIpat[WIN];     // (Ix, Iy) packed as two int16
+
+    for (int level = maxLevel; level >= 0; --level) {
+        const HvLevel LI = PI.lv[level];
+        const HvLevel LJ = PJ.lv[level];
+        const float lscale = (float)(1. / (1 << level));
+        float px = __fmul_rn(prevPt.x, lscale), py = __fmul_rn(prevPt.y, lscale);
+        float nx, ny;
+        if (level == maxLevel) {
+            if (job.useInitial) { nx = __fmul_rn(outPt.x, lscale); ny = __fmul_rn(outPt.y, lscale); }
+            else { nx = px; ny = py; }
+        } else { nx = __fmul_rn(outPt.x, 2.f); ny = __fmul_rn(outPt.y, 2.f); }
+        outPt.x = nx; outPt.y = ny;
+
+        px = __fsub_rn(px, halfWin); py = __fsub_rn(py, halfWin);
+        const int ipx = cv_floor(px), ipy = cv_floor(py);
+        if (ipx < -WIN || ipx >= LI.w || ipy < -WIN || ipy >= LI.h) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        int w00, w01, w10, w11;
+        bilin_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+
+        // ---- template patch + gradient covariance (lkpyramid.cpp:272-471)
+        int a11 = 0, a12 = 0, a22 = 0;
+        {
+            const int cx = ipx + col;
+            const bool colOk = (unsigned)cx < (unsigned)LI.w;
+            const int cxr = hv_reflect101(cx, LI.w);
+            int v[WIN + 1], d[WIN + 1];
+#pragma unroll
+            for (int y = 0; y <= WIN; y++) {
+                const int ry = ipy + y;
+                const int ryr = hv_reflect101(ry, LI.h);
+                v[y] = __ldg(LI.gray + (size_t)ryr * LI.gpitch + cxr);
+                d[y] = (colOk && (unsigned)ry < (unsigned)LI.h)
+                           ? __ldg(reinterpret_cast<const int*>(LI.deriv + (size_t)ry * LI.dpitch + cx)) : 0;
+            }
+            int vr0 = __shfl_down_sync(0xffffffffu, v[0], 1), dr0 = __shfl_down_sync(0xffffffffu, d[0], 1);
+#pragma unroll
+            for (int y = 0; y < WIN; y++) {
+                const int vr1 = __shfl_down_sync(0xffffffffu, v[y + 1], 1);
+                const int dr1 = __shfl_down_sync(0xffffffffu, d[y + 1], 1);
+                const int ival = (v[y] * w00 + vr0 * w01 + v[y + 1] * w10 + vr1 * w11 + (1 << 8)) >> 9;
+                const int x00 = (short)(d[y] & 0xffff), y00 = d[y] >> 16;
+                const int x01 = (short)(dr0 & 0xffff), y01 = dr0 >> 16;
+                const int x10 = (short)(d[y + 1] & 0xffff), y10 = d[y + 1] >> 16;
+                const int x11 = (short)(dr1 & 0xffff), y11 = dr1 >> 16;
+                const int ixv = (x00 * w00 + x01 * w01 + x10 * w10 + x11 * w11 + (1 << 13)) >> 14;
+                const int iyv = (y00 * w00 + y01 * w01 + y10 * w10 + y11 * w11 + (1 << 13)) >> 14;
+                Ipat[y] = ival;
+                dIpat[y] = (ixv & 0xffff) | (iyv << 16);
+                if (lane < WIN) { a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv; }
+                vr0 = vr1; dr0 = dr1;
+            }
+        }
+        const float A11 = __fmul_rn(__ll2float_rn(warp_sum_exact(a11)), FLT_SCALE);
+        const float A12 = __fmul_rn(__ll2float_rn(warp_sum_exact(a12)), FLT_SCALE);
+        const float A22 = __fmul_rn(__ll2float_rn(warp_sum_exact(a22)), FLT_SCALE);
+
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * WIN * WIN));
+        if (minEig < L.minEig || D < FLT_EPSILON) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+
+        // ---- Newton iterations (lkpyramid.cpp:492-681)
+        nx = __fsub_rn(nx, halfWin); ny = __fsub_rn(ny, halfWin);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < L.maxIter; j++) {
+            const int inx = cv_floor(nx), iny = cv_floor(ny);
+            if (inx < -WIN || inx >= LJ.w || iny < -WIN || iny >= LJ.h) {
+                if (level == 0) status = 0;
+                break;
+            }
+            bilin_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
+            const int cxr = hv_reflect101(inx + col, LJ.w);
+            const bool inside = iny >= 0 && iny + WIN < LJ.h;
+            const uint8_t* jb = LJ.gray + cxr;
+            int v[WIN + 1];
+#pragma unroll
+            for (int y = 0; y <= WIN; y++) {
+                const int ryr = inside ? iny + y : hv_reflect101(iny + y, LJ.h);
+                v[y] = __ldg(jb + (size_t)ryr * LJ.gpitch);
+            }
+            int b1 = 0, b2 = 0;
+            int vr0 = __shfl_down_sync(0xffffffffu, v[0], 1);
+#pragma unroll
+            for (int y = 0; y < WIN; y++) {
+                const int vr1 = __shfl_down_sync(0xffffffffu, v[y + 1], 1);
+                const int diff = ((v[y] * w00 + vr0 * w01 + v[y + 1] * w10 + vr1 * w11 + (1 << 8)) >> 9) - Ipat[y];
+                b1 += diff * (int)(short)(dIpat[y] & 0xffff);
+                b2 += diff * (dIpat[y] >> 16);
+                vr0 = vr1;
+            }
+            if (lane >= WIN) { b1 = 0; b2 = 0; }
+            const float fb1 = __fmul_rn(__ll2float_rn(warp_sum_exact(b1)), FLT_SCALE);
+            const float fb2 = __fmul_rn(__ll2float_rn(warp_sum_exact(b2)), FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
+            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+            outPt.x = __fadd_rn(nx, halfWin); outPt.y = __fadd_rn(ny, halfWin);
+            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= L.eps2) break;
+            if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+                outPt.x = __fsub_rn(outPt.x, __fmul_rn(dx, 0.5f));
+                outPt.y = __fsub_rn(outPt.y, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+
+        // ---- level-0 re-check of the final window position (lkpyramid.cpp:684-698; runs because HybVIO
+        //      requests `err`, src/tracker/optical_flow.cpp:46-49)
+        if (status && level == 0) {
+            const int ix = cv_floor(__fsub_rn(outPt.x, halfWin)), iy = cv_floor(__fsub_rn(outPt.y, halfWin));
+            if (ix < -WIN || ix >= LJ.w || iy < -WIN || iy >= LJ.h) status = 0;
+        }
+    }
+
+    if (lane == 0) {
+        job.nextPts[f] = outPt;
+        job.status[f] = (uint8_t)status;
+        if (job.trackStatus) {
+            // src/tracker/optical_flow.cpp:52-58 against level 0 of the *next* pyramid
+            int ts = status ? 0 /*TRACKED*/ : 2 /*FAILED_FLOW*/;
+            const float W = (float)PJ.lv[0].w, H = (float)PJ.lv[0].h;
+            if (outPt.x < 0.0f || outPt.x >= W || outPt.y < 0.0f || outPt.y >= H) ts = 4; /*FLOW_OUT_OF_RANGE*/
+            job.trackStatus[f] = ts;
+        }
+    }
+}
+
+cudaError_t hv_launch_lk(const LkLaunch& L, int win, cudaStream_t stream)
+{
+    int maxN = 0;
+    for (int i = 0; i < L.njobs; i++) maxN = max(maxN, L.jobs[i].n);
+    if (maxN == 0) return cudaSuccess;
+    dim3 grid((maxN + LK_WARPS_PER_CTA - 1) / LK_WARPS_PER_CTA, L.njobs);
+    dim3 block(LK_WARPS_PER_CTA * 32);
+    switch (win) {
+        case 31: hv_lk_kernel<31><<<grid, block, 0, stream>>>(L); break;
+        case 21: hv_lk_kernel<21><<<grid, block, 0, stream>>>(L); break;
+        case 15: hv_lk_kernel<15><<<grid, block, 0, stream>>>(L); break;
+        case 11: hv_lk_kernel<11><<<grid, block, 0, stream>>>(L); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}

@@ -1,0 +1,195 @@
+/*
+ * hybvio_b200.h -- C ABI of libhybvio_b200.so: the B200 (sm_100a) implementation of HybVIO's per-frame hot path.
+ *
+ * Boundary. Each entry point names the reference interface it replaces (paths relative to the
+ * reference root; OCV = 3rdparty/mobile-cv-suite/opencv/modules). The reference-side C++ adapter classes
+ * (CudaImagePyramid / CudaOpticalFlow / CudaEKF, hybvio_b200/host/) sit on top of exactly these calls.
+ *
+ * Conventions: every function returns HV_OK (0) or a negative hv_status; nothing throws across the boundary;
+ * handles are opaque; the caller owns host buffers, the library owns device buffers; matrices are fp64
+ * COLUMN-MAJOR with leading dimension = rows (Eigen's default layout). All work of a context is issued on one
+ * CUDA stream; calls taking host output buffers synchronise that stream before returning, `_device`/`_async`
+ * variants do not. A context must be used from one thread at a time (the reference drives Tracker and EKF from
+ * a single thread, src/api/api.cpp:425-428).
+ *
+ * There is NO CPU fallback: hv_ctx_create fails with HV_ERR_NO_DEVICE when no sm_100 GPU is present.
+ */
+#ifndef HYBVIO_B200_H_
+#define HYBVIO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum hv_status {
+    HV_OK = 0,
+    HV_ERR_INVALID = -1,      /* bad argument (NULL handle, n < 0, unsupported window size ...) */
+    HV_ERR_NO_DEVICE = -2,    /* no CUDA device / not sm_100 */
+    HV_ERR_CUDA = -3,         /* a CUDA runtime call failed; see hv_last_error */
+    HV_ERR_OOM = -4,
+    HV_ERR_UNSUPPORTED = -5,  /* e.g. pyrLKWindowSize not in {11,15,21,31}, maxLevel > 5 */
+    HV_ERR_STATE = -6         /* call order violated (e.g. unaugment with no augmented pose) */
+} hv_status;
+
+typedef struct hv_ctx hv_ctx;
+typedef struct hv_pyr hv_pyr;
+typedef struct hv_ekf hv_ekf;
+
+/* ---------------------------------------------------------------- context ------------------------------- */
+const char* hv_version(void);
+/* Last error text of this thread (valid until the next failing call). */
+const char* hv_last_error(void);
+int hv_device_count(void);
+/* Creates a context on `device` with its own non-blocking stream. */
+int hv_ctx_create(int device, hv_ctx** out);
+/* Same, but issues all work on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream). */
+int hv_ctx_create_on_stream(int device, void* cuda_stream, hv_ctx** out);
+int hv_ctx_destroy(hv_ctx* ctx);
+int hv_ctx_sync(hv_ctx* ctx);
+/* The stream as a cudaStream_t (for event timing by the caller). */
+void* hv_ctx_stream(hv_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long hv_ctx_launch_count(hv_ctx* ctx);
+
+/* ---------------------------------------------------------------- image pyramid ------------------------- */
+/* Replaces tracker::ImagePyramid + CpuImagePyramidFactory (src/tracker/image_pyramid.hpp:18-42,
+ * image_pyramid.cpp:28-48): one object per camera frame, recycled through a pool like util::Allocator.
+ * win = tracker.pyrLKWindowSize, max_level = tracker.pyrLKMaxLevel. Level sizes follow
+ * cv::buildOpticalFlowPyramid (OCV/video/src/lkpyramid.cpp:726-822): ((w+1)/2, (h+1)/2), stopping early when
+ * the next level would be <= win. */
+int hv_pyr_create(hv_ctx* ctx, int width, int height, int win, int max_level, hv_pyr** out);
+int hv_pyr_release(hv_pyr* pyr);
+int hv_pyr_levels(const hv_pyr* pyr);
+int hv_pyr_level_size(const hv_pyr* pyr, int level, int* width, int* height);
+/* Replaces ImagePyramid::Factory::compute -> cv::buildOpticalFlowPyramid. `gray` is a HOST 8-bit image
+ * (accelerated::Image CPU storage, row stride in bytes). Asynchronous: H2D copy + one fused kernel on the
+ * context stream; the host buffer must stay valid until the next synchronising call (use pinned memory for
+ * a truly asynchronous copy). */
+int hv_pyr_build(hv_pyr* pyr, const uint8_t* gray, size_t stride_bytes);
+/* Same for `n` images in ONE kernel launch (stereo pair: n = 2). src_is_device != 0: `gray[i]` are device
+ * pointers (frame already in HBM). All pyramids must belong to one context and have equal level-0 size. */
+int hv_pyr_build_batch(hv_pyr* const* pyrs, const uint8_t* const* gray, const size_t* stride_bytes, int n,
+                       int src_is_device);
+/* Test/debug accessors, replacing ImagePyramid::getGrayLevel/getGradientLevel/getOpenCv: copy one level to the
+ * host. gray: w*h u8; deriv: w*h*2 int16 interleaved (Ix,Iy), GRADIENT_SCALE_0_255 = 1/32
+ * (image_pyramid.hpp:19-26). Either pointer may be NULL. Synchronises. */
+int hv_pyr_download_level(hv_pyr* pyr, int level, uint8_t* gray, int16_t* deriv);
+/* Same, laid out exactly like the reference's cv::Mat level *with* its win-pixel padding (gray REFLECT_101,
+ * deriv CONSTANT 0; lkpyramid.cpp:761-808): (w+2win) x (h+2win). The device stores levels unpadded; the
+ * border is materialised on the host by this accessor only. */
+int hv_pyr_download_level_padded(hv_pyr* pyr, int level, uint8_t* gray, int16_t* deriv);
+
+/* ---------------------------------------------------------------- Lucas-Kanade -------------------------- */
+/* Replaces tracker::OpticalFlow::compute -> cv::calcOpticalFlowPyrLK (src/tracker/optical_flow.cpp:10-59,
+ * 78-102; OCV/video/src/lkpyramid.cpp:1236-1401, 183-724) with TermCriteria(COUNT|EPS, max_iter, eps),
+ * flags = use_initial ? OPTFLOW_USE_INITIAL_FLOW : 0, minEigThreshold = min_eig, `err` requested.
+ *   prev_xy   n x (x,y) float32, host
+ *   next_xy   n x (x,y) float32, host; in: initial guesses when use_initial, out: tracked end points
+ *   status    n x uint8, OpenCV status (1 tracked, 0 failed); may be NULL
+ *   track_status  n x int32 tracker::Feature::Status (src/tracker/track.hpp:9-20): TRACKED=0, FAILED_FLOW=2,
+ *             FLOW_OUT_OF_RANGE=4, exactly as optical_flow.cpp:52-58 derives it; may be NULL
+ * Synchronises. */
+int hv_lk_track(hv_ctx* ctx, hv_pyr* prev, hv_pyr* next, const float* prev_xy, float* next_xy, uint8_t* status,
+                int32_t* track_status, int n, int use_initial, int max_iter, double eps, double min_eig);
+/* Device-resident variant: all pointers are device pointers, nothing is copied, no synchronisation. */
+int hv_lk_track_device(hv_ctx* ctx, hv_pyr* prev, hv_pyr* next, const float* d_prev_xy, float* d_next_xy,
+                       uint8_t* d_status, int32_t* d_track_status, int n, int use_initial, int max_iter,
+                       double eps, double min_eig);
+/* Several independent LK calls (e.g. one per stream) in one launch; device pointers. */
+typedef struct hv_lk_job {
+    hv_pyr* prev; hv_pyr* next;
+    const float* d_prev_xy; float* d_next_xy; uint8_t* d_status; int32_t* d_track_status;
+    int n; int use_initial;
+} hv_lk_job;
+int hv_lk_track_batch_device(hv_ctx* ctx, const hv_lk_job* jobs, int njobs, int max_iter, double eps, double min_eig);
+
+/* ---------------------------------------------------------------- EKF ----------------------------------- */
+/* Replaces odometry::EKF / EKFImplementation (src/odometry/ekf.hpp:62-174, ekf.cpp). State m (N) and
+ * covariance P (N x N) are fp64 and live in HBM; N = 20 + 7*trail + 3*map (ekf.cpp:156-158). */
+typedef struct hv_ekf_params {          /* the odometry::Parameters fields EKFImplementation reads */
+    int camera_trail_length;            /* odometry.cameraTrailLength */
+    int hybrid_map_size;                /* odometry.hybridMapSize */
+    double noise_scale;                 /* odometry.noiseScale (the EKF uses its square, ekf.cpp:154) */
+    double gravity;                     /* odometry.gravity */
+    double noise_initial_pos, noise_initial_vel, noise_initial_ori;
+    double noise_initial_bga, noise_initial_baa, noise_initial_bat, noise_initial_sft;
+    double noise_initial_pos_trail, noise_initial_ori_trail;
+    double noise_process_acc, noise_process_gyro;
+    double noise_process_baa, noise_process_baa_rev, noise_process_bga, noise_process_bga_rev;
+    double augment_r, init_zupt_r, rotation_zupt_r;
+} hv_ekf_params;
+/* Fills `p` with the defaults of codegen/parameter_definitions.c. */
+void hv_ekf_default_params(hv_ekf_params* p);
+
+/* EKF::build (ekf.cpp:153-296, 1087-1092) */
+int hv_ekf_create(hv_ctx* ctx, const hv_ekf_params* params, hv_ekf** out);
+int hv_ekf_destroy(hv_ekf* ekf);
+/* EKF::clone (ekf.cpp:1074-1079): device-to-device copy of m, P, Q and the host-side time bookkeeping */
+int hv_ekf_clone(const hv_ekf* src, hv_ekf** out);
+int hv_ekf_state_dim(const hv_ekf* ekf);                       /* getStateDim */
+int hv_ekf_pose_count(const hv_ekf* ekf);                      /* getPoseCount = augmentCount + 1 */
+double hv_ekf_platform_time(const hv_ekf* ekf);                /* getPlatformTime */
+double hv_ekf_history_time(const hv_ekf* ekf, int i);          /* historyTime (ekf.cpp:556-562) */
+int hv_ekf_was_stationary(const hv_ekf* ekf);                  /* getWasStationary */
+int hv_ekf_set_first_sample_time(hv_ekf* ekf, double t);       /* setFirstSampleTime (ekf.cpp:1035-1041) */
+
+/* setState / setStateCovariance / getState / getStateCovariance (ekf.cpp:950-981). NULL = skip. download
+ * synchronises. */
+int hv_ekf_upload(hv_ekf* ekf, const double* m, const double* P);
+int hv_ekf_download(hv_ekf* ekf, double* m, double* P);
+/* getInertialState / setInertialState (ekf.cpp:679-690): first 20 entries / top-left 20x20 block. */
+int hv_ekf_download_inertial(hv_ekf* ekf, double* m20, double* P20x20);
+int hv_ekf_set_inertial_state(hv_ekf* ekf, const double* m20, const double* P20x20);
+int hv_ekf_set_process_noise(hv_ekf* ekf, const double* Q12x12);   /* setProcessNoise */
+int hv_ekf_get_dydx(hv_ekf* ekf, double* dydx20x20);               /* getDydx's non-identity block (tests) */
+
+int hv_ekf_initialize_orientation(hv_ekf* ekf, const double acc[3]);          /* ekf.cpp:299-317 */
+/* predict (ekf.cpp:320-514): mean propagation, Jacobians and the structured covariance update all run on the
+ * device; the host only keeps the sample-time bookkeeping (first sample / dt <= 0 are no-ops). Asynchronous. */
+int hv_ekf_predict(hv_ekf* ekf, double t, const double gyro[3], const double acc[3]);
+
+/* The fixed-H updates (ekf.cpp:573-677); rate limits and early-outs as in the reference. Asynchronous. */
+int hv_ekf_update_zupt(hv_ekf* ekf, double r);
+int hv_ekf_update_zupt_initialization(hv_ekf* ekf);
+int hv_ekf_update_zrupt(hv_ekf* ekf, const double gyro[3]);
+int hv_ekf_update_pseudo_velocity(hv_ekf* ekf, double default_speed, double r);
+int hv_ekf_update_position(hv_ekf* ekf, const double pos[3], double r);
+int hv_ekf_update_zero_height(hv_ekf* ekf, double r);
+int hv_ekf_update_orientation(hv_ekf* ekf, const double q[4], double r);
+
+/* visualTrackOutlierCheck (ekf.cpp:787-819). H is n x l column-major (host), f and y length n (host).
+ * *vu_status: odometry::VuOutlierStatus (ekf.hpp:54-59) INLIER=0, NOT_COMPUTED=1, RMSE=2, CHI2=3.
+ * *chi2 (optional) receives noiseScale * v' S^-1 v. Synchronises (the caller branches on the result,
+ * src/odometry/backend.cpp:1158-1161). */
+int hv_ekf_visual_check(hv_ekf* ekf, const double* H, int n, int l, const double* f, const double* y, double r,
+                        double track_rmse_threshold, int* vu_status, double* chi2);
+/* updateVisualTrack (ekf.cpp:829-844). Asynchronous. */
+int hv_ekf_visual_update(hv_ekf* ekf, const double* H, int n, int l, const double* f, const double* y, double r);
+/* Fused check + conditional update in one kernel and ONE host round trip: applies updateVisualTrack iff the
+ * check returns INLIER, and (if m_out != NULL) returns the updated state mean, which the caller needs to
+ * build the next track's H (backend.cpp:1054-1056). Equivalent to check followed by update. Synchronises. */
+int hv_ekf_visual_check_update(hv_ekf* ekf, const double* H, int n, int l, const double* f, const double* y,
+                               double r, double track_rmse_threshold, int* vu_status, double* chi2, double* m_out);
+/* Device-resident variant of the two calls above (H, f, y already in HBM; result words written to
+ * d_result[0] = status, d_result[1] = chi2 as doubles); mode: 0 = check only, 1 = update only,
+ * 2 = check then update-if-inlier. Asynchronous. */
+int hv_ekf_visual_device(hv_ekf* ekf, const double* d_H, int n, int l, const double* d_f, const double* d_y,
+                         double r, double track_rmse_threshold, int mode, double* d_result);
+
+int hv_ekf_augment(hv_ekf* ekf, int discarded_pose_index);     /* updateVisualPoseAugmentation (ekf.cpp:848-885) */
+int hv_ekf_unaugment(hv_ekf* ekf);                             /* updateUndoAugmentation (ekf.cpp:888-903) */
+int hv_ekf_symmetrize(hv_ekf* ekf);                            /* maintainPositiveSemiDefinite (ekf.cpp:1059-1067) */
+int hv_ekf_normalize_quaternions(hv_ekf* ekf, int only_current);   /* ekf.cpp:1024-1032 */
+int hv_ekf_translate_to(hv_ekf* ekf, const double pos[3]);     /* ekf.cpp:696-702 */
+int hv_ekf_transform_to(hv_ekf* ekf, const double pos[3], const double q[4], int pose_index); /* ekf.cpp:704-758 */
+int hv_ekf_insert_map_point(hv_ekf* ekf, int idx, const double pf[3]);   /* ekf.cpp:911-921 */
+int hv_ekf_condition_on_last_pose(hv_ekf* ekf);                /* ekf.cpp:928-942 */
+int hv_ekf_lock_biases(hv_ekf* ekf);                           /* ekf.cpp:944-947 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYBVIO_B200_H_ */

@@ -1,0 +1,39 @@
+"""CPU test: the C-ABI shared library loads without a GPU and exports every symbol include/hybvio_b200.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hybvio_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from hybvio_b200 import capi
+    assert os.path.exists(capi.LIB_PATH), "build the library first: make (or __graft_entry__.build())"
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 50
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, f"declared in include/hybvio_b200.h but not exported: {missing}"
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a GPU the context must fail loudly (HV_ERR_NO_DEVICE), never fall back to a CPU path."""
+    import torch
+    from hybvio_b200 import capi
+    lib = capi.load()
+    if torch.cuda.is_available():
+        return
+    h = ctypes.c_void_p()
+    rc = lib.hv_ctx_create(0, ctypes.byref(h))
+    assert rc == -2 and b"no CPU fallback" in lib.hv_last_error()
+
+
+def test_version_string():
+    from hybvio_b200 import capi
+    assert b"sm_100a" in capi.load().hv_version()

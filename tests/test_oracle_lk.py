@@ -1,0 +1,121 @@
+"""CPU tests (no GPU): the C oracle (oracle/hv_oracle_lk.c) against the golden vectors produced by the compiled
+reference, and -- where oracle/_ref exists -- against the compiled reference itself, bit for bit."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from hybvio_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "lk_golden.npz")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def test_synth_is_deterministic(gold):
+    L0, R0 = synth.stereo_frame(10)
+    L1, _ = synth.stereo_frame(11)
+    assert sha(L0) + sha(R0) + sha(L1) == str(gold["B_img_sha"])
+
+
+def test_oracle_pyramid_matches_golden_small(oracle_lk, gold):
+    p = oracle_lk.pyramid(gold["A_I"], 31, 3)
+    assert p.levels == int(gold["A_levels"]) == 3
+    for lv in range(p.levels):
+        g, d = p.download(lv, padded=True)
+        assert np.array_equal(g, gold[f"A_gray{lv}"])
+        assert sha(d) == str(gold[f"A_deriv_sha{lv}"])
+
+
+def test_oracle_pyramid_matches_golden_euroc_shape(oracle_lk, gold):
+    L0, _ = synth.stereo_frame(10)
+    p = oracle_lk.pyramid(L0, 31, 3)
+    assert p.levels == 4
+    assert [p.level_size(i) for i in range(4)] == [(752, 480), (376, 240), (188, 120), (94, 60)]
+    for lv in range(4):
+        g, d = p.download(lv, padded=True)
+        assert sha(g) == str(gold[f"B_gray_sha{lv}"])
+        assert sha(d) == str(gold[f"B_deriv_sha{lv}"])
+
+
+def test_oracle_lk_bit_exact_vs_golden(oracle_lk, gold):
+    pa, pb = oracle_lk.pyramid(gold["A_I"], 31, 3), oracle_lk.pyramid(gold["A_J"], 31, 3)
+    nxt, st, ts = oracle_lk.lk(pa, pb, gold["A_pts"], None, accum_mode=0)
+    assert np.array_equal(st, gold["A_status"]) and np.array_equal(ts, gold["A_ts"])
+    assert np.array_equal(nxt.view(np.uint32), gold["A_next"].view(np.uint32))
+    nxt, st, ts = oracle_lk.lk(pa, pb, gold["A_pts"], gold["A_init"], accum_mode=0)
+    assert np.array_equal(st, gold["A_status_init"]) and np.array_equal(ts, gold["A_ts_init"])
+    assert np.array_equal(nxt.view(np.uint32), gold["A_next_init"].view(np.uint32))
+    assert 0 < st.sum() < len(st)            # the flat patch and far-out points fail, the rest track
+    assert set(np.unique(ts)) <= {0, 2, 4}
+
+
+def test_oracle_lk_bit_exact_vs_golden_euroc_and_tumvi(oracle_lk, gold):
+    L0, R0 = synth.stereo_frame(10)
+    L1, _ = synth.stereo_frame(11)
+    p0, p1, pr = (oracle_lk.pyramid(x, 31, 3) for x in (L0, L1, R0))
+    n_t, s_t, ts_t = oracle_lk.lk(p0, p1, gold["B_pts"], None)
+    n_s, s_s, ts_s = oracle_lk.lk(p0, pr, gold["B_pts"], None)
+    assert np.array_equal(n_t.view(np.uint32), gold["B_next_t"].view(np.uint32)) and np.array_equal(ts_t, gold["B_ts_t"])
+    assert np.array_equal(n_s.view(np.uint32), gold["B_next_s"].view(np.uint32)) and np.array_equal(ts_s, gold["B_ts_s"])
+    # temporal flow of the synthetic stream is known: the tracker must find it
+    fx, fy = synth.true_flow(10, 11)
+    ok = ts_t == 0
+    assert np.abs(n_t[ok] - gold["B_pts"][ok] - [fx, fy]).max() < 0.25
+    a, _ = synth.stereo_frame(20, 512, 512)
+    b, _ = synth.stereo_frame(21, 512, 512)
+    pa, pb = oracle_lk.pyramid(a, 31, 3), oracle_lk.pyramid(b, 31, 3)
+    n_c, s_c, ts_c = oracle_lk.lk(pa, pb, gold["C_pts"], gold["C_init"])
+    assert np.array_equal(n_c.view(np.uint32), gold["C_next"].view(np.uint32)) and np.array_equal(ts_c, gold["C_ts"])
+
+
+def test_oracle_exact_integer_mode_is_within_tolerance_of_reference_order(oracle_lk, gold):
+    """accum_mode 1 (the CUDA kernel's arithmetic) vs accum_mode 0 (reference fp32 lane order): same statuses,
+    end points within 1e-3 px except rare flipped stop decisions (< 3e-2 px), SURVEY.md 8(c)."""
+    pa, pb = oracle_lk.pyramid(gold["A_I"], 31, 3), oracle_lk.pyramid(gold["A_J"], 31, 3)
+    n0, s0, _ = oracle_lk.lk(pa, pb, gold["A_pts"], gold["A_init"], accum_mode=0)
+    n1, s1, _ = oracle_lk.lk(pa, pb, gold["A_pts"], gold["A_init"], accum_mode=1)
+    assert np.array_equal(s0, s1)
+    d = np.abs(n0 - n1).max(axis=1)[s0 > 0]
+    assert (d <= 1e-3).mean() >= 0.99 and d.max() < 3e-2
+
+
+@pytest.mark.parametrize("w,h,max_level,n,use_init,seed", [
+    (752, 480, 3, 400, False, 1), (752, 480, 3, 400, True, 2), (512, 512, 3, 300, True, 3),
+    (751, 479, 2, 200, False, 4), (100, 70, 3, 50, False, 5), (33, 40, 3, 20, True, 6), (64, 64, 0, 30, False, 7)])
+def test_oracle_bit_exact_vs_compiled_reference(oracle_lk, ref_lk, w, h, max_level, n, use_init, seed):
+    I, _ = synth.stereo_frame(seed, w, h, seed=seed)
+    J, _ = synth.stereo_frame(seed + 1, w, h, seed=seed)
+    if w > 200:
+        I = I.copy(); I[100:160, 100:160] = 77
+    ra, rb = ref_lk.pyramid(I, 31, max_level), ref_lk.pyramid(J, 31, max_level)
+    oa, ob = oracle_lk.pyramid(I, 31, max_level), oracle_lk.pyramid(J, 31, max_level)
+    assert ra.levels == oa.levels
+    for lv in range(ra.levels):
+        for x, y in zip(ra.download(lv), oa.download(lv)):
+            assert np.array_equal(x, y)
+    pts = synth.feature_points(n, w, h, seed=seed)
+    fx, fy = synth.true_flow(seed, seed + 1)
+    init = (pts + [fx, fy] + np.random.RandomState(seed).uniform(-4, 4, pts.shape)).astype(np.float32) if use_init else None
+    n1, s1, t1 = ref_lk.lk(ra, rb, pts, init, max_level=max_level)
+    n2, s2, t2 = oracle_lk.lk(oa, ob, pts, init, max_level=max_level, accum_mode=0)
+    assert np.array_equal(s1, s2) and np.array_equal(t1, t2)
+    assert np.array_equal(n1.view(np.uint32), n2.view(np.uint32))
+
+
+def test_oracle_empty_and_single_point(oracle_lk):
+    I, _ = synth.stereo_frame(0, 96, 80)
+    p = oracle_lk.pyramid(I, 31, 3)
+    assert p.levels == 2   # 96x80 -> 48x40; the next (24x20) would be <= win, lkpyramid.cpp:811-816
+    nxt, st, ts = oracle_lk.lk(p, p, np.zeros((0, 2), np.float32))
+    assert nxt.shape == (0, 2) and st.shape == (0,)
+    nxt, st, ts = oracle_lk.lk(p, p, np.array([[40.5, 30.25]], np.float32))
+    assert st[0] == 1 and np.abs(nxt - [[40.5, 30.25]]).max() < 1e-3   # identical images: zero flow
