@@ -235,3 +235,116 @@ class Pyramid:
         if self.h:
             self.lib.hv_pyr_release(self.h)
             self.h = None
+
+
+def _dd(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Ekf:
+    """hv_ekf: odometry::EKF (src/odometry/ekf.hpp:62-174) with m and P resident on the device."""
+    name = "cuda"
+
+    def __init__(self, ctx, params=None, handle=None):
+        self.ctx, self.lib = ctx, ctx.lib
+        if handle is None:
+            if params is None:
+                params = EkfParams()
+                self.lib.hv_ekf_default_params(ctypes.byref(params))
+            h = c_void_p()
+            check(self.lib.hv_ekf_create(ctx.h, ctypes.byref(params), ctypes.byref(h)), "hv_ekf_create")
+            handle = h
+        self.params = params
+        self.h = handle
+        self.N = self.lib.hv_ekf_state_dim(self.h)
+
+    def clone(self):
+        h = c_void_p()
+        check(self.lib.hv_ekf_clone(self.h, ctypes.byref(h)), "hv_ekf_clone")
+        return Ekf(self.ctx, self.params, h)
+
+    def close(self):
+        if self.h:
+            self.lib.hv_ekf_destroy(self.h)
+            self.h = None
+
+    def upload(self, m=None, P=None):
+        m = None if m is None else _dd(m)
+        P = None if P is None else np.asfortranarray(P, dtype=np.float64)
+        check(self.lib.hv_ekf_upload(self.h, _ptr(m), _ptr(P)), "hv_ekf_upload")
+
+    def download(self):
+        m = np.zeros(self.N); P = np.zeros((self.N, self.N), order="F")
+        check(self.lib.hv_ekf_download(self.h, _ptr(m), _ptr(P)), "hv_ekf_download")
+        return m, P
+
+    def download_inertial(self):
+        m = np.zeros(20); P = np.zeros((20, 20), order="F")
+        check(self.lib.hv_ekf_download_inertial(self.h, _ptr(m), _ptr(P)), "hv_ekf_download_inertial")
+        return m, P
+
+    def set_inertial_state(self, m20, P20):
+        m20 = _dd(m20); P20 = np.asfortranarray(P20, dtype=np.float64)
+        check(self.lib.hv_ekf_set_inertial_state(self.h, _ptr(m20), _ptr(P20)), "hv_ekf_set_inertial_state")
+
+    def set_process_noise(self, Q):
+        Q = np.asfortranarray(Q, dtype=np.float64)
+        check(self.lib.hv_ekf_set_process_noise(self.h, _ptr(Q)), "hv_ekf_set_process_noise")
+
+    def get_dydx(self):
+        d = np.zeros((20, 20), order="F")
+        check(self.lib.hv_ekf_get_dydx(self.h, _ptr(d)), "hv_ekf_get_dydx")
+        return d
+
+    def pose_count(self): return self.lib.hv_ekf_pose_count(self.h)
+    def platform_time(self): return self.lib.hv_ekf_platform_time(self.h)
+    def history_time(self, i): return self.lib.hv_ekf_history_time(self.h, i)
+    def was_stationary(self): return bool(self.lib.hv_ekf_was_stationary(self.h))
+    def set_first_sample_time(self, t): check(self.lib.hv_ekf_set_first_sample_time(self.h, t), "hv_ekf_set_first_sample_time")
+
+    def initialize_orientation(self, acc): check(self.lib.hv_ekf_initialize_orientation(self.h, _ptr(_dd(acc))), "hv_ekf_initialize_orientation")
+
+    def predict(self, t, gyro, acc):
+        g, a = _dd(gyro), _dd(acc)
+        check(self.lib.hv_ekf_predict(self.h, t, _ptr(g), _ptr(a)), "hv_ekf_predict")
+
+    def update_zupt(self, r): check(self.lib.hv_ekf_update_zupt(self.h, r), "hv_ekf_update_zupt")
+    def update_zupt_initialization(self): check(self.lib.hv_ekf_update_zupt_initialization(self.h), "hv_ekf_update_zupt_initialization")
+    def update_zrupt(self, gyro): check(self.lib.hv_ekf_update_zrupt(self.h, _ptr(_dd(gyro))), "hv_ekf_update_zrupt")
+    def update_pseudo_velocity(self, speed, r): check(self.lib.hv_ekf_update_pseudo_velocity(self.h, speed, r), "hv_ekf_update_pseudo_velocity")
+    def update_position(self, pos, r): check(self.lib.hv_ekf_update_position(self.h, _ptr(_dd(pos)), r), "hv_ekf_update_position")
+    def update_zero_height(self, r): check(self.lib.hv_ekf_update_zero_height(self.h, r), "hv_ekf_update_zero_height")
+    def update_orientation(self, q, r): check(self.lib.hv_ekf_update_orientation(self.h, _ptr(_dd(q)), r), "hv_ekf_update_orientation")
+
+    def visual_check(self, H, f, y, r, rmse_thr=-1.0):
+        H = np.asfortranarray(H, dtype=np.float64); f, y = _dd(f), _dd(y)
+        st, chi2 = c_int(-1), c_double(0.0)
+        check(self.lib.hv_ekf_visual_check(self.h, _ptr(H), H.shape[0], H.shape[1], _ptr(f), _ptr(y), r, rmse_thr,
+                                           ctypes.byref(st), ctypes.byref(chi2)), "hv_ekf_visual_check")
+        return st.value, chi2.value
+
+    def visual_update(self, H, f, y, r):
+        H = np.asfortranarray(H, dtype=np.float64); f, y = _dd(f), _dd(y)
+        check(self.lib.hv_ekf_visual_update(self.h, _ptr(H), H.shape[0], H.shape[1], _ptr(f), _ptr(y), r), "hv_ekf_visual_update")
+
+    def visual_check_update(self, H, f, y, r, rmse_thr=-1.0):
+        H = np.asfortranarray(H, dtype=np.float64); f, y = _dd(f), _dd(y)
+        st, chi2 = c_int(-1), c_double(0.0)
+        m = np.zeros(self.N)
+        check(self.lib.hv_ekf_visual_check_update(self.h, _ptr(H), H.shape[0], H.shape[1], _ptr(f), _ptr(y), r, rmse_thr,
+                                                  ctypes.byref(st), ctypes.byref(chi2), _ptr(m)), "hv_ekf_visual_check_update")
+        return st.value, chi2.value, m
+
+    def visual_device(self, d_H, n, l, d_f, d_y, r, rmse_thr, mode, d_result=None):
+        check(self.lib.hv_ekf_visual_device(self.h, _ptr(d_H), n, l, _ptr(d_f), _ptr(d_y), r, rmse_thr, mode, _ptr(d_result)),
+              "hv_ekf_visual_device")
+
+    def augment(self, drop=-1): check(self.lib.hv_ekf_augment(self.h, drop), "hv_ekf_augment")
+    def unaugment(self): check(self.lib.hv_ekf_unaugment(self.h), "hv_ekf_unaugment")
+    def symmetrize(self): check(self.lib.hv_ekf_symmetrize(self.h), "hv_ekf_symmetrize")
+    def normalize_quaternions(self, only_current=False): check(self.lib.hv_ekf_normalize_quaternions(self.h, 1 if only_current else 0), "hv_ekf_normalize_quaternions")
+    def translate_to(self, pos): check(self.lib.hv_ekf_translate_to(self.h, _ptr(_dd(pos))), "hv_ekf_translate_to")
+    def transform_to(self, pos, q, i=-1): check(self.lib.hv_ekf_transform_to(self.h, _ptr(_dd(pos)), _ptr(_dd(q)), i), "hv_ekf_transform_to")
+    def insert_map_point(self, idx, pf): check(self.lib.hv_ekf_insert_map_point(self.h, idx, _ptr(_dd(pf))), "hv_ekf_insert_map_point")
+    def condition_on_last_pose(self): check(self.lib.hv_ekf_condition_on_last_pose(self.h), "hv_ekf_condition_on_last_pose")
+    def lock_biases(self): check(self.lib.hv_ekf_lock_biases(self.h), "hv_ekf_lock_biases")

@@ -1,0 +1,545 @@
+// hybvio_b200/csrc/ekf_capi.cu -- C ABI of the EKF (include/hybvio_b200.h). Host side of odometry::EKF:
+// the scalar bookkeeping EKFImplementation keeps next to m and P (sample times, ZUPT rate limits, augment times;
+// src/odometry/ekf.cpp:145-151) lives here; m, P and all arithmetic on them live on the device (ekf.cu).
+#include "capi_internal.h"
+#include "ekf.cuh"
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+struct hv_ekf {
+    hv_ctx* ctx = nullptr;
+    hv_ekf_params prm;
+    int N = 0, trail = 0, mapDim = 0;
+    double noiseScale = 1.0;      // = odometry.noiseScale^2 (ekf.cpp:154)
+    double* d_block = nullptr;    // one allocation: m | P | P2 | work | Hs | Q | dydx | res | in
+    EkfBufs b;
+    double* d_in = nullptr;       // staging for H, f, y uploads
+    size_t inDoubles = 0;
+    double* h_pin = nullptr;      // pinned host staging: [in (inDoubles) | out (N + 8)]
+    // host bookkeeping, exactly the members of EKFImplementation (ekf.cpp:145-151)
+    int augmentCount = 0;
+    std::vector<double> augmentTimes;
+    double time = 0.0, ZUPTtime = -1.0, ZRUPTtime = -1.0, initZUPTtime = -1.0;
+    bool wasStationary = false;
+    double prevSampleT = -1.0, firstSampleT = -1.0;
+    bool firstSample = true;
+    std::vector<double> chi2inv95;
+};
+
+// ---- chi-square 95% quantiles (the reference hard-codes the table odometry/util.hpp:23; recomputed here by
+// inverting the regularised incomplete gamma function to ~1e-14 relative)
+static double gamma_p(double a, double x)
+{
+    if (x <= 0) return 0.0;
+    const double gln = lgamma(a);
+    if (x < a + 1.0) {
+        double ap = a, sum = 1.0 / a, del = sum;
+        for (int i = 0; i < 2000; i++) { ap += 1.0; del *= x / ap; sum += del; if (fabs(del) < fabs(sum) * 1e-17) break; }
+        return sum * exp(-x + a * log(x) - gln);
+    }
+    double bq = x + 1.0 - a, c = 1e300, d = 1.0 / bq, h = d;
+    for (int i = 1; i < 2000; i++) {
+        const double an = -i * (i - a); bq += 2.0;
+        d = an * d + bq; if (fabs(d) < 1e-300) d = 1e-300;
+        c = bq + an / c; if (fabs(c) < 1e-300) c = 1e-300;
+        d = 1.0 / d; const double del = d * c; h *= del;
+        if (fabs(del - 1.0) < 1e-17) break;
+    }
+    return 1.0 - exp(-x + a * log(x) - gln) * h;
+}
+static double chi2inv(double p, int k)
+{
+    double lo = 0.0, hi = k + 10.0 * sqrt(2.0 * k) + 20.0;
+    for (int it = 0; it < 200; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (gamma_p(0.5 * k, 0.5 * mid) < p) lo = mid; else hi = mid;
+        if (hi - lo < 1e-15 * hi) break;
+    }
+    return 0.5 * (lo + hi);
+}
+
+static inline double pow2(double x) { return x * x; }
+
+static int ekf_check(const hv_ekf* e, const char* who)
+{
+    if (!e) { hv_set_error("%s: NULL ekf", who); return HV_ERR_INVALID; }
+    return HV_OK;
+}
+
+#define EKF_ENTER(e, who)                              \
+    do { int rc_ = ekf_check(e, who); if (rc_ != HV_OK) return rc_; HV_CUDA(cudaSetDevice((e)->ctx->device)); } while (0)
+
+static int launch_update(hv_ekf* e, EkfUpdateArgs& a)
+{
+    a.b = e->b;
+    a.noiseScale = e->noiseScale;
+    const size_t need = ekf_update_smem_bytes(a.n, e->N);
+    a.useGlobalWork = (a.op != EKF_OP_AUGMENT && need > 200 * 1024) ? 1 : 0;
+    HV_CUDA(ekf_launch_update(a, e->ctx->stream));
+    e->ctx->launches++;
+    return HV_OK;
+}
+
+static void fill_small(EkfUpdateArgs& a, int op, int n, int l, double Rdiag, int mode = EKF_MODE_UPDATE)
+{
+    memset(&a, 0, sizeof(a));
+    a.op = op; a.n = n; a.l = l; a.mode = mode; a.Rdiag = Rdiag; a.rmseThr = -1.0; a.chi2Thr = 0.0;
+}
+
+static int launch_ew(hv_ekf* e, int op, int ival0 = 0, const double* dv = nullptr, int ndv = 0)
+{
+    EkfEwArgs a; memset(&a, 0, sizeof(a));
+    a.b = e->b; a.op = op; a.ival0 = ival0;
+    for (int i = 0; i < ndv; i++) a.dval[i] = dv[i];
+    HV_CUDA(ekf_launch_elementwise(a, e->ctx->stream));
+    e->ctx->launches++;
+    return HV_OK;
+}
+
+static void swap_P(hv_ekf* e) { double* t = e->b.P; e->b.P = e->b.P2; e->b.P2 = t; }
+
+extern "C" {
+
+void hv_ekf_default_params(hv_ekf_params* p)
+{
+    // codegen/parameter_definitions.c:68-160
+    p->camera_trail_length = 20; p->hybrid_map_size = 0;
+    p->noise_scale = 100; p->gravity = 9.819;
+    p->noise_initial_pos = 1e-5; p->noise_initial_vel = 0.1; p->noise_initial_ori = 0.0316227766;
+    p->noise_initial_bga = 1e-3; p->noise_initial_baa = 1e-6; p->noise_initial_bat = 1e-5; p->noise_initial_sft = 1e-5;
+    p->noise_initial_pos_trail = 100; p->noise_initial_ori_trail = 3.16227766;
+    p->noise_process_acc = 0.003; p->noise_process_gyro = 0.00017;
+    p->noise_process_baa = 1e-4; p->noise_process_baa_rev = 0.1; p->noise_process_bga = 0; p->noise_process_bga_rev = 0.1;
+    p->augment_r = 1e-9; p->init_zupt_r = 1e-4; p->rotation_zupt_r = 1e-6;
+}
+
+static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
+{
+    hv_ekf* e = new hv_ekf;
+    e->ctx = c; e->prm = *prm;
+    e->trail = prm->camera_trail_length; e->mapDim = prm->hybrid_map_size * EKF_MAP_POINT;
+    e->N = EKF_INER + e->trail * EKF_POSE + e->mapDim;
+    e->noiseScale = prm->noise_scale * prm->noise_scale;
+    const size_t N = e->N, NN = N * N;
+    const size_t workD = N * (2 * N + 4);
+    e->inDoubles = NN + 2 * N;
+    const size_t total = N + NN + NN + workD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + 8 + e->inDoubles;
+    cudaError_t err = cudaMalloc(&e->d_block, total * sizeof(double));
+    if (err != cudaSuccess) { delete e; hv_set_error("hv_ekf_create: cudaMalloc failed: %s", cudaGetErrorString(err)); return HV_ERR_OOM; }
+    cudaMemsetAsync(e->d_block, 0, total * sizeof(double), c->stream);
+    double* p = e->d_block;
+    e->b.m = p; p += N; e->b.P = p; p += NN; e->b.P2 = p; p += NN; e->b.work = p; p += workD;
+    e->b.Hs = p; p += EKF_SMALL_MAXN * EKF_SMALL_MAXL; e->b.Q = p; p += 144; e->b.dydx = p; p += 400; e->b.res = p; p += 8;
+    e->d_in = p;
+    e->b.N = e->N; e->b.trail = e->trail; e->b.mapDim = e->mapDim;
+    err = cudaMallocHost(&e->h_pin, (e->inDoubles + N + 8) * sizeof(double));
+    if (err != cudaSuccess) { cudaFree(e->d_block); delete e; hv_set_error("hv_ekf_create: cudaMallocHost failed"); return HV_ERR_OOM; }
+    *out = e;
+    return HV_OK;
+}
+
+int hv_ekf_create(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
+{
+    if (!c || !prm || !out || prm->camera_trail_length < 1 || prm->hybrid_map_size < 0) {
+        hv_set_error("hv_ekf_create: invalid argument"); return HV_ERR_INVALID;
+    }
+    const int N = EKF_INER + prm->camera_trail_length * EKF_POSE + prm->hybrid_map_size * EKF_MAP_POINT;
+    if (N > 768) { hv_set_error("hv_ekf_create: state dimension %d > 768 unsupported", N); return HV_ERR_UNSUPPORTED; }
+    HV_CUDA(cudaSetDevice(c->device));
+    hv_ekf* e = nullptr;
+    int rc = ekf_alloc(c, prm, &e);
+    if (rc != HV_OK) return rc;
+    // initial state (ekf.cpp:174-225)
+    std::vector<double> m(N, 0.0), P((size_t)N * N, 0.0), Q(144, 0.0);
+    m[EKF_ORI] = 1.0;
+    for (int i = 0; i < 3; i++) m[EKF_BAT + i] = 1.0;
+    auto diag = [&](int i, double v) { P[(size_t)i * (N + 1)] = v; };
+    for (int i = 0; i < 3; i++) { diag(EKF_POS + i, pow2(prm->noise_initial_pos)); diag(EKF_VEL + i, pow2(prm->noise_initial_vel)); }
+    for (int i = 0; i < 4; i++) diag(EKF_ORI + i, 1.0);
+    for (int i = 0; i < 3; i++) { diag(EKF_BGA + i, pow2(prm->noise_initial_bga)); diag(EKF_BAA + i, pow2(prm->noise_initial_baa)); diag(EKF_BAT + i, pow2(prm->noise_initial_bat)); }
+    diag(EKF_SFT, pow2(prm->noise_initial_sft));
+    for (int p = 0; p < e->trail; p++) {
+        const int o = EKF_CAM + p * EKF_POSE;
+        for (int i = 0; i < 3; i++) diag(o + i, pow2(prm->noise_initial_pos_trail));
+        for (int i = 0; i < 4; i++) diag(o + 3 + i, pow2(prm->noise_initial_ori_trail));
+    }
+    for (int i = 0; i < 3; i++) { Q[(EKF_Q_ACC + i) * 13] = pow2(prm->noise_process_acc); Q[(EKF_Q_GYRO + i) * 13] = pow2(prm->noise_process_gyro); }
+    for (auto& v : P) v *= e->noiseScale;
+    for (auto& v : Q) v *= e->noiseScale;
+    HV_CUDA(cudaMemcpyAsync(e->b.m, m.data(), sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
+    HV_CUDA(cudaMemcpyAsync(e->b.P, P.data(), sizeof(double) * N * N, cudaMemcpyHostToDevice, c->stream));
+    HV_CUDA(cudaMemcpyAsync(e->b.Q, Q.data(), sizeof(double) * 144, cudaMemcpyHostToDevice, c->stream));
+    HV_CUDA(cudaStreamSynchronize(c->stream));
+    e->chi2inv95.resize(201);
+    e->chi2inv95[0] = 0.0;
+    for (int k = 1; k <= 200; k++) e->chi2inv95[k] = chi2inv(0.95, k);
+    *out = e;
+    return HV_OK;
+}
+
+int hv_ekf_destroy(hv_ekf* e)
+{
+    if (!e) return HV_OK;
+    cudaSetDevice(e->ctx->device);
+    cudaStreamSynchronize(e->ctx->stream);
+    cudaFree(e->d_block);
+    cudaFreeHost(e->h_pin);
+    delete e;
+    return HV_OK;
+}
+
+int hv_ekf_clone(const hv_ekf* src, hv_ekf** out)
+{
+    if (!src || !out) { hv_set_error("hv_ekf_clone: NULL"); return HV_ERR_INVALID; }
+    HV_CUDA(cudaSetDevice(src->ctx->device));
+    hv_ekf* e = nullptr;
+    int rc = ekf_alloc(src->ctx, &src->prm, &e);
+    if (rc != HV_OK) return rc;
+    const size_t N = src->N;
+    cudaStream_t s = src->ctx->stream;
+    HV_CUDA(cudaMemcpyAsync(e->b.m, src->b.m, sizeof(double) * N, cudaMemcpyDeviceToDevice, s));
+    HV_CUDA(cudaMemcpyAsync(e->b.P, src->b.P, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, s));
+    HV_CUDA(cudaMemcpyAsync(e->b.Q, src->b.Q, sizeof(double) * 144, cudaMemcpyDeviceToDevice, s));
+    HV_CUDA(cudaMemcpyAsync(e->b.dydx, src->b.dydx, sizeof(double) * 400, cudaMemcpyDeviceToDevice, s));
+    e->augmentCount = src->augmentCount; e->augmentTimes = src->augmentTimes;
+    e->time = src->time; e->ZUPTtime = src->ZUPTtime; e->ZRUPTtime = src->ZRUPTtime; e->initZUPTtime = src->initZUPTtime;
+    e->wasStationary = src->wasStationary; e->prevSampleT = src->prevSampleT; e->firstSampleT = src->firstSampleT;
+    e->firstSample = src->firstSample; e->chi2inv95 = src->chi2inv95;
+    *out = e;
+    return HV_OK;
+}
+
+int hv_ekf_state_dim(const hv_ekf* e) { return e ? e->N : HV_ERR_INVALID; }
+int hv_ekf_pose_count(const hv_ekf* e) { return e ? e->augmentCount + 1 : HV_ERR_INVALID; }
+double hv_ekf_platform_time(const hv_ekf* e) { return e ? e->firstSampleT + e->time : 0.0; }
+double hv_ekf_history_time(const hv_ekf* e, int i)
+{
+    if (!e) return 0.0;
+    if (i == -1) return hv_ekf_platform_time(e);
+    const int n = (int)e->augmentTimes.size();
+    if (i < 0 || i >= n) return 0.0;
+    return e->augmentTimes[n - i - 1];
+}
+int hv_ekf_was_stationary(const hv_ekf* e) { return e && e->wasStationary ? 1 : 0; }
+int hv_ekf_set_first_sample_time(hv_ekf* e, double t)
+{
+    if (!e || !(t > 0.0)) { hv_set_error("hv_ekf_set_first_sample_time: invalid"); return HV_ERR_INVALID; }
+    e->firstSample = false; e->firstSampleT = t; e->prevSampleT = t; e->time = t;   // ekf.cpp:1035-1041
+    return HV_OK;
+}
+
+int hv_ekf_upload(hv_ekf* e, const double* m, const double* P)
+{
+    EKF_ENTER(e, "hv_ekf_upload");
+    const size_t N = e->N;
+    if (m) HV_CUDA(cudaMemcpyAsync(e->b.m, m, sizeof(double) * N, cudaMemcpyHostToDevice, e->ctx->stream));
+    if (P) HV_CUDA(cudaMemcpyAsync(e->b.P, P, sizeof(double) * N * N, cudaMemcpyHostToDevice, e->ctx->stream));
+    HV_CUDA(cudaStreamSynchronize(e->ctx->stream));   // caller's buffers may be pageable / reused
+    return HV_OK;
+}
+
+int hv_ekf_download(hv_ekf* e, double* m, double* P)
+{
+    EKF_ENTER(e, "hv_ekf_download");
+    const size_t N = e->N;
+    if (m) HV_CUDA(cudaMemcpyAsync(m, e->b.m, sizeof(double) * N, cudaMemcpyDeviceToHost, e->ctx->stream));
+    if (P) HV_CUDA(cudaMemcpyAsync(P, e->b.P, sizeof(double) * N * N, cudaMemcpyDeviceToHost, e->ctx->stream));
+    HV_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    return HV_OK;
+}
+
+int hv_ekf_download_inertial(hv_ekf* e, double* m20, double* P20)
+{
+    EKF_ENTER(e, "hv_ekf_download_inertial");
+    if (m20) HV_CUDA(cudaMemcpyAsync(m20, e->b.m, sizeof(double) * 20, cudaMemcpyDeviceToHost, e->ctx->stream));
+    if (P20) HV_CUDA(cudaMemcpy2DAsync(P20, 20 * sizeof(double), e->b.P, e->N * sizeof(double), 20 * sizeof(double), 20,
+                                       cudaMemcpyDeviceToHost, e->ctx->stream));
+    HV_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    return HV_OK;
+}
+
+int hv_ekf_set_inertial_state(hv_ekf* e, const double* m20, const double* P20)
+{
+    EKF_ENTER(e, "hv_ekf_set_inertial_state");
+    if (!m20 || !P20) { hv_set_error("hv_ekf_set_inertial_state: NULL"); return HV_ERR_INVALID; }
+    HV_CUDA(cudaMemcpyAsync(e->b.m, m20, sizeof(double) * 20, cudaMemcpyHostToDevice, e->ctx->stream));
+    HV_CUDA(cudaMemcpy2DAsync(e->b.P, e->N * sizeof(double), P20, 20 * sizeof(double), 20 * sizeof(double), 20,
+                              cudaMemcpyHostToDevice, e->ctx->stream));
+    HV_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    e->augmentCount = 0; e->augmentTimes.clear();   // pose trail invalid (ekf.cpp:687-689)
+    return HV_OK;
+}
+
+int hv_ekf_set_process_noise(hv_ekf* e, const double* Q)
+{
+    EKF_ENTER(e, "hv_ekf_set_process_noise");
+    if (!Q) { hv_set_error("hv_ekf_set_process_noise: NULL"); return HV_ERR_INVALID; }
+    HV_CUDA(cudaMemcpyAsync(e->b.Q, Q, sizeof(double) * 144, cudaMemcpyHostToDevice, e->ctx->stream));
+    HV_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    return HV_OK;
+}
+
+int hv_ekf_get_dydx(hv_ekf* e, double* d)
+{
+    EKF_ENTER(e, "hv_ekf_get_dydx");
+    HV_CUDA(cudaMemcpyAsync(d, e->b.dydx, sizeof(double) * 400, cudaMemcpyDeviceToHost, e->ctx->stream));
+    HV_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    return HV_OK;
+}
+
+int hv_ekf_initialize_orientation(hv_ekf* e, const double xa[3])
+{
+    EKF_ENTER(e, "hv_ekf_initialize_orientation");
+    // Eigen::Quaterniond::FromTwoVectors(-gravity, xa), -gravity = (0, 0, +g)  (ekf.cpp:301)
+    const double nb = std::sqrt(xa[0] * xa[0] + xa[1] * xa[1] + xa[2] * xa[2]);
+    if (!(nb > 0)) { hv_set_error("hv_ekf_initialize_orientation: zero accelerometer sample"); return HV_ERR_INVALID; }
+    const double v0[3] = {0, 0, e->prm.gravity >= 0 ? 1.0 : -1.0}, v1[3] = {xa[0] / nb, xa[1] / nb, xa[2] / nb};
+    double c = v0[2] * v1[2];
+    double dv[5];
+    if (c < -1.0 + 1e-12) {
+        // antiparallel: Eigen takes the rotation axis from an SVD null vector (any axis orthogonal to v0); we fix
+        // the x axis, which keeps q[3] == 0 as ekf.cpp:310 asserts.
+        c = c < -1.0 ? -1.0 : c;
+        const double w2 = (1.0 + c) * 0.5;
+        dv[0] = std::sqrt(w2); dv[1] = std::sqrt(1.0 - w2); dv[2] = 0.0; dv[3] = 0.0;
+    } else {
+        const double ax[3] = {v0[1] * v1[2] - v0[2] * v1[1], v0[2] * v1[0] - v0[0] * v1[2], v0[0] * v1[1] - v0[1] * v1[0]};
+        const double s = std::sqrt((1.0 + c) * 2.0), invs = 1.0 / s;
+        dv[0] = s * 0.5; dv[1] = ax[0] * invs; dv[2] = ax[1] * invs; dv[3] = ax[2] * invs;
+    }
+    dv[4] = pow2(e->prm.noise_initial_ori) * e->noiseScale;
+    return launch_ew(e, EKF_EW_INIT_ORIENTATION, 0, dv, 5);
+}
+
+int hv_ekf_predict(hv_ekf* e, double t, const double xg[3], const double xa[3])
+{
+    EKF_ENTER(e, "hv_ekf_predict");
+    double dt = 0.0;                       // ekf.cpp:357-370
+    if (!e->firstSample) { dt = t - e->prevSampleT; e->time = t - e->firstSampleT; }
+    else { e->firstSampleT = t; e->firstSample = false; }
+    e->prevSampleT = t;
+    if (dt <= 0.0) return HV_OK;
+    EkfPredictArgs a; memset(&a, 0, sizeof(a));
+    a.b = e->b; a.dt = dt; a.gravity = e->prm.gravity;
+    for (int i = 0; i < 3; i++) { a.xg[i] = xg[i]; a.xa[i] = xa[i]; }
+    a.qBaa = -1.0; a.qBga = -1.0; a.baaDecay = 1.0; a.bgaDecay = 1.0;
+    if (e->prm.noise_process_baa > 0.0) {  // ekf.cpp:397-404, 443-445
+        const double th = e->prm.noise_process_baa_rev;
+        a.qBaa = e->noiseScale * pow2(e->prm.noise_process_baa);
+        if (th > 0.0) a.qBaa *= (1 - std::exp(-2 * dt * th)) / (2 * th);
+        a.baaDecay = std::exp(-dt * th);
+    }
+    if (e->prm.noise_process_bga > 0.0) {  // ekf.cpp:405-412, 446-448
+        const double th = e->prm.noise_process_bga_rev;
+        a.qBga = e->noiseScale * pow2(e->prm.noise_process_bga);
+        if (th > 0.0) a.qBga *= (1 - std::exp(-2 * dt * th)) / (2 * th);
+        a.bgaDecay = std::exp(-dt * th);
+    }
+    HV_CUDA(ekf_launch_predict(a, e->ctx->stream));
+    e->ctx->launches++;
+    return HV_OK;
+}
+
+int hv_ekf_update_zupt(hv_ekf* e, double r)
+{
+    EKF_ENTER(e, "hv_ekf_update_zupt");
+    if (e->time - e->ZUPTtime < 0.25) return HV_OK;          // ekf.cpp:574-578
+    e->ZUPTtime = e->time; e->wasStationary = true;
+    EkfUpdateArgs a; fill_small(a, EKF_OP_ZUPT, 3, EKF_VEL + 3, r * e->noiseScale);
+    return launch_update(e, a);
+}
+
+int hv_ekf_update_zupt_initialization(hv_ekf* e)
+{
+    EKF_ENTER(e, "hv_ekf_update_zupt_initialization");
+    if (e->wasStationary || e->time > 60 || e->time - e->initZUPTtime < 0.1) return HV_OK;   // ekf.cpp:598-601
+    e->initZUPTtime = e->time;
+    EkfUpdateArgs a; fill_small(a, EKF_OP_ZUPT, 3, EKF_VEL + 3, e->prm.init_zupt_r * e->noiseScale * std::exp(0.5 * e->time));
+    return launch_update(e, a);
+}
+
+int hv_ekf_update_zrupt(hv_ekf* e, const double xg[3])
+{
+    EKF_ENTER(e, "hv_ekf_update_zrupt");
+    if (e->time - e->ZRUPTtime < 0.25) return HV_OK;         // ekf.cpp:615-618
+    e->ZRUPTtime = e->time;
+    EkfUpdateArgs a; fill_small(a, EKF_OP_ZRUPT, 3, EKF_BGA + 3, e->prm.rotation_zupt_r * e->noiseScale);
+    for (int i = 0; i < 3; i++) a.ysmall[i] = xg[i];
+    return launch_update(e, a);
+}
+
+int hv_ekf_update_pseudo_velocity(hv_ekf* e, double defaultSpeed, double r)
+{
+    EKF_ENTER(e, "hv_ekf_update_pseudo_velocity");
+    EkfUpdateArgs a; fill_small(a, EKF_OP_PSEUDO_VELOCITY, 1, EKF_VEL + 2, r * e->noiseScale);
+    a.defaultSpeed = defaultSpeed;
+    return launch_update(e, a);
+}
+
+int hv_ekf_update_position(hv_ekf* e, const double y[3], double r)
+{
+    EKF_ENTER(e, "hv_ekf_update_position");
+    EkfUpdateArgs a; fill_small(a, EKF_OP_POSITION, 3, EKF_POS + 3, r * e->noiseScale);
+    for (int i = 0; i < 3; i++) a.ysmall[i] = y[i];
+    a.symmetrize = 1;
+    return launch_update(e, a);
+}
+
+int hv_ekf_update_zero_height(hv_ekf* e, double r)
+{
+    EKF_ENTER(e, "hv_ekf_update_zero_height");
+    EkfUpdateArgs a; fill_small(a, EKF_OP_ZERO_HEIGHT, 1, EKF_POS + 3, r * e->noiseScale);
+    a.symmetrize = 1;
+    return launch_update(e, a);
+}
+
+int hv_ekf_update_orientation(hv_ekf* e, const double q[4], double r)
+{
+    EKF_ENTER(e, "hv_ekf_update_orientation");
+    EkfUpdateArgs a; fill_small(a, EKF_OP_ORIENTATION, 4, EKF_ORI + 4, r * e->noiseScale);
+    for (int i = 0; i < 4; i++) a.ysmall[i] = q[i];
+    a.normalizeAll = 1; a.symmetrize = 1;
+    return launch_update(e, a);
+}
+
+static int visual_args(hv_ekf* e, const char* who, int n, int l, double r, double rmseThr, int mode, EkfUpdateArgs& a)
+{
+    if (n <= 0 || l <= 0 || l > e->N || n > e->N) {   // maxHRows = stateDim (ekf.cpp:177-180)
+        hv_set_error("%s: bad shape n=%d l=%d (N=%d)", who, n, l, e->N); return HV_ERR_INVALID;
+    }
+    if (mode != EKF_MODE_UPDATE && n >= (int)e->chi2inv95.size()) { hv_set_error("%s: n=%d exceeds the chi2 table", who, n); return HV_ERR_INVALID; }
+    memset(&a, 0, sizeof(a));
+    a.op = EKF_OP_DENSE; a.n = n; a.l = l; a.mode = mode;
+    a.Rdiag = (r * r) * e->noiseScale;                          // ekf.cpp:777
+    a.rmseThr = mode == EKF_MODE_UPDATE ? -1.0 : rmseThr;
+    a.chi2Thr = mode == EKF_MODE_UPDATE ? 0.0 : e->chi2inv95[n];
+    a.skipChi2 = (mode != EKF_MODE_UPDATE && r < 0.0) ? 1 : 0;
+    a.normalizeAll = 1;
+    return HV_OK;
+}
+
+static int visual_host(hv_ekf* e, const char* who, const double* H, int n, int l, const double* f, const double* y, double r,
+                       double rmseThr, int mode, int* vuStatus, double* chi2, double* mOut)
+{
+    if (!H || !f || !y) { hv_set_error("%s: NULL input", who); return HV_ERR_INVALID; }
+    EkfUpdateArgs a;
+    int rc = visual_args(e, who, n, l, r, rmseThr, mode, a);
+    if (rc != HV_OK) return rc;
+    cudaStream_t s = e->ctx->stream;
+    const size_t nl = (size_t)n * l, inD = nl + 2 * (size_t)n;
+    double* hin = e->h_pin;
+    memcpy(hin, H, nl * sizeof(double)); memcpy(hin + nl, f, n * sizeof(double)); memcpy(hin + nl + n, y, n * sizeof(double));
+    HV_CUDA(cudaMemcpyAsync(e->d_in, hin, inD * sizeof(double), cudaMemcpyHostToDevice, s));
+    a.H = e->d_in; a.f = e->d_in + nl; a.y = e->d_in + nl + n;
+    rc = launch_update(e, a);
+    if (rc != HV_OK) return rc;
+    if (mode == EKF_MODE_UPDATE && !mOut) return HV_OK;          // asynchronous
+    double* hout = e->h_pin + e->inDoubles;
+    HV_CUDA(cudaMemcpyAsync(hout, e->b.res, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (mOut) HV_CUDA(cudaMemcpyAsync(hout + 8, e->b.m, e->N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    HV_CUDA(cudaStreamSynchronize(s));
+    if (vuStatus) *vuStatus = (int)hout[0];
+    if (chi2) *chi2 = hout[1];
+    if (mOut) memcpy(mOut, hout + 8, e->N * sizeof(double));
+    if (hout[2] != 0.0) { hv_set_error("%s: innovation covariance not positive definite", who); return HV_ERR_STATE; }
+    return HV_OK;
+}
+
+int hv_ekf_visual_check(hv_ekf* e, const double* H, int n, int l, const double* f, const double* y, double r, double rmseThr,
+                        int* vuStatus, double* chi2)
+{
+    EKF_ENTER(e, "hv_ekf_visual_check");
+    return visual_host(e, "hv_ekf_visual_check", H, n, l, f, y, r, rmseThr, EKF_MODE_CHECK, vuStatus, chi2, nullptr);
+}
+
+int hv_ekf_visual_update(hv_ekf* e, const double* H, int n, int l, const double* f, const double* y, double r)
+{
+    EKF_ENTER(e, "hv_ekf_visual_update");
+    return visual_host(e, "hv_ekf_visual_update", H, n, l, f, y, r, -1.0, EKF_MODE_UPDATE, nullptr, nullptr, nullptr);
+}
+
+int hv_ekf_visual_check_update(hv_ekf* e, const double* H, int n, int l, const double* f, const double* y, double r, double rmseThr,
+                               int* vuStatus, double* chi2, double* mOut)
+{
+    EKF_ENTER(e, "hv_ekf_visual_check_update");
+    return visual_host(e, "hv_ekf_visual_check_update", H, n, l, f, y, r, rmseThr, EKF_MODE_CHECK_UPDATE, vuStatus, chi2, mOut);
+}
+
+int hv_ekf_visual_device(hv_ekf* e, const double* dH, int n, int l, const double* df, const double* dy, double r, double rmseThr,
+                         int mode, double* dResult)
+{
+    EKF_ENTER(e, "hv_ekf_visual_device");
+    if (!dH || !df || !dy || mode < 0 || mode > 2) { hv_set_error("hv_ekf_visual_device: invalid argument"); return HV_ERR_INVALID; }
+    EkfUpdateArgs a;
+    int rc = visual_args(e, "hv_ekf_visual_device", n, l, r, rmseThr, mode, a);
+    if (rc != HV_OK) return rc;
+    a.H = dH; a.f = df; a.y = dy;
+    rc = launch_update(e, a);
+    if (rc != HV_OK) return rc;
+    if (dResult) HV_CUDA(cudaMemcpyAsync(dResult, e->b.res, 2 * sizeof(double), cudaMemcpyDeviceToDevice, e->ctx->stream));
+    return HV_OK;
+}
+
+int hv_ekf_augment(hv_ekf* e, int discarded)
+{
+    EKF_ENTER(e, "hv_ekf_augment");
+    if (discarded == -1) discarded = e->trail - 1;               // ekf.cpp:849
+    if (discarded < 0 || discarded >= e->trail) { hv_set_error("hv_ekf_augment: pose index %d out of range", discarded); return HV_ERR_INVALID; }
+    EkfUpdateArgs a; fill_small(a, EKF_OP_AUGMENT, EKF_POSE, EKF_CAM + EKF_POSE, e->prm.augment_r * e->noiseScale);
+    a.dropIdx = discarded;
+    a.augNoisePos = pow2(e->prm.noise_initial_pos_trail) * e->noiseScale;
+    a.augNoiseOri = pow2(e->prm.noise_initial_ori_trail) * e->noiseScale;
+    a.normalizeAll = 1; a.symmetrize = 1;
+    int rc = launch_update(e, a);   // shift into P2, update there, Joseph product back into P: no swap
+    if (rc != HV_OK) return rc;
+    e->augmentTimes.push_back(hv_ekf_platform_time(e));          // ekf.cpp:876-884
+    if (e->augmentCount < e->trail) e->augmentCount++;
+    else e->augmentTimes.erase(e->augmentTimes.begin());
+    return HV_OK;
+}
+
+int hv_ekf_unaugment(hv_ekf* e)
+{
+    EKF_ENTER(e, "hv_ekf_unaugment");
+    if (e->augmentCount <= 0) { hv_set_error("hv_ekf_unaugment: no augmented pose (ekf.cpp:899 asserts)"); return HV_ERR_STATE; }
+    int rc = launch_ew(e, EKF_EW_UNAUGMENT);
+    if (rc != HV_OK) return rc;
+    swap_P(e);
+    e->augmentTimes.pop_back(); e->augmentCount--;
+    return HV_OK;
+}
+
+int hv_ekf_symmetrize(hv_ekf* e) { EKF_ENTER(e, "hv_ekf_symmetrize"); return launch_ew(e, EKF_EW_SYMMETRIZE); }
+int hv_ekf_normalize_quaternions(hv_ekf* e, int onlyCurrent) { EKF_ENTER(e, "hv_ekf_normalize_quaternions"); return launch_ew(e, EKF_EW_NORMALIZE, onlyCurrent ? 1 : 0); }
+int hv_ekf_translate_to(hv_ekf* e, const double pos[3]) { EKF_ENTER(e, "hv_ekf_translate_to"); return launch_ew(e, EKF_EW_TRANSLATE, 0, pos, 3); }
+
+int hv_ekf_transform_to(hv_ekf* e, const double pos[3], const double q[4], int poseIndex)
+{
+    EKF_ENTER(e, "hv_ekf_transform_to");
+    if (poseIndex < -1 || poseIndex >= e->trail) { hv_set_error("hv_ekf_transform_to: pose index out of range"); return HV_ERR_INVALID; }
+    const double dv[7] = {pos[0], pos[1], pos[2], q[0], q[1], q[2], q[3]};
+    int rc = launch_ew(e, EKF_EW_TRANSFORM, poseIndex, dv, 7);
+    if (rc != HV_OK) return rc;
+    swap_P(e);
+    return HV_OK;
+}
+
+int hv_ekf_insert_map_point(hv_ekf* e, int idx, const double pf[3])
+{
+    EKF_ENTER(e, "hv_ekf_insert_map_point");
+    const int off = e->N - e->mapDim + idx * EKF_MAP_POINT;      // getMapPointStateIndex (ekf.cpp:923-926)
+    if (idx < 0 || off + EKF_MAP_POINT > e->N) { hv_set_error("hv_ekf_insert_map_point: index out of range"); return HV_ERR_INVALID; }
+    return launch_ew(e, EKF_EW_INSERT_MAP_POINT, off, pf, 3);
+}
+
+int hv_ekf_condition_on_last_pose(hv_ekf* e)
+{
+    EKF_ENTER(e, "hv_ekf_condition_on_last_pose");
+    if (e->mapDim != 0 || e->augmentCount <= 0) { hv_set_error("hv_ekf_condition_on_last_pose: needs no hybrid map and >= 1 augmented pose"); return HV_ERR_STATE; }
+    return launch_ew(e, EKF_EW_CONDITION_LAST_POSE);
+}
+
+int hv_ekf_lock_biases(hv_ekf* e) { EKF_ENTER(e, "hv_ekf_lock_biases"); return launch_ew(e, EKF_EW_LOCK_BIASES); }
+
+} // extern "C"
