@@ -1,0 +1,510 @@
+#!/usr/bin/env python
+"""bench.py -- stereo frames/s of the HybVIO hot path (pyramid + LK + EKF) on B200, BASELINE.json's metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, libhybvio_b200.so)
+  python bench.py --impl reference ...                            the reference's own CPU path (oracle/_ref)
+
+A "step" is ONE stereo frame of BASELINE config 2 (EuRoC V1_02-shaped: 752x480 stereo, 150 features, 4-level pyramid,
+31x31 window, EKF state dimension 160) pushed through the whole hot path of one VIO session:
+    2 pyramids (one launch) -> LK prev-left -> left with predicted initial flow -> LK left -> right
+    -> 10 x EKF predict (200 Hz IMU at 20 fps) -> 20 visual-track outlier checks, the 5 designated ones followed by
+       their update (n = 8/20/40/84 rows) -> maintainPositiveSemiDefinite -> pose augmentation.
+Frames of one session are strictly sequential, so one stream per GPU is a latency-bound workload; --gpus N runs N
+independent sessions, one per GPU (BASELINE config 3; no data-path collective, NCCL only for the start barrier and
+the max-over-ranks reduction of the device time).
+
+`value`  = frames/s with every input already resident in HBM, no host synchronisation inside the timed region.
+`e2e`    = the same frames through the host-buffer C ABI the reference-side adapters call: each step copies its two
+           frames host->device from pinned memory, every LK call and every outlier check returns its result to the host
+           (the reference interface is synchronous there: src/odometry/backend.cpp:1158-1161), and the pose is read back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, NFEAT, WIN, MAXLEVEL, TRAIL = 752, 480, 150, 31, 3, 20
+VISUAL_R = 0.05
+N_ROWS = (8, 20, 40, 84)            # rows of the visual measurement models, cycled
+CHECKS, UPDATES, PREDICTS = 20, 5, 10
+POOL_FRAMES = int(os.environ.get("HV_BENCH_POOL_FRAMES", "128"))   # stereo pairs in the frame pool: 128 * 2 * 361 KB = 92 MB
+POOL_EKF = 64                       # frames of EKF inputs: 64 * 736 KB = 47 MB  (together 139 MB > 126 MB of L2)
+PYR_BYTES = 2_397_000               # algorithmic bytes per image
+LK_BYTES = NFEAT * 4 * 6144 + 12 * NFEAT
+
+
+def frame_index(k):                 # ping-pong through the pool so that consecutive steps are consecutive frames
+    p = 2 * (POOL_FRAMES - 1)
+    j = k % p
+    return j if j < POOL_FRAMES else p - j
+
+
+def ekf_rows(c):
+    n = N_ROWS[c % len(N_ROWS)]
+    return n, min(20 + 7 * TRAIL, 20 + 7 * max(1, n // 4))
+
+
+class Inputs:
+    """Deterministic synthetic inputs of one session, generated with torch on `device`."""
+
+    def __init__(self, device, seed=0):
+        import torch
+        from hybvio_b200 import synth
+        self.torch = torch
+        self.frames = synth.stereo_frames_torch(0, POOL_FRAMES, W, H, seed=42 + seed, device=device)    # (P, 2, H, W) u8
+        self.points = synth.interior_points(NFEAT, W, H, seed=7 + seed)
+        rng = np.random.RandomState(3 + seed)
+        # predicted initial flow = true flow of the synthetic stream + <= 1 px error (tracker.cpp:59-63 predictor)
+        self.init_noise = rng.uniform(-1, 1, (POOL_FRAMES, NFEAT, 2)).astype(np.float32)
+        self.flow = np.array([synth.true_flow(j, j + 1) for j in range(POOL_FRAMES)], np.float32)
+        irng = np.random.RandomState(11 + seed)
+        self.imu = np.zeros((POOL_EKF * PREDICTS, 6))
+        for i in range(len(self.imu)):
+            self.imu[i, :3] = np.array([0, 0, 0.2]) + irng.normal(0, 0.05, 3)
+            self.imu[i, 3:] = np.array([0.3 * np.sin(0.01 * i), 0.2 * np.cos(0.013 * i), 9.819]) + irng.normal(0, 0.2, 3)
+        # EKF measurement pool: per frame CHECKS x (H n x l column-major, f, y) packed in one fp64 buffer
+        self.ekf_off = []
+        off = 0
+        for c in range(CHECKS):
+            n, l = ekf_rows(c)
+            self.ekf_off.append((off, n, l))
+            off += n * l + 2 * n
+        self.ekf_stride = off
+        pool = np.zeros((POOL_EKF, off))
+        for fr in range(POOL_EKF):
+            for c, (o, n, l) in enumerate(self.ekf_off):
+                pool[fr, o:o + n * l] = rng.normal(0, 0.1, n * l)
+                f = rng.normal(0, 0.5, n)
+                # designated update slots (c < UPDATES) and most others are consistent measurements; every fourth is gross
+                y = f + rng.normal(0, 0.02 if (c < UPDATES or c % 4) else 40.0, n)
+                pool[fr, o + n * l:o + n * l + n] = f
+                pool[fr, o + n * l + n:o + n * l + 2 * n] = y
+        self.ekf_pool = pool
+
+    def init_guess(self, jp, j):
+        d = self.flow[min(jp, j)] * (1.0 if j > jp else -1.0)
+        return (self.points + d + self.init_noise[j]).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+class Session:
+    """One VIO session on one GPU: Tracker-side pyramids + LK and the EKF, all on one CUDA stream."""
+
+    def __init__(self, device_index, inputs):
+        import torch
+        from hybvio_b200 import capi
+        self.torch, self.capi, self.inp = torch, capi, inputs
+        self.dev = torch.device("cuda", device_index)
+        self.stream = torch.cuda.Stream(self.dev)
+        self.ctx = capi.Context(device_index, stream=self.stream.cuda_stream)
+        self.pyr = [self.ctx.pyramid(W, H, WIN, MAXLEVEL) for _ in range(4)]     # prevL, prevR, curL, curR
+        p = capi.EkfParams()
+        capi.load().hv_ekf_default_params(__import__("ctypes").byref(p))
+        p.camera_trail_length = TRAIL
+        self.ekf = capi.Ekf(self.ctx, p)
+        with torch.cuda.stream(self.stream):
+            self.d_frames = inputs.frames.to(self.dev)
+            self.d_points = torch.from_numpy(inputs.points).to(self.dev)
+            self.d_init = torch.from_numpy(np.stack([np.stack([inputs.init_guess(j - 1, j) for j in range(1, POOL_FRAMES)]),
+                                                     np.stack([inputs.init_guess(j + 1, j) for j in range(0, POOL_FRAMES - 1)])])).to(self.dev)
+            self.d_next = torch.zeros((NFEAT, 2), dtype=torch.float32, device=self.dev)
+            self.d_next2 = torch.zeros((NFEAT, 2), dtype=torch.float32, device=self.dev)
+            self.d_status = torch.zeros(NFEAT, dtype=torch.uint8, device=self.dev)
+            self.d_ts = torch.zeros(NFEAT, dtype=torch.int32, device=self.dev)
+            self.d_ekf_pool = torch.from_numpy(inputs.ekf_pool).to(self.dev)
+            self.d_res = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        self.h_frames = inputs.frames.cpu().pin_memory()
+        self.h_pose = torch.zeros(self.ekf.N, dtype=torch.float64).pin_memory()
+        self.t = 0.0
+        self.k = 0
+        self.prev_j = 0
+        self.ekf.initialize_orientation(inputs.imu[0, 3:])
+        # prime "previous frame" pyramids
+        self.ctx.build_pyramids(self.pyr[0:2], [self.d_frames[0, 0], self.d_frames[0, 1]], device=True)
+        self.ctx.sync()
+
+    def _ekf_inputs(self, k):
+        return k % POOL_EKF
+
+    def step_device(self):
+        """One frame, everything resident in HBM, no host synchronisation."""
+        self.k += 1
+        j = frame_index(self.k)
+        ctx, inp = self.ctx, self.inp
+        cur = self.pyr[2:4]
+        ctx.build_pyramids(cur, [self.d_frames[j, 0], self.d_frames[j, 1]], device=True)
+        init = self.d_init[0, j - 1] if j > self.prev_j else self.d_init[1, j]
+        self.d_next.copy_(init)                                   # predicted flow (host callback in the reference)
+        ctx.lk_track_device(self.pyr[0], cur[0], self.d_points, self.d_next, self.d_status, self.d_ts, NFEAT, True)
+        ctx.lk_track_device(cur[0], cur[1], self.d_next, self.d_next2, self.d_status, self.d_ts, NFEAT, False)
+        fr = self._ekf_inputs(self.k)
+        for s in range(PREDICTS):
+            self.t += 0.005
+            u = inp.imu[fr * PREDICTS + s]
+            self.ekf.predict(self.t, u[:3], u[3:])
+        base = self.d_ekf_pool[fr]
+        for c, (o, n, l) in enumerate(inp.ekf_off):
+            self.ekf.visual_device(base[o:], n, l, base[o + n * l:], base[o + n * l + n:], VISUAL_R, -1.0,
+                                   2 if c < UPDATES else 0, None)
+        self.ekf.symmetrize()
+        self.ekf.augment(-1)
+        self.pyr = self.pyr[2:4] + self.pyr[0:2]
+        self.prev_j = j
+
+    def step_e2e(self):
+        """The same frame through the host-buffer C ABI (what the reference-side adapters call)."""
+        self.k += 1
+        j = frame_index(self.k)
+        ctx, inp = self.ctx, self.inp
+        cur = self.pyr[2:4]
+        ctx.build_pyramids(cur, [self.h_frames[j, 0], self.h_frames[j, 1]], device=False)            # H2D inside
+        init = inp.init_guess(self.prev_j, j)
+        nxt, st, ts = ctx.lk_track(self.pyr[0], cur[0], inp.points, init)                           # H2D + D2H + sync
+        nxt2, st2, ts2 = ctx.lk_track(cur[0], cur[1], nxt)
+        fr = self._ekf_inputs(self.k)
+        for s in range(PREDICTS):
+            self.t += 0.005
+            u = inp.imu[fr * PREDICTS + s]
+            self.ekf.predict(self.t, u[:3], u[3:])
+        row = inp.ekf_pool[fr]
+        for c, (o, n, l) in enumerate(inp.ekf_off):
+            Hm = row[o:o + n * l].reshape((n, l), order="F")
+            f, y = row[o + n * l:o + n * l + n], row[o + n * l + n:o + n * l + 2 * n]
+            if c < UPDATES:
+                self.ekf.visual_check_update(Hm, f, y, VISUAL_R)                                     # one round trip
+            else:
+                self.ekf.visual_check(Hm, f, y, VISUAL_R)
+        self.ekf.symmetrize()
+        self.ekf.augment(-1)
+        m = self.ekf.download_inertial()[0]                                                          # pose read-back
+        self.pyr = self.pyr[2:4] + self.pyr[0:2]
+        self.prev_j = j
+        return m
+
+    H2D_BYTES = 2 * W * H + 2 * NFEAT * 16 + sum(8 * (n * l + 2 * n) for n, l in (ekf_rows(c) for c in range(CHECKS)))
+    D2H_BYTES = 2 * NFEAT * 13 + CHECKS * 24 + UPDATES * 8 * (20 + 7 * TRAIL) + 20 * 8 + 400 * 8
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def time_kernels(sess, reps=40):
+    """Average device time of each kernel class, CUDA events on the launching stream, inputs cycled through the pools."""
+    torch = sess.torch
+    out = {}
+
+    def timed(name, fn, launches, algo_bytes):
+        for i in range(3):
+            fn(i)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(sess.stream):
+            s.record(sess.stream)
+            for i in range(reps):
+                fn(i + 3)
+            e.record(sess.stream)
+        e.synchronize()
+        us = s.elapsed_time(e) * 1e3 / (reps * launches)
+        out[name] = {"us_per_launch": round(us, 3), "algo_bytes": algo_bytes, "gbs": round(algo_bytes / us * 1e-3, 2)}
+
+    inp, ctx, ekf = sess.inp, sess.ctx, sess.ekf
+    cur = sess.pyr[2:4]
+    timed("pyramid(2 images)", lambda i: ctx.build_pyramids(cur, [sess.d_frames[(7 * i) % POOL_FRAMES, 0], sess.d_frames[(7 * i) % POOL_FRAMES, 1]], device=True),
+          1, 2 * PYR_BYTES)
+    ctx.build_pyramids(cur, [sess.d_frames[1, 0], sess.d_frames[1, 1]], device=True)
+    ctx.build_pyramids(sess.pyr[0:2], [sess.d_frames[0, 0], sess.d_frames[0, 1]], device=True)
+
+    def lk_t(i):
+        sess.d_next.copy_(sess.d_init[0, 0])
+        ctx.lk_track_device(sess.pyr[0], cur[0], sess.d_points, sess.d_next, sess.d_status, sess.d_ts, NFEAT, True)
+    timed("lk_temporal(+init copy)", lk_t, 1, LK_BYTES)
+    timed("lk_stereo", lambda i: ctx.lk_track_device(cur[0], cur[1], sess.d_next, sess.d_next2, sess.d_status, sess.d_ts, NFEAT, False), 1, LK_BYTES)
+    N = ekf.N
+
+    def pred(i):
+        sess.t += 0.005
+        ekf.predict(sess.t, inp.imu[i % len(inp.imu), :3], inp.imu[i % len(inp.imu), 3:])
+    timed("ekf_predict", pred, 1, 2 * 8 * (40 * N - 400))
+    for n in N_ROWS:
+        c = N_ROWS.index(n)
+        o, n_, l = inp.ekf_off[c]
+
+        def chk(i, mode=0):
+            b = sess.d_ekf_pool[i % POOL_EKF]
+            ekf.visual_device(b[o:], n_, l, b[o + n_ * l:], b[o + n_ * l + n_:], VISUAL_R, -1.0, mode, None)
+        timed(f"ekf_check(n={n},l={l})", chk, 1, 8 * N * N + 8 * n * l)
+        timed(f"ekf_check_update(n={n},l={l})", lambda i: chk(i, 2), 1, 2 * 8 * N * N + 8 * n * l)
+        ekf.symmetrize()
+        ekf.augment(-1)
+    timed("ekf_symmetrize", lambda i: ekf.symmetrize(), 1, 2 * 8 * N * N)
+    timed("ekf_augment", lambda i: ekf.augment(-1), 1, 2 * 8 * N * N)
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device. hybvio_b200 has no CPU fallback; use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    inputs = Inputs(torch.device("cuda", local), seed=rank)
+    sess = Session(local, inputs)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        launches0 = sess.ctx.launches
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(sess.stream)
+        for _ in range(steps):
+            step()
+        e.record(sess.stream)
+        e.synchronize()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=sess.dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop() if sampler else None
+        return float(ms.item()), sess.ctx.launches - launches0, clocks
+
+    with torch.cuda.stream(sess.stream):
+        ms_dev, launches, clocks = timed_loop(sess.step_device, args.steps, args.warmup)
+        e2e_steps = max(3, min(args.steps, args.e2e_steps))
+        ms_e2e, _, _ = timed_loop(sess.step_e2e, e2e_steps, max(3, min(args.warmup, 10)))
+        m, P = sess.ekf.download()
+        healthy = bool(np.isfinite(m).all() and np.isfinite(P).all() and (np.diag(P) >= 0).all())
+        kern = time_kernels(sess) if rank == 0 else None
+
+    result = None
+    if rank == 0:
+        value = world * args.steps / (ms_dev * 1e-3)
+        e2e = world * e2e_steps / (ms_e2e * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        # per-step share of each kernel class
+        per_step = {"pyramid(2 images)": 1, "lk_temporal(+init copy)": 1, "lk_stereo": 1, "ekf_predict": PREDICTS, "ekf_symmetrize": 1, "ekf_augment": 1}
+        for c in range(CHECKS):
+            n, l = ekf_rows(c)
+            key = f"ekf_check_update(n={n},l={l})" if c < UPDATES else f"ekf_check(n={n},l={l})"
+            per_step[key] = per_step.get(key, 0) + 1
+        shares = {k: kern[k]["us_per_launch"] * cnt for k, cnt in per_step.items()}
+        tot = sum(shares.values())
+        fam = {"pyramid": 0.0, "lk": 0.0, "ekf_update_kernel": 0.0, "ekf_predict": 0.0, "ekf_other": 0.0}
+        for k, v in shares.items():
+            fam["pyramid" if k.startswith("pyr") else "lk" if k.startswith("lk") else "ekf_predict" if k == "ekf_predict" else
+                "ekf_update_kernel" if ("check" in k or "augment" in k) else "ekf_other"] += v
+        dom = max((k for k in shares if "check" in k), key=lambda k: shares[k]) if fam["ekf_update_kernel"] >= max(fam.values()) else \
+            max(shares, key=lambda k: shares[k])
+        roof = {"bound": "hbm", "kernel": ("ekf_update_kernel: " if "ekf_c" in dom or "augment" in dom else "") + dom,
+                "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": round(kern[dom]["gbs"] / peak, 5),
+                "traffic": None, "peak_source": peak_src, "share_of_step": round(shares[dom] / tot, 3),
+                "family_share_of_step": {k: round(v / tot, 3) for k, v in fam.items()},
+                "note": "algorithmic bytes (SURVEY.md 8(d)) / CUDA-event launch time; single-session workload is latency-bound"}
+        for k in kern:
+            kern[k]["frac_of_hbm_peak"] = round(kern[k]["gbs"] / peak, 5)
+        result = {
+            "metric": "stereo frames/sec (752x480, 150 tracks)", "value": round(value, 2), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16 fixed-point + f32 (pyramid, LK), f64 (EKF)", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: EuRoC V1_02-shaped stereo 752x480, 150 features, 4-level pyramid, win 31, "
+                                   "EKF N=160 (trail 20); per frame 2 pyramids + 2 LK calls + 10 predict + 20 checks (5 with update) + "
+                                   "symmetrise + augment; one independent session per GPU",
+                       "sessions_per_gpu": 1,
+                       "l2": f"inputs cycled through pools larger than L2 (frames {POOL_FRAMES * 2 * W * H / 1e6:.0f} MB + EKF inputs "
+                             f"{POOL_EKF * inputs.ekf_stride * 8 / 1e6:.0f} MB > 126 MB); no explicit flush",
+                       "ekf_healthy_after_run": healthy},
+            "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": Session.H2D_BYTES, "d2h_bytes_per_step": Session.D2H_BYTES,
+                    "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 5),
+                    "note": "host-buffer C ABI: pinned H2D of both frames, synchronous LK and outlier-check results, pose read-back"},
+            "gpu_launches": int(launches), "gpu_launches_per_step": round(launches / args.steps, 2),
+            "clocks": clocks, "roofline": roof, "kernels": kern,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            result["cpu_baseline"] = cpu_baseline(inputs, budget_s=args.cpu_budget)
+    sess.ctx.sync()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(result))
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+class RefSession:
+    """The reference's own CPU path for the same step: vendored OpenCV 4.3 pyramid + LK (oracle/_ref/libref_lk.so,
+    OpenCV pthreads on all cores) and src/odometry/ekf.cpp (oracle/_ref/libref_ekf.so, single thread like the
+    reference build's -DEIGEN_DONT_PARALLELIZE). Falls back to the C port (oracle/) where _ref was not built."""
+
+    def __init__(self, inputs):
+        import ctypes
+        from oracle import ekf_oracle, lk_oracle
+        self.inp = inputs
+        self.frames = inputs.frames.cpu().numpy()
+        if lk_oracle.have_ref() and ekf_oracle.have_ref():
+            self.kind, self.lk = "reference", lk_oracle.RefLK()
+            make_ekf = ekf_oracle.RefEKF
+            self.cores = self.lk.threads
+        else:
+            if not os.path.exists(lk_oracle.ORACLE_SO):
+                subprocess.check_call(["make", "-C", ROOT, "oracle"])
+            self.kind, self.lk = "port", lk_oracle.OracleLK()
+            make_ekf = ekf_oracle.OracleEKF
+            self.cores = 1
+        e = make_ekf()
+        p = e.default_params(); p.camera_trail_length = TRAIL
+        e.close()
+        self.ekf = make_ekf(p)
+        self.pyr = [self.lk.pyramid(self.frames[0, i % 2], WIN, MAXLEVEL) for i in range(4)]
+        self.t, self.k, self.prev_j = 0.0, 0, 0
+        self.ekf.initialize_orientation(inputs.imu[0, 3:])
+
+    def step(self):
+        self.k += 1
+        j = frame_index(self.k)
+        inp = self.inp
+        cur = self.pyr[2:4]
+        if self.kind == "reference":
+            self.lk.rebuild(cur[0], self.frames[j, 0]); self.lk.rebuild(cur[1], self.frames[j, 1])
+        else:
+            for q in cur:
+                q.free()
+            cur = [self.lk.pyramid(self.frames[j, 0], WIN, MAXLEVEL), self.lk.pyramid(self.frames[j, 1], WIN, MAXLEVEL)]
+            self.pyr[2:4] = cur
+        nxt, st, ts = self.lk.lk(self.pyr[0], cur[0], inp.points, inp.init_guess(self.prev_j, j), max_level=MAXLEVEL)
+        nxt2, st2, ts2 = self.lk.lk(cur[0], cur[1], nxt, None, max_level=MAXLEVEL)
+        fr = self.k % POOL_EKF
+        for s in range(PREDICTS):
+            self.t += 0.005
+            u = inp.imu[fr * PREDICTS + s]
+            self.ekf.predict(self.t, u[:3], u[3:])
+        row = inp.ekf_pool[fr]
+        for c, (o, n, l) in enumerate(inp.ekf_off):
+            Hm = row[o:o + n * l].reshape((n, l), order="F")
+            f, y = row[o + n * l:o + n * l + n], row[o + n * l + n:o + n * l + 2 * n]
+            st_, _ = self.ekf.visual_check(Hm, f, y, VISUAL_R)
+            if c < UPDATES and st_ == 0:
+                self.ekf.visual_update(Hm, f, y, VISUAL_R)
+        self.ekf.symmetrize()
+        self.ekf.augment(-1)
+        self.pyr = self.pyr[2:4] + self.pyr[0:2]
+        self.prev_j = j
+
+
+def cpu_baseline(inputs, budget_s=12.0):
+    rs = RefSession(inputs)
+    for _ in range(5):
+        rs.step()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        rs.step()
+    per = (time.perf_counter() - t0) / 10
+    n = int(max(20, min(1500, budget_s / per)))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        rs.step()
+    dt = time.perf_counter() - t0
+    return {"value": round(n / dt, 2), "unit": "frames/s", "cores": rs.cores, "kind": rs.kind, "host_cores": os.cpu_count(),
+            "sample": f"{n} consecutive stereo frames of the same workload ({dt:.1f} s); pyramid+LK on {rs.cores} OpenCV threads, EKF on 1 thread "
+                      f"(reference builds Eigen with EIGEN_DONT_PARALLELIZE)"}
+
+
+def run_reference(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
+    inputs = Inputs(dev, seed=0)       # torch is only the synthetic-input generator here; the timed path is pure CPU
+    rs = RefSession(inputs)
+    for _ in range(max(3, args.warmup)):
+        rs.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rs.step()
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "stereo frames/sec (752x480, 150 tracks)", "value": round(v, 2), "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(dt / args.steps * 1e3, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16 fixed-point + f32 (pyramid, LK), f64 (EKF)", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2 (same step as the CUDA arm) on the host CPU; one session"},
+        "cpu_baseline": {"value": round(v, 2), "unit": "frames/s", "cores": rs.cores, "kind": rs.kind, "host_cores": os.cpu_count(),
+                         "sample": f"{args.steps} stereo frames"},
+        "e2e": {"value": round(v, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

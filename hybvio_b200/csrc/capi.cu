@@ -173,6 +173,8 @@ int hv_pyr_build_batch(hv_pyr* const* pyrs, const uint8_t* const* gray, const si
     if (!c) { hv_set_error("hv_pyr_build_batch: NULL pyramid"); return HV_ERR_INVALID; }
     HV_CUDA(cudaSetDevice(c->device));
     std::vector<unsigned short> idx(n);
+    std::vector<const uint8_t*> src(n);
+    std::vector<int> srcPitch(n);
     int maxNl = 0;
     for (int i = 0; i < n; i++) {
         hv_pyr* p = pyrs[i];
@@ -181,13 +183,16 @@ int hv_pyr_build_batch(hv_pyr* const* pyrs, const uint8_t* const* gray, const si
             return HV_ERR_INVALID;
         }
         const HvLevel& L0 = p->desc.lv[0];
-        // the frame lands directly in the level-0 buffer: level 0 of the pyramid IS the input image
-        HV_CUDA(cudaMemcpy2DAsync(L0.gray, L0.gpitch, gray[i], strides[i], (size_t)p->w, (size_t)p->h,
-                                  srcIsDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+        if (srcIsDevice) {      // frame already in HBM: the kernel reads it in place and fills level 0 itself
+            src[i] = gray[i]; srcPitch[i] = (int)strides[i];
+        } else {                // the frame lands directly in the level-0 buffer: level 0 of the pyramid IS the input image
+            HV_CUDA(cudaMemcpy2DAsync(L0.gray, L0.gpitch, gray[i], strides[i], (size_t)p->w, (size_t)p->h, cudaMemcpyHostToDevice, c->stream));
+            src[i] = nullptr; srcPitch[i] = 0;
+        }
         idx[i] = (unsigned short)p->slot;
         if (p->nlevels > maxNl) maxNl = p->nlevels;
     }
-    HV_CUDA(hv_launch_pyr_fused(c->d_table, idx.data(), n, pyrs[0]->w, pyrs[0]->h, maxNl, c->stream));
+    HV_CUDA(hv_launch_pyr_fused(c->d_table, idx.data(), src.data(), srcPitch.data(), n, pyrs[0]->w, pyrs[0]->h, maxNl, c->stream));
     c->launches += (n + 59) / 60;
     return HV_OK;
 }

@@ -42,5 +42,5 @@ struct hv_pyr {
 int hv_ctx_reserve_stage(hv_ctx* ctx, size_t bytes);
 
 // kernels (pyramid.cu, lk.cu)
-cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* idx, int n, int w0, int h0, int maxNlevels,
-                                cudaStream_t stream);
+cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* idx, const uint8_t* const* src, const int* srcPitch,
+                                int n, int w0, int h0, int maxNlevels, cudaStream_t stream);

@@ -21,10 +21,16 @@
 
 #define PYR_NT 256
 
+#define PYR_MAX_BATCH 60
 struct PyrBuildList {
     const HvPyrDesc* table;   // device-resident descriptors of all pyramids of the context
     int n;                    // images in this launch
-    unsigned short idx[60];   // descriptor index per blockIdx.z
+    unsigned short idx[PYR_MAX_BATCH];   // descriptor index per blockIdx.z
+    // Frame already in HBM (e.g. decoded on the device): read level 0 from src[z] (row pitch srcPitch[z] bytes)
+    // and let each CTA also write its own 64x64 tile into the level-0 buffer. NULL: the frame was copied (H2D)
+    // straight into the level-0 buffer, which is then read in place.
+    const uint8_t* src[PYR_MAX_BATCH];
+    int srcPitch[PYR_MAX_BATCH];
 };
 
 struct Span { int o0, o1;   // owned output range [o0, o1) at this level
@@ -125,6 +131,7 @@ __global__ void __launch_bounds__(PYR_NT) hv_pyr_fused_kernel(PyrBuildList list)
     }
 
     // ---- stage the level-0 region with 32-bit loads (gpitch is a multiple of 128, rows are 4-byte aligned)
+    const uint8_t* ext = list.src[blockIdx.z];
     {
         const HvLevel& L0 = P.lv[0];
         const int x0a = sx[0].s0 & ~3;
@@ -132,15 +139,26 @@ __global__ void __launch_bounds__(PYR_NT) hv_pyr_fused_kernel(PyrBuildList list)
         uint8_t* b0 = smem + bufOff[0];
         const int bp = bufPitch[0];
         const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-        for (int r = wrp; r < rows; r += PYR_NT / 32) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(L0.gray + (size_t)(sy[0].s0 + r) * L0.gpitch + x0a);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(b0 + r * bp);
-            for (int c = lane; c < words; c += 32) dst[c] = __ldg(src + c);
+        const bool aligned = ext == nullptr || ((((size_t)ext) | (size_t)list.srcPitch[blockIdx.z]) & 3) == 0;
+        const uint8_t* base = ext ? ext : L0.gray;
+        const int pitch = ext ? list.srcPitch[blockIdx.z] : L0.gpitch;
+        if (aligned && (ext == nullptr || x0a + words * 4 <= pitch)) {
+            for (int r = wrp; r < rows; r += PYR_NT / 32) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(base + (size_t)(sy[0].s0 + r) * pitch + x0a);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(b0 + r * bp);
+                for (int c = lane; c < words; c += 32) dst[c] = __ldg(src + c);
+            }
+        } else {   // arbitrary external pitch / alignment: byte loads, never past the last image column
+            const int nbytes = min(words * 4, L0.w - x0a);
+            for (int r = wrp; r < rows; r += PYR_NT / 32) {
+                const uint8_t* src = base + (size_t)(sy[0].s0 + r) * pitch + x0a;
+                for (int c = lane; c < nbytes; c += 32) b0[r * bp + c] = __ldg(src + c);
+            }
         }
         sx[0].s0 = x0a;   // stored origin is the aligned one
     }
     __syncthreads();
-    emit_level(P.lv[0], smem + bufOff[0], bufPitch[0], sx[0].s0, sy[0].s0, sx[0], sy[0], false, 4);
+    emit_level(P.lv[0], smem + bufOff[0], bufPitch[0], sx[0].s0, sy[0].s0, sx[0], sy[0], ext != nullptr, 4);
 
     // ---- coarser levels: 5x5 [1 4 6 4 1]^2, (sum+128)>>8, reflect-101 inside the finer level
     for (int k = 1; k < nl; k++) {
@@ -182,8 +200,8 @@ size_t hv_pyr_smem_bytes(int nlevels)
     return off;
 }
 
-cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* idx, int n, int w0, int h0, int maxNlevels,
-                                cudaStream_t stream)
+cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* idx, const uint8_t* const* src, const int* srcPitch,
+                                int n, int w0, int h0, int maxNlevels, cudaStream_t stream)
 {
     static bool attrSet = false;
     size_t smem = hv_pyr_smem_bytes(maxNlevels);
@@ -192,10 +210,14 @@ cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* id
         if (e != cudaSuccess) return e;
         attrSet = true;
     }
-    for (int base = 0; base < n; base += 60) {
+    for (int base = 0; base < n; base += PYR_MAX_BATCH) {
         PyrBuildList list;
-        list.table = table; list.n = min(60, n - base);
-        for (int i = 0; i < list.n; i++) list.idx[i] = idx[base + i];
+        list.table = table; list.n = min(PYR_MAX_BATCH, n - base);
+        for (int i = 0; i < list.n; i++) {
+            list.idx[i] = idx[base + i];
+            list.src[i] = src ? src[base + i] : nullptr;
+            list.srcPitch[i] = src ? srcPitch[base + i] : 0;
+        }
         dim3 grid((w0 + HV_PYR_TILE - 1) / HV_PYR_TILE, (h0 + HV_PYR_TILE - 1) / HV_PYR_TILE, list.n);
         hv_pyr_fused_kernel<<<grid, PYR_NT, smem, stream>>>(list);
     }

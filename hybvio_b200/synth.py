@@ -82,3 +82,39 @@ def interior_points(n, width=752, height=480, seed=7, margin=40.0):
     pts[:, 0] = rng.uniform(margin, width - margin, n)
     pts[:, 1] = rng.uniform(margin, height - margin, n)
     return pts.astype(np.float32)
+
+
+def stereo_frames_torch(k0, count, width=752, height=480, seed=42, device="cpu"):
+    """Frames k0 .. k0+count-1 as a (count, 2, H, W) uint8 torch tensor, same formulas as stereo_frame() evaluated with
+    torch float64/int64 ops (bench.py uses it to fill its frame pool quickly on the GPU; tests use the numpy version;
+    the two agree except possibly at exact rounding ties)."""
+    import torch
+    dev = torch.device(device)
+    y, x = torch.meshgrid(torch.arange(height, dtype=torch.float64, device=dev), torch.arange(width, dtype=torch.float64, device=dev), indexing="ij")
+
+    def hash01(ix, iy, s):
+        h = (ix * 374761393 + iy * 668265263 + s * 2246822519) & 0xFFFFFFFF
+        h = ((h ^ (h >> 13)) * 1274126177) & 0xFFFFFFFF
+        h = (h ^ (h >> 16)) & 0xFFFFFFFF
+        return h.to(torch.float64) / 4294967296.0
+
+    def tex(u, v):
+        out = torch.full_like(u, 128.0)
+        for o, (cell, amp) in enumerate(zip(CELLS, AMPS)):
+            xs, ys = u / cell, v / cell
+            x0, y0 = torch.floor(xs), torch.floor(ys)
+            fx, fy = xs - x0, ys - y0
+            ix, iy = x0.to(torch.int64), y0.to(torch.int64)
+            s = seed + 101 * o
+            n = (hash01(ix, iy, s) * (1 - fx) + hash01(ix + 1, iy, s) * fx) * (1 - fy) + \
+                (hash01(ix, iy + 1, s) * (1 - fx) + hash01(ix + 1, iy + 1, s) * fx) * fy
+            out = out + amp * (2.0 * n - 1.0) * 0.5
+        return out
+
+    frames = torch.empty((count, 2, height, width), dtype=torch.uint8, device=dev)
+    xr = x - 12.0 - 4.0 * torch.sin(0.002 * (x + y))
+    for i in range(count):
+        cx, cy = camera_offset(k0 + i)
+        frames[i, 0] = torch.clamp(torch.floor(tex(x + cx, y + cy) + 0.5), 0, 255).to(torch.uint8)
+        frames[i, 1] = torch.clamp(torch.floor(tex(xr + cx, y + cy) + 0.5), 0, 255).to(torch.uint8)
+    return frames
