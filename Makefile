@@ -1,7 +1,7 @@
 # Builds hybvio_b200/libhybvio_b200.so (sm_100a only) and the test oracles.
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v $(if $(TIMING),-DHV_EKF_TIMING,)
 CSRC := hybvio_b200/csrc
 OBJ := build/obj
 LIB := hybvio_b200/libhybvio_b200.so

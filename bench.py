@@ -122,6 +122,26 @@ class Session:
             self.d_ts = torch.zeros(NFEAT, dtype=torch.int32, device=self.dev)
             self.d_ekf_pool = torch.from_numpy(inputs.ekf_pool).to(self.dev)
             self.d_res = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        # per-frame EKF op lists (hv_ekf_run_*: one crossing of the language boundary per frame)
+        self.ops_dev, self.ops_host = [], []
+        nops = PREDICTS + CHECKS + 2
+        for fr in range(POOL_EKF):
+            od, oh = (capi.EkfOp * nops)(), (capi.EkfOp * nops)()
+            for ops, base in ((od, self.d_ekf_pool[fr].data_ptr()), (oh, inputs.ekf_pool[fr].ctypes.data)):
+                for s_ in range(PREDICTS):
+                    u = inputs.imu[fr * PREDICTS + s_]
+                    ops[s_].kind = capi.OP_PREDICT
+                    for q in range(3):
+                        ops[s_].gyro[q] = u[q]; ops[s_].acc[q] = u[3 + q]
+                for c, (o, n, l) in enumerate(inputs.ekf_off):
+                    op = ops[PREDICTS + c]
+                    op.kind, op.n, op.l, op.mode, op.r, op.rmse_thr = capi.OP_VISUAL, n, l, (2 if c < UPDATES else 0), VISUAL_R, -1.0
+                    op.H, op.f, op.y = base + 8 * o, base + 8 * (o + n * l), base + 8 * (o + n * l + n)
+                ops[PREDICTS + CHECKS].kind = capi.OP_SYMMETRIZE
+                ops[PREDICTS + CHECKS + 1].kind = capi.OP_AUGMENT
+                ops[PREDICTS + CHECKS + 1].index = -1
+            self.ops_dev.append(od); self.ops_host.append(oh)
+        self.nops = nops
         self.h_frames = inputs.frames.cpu().pin_memory()
         self.h_pose = torch.zeros(self.ekf.N, dtype=torch.float64).pin_memory()
         self.t = 0.0
@@ -147,16 +167,11 @@ class Session:
         ctx.lk_track_device(self.pyr[0], cur[0], self.d_points, self.d_next, self.d_status, self.d_ts, NFEAT, True)
         ctx.lk_track_device(cur[0], cur[1], self.d_next, self.d_next2, self.d_status, self.d_ts, NFEAT, False)
         fr = self._ekf_inputs(self.k)
+        ops = self.ops_dev[fr]
         for s in range(PREDICTS):
             self.t += 0.005
-            u = inp.imu[fr * PREDICTS + s]
-            self.ekf.predict(self.t, u[:3], u[3:])
-        base = self.d_ekf_pool[fr]
-        for c, (o, n, l) in enumerate(inp.ekf_off):
-            self.ekf.visual_device(base[o:], n, l, base[o + n * l:], base[o + n * l + n:], VISUAL_R, -1.0,
-                                   2 if c < UPDATES else 0, None)
-        self.ekf.symmetrize()
-        self.ekf.augment(-1)
+            ops[s].t = self.t
+        self.ekf.run_device(ops, self.nops)
         self.pyr = self.pyr[2:4] + self.pyr[0:2]
         self.prev_j = j
 
@@ -171,27 +186,18 @@ class Session:
         nxt, st, ts = ctx.lk_track(self.pyr[0], cur[0], inp.points, init)                           # H2D + D2H + sync
         nxt2, st2, ts2 = ctx.lk_track(cur[0], cur[1], nxt)
         fr = self._ekf_inputs(self.k)
+        ops = self.ops_host[fr]
         for s in range(PREDICTS):
             self.t += 0.005
-            u = inp.imu[fr * PREDICTS + s]
-            self.ekf.predict(self.t, u[:3], u[3:])
-        row = inp.ekf_pool[fr]
-        for c, (o, n, l) in enumerate(inp.ekf_off):
-            Hm = row[o:o + n * l].reshape((n, l), order="F")
-            f, y = row[o + n * l:o + n * l + n], row[o + n * l + n:o + n * l + 2 * n]
-            if c < UPDATES:
-                self.ekf.visual_check_update(Hm, f, y, VISUAL_R)                                     # one round trip
-            else:
-                self.ekf.visual_check(Hm, f, y, VISUAL_R)
-        self.ekf.symmetrize()
-        self.ekf.augment(-1)
-        m = self.ekf.download_inertial()[0]                                                          # pose read-back
+            ops[s].t = self.t
+        # 20 synchronous round trips (every check returns its VuOutlierStatus to the host) + state read-back
+        st, chi2, m = self.ekf.run_host(ops, self.nops, want_m=True)
         self.pyr = self.pyr[2:4] + self.pyr[0:2]
         self.prev_j = j
         return m
 
     H2D_BYTES = 2 * W * H + 2 * NFEAT * 16 + sum(8 * (n * l + 2 * n) for n, l in (ekf_rows(c) for c in range(CHECKS)))
-    D2H_BYTES = 2 * NFEAT * 13 + CHECKS * 24 + UPDATES * 8 * (20 + 7 * TRAIL) + 20 * 8 + 400 * 8
+    D2H_BYTES = 2 * NFEAT * 13 + CHECKS * 24 + 8 * (20 + 7 * TRAIL)
 
 
 class ClockSampler:

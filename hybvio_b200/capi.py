@@ -34,6 +34,15 @@ class EkfParams(ctypes.Structure):
     ]
 
 
+class EkfOp(ctypes.Structure):
+    _fields_ = [("kind", c_int), ("n", c_int), ("l", c_int), ("mode", c_int), ("index", c_int),
+                ("t", c_double), ("r", c_double), ("rmse_thr", c_double), ("gyro", c_double * 3), ("acc", c_double * 3),
+                ("H", c_void_p), ("f", c_void_p), ("y", c_void_p)]
+
+
+OP_PREDICT, OP_VISUAL, OP_SYMMETRIZE, OP_AUGMENT, OP_UNAUGMENT, OP_NORMALIZE = range(6)
+
+
 class LkJob(ctypes.Structure):
     _fields_ = [("prev", c_void_p), ("next", c_void_p), ("d_prev_xy", c_void_p), ("d_next_xy", c_void_p),
                 ("d_status", c_void_p), ("d_track_status", c_void_p), ("n", c_int), ("use_initial", c_int)]
@@ -114,6 +123,8 @@ def _bind_ekf(lib):
                                                ctypes.POINTER(c_int), dp, c_void_p]
     lib.hv_ekf_visual_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p]
     lib.hv_ekf_augment.argtypes = [c_void_p, c_int]
+    lib.hv_ekf_run_device.argtypes = [c_void_p, ctypes.POINTER(EkfOp), c_int]
+    lib.hv_ekf_run_host.argtypes = [c_void_p, ctypes.POINTER(EkfOp), c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double), c_void_p]
     lib.hv_ekf_normalize_quaternions.argtypes = [c_void_p, c_int]
     lib.hv_ekf_translate_to.argtypes = [c_void_p, c_void_p]
     lib.hv_ekf_transform_to.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
@@ -338,6 +349,18 @@ class Ekf:
     def visual_device(self, d_H, n, l, d_f, d_y, r, rmse_thr, mode, d_result=None):
         check(self.lib.hv_ekf_visual_device(self.h, _ptr(d_H), n, l, _ptr(d_f), _ptr(d_y), r, rmse_thr, mode, _ptr(d_result)),
               "hv_ekf_visual_device")
+
+    def run_device(self, ops, nops):
+        """ops: (EkfOp * k) array with DEVICE pointers; asynchronous."""
+        check(self.lib.hv_ekf_run_device(self.h, ops, nops), "hv_ekf_run_device")
+
+    def run_host(self, ops, nops, want_m=False):
+        """ops with HOST pointers; returns (vu_status int32[nops], chi2 float64[nops], m or None)."""
+        st = (c_int * nops)(*([-1] * nops))
+        chi2 = (c_double * nops)()
+        m = np.zeros(self.N) if want_m else None
+        check(self.lib.hv_ekf_run_host(self.h, ops, nops, st, chi2, _ptr(m)), "hv_ekf_run_host")
+        return np.frombuffer(st, dtype=np.int32).copy(), np.frombuffer(chi2, dtype=np.float64).copy(), m
 
     def augment(self, drop=-1): check(self.lib.hv_ekf_augment(self.h, drop), "hv_ekf_augment")
     def unaugment(self): check(self.lib.hv_ekf_unaugment(self.h), "hv_ekf_unaugment")

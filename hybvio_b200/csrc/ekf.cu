@@ -23,6 +23,7 @@
 // fp64 differences to the reference are rounding-order only (tests: relative 1e-9 on P, 1e-10 on m).
 #include "ekf.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ void normalize_quat(double* q)
@@ -40,8 +41,8 @@ __device__ __forceinline__ void normalize_all(double* m, int trail, bool onlyCur
 
 __device__ __forceinline__ void symmetrize(double* P, int N)
 {
-    // P = 0.5 (P + P')  (ekf.cpp:1065)
-    for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+    // P = 0.5 (P + P')  (ekf.cpp:1065); grid-stride: every (i > j) pair is owned by exactly one thread
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * N; idx += gridDim.x * blockDim.x) {
         const int i = idx % N, j = idx / N;
         if (i > j) {
             const double s = 0.5 * (P[i + (size_t)j * N] + P[j + (size_t)i * N]);
@@ -70,11 +71,12 @@ __device__ __forceinline__ int unaug_src(int i, int poseTrailDim)
 template <class SrcFn>
 __device__ __forceinline__ void shift_state(const double* __restrict__ P, double* __restrict__ P2, double* m, int N, SrcFn src)
 {
-    for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * N; idx += gridDim.x * blockDim.x) {
         const int i = idx % N, j = idx / N;
         const int si = src(i), sj = src(j);
         P2[idx] = (si < 0 || sj < 0) ? 0.0 : P[si + (size_t)sj * N];
     }
+    if (blockIdx.x != 0) return;   // the state vector is shifted by block 0
     double tmp[4];   // N <= 4 * EKF_NT
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -368,6 +370,12 @@ __global__ void __launch_bounds__(EKF_NT) ekf_predict_kernel(EkfPredictArgs a)
     }
     __syncthreads();
     if (tid == 0) {
+        // the serial part works on a register copy of the 20 inertial states: 20 independent loads in flight
+        // instead of one dependent L2 round trip per use
+        double mm[EKF_INER];
+#pragma unroll
+        for (int i = 0; i < EKF_INER; i++) mm[i] = a.b.m[i];
+        double* m = mm;
         const double dt = a.dt;
         // gyro rotation: A = exp(S), S = -dt/2 * Omega(w) (ekf.cpp:414-425). Omega^2 = -|w|^2 I, so
         // exp(S) = cos(th) I + sin(th)/th S with th = |w| dt / 2 (closed form of the reference's Pade S.exp()).
@@ -423,6 +431,8 @@ __global__ void __launch_bounds__(EKF_NT) ekf_predict_kernel(EkfPredictArgs a)
         for (int i = 0; i < 4; i++) for (int j = 0; j < 3; j++) DX(EKF_ORI + i, EKF_BGA + j) = -DQ(EKF_ORI + i, EKF_Q_GYRO + j);
         for (int i = 0; i < 3; i++)
             for (int j = 0; j < 3; j++) { DX(EKF_VEL + i, EKF_BAA + j) = -R[j * 3 + i] * dt; DX(EKF_VEL + i, EKF_BAT + j) = R[j * 3 + i] * a.xa[j] * dt; }
+#pragma unroll
+        for (int i = 0; i < EKF_INER; i++) a.b.m[i] = mm[i];
     }
     __syncthreads();
     for (int i = tid; i < 400; i += EKF_NT) a.b.dydx[i] = s_dydx[i];
@@ -658,6 +668,11 @@ static size_t ekf_augment_smem_bytes(int N)
 
 cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s)
 {
+    // 8-CTA cluster kernel whenever its shared-memory working set fits (n <= 84 at N = 160); the single-CTA kernel
+    // below remains for oversized batch updates (n up to N) and as an A/B switch (HV_EKF_SINGLE_CTA=1).
+    static const bool forceSingle = getenv("HV_EKF_SINGLE_CTA") != nullptr;
+    if (!forceSingle && !a.useGlobalWork && ekf_cluster_smem_bytes(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT) <= 216 * 1024)
+        return ekf_launch_update_cluster(a, s);
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(ekf_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -676,6 +691,11 @@ cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s)
 cudaError_t ekf_launch_elementwise(const EkfEwArgs& a, cudaStream_t s)
 {
     if (a.op == EKF_EW_CONDITION_LAST_POSE || a.op == EKF_EW_TRANSFORM) ekf_ew_heavy_kernel<<<1, EKF_NT, 0, s>>>(a);
-    else ekf_ew_kernel<<<1, EKF_NT, 0, s>>>(a);
+    else {
+        // purely elementwise N x N passes are spread over several SMs (they are L2-latency bound on one)
+        int grid = 1;
+        if (a.op == EKF_EW_SYMMETRIZE || a.op == EKF_EW_UNAUGMENT) { grid = (a.b.N * a.b.N + 4 * EKF_NT - 1) / (4 * EKF_NT); if (grid > 32) grid = 32; }
+        ekf_ew_kernel<<<grid, EKF_NT, 0, s>>>(a);
+    }
     return cudaGetLastError();
 }

@@ -30,6 +30,7 @@ struct EkfBufs {
     double* P;        // N x N   (current)
     double* P2;       // N x N   (target of out-of-place shifts/transforms; host swaps after the launch)
     double* work;     // global fallback for the elimination tableau when it does not fit shared memory
+    double* cwork;    // cluster kernel exchange buffers through L2: 8 partial S | reduced S | gathered Z  (10 x N x N)
     double* Hs;       // EKF_SMALL_MAXN x EKF_SMALL_MAXL built-in measurement matrix
     double* Q;        // 12 x 12 process noise
     double* dydx;     // 20 x 20 last predict Jacobian (getDydx)
@@ -104,5 +105,7 @@ struct EkfEwArgs {
 
 size_t ekf_update_smem_bytes(int n, int N);
 cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s);
+size_t ekf_cluster_smem_bytes(int n, int l, int N, bool joseph);
+cudaError_t ekf_launch_update_cluster(const EkfUpdateArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_elementwise(const EkfEwArgs& a, cudaStream_t s);

@@ -123,14 +123,15 @@ static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
     e->noiseScale = prm->noise_scale * prm->noise_scale;
     const size_t N = e->N, NN = N * N;
     const size_t workD = N * (2 * N + 4);
+    const size_t cworkD = 10 * NN;
     e->inDoubles = NN + 2 * N;
-    const size_t total = N + NN + NN + workD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + 8 + e->inDoubles;
+    const size_t total = N + NN + NN + workD + cworkD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + 32 + e->inDoubles;
     cudaError_t err = cudaMalloc(&e->d_block, total * sizeof(double));
     if (err != cudaSuccess) { delete e; hv_set_error("hv_ekf_create: cudaMalloc failed: %s", cudaGetErrorString(err)); return HV_ERR_OOM; }
     cudaMemsetAsync(e->d_block, 0, total * sizeof(double), c->stream);
     double* p = e->d_block;
-    e->b.m = p; p += N; e->b.P = p; p += NN; e->b.P2 = p; p += NN; e->b.work = p; p += workD;
-    e->b.Hs = p; p += EKF_SMALL_MAXN * EKF_SMALL_MAXL; e->b.Q = p; p += 144; e->b.dydx = p; p += 400; e->b.res = p; p += 8;
+    e->b.m = p; p += N; e->b.P = p; p += NN; e->b.P2 = p; p += NN; e->b.work = p; p += workD; e->b.cwork = p; p += cworkD;
+    e->b.Hs = p; p += EKF_SMALL_MAXN * EKF_SMALL_MAXL; e->b.Q = p; p += 144; e->b.dydx = p; p += 400; e->b.res = p; p += 32;
     e->d_in = p;
     e->b.N = e->N; e->b.trail = e->trail; e->b.mapDim = e->mapDim;
     err = cudaMallocHost(&e->h_pin, (e->inDoubles + N + 8) * sizeof(double));
@@ -538,6 +539,52 @@ int hv_ekf_condition_on_last_pose(hv_ekf* e)
     EKF_ENTER(e, "hv_ekf_condition_on_last_pose");
     if (e->mapDim != 0 || e->augmentCount <= 0) { hv_set_error("hv_ekf_condition_on_last_pose: needs no hybrid map and >= 1 augmented pose"); return HV_ERR_STATE; }
     return launch_ew(e, EKF_EW_CONDITION_LAST_POSE);
+}
+
+static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vuStatus, double* chi2, double* mOut)
+{
+    if (!ops || nops < 0) { hv_set_error("hv_ekf_run: invalid argument"); return HV_ERR_INVALID; }
+    for (int i = 0; i < nops; i++) {
+        const hv_ekf_op& o = ops[i];
+        int rc = HV_OK;
+        switch (o.kind) {
+            case HV_EKF_OP_PREDICT: rc = hv_ekf_predict(e, o.t, o.gyro, o.acc); break;
+            case HV_EKF_OP_VISUAL:
+                if (o.mode < 0 || o.mode > 2) { hv_set_error("hv_ekf_run: op %d: bad mode", i); return HV_ERR_INVALID; }
+                if (host) rc = visual_host(e, "hv_ekf_run_host", o.H, o.n, o.l, o.f, o.y, o.r, o.rmse_thr, o.mode,
+                                           vuStatus ? vuStatus + i : nullptr, chi2 ? chi2 + i : nullptr, nullptr);
+                else rc = hv_ekf_visual_device(e, o.H, o.n, o.l, o.f, o.y, o.r, o.rmse_thr, o.mode, nullptr);
+                break;
+            case HV_EKF_OP_SYMMETRIZE: rc = hv_ekf_symmetrize(e); break;
+            case HV_EKF_OP_AUGMENT: rc = hv_ekf_augment(e, o.index); break;
+            case HV_EKF_OP_UNAUGMENT: rc = hv_ekf_unaugment(e); break;
+            case HV_EKF_OP_NORMALIZE: rc = hv_ekf_normalize_quaternions(e, o.index); break;
+            default: hv_set_error("hv_ekf_run: op %d: unknown kind %d", i, o.kind); return HV_ERR_INVALID;
+        }
+        if (rc != HV_OK) return rc;
+    }
+    if (host && mOut) return hv_ekf_download(e, mOut, nullptr);
+    return HV_OK;
+}
+
+int hv_ekf_run_device(hv_ekf* e, const hv_ekf_op* ops, int nops)
+{
+    EKF_ENTER(e, "hv_ekf_run_device");
+    return run_ops(e, ops, nops, false, nullptr, nullptr, nullptr);
+}
+
+int hv_ekf_run_host(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vuStatus, double* chi2, double* mOut)
+{
+    EKF_ENTER(e, "hv_ekf_run_host");
+    return run_ops(e, ops, nops, true, vuStatus, chi2, mOut);
+}
+
+int hv_ekf_debug_result_words(hv_ekf* e, double* out32)
+{
+    EKF_ENTER(e, "hv_ekf_debug_result_words");
+    HV_CUDA(cudaMemcpyAsync(out32, e->b.res, 32 * sizeof(double), cudaMemcpyDeviceToHost, e->ctx->stream));
+    HV_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    return HV_OK;
 }
 
 int hv_ekf_lock_biases(hv_ekf* e) { EKF_ENTER(e, "hv_ekf_lock_biases"); return launch_ew(e, EKF_EW_LOCK_BIASES); }

@@ -179,6 +179,31 @@ int hv_ekf_visual_check_update(hv_ekf* ekf, const double* H, int n, int l, const
 int hv_ekf_visual_device(hv_ekf* ekf, const double* d_H, int n, int l, const double* d_f, const double* d_y,
                          double r, double track_rmse_threshold, int mode, double* d_result);
 
+/* Batch submission: executes `nops` EKF calls in order with ONE crossing of the language boundary (what
+ * Session::process issues per frame: the IMU predicts, the per-track checks/updates, symmetrise, augment;
+ * src/odometry/backend.cpp:716-867). Each op is exactly the single call of the same name. */
+typedef enum hv_ekf_op_kind {
+    HV_EKF_OP_PREDICT = 0,        /* t, gyro, acc */
+    HV_EKF_OP_VISUAL = 1,         /* H, n, l, f, y, r, rmse_thr, mode (0 check, 1 update, 2 check+update-if-inlier) */
+    HV_EKF_OP_SYMMETRIZE = 2,
+    HV_EKF_OP_AUGMENT = 3,        /* index = discarded pose */
+    HV_EKF_OP_UNAUGMENT = 4,
+    HV_EKF_OP_NORMALIZE = 5       /* index = only_current */
+} hv_ekf_op_kind;
+typedef struct hv_ekf_op {
+    int kind;
+    int n, l, mode, index;
+    double t, r, rmse_thr;
+    double gyro[3], acc[3];
+    const double* H; const double* f; const double* y;
+} hv_ekf_op;
+/* H/f/y are DEVICE pointers; fully asynchronous. */
+int hv_ekf_run_device(hv_ekf* ekf, const hv_ekf_op* ops, int nops);
+/* H/f/y are HOST pointers; every VISUAL op with mode 0 or 2 returns its VuOutlierStatus / chi2 into
+ * vu_status[i] / chi2[i] (arrays of length nops, entries of other ops untouched) -- i.e. each such op is a host
+ * round trip, as in the reference interface. m_out (optional, N doubles) receives the final state mean. */
+int hv_ekf_run_host(hv_ekf* ekf, const hv_ekf_op* ops, int nops, int* vu_status, double* chi2, double* m_out);
+
 int hv_ekf_augment(hv_ekf* ekf, int discarded_pose_index);     /* updateVisualPoseAugmentation (ekf.cpp:848-885) */
 int hv_ekf_unaugment(hv_ekf* ekf);                             /* updateUndoAugmentation (ekf.cpp:888-903) */
 int hv_ekf_symmetrize(hv_ekf* ekf);                            /* maintainPositiveSemiDefinite (ekf.cpp:1059-1067) */
@@ -188,6 +213,9 @@ int hv_ekf_transform_to(hv_ekf* ekf, const double pos[3], const double q[4], int
 int hv_ekf_insert_map_point(hv_ekf* ekf, int idx, const double pf[3]);   /* ekf.cpp:911-921 */
 int hv_ekf_condition_on_last_pose(hv_ekf* ekf);                /* ekf.cpp:928-942 */
 int hv_ekf_lock_biases(hv_ekf* ekf);                           /* ekf.cpp:944-947 */
+/* Debug: the 32 result words of the last update kernel ([0] status, [1] chi2, [2] flag, [8..] phase timestamps when
+ * the library is built with -DHV_EKF_TIMING). */
+int hv_ekf_debug_result_words(hv_ekf* ekf, double* out32);
 
 #ifdef __cplusplus
 }
