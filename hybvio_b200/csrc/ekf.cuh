@@ -77,13 +77,30 @@ struct EkfUpdateArgs {
     int useGlobalWork;    // tableau in b.work instead of shared memory
 };
 
-struct EkfPredictArgs {
-    EkfBufs b;
+// Independent outlier checks against the same (m, P): one launch, one 8-CTA cluster per measurement
+#define EKF_MAX_BATCH 24
+#define EKF_RES_STRIDE 32
+struct EkfCheckItem {
+    const double* H; const double* f; const double* y;   // device
+    int n, l;
+    double Rdiag, chi2Thr, rmseThr;
+    int skipChi2, pad;
+};
+struct EkfCheckBatch { int count; int pad; EkfCheckItem it[EKF_MAX_BATCH]; };
+
+#define EKF_MAX_PREDICT 16
+struct EkfPredictSample {
     double dt;
     double xg[3], xa[3];
-    double gravity;                 // gravity vector = (0, 0, -gravity)
     double baaDecay, bgaDecay;      // exp(-dt * rev) or 1 when the random walk is off (ekf.cpp:443-448)
     double qBaa, qBga;              // >= 0: value of the Q drift-block diagonal for this dt (ekf.cpp:397-412); < 0: keep
+};
+// `count` consecutive IMU samples in one launch (the 10 samples between two frames at 200 Hz / 20 fps)
+struct EkfPredictArgs {
+    EkfBufs b;
+    double gravity;                 // gravity vector = (0, 0, -gravity)
+    int count;
+    EkfPredictSample s[EKF_MAX_PREDICT];
 };
 
 // elementwise / structural operations on (m, P)
@@ -107,5 +124,6 @@ size_t ekf_update_smem_bytes(int n, int N);
 cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s);
 size_t ekf_cluster_smem_bytes(int n, int l, int N, bool joseph);
 cudaError_t ekf_launch_update_cluster(const EkfUpdateArgs& a, cudaStream_t s);
+cudaError_t ekf_launch_check_batch(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s);
 cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_elementwise(const EkfEwArgs& a, cudaStream_t s);

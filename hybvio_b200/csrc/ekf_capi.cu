@@ -4,6 +4,7 @@
 #include "capi_internal.h"
 #include "ekf.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -123,18 +124,18 @@ static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
     e->noiseScale = prm->noise_scale * prm->noise_scale;
     const size_t N = e->N, NN = N * N;
     const size_t workD = N * (2 * N + 4);
-    const size_t cworkD = 10 * NN;
-    e->inDoubles = NN + 2 * N;
-    const size_t total = N + NN + NN + workD + cworkD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + 32 + e->inDoubles;
+    const size_t cworkD = (size_t)EKF_MAX_BATCH * 10 * NN;
+    e->inDoubles = (size_t)EKF_MAX_BATCH * (NN + 2 * N);
+    const size_t total = N + NN + NN + workD + cworkD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + EKF_RES_STRIDE * (EKF_MAX_BATCH + 1) + e->inDoubles;
     cudaError_t err = cudaMalloc(&e->d_block, total * sizeof(double));
     if (err != cudaSuccess) { delete e; hv_set_error("hv_ekf_create: cudaMalloc failed: %s", cudaGetErrorString(err)); return HV_ERR_OOM; }
     cudaMemsetAsync(e->d_block, 0, total * sizeof(double), c->stream);
     double* p = e->d_block;
     e->b.m = p; p += N; e->b.P = p; p += NN; e->b.P2 = p; p += NN; e->b.work = p; p += workD; e->b.cwork = p; p += cworkD;
-    e->b.Hs = p; p += EKF_SMALL_MAXN * EKF_SMALL_MAXL; e->b.Q = p; p += 144; e->b.dydx = p; p += 400; e->b.res = p; p += 32;
+    e->b.Hs = p; p += EKF_SMALL_MAXN * EKF_SMALL_MAXL; e->b.Q = p; p += 144; e->b.dydx = p; p += 400; e->b.res = p; p += EKF_RES_STRIDE * (EKF_MAX_BATCH + 1);
     e->d_in = p;
     e->b.N = e->N; e->b.trail = e->trail; e->b.mapDim = e->mapDim;
-    err = cudaMallocHost(&e->h_pin, (e->inDoubles + N + 8) * sizeof(double));
+    err = cudaMallocHost(&e->h_pin, (e->inDoubles + N + 8 + EKF_RES_STRIDE * EKF_MAX_BATCH) * sizeof(double));
     if (err != cudaSuccess) { cudaFree(e->d_block); delete e; hv_set_error("hv_ekf_create: cudaMallocHost failed"); return HV_ERR_OOM; }
     *out = e;
     return HV_OK;
@@ -313,33 +314,48 @@ int hv_ekf_initialize_orientation(hv_ekf* e, const double xa[3])
     return launch_ew(e, EKF_EW_INIT_ORIENTATION, 0, dv, 5);
 }
 
-int hv_ekf_predict(hv_ekf* e, double t, const double xg[3], const double xa[3])
+// Host bookkeeping of one predict() call (ekf.cpp:357-370); appends a device sample unless the call is a no-op.
+static void predict_bookkeep(hv_ekf* e, double t, const double xg[3], const double xa[3], EkfPredictArgs& a)
 {
-    EKF_ENTER(e, "hv_ekf_predict");
-    double dt = 0.0;                       // ekf.cpp:357-370
+    double dt = 0.0;
     if (!e->firstSample) { dt = t - e->prevSampleT; e->time = t - e->firstSampleT; }
     else { e->firstSampleT = t; e->firstSample = false; }
     e->prevSampleT = t;
-    if (dt <= 0.0) return HV_OK;
-    EkfPredictArgs a; memset(&a, 0, sizeof(a));
-    a.b = e->b; a.dt = dt; a.gravity = e->prm.gravity;
-    for (int i = 0; i < 3; i++) { a.xg[i] = xg[i]; a.xa[i] = xa[i]; }
-    a.qBaa = -1.0; a.qBga = -1.0; a.baaDecay = 1.0; a.bgaDecay = 1.0;
+    if (dt <= 0.0) return;
+    EkfPredictSample& s = a.s[a.count++];
+    s.dt = dt;
+    for (int i = 0; i < 3; i++) { s.xg[i] = xg[i]; s.xa[i] = xa[i]; }
+    s.qBaa = -1.0; s.qBga = -1.0; s.baaDecay = 1.0; s.bgaDecay = 1.0;
     if (e->prm.noise_process_baa > 0.0) {  // ekf.cpp:397-404, 443-445
         const double th = e->prm.noise_process_baa_rev;
-        a.qBaa = e->noiseScale * pow2(e->prm.noise_process_baa);
-        if (th > 0.0) a.qBaa *= (1 - std::exp(-2 * dt * th)) / (2 * th);
-        a.baaDecay = std::exp(-dt * th);
+        s.qBaa = e->noiseScale * pow2(e->prm.noise_process_baa);
+        if (th > 0.0) s.qBaa *= (1 - std::exp(-2 * dt * th)) / (2 * th);
+        s.baaDecay = std::exp(-dt * th);
     }
     if (e->prm.noise_process_bga > 0.0) {  // ekf.cpp:405-412, 446-448
         const double th = e->prm.noise_process_bga_rev;
-        a.qBga = e->noiseScale * pow2(e->prm.noise_process_bga);
-        if (th > 0.0) a.qBga *= (1 - std::exp(-2 * dt * th)) / (2 * th);
-        a.bgaDecay = std::exp(-dt * th);
+        s.qBga = e->noiseScale * pow2(e->prm.noise_process_bga);
+        if (th > 0.0) s.qBga *= (1 - std::exp(-2 * dt * th)) / (2 * th);
+        s.bgaDecay = std::exp(-dt * th);
     }
+}
+
+static int predict_launch(hv_ekf* e, EkfPredictArgs& a)
+{
+    if (a.count == 0) return HV_OK;
+    a.b = e->b; a.gravity = e->prm.gravity;
     HV_CUDA(ekf_launch_predict(a, e->ctx->stream));
     e->ctx->launches++;
+    a.count = 0;
     return HV_OK;
+}
+
+int hv_ekf_predict(hv_ekf* e, double t, const double xg[3], const double xa[3])
+{
+    EKF_ENTER(e, "hv_ekf_predict");
+    EkfPredictArgs a; a.count = 0;
+    predict_bookkeep(e, t, xg, xa, a);
+    return predict_launch(e, a);
 }
 
 int hv_ekf_update_zupt(hv_ekf* e, double r)
@@ -541,12 +557,84 @@ int hv_ekf_condition_on_last_pose(hv_ekf* e)
     return launch_ew(e, EKF_EW_CONDITION_LAST_POSE);
 }
 
+// A run of consecutive check-only VISUAL ops (mode 0) reads the same (m, P) and is therefore issued as ONE launch
+// (one cluster per measurement); with host buffers it is also one H2D copy, one D2H copy and one synchronisation.
+static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, bool host, int* vuStatus, double* chi2)
+{
+    if (count == 0) return HV_OK;
+    cudaStream_t s = e->ctx->stream;
+    EkfUpdateArgs a; EkfCheckBatch b;
+    memset(&b, 0, sizeof(b));
+    b.count = count;
+    size_t off = 0;
+    for (int i = 0; i < count; i++) {
+        const hv_ekf_op& o = ops[first + i];
+        EkfUpdateArgs tmp;
+        int rc = visual_args(e, "hv_ekf_run", o.n, o.l, o.r, o.rmse_thr, EKF_MODE_CHECK, tmp);
+        if (rc != HV_OK) return rc;
+        if (i == 0) a = tmp;
+        if (!o.H || !o.f || !o.y) { hv_set_error("hv_ekf_run: op %d: NULL input", first + i); return HV_ERR_INVALID; }
+        EkfCheckItem& it = b.it[i];
+        it.n = o.n; it.l = o.l; it.Rdiag = tmp.Rdiag; it.chi2Thr = tmp.chi2Thr; it.rmseThr = tmp.rmseThr; it.skipChi2 = tmp.skipChi2;
+        const size_t nl = (size_t)o.n * o.l;
+        if (host) {
+            double* hin = e->h_pin + off;
+            memcpy(hin, o.H, nl * sizeof(double)); memcpy(hin + nl, o.f, o.n * sizeof(double)); memcpy(hin + nl + o.n, o.y, o.n * sizeof(double));
+            it.H = e->d_in + off; it.f = e->d_in + off + nl; it.y = e->d_in + off + nl + o.n;
+            off += nl + 2 * (size_t)o.n;
+        } else { it.H = o.H; it.f = o.f; it.y = o.y; }
+    }
+    if (host) HV_CUDA(cudaMemcpyAsync(e->d_in, e->h_pin, off * sizeof(double), cudaMemcpyHostToDevice, s));
+    a.b = e->b; a.noiseScale = e->noiseScale; a.useGlobalWork = 0;
+    HV_CUDA(ekf_launch_check_batch(a, b, s));
+    e->ctx->launches++;
+    if (host) {
+        double* hout = e->h_pin + e->inDoubles + e->N + 8;
+        HV_CUDA(cudaMemcpyAsync(hout, e->b.res, sizeof(double) * EKF_RES_STRIDE * count, cudaMemcpyDeviceToHost, s));
+        HV_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < count; i++) {
+            if (vuStatus) vuStatus[first + i] = (int)hout[EKF_RES_STRIDE * i];
+            if (chi2) chi2[first + i] = hout[EKF_RES_STRIDE * i + 1];
+            if (hout[EKF_RES_STRIDE * i + 2] != 0.0) { hv_set_error("hv_ekf_run: op %d: innovation covariance not positive definite", first + i); return HV_ERR_STATE; }
+        }
+    }
+    return HV_OK;
+}
+
+static bool batchable_check(const hv_ekf* e, const hv_ekf_op& o)
+{
+    return o.kind == HV_EKF_OP_VISUAL && o.mode == 0 && o.n > 0 && o.l > 0 && o.l <= e->N && o.n <= e->N &&
+           ekf_cluster_smem_bytes(o.n, o.l, e->N, false) <= 216 * 1024;
+}
+
 static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vuStatus, double* chi2, double* mOut)
 {
     if (!ops || nops < 0) { hv_set_error("hv_ekf_run: invalid argument"); return HV_ERR_INVALID; }
+    static const bool noBatch = getenv("HV_EKF_NO_BATCH") != nullptr;
     for (int i = 0; i < nops; i++) {
         const hv_ekf_op& o = ops[i];
         int rc = HV_OK;
+        if (!noBatch && batchable_check(e, o)) {
+            int cnt = 1;
+            while (i + cnt < nops && cnt < EKF_MAX_BATCH && batchable_check(e, ops[i + cnt])) cnt++;
+            rc = flush_checks(e, ops, i, cnt, host, vuStatus, chi2);
+            if (rc != HV_OK) return rc;
+            i += cnt - 1;
+            continue;
+        }
+        if (!noBatch && o.kind == HV_EKF_OP_PREDICT) {
+            // consecutive IMU samples are one launch (see ekf_predict_kernel)
+            EkfPredictArgs pa; pa.count = 0;
+            int j = i;
+            for (; j < nops && ops[j].kind == HV_EKF_OP_PREDICT; j++) {
+                predict_bookkeep(e, ops[j].t, ops[j].gyro, ops[j].acc, pa);
+                if (pa.count == EKF_MAX_PREDICT) { rc = predict_launch(e, pa); if (rc != HV_OK) return rc; }
+            }
+            rc = predict_launch(e, pa);
+            if (rc != HV_OK) return rc;
+            i = j - 1;
+            continue;
+        }
         switch (o.kind) {
             case HV_EKF_OP_PREDICT: rc = hv_ekf_predict(e, o.t, o.gyro, o.acc); break;
             case HV_EKF_OP_VISUAL:

@@ -30,6 +30,18 @@ namespace cg = cooperative_groups;
 #define PHASE_MARK(i) do { } while (0)
 #endif
 
+// Block copy global -> shared with 8 independent loads in flight per thread (one L2 round trip moves 8 x 512 doubles)
+__device__ __forceinline__ void cta_copy8(double* __restrict__ dst, const double* __restrict__ src, int count, int tid)
+{
+    for (int base = 0; base < count; base += 8 * EKC_NT) {
+        double r[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int i = base + u * EKC_NT + tid; r[u] = i < count ? src[i] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int i = base + u * EKC_NT + tid; if (i < count) dst[i] = r[u]; }
+    }
+}
+
 __device__ __forceinline__ void ck_normalize_quat(double* q)
 {
     const double z = (q[0] * q[0] + q[2] * q[2]) + (q[1] * q[1] + q[3] * q[3]);
@@ -60,7 +72,7 @@ __host__ __device__ inline EkcGeom ekc_geom(int n, int l, int N, bool joseph)
     return g;
 }
 
-__global__ void __cluster_dims__(EKC, 1, 1) __launch_bounds__(EKC_NT) ekf_update_cluster_kernel(EkfUpdateArgs a)
+__device__ __forceinline__ void ekf_cluster_body(EkfUpdateArgs& a)
 {
     extern __shared__ double sm[];
     __shared__ double s_scalar[2];
@@ -111,8 +123,7 @@ __global__ void __cluster_dims__(EKC, 1, 1) __launch_bounds__(EKC_NT) ekf_update
     // ---- phase 1: measurement model into shared memory (ld = n)
     double hspeed = 0.0;
     if (a.op == EKF_OP_DENSE) {
-#pragma unroll 4
-        for (int i = tid; i < n * l; i += EKC_NT) X[i] = a.H[i];
+        cta_copy8(X, a.H, n * l, tid);
     } else {
         for (int i = tid; i < n * l; i += EKC_NT) X[i] = 0.0;
         if (a.op == EKF_OP_PSEUDO_VELOCITY) {
@@ -136,9 +147,13 @@ __global__ void __cluster_dims__(EKC, 1, 1) __launch_bounds__(EKC_NT) ekf_update
         }
     }
     // stage P[0:l, J_c] (columns are contiguous in memory)
-    for (int idx = tid; idx < l * Bc; idx += EKC_NT) {
-        const int k = idx % l, jj = idx / l;
-        PC[idx] = P[k + (size_t)(J0 + jj) * N];
+    if (l == N) cta_copy8(PC, P + (size_t)J0 * N, l * Bc, tid);      // whole columns: one contiguous block
+    else {
+#pragma unroll 4
+        for (int idx = tid; idx < l * Bc; idx += EKC_NT) {
+            const int k = idx % l, jj = idx / l;
+            PC[idx] = P[k + (size_t)(J0 + jj) * N];
+        }
     }
     __syncthreads();
     const double* Hs = X;
@@ -180,12 +195,18 @@ __global__ void __cluster_dims__(EKC, 1, 1) __launch_bounds__(EKC_NT) ekf_update
             const int j0 = tj, j1 = min(tj + tn, Bc - 1);
             const double* p0 = PC + (size_t)j0 * l;
             const double* p1 = PC + (size_t)j1 * l;
-            double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-#pragma unroll 4
-            for (int k = 0; k < l; k++) {
+            // 2 x 2 tile, even / odd k in separate accumulators: 8 independent fp64 chains per thread
+            double c00 = 0, c01 = 0, c10 = 0, c11 = 0, e00 = 0, e01 = 0, e10 = 0, e11 = 0;
+            int k = 0;
+#pragma unroll 2
+            for (; k + 1 < l; k += 2) {
                 const double h0 = Hs[i0 + (size_t)k * n], h1 = Hs[i1 + (size_t)k * n], b0 = p0[k], b1 = p1[k];
+                const double g0 = Hs[i0 + (size_t)(k + 1) * n], g1 = Hs[i1 + (size_t)(k + 1) * n], d0 = p0[k + 1], d1 = p1[k + 1];
                 c00 += h0 * b0; c01 += h0 * b1; c10 += h1 * b0; c11 += h1 * b1;
+                e00 += g0 * d0; e01 += g0 * d1; e10 += g1 * d0; e11 += g1 * d1;
             }
+            if (k < l) { const double h0 = Hs[i0 + (size_t)k * n], h1 = Hs[i1 + (size_t)k * n], b0 = p0[k], b1 = p1[k]; c00 += h0 * b0; c01 += h0 * b1; c10 += h1 * b0; c11 += h1 * b1; }
+            c00 += e00; c01 += e01; c10 += e10; c11 += e11;
             T[(size_t)i0 * W + n + j0] = c00;
             if (tj + tn < Bc) T[(size_t)i0 * W + n + j1] = c01;
             if (ti + tm < n) { T[(size_t)i1 * W + n + j0] = c10; if (tj + tn < Bc) T[(size_t)i1 * W + n + j1] = c11; }
@@ -197,12 +218,18 @@ __global__ void __cluster_dims__(EKC, 1, 1) __launch_bounds__(EKC_NT) ekf_update
     {
         const int kc = max(0, min(Bc, l - J0));
         double* mine = Spart + (size_t)c * n * n;
-        for (int t = tid; t < n * n; t += EKC_NT) {
-            const int ip = t % n, i = t / n;
-            const double* hp = T + (size_t)i * W + n;
-            double s = 0.0;
-            for (int k = 0; k < kc; k++) s += hp[k] * Hs[ip + (size_t)(J0 + k) * n];
-            mine[t] = s;
+        // 4 outputs per thread in flight (each is a kc-term dependent chain)
+        for (int t0 = tid; t0 < n * n; t0 += 4 * EKC_NT) {
+            double acc[4] = {0, 0, 0, 0};
+            const double* hp[4]; const double* hh[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int t = min(t0 + u * EKC_NT, n * n - 1); hp[u] = T + (size_t)(t / n) * W + n; hh[u] = Hs + (t % n) + (size_t)J0 * n; }
+            for (int k = 0; k < kc; k++) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) acc[u] += hp[u][k] * hh[u][(size_t)k * n];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int t = t0 + u * EKC_NT; if (t < n * n) mine[t] = acc[u]; }
         }
     }
     PHASE_MARK(4);
@@ -219,6 +246,7 @@ __global__ void __cluster_dims__(EKC, 1, 1) __launch_bounds__(EKC_NT) ekf_update
         }
     }
     cluster.sync();
+#pragma unroll 4
     for (int t = tid; t < n * n; t += EKC_NT) T[(size_t)(t / n) * W + (t % n)] = Sg[t];
     __syncthreads();
 
@@ -300,8 +328,7 @@ __global__ void __cluster_dims__(EKC, 1, 1) __launch_bounds__(EKC_NT) ekf_update
     }
     cluster.sync();
     double* Z = X;                                   // n x N row-major (H is dead)
-#pragma unroll 4
-    for (int t = tid; t < n * N; t += EKC_NT) Z[t] = Zg[t];
+    cta_copy8(Z, Zg, n * N, tid);
     __syncthreads();
     {
         const int ti_n = (N + 3) >> 2, tj_n = (Bc + 1) >> 1;
@@ -388,6 +415,24 @@ __global__ void __cluster_dims__(EKC, 1, 1) __launch_bounds__(EKC_NT) ekf_update
     }
 }
 
+__global__ void __cluster_dims__(EKC, 1, 1) __launch_bounds__(EKC_NT) ekf_update_cluster_kernel(EkfUpdateArgs a)
+{
+    ekf_cluster_body(a);
+}
+
+// Batched outlier checks: cluster i works on measurement i against the same state (read-only), with its own
+// exchange buffers and result words. This is what makes the 15-20 candidate tracks of a frame one launch.
+__global__ void __cluster_dims__(EKC, 1, 1) __launch_bounds__(EKC_NT) ekf_check_batch_cluster_kernel(EkfUpdateArgs a, EkfCheckBatch b)
+{
+    const int inst = blockIdx.x / EKC;
+    const EkfCheckItem& it = b.it[inst];
+    a.H = it.H; a.f = it.f; a.y = it.y; a.n = it.n; a.l = it.l;
+    a.Rdiag = it.Rdiag; a.chi2Thr = it.chi2Thr; a.rmseThr = it.rmseThr; a.skipChi2 = it.skipChi2;
+    a.b.res += (size_t)EKF_RES_STRIDE * inst;
+    a.b.cwork += (size_t)inst * 10 * a.b.N * a.b.N;
+    ekf_cluster_body(a);
+}
+
 size_t ekf_cluster_smem_bytes(int n, int l, int N, bool joseph)
 {
     const EkcGeom g = ekc_geom(n, l, N, joseph);
@@ -404,5 +449,19 @@ cudaError_t ekf_launch_update_cluster(const EkfUpdateArgs& a, cudaStream_t s)
     }
     const size_t smem = ekf_cluster_smem_bytes(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT);
     ekf_update_cluster_kernel<<<EKC, EKC_NT, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t ekf_launch_check_batch(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s)
+{
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(ekf_check_batch_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    size_t smem = 0;
+    for (int i = 0; i < b.count; i++) { const size_t v = ekf_cluster_smem_bytes(b.it[i].n, b.it[i].l, a.b.N, false); if (v > smem) smem = v; }
+    ekf_check_batch_cluster_kernel<<<EKC * b.count, EKC_NT, smem, s>>>(a, b);
     return cudaGetLastError();
 }

@@ -114,3 +114,70 @@ def test_bookkeeping_and_error_codes(cuda):
     assert e.visual_check(H, np.zeros(8), np.ones(8) * 100, -1.0)[0] == 0
     assert e.visual_check(H, np.zeros(8), np.ones(8) * 100, 0.05, rmse_thr=1.0)[0] == 2
     e.close()
+
+
+def _frame_ops(capi, rng, irng, N, t, n_list, keep):
+    """One frame's op list with HOST pointers: 10 predicts, 3 check+update, 8 check-only, symmetrise, augment."""
+    nops = 10 + 3 + 8 + 2
+    ops = (capi.EkfOp * nops)()
+    meas = []
+    k = 0
+    for s in range(10):
+        t += 0.005
+        g, a = ekf_script.imu_sample(irng, s + 1)
+        ops[k].kind, ops[k].t = capi.OP_PREDICT, t
+        for q in range(3):
+            ops[k].gyro[q] = g[q]; ops[k].acc[q] = a[q]
+        meas.append(("predict", t, g, a)); k += 1
+    for c in range(11):
+        n = n_list[c % len(n_list)]
+        H, f, y = ekf_script.visual_measurement(rng, n, N, 0.02 if c % 4 else 40.0)
+        H = np.asfortranarray(H); f = np.ascontiguousarray(f); y = np.ascontiguousarray(y)
+        keep += [H, f, y]
+        op = ops[k]
+        op.kind, op.n, op.l, op.mode, op.r, op.rmse_thr = capi.OP_VISUAL, n, H.shape[1], (2 if c < 3 else 0), ekf_script.VISUAL_R, -1.0
+        op.H, op.f, op.y = H.ctypes.data, f.ctypes.data, y.ctypes.data
+        meas.append(("visual", H, f, y, op.mode)); k += 1
+    ops[k].kind = capi.OP_SYMMETRIZE; meas.append(("sym",)); k += 1
+    ops[k].kind, ops[k].index = capi.OP_AUGMENT, -1; meas.append(("aug",)); k += 1
+    return ops, nops, meas, t
+
+
+@pytest.mark.parametrize("trail", [6, 20])
+def test_batch_submission_matches_single_calls(cuda, oracle_lk, trail):
+    """hv_ekf_run_host: fused multi-sample predict (one launch for the 10 IMU samples) and batched outlier checks (one
+    launch, one cluster per measurement) must equal the same calls issued one by one -- here against the oracle."""
+    from hybvio_b200 import capi
+    from oracle import ekf_oracle
+    p = C.params_with(default_params, trail)
+    a, b = cuda(p), ekf_oracle.OracleEKF(p)
+    rng, irng = np.random.RandomState(4), np.random.RandomState(12)
+    acc0 = ekf_script.imu_sample(np.random.RandomState(1), 0)[1]
+    a.initialize_orientation(acc0); b.initialize_orientation(acc0)
+    t = 0.0
+    for frame in range(4):
+        keep = []
+        ops, nops, meas, t = _frame_ops(capi, rng, irng, a.N, t, (8, 20, 40, 84) if trail == 20 else (8, 20), keep)
+        st, chi2, m = a.run_host(ops, nops, want_m=True)
+        exp_st = []
+        for i, mm in enumerate(meas):
+            if mm[0] == "predict":
+                b.predict(mm[1], mm[2], mm[3])
+            elif mm[0] == "visual":
+                s_, c_ = b.visual_check(mm[1], mm[2], mm[3], ekf_script.VISUAL_R)
+                exp_st.append((i, s_, c_))
+                if mm[4] == 2 and s_ == 0:
+                    b.visual_update(mm[1], mm[2], mm[3], ekf_script.VISUAL_R)
+            elif mm[0] == "sym":
+                b.symmetrize()
+            else:
+                b.augment(-1)
+        for i, s_, c_ in exp_st:
+            assert st[i] == s_, f"frame {frame} op {i}: status {st[i]} != {s_}"
+            assert abs(chi2[i] - c_) <= 1e-8 * max(1.0, abs(c_))
+        mb, Pb = b.download()
+        ma, Pa = a.download()
+        assert np.array_equal(m, ma)
+        assert np.abs(ma - mb).max() < C.TOL_M and ekf_script.rel_err(Pa, Pb) < C.TOL_P_REL, f"frame {frame}"
+        assert abs(a.platform_time() - b.platform_time()) < 1e-12 and a.pose_count() == b.pose_count()
+    a.close(); b.close()

@@ -175,3 +175,28 @@ def test_lk_properties_at_baseline_size(hv):
     assert np.array_equal(half[0], a[0][:75])
     for p in (p0, p1, pr):
         p.release()
+
+
+def test_pyramid_from_device_frame_and_device_lk(hv, oracle_lk):
+    """Frame already in HBM (hv_pyr_build_batch src_is_device): aligned and odd-pitch sources; device-pointer LK."""
+    import torch
+    L, R = synth.stereo_frame(7)
+    dL = torch.from_numpy(L).cuda()
+    odd = torch.zeros((480, 757), dtype=torch.uint8, device="cuda")    # pitch 757: not a multiple of 4
+    odd[:, :752] = torch.from_numpy(R).cuda()
+    pl, pr = hv.pyramid(752, 480), hv.pyramid(752, 480)
+    hv.build_pyramids([pl, pr], [dL, odd[:, :752]], device=True)
+    for p, img in ((pl, L), (pr, R)):
+        o = oracle_lk.pyramid(img)
+        for lv in range(4):
+            for a, b in zip(p.download(lv), o.download(lv, padded=False)):
+                assert np.array_equal(a, b)
+    pts = synth.interior_points(150, seed=5)
+    d_prev = torch.from_numpy(pts).cuda()
+    d_next = torch.zeros_like(d_prev)
+    d_st = torch.zeros(150, dtype=torch.uint8, device="cuda"); d_ts = torch.zeros(150, dtype=torch.int32, device="cuda")
+    hv.lk_track_device(pl, pr, d_prev, d_next, d_st, d_ts, 150, False)
+    hv.sync()
+    n_host, st_host, ts_host = hv.lk_track(pl, pr, pts)
+    assert np.array_equal(d_next.cpu().numpy(), n_host) and np.array_equal(d_ts.cpu().numpy(), ts_host)
+    pl.release(); pr.release()

@@ -30,3 +30,9 @@ for n in (8, 20, 40, 84):
                 line += f"{names[k]} {(ts[k] - prev) / 1e3:.1f} | "; prev = ts[k]
         print(line)
     ekf.symmetrize(); ekf.augment(-1)
+
+for rep in range(3):
+    ekf.predict(1.0 + 0.005 * (rep + 1), [0.01, 0.02, 0.2], [0.1, 0.2, 9.8])
+w = np.zeros(32); lib.hv_ekf_debug_result_words(ekf.h, w.ctypes.data)
+ts = w[8:13]
+print("predict: loads %.1f us | jacobian stages %.1f | strips %.1f | P00 %.1f | total %.1f" % tuple([(ts[i + 1] - ts[i]) / 1e3 for i in range(4)] + [(ts[4] - ts[0]) / 1e3]))
