@@ -1,0 +1,192 @@
+// hybvio_b200/host/cuda_ekf.cpp -- odometry::EKF implemented on top of the hv_ekf_* C ABI (include/hybvio_b200.h).
+//
+// Drop-in replacement for the reference's src/odometry/ekf.cpp: it defines odometry::EKF::build / ~EKF and a class
+// with the same 56 virtuals (src/odometry/ekf.hpp:62-174), so backend.cpp, triangulation.cpp, output.cpp, api.cpp, the
+// viewers and the reference's own unit tests (test/ekf.cpp, test/triangulation.cpp) compile and link UNCHANGED when this
+// file is compiled in place of ekf.cpp. State m and covariance P live on the GPU; the getters that
+// return Eigen references (getState, getStateCovarianceRef) are served from a lazily synchronised host mirror.
+// There is no CPU fallback: build() aborts with the library's error text if no B200 context can be created.
+#include "ekf.hpp"
+#include "parameters.hpp"
+#include "../../include/hybvio_b200.h"
+
+#include <Eigen/Eigenvalues>
+#include <cstdio>
+#include <cstdlib>
+#include <iomanip>
+#include <sstream>
+
+namespace {
+using namespace odometry;
+
+[[noreturn]] void fail(const char* what) {
+    std::fprintf(stderr, "hybvio_b200: %s failed: %s\n", what, hv_last_error());
+    std::abort();
+}
+#define HV(call) do { if ((call) != HV_OK) fail(#call); } while (0)
+
+// One context (stream) per process is enough for the reference's single-threaded Session; HV_DEVICE selects the GPU.
+hv_ctx* sharedContext() {
+    static hv_ctx* ctx = [] {
+        hv_ctx* c = nullptr;
+        const char* dev = std::getenv("HV_DEVICE");
+        if (hv_ctx_create(dev ? std::atoi(dev) : 0, &c) != HV_OK) fail("hv_ctx_create");
+        return c;
+    }();
+    return ctx;
+}
+
+struct CudaEKF : public EKF {
+    const Parameters& parameters;
+    hv_ekf* h = nullptr;
+    const int camPoseCount, hybridMapDim, stateDim;
+    const double noiseScale;
+    mutable Eigen::VectorXd m;          // host mirrors
+    mutable Eigen::MatrixXd P;
+    mutable bool mStale = true, PStale = true;
+
+    explicit CudaEKF(const Parameters& p)
+        : parameters(p), camPoseCount(p.odometry.cameraTrailLength), hybridMapDim(p.odometry.hybridMapSize * MAP_POINT_DIM),
+          stateDim(INER_DIM + camPoseCount * POSE_DIM + hybridMapDim), noiseScale(p.odometry.noiseScale * p.odometry.noiseScale) {
+        const ParametersOdometry& po = p.odometry;
+        hv_ekf_params q;
+        q.camera_trail_length = po.cameraTrailLength; q.hybrid_map_size = po.hybridMapSize;
+        q.noise_scale = po.noiseScale; q.gravity = po.gravity;
+        q.noise_initial_pos = po.noiseInitialPos; q.noise_initial_vel = po.noiseInitialVel; q.noise_initial_ori = po.noiseInitialOri;
+        q.noise_initial_bga = po.noiseInitialBGA; q.noise_initial_baa = po.noiseInitialBAA; q.noise_initial_bat = po.noiseInitialBAT;
+        q.noise_initial_sft = po.noiseInitialSFT; q.noise_initial_pos_trail = po.noiseInitialPosTrail; q.noise_initial_ori_trail = po.noiseInitialOriTrail;
+        q.noise_process_acc = po.noiseProcessAcc; q.noise_process_gyro = po.noiseProcessGyro;
+        q.noise_process_baa = po.noiseProcessBAA; q.noise_process_baa_rev = po.noiseProcessBAARev;
+        q.noise_process_bga = po.noiseProcessBGA; q.noise_process_bga_rev = po.noiseProcessBGARev;
+        q.augment_r = po.augmentR; q.init_zupt_r = po.initZuptR; q.rotation_zupt_r = po.rotationZuptR;
+        HV(hv_ekf_create(sharedContext(), &q, &h));
+        m.resize(stateDim); P.resize(stateDim, stateDim);
+    }
+    CudaEKF(const CudaEKF& o)
+        : EKF(o), parameters(o.parameters), camPoseCount(o.camPoseCount), hybridMapDim(o.hybridMapDim), stateDim(o.stateDim),
+          noiseScale(o.noiseScale), m(o.m), P(o.P), mStale(o.mStale), PStale(o.PStale) {
+        HV(hv_ekf_clone(o.h, &h));
+    }
+    ~CudaEKF() override { hv_ekf_destroy(h); }
+    std::unique_ptr<EKF> clone() const final { return std::unique_ptr<EKF>(new CudaEKF(*this)); }
+
+    void touched() { mStale = true; PStale = true; }
+    const Eigen::VectorXd& mean() const { if (mStale) { HV(hv_ekf_download(h, m.data(), nullptr)); mStale = false; } return m; }
+    const Eigen::MatrixXd& cov() const { if (PStale) { HV(hv_ekf_download(h, nullptr, P.data())); PStale = false; } return P; }
+
+    void initializeOrientation(const Eigen::Vector3d& xa) final { HV(hv_ekf_initialize_orientation(h, xa.data())); touched(); }
+    void predict(double t, const Eigen::Vector3d& xg, const Eigen::Vector3d& xa) final { HV(hv_ekf_predict(h, t, xg.data(), xa.data())); touched(); }
+    Eigen::Vector3d position() const final { return mean().segment(POS, 3); }
+    Eigen::Vector3d velocity() const final { return mean().segment(VEL, 3); }
+    Eigen::Vector4d orientation() const final { return mean().segment(ORI, 4); }
+    Eigen::Vector3d biasGyroscopeAdditive() const final { return mean().segment(BGA, 3); }
+    Eigen::Vector3d biasAccelerometerAdditive() const final { return mean().segment(BAA, 3); }
+    Eigen::Vector3d biasAccelerometerTransform() const final { return mean().segment(BAT, 3); }
+    int camTrailSize() const final { return camPoseCount; }
+    Eigen::Vector3d historyPosition(int i) const final { return i == -1 ? position() : Eigen::Vector3d(mean().segment(CAM + POSE_DIM * i, 3)); }
+    Eigen::Vector4d historyOrientation(int i) const final { return i == -1 ? orientation() : Eigen::Vector4d(mean().segment(CAM + POSE_DIM * i + 3, 4)); }
+    double historyTime(int i) const final { return hv_ekf_history_time(h, i); }
+    double speed() const final { return mean().segment(VEL, 3).norm(); }
+    double horizontalSpeed() const final { return mean().segment(VEL, 2).norm(); }
+    void updateZupt(double r) final { HV(hv_ekf_update_zupt(h, r)); touched(); }
+    void updateZuptInitialization() final { HV(hv_ekf_update_zupt_initialization(h)); touched(); }
+    void updateZrupt(const Eigen::Vector3d& xg) final { HV(hv_ekf_update_zrupt(h, xg.data())); touched(); }
+    void updatePseudoVelocity(double defaultSpeed, double r) final { HV(hv_ekf_update_pseudo_velocity(h, defaultSpeed, r)); touched(); }
+    void updatePosition(const Eigen::Vector3d& pos, double r) final { HV(hv_ekf_update_position(h, pos.data(), r)); touched(); }
+    void updateZeroHeight(double r) final { HV(hv_ekf_update_zero_height(h, r)); touched(); }
+    void updateOrientation(const Eigen::Vector4d& q, double r) final { HV(hv_ekf_update_orientation(h, q.data(), r)); touched(); }
+
+    void getInertialState(VectorInertialMean& mean_, MatrixInertialCov& cov_) const final { HV(hv_ekf_download_inertial(h, mean_.data(), cov_.data())); }
+    void setInertialState(const VectorInertialMean& mean_, const MatrixInertialCov& cov_) final { HV(hv_ekf_set_inertial_state(h, mean_.data(), cov_.data())); touched(); }
+    double getImuToCameraTimeShift() const final { return mean()(SFT); }
+    void translateTo(const Eigen::Vector3d& pos) final { HV(hv_ekf_translate_to(h, pos.data())); touched(); }
+    void transformTo(const Eigen::Vector3d& pos, const Eigen::Vector4d& q, int i = -1) final { HV(hv_ekf_transform_to(h, pos.data(), q.data(), i)); touched(); }
+
+    VuOutlierStatus visualTrackOutlierCheck(const Eigen::MatrixXd& visH, const Eigen::VectorXd& f, const Eigen::VectorXd& y, double r,
+                                            double trackRmseThreshold) final {
+        int st = 0;
+        HV(hv_ekf_visual_check(h, visH.data(), (int)visH.rows(), (int)visH.cols(), f.data(), y.data(), r, trackRmseThreshold, &st, nullptr));
+        return static_cast<VuOutlierStatus>(st);
+    }
+    void updateVisualTrack(const Eigen::MatrixXd& visH, const Eigen::VectorXd& f, const Eigen::VectorXd& y, double r) final {
+        HV(hv_ekf_visual_update(h, visH.data(), (int)visH.rows(), (int)visH.cols(), f.data(), y.data(), r));
+        touched();
+    }
+    void updateVisualPoseAugmentation(int discardedPoseIndex = -1) final { HV(hv_ekf_augment(h, discardedPoseIndex)); touched(); }
+    void updateUndoAugmentation() final { HV(hv_ekf_unaugment(h)); touched(); }
+
+    Eigen::Vector3d getMapPoint(int idx) const final { return mean().segment<3>(getMapPointStateIndex(idx)); }
+    void insertMapPoint(int idx, const Eigen::Vector3d& pf) final { HV(hv_ekf_insert_map_point(h, idx, pf.data())); touched(); }
+    int getMapPointStateIndex(int idx) const final { return idx == -1 ? -1 : stateDim - hybridMapDim + idx * MAP_POINT_DIM; }
+
+    void conditionOnLastPose() final { HV(hv_ekf_condition_on_last_pose(h)); touched(); }
+    void lockBiases() final { HV(hv_ekf_lock_biases(h)); touched(); }
+    void normalizeQuaternions(bool onlyCurrent) final { HV(hv_ekf_normalize_quaternions(h, onlyCurrent ? 1 : 0)); mStale = true; }
+    void setFirstSampleTime(double t) final { HV(hv_ekf_set_first_sample_time(h, t)); }
+    bool isPositiveSemiDefinite() final {   // "Expensive, use only for debugging" (ekf.cpp:1043-1057)
+        Eigen::SelfAdjointEigenSolver<Eigen::MatrixXd> es(cov());
+        return es.info() == Eigen::Success && es.eigenvalues().minCoeff() >= 0.0;
+    }
+    void maintainPositiveSemiDefinite() final { HV(hv_ekf_symmetrize(h)); PStale = true; }
+    void setState(const Eigen::VectorXd& m_) final { HV(hv_ekf_upload(h, m_.data(), nullptr)); mStale = true; }
+    void setStateCovariance(const Eigen::MatrixXd& P_) final { HV(hv_ekf_upload(h, nullptr, P_.data())); PStale = true; }
+    void setProcessNoise(const Eigen::MatrixXd& Q_) final { Eigen::Matrix<double, Q_DIM, Q_DIM> q = Q_; HV(hv_ekf_set_process_noise(h, q.data())); }
+    double getPlatformTime() const final { return hv_ekf_platform_time(h); }
+    int getPoseCount() const final { return hv_ekf_pose_count(h); }
+    const Eigen::VectorXd& getState() const final { return mean(); }
+    Eigen::MatrixXd getStateCovariance() const final { return cov(); }
+    const Eigen::MatrixXd& getStateCovarianceRef() const final { return cov(); }
+    int getStateDim() const final { return stateDim; }
+    bool getWasStationary() const final { return hv_ekf_was_stationary(h) != 0; }
+
+    // constant structure matrices, only used by debug viewers / tests (ekf.cpp:229-291)
+    Eigen::MatrixXd getVisAugH() const final {
+        Eigen::MatrixXd H = Eigen::MatrixXd::Zero(POSE_DIM, stateDim);
+        for (int i = 0; i < 3; i++) { H(i, POS + i) = 1; H(i, CAM + i) = -1; }
+        for (int i = 0; i < 4; i++) { H(3 + i, ORI + i) = 1; H(3 + i, CAM + 3 + i) = -1; }
+        return H;
+    }
+    Eigen::MatrixXd getVisAugA() const final {   // drops the last pose of the trail
+        Eigen::MatrixXd A = Eigen::MatrixXd::Zero(stateDim, stateDim);
+        const int drop = camPoseCount - 1;
+        for (int i = 0; i < CAM; i++) A(i, i) = 1;
+        for (int i = CAM; i < CAM + drop * POSE_DIM; ++i) A(i + POSE_DIM, i) = 1;
+        for (int i = CAM + (drop + 1) * POSE_DIM; i < stateDim; i++) A(i, i) = 1;
+        return A;
+    }
+    Eigen::MatrixXd getVisAugQ() const final {
+        Eigen::MatrixXd Q = Eigen::MatrixXd::Zero(stateDim, stateDim);
+        const ParametersOdometry& po = parameters.odometry;
+        for (int i = CAM; i < CAM + 3; i++) Q(i, i) = po.noiseInitialPosTrail * po.noiseInitialPosTrail * noiseScale;
+        for (int i = CAM + 3; i < CAM + POSE_DIM; i++) Q(i, i) = po.noiseInitialOriTrail * po.noiseInitialOriTrail * noiseScale;
+        return Q;
+    }
+    Eigen::MatrixXd getDydx() const final {
+        Eigen::MatrixXd full = Eigen::MatrixXd::Identity(stateDim, stateDim);
+        Eigen::Matrix<double, INER_DIM, INER_DIM> d;
+        HV(hv_ekf_get_dydx(h, d.data()));
+        full.topLeftCorner<INER_DIM, INER_DIM>() = d;
+        return full;
+    }
+    std::string stateAsString() const final {   // same layout as ekf.cpp:997-1022
+        std::stringstream ss;
+        Eigen::Matrix<double, INER_DIM, 1> var = cov().block(0, 0, INER_DIM, INER_DIM).diagonal();
+        for (size_t i = 0; i < STATE_PARTS.size(); i++) {
+            const int part = STATE_PARTS[i], size = STATE_PART_SIZES[i];
+            ss << STATE_PART_NAMES[i] << " ";
+            for (int j = 0; j < size; j++) ss << std::setprecision(3) << mean()(part + j) << " ";
+            ss << std::setprecision(2) << " [" << std::sqrt(var.segment(part, size).maxCoeff()) << "], ";
+            if (i == 2) ss << std::endl << " ";
+        }
+        ss << std::fixed << std::setprecision(3) << "t " << (hv_ekf_platform_time(h));
+        return ss.str();
+    }
+};
+} // namespace
+
+namespace odometry {
+EKF::~EKF() = default;
+EKF::EKF(const EKF& other) = default;
+EKF::EKF() {}
+std::unique_ptr<EKF> EKF::build(const Parameters& parameters) { return std::unique_ptr<EKF>(new CudaEKF(parameters)); }
+} // namespace odometry

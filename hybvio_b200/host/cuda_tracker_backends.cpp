@@ -1,0 +1,142 @@
+// hybvio_b200/host/cuda_tracker_backends.cpp -- tracker::ImagePyramid / ImagePyramid::Factory / tracker::OpticalFlow
+// implemented on top of the hv_pyr_* / hv_lk_* C ABI (include/hybvio_b200.h).
+//
+// Plugs into the single seam where the reference chooses its back ends, ImageImplementation::SharedData
+// (src/tracker/image.cpp:55-56): replace
+//     ImagePyramid::Factory::buildOpenCv(parameters.tracker) -> tracker::buildCudaImagePyramidFactory(parameters.tracker)
+//     OpticalFlow::buildOpenCv(parameters.tracker)           -> tracker::buildCudaOpticalFlow(parameters.tracker)
+// (a two-line change, or compile this file instead of image_pyramid.cpp / optical_flow.cpp and keep the buildOpenCv
+// names: define HV_REPLACE_OPENCV_BACKENDS). tracker.cpp, image.cpp and everything above them are unchanged: the
+// pyramid stays an opaque tracker::ImagePyramid handed from Image::opticalFlow to OpticalFlow::compute
+// (src/tracker/image.cpp:87-106), and getOpenCv() is only ever called by the OpenCV flow back end
+// (src/tracker/optical_flow.cpp:96-97), which this file replaces.
+#include "image_pyramid.hpp"
+#include "optical_flow.hpp"
+#include "parameters.hpp"
+#include "../../include/hybvio_b200.h"
+
+#include <accelerated-arrays/cpu/image.hpp>
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+
+namespace cv { class Mat; }
+
+namespace tracker {
+namespace {
+[[noreturn]] void fail(const char* what) {
+    std::fprintf(stderr, "hybvio_b200: %s failed: %s\n", what, hv_last_error());
+    std::abort();
+}
+#define HV(call) do { if ((call) != HV_OK) fail(#call); } while (0)
+
+hv_ctx* sharedContext() {
+    static hv_ctx* ctx = [] {
+        hv_ctx* c = nullptr;
+        const char* dev = std::getenv("HV_DEVICE");
+        if (hv_ctx_create(dev ? std::atoi(dev) : 0, &c) != HV_OK) fail("hv_ctx_create");
+        return c;
+    }();
+    return ctx;
+}
+
+// Pool of device pyramids, recycled like the reference's util::Allocator ring (image_pyramid.cpp:31,37): a pyramid
+// returns to the pool when the last tracker::Image holding it dies (prevImage, SLAM queue, ...).
+struct PyramidPool {
+    std::mutex mutex;
+    std::vector<hv_pyr*> free;
+    int w = 0, h = 0, win = 0, maxLevel = 0;
+    hv_pyr* acquire(int width, int height, int win_, int maxLevel_) {
+        std::lock_guard<std::mutex> lock(mutex);
+        if (width != w || height != h || win_ != win || maxLevel_ != maxLevel) {
+            for (hv_pyr* p : free) hv_pyr_release(p);
+            free.clear(); w = width; h = height; win = win_; maxLevel = maxLevel_;
+        }
+        if (!free.empty()) { hv_pyr* p = free.back(); free.pop_back(); return p; }
+        hv_pyr* p = nullptr;
+        HV(hv_pyr_create(sharedContext(), width, height, win_, maxLevel_, &p));
+        return p;
+    }
+    void release(hv_pyr* p, int width, int height) {
+        std::lock_guard<std::mutex> lock(mutex);
+        if (width == w && height == h) free.push_back(p); else hv_pyr_release(p);
+    }
+};
+
+struct CudaImagePyramid : ImagePyramid {
+    std::shared_ptr<PyramidPool> pool;
+    hv_pyr* pyr = nullptr;
+    int width = 0, height = 0;
+    std::shared_ptr<accelerated::Image> source;   // keeps the host gray image alive until the async H2D has been consumed
+
+    ~CudaImagePyramid() override { if (pyr) pool->release(pyr, width, height); }
+    // The device layout is not an accelerated::Image; like the reference's CPU pyramid (image_pyramid.cpp:17-25) these
+    // two accessors are not used by any caller.
+    accelerated::Image& getGrayLevel(std::size_t) final { assert(false && "device-resident pyramid"); std::abort(); }
+    accelerated::Image& getGradientLevel(std::size_t) final { assert(false && "device-resident pyramid"); std::abort(); }
+    const std::vector<cv::Mat>& getOpenCv() final { assert(false && "device-resident pyramid: no cv::Mat view"); std::abort(); }
+};
+
+class CudaImagePyramidFactory : public ImagePyramid::Factory {
+    const odometry::ParametersTracker& parameters;
+    std::shared_ptr<PyramidPool> pool = std::make_shared<PyramidPool>();
+public:
+    explicit CudaImagePyramidFactory(const odometry::ParametersTracker& p) : parameters(p) {}
+    std::shared_ptr<ImagePyramid> compute(std::shared_ptr<accelerated::Image> img) final {
+        assert(img->channels == 1 && img->bytesPerChannel() == 1);   // gray u8 (ImagePyramid::GrayType)
+        auto& cpu = accelerated::cpu::Image::castFrom(*img);
+        auto pyramid = std::make_shared<CudaImagePyramid>();
+        pyramid->pool = pool; pyramid->width = img->width; pyramid->height = img->height; pyramid->source = img;
+        pyramid->pyr = pool->acquire(img->width, img->height, parameters.pyrLKWindowSize, parameters.pyrLKMaxLevel);
+        // H2D copy + one fused kernel, asynchronous on the context stream (cv::buildOpticalFlowPyramid in the reference)
+        HV(hv_pyr_build(pyramid->pyr, cpu.getData<std::uint8_t>(), static_cast<size_t>(cpu.bytesPerRow())));
+        return pyramid;
+    }
+};
+
+class CudaOpticalFlow : public OpticalFlow {
+    const odometry::ParametersTracker& parameters;
+    std::vector<std::int32_t> status32;
+public:
+    explicit CudaOpticalFlow(const odometry::ParametersTracker& p) : parameters(p) {}
+    void compute(ImagePyramid& prevImagePyramid, ImagePyramid& imagePyramid, const std::vector<Feature::Point>& prevCorners,
+                 std::vector<Feature::Point>& corners, std::vector<Feature::Status>& trackStatus, bool useInitialCorners,
+                 int overrideMaxIterations) final {
+        auto& prev = static_cast<CudaImagePyramid&>(prevImagePyramid);
+        auto& next = static_cast<CudaImagePyramid&>(imagePyramid);
+        const int n = static_cast<int>(prevCorners.size());
+        trackStatus.clear();
+        trackStatus.resize(prevCorners.size(), Feature::Status::FAILED_FLOW);
+        if (n == 0) { corners.clear(); return; }                       // optical_flow.cpp:41-44
+        if (!useInitialCorners) corners.resize(prevCorners.size());
+        assert(corners.size() == prevCorners.size());
+        status32.resize(n);
+        static_assert(sizeof(Feature::Point) == 2 * sizeof(float), "Feature::Point is {float x, y}");
+        const int maxIter = overrideMaxIterations > 0 ? overrideMaxIterations : parameters.pyrLKMaxIter;
+        // TRACKED / FAILED_FLOW / FLOW_OUT_OF_RANGE are derived on the device exactly as optical_flow.cpp:52-58 does
+        HV(hv_lk_track(sharedContext(), prev.pyr, next.pyr, reinterpret_cast<const float*>(prevCorners.data()),
+                       reinterpret_cast<float*>(corners.data()), nullptr, status32.data(), n, useInitialCorners ? 1 : 0, maxIter,
+                       parameters.pyrLKEpsilon, parameters.pyrLKMinEigThreshold));
+        for (int i = 0; i < n; i++) trackStatus[i] = static_cast<Feature::Status>(status32[i]);
+    }
+};
+} // namespace
+
+std::unique_ptr<ImagePyramid::Factory> buildCudaImagePyramidFactory(const odometry::ParametersTracker& p) {
+    return std::unique_ptr<ImagePyramid::Factory>(new CudaImagePyramidFactory(p));
+}
+std::unique_ptr<OpticalFlow> buildCudaOpticalFlow(const odometry::ParametersTracker& p) {
+    return std::unique_ptr<OpticalFlow>(new CudaOpticalFlow(p));
+}
+
+#ifdef HV_REPLACE_OPENCV_BACKENDS
+// compiled INSTEAD of src/tracker/image_pyramid.cpp and optical_flow.cpp: same symbols, CUDA back ends
+std::unique_ptr<ImagePyramid::Factory> ImagePyramid::Factory::buildOpenCv(const odometry::ParametersTracker& p) { return buildCudaImagePyramidFactory(p); }
+std::unique_ptr<OpticalFlow> OpticalFlow::buildOpenCv(const odometry::ParametersTracker& p) { return buildCudaOpticalFlow(p); }
+ImagePyramid::~ImagePyramid() = default;
+ImagePyramid::Factory::~Factory() = default;
+OpticalFlow::~OpticalFlow() = default;
+#endif
+} // namespace tracker

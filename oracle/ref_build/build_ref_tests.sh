@@ -1,0 +1,36 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE: builds oracle/_ref/run_ref_ekf_tests = the reference's OWN Catch2 unit tests for the EKF
+# (test/ekf.cpp: "chi-squared innovation test", "der_predict", "tranformTo"; test/test_main.cpp, test/helpers.cpp),
+# compiled UNMODIFIED, but linked against hybvio_b200/host/cuda_ekf.cpp (+ libhybvio_b200.so) instead of the
+# reference's src/odometry/ekf.cpp. Passing it on a B200 shows that CudaEKF is a drop-in for odometry::EKF.
+# The fixtures test/data/{P,m}.csv are copied next to the binary (build output, git-ignored).
+set -e
+REF=${REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+ROOT=$(cd "$HERE/../.." && pwd)
+OUT=${OUT:-$HERE/../_ref}
+M=$REF/3rdparty/mobile-cv-suite
+OCV=$M/opencv/modules
+[ -f "$OUT/gen/output/parameters.hpp" ] || "$HERE/build_ekf.sh"
+mkdir -p "$OUT/obj_tests" "$OUT/inc" "$OUT/test/data"
+ln -sfn "$M/accelerated-arrays/src" "$OUT/inc/accelerated-arrays"
+ln -sfn "$M/jsonl-recorder" "$OUT/inc/jsonl-recorder"
+# test/ekf.cpp includes "../src/odometry/parameters.hpp", a dangling symlink in the read-only tree: shadow it
+mkdir -p "$OUT/inc/src/odometry" "$OUT/inc/shadow" "$OUT/inc/src/shadow"
+ln -sfn "$OUT/gen/output/parameters.hpp" "$OUT/inc/src/odometry/parameters.hpp"
+cp "$REF/test/data/P.csv" "$REF/test/data/m.csv" "$OUT/test/data/"
+FL="-std=c++17 -O1 -w -DEIGEN_MPL2_ONLY -DEIGEN_DONT_PARALLELIZE"
+INC="-I$OUT/gen/output -I$M/eigen -I$M/json/single_include -I$REF/src/odometry -I$REF/src/tracker -I$REF/src -I$REF/test -I$OUT/inc -I$OUT/inc/shadow -I$OUT/inc/src/shadow \
+  -I$HERE/stubs -I$OCV/core/include -I$OCV/imgproc/include -I$OCV/video/include -I$OCV/calib3d/include -I$OCV/features2d/include \
+  -I$OCV/flann/include -I$OCV/highgui/include -I$OCV/imgcodecs/include -I$OCV/videoio/include -I$OCV/../include"
+O=$OUT/obj_tests
+g++ $FL $INC -c "$REF/test/ekf.cpp" -o $O/test_ekf.o &
+g++ $FL $INC -c "$REF/test/test_main.cpp" -o $O/test_main.o &
+g++ $FL $INC -c "$REF/test/helpers.cpp" -o $O/helpers.o &
+g++ $FL $INC -c "$ROOT/hybvio_b200/host/cuda_ekf.cpp" -o $O/cuda_ekf.o &
+wait
+# parameters.o / odo_util.o ... come from build_ekf.sh (the reference's own support objects, minus ekf.o)
+g++ -o "$OUT/run_ref_ekf_tests" $O/test_ekf.o $O/test_main.o $O/helpers.o $O/cuda_ekf.o \
+    $OUT/obj_ekf/parameters.o $OUT/obj_ekf/odo_util.o $OUT/obj_ekf/timer.o $OUT/obj_ekf/util_util.o $OUT/obj_ekf/parameter_parser.o \
+    -Wl,--gc-sections -L"$ROOT/hybvio_b200" -lhybvio_b200 -Wl,-rpath,'$ORIGIN/../../hybvio_b200' -lpthread
+echo built $OUT/run_ref_ekf_tests

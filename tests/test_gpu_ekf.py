@@ -181,3 +181,17 @@ def test_batch_submission_matches_single_calls(cuda, oracle_lk, trail):
         assert np.abs(ma - mb).max() < C.TOL_M and ekf_script.rel_err(Pa, Pb) < C.TOL_P_REL, f"frame {frame}"
         assert abs(a.platform_time() - b.platform_time()) < 1e-12 and a.pose_count() == b.pose_count()
     a.close(); b.close()
+
+
+def test_reference_catch2_suite_against_cuda_ekf():
+    """The reference's OWN unit tests (test/ekf.cpp: chi-squared KAT, der_predict, tranformTo with test/data/P.csv,
+    m.csv), compiled unmodified but linked against hybvio_b200/host/cuda_ekf.cpp instead of src/odometry/ekf.cpp
+    (oracle/ref_build/build_ref_tests.sh). Drop-in proof for the odometry::EKF interface."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "run_ref_ekf_tests")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/run_ref_ekf_tests not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], cwd=os.path.join(root, "oracle", "_ref"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "All tests passed" in r.stdout and "3 test cases" in r.stdout, r.stdout[-500:]
