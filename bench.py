@@ -284,6 +284,36 @@ def time_kernels(sess, reps=40):
     return out
 
 
+def aggregate_ms(ms_local, device, world):
+    """Device time of the step loop = MAX over ranks (each rank runs its own independent session)."""
+    import torch
+    import torch.distributed as dist
+    ms = torch.tensor([ms_local], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def frames_per_second(world, steps, ms):
+    """Whole-job throughput: every rank processed `steps` frames of its own session in `ms` (weak scaling)."""
+    return world * steps / (ms * 1e-3)
+
+
+def run_selftest_dist(args):
+    """CPU-only check of the multi-process plumbing (gloo): rank r pretends its loop took (10 + r) ms."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        dist.init_process_group("gloo")
+        dist.barrier()
+    ms = aggregate_ms(10.0 + rank, torch.device("cpu"), world)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps({"selftest": True, "n_gpus": world, "ms": ms, "value": frames_per_second(world, args.steps, ms), "scaling": "weak"}))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -317,11 +347,9 @@ def run_ours(args):
         e.record(sess.stream)
         e.synchronize()
         barrier()
-        ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=sess.dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = aggregate_ms(s.elapsed_time(e), sess.dev, world)
         clocks = sampler.stop() if sampler else None
-        return float(ms.item()), sess.ctx.launches - launches0, clocks
+        return ms, sess.ctx.launches - launches0, clocks
 
     with torch.cuda.stream(sess.stream):
         ms_dev, launches, clocks = timed_loop(sess.step_device, args.steps, args.warmup)
@@ -333,8 +361,8 @@ def run_ours(args):
 
     result = None
     if rank == 0:
-        value = world * args.steps / (ms_dev * 1e-3)
-        e2e = world * e2e_steps / (ms_e2e * 1e-3)
+        value = frames_per_second(world, args.steps, ms_dev)
+        e2e = frames_per_second(world, e2e_steps, ms_e2e)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -504,9 +532,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--selftest-dist", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
-    if args.impl == "reference":
+    if args.selftest_dist:
+        run_selftest_dist(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -1,0 +1,45 @@
+"""CPU tests of bench.py's multi-process plumbing (gloo, world_size 2) and of its workload definitions."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun(nproc, *extra, env=None):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(ROOT, "bench.py"), *extra]
+    e = dict(os.environ); e.update(env or {})
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=e)
+
+
+def test_two_rank_max_reduction_and_weak_scaling_value():
+    r = _torchrun(2, "--selftest-dist", "--steps", "100")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, "exactly one JSON line, printed by rank 0"
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["ms"] == 11.0            # MAX over ranks of (10 + rank)
+    assert abs(d["value"] - 2 * 100 / 0.011) < 1e-6         # both sessions' frames over the slower rank's time
+    assert d["scaling"] == "weak"
+
+
+def test_single_process_selftest():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--selftest-dist", "--steps", "50"], capture_output=True, text=True, cwd=ROOT)
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["n_gpus"] == 1 and d["ms"] == 10.0 and abs(d["value"] - 5000.0) < 1e-9
+
+
+def test_workload_definition_matches_baseline_config():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert (bench.W, bench.H, bench.NFEAT, bench.WIN, bench.MAXLEVEL, bench.TRAIL) == (752, 480, 150, 31, 3, 20)
+    assert (bench.CHECKS, bench.UPDATES, bench.PREDICTS) == (20, 5, 10)
+    assert bench.PYR_BYTES == 2_397_000 and bench.LK_BYTES == 3_688_200
+    assert [bench.ekf_rows(c) for c in range(4)] == [(8, 34), (20, 55), (40, 90), (84, 160)]
+    seen = [bench.frame_index(k) for k in range(1, 600)]
+    assert all(abs(a - b) == 1 for a, b in zip(seen, seen[1:]))               # consecutive steps are consecutive frames
+    assert min(seen) == 0 and max(seen) == bench.POOL_FRAMES - 1
+    pool_mb = bench.POOL_FRAMES * 2 * bench.W * bench.H / 1e6
+    assert pool_mb + 40 > 126                                                   # inputs larger than L2
