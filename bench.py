@@ -233,11 +233,12 @@ class ClockSampler:
 
 
 def time_kernels(sess, reps=40):
-    """Average device time of each kernel class, CUDA events on the launching stream, inputs cycled through the pools."""
+    """Average device time of every launch of one step, CUDA events on the launching stream, inputs cycled through the
+    pools. Returns {launch name: {us_per_launch, algo_bytes, gbs, per_step}} in step order."""
     torch = sess.torch
     out = {}
 
-    def timed(name, fn, launches, algo_bytes):
+    def timed(name, fn, algo_bytes, per_step=1):
         for i in range(3):
             fn(i)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -247,40 +248,90 @@ def time_kernels(sess, reps=40):
                 fn(i + 3)
             e.record(sess.stream)
         e.synchronize()
-        us = s.elapsed_time(e) * 1e3 / (reps * launches)
-        out[name] = {"us_per_launch": round(us, 3), "algo_bytes": algo_bytes, "gbs": round(algo_bytes / us * 1e-3, 2)}
+        us = s.elapsed_time(e) * 1e3 / reps
+        out[name] = {"us_per_launch": round(us, 3), "algo_bytes": algo_bytes, "gbs": round(algo_bytes / us * 1e-3, 2), "per_step": per_step}
 
-    inp, ctx, ekf = sess.inp, sess.ctx, sess.ekf
+    inp, ctx, ekf, capi = sess.inp, sess.ctx, sess.ekf, sess.capi
     cur = sess.pyr[2:4]
-    timed("pyramid(2 images)", lambda i: ctx.build_pyramids(cur, [sess.d_frames[(7 * i) % POOL_FRAMES, 0], sess.d_frames[(7 * i) % POOL_FRAMES, 1]], device=True),
-          1, 2 * PYR_BYTES)
+    N = ekf.N
+    timed("hv_pyr_fused_kernel (2 images)", lambda i: ctx.build_pyramids(cur, [sess.d_frames[(7 * i) % POOL_FRAMES, 0], sess.d_frames[(7 * i) % POOL_FRAMES, 1]], device=True),
+          2 * PYR_BYTES)
     ctx.build_pyramids(cur, [sess.d_frames[1, 0], sess.d_frames[1, 1]], device=True)
     ctx.build_pyramids(sess.pyr[0:2], [sess.d_frames[0, 0], sess.d_frames[0, 1]], device=True)
 
     def lk_t(i):
         sess.d_next.copy_(sess.d_init[0, 0])
         ctx.lk_track_device(sess.pyr[0], cur[0], sess.d_points, sess.d_next, sess.d_status, sess.d_ts, NFEAT, True)
-    timed("lk_temporal(+init copy)", lk_t, 1, LK_BYTES)
-    timed("lk_stereo", lambda i: ctx.lk_track_device(cur[0], cur[1], sess.d_next, sess.d_next2, sess.d_status, sess.d_ts, NFEAT, False), 1, LK_BYTES)
-    N = ekf.N
+    timed("hv_lk_kernel temporal (+ init copy)", lk_t, LK_BYTES)
+    timed("hv_lk_kernel stereo", lambda i: ctx.lk_track_device(cur[0], cur[1], sess.d_next, sess.d_next2, sess.d_status, sess.d_ts, NFEAT, False), LK_BYTES)
 
     def pred(i):
-        sess.t += 0.005
-        ekf.predict(sess.t, inp.imu[i % len(inp.imu), :3], inp.imu[i % len(inp.imu), 3:])
-    timed("ekf_predict", pred, 1, 2 * 8 * (40 * N - 400))
-    for n in N_ROWS:
-        c = N_ROWS.index(n)
-        o, n_, l = inp.ekf_off[c]
+        ops = sess.ops_dev[i % POOL_EKF]
+        for s_ in range(PREDICTS):
+            sess.t += 0.005
+            ops[s_].t = sess.t
+        ekf.run_device(ops, PREDICTS)
+    timed(f"ekf_predict_kernel ({PREDICTS} samples fused)", pred, PREDICTS * 2 * 8 * (40 * N - 400))
+    for c in range(UPDATES):
+        n, l = ekf_rows(c)
 
-        def chk(i, mode=0):
-            b = sess.d_ekf_pool[i % POOL_EKF]
-            ekf.visual_device(b[o:], n_, l, b[o + n_ * l:], b[o + n_ * l + n_:], VISUAL_R, -1.0, mode, None)
-        timed(f"ekf_check(n={n},l={l})", chk, 1, 8 * N * N + 8 * n * l)
-        timed(f"ekf_check_update(n={n},l={l})", lambda i: chk(i, 2), 1, 2 * 8 * N * N + 8 * n * l)
-        ekf.symmetrize()
-        ekf.augment(-1)
-    timed("ekf_symmetrize", lambda i: ekf.symmetrize(), 1, 2 * 8 * N * N)
-    timed("ekf_augment", lambda i: ekf.augment(-1), 1, 2 * 8 * N * N)
+        def upd(i, c=c):
+            ops = sess.ops_dev[i % POOL_EKF]
+            ekf.run_device(ctypes_slice(ops, PREDICTS + c, 1), 1)
+        timed(f"ekf_update_cluster_kernel check+update #{c} (n={n},l={l})", upd, 2 * 8 * N * N + 8 * n * l)
+        ekf.symmetrize(); ekf.augment(-1)
+
+    def chk(i):
+        ops = sess.ops_dev[i % POOL_EKF]
+        ekf.run_device(ctypes_slice(ops, PREDICTS + UPDATES, CHECKS - UPDATES), CHECKS - UPDATES)
+    timed(f"ekf_check_batch_cluster_kernel ({CHECKS - UPDATES} tracks, one cluster each)", chk,
+          sum(8 * N * N + 8 * n * l for n, l in (ekf_rows(c) for c in range(UPDATES, CHECKS))))
+    timed("ekf_ew_kernel symmetrize", lambda i: ekf.symmetrize(), 2 * 8 * N * N)
+    timed("ekf_update_cluster_kernel augment", lambda i: ekf.augment(-1), 2 * 8 * N * N)
+    return out
+
+
+def ctypes_slice(arr, start, count):
+    import ctypes
+    return ctypes.cast(ctypes.byref(arr, start * ctypes.sizeof(arr._type_)), ctypes.POINTER(arr._type_))
+
+
+def time_batched(sess, reps=20):
+    """What the same kernels reach when one launch carries many independent sessions (pyramid: 32 images, LK: 8 jobs x
+    150 features): shows how far the single-session numbers are from the kernels' own limits."""
+    torch = sess.torch
+    out = {}
+    ctx = sess.ctx
+    pyrs = [ctx.pyramid(W, H, WIN, MAXLEVEL) for _ in range(32)]
+    imgs = [sess.d_frames[(3 * i) % POOL_FRAMES, i % 2] for i in range(32)]
+
+    def run(name, fn, algo):
+        for _ in range(3):
+            fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(sess.stream):
+            s.record(sess.stream)
+            for _ in range(reps):
+                fn()
+            e.record(sess.stream)
+        e.synchronize()
+        us = s.elapsed_time(e) * 1e3 / reps
+        out[name] = {"us_per_launch": round(us, 2), "algo_bytes": algo, "gbs": round(algo / us * 1e-3, 1)}
+    run("hv_pyr_fused_kernel (32 images, one launch)", lambda: ctx.build_pyramids(pyrs, imgs, device=True), 32 * PYR_BYTES)
+    capi = sess.capi
+    jobs = (capi.LkJob * 8)()
+    bufs = []
+    for j in range(8):
+        nxt = torch.zeros((NFEAT, 2), dtype=torch.float32, device=sess.dev); st = torch.zeros(NFEAT, dtype=torch.uint8, device=sess.dev)
+        bufs += [nxt, st]
+        jobs[j].prev, jobs[j].next = pyrs[2 * j].h, pyrs[2 * j + 1].h
+        jobs[j].d_prev_xy, jobs[j].d_next_xy, jobs[j].d_status, jobs[j].d_track_status = sess.d_points.data_ptr(), nxt.data_ptr(), st.data_ptr(), None
+        jobs[j].n, jobs[j].use_initial = NFEAT, 0
+    lib = capi.load()
+    run("hv_lk_kernel (8 sessions x 150 features, one launch)", lambda: capi.check(lib.hv_lk_track_batch_device(ctx.h, jobs, 8, 20, 0.03, 1e-3), "lk batch"), 8 * LK_BYTES)
+    ctx.sync()
+    for p in pyrs:
+        p.release()
     return out
 
 
@@ -358,6 +409,7 @@ def run_ours(args):
         m, P = sess.ekf.download()
         healthy = bool(np.isfinite(m).all() and np.isfinite(P).all() and (np.diag(P) >= 0).all())
         kern = time_kernels(sess) if rank == 0 else None
+        kbatch = time_batched(sess) if rank == 0 else None
 
     result = None
     if rank == 0:
@@ -369,27 +421,30 @@ def run_ours(args):
         except Exception:
             pass
         peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-        # per-step share of each kernel class
-        per_step = {"pyramid(2 images)": 1, "lk_temporal(+init copy)": 1, "lk_stereo": 1, "ekf_predict": PREDICTS, "ekf_symmetrize": 1, "ekf_augment": 1}
-        for c in range(CHECKS):
-            n, l = ekf_rows(c)
-            key = f"ekf_check_update(n={n},l={l})" if c < UPDATES else f"ekf_check(n={n},l={l})"
-            per_step[key] = per_step.get(key, 0) + 1
-        shares = {k: kern[k]["us_per_launch"] * cnt for k, cnt in per_step.items()}
+        shares = {k: v["us_per_launch"] * v["per_step"] for k, v in kern.items()}
         tot = sum(shares.values())
-        fam = {"pyramid": 0.0, "lk": 0.0, "ekf_update_kernel": 0.0, "ekf_predict": 0.0, "ekf_other": 0.0}
+        fam = {}
         for k, v in shares.items():
-            fam["pyramid" if k.startswith("pyr") else "lk" if k.startswith("lk") else "ekf_predict" if k == "ekf_predict" else
-                "ekf_update_kernel" if ("check" in k or "augment" in k) else "ekf_other"] += v
-        dom = max((k for k in shares if "check" in k), key=lambda k: shares[k]) if fam["ekf_update_kernel"] >= max(fam.values()) else \
-            max(shares, key=lambda k: shares[k])
-        roof = {"bound": "hbm", "kernel": ("ekf_update_kernel: " if "ekf_c" in dom or "augment" in dom else "") + dom,
-                "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": round(kern[dom]["gbs"] / peak, 5),
-                "traffic": None, "peak_source": peak_src, "share_of_step": round(shares[dom] / tot, 3),
-                "family_share_of_step": {k: round(v / tot, 3) for k, v in fam.items()},
-                "note": "algorithmic bytes (SURVEY.md 8(d)) / CUDA-event launch time; single-session workload is latency-bound"}
+            fam[k.split(" ")[0]] = fam.get(k.split(" ")[0], 0.0) + v
+        domfam = max(fam, key=lambda k: fam[k])
+        dom = max((k for k in shares if k.startswith(domfam)), key=lambda k: shares[k])
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same launch from the committed ncu --set full capture
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))
+            key = "check+update n=84" if "n=84" in dom else "augment" if "augment" in dom else None
+            traffic = next((int(e["dram_bytes"]) for e in prof["kernels"] if key and key in e["launch"]), None)
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": round(kern[dom]["gbs"] / peak, 5),
+                "traffic": traffic, "peak_source": peak_src, "share_of_step": round(shares[dom] / tot, 3),
+                "kernel_family_share_of_step": {k: round(v / tot, 3) for k, v in fam.items()},
+                "note": "achieved = algorithmic bytes (SURVEY.md 8(d)) / CUDA-event launch time of the largest launch of the kernel with the largest "
+                        "share of the step; one VIO session is a chain of small dependent launches (latency-bound), see DESIGN.md 4 and kernels_batched"}
         for k in kern:
             kern[k]["frac_of_hbm_peak"] = round(kern[k]["gbs"] / peak, 5)
+            kern[k]["share_of_step"] = round(shares[k] / tot, 3)
+        for k in kbatch:
+            kbatch[k]["frac_of_hbm_peak"] = round(kbatch[k]["gbs"] / peak, 5)
         result = {
             "metric": "stereo frames/sec (752x480, 150 tracks)", "value": round(value, 2), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 5), "higher_is_better": True,
@@ -405,7 +460,7 @@ def run_ours(args):
                     "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 5),
                     "note": "host-buffer C ABI: pinned H2D of both frames, synchronous LK and outlier-check results, pose read-back"},
             "gpu_launches": int(launches), "gpu_launches_per_step": round(launches / args.steps, 2),
-            "clocks": clocks, "roofline": roof, "kernels": kern,
+            "clocks": clocks, "roofline": roof, "kernels": kern, "kernels_batched": kbatch,
         }
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(inputs, budget_s=args.cpu_budget)

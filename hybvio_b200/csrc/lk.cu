@@ -25,6 +25,11 @@
 #include "hv_common.cuh"
 #include <float.h>
 
+// search-window region of the next image staged per warp in shared memory: (32 + 2*margin) rows x 48 bytes
+#define LK_REG_M 6
+#define LK_REG_H (32 + 2 * LK_REG_M)
+#define LK_REG_W 48
+
 __device__ __forceinline__ int cv_floor(float v)
 {
     // cvFloor (OCV/core/include/opencv2/core/fast_math.hpp:340-352) with the x86 out-of-range result
@@ -70,6 +75,9 @@ __global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32) hv_lk_kernel(LkLaunch L
     const float2 prevPt = job.prevPts[f];
     float2 outPt = job.useInitial ? job.nextPts[f] : prevPt;
     int status = 1;
+
+    __shared__ __align__(16) uint8_t s_region[LK_WARPS_PER_CTA][LK_REG_H * LK_REG_W];
+    uint8_t* reg = s_region[threadIdx.x >> 5];
 
     int Ipat[WIN];      // I patch column, x32 fixed point (lkpyramid.cpp:441)
     int dIpat[WIN];     // (Ix, Iy) packed as two int16
@@ -145,6 +153,8 @@ __global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32) hv_lk_kernel(LkLaunch L
         // ---- Newton iterations (lkpyramid.cpp:492-681)
         nx = __fsub_rn(nx, halfWin); ny = __fsub_rn(ny, halfWin);
         float pdx = 0.f, pdy = 0.f;
+        bool rgOk = false;          // the staged region belongs to this level's image
+        int rx0 = 0, ry0 = 0;
         for (int j = 0; j < L.maxIter; j++) {
             const int inx = cv_floor(nx), iny = cv_floor(ny);
             if (inx < -WIN || inx >= LJ.w || iny < -WIN || iny >= LJ.h) {
@@ -152,15 +162,42 @@ __global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32) hv_lk_kernel(LkLaunch L
                 break;
             }
             bilin_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
-            const int cxr = hv_reflect101(inx + col, LJ.w);
-            const bool inside = iny >= 0 && iny + WIN < LJ.h;
-            const uint8_t* jb = LJ.gray + cxr;
+            // The 32 x 32 search window is read from a (32 + 2*6)^2 region of the next image staged in shared memory; the
+            // region is (re)filled only when the window leaves it, so an iteration costs shared-memory latency instead
+            // of an L2 round trip. Region bytes are gray[reflect(y)][reflect(x)], i.e. exactly the reference's padded
+            // image, so the samples are unchanged.
+            if (!(rgOk && inx >= rx0 && inx + 32 <= rx0 + LK_REG_W && iny >= ry0 && iny + 32 <= ry0 + LK_REG_H)) {
+                __syncwarp();
+                rx0 = (inx - LK_REG_M) & ~3; ry0 = iny - LK_REG_M;
+                if (rx0 >= 0 && rx0 + LK_REG_W <= LJ.w && ry0 >= 0 && ry0 + LK_REG_H <= LJ.h) {
+                    const uint8_t* g0 = LJ.gray + (size_t)ry0 * LJ.gpitch + rx0;        // 4-byte aligned: gpitch % 128 == 0
+#pragma unroll 6
+                    for (int idx = lane; idx < LK_REG_H * (LK_REG_W / 4); idx += 32) {
+                        const int row = idx / (LK_REG_W / 4), wd = idx - row * (LK_REG_W / 4);
+                        reinterpret_cast<uint32_t*>(reg)[row * (LK_REG_W / 4) + wd] =
+                            __ldg(reinterpret_cast<const uint32_t*>(g0 + (size_t)row * LJ.gpitch) + wd);
+                    }
+                } else {
+                    // region touches the image border (common on the coarse levels): per-lane reflected columns once,
+                    // rows reflected per row, all loads of 4 rows in flight
+                    const int cA = hv_reflect101(rx0 + lane, LJ.w);
+                    const bool hasB = lane + 32 < LK_REG_W;
+                    const int cB = hv_reflect101(rx0 + (hasB ? lane + 32 : lane), LJ.w);
+#pragma unroll 4
+                    for (int row = 0; row < LK_REG_H; row++) {
+                        const uint8_t* grow = LJ.gray + (size_t)hv_reflect101(ry0 + row, LJ.h) * LJ.gpitch;
+                        const uint8_t a0 = __ldg(grow + cA), b0 = __ldg(grow + cB);
+                        reg[row * LK_REG_W + lane] = a0;
+                        if (hasB) reg[row * LK_REG_W + lane + 32] = b0;
+                    }
+                }
+                rgOk = true;
+                __syncwarp();
+            }
+            const uint8_t* rp = reg + (iny - ry0) * LK_REG_W + (inx - rx0) + col;
             int v[WIN + 1];
 #pragma unroll
-            for (int y = 0; y <= WIN; y++) {
-                const int ryr = inside ? iny + y : hv_reflect101(iny + y, LJ.h);
-                v[y] = __ldg(jb + (size_t)ryr * LJ.gpitch);
-            }
+            for (int y = 0; y <= WIN; y++) v[y] = rp[y * LK_REG_W];
             int b1 = 0, b2 = 0;
             int vr0 = __shfl_down_sync(0xffffffffu, v[0], 1);
 #pragma unroll
