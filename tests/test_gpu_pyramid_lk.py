@@ -117,7 +117,8 @@ def test_lk_matches_reference_golden(hv, gold):
 
 @pytest.mark.parametrize("w,h,max_level,n,use_init,seed", [
     (752, 480, 3, 600, False, 1), (752, 480, 3, 600, True, 2), (512, 512, 3, 400, True, 3), (752, 480, 2, 100, True, 8),
-    (751, 479, 2, 200, False, 4), (100, 70, 3, 64, False, 5), (33, 40, 3, 20, True, 6), (64, 64, 0, 30, False, 7)])
+    (751, 479, 2, 200, False, 4), (100, 70, 3, 64, False, 5), (33, 40, 3, 20, True, 6), (64, 64, 0, 30, False, 7),
+    (752, 480, 3, 1000, True, 9)])   # > 640 features: warp-per-feature kernel; <= 640: CTA-per-feature kernel
 def test_lk_bit_exact_vs_oracle_exact_mode_and_close_to_reference_order(hv, oracle_lk, w, h, max_level, n, use_init, seed):
     I, _ = synth.stereo_frame(seed, w, h, seed=seed)
     J, _ = synth.stereo_frame(seed + 1, w, h, seed=seed)
