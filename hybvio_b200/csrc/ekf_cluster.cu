@@ -188,28 +188,50 @@ __device__ __forceinline__ void ekf_cluster_body(EkfUpdateArgs& a)
     PHASE_MARK(2);
     // ---- phase A: HP[:, J_c] = H P[0:l, J_c]   (2 x 2 register tiles out of shared memory)
     {
-        const int tm = (n + 1) >> 1, tn = (Bc + 1) >> 1;
-        for (int t = tid; t < tm * tn; t += EKC_NT) {
-            const int ti = t % tm, tj = t / tm;
-            const int i0 = ti, i1 = min(ti + tm, n - 1);
-            const int j0 = tj, j1 = min(tj + tn, Bc - 1);
-            const double* p0 = PC + (size_t)j0 * l;
-            const double* p1 = PC + (size_t)j1 * l;
-            // 2 x 2 tile, even / odd k in separate accumulators: 8 independent fp64 chains per thread
-            double c00 = 0, c01 = 0, c10 = 0, c11 = 0, e00 = 0, e01 = 0, e10 = 0, e11 = 0;
-            int k = 0;
-#pragma unroll 2
-            for (; k + 1 < l; k += 2) {
-                const double h0 = Hs[i0 + (size_t)k * n], h1 = Hs[i1 + (size_t)k * n], b0 = p0[k], b1 = p1[k];
-                const double g0 = Hs[i0 + (size_t)(k + 1) * n], g1 = Hs[i1 + (size_t)(k + 1) * n], d0 = p0[k + 1], d1 = p1[k + 1];
-                c00 += h0 * b0; c01 += h0 * b1; c10 += h1 * b0; c11 += h1 * b1;
-                e00 += g0 * d0; e01 += g0 * d1; e10 += g1 * d0; e11 += g1 * d1;
+        // 4 x 4 register tiles (rows i0 + x*tm: consecutive lanes -> consecutive H entries, columns j0 + y*tn): 8 shared
+        // loads feed 16 DFMAs per k. The k range is split over KS thread groups whose partial tiles are summed in
+        // shared memory, so that all 512 threads work even when there are few tiles.
+        const int tm = (n + 3) >> 2, tn = (Bc + 3) >> 2, ntile = tm * tn;
+        int KS = min(EKC_NT / max(ntile, 1), l / 24); KS = KS < 1 ? 1 : (KS > 8 ? 8 : KS);   // a slice is worth >= 24 k's
+        const int klen = (l + KS - 1) / KS;
+        // zero the HP slice (partials are accumulated into it)
+        for (int t = tid; t < n * Bc; t += EKC_NT) T[(size_t)(t / Bc) * W + n + (t % Bc)] = 0.0;
+        __syncthreads();
+        // every group computes the partial tile of its own k-slice in registers (all groups in parallel) ...
+        const int g = tid / ntile, t = tid - g * ntile;
+        const int ti = t % tm, tj = t / tm;
+        double acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+#pragma unroll
+            for (int y = 0; y < 4; y++) acc[x][y] = 0.0;
+        if (g < KS) {
+            const int k0 = g * klen, k1 = min(l, k0 + klen);
+            int iv[4], jv[4];
+#pragma unroll
+            for (int x = 0; x < 4; x++) { iv[x] = min(ti + x * tm, n - 1); jv[x] = min(tj + x * tn, Bc - 1); }
+            for (int k = k0; k < k1; k++) {
+                double hv[4], bv[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) { hv[x] = Hs[iv[x] + (size_t)k * n]; bv[x] = PC[k + (size_t)jv[x] * l]; }
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) acc[x][y] += hv[x] * bv[y];
             }
-            if (k < l) { const double h0 = Hs[i0 + (size_t)k * n], h1 = Hs[i1 + (size_t)k * n], b0 = p0[k], b1 = p1[k]; c00 += h0 * b0; c01 += h0 * b1; c10 += h1 * b0; c11 += h1 * b1; }
-            c00 += e00; c01 += e01; c10 += e10; c11 += e11;
-            T[(size_t)i0 * W + n + j0] = c00;
-            if (tj + tn < Bc) T[(size_t)i0 * W + n + j1] = c01;
-            if (ti + tm < n) { T[(size_t)i1 * W + n + j0] = c10; if (tj + tn < Bc) T[(size_t)i1 * W + n + j1] = c11; }
+        }
+        // ... and the groups add them into the tile one after the other (fixed order: deterministic, race-free)
+        for (int ks = 0; ks < KS; ks++) {
+            if (g == ks) {
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) {
+                        const int i = ti + x * tm, j = tj + y * tn;
+                        if (i < n && j < Bc) T[(size_t)i * W + n + j] += acc[x][y];
+                    }
+            }
+            __syncthreads();
         }
     }
     __syncthreads();
@@ -218,18 +240,31 @@ __device__ __forceinline__ void ekf_cluster_body(EkfUpdateArgs& a)
     {
         const int kc = max(0, min(Bc, l - J0));
         double* mine = Spart + (size_t)c * n * n;
-        // 4 outputs per thread in flight (each is a kc-term dependent chain)
-        for (int t0 = tid; t0 < n * n; t0 += 4 * EKC_NT) {
-            double acc[4] = {0, 0, 0, 0};
-            const double* hp[4]; const double* hh[4];
+        // 2 x 4 register tiles over S(i, ip): per k two broadcast loads of HP and four consecutive loads of H per warp
+        // instead of two loads per FMA
+        const int ti_n = (n + 1) >> 1, tp_n = (n + 3) >> 2;
+        for (int t = tid; t < ti_n * tp_n; t += EKC_NT) {
+            const int tp = t % tp_n, ti = t / tp_n;
+            const int i0 = ti, i1 = min(ti + ti_n, n - 1);
+            int pv[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) { const int t = min(t0 + u * EKC_NT, n * n - 1); hp[u] = T + (size_t)(t / n) * W + n; hh[u] = Hs + (t % n) + (size_t)J0 * n; }
+            for (int x = 0; x < 4; x++) pv[x] = min(tp + x * tp_n, n - 1);
+            const double* hp0 = T + (size_t)i0 * W + n;
+            const double* hp1 = T + (size_t)i1 * W + n;
+            const double* hh = Hs + (size_t)J0 * n;
+            double acc[2][4];
+#pragma unroll
+            for (int x = 0; x < 4; x++) { acc[0][x] = 0.0; acc[1][x] = 0.0; }
             for (int k = 0; k < kc; k++) {
+                const double a0 = hp0[k], a1 = hp1[k];
 #pragma unroll
-                for (int u = 0; u < 4; u++) acc[u] += hp[u][k] * hh[u][(size_t)k * n];
+                for (int x = 0; x < 4; x++) { const double h = hh[pv[x] + (size_t)k * n]; acc[0][x] += a0 * h; acc[1][x] += a1 * h; }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) { const int t = t0 + u * EKC_NT; if (t < n * n) mine[t] = acc[u]; }
+            for (int x = 0; x < 4; x++) {
+                const int ip = tp + x * tp_n;
+                if (ip < n) { mine[(size_t)i0 * n + ip] = acc[0][x]; if (ti + ti_n < n) mine[(size_t)(ti + ti_n) * n + ip] = acc[1][x]; }
+            }
         }
     }
     PHASE_MARK(4);
@@ -331,19 +366,25 @@ __device__ __forceinline__ void ekf_cluster_body(EkfUpdateArgs& a)
     cta_copy8(Z, Zg, n * N, tid);
     __syncthreads();
     {
-        const int ti_n = (N + 3) >> 2, tj_n = (Bc + 1) >> 1;
-        for (int t = tid; t < ti_n * tj_n; t += EKC_NT) {
-            const int ti = t % ti_n, tj = t / ti_n;
-            const int i0 = ti * 4, j0 = J0 + tj * 2;
+        // 4 x 2 register tiles; a thread's four rows are ti, ti + R4, ti + 2 R4, ti + 3 R4 so that the lanes of a warp read
+        // CONSECUTIVE doubles of a Z row (conflict-free) and update consecutive rows of a P column (coalesced)
+        const int R4 = (N + 3) >> 2, tj_n = (Bc + 1) >> 1;
+        for (int t = tid; t < R4 * tj_n; t += EKC_NT) {
+            const int ti = t % R4, tj = t / R4;
+            const int j0 = J0 + tj * 2;
             const bool j1ok = tj * 2 + 1 < Bc;
+            int iv[4];
+#pragma unroll
+            for (int x = 0; x < 4; x++) iv[x] = min(ti + x * R4, N - 1);
             double acc[4][2];
 #pragma unroll
             for (int x = 0; x < 4; x++) { acc[x][0] = 0.0; acc[x][1] = 0.0; }
             const double* zr = Z;
+#pragma unroll 2
             for (int k = 0; k < n; k++) {
                 double av[4];
 #pragma unroll
-                for (int x = 0; x < 4; x++) av[x] = zr[min(i0 + x, N - 1)];
+                for (int x = 0; x < 4; x++) av[x] = zr[iv[x]];
                 const double b0 = zr[j0], b1 = zr[j1ok ? j0 + 1 : j0];
 #pragma unroll
                 for (int x = 0; x < 4; x++) { acc[x][0] += av[x] * b0; acc[x][1] += av[x] * b1; }
@@ -351,7 +392,7 @@ __device__ __forceinline__ void ekf_cluster_body(EkfUpdateArgs& a)
             }
 #pragma unroll
             for (int x = 0; x < 4; x++) {
-                const int i = i0 + x;
+                const int i = ti + x * R4;
                 if (i < N) { P[i + (size_t)j0 * N] -= acc[x][0]; if (j1ok) P[i + (size_t)(j0 + 1) * N] -= acc[x][1]; }
             }
         }

@@ -85,7 +85,10 @@ def test_cuda_vs_oracle_live(cuda, oracle_lk, trail, map_size, frames, nlist):
     # 120/160-row updates against 1e8 priors: cond(S) ~ 1e10, so two correct fp64 solvers differ by ~1e-9 in m;
     # that stress case gets 1e-7 / 1e-8, everything else the stated 1e-9 / 1e-9.
     stress = max(nlist) > 100
-    C.check_pair(a, b, frames, nlist, TOL_M=1e-7 if stress else C.TOL_M, TOL_P_REL=1e-8 if stress else C.TOL_P_REL)
+    # CUDA and the C port are two independent non-reference implementations, each gated at 1e-9 against the compiled
+    # reference (golden tests above); against each other the bound is the sum, 2e-9 (the first frames, where random dense
+    # updates collapse the 1e8 trail priors by 5 orders of magnitude, sit at ~1e-9).
+    C.check_pair(a, b, frames, nlist, TOL_M=1e-7 if stress else 2 * C.TOL_M, TOL_P_REL=1e-8 if stress else 2 * C.TOL_P_REL)
     a.close(); b.close()
 
 
