@@ -8,6 +8,8 @@
 // the rank-2 update to its registers. S is symmetric, so the multipliers of row i are read from the published rows
 // (S[k0,i] / p0 and S'[k1,i] / p1): the strictly lower triangle of S is never needed and never updated.
 //
+// Look-ahead: see elim_group.
+//
 // Why this shape: on B200 a dependent DFMA costs 24 cycles, an fp64 division ~70-90, a publish-barrier-read handshake
 // ~100, and at most ~45 DFMA/clk/SM issue (tools/ubench.cu); profiling the one-pivot-per-barrier version showed 60 % of
 // all warp samples waiting at the barrier for the pivot owner's serial chain (profiles/), i.e. the factorisation is
@@ -23,33 +25,50 @@
 // shared scratch (doubles): rows[2 buffers][2 rows][ELIM_ROWBUF] | piv[2 buffers][4] | pivots[96]
 #define ELIM_SMEM_DOUBLES (2 * 2 * ELIM_ROWBUF + 2 * 4 + ELIM_RA * 32)
 
+// Owner-side work for pivot pair (k0, k0+1) held in t[KA][0..1][*] of the calling warp: eliminate k0 from row k1
+// locally, publish both rows, the pivots and their reciprocals into buffer (pp & 1).
+template <int NCJ, int KA>
+__device__ __forceinline__ void elim_publish(double (&t)[ELIM_RA][2][ELIM_CJ], int n, int lane, int pp, double* sh)
+{
+    constexpr int KB = KA;
+    const int k0 = 32 * KA + 2 * pp, k1 = k0 + 1;
+    const bool has1 = k1 < n;
+    double* row0 = sh + (pp & 1) * (2 * ELIM_ROWBUF);
+    double* row1 = row0 + ELIM_ROWBUF;
+    double* pv = sh + 2 * 2 * ELIM_ROWBUF + (pp & 1) * 4;
+    double* s_pivots = sh + 2 * 2 * ELIM_ROWBUF + 8;
+    const double p0 = __shfl_sync(0xffffffffu, t[KA][0][KB], k0 & 31);
+    const double rinv0 = 1.0 / p0;
+    const double f = __shfl_sync(0xffffffffu, t[KA][0][KB], k1 & 31) * rinv0;   // S[k0,k1] / p0
+#pragma unroll
+    for (int bb = KB; bb < NCJ; bb++) {
+        row0[lane + 32 * bb] = t[KA][0][bb];
+        if (bb > KB || lane + 32 * KB > k0) t[KA][1][bb] -= f * t[KA][0][bb];
+        row1[lane + 32 * bb] = t[KA][1][bb];
+    }
+    const double p1 = has1 ? __shfl_sync(0xffffffffu, t[KA][1][KB], k1 & 31) : 1.0;
+    const double rinv1 = 1.0 / p1;                    // all lanes: no divergent section on the critical chain
+    if (lane == 0) { pv[0] = p0; pv[1] = rinv0; pv[2] = p1; pv[3] = rinv1; s_pivots[k0] = p0; if (has1) s_pivots[k1] = p1; }
+}
+
+// One group of 16 pivot pairs. The barrier of pair pp separates "rows of pair pp are published" from "everyone
+// applies them"; the warp that owns pair pp+1 applies them to ITS pivot rows first and immediately runs the
+// owner-side chain of pair pp+1 (look-ahead), so that chain overlaps with the other warps' bulk update instead of
+// preceding it.
 template <int NRA, int NCJ, int KA>
 __device__ __forceinline__ bool elim_group(double (&t)[ELIM_RA][2][ELIM_CJ], int n, int lane, int wrp, double* sh)
 {
     constexpr int KB = KA;                            // pivots 32 KA .. 32 KA + 31 live in column block KA
     double* s_piv = sh + 2 * 2 * ELIM_ROWBUF;
-    double* s_pivots = s_piv + 8;
+    if (32 * KA >= n) return true;
+    if (wrp == 0) elim_publish<NCJ, KA>(t, n, lane, 0, sh);          // first pair of the group: no look-ahead possible
 #pragma unroll 1
     for (int pp = 0; pp < 16; pp++) {
         const int k0 = 32 * KA + 2 * pp, k1 = k0 + 1;
         if (k0 >= n) return true;
-        const bool has1 = k1 < n;
-        double* row0 = sh + (pp & 1) * (2 * ELIM_ROWBUF);
-        double* row1 = row0 + ELIM_ROWBUF;
-        double* pv = s_piv + (pp & 1) * 4;
-        if (wrp == pp) {                              // owner warp: rows k0, k1 are t[KA][0][*], t[KA][1][*]
-            const double p0 = __shfl_sync(0xffffffffu, t[KA][0][KB], k0 & 31);
-            const double rinv0 = 1.0 / p0;
-            const double f = __shfl_sync(0xffffffffu, t[KA][0][KB], k1 & 31) * rinv0;   // S[k0,k1] / p0
-#pragma unroll
-            for (int bb = KB; bb < NCJ; bb++) {
-                row0[lane + 32 * bb] = t[KA][0][bb];
-                if (bb > KB || lane + 32 * KB > k0) t[KA][1][bb] -= f * t[KA][0][bb];
-                row1[lane + 32 * bb] = t[KA][1][bb];
-            }
-            const double p1 = has1 ? __shfl_sync(0xffffffffu, t[KA][1][KB], k1 & 31) : 1.0;
-            if (lane == 0) { pv[0] = p0; pv[1] = rinv0; pv[2] = p1; pv[3] = 1.0 / p1; s_pivots[k0] = p0; if (has1) s_pivots[k1] = p1; }
-        }
+        const double* row0 = sh + (pp & 1) * (2 * ELIM_ROWBUF);
+        const double* row1 = row0 + ELIM_ROWBUF;
+        const double* pv = s_piv + (pp & 1) * 4;
         __syncthreads();
         const double p0 = pv[0], rinv0 = pv[1], p1 = pv[2], rinv1 = pv[3];
         if (!(p0 > 0.0) || !(p1 > 0.0)) return false;
@@ -57,6 +76,7 @@ __device__ __forceinline__ bool elim_group(double (&t)[ELIM_RA][2][ELIM_CJ], int
 #pragma unroll
         for (int bb = KB; bb < NCJ; bb++) { rb0[bb] = row0[lane + 32 * bb]; rb1[bb] = row1[lane + 32 * bb]; }
         const bool diagCol = lane + 32 * KB > k1;     // per lane: column of block KB right of both pivots
+        const bool nextOwner = wrp == pp + 1 && pp + 1 < 16 && k0 + 2 < n;   // warp-uniform
 #pragma unroll
         for (int aa = KA; aa < NRA; aa++) {
             const bool later = aa > KA || wrp > pp;   // warp-uniform: this thread's row pair comes after the pivot pair
@@ -70,6 +90,8 @@ __device__ __forceinline__ bool elim_group(double (&t)[ELIM_RA][2][ELIM_CJ], int
 #pragma unroll
                 for (int bb = KB + 1; bb < NCJ; bb++) t[aa][s][bb] = fma(-g, rb1[bb], fma(-f, rb0[bb], t[aa][s][bb]));
             }
+            // look-ahead: my slot-KA rows are the next pivot pair and are now up to date -> publish them right away
+            if (aa == KA && nextOwner) elim_publish<NCJ, KA>(t, n, lane, pp + 1, sh);
         }
     }
     return true;
