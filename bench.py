@@ -362,7 +362,7 @@ def run_selftest_dist(args):
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps({"selftest": True, "n_gpus": world, "ms": ms, "value": frames_per_second(world, args.steps, ms), "scaling": "weak"}))
+        emit(json.dumps({"selftest": True, "n_gpus": world, "ms": ms, "value": frames_per_second(world, args.steps, ms), "scaling": "weak"}))
 
 
 def run_ours(args):
@@ -469,7 +469,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(result))
+        emit(json.dumps(result))
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -567,7 +567,7 @@ def run_reference(args):
         rs.step()
     dt = time.perf_counter() - t0
     v = args.steps / dt
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "stereo frames/sec (752x480, 150 tracks)", "value": round(v, 2), "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(dt / args.steps * 1e3, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16 fixed-point + f32 (pyramid, LK), f64 (EKF)", "data": "synthetic",
@@ -578,7 +578,26 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Only the final JSON line may reach stdout: libraries (NCCL prints its version banner there) are redirected to
+    stderr for the whole run."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    _REAL_STDOUT.write(line + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
