@@ -8,7 +8,8 @@ LIB := hybvio_b200/libhybvio_b200.so
 CU := $(wildcard $(CSRC)/*.cu)
 OBJS := $(patsubst $(CSRC)/%.cu,$(OBJ)/%.o,$(CU))
 
-all: $(LIB) oracle
+DRV := hybvio_b200/libhv_e2e_driver.so
+all: $(LIB) $(DRV) oracle
 
 $(OBJ)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/hybvio_b200.h
 	@mkdir -p $(OBJ)
@@ -16,6 +17,10 @@ $(OBJ)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) inclu
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker --version-script=$(CSRC)/exports.map
+
+# bench harness: native e2e caller of the C ABI (not part of the product library)
+$(DRV): hybvio_b200/host/e2e_driver.cu include/hybvio_b200.h $(LIB)
+	$(NVCC) $(ARCH) -O2 -std=c++17 -Xcompiler -fPIC -shared -o $@ $< -Lhybvio_b200 -lhybvio_b200 -Xlinker -rpath,'$$ORIGIN'
 
 oracle: oracle/libhv_oracle.so
 oracle/libhv_oracle.so: $(wildcard oracle/*.c)
@@ -25,5 +30,5 @@ ref:
 	$(MAKE) -C oracle/ref_build -f Makefile.lk -j8
 
 clean:
-	rm -rf build $(LIB) oracle/libhv_oracle.so
+	rm -rf build $(LIB) $(DRV) oracle/libhv_oracle.so
 .PHONY: all oracle ref clean

@@ -1,0 +1,65 @@
+// hybvio_b200/host/e2e_driver.cu -- native caller of the C ABI for bench.py's `e2e` number.
+//
+// Plays the role of the reference's Session::process (src/odometry/backend.cpp:716-867) for one stereo frame after the
+// other, entirely through the public host-buffer entry points of include/hybvio_b200.h -- the calls the C++ adapters in
+// this directory make -- so that the end-to-end measurement contains the ABI, the host<->device copies and every
+// synchronisation, but not the Python interpreter of the harness. Not part of the product library
+// (libhv_e2e_driver.so links libhybvio_b200.so).
+#include "../../include/hybvio_b200.h"
+#include <cuda_runtime.h>
+#include <vector>
+
+extern "C" {
+
+typedef struct hv_e2e_frame {
+    const uint8_t* left; const uint8_t* right;   // host (pinned) gray images
+    size_t stride;
+    const float* init_xy;                        // predicted end points for the temporal LK call (n x 2)
+    const hv_ekf_op* ops;                        // the frame's EKF calls, HOST pointers (predicts, checks/updates, symmetrise, augment)
+    int nops;
+} hv_e2e_frame;
+
+// pyr[0..1] = previous left/right, pyr[2..3] = scratch for the current frame (swapped every frame).
+// pose_out: 20 doubles (inertial state after the last frame). elapsed_ms: device time of the whole loop (CUDA events
+// on the tracker stream, taken after both streams are idle).
+int hv_e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const float* points, int n, const hv_e2e_frame* frames,
+               int nframes, double* pose_out, float* elapsed_ms)
+{
+    std::vector<float> nxt(2 * (size_t)n), nxt2(2 * (size_t)n);
+    std::vector<uint8_t> st(n);
+    std::vector<int32_t> ts(n);
+    std::vector<int> vu(64);
+    std::vector<double> chi2(64), m(hv_ekf_state_dim(ekf));
+    hv_pyr* p[4] = {pyr[0], pyr[1], pyr[2], pyr[3]};
+    cudaStream_t s = (cudaStream_t)hv_ctx_stream(trk);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    hv_ctx_sync(trk); hv_ctx_sync(ekf_ctx);
+    cudaEventRecord(e0, s);
+    int rc = HV_OK;
+    for (int k = 0; k < nframes && rc == HV_OK; k++) {
+        const hv_e2e_frame& f = frames[k];
+        hv_pyr* cur[2] = {p[2], p[3]};
+        const uint8_t* img[2] = {f.left, f.right};
+        const size_t strides[2] = {f.stride, f.stride};
+        rc = hv_pyr_build_batch(cur, img, strides, 2, 0);                                   // H2D + one kernel
+        if (rc != HV_OK) break;
+        for (int i = 0; i < 2 * n; i++) nxt[i] = f.init_xy[i];
+        rc = hv_lk_track(trk, p[0], cur[0], points, nxt.data(), st.data(), ts.data(), n, 1, 20, 0.03, 1e-3);   // sync
+        if (rc != HV_OK) break;
+        rc = hv_lk_track(trk, cur[0], cur[1], nxt.data(), nxt2.data(), st.data(), ts.data(), n, 0, 20, 0.03, 1e-3);
+        if (rc != HV_OK) break;
+        if ((int)vu.size() < f.nops) { vu.resize(f.nops); chi2.resize(f.nops); }
+        rc = hv_ekf_run_host(ekf, f.ops, f.nops, vu.data(), chi2.data(), m.data());          // every check is a round trip
+        hv_pyr* t0 = p[0]; hv_pyr* t1 = p[1]; p[0] = p[2]; p[1] = p[3]; p[2] = t0; p[3] = t1;
+    }
+    hv_ctx_sync(ekf_ctx);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(elapsed_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (int i = 0; i < 4; i++) pyr[i] = p[i];
+    if (pose_out) for (int i = 0; i < 20; i++) pose_out[i] = m[i];
+    return rc;
+}
+}
