@@ -22,6 +22,15 @@ $(LIB): $(OBJS)
 $(DRV): hybvio_b200/host/e2e_driver.cu include/hybvio_b200.h $(LIB)
 	$(NVCC) $(ARCH) -O2 -std=c++17 -Xcompiler -fPIC -shared -o $@ $< -Lhybvio_b200 -lhybvio_b200 -Xlinker -rpath,'$$ORIGIN'
 
+# instrumented copy (globaltimer phase marks in the EKF kernels) for tools/ekf_phases.py; never loaded by tests / bench
+TOBJ := build/obj_timing
+TLIB := hybvio_b200/libhybvio_b200_timing.so
+$(TOBJ)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/hybvio_b200.h
+	@mkdir -p $(TOBJ)
+	$(NVCC) $(NVFLAGS) -DHV_EKF_TIMING $(if $(filter lk,$*),--fmad=false,) -c $< -o $@ 2> $(TOBJ)/$*.ptxas.log || (cat $(TOBJ)/$*.ptxas.log; false)
+timing: $(patsubst $(CSRC)/%.cu,$(TOBJ)/%.o,$(CU))
+	$(NVCC) $(ARCH) -shared -o $(TLIB) $^ -Xlinker --version-script=$(CSRC)/exports.map
+
 oracle: oracle/libhv_oracle.so
 oracle/libhv_oracle.so: $(wildcard oracle/*.c)
 	gcc -O2 -ffp-contract=off -fPIC -shared -o $@ $^ -lm
@@ -31,4 +40,4 @@ ref:
 
 clean:
 	rm -rf build $(LIB) $(DRV) oracle/libhv_oracle.so
-.PHONY: all oracle ref clean
+.PHONY: all oracle ref clean timing

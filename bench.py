@@ -244,10 +244,13 @@ class Session:
         P = (ctypes.c_void_p * 4)(*[p.h for p in self.pyr])
         pose = (ctypes.c_double * 20)()
         ms = ctypes.c_float(0.0)
-        drv.hv_e2e_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
-                                   ctypes.POINTER(Frame), ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
-        capi.check(drv.hv_e2e_run(self.ctx.h, self.ctx_b.h, P, self.ekf.h, self.inp.points.ctypes.data, NFEAT, frames, nframes, pose, ctypes.byref(ms)),
-                   "hv_e2e_run")
+        phases = (ctypes.c_double * 4)()
+        drv.hv_e2e_run_phases.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                          ctypes.POINTER(Frame), ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float),
+                                          ctypes.POINTER(ctypes.c_double)]
+        capi.check(drv.hv_e2e_run_phases(self.ctx.h, self.ctx_b.h, P, self.ekf.h, self.inp.points.ctypes.data, NFEAT, frames, nframes, pose,
+                                         ctypes.byref(ms), phases), "hv_e2e_run")
+        self.e2e_host_phase_us = {k: round(phases[i] / nframes, 2) for i, k in enumerate(("pyramids_submit", "lk_temporal", "lk_stereo", "ekf_ops"))}
         by_handle = {p.h.value: p for p in self.pyr}
         self.pyr = [by_handle[P[i]] for i in range(4)]
         return float(ms.value), np.array(pose)
@@ -526,6 +529,7 @@ def run_ours(args):
                        "ekf_healthy_after_run": healthy},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": Session.H2D_BYTES, "d2h_bytes_per_step": Session.D2H_BYTES,
                     "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 5),
+                    "host_phase_us_per_step": sess.e2e_host_phase_us,
                     "python_harness": {"value": round(frames_per_second(world, e2e_steps, ms_e2e_py), 2), "ms_per_step": round(ms_e2e_py / e2e_steps, 5)},
                     "note": "host-buffer C ABI driven by a native caller (host/e2e_driver.cu): pinned H2D of both frames, synchronous LK results, every check+update and the batched checks return to the host, pose read-back"},
             "gpu_launches": int(launches), "gpu_launches_per_step": round(launches / args.steps, 2),

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhybvio_b200.so")
+# HV_LIB_PATH: tools/ only (e.g. the -DHV_EKF_TIMING build used by tools/ekf_phases.py)
+LIB_PATH = os.environ.get("HV_LIB_PATH") or os.path.join(_HERE, "libhybvio_b200.so")
 
 c_int, c_double, c_void_p, c_size_t = ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t
 

@@ -365,7 +365,7 @@ __device__ __forceinline__ void quat2rmat_d(const double* q, double* R /*row-maj
 // applying every dydx in turn (fp64 differences are association-order rounding, ~1e-16 relative).
 // A dependent fp64 operation costs 24 cycles on B200, so the ~600-flop Jacobian sequence is cut into barrier-separated
 // stages whose independent pieces run in different warps / lanes.
-__global__ void __launch_bounds__(EKF_NT) ekf_predict_kernel(EkfPredictArgs a)
+__global__ void __launch_bounds__(EKF_NT) ekf_predict_v1_kernel(EkfPredictArgs a)
 {
     __shared__ double s_dydx[400], s_dydq[240], s_Q[144], s_P00[400], s_T1[400], s_G1[240], s_acc[400];
     __shared__ double s_m[EKF_INER], s_A[16], s_qn[4], s_Tx[3], s_B[12];
@@ -575,6 +575,16 @@ __global__ void __launch_bounds__(EKF_NT) ekf_predict_kernel(EkfPredictArgs a)
     PMARK(4);
 }
 
+// Current predict kernel: parallel-over-samples Jacobians + short sequential chains (ekf_predict.cuh). The kernel above
+// (one sample after the other, ~9 barriers per sample) is kept this round as an A/B switch: HV_EKF_PREDICT_V1=1.
+#define EKF_PMARK(i) PMARK(i)
+#include "ekf_predict.cuh"
+__global__ void __launch_bounds__(EKF_NT) ekf_predict_kernel(EkfPredictArgs a)
+{
+    extern __shared__ __align__(16) double ekf_predict_dyn[];
+    ekf_predict_body(a, ekf_predict_dyn);
+}
+
 // ------------------------------------------------------------------------------------------------ elementwise / structural
 __device__ __forceinline__ void quat_to_rot(const double* q /*w,x,y,z*/, double* R /*row-major*/)
 {
@@ -772,7 +782,15 @@ cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s)
 }
 cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s)
 {
-    ekf_predict_kernel<<<1, EKF_NT, 0, s>>>(a);
+    static const bool v1 = getenv("HV_EKF_PREDICT_V1") != nullptr;
+    if (v1) { ekf_predict_v1_kernel<<<1, EKF_NT, 0, s>>>(a); return cudaGetLastError(); }
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(ekf_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ekf_predict_smem_bytes(EKF_MAX_PREDICT));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    ekf_predict_kernel<<<1, EKF_NT, ekf_predict_smem_bytes(a.count), s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t ekf_launch_elementwise(const EkfEwArgs& a, cudaStream_t s)

@@ -19,7 +19,9 @@
 // is 361 KB).
 #include "hv_common.cuh"
 
+#ifndef PYR_NT
 #define PYR_NT 256
+#endif
 
 #define PYR_MAX_BATCH 60
 struct PyrBuildList {

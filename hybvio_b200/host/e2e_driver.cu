@@ -7,6 +7,7 @@
 // (libhv_e2e_driver.so links libhybvio_b200.so).
 #include "../../include/hybvio_b200.h"
 #include <cuda_runtime.h>
+#include <chrono>
 #include <vector>
 
 extern "C" {
@@ -22,9 +23,15 @@ typedef struct hv_e2e_frame {
 // pyr[0..1] = previous left/right, pyr[2..3] = scratch for the current frame (swapped every frame).
 // pose_out: 20 doubles (inertial state after the last frame). elapsed_ms: device time of the whole loop (CUDA events
 // on the tracker stream, taken after both streams are idle).
-int hv_e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const float* points, int n, const hv_e2e_frame* frames,
-               int nframes, double* pose_out, float* elapsed_ms)
+//
+// host_phase_us (optional, 4 doubles): host wall time summed over the frames of {pyramid submit, temporal LK, stereo LK,
+// EKF op list} -- where the end-to-end time goes (the calls are synchronous, so host time == critical path).
+static int e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const float* points, int n, const hv_e2e_frame* frames,
+                   int nframes, double* pose_out, float* elapsed_ms, double* host_phase_us)
 {
+    using clk = std::chrono::steady_clock;
+    auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    double ph[4] = {0, 0, 0, 0};
     std::vector<float> nxt(2 * (size_t)n), nxt2(2 * (size_t)n);
     std::vector<uint8_t> st(n);
     std::vector<int32_t> ts(n);
@@ -42,16 +49,22 @@ int hv_e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
         hv_pyr* cur[2] = {p[2], p[3]};
         const uint8_t* img[2] = {f.left, f.right};
         const size_t strides[2] = {f.stride, f.stride};
+        const auto t0 = clk::now();
         rc = hv_pyr_build_batch(cur, img, strides, 2, 0);                                   // H2D + one kernel
         if (rc != HV_OK) break;
         for (int i = 0; i < 2 * n; i++) nxt[i] = f.init_xy[i];
+        const auto t1 = clk::now();
         rc = hv_lk_track(trk, p[0], cur[0], points, nxt.data(), st.data(), ts.data(), n, 1, 20, 0.03, 1e-3);   // sync
         if (rc != HV_OK) break;
+        const auto t2 = clk::now();
         rc = hv_lk_track(trk, cur[0], cur[1], nxt.data(), nxt2.data(), st.data(), ts.data(), n, 0, 20, 0.03, 1e-3);
         if (rc != HV_OK) break;
+        const auto t3 = clk::now();
         if ((int)vu.size() < f.nops) { vu.resize(f.nops); chi2.resize(f.nops); }
         rc = hv_ekf_run_host(ekf, f.ops, f.nops, vu.data(), chi2.data(), m.data());          // every check is a round trip
-        hv_pyr* t0 = p[0]; hv_pyr* t1 = p[1]; p[0] = p[2]; p[1] = p[3]; p[2] = t0; p[3] = t1;
+        const auto t4 = clk::now();
+        ph[0] += us(t0, t1); ph[1] += us(t1, t2); ph[2] += us(t2, t3); ph[3] += us(t3, t4);
+        hv_pyr* q0 = p[0]; hv_pyr* q1 = p[1]; p[0] = p[2]; p[1] = p[3]; p[2] = q0; p[3] = q1;
     }
     hv_ctx_sync(ekf_ctx);
     cudaEventRecord(e1, s);
@@ -60,6 +73,19 @@ int hv_e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     for (int i = 0; i < 4; i++) pyr[i] = p[i];
     if (pose_out) for (int i = 0; i < 20; i++) pose_out[i] = m[i];
+    if (host_phase_us) for (int i = 0; i < 4; i++) host_phase_us[i] = ph[i];
     return rc;
+}
+
+int hv_e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const float* points, int n, const hv_e2e_frame* frames,
+               int nframes, double* pose_out, float* elapsed_ms)
+{
+    return e2e_run(trk, ekf_ctx, pyr, ekf, points, n, frames, nframes, pose_out, elapsed_ms, nullptr);
+}
+
+int hv_e2e_run_phases(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const float* points, int n, const hv_e2e_frame* frames,
+                      int nframes, double* pose_out, float* elapsed_ms, double* host_phase_us)
+{
+    return e2e_run(trk, ekf_ctx, pyr, ekf, points, n, frames, nframes, pose_out, elapsed_ms, host_phase_us);
 }
 }

@@ -1,0 +1,77 @@
+// tools/emu/cuda_emu.h -- a very small host emulation of the CUDA execution model, for testing kernel LOGIC without a
+// GPU (this container has none; GPU minutes are scarce). Test infrastructure only -- never part of the product.
+//
+// Every CUDA thread of ONE CTA is an OS thread; __syncthreads / __syncwarp are std::barrier, full-warp shuffles go
+// through a per-warp exchange buffer. `__shared__` becomes `static` (one CTA at a time per process; cluster kernels are
+// emulated with one forked process per CTA and MAP_SHARED global memory, see emu_cluster.h). Data races between
+// barriers are NOT detected; what this catches is indexing, staging, ownership and protocol mistakes.
+#pragma once
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __cluster_dims__(...)
+#define __restrict__
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+struct emu_dim3 { unsigned x = 0, y = 0, z = 0; };
+inline thread_local emu_dim3 threadIdx, blockIdx;
+inline emu_dim3 blockDim, gridDim;
+struct alignas(16) double2 { double x, y; };
+
+namespace emu {
+struct Cta {
+    int nthreads, nwarps;
+    std::barrier<> bar;
+    std::vector<std::unique_ptr<std::barrier<>>> wbar;
+    std::vector<double> xch;     // nwarps x 32 exchange slots
+    explicit Cta(int nt) : nthreads(nt), nwarps((nt + 31) / 32), bar(nt), xch((size_t)((nt + 31) / 32) * 32)
+    {
+        for (int w = 0; w < nwarps; w++) wbar.emplace_back(new std::barrier<>(std::min(32, nt - 32 * w)));
+    }
+};
+inline Cta* cta = nullptr;
+
+template <class F>
+void launch_cta(int nthreads, unsigned bx, F&& body)
+{
+    Cta c(nthreads);
+    cta = &c;
+    blockDim.x = nthreads; blockDim.y = blockDim.z = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([&, t] { threadIdx.x = t; threadIdx.y = threadIdx.z = 0; blockIdx.x = bx; blockIdx.y = blockIdx.z = 0; body(); });
+    for (auto& x : th) x.join();
+    cta = nullptr;
+}
+}  // namespace emu
+
+inline void __syncthreads() { emu::cta->bar.arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::cta->wbar[threadIdx.x >> 5]->arrive_and_wait(); }
+// full-warp shuffle: EVERY lane of the warp must call it (what the kernels written for the emulator do)
+inline double __shfl_sync(unsigned, double v, int src)
+{
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* slot = emu::cta->xch.data() + (size_t)w * 32;
+    slot[lane] = v;
+    emu::cta->wbar[w]->arrive_and_wait();
+    const double r = slot[src & 31];
+    emu::cta->wbar[w]->arrive_and_wait();
+    return r;
+}
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+template <class T> inline T min(T a, T b) { return a < b ? a : b; }
+template <class T> inline T max(T a, T b) { return a > b ? a : b; }
+using std::fma;

@@ -1,0 +1,5 @@
+// stub of <cuda_runtime.h> for the host emulation build (tools/emu)
+#pragma once
+#include <cstddef>
+typedef void* cudaStream_t;
+typedef int cudaError_t;
