@@ -7,7 +7,7 @@
 A "step" is ONE stereo frame of BASELINE config 2 (EuRoC V1_02-shaped: 752x480 stereo, 150 features, 4-level pyramid,
 31x31 window, EKF state dimension 160) pushed through the whole hot path of one VIO session:
     2 pyramids (one launch) -> LK prev-left -> left with predicted initial flow -> LK left -> right
-    -> 10 x EKF predict (200 Hz IMU at 20 fps) -> 20 visual-track outlier checks, the 5 designated ones followed by
+    -> 10 x (EKF predict + normalizeQuaternions(true)) (200 Hz IMU at 20 fps; backend.cpp:734-735) -> 20 visual-track outlier checks, the 5 designated ones followed by
        their update (n = 8/20/40/84 rows) -> maintainPositiveSemiDefinite -> pose augmentation.
 Frames of one session are strictly sequential, so one stream per GPU is a latency-bound workload; --gpus N runs N
 independent sessions, one per GPU (BASELINE config 3; no data-path collective, NCCL only for the start barrier and
@@ -36,6 +36,7 @@ W, H, NFEAT, WIN, MAXLEVEL, TRAIL = 752, 480, 150, 31, 3, 20
 VISUAL_R = 0.05
 N_ROWS = (8, 20, 40, 84)            # rows of the visual measurement models, cycled
 CHECKS, UPDATES, PREDICTS = 20, 5, 10
+IMU_OPS = 2 * PREDICTS               # every predict is followed by normalizeQuaternions(true) (src/odometry/backend.cpp:734-735)
 POOL_FRAMES = int(os.environ.get("HV_BENCH_POOL_FRAMES", "128"))   # stereo pairs in the frame pool: 128 * 2 * 361 KB = 92 MB
 POOL_EKF = 64                       # frames of EKF inputs: 64 * 736 KB = 47 MB  (together 139 MB > 126 MB of L2)
 PYR_BYTES = 2_397_000               # algorithmic bytes per image
@@ -132,22 +133,23 @@ class Session:
             self.d_res = torch.zeros(2, dtype=torch.float64, device=self.dev)
         # per-frame EKF op lists (hv_ekf_run_*: one crossing of the language boundary per frame)
         self.ops_dev, self.ops_host = [], []
-        nops = PREDICTS + CHECKS + 2
+        nops = IMU_OPS + CHECKS + 2
         for fr in range(POOL_EKF):
             od, oh = (capi.EkfOp * nops)(), (capi.EkfOp * nops)()
             for ops, base in ((od, self.d_ekf_pool[fr].data_ptr()), (oh, inputs.ekf_pool[fr].ctypes.data)):
                 for s_ in range(PREDICTS):
                     u = inputs.imu[fr * PREDICTS + s_]
-                    ops[s_].kind = capi.OP_PREDICT
+                    ops[2 * s_].kind = capi.OP_PREDICT
                     for q in range(3):
-                        ops[s_].gyro[q] = u[q]; ops[s_].acc[q] = u[3 + q]
+                        ops[2 * s_].gyro[q] = u[q]; ops[2 * s_].acc[q] = u[3 + q]
+                    ops[2 * s_ + 1].kind, ops[2 * s_ + 1].index = capi.OP_NORMALIZE, 1     # normalizeQuaternions(true)
                 for c, (o, n, l) in enumerate(inputs.ekf_off):
-                    op = ops[PREDICTS + c]
+                    op = ops[IMU_OPS + c]
                     op.kind, op.n, op.l, op.mode, op.r, op.rmse_thr = capi.OP_VISUAL, n, l, (2 if c < UPDATES else 0), VISUAL_R, -1.0
                     op.H, op.f, op.y = base + 8 * o, base + 8 * (o + n * l), base + 8 * (o + n * l + n)
-                ops[PREDICTS + CHECKS].kind = capi.OP_SYMMETRIZE
-                ops[PREDICTS + CHECKS + 1].kind = capi.OP_AUGMENT
-                ops[PREDICTS + CHECKS + 1].index = -1
+                ops[IMU_OPS + CHECKS].kind = capi.OP_SYMMETRIZE
+                ops[IMU_OPS + CHECKS + 1].kind = capi.OP_AUGMENT
+                ops[IMU_OPS + CHECKS + 1].index = -1
             self.ops_dev.append(od); self.ops_host.append(oh)
         self.nops = nops
         self.h_frames = inputs.frames.cpu().pin_memory()
@@ -176,10 +178,11 @@ class Session:
         ops = self.ops_dev[fr]
         for s in range(PREDICTS):
             self.t += 0.005
-            ops[s].t = self.t
+            ops[2 * s].t = self.t
         if not self.overlap:
             A.wait_stream(B); B.wait_stream(A)
-        self.ekf.run_device(ops, PREDICTS)                                                         # B: IMU burst
+        self.ekf.run_device(ops, IMU_OPS)                                                          # B: IMU burst (queued) ...
+        self.ekf.flush()                                                                           # ... issued now: overlaps the tracker
         A.wait_event(self.ev_ekf)                                                                  # flow predictor needs EKF(k-1)
         init = self.d_init[0, j - 1] if j > self.prev_j else self.d_init[1, j]
         with self.torch.cuda.stream(A):
@@ -188,7 +191,7 @@ class Session:
         ctx.lk_track_device(cur[0], cur[1], self.d_next, self.d_next2, self.d_status, self.d_ts, NFEAT, False)
         self.ev_lk.record(A)
         B.wait_event(self.ev_lk)                                                                   # visual updates need the tracks
-        self.ekf.run_device(ctypes_slice(ops, PREDICTS, self.nops - PREDICTS), self.nops - PREDICTS)
+        self.ekf.run_device(ctypes_slice(ops, IMU_OPS, self.nops - IMU_OPS), self.nops - IMU_OPS)
         self.ev_ekf.record(B)
         self.pyr = self.pyr[2:4] + self.pyr[0:2]
         self.prev_j = j
@@ -207,7 +210,7 @@ class Session:
         ops = self.ops_host[fr]
         for s in range(PREDICTS):
             self.t += 0.005
-            ops[s].t = self.t
+            ops[2 * s].t = self.t
         # 20 synchronous round trips (every check returns its VuOutlierStatus to the host) + state read-back
         st, chi2, m = self.ekf.run_host(ops, self.nops, want_m=True)
         self.pyr = self.pyr[2:4] + self.pyr[0:2]
@@ -235,7 +238,7 @@ class Session:
             ctypes.memmove(ops, src, ctypes.sizeof(ops))
             for s_ in range(PREDICTS):
                 self.t += 0.005
-                ops[s_].t = self.t
+                ops[2 * s_].t = self.t
             keep += [init, ops]
             fr = frames[i]
             fr.left, fr.right, fr.stride = self.h_frames[j, 0].data_ptr(), self.h_frames[j, 1].data_ptr(), W
@@ -330,26 +333,28 @@ def time_kernels(sess, reps=40):
         ops = sess.ops_dev[i % POOL_EKF]
         for s_ in range(PREDICTS):
             sess.t += 0.005
-            ops[s_].t = sess.t
-        ekf.run_device(ops, PREDICTS)
+            ops[2 * s_].t = sess.t
+        ekf.run_device(ops, IMU_OPS)
+        ekf.flush()
     B = sess.stream_b
-    timed(f"ekf_predict_kernel ({PREDICTS} samples fused)", pred, PREDICTS * 2 * 8 * (40 * N - 400), stream=B)
+    timed(f"ekf_predict_kernel ({PREDICTS} samples + normalisations, one launch)", pred, PREDICTS * 2 * 8 * (40 * N - 400), stream=B)
     for c in range(UPDATES):
         n, l = ekf_rows(c)
 
         def upd(i, c=c):
             ops = sess.ops_dev[i % POOL_EKF]
-            ekf.run_device(ctypes_slice(ops, PREDICTS + c, 1), 1)
+            ekf.run_device(ctypes_slice(ops, IMU_OPS + c, 1), 1)
         timed(f"ekf_update_cluster_kernel check+update #{c} (n={n},l={l})", upd, 2 * 8 * N * N + 8 * n * l, stream=B)
         ekf.symmetrize(); ekf.augment(-1)
 
     def chk(i):
         ops = sess.ops_dev[i % POOL_EKF]
-        ekf.run_device(ctypes_slice(ops, PREDICTS + UPDATES, CHECKS - UPDATES), CHECKS - UPDATES)
+        ekf.run_device(ctypes_slice(ops, IMU_OPS + UPDATES, CHECKS - UPDATES), CHECKS - UPDATES)
     timed(f"ekf_check_batch_cluster_kernel ({CHECKS - UPDATES} tracks, one cluster each)", chk,
           sum(8 * N * N + 8 * n * l for n, l in (ekf_rows(c) for c in range(UPDATES, CHECKS))), stream=B)
-    timed("ekf_ew_kernel symmetrize", lambda i: ekf.symmetrize(), 2 * 8 * N * N, stream=B)
-    timed("ekf_update_cluster_kernel augment", lambda i: ekf.augment(-1), 2 * 8 * N * N, stream=B)
+    def sym_aug(i):
+        ekf.symmetrize(); ekf.augment(-1)
+    timed("ekf_update_cluster_kernel symmetrise + augment (one launch)", sym_aug, 2 * 8 * N * N, stream=B)
     return out
 
 
@@ -520,7 +525,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16 fixed-point + f32 (pyramid, LK), f64 (EKF)", "data": "synthetic",
             "config": {"workload": "BASELINE config 2: EuRoC V1_02-shaped stereo 752x480, 150 features, 4-level pyramid, win 31, "
-                                   "EKF N=160 (trail 20); per frame 2 pyramids + 2 LK calls + 10 predict + 20 checks (5 with update) + "
+                                   "EKF N=160 (trail 20); per frame 2 pyramids + 2 LK calls + 10 x (predict + normalizeQuaternions(true)) + 20 checks (5 with update) + "
                                    "symmetrise + augment; one independent session per GPU",
                        "sessions_per_gpu": 1,
                        "streams": "2 per session (tracker / EKF) with event dependencies: LK(k) after EKF(k-1), visual updates(k) after LK(k)",
@@ -593,6 +598,7 @@ class RefSession:
             self.t += 0.005
             u = inp.imu[fr * PREDICTS + s]
             self.ekf.predict(self.t, u[:3], u[3:])
+            self.ekf.normalize_quaternions(True)
         row = inp.ekf_pool[fr]
         for c, (o, n, l) in enumerate(inp.ekf_off):
             Hm = row[o:o + n * l].reshape((n, l), order="F")

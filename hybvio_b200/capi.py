@@ -96,7 +96,7 @@ def _bind_ekf(lib):
     lib.hv_ekf_destroy.argtypes = [c_void_p]
     lib.hv_ekf_clone.argtypes = [c_void_p, ctypes.POINTER(c_void_p)]
     for name in ("hv_ekf_state_dim", "hv_ekf_pose_count", "hv_ekf_was_stationary", "hv_ekf_unaugment", "hv_ekf_symmetrize",
-                 "hv_ekf_condition_on_last_pose", "hv_ekf_lock_biases", "hv_ekf_update_zupt_initialization"):
+                 "hv_ekf_condition_on_last_pose", "hv_ekf_lock_biases", "hv_ekf_update_zupt_initialization", "hv_ekf_flush"):
         getattr(lib, name).argtypes = [c_void_p]
     lib.hv_ekf_platform_time.argtypes = [c_void_p]
     lib.hv_ekf_platform_time.restype = c_double
@@ -124,6 +124,7 @@ def _bind_ekf(lib):
                                                ctypes.POINTER(c_int), dp, c_void_p]
     lib.hv_ekf_visual_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p]
     lib.hv_ekf_augment.argtypes = [c_void_p, c_int]
+    lib.hv_ekf_set_imu_batching.argtypes = [c_void_p, c_int]
     lib.hv_ekf_run_device.argtypes = [c_void_p, ctypes.POINTER(EkfOp), c_int]
     lib.hv_ekf_run_host.argtypes = [c_void_p, ctypes.POINTER(EkfOp), c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double), c_void_p]
     lib.hv_ekf_normalize_quaternions.argtypes = [c_void_p, c_int]
@@ -366,6 +367,8 @@ class Ekf:
     def augment(self, drop=-1): check(self.lib.hv_ekf_augment(self.h, drop), "hv_ekf_augment")
     def unaugment(self): check(self.lib.hv_ekf_unaugment(self.h), "hv_ekf_unaugment")
     def symmetrize(self): check(self.lib.hv_ekf_symmetrize(self.h), "hv_ekf_symmetrize")
+    def flush(self): check(self.lib.hv_ekf_flush(self.h), "hv_ekf_flush")
+    def set_imu_batching(self, max_samples): check(self.lib.hv_ekf_set_imu_batching(self.h, int(max_samples)), "hv_ekf_set_imu_batching")
     def normalize_quaternions(self, only_current=False): check(self.lib.hv_ekf_normalize_quaternions(self.h, 1 if only_current else 0), "hv_ekf_normalize_quaternions")
     def translate_to(self, pos): check(self.lib.hv_ekf_translate_to(self.h, _ptr(_dd(pos))), "hv_ekf_translate_to")
     def transform_to(self, pos, q, i=-1): check(self.lib.hv_ekf_transform_to(self.h, _ptr(_dd(pos)), _ptr(_dd(q)), i), "hv_ekf_transform_to")

@@ -75,6 +75,7 @@ struct EkfUpdateArgs {
     double augNoisePos, augNoiseOri;   // visAugQ diagonal (noiseScale applied)
     double defaultSpeed;  // EKF_OP_PSEUDO_VELOCITY
     int useGlobalWork;    // tableau in b.work instead of shared memory
+    int symFirst;         // EKF_OP_AUGMENT (cluster kernel): a deferred maintainPositiveSemiDefinite() is applied while P is read
 };
 
 // Independent outlier checks against the same (m, P): one launch, one 8-CTA cluster per measurement
@@ -94,6 +95,7 @@ struct EkfPredictSample {
     double xg[3], xa[3];
     double baaDecay, bgaDecay;      // exp(-dt * rev) or 1 when the random walk is off (ekf.cpp:443-448)
     double qBaa, qBga;              // >= 0: value of the Q drift-block diagonal for this dt (ekf.cpp:397-412); < 0: keep
+    int normAfter, pad;             // normalizeQuaternions(true) follows this sample (backend.cpp:734-735): folded into the chain
 };
 // `count` consecutive IMU samples in one launch (the 10 samples between two frames at 200 Hz / 20 fps)
 struct EkfPredictArgs {

@@ -26,6 +26,13 @@ struct hv_ekf {
     double prevSampleT = -1.0, firstSampleT = -1.0;
     bool firstSample = true;
     std::vector<double> chi2inv95;
+    // Deferred work (issued by the next call that needs the state, or hv_ekf_flush): the IMU samples of consecutive
+    // predict() calls -- with the normalizeQuaternions(true) that follows each of them in the reference loop
+    // (src/odometry/backend.cpp:734-735) -- become ONE launch; a maintainPositiveSemiDefinite() directly followed by the
+    // pose augmentation (backend.cpp:1267 -> 805) is applied inside the augmentation kernel.
+    EkfPredictArgs pend;
+    bool pendSym = false;
+    int imuBatch = EKF_MAX_PREDICT;
 };
 
 // ---- chi-square 95% quantiles (the reference hard-codes the table odometry/util.hpp:23; recomputed here by
@@ -68,8 +75,12 @@ static int ekf_check(const hv_ekf* e, const char* who)
     return HV_OK;
 }
 
-#define EKF_ENTER(e, who)                              \
+extern "C" { static int flush_pending(hv_ekf* e); }
+// EKF_ENTER_LAZY: entry points that only extend the deferred queue; EKF_ENTER: everything else issues the queue first
+#define EKF_ENTER_LAZY(e, who)                         \
     do { int rc_ = ekf_check(e, who); if (rc_ != HV_OK) return rc_; HV_CUDA(cudaSetDevice((e)->ctx->device)); } while (0)
+#define EKF_ENTER(e, who)                              \
+    do { EKF_ENTER_LAZY(e, who); int rc2_ = flush_pending(e); if (rc2_ != HV_OK) return rc2_; } while (0)
 
 static int launch_update(hv_ekf* e, EkfUpdateArgs& a)
 {
@@ -118,6 +129,7 @@ void hv_ekf_default_params(hv_ekf_params* p)
 static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
 {
     hv_ekf* e = new hv_ekf;
+    memset(&e->pend, 0, sizeof(e->pend));
     e->ctx = c; e->prm = *prm;
     e->trail = prm->camera_trail_length; e->mapDim = prm->hybrid_map_size * EKF_MAP_POINT;
     e->N = EKF_INER + e->trail * EKF_POSE + e->mapDim;
@@ -196,7 +208,9 @@ int hv_ekf_clone(const hv_ekf* src, hv_ekf** out)
     if (!src || !out) { hv_set_error("hv_ekf_clone: NULL"); return HV_ERR_INVALID; }
     HV_CUDA(cudaSetDevice(src->ctx->device));
     hv_ekf* e = nullptr;
-    int rc = ekf_alloc(src->ctx, &src->prm, &e);
+    int rc = flush_pending(const_cast<hv_ekf*>(src));     // deferred work belongs to the state being copied
+    if (rc != HV_OK) return rc;
+    rc = ekf_alloc(src->ctx, &src->prm, &e);
     if (rc != HV_OK) return rc;
     const size_t N = src->N;
     cudaStream_t s = src->ctx->stream;
@@ -207,7 +221,7 @@ int hv_ekf_clone(const hv_ekf* src, hv_ekf** out)
     e->augmentCount = src->augmentCount; e->augmentTimes = src->augmentTimes;
     e->time = src->time; e->ZUPTtime = src->ZUPTtime; e->ZRUPTtime = src->ZRUPTtime; e->initZUPTtime = src->initZUPTtime;
     e->wasStationary = src->wasStationary; e->prevSampleT = src->prevSampleT; e->firstSampleT = src->firstSampleT;
-    e->firstSample = src->firstSample; e->chi2inv95 = src->chi2inv95;
+    e->firstSample = src->firstSample; e->chi2inv95 = src->chi2inv95; e->imuBatch = src->imuBatch;
     *out = e;
     return HV_OK;
 }
@@ -325,7 +339,7 @@ static void predict_bookkeep(hv_ekf* e, double t, const double xg[3], const doub
     EkfPredictSample& s = a.s[a.count++];
     s.dt = dt;
     for (int i = 0; i < 3; i++) { s.xg[i] = xg[i]; s.xa[i] = xa[i]; }
-    s.qBaa = -1.0; s.qBga = -1.0; s.baaDecay = 1.0; s.bgaDecay = 1.0;
+    s.qBaa = -1.0; s.qBga = -1.0; s.baaDecay = 1.0; s.bgaDecay = 1.0; s.normAfter = 0; s.pad = 0;
     if (e->prm.noise_process_baa > 0.0) {  // ekf.cpp:397-404, 443-445
         const double th = e->prm.noise_process_baa_rev;
         s.qBaa = e->noiseScale * pow2(e->prm.noise_process_baa);
@@ -350,12 +364,44 @@ static int predict_launch(hv_ekf* e, EkfPredictArgs& a)
     return HV_OK;
 }
 
+static int flush_predicts(hv_ekf* e) { return predict_launch(e, e->pend); }
+static int flush_sym(hv_ekf* e)
+{
+    if (!e->pendSym) return HV_OK;
+    e->pendSym = false;
+    return launch_ew(e, EKF_EW_SYMMETRIZE);
+}
+// At most one kind of work is pending at a time (predict() issues a pending symmetrisation first, symmetrize() issues
+// pending samples first), so the order of the reference's calls is preserved.
+static int flush_pending(hv_ekf* e)
+{
+    int rc = flush_predicts(e);
+    if (rc != HV_OK) return rc;
+    return flush_sym(e);
+}
+
 int hv_ekf_predict(hv_ekf* e, double t, const double xg[3], const double xa[3])
 {
-    EKF_ENTER(e, "hv_ekf_predict");
-    EkfPredictArgs a; a.count = 0;
-    predict_bookkeep(e, t, xg, xa, a);
-    return predict_launch(e, a);
+    EKF_ENTER_LAZY(e, "hv_ekf_predict");
+    int rc = flush_sym(e);
+    if (rc != HV_OK) return rc;
+    predict_bookkeep(e, t, xg, xa, e->pend);
+    if (e->pend.count >= e->imuBatch) return flush_predicts(e);
+    return HV_OK;
+}
+
+int hv_ekf_flush(hv_ekf* e)
+{
+    EKF_ENTER(e, "hv_ekf_flush");
+    return HV_OK;
+}
+
+int hv_ekf_set_imu_batching(hv_ekf* e, int max_samples)
+{
+    EKF_ENTER(e, "hv_ekf_set_imu_batching");
+    if (max_samples < 1 || max_samples > EKF_MAX_PREDICT) { hv_set_error("hv_ekf_set_imu_batching: 1..%d", EKF_MAX_PREDICT); return HV_ERR_INVALID; }
+    e->imuBatch = max_samples;
+    return HV_OK;
 }
 
 int hv_ekf_update_zupt(hv_ekf* e, double r)
@@ -500,10 +546,14 @@ int hv_ekf_visual_device(hv_ekf* e, const double* dH, int n, int l, const double
 
 int hv_ekf_augment(hv_ekf* e, int discarded)
 {
-    EKF_ENTER(e, "hv_ekf_augment");
+    EKF_ENTER_LAZY(e, "hv_ekf_augment");
+    int rcf = flush_predicts(e);
+    if (rcf != HV_OK) return rcf;
     if (discarded == -1) discarded = e->trail - 1;               // ekf.cpp:849
     if (discarded < 0 || discarded >= e->trail) { hv_set_error("hv_ekf_augment: pose index %d out of range", discarded); return HV_ERR_INVALID; }
     EkfUpdateArgs a; fill_small(a, EKF_OP_AUGMENT, EKF_POSE, EKF_CAM + EKF_POSE, e->prm.augment_r * e->noiseScale);
+    a.symFirst = e->pendSym ? 1 : 0;                             // a deferred symmetrisation rides along (cluster kernel)
+    e->pendSym = false;
     a.dropIdx = discarded;
     a.augNoisePos = pow2(e->prm.noise_initial_pos_trail) * e->noiseScale;
     a.augNoiseOri = pow2(e->prm.noise_initial_ori_trail) * e->noiseScale;
@@ -527,8 +577,28 @@ int hv_ekf_unaugment(hv_ekf* e)
     return HV_OK;
 }
 
-int hv_ekf_symmetrize(hv_ekf* e) { EKF_ENTER(e, "hv_ekf_symmetrize"); return launch_ew(e, EKF_EW_SYMMETRIZE); }
-int hv_ekf_normalize_quaternions(hv_ekf* e, int onlyCurrent) { EKF_ENTER(e, "hv_ekf_normalize_quaternions"); return launch_ew(e, EKF_EW_NORMALIZE, onlyCurrent ? 1 : 0); }
+int hv_ekf_symmetrize(hv_ekf* e)
+{
+    EKF_ENTER(e, "hv_ekf_symmetrize");
+    // deferred: rides along with a directly following augmentation, otherwise issued by the next call. The single-CTA
+    // A/B path (HV_EKF_SINGLE_CTA) has no fused variant.
+    static const bool eager = getenv("HV_EKF_SINGLE_CTA") != nullptr || getenv("HV_EKF_EAGER") != nullptr;
+    if (eager) return launch_ew(e, EKF_EW_SYMMETRIZE);
+    e->pendSym = true;
+    return HV_OK;
+}
+int hv_ekf_normalize_quaternions(hv_ekf* e, int onlyCurrent)
+{
+    EKF_ENTER_LAZY(e, "hv_ekf_normalize_quaternions");
+    static const bool v1 = getenv("HV_EKF_PREDICT_V1") != nullptr;
+    if (onlyCurrent && !v1 && e->pend.count > 0 && !e->pend.s[e->pend.count - 1].normAfter) {
+        e->pend.s[e->pend.count - 1].normAfter = 1;              // folded into the deferred predict launch
+        return HV_OK;
+    }
+    int rc = flush_pending(e);
+    if (rc != HV_OK) return rc;
+    return launch_ew(e, EKF_EW_NORMALIZE, onlyCurrent ? 1 : 0);
+}
 int hv_ekf_translate_to(hv_ekf* e, const double pos[3]) { EKF_ENTER(e, "hv_ekf_translate_to"); return launch_ew(e, EKF_EW_TRANSLATE, 0, pos, 3); }
 
 int hv_ekf_transform_to(hv_ekf* e, const double pos[3], const double q[4], int poseIndex)
@@ -614,25 +684,13 @@ static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vu
     for (int i = 0; i < nops; i++) {
         const hv_ekf_op& o = ops[i];
         int rc = HV_OK;
+        if (o.kind == HV_EKF_OP_VISUAL) { rc = flush_pending(e); if (rc != HV_OK) return rc; }   // the other kinds enter through their own entry points
         if (!noBatch && batchable_check(e, o)) {
             int cnt = 1;
             while (i + cnt < nops && cnt < EKF_MAX_BATCH && batchable_check(e, ops[i + cnt])) cnt++;
             rc = flush_checks(e, ops, i, cnt, host, vuStatus, chi2);
             if (rc != HV_OK) return rc;
             i += cnt - 1;
-            continue;
-        }
-        if (!noBatch && o.kind == HV_EKF_OP_PREDICT) {
-            // consecutive IMU samples are one launch (see ekf_predict_kernel)
-            EkfPredictArgs pa; pa.count = 0;
-            int j = i;
-            for (; j < nops && ops[j].kind == HV_EKF_OP_PREDICT; j++) {
-                predict_bookkeep(e, ops[j].t, ops[j].gyro, ops[j].acc, pa);
-                if (pa.count == EKF_MAX_PREDICT) { rc = predict_launch(e, pa); if (rc != HV_OK) return rc; }
-            }
-            rc = predict_launch(e, pa);
-            if (rc != HV_OK) return rc;
-            i = j - 1;
             continue;
         }
         switch (o.kind) {

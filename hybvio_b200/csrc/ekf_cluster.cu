@@ -104,6 +104,8 @@ __device__ __forceinline__ void ekf_cluster_body(EkfUpdateArgs& a)
             const int i = idx % N, j = J0 + idx / N;
             const int si = ck_aug_src(i, drop), sj = ck_aug_src(j, drop);
             double v = (si < 0 || sj < 0) ? 0.0 : P[si + (size_t)sj * N];
+            // deferred maintainPositiveSemiDefinite (ekf.cpp:1059-1067): 0.5 (P + P') evaluated while the shift reads P
+            if (a.symFirst && si >= 0 && sj >= 0 && si != sj) v = 0.5 * (v + P[sj + (size_t)si * N]);
             if (i == j && i >= EKF_CAM && i < EKF_CAM + EKF_POSE) v += (i - EKF_CAM) < 3 ? a.augNoisePos : a.augNoiseOri;
             P2[i + (size_t)j * N] = v;
         }

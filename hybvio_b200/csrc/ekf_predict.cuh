@@ -2,7 +2,8 @@
 //
 // predict() of odometry::EKF (src/odometry/ekf.cpp:320-514) applied to `count` (<= 16) consecutive IMU samples in ONE
 // launch of one CTA. What is sequential in the reference is only
-//   * the quaternion chain            q_{k+1} = A_k q_k                      (4x4 mat-vec per sample),
+//   * the quaternion chain            q_{k+1} = A_k q_k [/ |.|]               (4x4 mat-vec per sample; the
+//                                     normalizeQuaternions(true) the reference calls after every predict is folded in),
 //   * velocity / position sums        v_{k+1} = v_k + dv_k, p_{k+1} = p_k + v_k dt_k,
 //   * the 20x20 covariance recursion  P00 <- D_k P00 D_k' + W_k,  Dacc <- D_k Dacc   (two barriers per sample);
 // everything else of a sample depends on the state only through quantities that are known up front:
@@ -102,6 +103,13 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
             double v = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) v += A[r * 4 + j] * __shfl_sync(0xffffffffu, q, j);
+            if (a.s[k].normAfter) {               // normalizeQuaternions(true) right after this sample (ekf.cpp:1024-1032)
+                const double sq = v * v;
+                const double z0 = __shfl_sync(0xffffffffu, sq, 0), z1 = __shfl_sync(0xffffffffu, sq, 1);
+                const double z2 = __shfl_sync(0xffffffffu, sq, 2), z3 = __shfl_sync(0xffffffffu, sq, 3);
+                const double z = (z0 + z2) + (z1 + z3);
+                if (z > 0.0) v /= sqrt(z);
+            }
             q = v;
         }
         if (lane < 4) s_q[cnt * 4 + lane] = q;

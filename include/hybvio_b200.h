@@ -150,6 +150,13 @@ int hv_ekf_initialize_orientation(hv_ekf* ekf, const double acc[3]);          /*
 /* predict (ekf.cpp:320-514): mean propagation, Jacobians and the structured covariance update all run on the
  * device; the host only keeps the sample-time bookkeeping (first sample / dt <= 0 are no-ops). Asynchronous. */
 int hv_ekf_predict(hv_ekf* ekf, double t, const double gyro[3], const double acc[3]);
+/* IMU samples are DEFERRED: consecutive predict() calls -- each optionally followed by normalize_quaternions(ekf, 1), as in
+ * the reference's sample loop (src/odometry/backend.cpp:734-735) -- are queued on the host (up to max_samples, default and
+ * maximum 16) and issued as ONE launch by the next call that needs the state, or by hv_ekf_flush. Results are identical
+ * to issuing every sample on its own (max_samples = 1). Likewise hv_ekf_symmetrize directly followed by hv_ekf_augment
+ * (backend.cpp:1267 -> 805) is one launch. */
+int hv_ekf_flush(hv_ekf* ekf);
+int hv_ekf_set_imu_batching(hv_ekf* ekf, int max_samples);
 
 /* The fixed-H updates (ekf.cpp:573-677); rate limits and early-outs as in the reference. Asynchronous. */
 int hv_ekf_update_zupt(hv_ekf* ekf, double r);

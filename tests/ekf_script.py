@@ -32,7 +32,7 @@ def visual_measurement(rng, n, N, scale_v):
 
 
 def run_frames(ekf, frames=6, n_list=(8, 20, 40), seed=3, fused=False, snapshots=None, checks=None,
-               updates_per_frame=3, checks_per_frame=6, t0=0.0, frame0=0):
+               updates_per_frame=3, checks_per_frame=6, t0=0.0, frame0=0, norm_each=False):
     """The per-frame pattern of Session::process (src/odometry/backend.cpp:716-867): IMU predicts, optional
     un-augmentation of a non-keyframe, outlier checks + visual updates, symmetrise, augmentation."""
     rng = np.random.RandomState(seed)
@@ -49,7 +49,10 @@ def run_frames(ekf, frames=6, n_list=(8, 20, 40), seed=3, fused=False, snapshots
             t += 0.005
             g, a = imu_sample(irng, k)
             ekf.predict(t, g, a)
-        ekf.normalize_quaternions(True)
+            if norm_each:                        # the reference's sample loop (backend.cpp:734-735)
+                ekf.normalize_quaternions(True)
+        if not norm_each:
+            ekf.normalize_quaternions(True)
         if fr % 4 == 3 and ekf.pose_count() > 1:
             ekf.unaugment()                      # non-keyframe (backend.cpp:793-796)
         done = 0

@@ -1,0 +1,19 @@
+"""CPU test: the REAL body of the fused predict kernel (hybvio_b200/csrc/ekf_predict.cuh) compiled for the host thread
+emulator (tools/emu) and compared with the C oracle -- catches indexing / staging / protocol mistakes without a GPU.
+The GPU parity tests (test_gpu_ekf.py) remain the authority on the compiled sm_100a code."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_predict_kernel_body_on_host_emulator(tmp_path):
+    exe = str(tmp_path / "emu_predict")
+    obj = str(tmp_path / "orc_ekf.o")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", "hv_oracle_ekf.c"), "-o", obj])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tools", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tools", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tools", "emu", "emu_predict.cpp"), obj, "-lm", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count(" ok") == 3

@@ -198,3 +198,68 @@ def test_reference_catch2_suite_against_cuda_ekf():
     r = subprocess.run([exe], cwd=os.path.join(root, "oracle", "_ref"), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "All tests passed" in r.stdout and "3 test cases" in r.stdout, r.stdout[-500:]
+
+
+def test_deferred_imu_queue_matches_sample_by_sample(cuda, oracle_lk):
+    """hv_ekf_predict queues IMU samples (with the normalizeQuaternions(true) that follows each one in the reference's
+    sample loop, backend.cpp:734-735) and issues them as one launch. Same script with batching 16 / 4 / 1 (= one launch
+    per sample, then a separate normalisation launch) and on the C oracle, which applies every call eagerly."""
+    from oracle import ekf_oracle
+    p = C.params_with(default_params, 20)
+    runs = {}
+    for batch in (16, 4, 1):
+        e = cuda(p)
+        e.set_imu_batching(batch)
+        snaps = []
+        ekf_script.run_frames(e, frames=4, n_list=(8, 20, 40), snapshots=snaps, norm_each=True)
+        runs[batch] = snaps
+        e.close()
+    o = ekf_oracle.OracleEKF(p)
+    so = []
+    ekf_script.run_frames(o, frames=4, n_list=(8, 20, 40), snapshots=so, norm_each=True)
+    o.close()
+    for batch, snaps in runs.items():
+        for (ma, Pa), (mb, Pb) in zip(snaps, so):
+            assert np.abs(ma - mb).max() < C.TOL_M, batch
+            assert ekf_script.rel_err(Pa, Pb) < C.TOL_P_REL, batch
+    for (ma, Pa), (mb, Pb) in zip(runs[16], runs[1]):       # batching itself: association-order rounding only
+        assert np.abs(ma - mb).max() < 1e-12 and ekf_script.rel_err(Pa, Pb) < 1e-12
+
+
+def test_deferred_work_is_flushed_by_every_reader(cuda):
+    """Queued samples / a deferred symmetrisation must be visible to whatever reads the state next."""
+    p = C.params_with(default_params, 6)
+    a, b = cuda(p), cuda(p)
+    b.set_imu_batching(1)
+    acc = np.array([0.1, 0.2, 9.8])
+    for e in (a, b):
+        e.initialize_orientation(acc)
+    t = 0.0
+    for k in range(7):
+        t += 0.005
+        for e in (a, b):
+            e.predict(t, [0.01, -0.02, 0.2], acc)
+            e.normalize_quaternions(True)
+    m20a, P20a = a.download_inertial()                # reader 1: inertial download
+    m20b, P20b = b.download_inertial()
+    assert np.abs(m20a - m20b).max() < 1e-12 and ekf_script.rel_err(P20a, P20b) < 1e-12
+    for e in (a, b):
+        e.predict(t + 0.005, [0.0, 0.0, 0.1], acc)
+    ca, cb = a.clone(), b.clone()                     # reader 2: clone
+    assert np.abs(ca.download()[0] - cb.download()[0]).max() < 1e-12
+    assert np.abs(a.get_dydx() - b.get_dydx()).max() < 1e-12      # reader 3: getDydx
+    # symmetrize followed by something that is NOT an augmentation must still happen
+    for e in (a, b):
+        P = e.download()[1]; P[3, 9] += 1e-3; e.upload(None, P)
+        e.symmetrize()
+    Pa, Pb = a.download()[1], b.download()[1]
+    assert np.array_equal(Pa, Pa.T) and np.array_equal(Pa, Pb)
+    # ... and symmetrize -> augment (fused) equals symmetrize, flush, augment
+    for e in (a, b):
+        P = e.download()[1]; P[2, 11] -= 2e-3; e.upload(None, P)
+    a.symmetrize(); a.augment(-1)
+    b.symmetrize(); b.flush(); b.augment(-1)
+    (ma, Pa), (mb, Pb) = a.download(), b.download()
+    assert np.array_equal(ma, mb) and np.array_equal(Pa, Pb)
+    for e in (a, b, ca, cb):
+        e.close()

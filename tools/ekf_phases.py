@@ -31,8 +31,13 @@ for n in (8, 20, 40, 84):
         print(line)
     ekf.symmetrize(); ekf.augment(-1)
 
+t = 1.0
 for rep in range(3):
-    ekf.predict(1.0 + 0.005 * (rep + 1), [0.01, 0.02, 0.2], [0.1, 0.2, 9.8])
+    for k in range(10):
+        t += 0.005
+        ekf.predict(t, [0.01, 0.02, 0.2], [0.1, 0.2, 9.8]); ekf.normalize_quaternions(True)
+    ekf.flush()
 w = np.zeros(32); lib.hv_ekf_debug_result_words(ekf.h, w.ctypes.data)
-ts = w[8:13]
-print("predict: loads %.1f us | jacobian stages %.1f | strips %.1f | P00 %.1f | total %.1f" % tuple([(ts[i + 1] - ts[i]) / 1e3 for i in range(4)] + [(ts[4] - ts[0]) / 1e3]))
+ts = w[8:14]
+print("predict x10 (one launch): loads %.1f us | A_k + quaternion chain %.1f | Jacobians + W_k %.1f | covariance recursion %.1f | write-back + strips %.1f | total %.1f"
+      % tuple([(ts[i + 1] - ts[i]) / 1e3 for i in range(5)] + [(ts[5] - ts[0]) / 1e3]))

@@ -15,6 +15,7 @@ void orc_ekf_download(const orc_ekf*, double*, double*);
 void orc_ekf_set_first_sample_time(orc_ekf*, double);
 void orc_ekf_predict(orc_ekf*, double, const double*, const double*);
 void orc_ekf_get_dydx(const orc_ekf*, double*);
+void orc_ekf_normalize_quaternions(orc_ekf*, int);
 int orc_ekf_state_dim(const orc_ekf*);
 }
 
@@ -58,10 +59,11 @@ int main()
             double xg[3] = {0.05 * rnd(), 0.05 * rnd(), 0.2 + 0.05 * rnd()}, xa[3] = {0.3 * rnd(), 0.2 * rnd(), 9.8 + 0.2 * rnd()};
             EkfPredictSample& s = a.s[k];
             s.dt = dt; for (int i = 0; i < 3; i++) { s.xg[i] = xg[i]; s.xa[i] = xa[i]; }
-            s.qBaa = s.qBga = -1.0; s.baaDecay = s.bgaDecay = 1.0;
+            s.qBaa = s.qBga = -1.0; s.baaDecay = s.bgaDecay = 1.0; s.normAfter = (trial >= 1 && k != 1) ? 1 : 0; s.pad = 0;
             if (prm.v[13] > 0) { const double th = prm.v[14]; s.qBaa = ns * prm.v[13] * prm.v[13]; if (th > 0) s.qBaa *= (1 - std::exp(-2 * dt * th)) / (2 * th); s.baaDecay = std::exp(-dt * th); }
             if (prm.v[15] > 0) { const double th = prm.v[16]; s.qBga = ns * prm.v[15] * prm.v[15]; if (th > 0) s.qBga *= (1 - std::exp(-2 * dt * th)) / (2 * th); s.bgaDecay = std::exp(-dt * th); }
             orc_ekf_predict(o, t, xg, xa);
+            if (s.normAfter) orc_ekf_normalize_quaternions(o, 1);
         }
         std::vector<double> dyn(ekf_predict_smem_bytes(cnt) / 8);
         emu::launch_cta(EKF_NT, 0, [&] { ekf_predict_body(a, dyn.data()); });
