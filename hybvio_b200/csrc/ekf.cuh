@@ -127,5 +127,8 @@ cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s);
 size_t ekf_cluster_smem_bytes(int n, int l, int N, bool joseph);
 cudaError_t ekf_launch_update_cluster(const EkfUpdateArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_check_batch(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s);
+bool ekf_cluster2_fits(int n, int l, int N, bool joseph);
+cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s);
+cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s);
 cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_elementwise(const EkfEwArgs& a, cudaStream_t s);

@@ -656,7 +656,10 @@ static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, b
     }
     if (host) HV_CUDA(cudaMemcpyAsync(e->d_in, e->h_pin, off * sizeof(double), cudaMemcpyHostToDevice, s));
     a.b = e->b; a.noiseScale = e->noiseScale; a.useGlobalWork = 0;
-    HV_CUDA(ekf_launch_check_batch(a, b, s));
+    static const bool v1 = getenv("HV_EKF_CLUSTER_V1") != nullptr;
+    bool fits2 = !v1;
+    for (int i = 0; i < count && fits2; i++) fits2 = ekf_cluster2_fits(b.it[i].n, b.it[i].l, e->N, false);
+    HV_CUDA(fits2 ? ekf_launch_check_batch2(a, b, s) : ekf_launch_check_batch(a, b, s));
     e->ctx->launches++;
     if (host) {
         double* hout = e->h_pin + e->inDoubles + e->N + 8;

@@ -1,0 +1,85 @@
+// hybvio_b200/csrc/ekf_cluster2.cu -- kernels and launchers of the second-generation cluster update (ekf_cluster2.cuh):
+// P column blocks resident in shared memory, all inter-CTA exchanges through distributed shared memory.
+#include <cooperative_groups.h>
+#include <math.h>
+#include <stdlib.h>
+namespace cg = cooperative_groups;
+
+#ifdef HV_EKF_TIMING
+// phase timestamps (globaltimer, ns) into res[8 + i] (tools/ekf_phases.py)
+#define EK2_PHASE(i) do { if (c == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.b.res[8 + (i)] = (double)t_; } } while (0)
+#endif
+#include "ekf_cluster2.cuh"
+
+__global__ void __launch_bounds__(EK2_NT) ekf_update_cluster2_kernel(EkfUpdateArgs a)
+{
+    extern __shared__ __align__(16) double ek2_sm[];
+    ek2_body(a, ek2_sm, cg::this_cluster());
+}
+
+// Batched outlier checks: cluster i works on measurement i against the same state (read-only), with its own result words.
+__global__ void __launch_bounds__(EK2_NT) ekf_check_batch_cluster2_kernel(EkfUpdateArgs a, EkfCheckBatch b)
+{
+    extern __shared__ __align__(16) double ek2_sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int inst = blockIdx.x / (int)cluster.num_blocks();
+    const EkfCheckItem& it = b.it[inst];
+    a.H = it.H; a.f = it.f; a.y = it.y; a.n = it.n; a.l = it.l;
+    a.Rdiag = it.Rdiag; a.chi2Thr = it.chi2Thr; a.rmseThr = it.rmseThr; a.skipChi2 = it.skipChi2;
+    a.b.res += (size_t)EKF_RES_STRIDE * inst;
+    ek2_body(a, ek2_sm, cluster);
+}
+
+#define EK2_STATIC_SMEM (sizeof(double) * (2 + ELIM_SMEM_DOUBLES + EK2_MAXN) + 256)
+#define EK2_SMEM_LIMIT (227 * 1024)
+
+// Cluster size: 8 (portable) unless HV_EKF_CLUSTER=16 asks for the non-portable size (A/B switch this round).
+static int ek2_cluster_size()
+{
+    static const int C = [] { const char* s = getenv("HV_EKF_CLUSTER"); const int v = s ? atoi(s) : 8; return (v == 16 || v == 4 || v == 2) ? v : 8; }();
+    return C;
+}
+
+bool ekf_cluster2_fits(int n, int l, int N, bool joseph)
+{
+    return N <= EK2_MAXN && ek2_smem_bytes(n, l, N, joseph, ek2_cluster_size()) + EK2_STATIC_SMEM <= EK2_SMEM_LIMIT;
+}
+
+template <class K, class... Args>
+static cudaError_t ek2_launch(K kernel, int C, int nclusters, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C * nclusters); cfg.blockDim = dim3(EK2_NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = C; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+template <class K>
+static cudaError_t ek2_prepare(K kernel, int C)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EK2_SMEM_LIMIT - EK2_STATIC_SMEM));
+    if (e != cudaSuccess) return e;
+    if (C > 8) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    return e;
+}
+
+cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s)
+{
+    const int C = ek2_cluster_size();
+    static bool ready = false;
+    if (!ready) { cudaError_t e = ek2_prepare(ekf_update_cluster2_kernel, C); if (e != cudaSuccess) return e; ready = true; }
+    const size_t smem = ek2_smem_bytes(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT, C);
+    return ek2_launch(ekf_update_cluster2_kernel, C, 1, smem, s, a);
+}
+
+cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s)
+{
+    const int C = ek2_cluster_size();
+    static bool ready = false;
+    if (!ready) { cudaError_t e = ek2_prepare(ekf_check_batch_cluster2_kernel, C); if (e != cudaSuccess) return e; ready = true; }
+    size_t smem = 0;
+    for (int i = 0; i < b.count; i++) { const size_t v = ek2_smem_bytes(b.it[i].n, b.it[i].l, a.b.N, false, C); if (v > smem) smem = v; }
+    return ek2_launch(ekf_check_batch_cluster2_kernel, C, b.count, smem, s, a, b);
+}

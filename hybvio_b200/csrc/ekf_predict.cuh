@@ -52,7 +52,7 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
 {
     __shared__ double s_Q[144], s_P00[400], s_T1[400];
     __shared__ __align__(16) double s_acc[400];
-    __shared__ double s_m[EKF_INER], s_q[(EKF_MAX_PREDICT + 1) * 4], s_mfinal[EKF_INER];
+    __shared__ double s_m[EKF_INER], s_q[(EKF_MAX_PREDICT + 1) * 4], s_qn[EKF_MAX_PREDICT * 4], s_mfinal[EKF_INER];
     const int tid = threadIdx.x, N = a.b.N, cnt = a.count;
     const int lane = tid & 31, wrp = tid >> 5;
     double* P = a.b.P;
@@ -103,6 +103,7 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
             double v = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) v += A[r * 4 + j] * __shfl_sync(0xffffffffu, q, j);
+            if (lane < 4) s_qn[k * 4 + lane] = v;   // what predict() itself leaves in the state: the Jacobians use this one
             if (a.s[k].normAfter) {               // normalizeQuaternions(true) right after this sample (ekf.cpp:1024-1032)
                 const double sq = v * v;
                 const double z0 = __shfl_sync(0xffffffffu, sq, 0), z1 = __shfl_sync(0xffffffffu, sq, 1);
@@ -126,7 +127,7 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
         const double* Tx = smp + PS_TX;
         const double dt = S.dt;
         const double* qo = s_q + k * 4;           // orientation before the sample
-        const double* qn = s_q + (k + 1) * 4;     // and after
+        const double* qn = s_qn + k * 4;          // and after (before a normalizeQuaternions that may follow)
         if (lane < 3) {
             // d(orientation)/d(gyro noise) columns A dS_j q (ekf.cpp:470-476) and their negatives (ekf.cpp:492)
             const int j = lane;

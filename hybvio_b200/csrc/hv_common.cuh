@@ -10,7 +10,7 @@
 // sides, OCV/video/src/lkpyramid.cpp:761-808; here the reflect-101 / zero border is applied by index
 // arithmetic in the LK kernel instead, which saves 0.79 MB of writes per 752x480 image).
 struct HvLevel {
-    uint8_t* gray;    // w x h, row pitch gpitch bytes (multiple of 128)
+    uint8_t* gray;    // w x h, row pitch gpitch bytes (multiple of 4; level 0: w when w % 4 == 0, else / coarser levels: multiple of 128)
     short2*  deriv;   // w x h (Ix, Iy) Scharr x32, row pitch dpitch elements (multiple of 32 => 128 B)
     int w, h;
     int gpitch;

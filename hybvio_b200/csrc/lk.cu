@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32) hv_lk_kernel(LkLaunch L
                 __syncwarp();
                 rx0 = (inx - LK_REG_M) & ~3; ry0 = iny - LK_REG_M;
                 if (rx0 >= 0 && rx0 + LK_REG_W <= LJ.w && ry0 >= 0 && ry0 + LK_REG_H <= LJ.h) {
-                    const uint8_t* g0 = LJ.gray + (size_t)ry0 * LJ.gpitch + rx0;        // 4-byte aligned: gpitch % 128 == 0
+                    const uint8_t* g0 = LJ.gray + (size_t)ry0 * LJ.gpitch + rx0;        // 4-byte aligned: gpitch % 4 == 0
 #pragma unroll 6
                     for (int idx = lane; idx < LK_REG_H * (LK_REG_W / 4); idx += 32) {
                         const int row = idx / (LK_REG_W / 4), wd = idx - row * (LK_REG_W / 4);

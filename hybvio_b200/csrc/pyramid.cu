@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(PYR_NT) hv_pyr_fused_kernel(PyrBuildList list)
         }
     }
 
-    // ---- stage the level-0 region with 32-bit loads (gpitch is a multiple of 128, rows are 4-byte aligned)
+    // ---- stage the level-0 region with 32-bit loads (gpitch is a multiple of 4: rows are 4-byte aligned)
     const uint8_t* ext = list.src[blockIdx.z];
     {
         const HvLevel& L0 = P.lv[0];

@@ -44,14 +44,23 @@ static int e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, cons
     hv_ctx_sync(trk); hv_ctx_sync(ekf_ctx);
     cudaEventRecord(e0, s);
     int rc = HV_OK;
+    // Frame k+1 is handed to the tracker as soon as frame k's optical flow is done (the reference creates the
+    // tracker::Image on the frame-input thread, src/api/api.cpp:602-605): its H2D copy and pyramid build run on the tracker
+    // stream while the EKF stream works on frame k. The pyramids of frame k-1 are free at that point and take frame k+1.
+    auto submit = [&](int k, hv_pyr* const* dst) {
+        const uint8_t* img[2] = {frames[k].left, frames[k].right};
+        const size_t strides[2] = {frames[k].stride, frames[k].stride};
+        return hv_pyr_build_batch(dst, img, strides, 2, 0);                                 // H2D + one kernel, asynchronous
+    };
+    {
+        const auto t0 = clk::now();
+        hv_pyr* cur[2] = {p[2], p[3]};
+        if (nframes > 0) rc = submit(0, cur);
+        ph[0] += us(t0, clk::now());
+    }
     for (int k = 0; k < nframes && rc == HV_OK; k++) {
         const hv_e2e_frame& f = frames[k];
         hv_pyr* cur[2] = {p[2], p[3]};
-        const uint8_t* img[2] = {f.left, f.right};
-        const size_t strides[2] = {f.stride, f.stride};
-        const auto t0 = clk::now();
-        rc = hv_pyr_build_batch(cur, img, strides, 2, 0);                                   // H2D + one kernel
-        if (rc != HV_OK) break;
         for (int i = 0; i < 2 * n; i++) nxt[i] = f.init_xy[i];
         const auto t1 = clk::now();
         rc = hv_lk_track(trk, p[0], cur[0], points, nxt.data(), st.data(), ts.data(), n, 1, 20, 0.03, 1e-3);   // sync
@@ -60,10 +69,12 @@ static int e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, cons
         rc = hv_lk_track(trk, cur[0], cur[1], nxt.data(), nxt2.data(), st.data(), ts.data(), n, 0, 20, 0.03, 1e-3);
         if (rc != HV_OK) break;
         const auto t3 = clk::now();
+        if (k + 1 < nframes) { hv_pyr* nxtp[2] = {p[0], p[1]}; rc = submit(k + 1, nxtp); if (rc != HV_OK) break; }
+        const auto t3b = clk::now();
         if ((int)vu.size() < f.nops) { vu.resize(f.nops); chi2.resize(f.nops); }
         rc = hv_ekf_run_host(ekf, f.ops, f.nops, vu.data(), chi2.data(), m.data());          // every check is a round trip
         const auto t4 = clk::now();
-        ph[0] += us(t0, t1); ph[1] += us(t1, t2); ph[2] += us(t2, t3); ph[3] += us(t3, t4);
+        ph[0] += us(t3, t3b); ph[1] += us(t1, t2); ph[2] += us(t2, t3); ph[3] += us(t3b, t4);
         hv_pyr* q0 = p[0]; hv_pyr* q1 = p[1]; p[0] = p[2]; p[1] = p[3]; p[2] = q0; p[3] = q1;
     }
     hv_ctx_sync(ekf_ctx);

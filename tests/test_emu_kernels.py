@@ -16,4 +16,18 @@ def test_predict_kernel_body_on_host_emulator(tmp_path):
                            os.path.join(ROOT, "tools", "emu", "emu_predict.cpp"), obj, "-lm", "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count(" ok") == 3
+    assert out.stdout.count(" ok") == 12 and "FAIL" not in out.stdout
+
+
+def test_cluster_update_kernel_body_on_host_emulator(tmp_path):
+    """ekf_cluster2.cuh (8 / 16 CTAs as forked processes, distributed shared memory as a shared mapping): dense check /
+    update / check+update at n = 8..84, augmentation incl. the deferred symmetrisation, selector updates; vs the C oracle."""
+    exe = str(tmp_path / "emu_update")
+    obj = str(tmp_path / "orc_ekf.o")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", "hv_oracle_ekf.c"), "-o", obj])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tools", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tools", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tools", "emu", "emu_update.cpp"), obj, "-lm", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count(" ok") == 11 and "FAIL" not in out.stdout

@@ -177,7 +177,7 @@ def test_batch_submission_matches_single_calls(cuda, oracle_lk, trail):
                 b.augment(-1)
         for i, s_, c_ in exp_st:
             assert st[i] == s_, f"frame {frame} op {i}: status {st[i]} != {s_}"
-            assert abs(chi2[i] - c_) <= 1e-8 * max(1.0, abs(c_))
+            assert abs(chi2[i] - c_) <= 1e-8 * max(1.0, abs(c_)), f"frame {frame} op {i}: chi2 {chi2[i]} != {c_}"
         mb, Pb = b.download()
         ma, Pa = a.download()
         assert np.array_equal(m, ma)

@@ -11,8 +11,12 @@ ekf = capi.Ekf(hv, p)
 ekf.initialize_orientation([0.1, 0.2, 9.8])
 lib = capi.load(); lib.hv_ekf_debug_result_words.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 rng = np.random.RandomState(0)
-names = {0: "start", 1: "shift(aug)", 2: "H+P staged, residual", 3: "HP (phase A)", 4: "partial S stored", 5: "cluster.sync", 6: "S reduced+gathered",
-         7: "elimination", 8: "chi2/decision", 9: "Z exchange + P/m update"}
+if os.environ.get("HV_EKF_CLUSTER_V1"):
+    names = {0: "start", 1: "shift(aug)", 2: "H+P staged, residual", 3: "HP (phase A)", 4: "partial S stored", 5: "cluster.sync", 6: "S reduced+gathered",
+             7: "elimination", 8: "chi2/decision", 9: "Z exchange + P/m update"}
+else:   # ekf_cluster2.cuh
+    names = {0: "start", 1: "P block + H staged, residual", 2: "HP", 3: "partial S", 4: "S reduced (DSMEM)", 5: "elimination", 6: "chi2/decision",
+             7: "Z gathered (DSMEM)", 8: "P block downdate + m", 9: "stores (+Joseph/symmetrise)"}
 for n in (8, 20, 40, 84):
     l = min(160, 20 + 7 * max(1, n // 4))
     Hm = torch.from_numpy(np.asfortranarray(rng.normal(0, 0.1, (n, l))).ravel(order="F").copy()).cuda()

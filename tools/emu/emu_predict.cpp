@@ -22,11 +22,12 @@ int orc_ekf_state_dim(const orc_ekf*);
 int main()
 {
     int fails = 0;
-    for (int trial = 0; trial < 3; trial++) {
+    const int ntrials = 12;
+    for (int trial = 0; trial < ntrials; trial++) {
         orc_params prm; orc_ekf_default_params(&prm);
-        prm.camera_trail_length = trial == 2 ? 6 : 20;
+        prm.camera_trail_length = (trial % 3) == 2 ? 6 : 20;
         // v[] = hv_ekf_params after the two ints: noise_scale 0, gravity 1, noise_initial_* 2..10, noise_process_acc 11, gyro 12, baa 13, baa_rev 14, bga 15, bga_rev 16
-        if (trial == 1) prm.v[15] = 2e-5;       // gyro-bias random walk on: exercises bgaDecay / qBga
+        if ((trial % 3) == 1) prm.v[15] = 2e-5;       // gyro-bias random walk on: exercises bgaDecay / qBga
         orc_ekf* o = orc_ekf_create(&prm);
         const int N = orc_ekf_state_dim(o);
         std::vector<double> m(N), P((size_t)N * N), Q(144, 0.0);
@@ -50,7 +51,7 @@ int main()
         EkfPredictArgs a; memset(&a, 0, sizeof(a));
         a.b.m = dm.data(); a.b.P = dP.data(); a.b.Q = dQ.data(); a.b.dydx = ddydx.data(); a.b.res = res.data(); a.b.N = N; a.b.trail = prm.camera_trail_length;
         a.gravity = prm.v[1];
-        const int cnt = trial == 2 ? 3 : 10;
+        const int cnt = trial == 2 ? 3 : trial < 3 ? 10 : 1 + (trial * 5) % 16;
         a.count = cnt;
         double t = 0.0;
         for (int k = 0; k < cnt; k++) {
@@ -59,7 +60,7 @@ int main()
             double xg[3] = {0.05 * rnd(), 0.05 * rnd(), 0.2 + 0.05 * rnd()}, xa[3] = {0.3 * rnd(), 0.2 * rnd(), 9.8 + 0.2 * rnd()};
             EkfPredictSample& s = a.s[k];
             s.dt = dt; for (int i = 0; i < 3; i++) { s.xg[i] = xg[i]; s.xa[i] = xa[i]; }
-            s.qBaa = s.qBga = -1.0; s.baaDecay = s.bgaDecay = 1.0; s.normAfter = (trial >= 1 && k != 1) ? 1 : 0; s.pad = 0;
+            s.qBaa = s.qBga = -1.0; s.baaDecay = s.bgaDecay = 1.0; s.normAfter = ((trial % 3) >= 1 && trial < 6 && k != 1) ? 1 : 0; s.pad = 0;
             if (prm.v[13] > 0) { const double th = prm.v[14]; s.qBaa = ns * prm.v[13] * prm.v[13]; if (th > 0) s.qBaa *= (1 - std::exp(-2 * dt * th)) / (2 * th); s.baaDecay = std::exp(-dt * th); }
             if (prm.v[15] > 0) { const double th = prm.v[16]; s.qBga = ns * prm.v[15] * prm.v[15]; if (th > 0) s.qBga *= (1 - std::exp(-2 * dt * th)) / (2 * th); s.bgaDecay = std::exp(-dt * th); }
             orc_ekf_predict(o, t, xg, xa);
