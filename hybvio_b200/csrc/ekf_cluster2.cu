@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(EK2_NT) ekf_check_batch_cluster2_kernel(EkfUpd
     ek2_body(a, ek2_sm, cluster);
 }
 
-#define EK2_STATIC_SMEM (sizeof(double) * (2 + ELIM_SMEM_DOUBLES + EK2_MAXN) + 256)
+#define EK2_STATIC_SMEM (sizeof(double) * (2 + 64 + 2 + EK2_MAXN) + 256)
 #define EK2_SMEM_LIMIT (227 * 1024)
 
 // Cluster size: 8 (portable) unless HV_EKF_CLUSTER=16 asks for the non-portable size (A/B switch this round).

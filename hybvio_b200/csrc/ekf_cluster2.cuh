@@ -25,7 +25,7 @@
 // oracle without a GPU).
 #pragma once
 #include "ekf.cuh"
-#include "ekf_elim.cuh"
+#include "hv_dmma.cuh"
 
 #define EK2_NT 512
 #define EK2_MAXN 768
@@ -33,21 +33,23 @@
 #define EK2_PHASE(i) do { } while (0)
 #endif
 
-struct Ek2Geom { int C, B, X, W, T, PB, RS, EXTRA, oneStage; };
+struct Ek2Geom { int C, B, X, W, T, PB, RS, EXTRA, oneStage, LD; };
 __host__ __device__ inline Ek2Geom ek2_geom(int n, int l, int N, bool joseph, int C)
 {
     Ek2Geom g;
     g.C = C;
     g.B = (N + C - 1) / C;
-    g.X = n * (l > N ? l : N);                              // H (n x l, ld n), later the gathered Z (n x N, ld N)
+    // Leading dimension of the P block and of the gathered Z: = 4 (mod 16) doubles, so that the DMMA fragment loads (8
+    // consecutive + 4 strided elements per half-warp) touch 16 distinct 8-byte banks
+    g.LD = N + ((20 - (N & 15)) & 15);
+    g.X = n * (l > g.LD ? l : g.LD);                        // H (n x l, ld n), later the gathered Z (n x N, ld LD)
     g.W = (n + g.B + 1 + (joseph ? n : 0)) | 1;             // tableau row: [S | HP_J | v | (I)]
     g.T = n * g.W;
-    g.PB = N * g.B;                                         // own column block of P, ld N
+    g.PB = g.LD * g.B;                                      // own column block of P, ld LD
     const int E = (n * n + C - 1) / C;
-    const int cend = n + g.B + (joseph ? n : 0);
-    // small S is summed directly by every CTA into RS (and eliminated from there: register path only)
-    g.oneStage = (n * n <= 1024 && n <= ELIM_RA * 32 && cend < ELIM_CJ * 32) ? 1 : 0;
-    g.RS = g.oneStage ? n * n : E;                          // reduced S (small n: all of it; else the own slice)
+    // small S: every CTA leaves its partial in RS and sums all of them itself; else reduce-scatter (own slice in RS) + all-gather
+    g.oneStage = n * n <= 1024 ? 1 : 0;
+    g.RS = g.oneStage ? n * n : E;
     g.EXTRA = joseph ? N * (EKF_POSE + 14 + 14) + N * g.B : 0;   // K | T1c | special columns of G | P'' block
     return g;
 }
@@ -81,12 +83,156 @@ __device__ __forceinline__ int ek2_aug_src(int i, int drop)
 }
 __device__ __forceinline__ int ek2_special_col(int c) { return c < 3 ? EKF_POS + c : c < 7 ? EKF_ORI + c - 3 : EKF_CAM + c - 7; }
 
+// C(M x Nn) = cinit + A(M x K) B(K x Nn) on the fp64 tensor cores, 8 x 8 tiles dealt to the 16 warps, up to EK2_NI tiles
+// of a warp advance together through k (independent DMMA chains). fa(m, k) / fb(k, n) return the operands (0 outside the
+// matrix), cinit(m, n) the initial value, store(m, n, v0, v1) receives C(m, n), C(m, n + 1) for m < M, n < Nn (n even).
+#define EK2_NI 4
+template <class FA, class FB, class FCI, class FST>
+__device__ __forceinline__ void ek2_dmma_gemm(int M, int Nn, int K, int wrp, int lane, FA fa, FB fb, FCI cinit, FST store)
+{
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int MT = (M + 7) >> 3, NT = (Nn + 7) >> 3, tiles = MT * NT, KT = (K + 3) >> 2;
+    const int nwarps = EK2_NT / 32;
+    for (int base = wrp; base < tiles; base += nwarps * EK2_NI) {
+        double c0[EK2_NI], c1[EK2_NI];
+        int row[EK2_NI], colb[EK2_NI], col[EK2_NI];
+        bool ok[EK2_NI];
+#pragma unroll
+        for (int q = 0; q < EK2_NI; q++) {
+            const int tile = base + q * nwarps;
+            ok[q] = tile < tiles;                                         // warp-uniform
+            const int mt = tile % MT, nt = tile / MT;
+            row[q] = mt * 8 + g8; colb[q] = nt * 8 + g8; col[q] = nt * 8 + 2 * t4;
+            c0[q] = 0.0; c1[q] = 0.0;
+            if (ok[q] && row[q] < M) { if (col[q] < Nn) c0[q] = cinit(row[q], col[q]); if (col[q] + 1 < Nn) c1[q] = cinit(row[q], col[q] + 1); }
+        }
+        for (int kt = 0; kt < KT; kt++) {
+            const int kk = kt * 4 + t4;
+#pragma unroll
+            for (int q = 0; q < EK2_NI; q++)
+                if (ok[q]) hv_dmma(c0[q], c1[q], fa(row[q], kk), fb(kk, colb[q]));
+        }
+#pragma unroll
+        for (int q = 0; q < EK2_NI; q++)
+            if (ok[q] && row[q] < M && col[q] < Nn) store(row[q], col[q], c0[q], c1[q]);
+    }
+}
+
+// Blocked forward elimination of the tableau T = [ S | Y ] (n rows, columns 0 .. ncols-1, row-major, ld W) in shared
+// memory: S = L L' (never pivoted: R > 0 makes S positive definite), Y <- L^-1 Y, by 8-row blocks:
+//   1. ONE warp factors the 8 x 8 diagonal block D of the current Schur complement with shuffles only (column per lane;
+//      the same row operations applied to an identity give L_jj^-1) -- the only serial part: 8 pivots per block;
+//   2. all warps: rows of the block <- L_jj^-1 * rows (8 x 8 x 8 DMMA per column tile);
+//   3. all warps: trailing update T[i, c] -= U_j[:, i]' U_j[:, c] for the rows below, upper triangle of S and all of Y
+//      (8 x 8 x 8 DMMA per tile, several tiles of a warp in flight).
+// Three barriers per 8 pivots; the first generation (ekf_elim.cuh) needed one barrier per two pivots and kept the
+// tableau in registers, which bounded n <= 96. Returns false (uniformly) on a non-positive pivot.
+__device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int ncols, int wrp, int lane, double* s_linv, volatile int* s_bad)
+{
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int nwarps = EK2_NT / 32;
+    const int MT = (n + 7) >> 3, CT = (ncols + 7) >> 3;
+    if (wrp == 0 && lane == 0) *s_bad = 0;
+    __syncthreads();
+    for (int j = 0; j < MT; j++) {
+        const int r0 = 8 * j, nb = min(8, n - r0);
+        // ---- 1. diagonal block: lanes 0..7 hold the columns of D (padded with the identity), lanes 8..15 those of I
+        if (wrp == 0) {
+            double v[8];
+            const int cidx = lane & 7;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                double x = (i == cidx) ? 1.0 : 0.0;
+                if (lane < 8 && i < nb && cidx < nb) x = T[(size_t)(r0 + i) * W + r0 + cidx];
+                if (lane >= 16) x = 0.0;
+                v[i] = x;
+            }
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const double akk = __shfl_sync(0xffffffffu, v[k], k);
+                if (!(akk > 0.0)) ok = false;
+                const double r = rsqrt(akk);
+                const double u = v[k] * r;                 // scaled pivot row, entry of this column
+                v[k] = u;
+#pragma unroll
+                for (int i = k + 1; i < 8; i++) {
+                    const double mi = __shfl_sync(0xffffffffu, u, i);      // S is symmetric: multiplier of row i = entry i of the scaled pivot row
+                    v[i] = fma(-mi, u, v[i]);
+                }
+            }
+            if (lane >= 8 && lane < 16) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) s_linv[i * 8 + (lane - 8)] = v[i];      // L_jj^-1 (lower triangular)
+            }
+            if (!ok && lane == 0) *s_bad = 1;
+        }
+        __syncthreads();
+        if (*s_bad) return false;
+        // ---- 2. rows of the block <- L_jj^-1 * rows, column tiles j .. CT-1
+        for (int ct = j + wrp; ct < CT; ct += nwarps) {
+            double c0 = 0.0, c1 = 0.0;
+            const int colb = 8 * ct + g8;
+            double bf[2];
+#pragma unroll
+            for (int kt = 0; kt < 2; kt++) { const int k = kt * 4 + t4; bf[kt] = (k < nb && colb < ncols) ? T[(size_t)(r0 + k) * W + colb] : 0.0; }
+#pragma unroll
+            for (int kt = 0; kt < 2; kt++) hv_dmma(c0, c1, s_linv[g8 * 8 + kt * 4 + t4], bf[kt]);
+            const int col = 8 * ct + 2 * t4;
+            if (g8 < nb) { if (col < ncols) T[(size_t)(r0 + g8) * W + col] = c0; if (col + 1 < ncols) T[(size_t)(r0 + g8) * W + col + 1] = c1; }
+        }
+        __syncthreads();
+        // ---- 3. trailing update: row tiles mt > j, column tiles nt >= mt
+        if (j + 1 < MT) {
+            const int first = j + 1;
+            int total = 0;
+            for (int mt = first; mt < MT; mt++) total += CT - mt;
+            for (int base = wrp; base < total; base += nwarps * EK2_NI) {
+                double c0[EK2_NI], c1[EK2_NI], af[EK2_NI][2], bfr[EK2_NI][2];
+                int rowi[EK2_NI], coli[EK2_NI];
+                bool ok[EK2_NI];
+#pragma unroll
+                for (int q = 0; q < EK2_NI; q++) {
+                    int idx = base + q * nwarps;
+                    ok[q] = idx < total;                                   // warp-uniform
+                    int mt = first;
+                    while (ok[q] && idx >= CT - mt) { idx -= CT - mt; mt++; }
+                    const int nt = mt + idx;
+                    rowi[q] = 8 * mt + g8; coli[q] = 8 * nt + 2 * t4;
+                    c0[q] = 0.0; c1[q] = 0.0; af[q][0] = af[q][1] = bfr[q][0] = bfr[q][1] = 0.0;
+                    if (ok[q]) {
+                        if (rowi[q] < n) { if (coli[q] < ncols) c0[q] = T[(size_t)rowi[q] * W + coli[q]]; if (coli[q] + 1 < ncols) c1[q] = T[(size_t)rowi[q] * W + coli[q] + 1]; }
+#pragma unroll
+                        for (int kt = 0; kt < 2; kt++) {
+                            const int k = kt * 4 + t4;
+                            const int am = 8 * mt + g8, bn = 8 * nt + g8;
+                            af[q][kt] = (k < nb && am < ncols) ? -T[(size_t)(r0 + k) * W + am] : 0.0;     // A[m][k] = -U_j[k][8 mt + m]
+                            bfr[q][kt] = (k < nb && bn < ncols) ? T[(size_t)(r0 + k) * W + bn] : 0.0;     // B[k][nn] = U_j[k][8 nt + nn]
+                        }
+                    }
+                }
+#pragma unroll
+                for (int kt = 0; kt < 2; kt++)
+#pragma unroll
+                    for (int q = 0; q < EK2_NI; q++)
+                        if (ok[q]) hv_dmma(c0[q], c1[q], af[q][kt], bfr[q][kt]);
+#pragma unroll
+                for (int q = 0; q < EK2_NI; q++)
+                    if (ok[q] && rowi[q] < n) { if (coli[q] < ncols) T[(size_t)rowi[q] * W + coli[q]] = c0[q]; if (coli[q] + 1 < ncols) T[(size_t)rowi[q] * W + coli[q] + 1] = c1[q]; }
+            }
+            __syncthreads();
+        }
+    }
+    return true;
+}
+
 // `Cluster` is cooperative_groups::cluster_group (or the emulator's stand-in).
 template <class Cluster>
 __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster cluster)
 {
     __shared__ double s_scalar[2];
-    __shared__ double s_elim[ELIM_SMEM_DOUBLES];
+    __shared__ double s_linv[64];
+    __shared__ int s_bad;
     __shared__ double s_m[EK2_MAXN];
     const int c = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, nwarps = EK2_NT / 32;
@@ -98,7 +244,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     double* PB = T + g.T;           // P[:, J_c]
     double* RS = PB + g.PB;         // reduced S
     double* EX = RS + g.RS;         // Joseph-form extras
-    const int W = g.W, B = g.B;
+    const int W = g.W, B = g.B, LD = g.LD;
     const int J0 = c * B, Bc = max(0, min(B, N - J0));
     const int vcol = n + B, cend = joseph ? vcol + n : vcol;
     const bool oneStage = g.oneStage != 0;
@@ -116,11 +262,20 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
             // deferred maintainPositiveSemiDefinite (ekf.cpp:1059-1067): 0.5 (P + P') evaluated while the shift reads P
             if (a.symFirst && si >= 0 && sj >= 0 && si != sj) v = 0.5 * (v + P[sj + (size_t)si * N]);
             if (i == j && i >= EKF_CAM && i < EKF_CAM + EKF_POSE) v += (i - EKF_CAM) < 3 ? a.augNoisePos : a.augNoiseOri;
-            PB[idx] = v;
+            PB[i + (size_t)(idx / N) * LD] = v;
         }
     } else {
         for (int i = tid; i < N; i += EK2_NT) s_m[i] = a.b.m[i];
-        ek2_copy8(PB, P + (size_t)J0 * N, N * Bc, tid);          // whole columns: one contiguous block
+        // whole columns: one contiguous block of global memory, 8 loads in flight per thread
+        const double* src = P + (size_t)J0 * N;
+        const int count = N * Bc;
+        for (int base = 0; base < count; base += 8 * EK2_NT) {
+            double r[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int i = base + u * EK2_NT + tid; r[u] = i < count ? src[i] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int i = base + u * EK2_NT + tid; if (i < count) PB[(i % N) + (size_t)(i / N) * LD] = r[u]; }
+        }
     }
 
     // ---- measurement model into shared memory (ld = n)
@@ -181,77 +336,25 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     }
 
     EK2_PHASE(1);
-    // ---- phase A: HP[:, J_c] = H P[0:l, J_c]  (4 x 4 register tiles out of shared memory; the k range is split over KS
-    // thread groups whose partial tiles are summed in shared memory in a fixed order)
-    {
-        const int tm = (n + 3) >> 2, tn = (Bc + 3) >> 2, ntile = tm * tn;
-        int KS = min(EK2_NT / max(ntile, 1), l / 24); KS = KS < 1 ? 1 : (KS > 8 ? 8 : KS);   // a slice is worth >= 24 k's
-        const int klen = (l + KS - 1) / KS;
-        for (int t = tid; t < n * Bc; t += EK2_NT) T[(size_t)(t / Bc) * W + n + (t % Bc)] = 0.0;
-        __syncthreads();
-        const int grp = tid / max(ntile, 1), t = tid - grp * ntile;
-        const int ti = t % max(tm, 1), tj = t / max(tm, 1);
-        double acc[4][4];
-#pragma unroll
-        for (int x = 0; x < 4; x++)
-#pragma unroll
-            for (int y = 0; y < 4; y++) acc[x][y] = 0.0;
-        if (grp < KS && ntile > 0) {
-            const int k0 = grp * klen, k1 = min(l, k0 + klen);
-            int iv[4], jv[4];
-#pragma unroll
-            for (int x = 0; x < 4; x++) { iv[x] = min(ti + x * tm, n - 1); jv[x] = min(tj + x * tn, Bc - 1); }
-            for (int k = k0; k < k1; k++) {
-                double hv[4], bv[4];
-#pragma unroll
-                for (int x = 0; x < 4; x++) { hv[x] = Hs[iv[x] + (size_t)k * n]; bv[x] = PB[k + (size_t)jv[x] * N]; }
-#pragma unroll
-                for (int x = 0; x < 4; x++)
-#pragma unroll
-                    for (int y = 0; y < 4; y++) acc[x][y] += hv[x] * bv[y];
-            }
-        }
-        for (int ks = 0; ks < KS; ks++) {
-            if (grp == ks && ntile > 0) {
-#pragma unroll
-                for (int x = 0; x < 4; x++)
-#pragma unroll
-                    for (int y = 0; y < 4; y++) {
-                        const int i = ti + x * tm, j = tj + y * tn;
-                        if (i < n && j < Bc) T[(size_t)i * W + n + j] += acc[x][y];
-                    }
-            }
-            __syncthreads();
-        }
-    }
+    // ---- phase A: HP[:, J_c] = H P[0:l, J_c] on the fp64 tensor cores (n x Bc x l)
+    ek2_dmma_gemm(n, Bc, l, wrp, lane,
+                  [&](int i, int k) { return (i < n && k < l) ? Hs[i + (size_t)k * n] : 0.0; },
+                  [&](int k, int j) { return (k < l && j < Bc) ? PB[k + (size_t)j * LD] : 0.0; },
+                  [](int, int) { return 0.0; },
+                  [&](int i, int j, double v0, double v1) { T[(size_t)i * W + n + j] = v0; if (j + 1 < Bc) T[(size_t)i * W + n + j + 1] = v1; });
+    __syncthreads();
     EK2_PHASE(2);
-    // ---- phase B: partial S over the own columns inside [0, l) into the S part of the own tableau
+    // ---- phase B: partial S = HP[:, J_c within [0, l)] H[:, J_c]' into the S part of the own tableau (n x n x kc)
     {
         const int kc = max(0, min(Bc, l - J0));
-        const int ti_n = (n + 1) >> 1, tp_n = (n + 3) >> 2;
-        for (int t = tid; t < ti_n * tp_n; t += EK2_NT) {
-            const int tp = t % tp_n, ti = t / tp_n;
-            const int i0 = ti, i1 = min(ti + ti_n, n - 1);
-            int pv[4];
-#pragma unroll
-            for (int x = 0; x < 4; x++) pv[x] = min(tp + x * tp_n, n - 1);
-            const double* hp0 = T + (size_t)i0 * W + n;
-            const double* hp1 = T + (size_t)i1 * W + n;
-            const double* hh = Hs + (size_t)J0 * n;
-            double acc[2][4];
-#pragma unroll
-            for (int x = 0; x < 4; x++) { acc[0][x] = 0.0; acc[1][x] = 0.0; }
-            for (int k = 0; k < kc; k++) {
-                const double a0 = hp0[k], a1 = hp1[k];
-#pragma unroll
-                for (int x = 0; x < 4; x++) { const double h = hh[pv[x] + (size_t)k * n]; acc[0][x] += a0 * h; acc[1][x] += a1 * h; }
-            }
-#pragma unroll
-            for (int x = 0; x < 4; x++) {
-                const int ip = tp + x * tp_n;
-                if (ip < n) { T[(size_t)i0 * W + ip] = acc[0][x]; if (ti + ti_n < n) T[(size_t)(ti + ti_n) * W + ip] = acc[1][x]; }
-            }
-        }
+        ek2_dmma_gemm(n, n, kc, wrp, lane,
+                      [&](int i, int k) { return (i < n && k < kc) ? T[(size_t)i * W + n + k] : 0.0; },
+                      [&](int k, int j) { return (k < kc && j < n) ? Hs[j + (size_t)(J0 + k) * n] : 0.0; },
+                      [](int, int) { return 0.0; },
+                      [&](int i, int j, double v0, double v1) {
+                          if (oneStage) { RS[i * n + j] = v0; if (j + 1 < n) RS[i * n + j + 1] = v1; }      // partial stays out of the tableau
+                          else { T[(size_t)i * W + j] = v0; if (j + 1 < n) T[(size_t)i * W + j + 1] = v1; }
+                      });
     }
     EK2_PHASE(3);
     cluster.sync();                                   // #1: every partial S is in place (and from here on shared memory is exposed)
@@ -260,9 +363,9 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         for (int e = tid; e < n * n; e += EK2_NT) {
             const int i = e / n, ip = e - i * n;
             double s = 0.0;
-            for (int r = 0; r < C; r++) s += cluster.map_shared_rank(T, r)[(size_t)i * W + ip];
+            for (int r = 0; r < C; r++) s += cluster.map_shared_rank(RS, r)[e];
             if (i == ip) s += a.Rdiag;
-            RS[e] = s;
+            T[(size_t)i * W + ip] = s;                 // the own tableau is not read by anybody else
         }
         __syncthreads();
     } else {
@@ -283,62 +386,8 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     }
 
     EK2_PHASE(4);
-    // ---- unpivoted forward elimination of [S | HP_Jc | v | (I)], then Z = D^-1/2 (.)   (ekf_elim.cuh)
-    bool bad = false;
-    if (n <= ELIM_RA * 32 && cend < ELIM_CJ * 32) {
-        double t[ELIM_RA][2][ELIM_CJ];
-#pragma unroll
-        for (int aa = 0; aa < ELIM_RA; aa++)
-#pragma unroll
-            for (int sr = 0; sr < 2; sr++)
-#pragma unroll
-                for (int bb = 0; bb < ELIM_CJ; bb++) {
-                    const int i = elim_row(wrp, aa, sr), j = lane + 32 * bb;
-                    double v = 0.0;
-                    if (i < n && j <= cend) v = (oneStage && j < n) ? RS[i * n + j] : T[(size_t)i * W + j];
-                    t[aa][sr][bb] = v;
-                }
-        bad = !elim_dispatch(t, n, cend + 1, lane, wrp, s_elim);
-        if (!bad) {
-            __syncthreads();
-            const double* pivots = s_elim + 2 * 2 * ELIM_ROWBUF + 8;
-#pragma unroll
-            for (int aa = 0; aa < ELIM_RA; aa++)
-#pragma unroll
-                for (int sr = 0; sr < 2; sr++) {
-                    const int i = elim_row(wrp, aa, sr);
-                    if (i < n) {
-                        const double sc = 1.0 / sqrt(pivots[i]);
-#pragma unroll
-                        for (int bb = 0; bb < ELIM_CJ; bb++) {
-                            const int j = lane + 32 * bb;
-                            if (j >= n && j <= cend) T[(size_t)i * W + j] = t[aa][sr][bb] * sc;
-                        }
-                    }
-                }
-        }
-    } else {
-        // oversized rows (n > 96 or a very wide block): in place in shared memory, one pivot per barrier (two-stage S only)
-        for (int k = 0; k < n; k++) {
-            const double piv = T[(size_t)k * W + k];
-            if (!(piv > 0.0)) { bad = true; break; }
-            const double rinv = 1.0 / piv;
-            const double* rk = T + (size_t)k * W;
-            for (int i = k + 1 + wrp; i < n; i += nwarps) {
-                double* ri = T + (size_t)i * W;
-                const double f = ri[k] * rinv;
-                for (int j = k + 1 + lane; j <= cend; j += 32) ri[j] -= f * rk[j];
-            }
-            __syncthreads();
-        }
-        if (!bad) {
-            for (int k = wrp; k < n; k += nwarps) {
-                const double sc = 1.0 / sqrt(T[(size_t)k * W + k]);
-                double* rk = T + (size_t)k * W;
-                for (int j = n + lane; j <= cend; j += 32) rk[j] *= sc;
-            }
-        }
-    }
+    // ---- blocked forward elimination of [S | HP_Jc | v | (I)]: the right part becomes Z = L^-1 (.)
+    const bool bad = !ek2_block_eliminate(T, W, n, cend + 1, wrp, lane, s_linv, &s_bad);
     if (bad) {                                        // uniform over the cluster
         if (c == 0 && tid == 0) { a.b.res[0] = 1.0; a.b.res[1] = 0.0; a.b.res[2] = 1.0; }
         cluster.sync();
@@ -359,54 +408,24 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     // ---- gather Z (n x N, row-major) out of the neighbours' tableaus, then P[:, J_c] -= Z' Z[:, J_c] in shared memory
     cluster.sync();                                   // #3: every Z slice is final
     double* Z = X;                                    // H is dead
-    for (int r = 0; r < C; r++) {
-        const int j0r = r * B, bcr = max(0, min(B, N - j0r));
-        const double* Tr = cluster.map_shared_rank(T, r);
-        for (int t = tid; t < n * bcr; t += EK2_NT) {
-            const int jj = t % bcr, k = t / bcr;
-            Z[(size_t)k * N + j0r + jj] = Tr[(size_t)k * W + n + jj];
-        }
+    for (int t = tid; t < n * N; t += EK2_NT) {       // one flat pass: all remote loads of a thread are independent
+        const int k = t / N, col = t - k * N, r = col / B;
+        Z[(size_t)k * LD + col] = cluster.map_shared_rank(T, r)[(size_t)k * W + n + (col - r * B)];
     }
     __syncthreads();
     EK2_PHASE(7);
-    {
-        // 4 x 2 register tiles; a thread's four rows are ti, ti + R4, ti + 2 R4, ti + 3 R4 so that the lanes of a warp read
-        // CONSECUTIVE doubles of a Z row (conflict-free) and update consecutive rows of a P column
-        const int R4 = (N + 3) >> 2, tj_n = (Bc + 1) >> 1;
-        for (int t = tid; t < R4 * tj_n; t += EK2_NT) {
-            const int ti = t % R4, tj = t / R4;
-            const int jj0 = tj * 2, j0 = J0 + jj0;
-            const bool j1ok = jj0 + 1 < Bc;
-            int iv[4];
-#pragma unroll
-            for (int x = 0; x < 4; x++) iv[x] = min(ti + x * R4, N - 1);
-            double acc[4][2];
-#pragma unroll
-            for (int x = 0; x < 4; x++) { acc[x][0] = 0.0; acc[x][1] = 0.0; }
-            const double* zr = Z;
-#pragma unroll 2
-            for (int k = 0; k < n; k++) {
-                double av[4];
-#pragma unroll
-                for (int x = 0; x < 4; x++) av[x] = zr[iv[x]];
-                const double b0 = zr[j0], b1 = zr[j1ok ? j0 + 1 : j0];
-#pragma unroll
-                for (int x = 0; x < 4; x++) { acc[x][0] += av[x] * b0; acc[x][1] += av[x] * b1; }
-                zr += N;
-            }
-#pragma unroll
-            for (int x = 0; x < 4; x++) {
-                const int i = ti + x * R4;
-                if (i < N) { PB[i + (size_t)jj0 * N] -= acc[x][0]; if (j1ok) PB[i + (size_t)(jj0 + 1) * N] -= acc[x][1]; }
-            }
-        }
-    }
+    // P[:, J_c] -= Z' Z[:, J_c] on the fp64 tensor cores (N x Bc x n), in place in the shared-memory block
+    ek2_dmma_gemm(N, Bc, n, wrp, lane,
+                  [&](int i, int k) { return (i < N && k < n) ? -Z[(size_t)k * LD + i] : 0.0; },
+                  [&](int k, int j) { return (k < n && j < Bc) ? Z[(size_t)k * LD + J0 + j] : 0.0; },
+                  [&](int i, int j) { return PB[i + (size_t)j * LD]; },
+                  [&](int i, int j, double v0, double v1) { PB[i + (size_t)j * LD] = v0; if (j + 1 < Bc) PB[i + (size_t)(j + 1) * LD] = v1; });
     // state mean: m += Z' z_v (CTA 0 owns the write-back; quaternion normalisation: updateCommon normalises the current
     // orientation only, the visual update and the augmentation all of them, ekf.cpp:31, 843, 874)
     if (c == 0) {
         for (int i = tid; i < N; i += EK2_NT) {
             double s = 0.0;
-            for (int k = 0; k < n; k++) s += Z[(size_t)k * N + i] * T[(size_t)k * W + vcol];
+            for (int k = 0; k < n; k++) s += Z[(size_t)k * LD + i] * T[(size_t)k * W + vcol];
             s_m[i] += s;
         }
         __syncthreads();
@@ -417,7 +436,8 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     } else __syncthreads();
     EK2_PHASE(8);
 
-    double* Pblk = PB;                                // block holding this CTA's final columns
+    double* Pblk = PB;                                // block holding this CTA's final columns ...
+    int ldb = LD;                                     // ... and its leading dimension
     if (joseph) {
         // ---- Joseph form (ekf.cpp:35-50): P'' = G T1' + K R K', G = T1 P' = P' - Z'Z (in PB now), T1 = I - K visAugH
         double* Ks = EX;                              // N x 7
@@ -427,7 +447,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         for (int t = tid; t < N * EKF_POSE; t += EK2_NT) {
             const int i = t % N, r = t / N;
             double s = 0.0;
-            for (int k = 0; k < n; k++) s += Z[(size_t)k * N + i] * T[(size_t)k * W + vcol + 1 + r];
+            for (int k = 0; k < n; k++) s += Z[(size_t)k * LD + i] * T[(size_t)k * W + vcol + 1 + r];
             Ks[t] = s;
         }
         __syncthreads();
@@ -440,13 +460,13 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         for (int t = tid; t < N * 14; t += EK2_NT) {
             const int i = t % N, cc = t / N;
             const int col = ek2_special_col(cc), r = col / B;
-            GS[t] = cluster.map_shared_rank(PB, r)[i + (size_t)(col - r * B) * N];
+            GS[t] = cluster.map_shared_rank(PB, r)[i + (size_t)(col - r * B) * LD];
         }
         __syncthreads();
         for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
             const int i = idx % N, j = J0 + idx / N;
             const bool jsp = j < 3 || (j >= EKF_ORI && j < EKF_ORI + 4) || (j >= EKF_CAM && j < EKF_CAM + EKF_POSE);
-            double s = jsp ? 0.0 : PB[idx];
+            double s = jsp ? 0.0 : PB[i + (size_t)(idx / N) * LD];
 #pragma unroll
             for (int cc = 0; cc < 14; cc++) s += GS[i + cc * N] * T1c[j + cc * N];
             double kr = 0.0;
@@ -454,22 +474,22 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
             for (int r = 0; r < EKF_POSE; r++) kr += Ks[i + r * N] * (a.Rdiag * Ks[j + r * N]);
             P2[idx] = s + kr;
         }
-        Pblk = P2;
+        Pblk = P2; ldb = N;
     }
     if (a.symmetrize) {
         cluster.sync();                               // #5: every final block is in shared memory
         for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
             const int i = idx % N, j = J0 + idx / N;
-            double v = Pblk[idx];
+            double v = Pblk[i + (size_t)(idx / N) * ldb];
             if (i != j) {
                 const int r = i / B;                  // owner of column i, which holds P(j, i)
-                const double w = cluster.map_shared_rank(Pblk, r)[j + (size_t)(i - r * B) * N];
+                const double w = cluster.map_shared_rank(Pblk, r)[j + (size_t)(i - r * B) * ldb];
                 v = i > j ? 0.5 * (v + w) : 0.5 * (w + v);      // same operand order as P(i>j) + P(j<i) on both sides
             }
             P[i + (size_t)j * N] = v;
         }
     } else {
-        for (int idx = tid; idx < N * Bc; idx += EK2_NT) P[(size_t)J0 * N + idx] = Pblk[idx];
+        for (int idx = tid; idx < N * Bc; idx += EK2_NT) P[(size_t)J0 * N + idx] = Pblk[(idx % N) + (size_t)(idx / N) * ldb];
     }
     EK2_PHASE(9);
     cluster.sync();                                   // nobody may leave while its shared memory can still be read

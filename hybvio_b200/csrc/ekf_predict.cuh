@@ -22,6 +22,7 @@
 // __syncwarp, full-warp shuffles), so that the indexing logic is testable without a GPU (tools/emu/emu_predict.cpp).
 #pragma once
 #include "ekf.cuh"
+#include "hv_dmma.cuh"
 
 // per-sample scratch in dynamic shared memory (doubles)
 #define PS_D 0          // dydx 20 x 20, column-major
@@ -53,6 +54,7 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
     __shared__ double s_Q[144], s_P00[400], s_T1[400];
     __shared__ __align__(16) double s_acc[400];
     __shared__ double s_m[EKF_INER], s_q[(EKF_MAX_PREDICT + 1) * 4], s_qn[EKF_MAX_PREDICT * 4], s_mfinal[EKF_INER];
+    __shared__ double s_u[(EKF_MAX_PREDICT + 1) * 4], s_nrm[EKF_MAX_PREDICT + 1];
     const int tid = threadIdx.x, N = a.b.N, cnt = a.count;
     const int lane = tid & 31, wrp = tid >> 5;
     double* P = a.b.P;
@@ -93,27 +95,41 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
     }
     __syncthreads();
 
-    // ---- quaternion chain q_{k+1} = A_k q_k (warp 0; every lane takes part in the shuffles, lanes 0..3 hold q)
+    // ---- quaternion chain (warp 0). The rotations are applied to the UNNORMALISED chain u_{k+1} = A_k u_k (4 FMAs per
+    // sample on the critical path); the normalizeQuaternions(true) calls that follow samples in the reference loop only
+    // rescale: state before sample k = u_k / n_j, state left by predict k = u_{k+1} / n_j, with n_j = |u_j| of the latest
+    // normalisation j <= k (ekf.cpp:1024-1032) -- all divisions happen afterwards, in parallel over the samples.
     if (wrp == 0) {
         const int r = lane & 3;
-        double q = s_m[EKF_ORI + r];
+        double u = s_m[EKF_ORI + r];
         for (int k = 0; k < cnt; k++) {
-            if (lane < 4) s_q[k * 4 + lane] = q;
+            if (lane < 4) s_u[k * 4 + lane] = u;
             const double* A = dyn + (size_t)k * PS_STRIDE + PS_A;
+            const double u0 = __shfl_sync(0xffffffffu, u, 0), u1 = __shfl_sync(0xffffffffu, u, 1);
+            const double u2 = __shfl_sync(0xffffffffu, u, 2), u3 = __shfl_sync(0xffffffffu, u, 3);
             double v = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) v += A[r * 4 + j] * __shfl_sync(0xffffffffu, q, j);
-            if (lane < 4) s_qn[k * 4 + lane] = v;   // what predict() itself leaves in the state: the Jacobians use this one
-            if (a.s[k].normAfter) {               // normalizeQuaternions(true) right after this sample (ekf.cpp:1024-1032)
-                const double sq = v * v;
-                const double z0 = __shfl_sync(0xffffffffu, sq, 0), z1 = __shfl_sync(0xffffffffu, sq, 1);
-                const double z2 = __shfl_sync(0xffffffffu, sq, 2), z3 = __shfl_sync(0xffffffffu, sq, 3);
-                const double z = (z0 + z2) + (z1 + z3);
-                if (z > 0.0) v /= sqrt(z);
-            }
-            q = v;
+            v += A[r * 4] * u0; v += A[r * 4 + 1] * u1; v += A[r * 4 + 2] * u2; v += A[r * 4 + 3] * u3;
+            u = v;
         }
-        if (lane < 4) s_q[cnt * 4 + lane] = q;
+        if (lane < 4) s_u[cnt * 4 + lane] = u;
+        __syncwarp();
+        if (lane <= cnt) {                       // lane j: n_j = |u_j| (only used where a normalisation ends at j)
+            const double* uj = s_u + lane * 4;
+            const double z = (uj[0] * uj[0] + uj[2] * uj[2]) + (uj[1] * uj[1] + uj[3] * uj[3]);
+            s_nrm[lane] = z > 0.0 ? sqrt(z) : 1.0;
+        }
+        __syncwarp();
+        if (lane <= cnt) {                       // lane k: scale in force while sample k runs
+            int j = lane;
+            while (j > 0 && !a.s[j - 1].normAfter) j--;
+            const double nj = j > 0 ? s_nrm[j] : 1.0;
+            const bool scaled = j > 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                s_q[lane * 4 + i] = scaled ? s_u[lane * 4 + i] / nj : s_u[lane * 4 + i];
+                if (lane < cnt) s_qn[lane * 4 + i] = scaled ? s_u[(lane + 1) * 4 + i] / nj : s_u[(lane + 1) * 4 + i];
+            }
+        }
     }
     __syncthreads();
     EKF_PMARK(2);
@@ -198,27 +214,37 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
         // drift-block values in force at this sample (the last one set at or before k; ekf.cpp:397-412)
         double qBaa = -1.0, qBga = -1.0;
         for (int j = 0; j <= k; j++) { if (a.s[j].qBaa >= 0.0) qBaa = a.s[j].qBaa; if (a.s[j].qBga >= 0.0) qBga = a.s[j].qBga; }
-        for (int t = lane; t < 240; t += 32) {
-            const int i = t % 20, j = t / 20;
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        // G1 = G Q_k (20 x 12 x 12) and W = G1 G' (20 x 20 x 12) on the fp64 tensor cores (hv_dmma.cuh): 8 x 8 tiles, k in steps of 4
+        const int g8 = lane >> 2, t4 = lane & 3;
+        for (int mt = 0; mt < 3; mt++)
+            for (int nt = 0; nt < 2; nt++) {
+                double c0 = 0.0, c1 = 0.0;
+                const int row = mt * 8 + g8, colb = nt * 8 + g8;
 #pragma unroll
-            for (int kk = 0; kk < 12; kk += 4) {
-                s0 += PDQ(i, kk) * ps_qval(s_Q, kk, j, qBaa, qBga); s1 += PDQ(i, kk + 1) * ps_qval(s_Q, kk + 1, j, qBaa, qBga);
-                s2 += PDQ(i, kk + 2) * ps_qval(s_Q, kk + 2, j, qBaa, qBga); s3 += PDQ(i, kk + 3) * ps_qval(s_Q, kk + 3, j, qBaa, qBga);
+                for (int kt = 0; kt < 3; kt++) {
+                    const int kk = kt * 4 + t4;
+                    const double av = row < 20 ? PDQ(row, kk) : 0.0;
+                    const double bv = colb < 12 ? ps_qval(s_Q, kk, colb, qBaa, qBga) : 0.0;
+                    hv_dmma(c0, c1, av, bv);
+                }
+                const int col = nt * 8 + 2 * t4;
+                if (row < 20 && col < 12) { G1[row + col * 20] = c0; G1[row + (col + 1) * 20] = c1; }
             }
-            G1[t] = (s0 + s1) + (s2 + s3);
-        }
         __syncwarp();
-        for (int t = lane; t < 400; t += 32) {
-            const int i = t % 20, j = t / 20;
-            double g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+        for (int mt = 0; mt < 3; mt++)
+            for (int nt = 0; nt < 3; nt++) {
+                double c0 = 0.0, c1 = 0.0;
+                const int row = mt * 8 + g8, colb = nt * 8 + g8;
 #pragma unroll
-            for (int kk = 0; kk < 12; kk += 4) {
-                g0 += G1[i + kk * 20] * PDQ(j, kk); g1 += G1[i + (kk + 1) * 20] * PDQ(j, kk + 1);
-                g2 += G1[i + (kk + 2) * 20] * PDQ(j, kk + 2); g3 += G1[i + (kk + 3) * 20] * PDQ(j, kk + 3);
+                for (int kt = 0; kt < 3; kt++) {
+                    const int kk = kt * 4 + t4;
+                    const double av = row < 20 ? G1[row + kk * 20] : 0.0;
+                    const double bv = colb < 20 ? PDQ(colb, kk) : 0.0;       // B = G': B[k][n] = G(n, k)
+                    hv_dmma(c0, c1, av, bv);
+                }
+                const int col = nt * 8 + 2 * t4;
+                if (row < 20 && col < 20) { W[row + col * 20] = c0; W[row + (col + 1) * 20] = c1; }
             }
-            W[t] = (g0 + g1) + (g2 + g3);
-        }
     }
     __syncthreads();
     EKF_PMARK(3);
@@ -236,40 +262,46 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
         else if (lane < 17) s_mfinal[EKF_BAT + lane - 13] = s_m[EKF_BAT + lane - 13];     // BAT (3) and SFT (1) are constant
     }
 
-    // ---- covariance recursion: P00 = D P00 D' + W and Dacc = D Dacc (4 interleaved partial sums per dot product)
-    for (int k = 0; k < cnt; k++) {
-        const double* D = dyn + (size_t)k * PS_STRIDE + PS_D;
-        const double* W = dyn + (size_t)k * PS_STRIDE + PS_W;
-        double accNew = 0.0;
-        if (tid < 400) {
-            const int i = tid % 20, j = tid / 20;
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0, u0 = 0, u1 = 0, u2 = 0, u3 = 0;
-            if (k == 0) {
+    // ---- covariance recursion on the fp64 tensor cores: T1 = D P00 and Dacc' = D Dacc (one 8 x 8 tile of each per warp,
+    // warps 0..8), barrier, P00 = T1 D' + W, barrier. Two barriers and two 5-deep DMMA chains per sample.
+    {
+        const int g8 = lane >> 2, t4 = lane & 3;
+        const int mt = wrp / 3, nt = wrp % 3;                 // tile of warps 0..8
+        const int row = mt * 8 + g8, colb = nt * 8 + g8, col = nt * 8 + 2 * t4;
+        const bool tileWarp = wrp < 9;
+        for (int k = 0; k < cnt; k++) {
+            const double* D = dyn + (size_t)k * PS_STRIDE + PS_D;
+            const double* W = dyn + (size_t)k * PS_STRIDE + PS_W;
+            double a0 = 0.0, a1 = 0.0;                        // Dacc' tile
+            if (tileWarp) {
+                double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-                for (int kk = 0; kk < 20; kk += 4) {
-                    s0 += PDX(i, kk) * s_P00[kk + j * 20]; s1 += PDX(i, kk + 1) * s_P00[kk + 1 + j * 20]; s2 += PDX(i, kk + 2) * s_P00[kk + 2 + j * 20]; s3 += PDX(i, kk + 3) * s_P00[kk + 3 + j * 20];
+                for (int kt = 0; kt < 5; kt++) {
+                    const int kk = kt * 4 + t4;
+                    const double dv = row < 20 ? PDX(row, kk) : 0.0;
+                    const double pv = colb < 20 ? s_P00[kk + colb * 20] : 0.0;
+                    hv_dmma(t0, t1, dv, pv);
+                    if (k > 0) { const double cv = colb < 20 ? s_acc[kk + colb * 20] : 0.0; hv_dmma(a0, a1, dv, cv); }
                 }
-                accNew = PDX(i, j);
-            } else {
-#pragma unroll
-                for (int kk = 0; kk < 20; kk += 4) {
-                    s0 += PDX(i, kk) * s_P00[kk + j * 20]; s1 += PDX(i, kk + 1) * s_P00[kk + 1 + j * 20]; s2 += PDX(i, kk + 2) * s_P00[kk + 2 + j * 20]; s3 += PDX(i, kk + 3) * s_P00[kk + 3 + j * 20];
-                    u0 += PDX(i, kk) * s_acc[kk + j * 20]; u1 += PDX(i, kk + 1) * s_acc[kk + 1 + j * 20]; u2 += PDX(i, kk + 2) * s_acc[kk + 2 + j * 20]; u3 += PDX(i, kk + 3) * s_acc[kk + 3 + j * 20];
-                }
-                accNew = (u0 + u1) + (u2 + u3);
+                if (k == 0 && row < 20 && col < 20) { a0 = PDX(row, col); a1 = PDX(row, col + 1); }      // Dacc = D_0
+                if (row < 20 && col < 20) { s_T1[row + col * 20] = t0; s_T1[row + (col + 1) * 20] = t1; }   // T1 was last read before the previous barrier
             }
-            s_T1[tid] = (s0 + s1) + (s2 + s3);      // T1 was last read before the previous barrier
-        }
-        __syncthreads();
-        if (tid < 400) {
-            const int i = tid % 20, j = tid / 20;
-            s_acc[tid] = accNew;                    // all reads of Dacc happened before the barrier above
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            __syncthreads();
+            if (tileWarp) {
+                if (row < 20 && col < 20) { s_acc[row + col * 20] = a0; s_acc[row + (col + 1) * 20] = a1; }   // all reads of Dacc happened before the barrier
+                double p0 = 0.0, p1 = 0.0;
+                if (row < 20 && col < 20) { p0 = W[row + col * 20]; p1 = W[row + (col + 1) * 20]; }
 #pragma unroll
-            for (int kk = 0; kk < 20; kk += 4) { s0 += s_T1[i + kk * 20] * PDX(j, kk); s1 += s_T1[i + (kk + 1) * 20] * PDX(j, kk + 1); s2 += s_T1[i + (kk + 2) * 20] * PDX(j, kk + 2); s3 += s_T1[i + (kk + 3) * 20] * PDX(j, kk + 3); }
-            s_P00[tid] = ((s0 + s1) + (s2 + s3)) + W[tid];
+                for (int kt = 0; kt < 5; kt++) {
+                    const int kk = kt * 4 + t4;
+                    const double tv = row < 20 ? s_T1[row + kk * 20] : 0.0;
+                    const double dv = colb < 20 ? PDX(colb, kk) : 0.0;      // B = D': B[k][n] = D(n, k)
+                    hv_dmma(p0, p1, tv, dv);
+                }
+                if (row < 20 && col < 20) { s_P00[row + col * 20] = p0; s_P00[row + (col + 1) * 20] = p1; }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     EKF_PMARK(4);
 
@@ -282,41 +314,48 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
         for (int j = 0; j < cnt; j++) { if (a.s[j].qBaa >= 0.0) qBaa = a.s[j].qBaa; if (a.s[j].qBga >= 0.0) qBga = a.s[j].qBga; }
         for (int i = tid; i < 144; i += EKF_NT) a.b.Q[i] = ps_qval(s_Q, i % 12, i / 12, qBaa, qBga);
     }
-#define PAC(i, j) s_acc[(i) + (j) * 20]
-    const int rest = N - EKF_INER;
-    for (int r = tid; r < 2 * rest && cnt > 0; r += EKF_NT) {
-        if (r < rest) {                                     // P[20+r, 0:20] = P[20+r, 0:20] * Dacc'
-            const int i = EKF_INER + r;
-            double row[20], out[20];
+    // ---- the two strips as ONE product on the tensor cores: X = [ P[20:, 0:20] ; P[0:20, 20:]' ] (2 (N-20) x 20),
+    // Y = X Dacc' (ekf.cpp:506-508: P[20:,0:20] Dacc'  and  Dacc P[0:20,20:]); 8-row tiles dealt to the warps, the A
+    // fragments of all tiles of a warp are loaded first (one L2 round trip), Dacc' fragments live in registers.
+    if (cnt > 0) {
+        const int g8 = lane >> 2, t4 = lane & 3;
+        const int rest = N - EKF_INER, rows = 2 * rest, ntile = (rows + 7) >> 3;
+        double bf[3][5];
 #pragma unroll
-            for (int k = 0; k < 20; k++) row[k] = P[i + (size_t)k * N];
+        for (int nt = 0; nt < 3; nt++)
 #pragma unroll
-            for (int j = 0; j < 20; j++) out[j] = 0.0;
+            for (int kt = 0; kt < 5; kt++) { const int nn = nt * 8 + g8, kk = kt * 4 + t4; bf[nt][kt] = nn < 20 ? s_acc[nn + kk * 20] : 0.0; }   // B[k][n] = Dacc(n, k)
+        for (int tb = wrp; tb < ntile; tb += 3 * (EKF_NT / 32)) {
+            double af[3][5];
 #pragma unroll
-            for (int k = 0; k < 20; k++) {
-                const double rk = row[k];
-                const double2* ac = reinterpret_cast<const double2*>(&PAC(0, k));     // column k of Dacc: 10 x 16-byte loads
+            for (int q = 0; q < 3; q++) {
+                const int r = (tb + q * (EKF_NT / 32)) * 8 + g8;
 #pragma unroll
-                for (int j = 0; j < 10; j++) { const double2 v = ac[j]; out[2 * j] += rk * v.x; out[2 * j + 1] += rk * v.y; }
+                for (int kt = 0; kt < 5; kt++) {
+                    const int kk = kt * 4 + t4;
+                    double v = 0.0;
+                    if (r < rest) v = P[EKF_INER + r + (size_t)kk * N];
+                    else if (r < rows) v = P[kk + (size_t)(EKF_INER + r - rest) * N];
+                    af[q][kt] = v;
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 20; j++) P[i + (size_t)j * N] = out[j];
-        } else {                                            // P[0:20, 20+c] = Dacc * P[0:20, 20+c]
-            double* colp = P + (size_t)(EKF_INER + r - rest) * N;
-            double col[20], out[20];
+            for (int q = 0; q < 3; q++) {
+                const int tile = tb + q * (EKF_NT / 32);
+                if (tile >= ntile) break;                                   // warp-uniform
+                const int r = tile * 8 + g8;
 #pragma unroll
-            for (int k = 0; k < 20; k++) col[k] = colp[k];
+                for (int nt = 0; nt < 3; nt++) {
+                    double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-            for (int j = 0; j < 20; j++) out[j] = 0.0;
-#pragma unroll
-            for (int k = 0; k < 20; k++) {
-                const double ck = col[k];
-                const double2* ac = reinterpret_cast<const double2*>(&PAC(0, k));
-#pragma unroll
-                for (int j = 0; j < 10; j++) { const double2 v = ac[j]; out[2 * j] += v.x * ck; out[2 * j + 1] += v.y * ck; }
+                    for (int kt = 0; kt < 5; kt++) hv_dmma(c0, c1, af[q][kt], bf[nt][kt]);
+                    const int col = nt * 8 + 2 * t4;
+                    if (col < 20) {
+                        if (r < rest) { P[EKF_INER + r + (size_t)col * N] = c0; P[EKF_INER + r + (size_t)(col + 1) * N] = c1; }
+                        else if (r < rows) { double* cp = P + (size_t)(EKF_INER + r - rest) * N; cp[col] = c0; cp[col + 1] = c1; }
+                    }
+                }
             }
-#pragma unroll
-            for (int j = 0; j < 20; j++) colp[j] = out[j];
         }
     }
     EKF_PMARK(5);

@@ -30,4 +30,4 @@ def test_cluster_update_kernel_body_on_host_emulator(tmp_path):
                            os.path.join(ROOT, "tools", "emu", "emu_update.cpp"), obj, "-lm", "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count(" ok") == 11 and "FAIL" not in out.stdout
+    assert out.stdout.count(" ok") == 13 and "FAIL" not in out.stdout

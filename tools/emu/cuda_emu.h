@@ -16,6 +16,7 @@
 #include <thread>
 #include <vector>
 
+#define HV_EMU 1
 #define __global__
 #define __device__
 #define __host__
@@ -36,8 +37,8 @@ struct Cta {
     int nthreads, nwarps;
     std::barrier<> bar;
     std::vector<std::unique_ptr<std::barrier<>>> wbar;
-    std::vector<double> xch;     // nwarps x 32 exchange slots
-    explicit Cta(int nt) : nthreads(nt), nwarps((nt + 31) / 32), bar(nt), xch((size_t)((nt + 31) / 32) * 32)
+    std::vector<double> xch, xch2;     // nwarps x 32 exchange slots
+    explicit Cta(int nt) : nthreads(nt), nwarps((nt + 31) / 32), bar(nt), xch((size_t)((nt + 31) / 32) * 32), xch2((size_t)((nt + 31) / 32) * 32)
     {
         for (int w = 0; w < nwarps; w++) wbar.emplace_back(new std::barrier<>(std::min(32, nt - 32 * w)));
     }
@@ -70,6 +71,17 @@ inline double __shfl_sync(unsigned, double v, int src)
     const double r = slot[src & 31];
     emu::cta->wbar[w]->arrive_and_wait();
     return r;
+}
+// mma.sync.m8n8k4.f64: a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1] (g = lane >> 2, t = lane & 3); every lane calls it
+inline void emu_dmma(double& c0, double& c1, double a, double b)
+{
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double* A = emu::cta->xch.data() + (size_t)w * 32;
+    double* B = emu::cta->xch2.data() + (size_t)w * 32;
+    A[lane] = a; B[lane] = b;
+    emu::cta->wbar[w]->arrive_and_wait();
+    for (int k = 0; k < 4; k++) { c0 = std::fma(A[g * 4 + k], B[(2 * t) * 4 + k], c0); c1 = std::fma(A[g * 4 + k], B[(2 * t + 1) * 4 + k], c1); }
+    emu::cta->wbar[w]->arrive_and_wait();
 }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 template <class T> inline T min(T a, T b) { return a < b ? a : b; }

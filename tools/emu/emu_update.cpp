@@ -41,6 +41,8 @@ int main(int argc, char** argv)
         {"augment C=16", 20, 16, EKF_OP_AUGMENT, 7, 27, EKF_MODE_UPDATE, 0, 0, -1},
         {"position update (symmetrise)", 20, 8, EKF_OP_POSITION, 3, 3, EKF_MODE_UPDATE, 0, 0, 0},
         {"zupt", 6, 8, EKF_OP_ZUPT, 3, 6, EKF_MODE_UPDATE, 0, 0, 0},
+        {"dense n=120 update (batch visual update)", 30, 8, EKF_OP_DENSE, 120, 160, EKF_MODE_UPDATE, 0.02, 0, 0},
+        {"dense n=13 check+update N=62 (odd sizes)", 6, 8, EKF_OP_DENSE, 13, 41, EKF_MODE_CHECK_UPDATE, 0.02, 0, 0},
     };
     const int only = argc > 1 ? atoi(argv[1]) : -1;
     int fails = 0, idx = -1;
