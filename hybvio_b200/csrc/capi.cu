@@ -62,6 +62,7 @@ int hv_ctx_destroy(hv_ctx* c)
     if (c->d_table) cudaFree(c->d_table);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_done) cudaFree(c->d_done);
     if (c->d_ekfStage) cudaFree(c->d_ekfStage);
     if (c->h_ekfStage) cudaFreeHost(c->h_ekfStage);
     if (c->ownStream) cudaStreamDestroy(c->stream);
@@ -89,8 +90,30 @@ int hv_ctx_reserve_stage(hv_ctx* c, size_t bytes)
     c->d_stage = nullptr; c->h_stage = nullptr; c->stageBytes = 0;
     size_t cap = 4096; while (cap < bytes) cap *= 2;
     HV_CUDA(cudaMalloc(&c->d_stage, cap));
-    HV_CUDA(cudaMallocHost(&c->h_stage, cap));
+    HV_CUDA(cudaHostAlloc(&c->h_stage, cap + 64, cudaHostAllocMapped));          // + 64: the completion flag
+    HV_CUDA(cudaHostGetDevicePointer(&c->hd_stage, c->h_stage, 0));
+    memset(c->h_stage, 0, cap + 64);
+    if (!c->d_done) { HV_CUDA(cudaMalloc(&c->d_done, sizeof(unsigned))); HV_CUDA(cudaMemset(c->d_done, 0, sizeof(unsigned))); c->doneCount = 0; }
     c->stageBytes = cap;
+    return HV_OK;
+}
+
+// HV_NO_POLL=1: results come back with a D2H copy + stream synchronisation instead (A/B switch)
+bool hv_polling_enabled() { static const bool on = getenv("HV_NO_POLL") == nullptr; return on; }
+
+int hv_poll_flag(volatile unsigned* flag, unsigned seq, cudaStream_t stream, const char* who)
+{
+    for (unsigned long long spins = 1;; spins++) {
+        if (*flag == seq) break;
+        if ((spins & 0xfff) == 0) {
+            const cudaError_t q = cudaStreamQuery(stream);
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) { hv_set_error("%s: %s while waiting for the result", who, cudaGetErrorString(q)); return HV_ERR_CUDA; }
+            if (*flag == seq) break;
+            hv_set_error("%s: the kernel finished without raising its completion flag", who); return HV_ERR_STATE;
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
     return HV_OK;
 }
 
@@ -257,6 +280,7 @@ static int lk_fill(LkLaunch& L, hv_ctx* c, int maxLevel, int maxIter, double eps
     double e = eps < 0. ? 0. : (eps > 10. ? 10. : eps);
     L.eps2 = e * e;
     L.minEig = (float)minEig;
+    L.doneCounter = nullptr; L.doneTarget = 0; L.seq = 0; L.hostFlag = nullptr;
     return HV_OK;
 }
 
@@ -323,12 +347,38 @@ int hv_lk_track(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* prevXY, floa
     uint8_t* hs = (uint8_t*)c->h_stage; uint8_t* ds = (uint8_t*)c->d_stage;
     memcpy(hs + oPrev, prevXY, 8 * (size_t)n);
     if (useInitial) memcpy(hs + oNext, nextXY, 8 * (size_t)n);
-    HV_CUDA(cudaMemcpyAsync(ds, hs, useInitial ? 16 * (size_t)n : 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    rc = hv_lk_track_device(c, prev, next, (const float*)(ds + oPrev), (float*)(ds + oNext), ds + oSt, (int32_t*)(ds + oTs),
-                            n, useInitial, maxIter, eps, minEig);
-    if (rc != HV_OK) return rc;
-    HV_CUDA(cudaMemcpyAsync(hs + oNext, ds + oNext, total - oNext, cudaMemcpyDeviceToHost, c->stream));
-    HV_CUDA(cudaStreamSynchronize(c->stream));
+    static const bool warpKernel = getenv("HV_LK_WARP_PER_FEATURE") != nullptr;    // that kernel does not signal
+    if (hv_polling_enabled() && !warpKernel && n <= 640) {
+        // The kernel reads the points from and writes the results to the mapped pinned block itself (a few KB over PCIe) and
+        // raises a flag there when the last feature is done: no H2D / D2H copy calls, no stream synchronisation.
+        uint8_t* hd = (uint8_t*)c->hd_stage;
+        LkLaunch L;
+        LkJob& d = L.jobs[0];
+        d.prevIdx = prev->slot; d.nextIdx = next->slot; d.n = n; d.useInitial = useInitial;
+        d.prevPts = (const float2*)(hd + oPrev); d.nextPts = (float2*)(hd + oNext);
+        d.status = hd + oSt; d.trackStatus = (int32_t*)(hd + oTs);
+        L.njobs = 1;
+        lk_fill(L, c, HV_MAX_LEVELS, maxIter, eps, minEig);
+        volatile unsigned* flag = (volatile unsigned*)(hs + c->stageBytes);
+        L.doneCounter = c->d_done; c->doneCount += (unsigned)n; L.doneTarget = c->doneCount;
+        L.seq = ++c->seq; L.hostFlag = (volatile unsigned*)(hd + c->stageBytes);
+        cudaError_t e = hv_launch_lk(L, prev->win, c->stream);
+        if (e == cudaErrorInvalidValue) { hv_set_error("hv_lk_track: window size %d unsupported (supported: 11, 15, 21, 31)", prev->win); return HV_ERR_UNSUPPORTED; }
+        HV_CUDA(e);
+        c->launches += 1;
+        rc = hv_poll_flag(flag, L.seq, c->stream, "hv_lk_track");
+        if (rc != HV_OK) {      // resynchronise the counter before anybody polls again
+            cudaStreamSynchronize(c->stream); cudaMemset(c->d_done, 0, sizeof(unsigned)); c->doneCount = 0;
+            return rc;
+        }
+    } else {
+        HV_CUDA(cudaMemcpyAsync(ds, hs, useInitial ? 16 * (size_t)n : 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        rc = hv_lk_track_device(c, prev, next, (const float*)(ds + oPrev), (float*)(ds + oNext), ds + oSt, (int32_t*)(ds + oTs),
+                                n, useInitial, maxIter, eps, minEig);
+        if (rc != HV_OK) return rc;
+        HV_CUDA(cudaMemcpyAsync(hs + oNext, ds + oNext, total - oNext, cudaMemcpyDeviceToHost, c->stream));
+        HV_CUDA(cudaStreamSynchronize(c->stream));
+    }
     memcpy(nextXY, hs + oNext, 8 * (size_t)n);
     if (trackStatus) memcpy(trackStatus, hs + oTs, 4 * (size_t)n);
     if (status) memcpy(status, hs + oSt, (size_t)n);

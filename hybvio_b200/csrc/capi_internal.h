@@ -26,6 +26,9 @@ struct hv_ctx {
     long long launches = 0;
     // LK staging (host-buffer API): one pinned block + one device block, grown on demand
     void* h_stage = nullptr; void* d_stage = nullptr; size_t stageBytes = 0;
+    void* hd_stage = nullptr;          // device alias of h_stage (mapped pinned memory): results are written straight to the host
+    unsigned* d_done = nullptr;        // completion counter of the polled launches (device)
+    unsigned doneCount = 0, seq = 0;   // host mirror of the counter / sequence number of the last polled launch
     // EKF staging
     void* h_ekfStage = nullptr; void* d_ekfStage = nullptr; size_t ekfStageBytes = 0;
 };
@@ -40,6 +43,9 @@ struct hv_pyr {
 };
 
 int hv_ctx_reserve_stage(hv_ctx* ctx, size_t bytes);
+// Spins until *flag == seq (mapped pinned memory written by a kernel on `stream`); checks the stream for errors while waiting.
+int hv_poll_flag(volatile unsigned* flag, unsigned seq, cudaStream_t stream, const char* who);
+bool hv_polling_enabled();
 
 // kernels (pyramid.cu, lk.cu)
 cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* idx, const uint8_t* const* src, const int* srcPitch,

@@ -763,6 +763,12 @@ static size_t ekf_augment_smem_bytes(int N)
     return ((size_t)n * (size_t)((n + N + 1 + n) | 1) + (size_t)N * 21) * sizeof(double);
 }
 
+bool ekf_update_uses_cluster2(const EkfUpdateArgs& a)
+{
+    static const bool forceSingle = getenv("HV_EKF_SINGLE_CTA") != nullptr, v1 = getenv("HV_EKF_CLUSTER_V1") != nullptr;
+    return !forceSingle && !v1 && !a.useGlobalWork && ekf_cluster2_fits(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT);
+}
+
 cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s)
 {
     // 8-CTA cluster kernel whenever its shared-memory working set fits (n <= 84 at N = 160); the single-CTA kernel

@@ -76,6 +76,10 @@ struct EkfUpdateArgs {
     double defaultSpeed;  // EKF_OP_PSEUDO_VELOCITY
     int useGlobalWork;    // tableau in b.work instead of shared memory
     int symFirst;         // EKF_OP_AUGMENT (cluster kernel): a deferred maintainPositiveSemiDefinite() is applied while P is read
+    // Result words for a polling host (ekf_cluster2.cuh only): sig[0..2] = res[0..2], then sig[3] = sigSeq, written to
+    // mapped pinned host memory at decision time (a check+update continues with the update afterwards). NULL: none.
+    double* sig;
+    double sigSeq;
 };
 
 // Independent outlier checks against the same (m, P): one launch, one 8-CTA cluster per measurement
@@ -128,6 +132,7 @@ size_t ekf_cluster_smem_bytes(int n, int l, int N, bool joseph);
 cudaError_t ekf_launch_update_cluster(const EkfUpdateArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_check_batch(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s);
 bool ekf_cluster2_fits(int n, int l, int N, bool joseph);
+bool ekf_update_uses_cluster2(const EkfUpdateArgs& a);    // the kernel ekf_launch_update will pick reports through a.sig
 cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s);
 cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s);

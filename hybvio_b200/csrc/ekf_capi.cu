@@ -18,6 +18,9 @@ struct hv_ekf {
     double* d_in = nullptr;       // staging for H, f, y uploads
     size_t inDoubles = 0;
     double* h_pin = nullptr;      // pinned host staging: [in (inDoubles) | out (N + 8)]
+    double* h_sig = nullptr;      // mapped pinned result words the kernels write for a polling host: 4 doubles per batch slot
+    double* d_sig = nullptr;      // (device alias)
+    double sigSeq = 0.0;
     // host bookkeeping, exactly the members of EKFImplementation (ekf.cpp:145-151)
     int augmentCount = 0;
     std::vector<double> augmentTimes;
@@ -82,12 +85,16 @@ extern "C" { static int flush_pending(hv_ekf* e); }
 #define EKF_ENTER(e, who)                              \
     do { EKF_ENTER_LAZY(e, who); int rc2_ = flush_pending(e); if (rc2_ != HV_OK) return rc2_; } while (0)
 
-static int launch_update(hv_ekf* e, EkfUpdateArgs& a)
+static void prep_update(hv_ekf* e, EkfUpdateArgs& a)
 {
     a.b = e->b;
     a.noiseScale = e->noiseScale;
     const size_t need = ekf_update_smem_bytes(a.n, e->N);
-    a.useGlobalWork = (a.op != EKF_OP_AUGMENT && need > 200 * 1024) ? 1 : 0;
+    a.useGlobalWork = (a.op != EKF_OP_AUGMENT && need > 200 * 1024 && !ekf_cluster2_fits(a.n, a.l, e->N, false)) ? 1 : 0;
+}
+static int launch_update(hv_ekf* e, EkfUpdateArgs& a)
+{
+    prep_update(e, a);
     HV_CUDA(ekf_launch_update(a, e->ctx->stream));
     e->ctx->launches++;
     return HV_OK;
@@ -149,6 +156,10 @@ static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
     e->b.N = e->N; e->b.trail = e->trail; e->b.mapDim = e->mapDim;
     err = cudaMallocHost(&e->h_pin, (e->inDoubles + N + 8 + EKF_RES_STRIDE * EKF_MAX_BATCH) * sizeof(double));
     if (err != cudaSuccess) { cudaFree(e->d_block); delete e; hv_set_error("hv_ekf_create: cudaMallocHost failed"); return HV_ERR_OOM; }
+    err = cudaHostAlloc(&e->h_sig, 4 * sizeof(double) * (EKF_MAX_BATCH + 1), cudaHostAllocMapped);
+    if (err == cudaSuccess) err = cudaHostGetDevicePointer(&e->d_sig, e->h_sig, 0);
+    if (err != cudaSuccess) { cudaFree(e->d_block); cudaFreeHost(e->h_pin); delete e; hv_set_error("hv_ekf_create: mapped result buffer: %s", cudaGetErrorString(err)); return HV_ERR_OOM; }
+    memset(e->h_sig, 0, 4 * sizeof(double) * (EKF_MAX_BATCH + 1));
     *out = e;
     return HV_OK;
 }
@@ -199,6 +210,7 @@ int hv_ekf_destroy(hv_ekf* e)
     cudaStreamSynchronize(e->ctx->stream);
     cudaFree(e->d_block);
     cudaFreeHost(e->h_pin);
+    cudaFreeHost(e->h_sig);
     delete e;
     return HV_OK;
 }
@@ -482,6 +494,28 @@ static int visual_args(hv_ekf* e, const char* who, int n, int l, double r, doubl
     return HV_OK;
 }
 
+// Waits for `count` result slots of the mapped buffer to carry sequence number seq (kernels of ekf_cluster2.cuh).
+static int poll_results(hv_ekf* e, int count, double seq, const char* who)
+{
+    cudaStream_t s = e->ctx->stream;
+    for (int i = 0; i < count; i++) {
+        volatile double* flag = e->h_sig + 4 * i + 3;
+        for (unsigned long long spins = 1;; spins++) {
+            if (*flag == seq) break;
+            if ((spins & 0xfff) == 0) {
+                const cudaError_t q = cudaStreamQuery(s);
+                if (q == cudaErrorNotReady) continue;
+                if (q != cudaSuccess) { hv_set_error("%s: %s while waiting for the result", who, cudaGetErrorString(q)); return HV_ERR_CUDA; }
+                if (*flag == seq) break;
+                hv_set_error("%s: the kernel finished without reporting its result", who); return HV_ERR_STATE;
+            }
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return HV_OK;
+}
+static bool ekf_polling() { static const bool on = getenv("HV_NO_POLL") == nullptr; return on; }
+
 static int visual_host(hv_ekf* e, const char* who, const double* H, int n, int l, const double* f, const double* y, double r,
                        double rmseThr, int mode, int* vuStatus, double* chi2, double* mOut)
 {
@@ -495,9 +529,22 @@ static int visual_host(hv_ekf* e, const char* who, const double* H, int n, int l
     memcpy(hin, H, nl * sizeof(double)); memcpy(hin + nl, f, n * sizeof(double)); memcpy(hin + nl + n, y, n * sizeof(double));
     HV_CUDA(cudaMemcpyAsync(e->d_in, hin, inD * sizeof(double), cudaMemcpyHostToDevice, s));
     a.H = e->d_in; a.f = e->d_in + nl; a.y = e->d_in + nl + n;
+    prep_update(e, a);
+    const bool polled = ekf_polling() && mode != EKF_MODE_UPDATE && !mOut && ekf_update_uses_cluster2(a);
+    if (polled) { a.sig = e->d_sig; a.sigSeq = (e->sigSeq += 1.0); }
     rc = launch_update(e, a);
     if (rc != HV_OK) return rc;
     if (mode == EKF_MODE_UPDATE && !mOut) return HV_OK;          // asynchronous
+    if (polled) {
+        // the kernel writes (status, chi2, flag) into mapped pinned memory the moment the decision is known; a check+update
+        // carries on with the update while the host already prepares its next call (which is stream-ordered behind it)
+        rc = poll_results(e, 1, a.sigSeq, who);
+        if (rc != HV_OK) return rc;
+        if (vuStatus) *vuStatus = (int)e->h_sig[0];
+        if (chi2) *chi2 = e->h_sig[1];
+        if (e->h_sig[2] != 0.0) { hv_set_error("%s: innovation covariance not positive definite", who); return HV_ERR_STATE; }
+        return HV_OK;
+    }
     double* hout = e->h_pin + e->inDoubles;
     HV_CUDA(cudaMemcpyAsync(hout, e->b.res, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (mOut) HV_CUDA(cudaMemcpyAsync(hout + 8, e->b.m, e->N * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -659,9 +706,19 @@ static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, b
     static const bool v1 = getenv("HV_EKF_CLUSTER_V1") != nullptr;
     bool fits2 = !v1;
     for (int i = 0; i < count && fits2; i++) fits2 = ekf_cluster2_fits(b.it[i].n, b.it[i].l, e->N, false);
+    const bool polled = host && fits2 && ekf_polling();
+    if (polled) { a.sig = e->d_sig; a.sigSeq = (e->sigSeq += 1.0); }
     HV_CUDA(fits2 ? ekf_launch_check_batch2(a, b, s) : ekf_launch_check_batch(a, b, s));
     e->ctx->launches++;
-    if (host) {
+    if (polled) {
+        int rc = poll_results(e, count, a.sigSeq, "hv_ekf_run");
+        if (rc != HV_OK) return rc;
+        for (int i = 0; i < count; i++) {
+            if (vuStatus) vuStatus[first + i] = (int)e->h_sig[4 * i];
+            if (chi2) chi2[first + i] = e->h_sig[4 * i + 1];
+            if (e->h_sig[4 * i + 2] != 0.0) { hv_set_error("hv_ekf_run: op %d: innovation covariance not positive definite", first + i); return HV_ERR_STATE; }
+        }
+    } else if (host) {
         double* hout = e->h_pin + e->inDoubles + e->N + 8;
         HV_CUDA(cudaMemcpyAsync(hout, e->b.res, sizeof(double) * EKF_RES_STRIDE * count, cudaMemcpyDeviceToHost, s));
         HV_CUDA(cudaStreamSynchronize(s));

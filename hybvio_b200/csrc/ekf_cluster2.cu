@@ -27,10 +27,11 @@ __global__ void __launch_bounds__(EK2_NT) ekf_check_batch_cluster2_kernel(EkfUpd
     a.H = it.H; a.f = it.f; a.y = it.y; a.n = it.n; a.l = it.l;
     a.Rdiag = it.Rdiag; a.chi2Thr = it.chi2Thr; a.rmseThr = it.rmseThr; a.skipChi2 = it.skipChi2;
     a.b.res += (size_t)EKF_RES_STRIDE * inst;
+    if (a.sig) a.sig += 4 * inst;
     ek2_body(a, ek2_sm, cluster);
 }
 
-#define EK2_STATIC_SMEM (sizeof(double) * (2 + 64 + 2 + EK2_MAXN) + 256)
+#define EK2_STATIC_SMEM (sizeof(double) * (2 + 128 + 2 + EK2_MAXN) + 256)
 #define EK2_SMEM_LIMIT (227 * 1024)
 
 // Cluster size: 8 (portable) unless HV_EKF_CLUSTER=16 asks for the non-portable size (A/B switch this round).

@@ -46,7 +46,8 @@ __host__ __device__ inline Ek2Geom ek2_geom(int n, int l, int N, bool joseph, in
     g.W = (n + g.B + 1 + (joseph ? n : 0)) | 1;             // tableau row: [S | HP_J | v | (I)]
     g.T = n * g.W;
     g.PB = g.LD * g.B;                                      // own column block of P, ld LD
-    const int E = (n * n + C - 1) / C;
+    const int MTn = (n + 7) >> 3;
+    const int E = (64 * (MTn * (MTn + 1) / 2) + C - 1) / C;    // two-stage: entries of the upper-triangular 8 x 8 tiles of S
     // small S: every CTA leaves its partial in RS and sums all of them itself; else reduce-scatter (own slice in RS) + all-gather
     g.oneStage = n * n <= 1024 ? 1 : 0;
     g.RS = g.oneStage ? n * n : E;
@@ -84,146 +85,208 @@ __device__ __forceinline__ int ek2_aug_src(int i, int drop)
 __device__ __forceinline__ int ek2_special_col(int c) { return c < 3 ? EKF_POS + c : c < 7 ? EKF_ORI + c - 3 : EKF_CAM + c - 7; }
 
 // C(M x Nn) = cinit + A(M x K) B(K x Nn) on the fp64 tensor cores, 8 x 8 tiles dealt to the 16 warps, up to EK2_NI tiles
-// of a warp advance together through k (independent DMMA chains). fa(m, k) / fb(k, n) return the operands (0 outside the
-// matrix), cinit(m, n) the initial value, store(m, n, v0, v1) receives C(m, n), C(m, n + 1) for m < M, n < Nn (n even).
+// of a warp advance together through k (independent DMMA chains, operands of step k+1 loaded while step k multiplies).
+// fa(m, k) / fb(k, n) are called with indices CLAMPED into the matrix (so every load is unconditional and in bounds: no
+// branches between the loads, which would serialise them behind the warp-synchronous MMAs); contributions of k >= K are
+// zeroed with a select, rows / columns beyond the matrix produce values that are never stored. cinit(m, n) gives the
+// initial value, store(m, n, v0, v1) receives C(m, n), C(m, n + 1) for m < M, n < Nn (n even).
 #define EK2_NI 4
-template <class FA, class FB, class FCI, class FST>
+// Upper-triangular tile list of a symmetric matrix (column-tile major): tu = nt (nt + 1) / 2 + mt, mt <= nt
+__host__ __device__ inline void ek2_upper_tile(int tu, int& mt, int& nt)
+{
+    nt = (int)((sqrtf(8.0f * (float)tu + 1.0f) - 1.0f) * 0.5f);
+    while ((nt + 1) * (nt + 2) / 2 <= tu) nt++;
+    while (nt * (nt + 1) / 2 > tu) nt--;
+    mt = tu - nt * (nt + 1) / 2;
+}
+// UPPER: C is symmetric (M == Nn) and only its tiles on or above the diagonal are computed and stored
+template <bool UPPER = false, class FA, class FB, class FCI, class FST>
 __device__ __forceinline__ void ek2_dmma_gemm(int M, int Nn, int K, int wrp, int lane, FA fa, FB fb, FCI cinit, FST store)
 {
     const int g8 = lane >> 2, t4 = lane & 3;
-    const int MT = (M + 7) >> 3, NT = (Nn + 7) >> 3, tiles = MT * NT, KT = (K + 3) >> 2;
+    const int MT = (M + 7) >> 3, NT = (Nn + 7) >> 3, tiles = UPPER ? MT * (MT + 1) / 2 : MT * NT, KT = (K + 3) >> 2;
     const int nwarps = EK2_NT / 32;
+    if (M <= 0 || Nn <= 0) return;
+    const int Kc = max(K, 1) - 1;                                         // last valid k (K == 0: nothing is multiplied, C = cinit)
     for (int base = wrp; base < tiles; base += nwarps * EK2_NI) {
         double c0[EK2_NI], c1[EK2_NI];
-        int row[EK2_NI], colb[EK2_NI], col[EK2_NI];
+        int row[EK2_NI], colb[EK2_NI], col[EK2_NI], rowc[EK2_NI], colbc[EK2_NI];
         bool ok[EK2_NI];
 #pragma unroll
         for (int q = 0; q < EK2_NI; q++) {
             const int tile = base + q * nwarps;
-            ok[q] = tile < tiles;                                         // warp-uniform
-            const int mt = tile % MT, nt = tile / MT;
+            ok[q] = tile < tiles;                                         // warp-uniform; surplus slots redo the last tile, unstored
+            const int tl = min(tile, tiles - 1);
+            int mt, nt;
+            if (UPPER) ek2_upper_tile(tl, mt, nt); else { mt = tl % MT; nt = tl / MT; }
             row[q] = mt * 8 + g8; colb[q] = nt * 8 + g8; col[q] = nt * 8 + 2 * t4;
-            c0[q] = 0.0; c1[q] = 0.0;
-            if (ok[q] && row[q] < M) { if (col[q] < Nn) c0[q] = cinit(row[q], col[q]); if (col[q] + 1 < Nn) c1[q] = cinit(row[q], col[q] + 1); }
+            rowc[q] = min(row[q], M - 1); colbc[q] = min(colb[q], Nn - 1);
+            c0[q] = cinit(rowc[q], min(col[q], Nn - 1)); c1[q] = cinit(rowc[q], min(col[q] + 1, Nn - 1));
         }
-        for (int kt = 0; kt < KT; kt++) {
-            const int kk = kt * 4 + t4;
-#pragma unroll
-            for (int q = 0; q < EK2_NI; q++)
-                if (ok[q]) hv_dmma(c0[q], c1[q], fa(row[q], kk), fb(kk, colb[q]));
+        // two operand buffers with STATIC indices (a runtime-indexed buffer would live in local memory)
+        double a0[EK2_NI], b0[EK2_NI], a1[EK2_NI], b1[EK2_NI];
+#define EK2_LOAD(A_, B_, KT_)                                                                                     \
+        {                                                                                                         \
+            const int kk_ = (KT_) * 4 + t4, kc_ = min(kk_, Kc);                                                   \
+            _Pragma("unroll") for (int q = 0; q < EK2_NI; q++) {                                                  \
+                const double x_ = fa(rowc[q], kc_); A_[q] = kk_ < K ? x_ : 0.0; B_[q] = fb(kc_, colbc[q]);        \
+            }                                                                                                     \
         }
+#define EK2_MMA(A_, B_) { _Pragma("unroll") for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], A_[q], B_[q]); }
+        EK2_LOAD(a0, b0, 0)
+        for (int kt = 0; kt < KT; kt += 2) {
+            EK2_LOAD(a1, b1, kt + 1)                                      // loads past the end are clamped and zeroed
+            EK2_MMA(a0, b0)
+            if (kt + 1 < KT) {
+                EK2_LOAD(a0, b0, kt + 2)
+                EK2_MMA(a1, b1)
+            }
+        }
+#undef EK2_LOAD
+#undef EK2_MMA
 #pragma unroll
         for (int q = 0; q < EK2_NI; q++)
             if (ok[q] && row[q] < M && col[q] < Nn) store(row[q], col[q], c0[q], c1[q]);
     }
 }
 
+// Factorisation of the 8 x 8 diagonal block D = T[r0 .. r0+nb, r0 .. r0+nb] of the current Schur complement by ONE warp with
+// shuffles only: lanes 0..7 hold the columns of D (padded with the identity), lanes 8..15 those of I; the row operations
+// of the Cholesky factorisation applied to both leave L_jj' in the first and L_jj^-1 (lower triangular) in the second
+// group, which is written to linv (8 x 8, row-major). 8 dependent pivots: the only serial part of the elimination.
+__device__ __forceinline__ void ek2_diag_factor(const double* T, int W, int r0, int nb, int lane, double* linv, volatile int* s_bad)
+{
+    double v[8];
+    const int cidx = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const double t = T[(size_t)(r0 + min(i, nb - 1)) * W + r0 + min(cidx, nb - 1)];
+        double x = (i == cidx) ? 1.0 : 0.0;
+        if (lane < 8 && i < nb && cidx < nb) x = t;
+        if (lane >= 16) x = 0.0;
+        v[i] = x;
+    }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const double akk = __shfl_sync(0xffffffffu, v[k], k);
+        if (!(akk > 0.0)) ok = false;
+        const double r = rsqrt(akk);
+        const double u = v[k] * r;                 // scaled pivot row, entry of this column
+        v[k] = u;
+#pragma unroll
+        for (int i = k + 1; i < 8; i++) {
+            const double mi = __shfl_sync(0xffffffffu, u, i);      // S is symmetric: multiplier of row i = entry i of the scaled pivot row
+            v[i] = fma(-mi, u, v[i]);
+        }
+    }
+    if (lane >= 8 && lane < 16) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) linv[i * 8 + (lane - 8)] = v[i];
+    }
+    if (!ok && lane == 0) *s_bad = 1;
+}
+
 // Blocked forward elimination of the tableau T = [ S | Y ] (n rows, columns 0 .. ncols-1, row-major, ld W) in shared
-// memory: S = L L' (never pivoted: R > 0 makes S positive definite), Y <- L^-1 Y, by 8-row blocks:
-//   1. ONE warp factors the 8 x 8 diagonal block D of the current Schur complement with shuffles only (column per lane;
-//      the same row operations applied to an identity give L_jj^-1) -- the only serial part: 8 pivots per block;
-//   2. all warps: rows of the block <- L_jj^-1 * rows (8 x 8 x 8 DMMA per column tile);
-//   3. all warps: trailing update T[i, c] -= U_j[:, i]' U_j[:, c] for the rows below, upper triangle of S and all of Y
-//      (8 x 8 x 8 DMMA per tile, several tiles of a warp in flight).
-// Three barriers per 8 pivots; the first generation (ekf_elim.cuh) needed one barrier per two pivots and kept the
-// tableau in registers, which bounded n <= 96. Returns false (uniformly) on a non-positive pivot.
+// memory: S = L L' (never pivoted: R > 0 makes S positive definite), Y <- L^-1 Y, by 8-row blocks j:
+//   a. all warps: rows of block j <- L_jj^-1 * rows (8 x 8 x 8 DMMA per column tile);
+//   b. trailing update T[i, c] -= U_j[:, i]' U_j[:, c] for the rows below, upper triangle of S and all of Y (8 x 8 x 8 DMMA
+//      per tile, several tiles of a warp in flight) by warps 1..15, WHILE warp 0 updates the next diagonal tile first and
+//      factors it (ek2_diag_factor: look-ahead), so that the serial pivot chain overlaps the bulk work.
+// Two barriers per 8 pivots; the first generation (ekf_elim.cuh) needed one barrier per two pivots and kept the tableau
+// in registers, which bounded n <= 96. Returns false (uniformly) on a non-positive pivot. s_linv: 2 x 64 doubles.
 __device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int ncols, int wrp, int lane, double* s_linv, volatile int* s_bad)
 {
     const int g8 = lane >> 2, t4 = lane & 3;
     const int nwarps = EK2_NT / 32;
     const int MT = (n + 7) >> 3, CT = (ncols + 7) >> 3;
-    if (wrp == 0 && lane == 0) *s_bad = 0;
+    if (wrp == 0) {
+        if (lane == 0) *s_bad = 0;
+        __syncwarp();
+        ek2_diag_factor(T, W, 0, min(8, n), lane, s_linv, s_bad);
+    }
     __syncthreads();
     for (int j = 0; j < MT; j++) {
-        const int r0 = 8 * j, nb = min(8, n - r0);
-        // ---- 1. diagonal block: lanes 0..7 hold the columns of D (padded with the identity), lanes 8..15 those of I
-        if (wrp == 0) {
-            double v[8];
-            const int cidx = lane & 7;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                double x = (i == cidx) ? 1.0 : 0.0;
-                if (lane < 8 && i < nb && cidx < nb) x = T[(size_t)(r0 + i) * W + r0 + cidx];
-                if (lane >= 16) x = 0.0;
-                v[i] = x;
-            }
-            bool ok = true;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const double akk = __shfl_sync(0xffffffffu, v[k], k);
-                if (!(akk > 0.0)) ok = false;
-                const double r = rsqrt(akk);
-                const double u = v[k] * r;                 // scaled pivot row, entry of this column
-                v[k] = u;
-#pragma unroll
-                for (int i = k + 1; i < 8; i++) {
-                    const double mi = __shfl_sync(0xffffffffu, u, i);      // S is symmetric: multiplier of row i = entry i of the scaled pivot row
-                    v[i] = fma(-mi, u, v[i]);
-                }
-            }
-            if (lane >= 8 && lane < 16) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) s_linv[i * 8 + (lane - 8)] = v[i];      // L_jj^-1 (lower triangular)
-            }
-            if (!ok && lane == 0) *s_bad = 1;
-        }
-        __syncthreads();
         if (*s_bad) return false;
-        // ---- 2. rows of the block <- L_jj^-1 * rows, column tiles j .. CT-1
+        const int r0 = 8 * j, nb = min(8, n - r0);
+        const double* linv = s_linv + (j & 1) * 64;
+        // ---- a. rows of the block <- L_jj^-1 * rows, column tiles j .. CT-1 (loads clamped into the tableau: no branches)
         for (int ct = j + wrp; ct < CT; ct += nwarps) {
             double c0 = 0.0, c1 = 0.0;
-            const int colb = 8 * ct + g8;
+            const int colbc = min(8 * ct + g8, ncols - 1);
             double bf[2];
 #pragma unroll
-            for (int kt = 0; kt < 2; kt++) { const int k = kt * 4 + t4; bf[kt] = (k < nb && colb < ncols) ? T[(size_t)(r0 + k) * W + colb] : 0.0; }
+            for (int kt = 0; kt < 2; kt++) {
+                const int k = kt * 4 + t4;
+                const double x = T[(size_t)(r0 + min(k, nb - 1)) * W + colbc];
+                bf[kt] = k < nb ? x : 0.0;
+            }
 #pragma unroll
-            for (int kt = 0; kt < 2; kt++) hv_dmma(c0, c1, s_linv[g8 * 8 + kt * 4 + t4], bf[kt]);
+            for (int kt = 0; kt < 2; kt++) hv_dmma(c0, c1, linv[g8 * 8 + kt * 4 + t4], bf[kt]);
             const int col = 8 * ct + 2 * t4;
             if (g8 < nb) { if (col < ncols) T[(size_t)(r0 + g8) * W + col] = c0; if (col + 1 < ncols) T[(size_t)(r0 + g8) * W + col + 1] = c1; }
         }
         __syncthreads();
-        // ---- 3. trailing update: row tiles mt > j, column tiles nt >= mt
+        // ---- b. trailing update: row tiles mt > j, column tiles nt >= mt; tile 0 of that list is the next diagonal tile
         if (j + 1 < MT) {
             const int first = j + 1;
             int total = 0;
             for (int mt = first; mt < MT; mt++) total += CT - mt;
-            for (int base = wrp; base < total; base += nwarps * EK2_NI) {
+            const bool ahead = wrp == 0;                                   // warp 0: next diagonal tile, then its factorisation
+            const int lanes_w = ahead ? 1 : nwarps - 1;                    // stride of this warp's tile list
+            for (int base = ahead ? 0 : wrp; base < (ahead ? 1 : total); base += lanes_w * EK2_NI) {
                 double c0[EK2_NI], c1[EK2_NI], af[EK2_NI][2], bfr[EK2_NI][2];
                 int rowi[EK2_NI], coli[EK2_NI];
                 bool ok[EK2_NI];
 #pragma unroll
                 for (int q = 0; q < EK2_NI; q++) {
-                    int idx = base + q * nwarps;
-                    ok[q] = idx < total;                                   // warp-uniform
+                    int idx = base + q * lanes_w;
+                    ok[q] = idx < total && !(ahead && q > 0);              // warp-uniform; surplus slots redo the last tile, unstored
+                    idx = min(idx, total - 1);
                     int mt = first;
-                    while (ok[q] && idx >= CT - mt) { idx -= CT - mt; mt++; }
+                    while (idx >= CT - mt) { idx -= CT - mt; mt++; }
                     const int nt = mt + idx;
                     rowi[q] = 8 * mt + g8; coli[q] = 8 * nt + 2 * t4;
-                    c0[q] = 0.0; c1[q] = 0.0; af[q][0] = af[q][1] = bfr[q][0] = bfr[q][1] = 0.0;
-                    if (ok[q]) {
-                        if (rowi[q] < n) { if (coli[q] < ncols) c0[q] = T[(size_t)rowi[q] * W + coli[q]]; if (coli[q] + 1 < ncols) c1[q] = T[(size_t)rowi[q] * W + coli[q] + 1]; }
+                    const int rc = min(rowi[q], n - 1);
+                    c0[q] = T[(size_t)rc * W + min(coli[q], ncols - 1)];
+                    c1[q] = T[(size_t)rc * W + min(coli[q] + 1, ncols - 1)];
+                    const int am = min(8 * mt + g8, ncols - 1), bn = min(8 * nt + g8, ncols - 1);
 #pragma unroll
-                        for (int kt = 0; kt < 2; kt++) {
-                            const int k = kt * 4 + t4;
-                            const int am = 8 * mt + g8, bn = 8 * nt + g8;
-                            af[q][kt] = (k < nb && am < ncols) ? -T[(size_t)(r0 + k) * W + am] : 0.0;     // A[m][k] = -U_j[k][8 mt + m]
-                            bfr[q][kt] = (k < nb && bn < ncols) ? T[(size_t)(r0 + k) * W + bn] : 0.0;     // B[k][nn] = U_j[k][8 nt + nn]
-                        }
+                    for (int kt = 0; kt < 2; kt++) {
+                        const int k = kt * 4 + t4;
+                        const double* rowk = T + (size_t)(r0 + min(k, nb - 1)) * W;
+                        const double xa = rowk[am], xb = rowk[bn];
+                        af[q][kt] = k < nb ? -xa : 0.0;                    // A[m][k] = -U_j[k][8 mt + m]
+                        bfr[q][kt] = xb;                                   // B[k][nn] = U_j[k][8 nt + nn]
                     }
                 }
 #pragma unroll
                 for (int kt = 0; kt < 2; kt++)
 #pragma unroll
-                    for (int q = 0; q < EK2_NI; q++)
-                        if (ok[q]) hv_dmma(c0[q], c1[q], af[q][kt], bfr[q][kt]);
+                    for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], af[q][kt], bfr[q][kt]);
 #pragma unroll
                 for (int q = 0; q < EK2_NI; q++)
                     if (ok[q] && rowi[q] < n) { if (coli[q] < ncols) T[(size_t)rowi[q] * W + coli[q]] = c0[q]; if (coli[q] + 1 < ncols) T[(size_t)rowi[q] * W + coli[q] + 1] = c1[q]; }
             }
+            if (ahead) {
+                __syncwarp();
+                ek2_diag_factor(T, W, 8 * first, min(8, n - 8 * first), lane, s_linv + (first & 1) * 64, s_bad);
+            }
             __syncthreads();
         }
     }
-    return true;
+    return !*s_bad;
+}
+
+// Result words (VuOutlierStatus, chi2, numeric flag): device copy + optional mapped-host copy with a sequence flag
+__device__ __forceinline__ void ek2_report(const EkfUpdateArgs& a, double st, double chi2, double flag)
+{
+    a.b.res[0] = st; a.b.res[1] = chi2; a.b.res[2] = flag;
+    if (a.sig) {
+        a.sig[0] = st; a.sig[1] = chi2; a.sig[2] = flag;
+        __threadfence_system();
+        ((volatile double*)a.sig)[3] = a.sigSeq;
+    }
 }
 
 // `Cluster` is cooperative_groups::cluster_group (or the emulator's stand-in).
@@ -231,7 +294,7 @@ template <class Cluster>
 __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster cluster)
 {
     __shared__ double s_scalar[2];
-    __shared__ double s_linv[64];
+    __shared__ double s_linv[128];
     __shared__ int s_bad;
     __shared__ double s_m[EK2_MAXN];
     const int c = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
@@ -328,28 +391,29 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     if (checking && a.rmseThr >= 0.0) {               // ekf.cpp:797-801
         if (tid == 0) { double ss = 0.0; for (int i = 0; i < n; i++) { const double v = T[(size_t)i * W + vcol]; ss += v * v; } s_scalar[0] = sqrt(ss / n); }
         __syncthreads();
-        if (s_scalar[0] > a.rmseThr) { if (c == 0 && tid == 0) { a.b.res[0] = 2.0; a.b.res[1] = 0.0; a.b.res[2] = 0.0; } return; }
+        if (s_scalar[0] > a.rmseThr) { if (c == 0 && tid == 0) ek2_report(a, 2.0, 0.0, 0.0); return; }
     }
     if (checking && a.skipChi2 && a.mode == EKF_MODE_CHECK) {
-        if (c == 0 && tid == 0) { a.b.res[0] = 0.0; a.b.res[1] = 0.0; a.b.res[2] = 0.0; }
+        if (c == 0 && tid == 0) ek2_report(a, 0.0, 0.0, 0.0);
         return;
     }
 
     EK2_PHASE(1);
     // ---- phase A: HP[:, J_c] = H P[0:l, J_c] on the fp64 tensor cores (n x Bc x l)
     ek2_dmma_gemm(n, Bc, l, wrp, lane,
-                  [&](int i, int k) { return (i < n && k < l) ? Hs[i + (size_t)k * n] : 0.0; },
-                  [&](int k, int j) { return (k < l && j < Bc) ? PB[k + (size_t)j * LD] : 0.0; },
+                  [&](int i, int k) { return Hs[i + (size_t)k * n]; },
+                  [&](int k, int j) { return PB[k + (size_t)j * LD]; },
                   [](int, int) { return 0.0; },
                   [&](int i, int j, double v0, double v1) { T[(size_t)i * W + n + j] = v0; if (j + 1 < Bc) T[(size_t)i * W + n + j + 1] = v1; });
     __syncthreads();
     EK2_PHASE(2);
-    // ---- phase B: partial S = HP[:, J_c within [0, l)] H[:, J_c]' into the S part of the own tableau (n x n x kc)
+    // ---- phase B: partial S = HP[:, J_c within [0, l)] H[:, J_c]' (n x n x kc), tiles on or above the diagonal only: the
+    // blocked elimination never reads S below its diagonal tiles
     {
         const int kc = max(0, min(Bc, l - J0));
-        ek2_dmma_gemm(n, n, kc, wrp, lane,
-                      [&](int i, int k) { return (i < n && k < kc) ? T[(size_t)i * W + n + k] : 0.0; },
-                      [&](int k, int j) { return (k < kc && j < n) ? Hs[j + (size_t)(J0 + k) * n] : 0.0; },
+        ek2_dmma_gemm<true>(n, n, kc, wrp, lane,
+                      [&](int i, int k) { return T[(size_t)i * W + n + k]; },
+                      [&](int k, int j) { return Hs[j + (size_t)(J0 + k) * n]; },
                       [](int, int) { return 0.0; },
                       [&](int i, int j, double v0, double v1) {
                           if (oneStage) { RS[i * n + j] = v0; if (j + 1 < n) RS[i * n + j + 1] = v1; }      // partial stays out of the tableau
@@ -359,75 +423,105 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     EK2_PHASE(3);
     cluster.sync();                                   // #1: every partial S is in place (and from here on shared memory is exposed)
     // ---- reduce S through distributed shared memory, fixed order r = 0 .. C-1 (+ R on the diagonal)
-    if (oneStage) {
-        for (int e = tid; e < n * n; e += EK2_NT) {
-            const int i = e / n, ip = e - i * n;
-            double s = 0.0;
-            for (int r = 0; r < C; r++) s += cluster.map_shared_rank(RS, r)[e];
-            if (i == ip) s += a.Rdiag;
-            T[(size_t)i * W + ip] = s;                 // the own tableau is not read by anybody else
+    {
+        const int MTs = (n + 7) >> 3, ETOT = 64 * (MTs * (MTs + 1) / 2);   // entries of the upper-triangular tiles, tile by tile
+        auto entry = [&](int e, int& i, int& ip) { int mt, nt; ek2_upper_tile(e >> 6, mt, nt); i = 8 * mt + ((e >> 3) & 7); ip = 8 * nt + (e & 7); };
+        if (oneStage) {
+            for (int e = tid; e < ETOT; e += EK2_NT) {
+                int i, ip; entry(e, i, ip);
+                if (i < n && ip < n) {
+                    double s = 0.0;
+                    for (int r = 0; r < C; r++) s += cluster.map_shared_rank(RS, r)[i * n + ip];
+                    if (i == ip) s += a.Rdiag;
+                    T[(size_t)i * W + ip] = s;             // the own tableau is not read by anybody else
+                }
+            }
+            __syncthreads();
+        } else {
+            const int E = (ETOT + C - 1) / C, e0 = c * E, e1 = min(ETOT, e0 + E);
+            for (int e = e0 + tid; e < e1; e += EK2_NT) {
+                int i, ip; entry(e, i, ip);
+                double s = 0.0;
+                if (i < n && ip < n) {
+                    for (int r = 0; r < C; r++) s += cluster.map_shared_rank(T, r)[(size_t)i * W + ip];
+                    if (i == ip) s += a.Rdiag;
+                }
+                RS[e - e0] = s;
+            }
+            cluster.sync();                               // #2: all slices reduced; nobody reads the partials any more
+            for (int e = tid; e < ETOT; e += EK2_NT) {
+                int i, ip; entry(e, i, ip);
+                const int r = e / E;
+                if (i < n && ip < n) T[(size_t)i * W + ip] = cluster.map_shared_rank(RS, r)[e - r * E];
+            }
+            __syncthreads();
         }
-        __syncthreads();
-    } else {
-        const int E = (n * n + C - 1) / C, e0 = c * E, e1 = min(n * n, e0 + E);
-        for (int e = e0 + tid; e < e1; e += EK2_NT) {
-            const int i = e / n, ip = e - i * n;
-            double s = 0.0;
-            for (int r = 0; r < C; r++) s += cluster.map_shared_rank(T, r)[(size_t)i * W + ip];
-            if (i == ip) s += a.Rdiag;
-            RS[e - e0] = s;
-        }
-        cluster.sync();                               // #2: all slices reduced; nobody reads the partials any more
-        for (int e = tid; e < n * n; e += EK2_NT) {
-            const int r = e / E;
-            T[(size_t)(e / n) * W + (e % n)] = cluster.map_shared_rank(RS, r)[e - r * E];
-        }
-        __syncthreads();
     }
 
     EK2_PHASE(4);
     // ---- blocked forward elimination of [S | HP_Jc | v | (I)]: the right part becomes Z = L^-1 (.)
     const bool bad = !ek2_block_eliminate(T, W, n, cend + 1, wrp, lane, s_linv, &s_bad);
     if (bad) {                                        // uniform over the cluster
-        if (c == 0 && tid == 0) { a.b.res[0] = 1.0; a.b.res[1] = 0.0; a.b.res[2] = 1.0; }
+        if (c == 0 && tid == 0) ek2_report(a, 1.0, 0.0, 1.0);
         cluster.sync();
         return;
     }
     __syncthreads();
     EK2_PHASE(5);
-    if (tid == 0) { double t = 0.0; for (int k = 0; k < n; k++) { const double z = T[(size_t)k * W + vcol]; t += z * z; } s_scalar[1] = a.noiseScale * t; }
+    if (wrp == 0) {                                   // chi2 = noiseScale |z_v|^2 (ekf.cpp:815): lane-strided sums, fixed shuffle tree
+        double t = 0.0;
+        for (int k = lane; k < n; k += 32) { const double z = T[(size_t)k * W + vcol]; t += z * z; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_sync(0xffffffffu, t, lane ^ o);
+        if (lane == 0) s_scalar[1] = a.noiseScale * t;
+    }
     __syncthreads();
     const double chi2 = s_scalar[1];
     if (checking) {
         const bool outlier = !a.skipChi2 && chi2 > a.chi2Thr;
-        if (c == 0 && tid == 0) { a.b.res[0] = outlier ? 3.0 : 0.0; a.b.res[1] = chi2; a.b.res[2] = 0.0; }
+        if (c == 0 && tid == 0) ek2_report(a, outlier ? 3.0 : 0.0, chi2, 0.0);
         if (outlier || a.mode == EKF_MODE_CHECK) { cluster.sync(); return; }
-    } else if (c == 0 && tid == 0) { a.b.res[0] = 0.0; a.b.res[1] = chi2; a.b.res[2] = 0.0; }
+    } else if (c == 0 && tid == 0) ek2_report(a, 0.0, chi2, 0.0);
 
     EK2_PHASE(6);
     // ---- gather Z (n x N, row-major) out of the neighbours' tableaus, then P[:, J_c] -= Z' Z[:, J_c] in shared memory
-    cluster.sync();                                   // #3: every Z slice is final
     double* Z = X;                                    // H is dead
-    for (int t = tid; t < n * N; t += EK2_NT) {       // one flat pass: all remote loads of a thread are independent
-        const int k = t / N, col = t - k * N, r = col / B;
-        Z[(size_t)k * LD + col] = cluster.map_shared_rank(T, r)[(size_t)k * W + n + (col - r * B)];
+    if ((size_t)n * N >= 4096 && a.b.cwork) {
+        // large Z: through L2 (measured on B200: a CTA pulls a remote shared-memory block at ~15 B/clk, an L2-resident one
+        // at ~34 B/clk); every CTA publishes its slice, cluster barrier (release / acquire covers global memory), bulk read
+        double* Zg = a.b.cwork;
+        for (int t = tid; t < n * Bc; t += EK2_NT) { const int k = t / Bc, jj = t - k * Bc; Zg[(size_t)k * N + J0 + jj] = T[(size_t)k * W + n + jj]; }
+        cluster.sync();                               // #3
+        for (int base = 0; base < n * N; base += 8 * EK2_NT) {
+            double r[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int t = base + u * EK2_NT + tid; r[u] = t < n * N ? Zg[t] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int t = base + u * EK2_NT + tid; if (t < n * N) Z[(size_t)(t / N) * LD + (t % N)] = r[u]; }
+        }
+    } else {
+        cluster.sync();                               // #3: every Z slice is final
+        for (int t = tid; t < n * N; t += EK2_NT) {   // small Z: straight out of the neighbours' tableaus, one flat pass
+            const int k = t / N, col = t - k * N, r = col / B;
+            Z[(size_t)k * LD + col] = cluster.map_shared_rank(T, r)[(size_t)k * W + n + (col - r * B)];
+        }
     }
     __syncthreads();
     EK2_PHASE(7);
     // P[:, J_c] -= Z' Z[:, J_c] on the fp64 tensor cores (N x Bc x n), in place in the shared-memory block
     ek2_dmma_gemm(N, Bc, n, wrp, lane,
-                  [&](int i, int k) { return (i < N && k < n) ? -Z[(size_t)k * LD + i] : 0.0; },
-                  [&](int k, int j) { return (k < n && j < Bc) ? Z[(size_t)k * LD + J0 + j] : 0.0; },
+                  [&](int i, int k) { return -Z[(size_t)k * LD + i]; },
+                  [&](int k, int j) { return Z[(size_t)k * LD + J0 + j]; },
                   [&](int i, int j) { return PB[i + (size_t)j * LD]; },
                   [&](int i, int j, double v0, double v1) { PB[i + (size_t)j * LD] = v0; if (j + 1 < Bc) PB[i + (size_t)(j + 1) * LD] = v1; });
     // state mean: m += Z' z_v (CTA 0 owns the write-back; quaternion normalisation: updateCommon normalises the current
     // orientation only, the visual update and the augmentation all of them, ekf.cpp:31, 843, 874)
     if (c == 0) {
-        for (int i = tid; i < N; i += EK2_NT) {
-            double s = 0.0;
-            for (int k = 0; k < n; k++) s += Z[(size_t)k * LD + i] * T[(size_t)k * W + vcol];
-            s_m[i] += s;
-        }
+        ek2_dmma_gemm(N, 1, n, wrp, lane,
+                      [&](int i, int k) { return Z[(size_t)k * LD + i]; },
+                      [&](int k, int) { return T[(size_t)k * W + vcol]; },
+                      [&](int i, int) { return s_m[i]; },
+                      [&](int i, int, double v0, double) { s_m[i] = v0; });
         __syncthreads();
         for (int q = tid; q < (a.normalizeAll ? a.b.trail + 1 : 1); q += EK2_NT)
             ek2_normalize_quat(q == 0 ? s_m + EKF_ORI : s_m + EKF_CAM + EKF_POSE * (q - 1) + 3);

@@ -79,8 +79,17 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
         const double dt = S.dt;
         const double w0 = S.xg[0] - bg0, w1 = S.xg[1] - bg1, w2 = S.xg[2] - bg2;
         const double c = -dt / 2;
-        const double th = sqrt(w0 * w0 + w1 * w1 + w2 * w2) * fabs(c);
-        const double ct = cos(th), sc = th < 1e-8 ? 1.0 - th * th / 6.0 : sin(th) / th;
+        // cos(th) and sin(th)/th are even in th = |w| dt / 2: for the small angles of an IMU step (th^2 < 0.01) their Taylor
+        // series in x = th^2 reach double precision with 6 terms -- no sqrt, no fp64 sin/cos on the critical path
+        const double x = (w0 * w0 + w1 * w1 + w2 * w2) * (c * c);
+        double ct, sc;
+        if (x < 0.01) {
+            ct = 1.0 + x * (-1.0 / 2 + x * (1.0 / 24 + x * (-1.0 / 720 + x * (1.0 / 40320 + x * (-1.0 / 3628800 + x * (1.0 / 479001600))))));
+            sc = 1.0 + x * (-1.0 / 6 + x * (1.0 / 120 + x * (-1.0 / 5040 + x * (1.0 / 362880 + x * (-1.0 / 39916800 + x * (1.0 / 6227020800.0))))));
+        } else {
+            const double th = sqrt(x);
+            ct = cos(th); sc = sin(th) / th;
+        }
         if (lane < 16) {
             // Omega row-major {0,-w0,-w1,-w2, w0,0,-w2,w1, w1,w2,0,-w0, w2,-w1,w0,0}: component (3 = zero) / sign per entry
             const int comp = (0xC6396C93u >> (2 * lane)) & 3;

@@ -57,6 +57,12 @@ struct LkLaunch {
     int maxIter;                // already clamped to [0,100]
     double eps2;                // already clamped and squared
     float minEig;
+    // Completion signal for the host-buffer API (single job, CTA-per-feature kernel): every CTA bumps *doneCounter after
+    // its results are visible system-wide; the one that reaches doneTarget stores seq into *hostFlag (mapped pinned host
+    // memory), which the host polls instead of a D2H copy + stream synchronisation. NULL: no signal.
+    unsigned* doneCounter;
+    unsigned doneTarget, seq;
+    volatile unsigned* hostFlag;
 };
 
 

@@ -59,6 +59,8 @@ void launch_cta(int nthreads, unsigned bx, F&& body)
 }
 }  // namespace emu
 
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __syncthreads() { emu::cta->bar.arrive_and_wait(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::cta->wbar[threadIdx.x >> 5]->arrive_and_wait(); }
 // full-warp shuffle: EVERY lane of the warp must call it (what the kernels written for the emulator do)
