@@ -99,18 +99,25 @@ __host__ __device__ inline void ek2_upper_tile(int tu, int& mt, int& nt)
     while (nt * (nt + 1) / 2 > tu) nt--;
     mt = tu - nt * (nt + 1) / 2;
 }
-// UPPER: C is symmetric (M == Nn) and only its tiles on or above the diagonal are computed and stored
-template <bool UPPER = false, class FA, class FB, class FCI, class FST>
-__device__ __forceinline__ void ek2_dmma_gemm(int M, int Nn, int K, int wrp, int lane, FA fa, FB fb, FCI cinit, FST store)
+// UPPER: C is symmetric (M == Nn) and only its tiles on or above the diagonal are computed and stored.
+// Operands are AFFINE views of shared memory, A(m, k) = A[m sAm + k sAk], B(k, n) = B[k sBk + n sBn]: a k-step of a tile is
+// two loads off running pointers and one DMMA -- with only 256 FMAs per MMA the instruction count around it decides the
+// speed (the first version took its operands through index-clamping lambdas: ~15 instructions per MMA, and was issue-bound
+// at a third of the tensor-core rate).
+template <bool UPPER = false, class FCI, class FST>
+__device__ __forceinline__ void ek2_dmma_gemm(int M, int Nn, int K, int wrp, int lane, const double* A, int sAm, int sAk,
+                                              const double* B, int sBk, int sBn, FCI cinit, FST store)
 {
     const int g8 = lane >> 2, t4 = lane & 3;
-    const int MT = (M + 7) >> 3, NT = (Nn + 7) >> 3, tiles = UPPER ? MT * (MT + 1) / 2 : MT * NT, KT = (K + 3) >> 2;
+    const int MT = (M + 7) >> 3, NT = (Nn + 7) >> 3, tiles = UPPER ? MT * (MT + 1) / 2 : MT * NT;
     const int nwarps = EK2_NT / 32;
     if (M <= 0 || Nn <= 0) return;
-    const int Kc = max(K, 1) - 1;                                         // last valid k (K == 0: nothing is multiplied, C = cinit)
+    const int KF = K >> 2, tail = K & 3;                                  // full k-steps, leftover k's
+    const int dA = 4 * sAk, dB = 4 * sBk;
     for (int base = wrp; base < tiles; base += nwarps * EK2_NI) {
         double c0[EK2_NI], c1[EK2_NI];
-        int row[EK2_NI], colb[EK2_NI], col[EK2_NI], rowc[EK2_NI], colbc[EK2_NI];
+        int row[EK2_NI], col[EK2_NI];
+        const double* pa[EK2_NI]; const double* pb[EK2_NI];
         bool ok[EK2_NI];
 #pragma unroll
         for (int q = 0; q < EK2_NI; q++) {
@@ -119,31 +126,41 @@ __device__ __forceinline__ void ek2_dmma_gemm(int M, int Nn, int K, int wrp, int
             const int tl = min(tile, tiles - 1);
             int mt, nt;
             if (UPPER) ek2_upper_tile(tl, mt, nt); else { mt = tl % MT; nt = tl / MT; }
-            row[q] = mt * 8 + g8; colb[q] = nt * 8 + g8; col[q] = nt * 8 + 2 * t4;
-            rowc[q] = min(row[q], M - 1); colbc[q] = min(colb[q], Nn - 1);
-            c0[q] = cinit(rowc[q], min(col[q], Nn - 1)); c1[q] = cinit(rowc[q], min(col[q] + 1, Nn - 1));
+            row[q] = mt * 8 + g8; col[q] = nt * 8 + 2 * t4;
+            const int rowc = min(row[q], M - 1), colbc = min(nt * 8 + g8, Nn - 1);   // rows / columns past the matrix: clamped, never stored
+            pa[q] = A + (size_t)rowc * sAm + (size_t)t4 * sAk;
+            pb[q] = B + (size_t)t4 * sBk + (size_t)colbc * sBn;
+            c0[q] = cinit(rowc, min(col[q], Nn - 1)); c1[q] = cinit(rowc, min(col[q] + 1, Nn - 1));
         }
-        // two operand buffers with STATIC indices (a runtime-indexed buffer would live in local memory)
-        double a0[EK2_NI], b0[EK2_NI], a1[EK2_NI], b1[EK2_NI];
-#define EK2_LOAD(A_, B_, KT_)                                                                                     \
-        {                                                                                                         \
-            const int kk_ = (KT_) * 4 + t4, kc_ = min(kk_, Kc);                                                   \
-            _Pragma("unroll") for (int q = 0; q < EK2_NI; q++) {                                                  \
-                const double x_ = fa(rowc[q], kc_); A_[q] = kk_ < K ? x_ : 0.0; B_[q] = fb(kc_, colbc[q]);        \
-            }                                                                                                     \
+        int kt = 0;
+        for (; kt + 2 <= KF; kt += 2) {
+            double a0[EK2_NI], b0[EK2_NI], a1[EK2_NI], b1[EK2_NI];
+#pragma unroll
+            for (int q = 0; q < EK2_NI; q++) { a0[q] = pa[q][0]; b0[q] = pb[q][0]; a1[q] = pa[q][dA]; b1[q] = pb[q][dB]; pa[q] += 2 * dA; pb[q] += 2 * dB; }
+#pragma unroll
+            for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], a0[q], b0[q]);
+#pragma unroll
+            for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], a1[q], b1[q]);
         }
-#define EK2_MMA(A_, B_) { _Pragma("unroll") for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], A_[q], B_[q]); }
-        EK2_LOAD(a0, b0, 0)
-        for (int kt = 0; kt < KT; kt += 2) {
-            EK2_LOAD(a1, b1, kt + 1)                                      // loads past the end are clamped and zeroed
-            EK2_MMA(a0, b0)
-            if (kt + 1 < KT) {
-                EK2_LOAD(a0, b0, kt + 2)
-                EK2_MMA(a1, b1)
+        if (kt < KF) {
+            double a0[EK2_NI], b0[EK2_NI];
+#pragma unroll
+            for (int q = 0; q < EK2_NI; q++) { a0[q] = pa[q][0]; b0[q] = pb[q][0]; pa[q] += dA; pb[q] += dB; }
+#pragma unroll
+            for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], a0[q], b0[q]);
+        }
+        if (tail) {                                                       // k = 4 KF + t4 is valid for t4 < tail: others re-read k = 4 KF, zeroed
+            const bool kv = t4 < tail;
+            double a0[EK2_NI], b0[EK2_NI];
+#pragma unroll
+            for (int q = 0; q < EK2_NI; q++) {
+                const double xa = kv ? pa[q][0] : pa[q][-(ptrdiff_t)t4 * sAk];
+                a0[q] = kv ? xa : 0.0;
+                b0[q] = kv ? pb[q][0] : pb[q][-(ptrdiff_t)t4 * sBk];
             }
+#pragma unroll
+            for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], a0[q], b0[q]);
         }
-#undef EK2_LOAD
-#undef EK2_MMA
 #pragma unroll
         for (int q = 0; q < EK2_NI; q++)
             if (ok[q] && row[q] < M && col[q] < Nn) store(row[q], col[q], c0[q], c1[q]);
@@ -152,8 +169,23 @@ __device__ __forceinline__ void ek2_dmma_gemm(int M, int Nn, int K, int wrp, int
 
 // Factorisation of the 8 x 8 diagonal block D = T[r0 .. r0+nb, r0 .. r0+nb] of the current Schur complement by ONE warp with
 // shuffles only: lanes 0..7 hold the columns of D (padded with the identity), lanes 8..15 those of I; the row operations
-// of the Cholesky factorisation applied to both leave L_jj' in the first and L_jj^-1 (lower triangular) in the second
-// group, which is written to linv (8 x 8, row-major). 8 dependent pivots: the only serial part of the elimination.
+// of the factorisation applied to both leave L_jj' in the first and L_jj^-1 (lower triangular) in the second group, which
+// is written to linv (8 x 8, row-major). 8 dependent pivots: the only serial part of the elimination.
+// 1 / x to double precision without the slow-path division: hardware approximation + 2 Newton steps (59 cycles dependent
+// on B200 against ~160 for 1.0 / x; tools/ubench.cu)
+__device__ __forceinline__ double ek2_rcp(double x)
+{
+#ifdef HV_EMU
+    return 1.0 / x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+#endif
+}
+
 __device__ __forceinline__ void ek2_diag_factor(const double* T, int W, int r0, int nb, int lane, double* linv, volatile int* s_bad)
 {
     double v[8];
@@ -166,20 +198,25 @@ __device__ __forceinline__ void ek2_diag_factor(const double* T, int W, int r0, 
         if (lane >= 16) x = 0.0;
         v[i] = x;
     }
+    // Row operations of the LDL' factorisation on [D | I] (rows stay unscaled on the dependent chain: per pivot one shuffle,
+    // one reciprocal, one multiply, one FMA); the D^-1/2 scaling that turns the rows into L' and L^-1 follows in parallel.
     bool ok = true;
+    double dsel = 1.0;                               // lane k keeps pivot k
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const double akk = __shfl_sync(0xffffffffu, v[k], k);
         if (!(akk > 0.0)) ok = false;
-        const double r = rsqrt(akk);
-        const double u = v[k] * r;                 // scaled pivot row, entry of this column
-        v[k] = u;
+        if (cidx == k) dsel = akk;
+        double raw[8];
 #pragma unroll
-        for (int i = k + 1; i < 8; i++) {
-            const double mi = __shfl_sync(0xffffffffu, u, i);      // S is symmetric: multiplier of row i = entry i of the scaled pivot row
-            v[i] = fma(-mi, u, v[i]);
-        }
+        for (int i = k + 1; i < 8; i++) raw[i] = __shfl_sync(0xffffffffu, v[k], i);   // S is symmetric: a_ik = entry i of row k
+        const double rinv = ek2_rcp(akk);
+#pragma unroll
+        for (int i = k + 1; i < 8; i++) v[i] = fma(-(raw[i] * rinv), v[k], v[i]);
     }
+    const double rs = rsqrt(dsel);                   // lane k (mod 8): 1 / sqrt(d_k)
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] *= __shfl_sync(0xffffffffu, rs, i);
     if (lane >= 8 && lane < 16) {
 #pragma unroll
         for (int i = 0; i < 8; i++) linv[i * 8 + (lane - 8)] = v[i];
@@ -227,46 +264,40 @@ __device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int
             if (g8 < nb) { if (col < ncols) T[(size_t)(r0 + g8) * W + col] = c0; if (col + 1 < ncols) T[(size_t)(r0 + g8) * W + col + 1] = c1; }
         }
         __syncthreads();
-        // ---- b. trailing update: row tiles mt > j, column tiles nt >= mt; tile 0 of that list is the next diagonal tile
+        // ---- b. trailing update: row tiles mt > j, column tiles nt >= mt (row-major list; entry 0 is the next diagonal tile).
+        // Warp 0 takes entry 0 and then factors it; warps 1..15 walk contiguous ranges of the rest, reloading the A
+        // fragment (-U_j[:, row tile]') only when the row tile changes.
         if (j + 1 < MT) {
             const int first = j + 1;
             int total = 0;
             for (int mt = first; mt < MT; mt++) total += CT - mt;
-            const bool ahead = wrp == 0;                                   // warp 0: next diagonal tile, then its factorisation
-            const int lanes_w = ahead ? 1 : nwarps - 1;                    // stride of this warp's tile list
-            for (int base = ahead ? 0 : wrp; base < (ahead ? 1 : total); base += lanes_w * EK2_NI) {
-                double c0[EK2_NI], c1[EK2_NI], af[EK2_NI][2], bfr[EK2_NI][2];
-                int rowi[EK2_NI], coli[EK2_NI];
-                bool ok[EK2_NI];
-#pragma unroll
-                for (int q = 0; q < EK2_NI; q++) {
-                    int idx = base + q * lanes_w;
-                    ok[q] = idx < total && !(ahead && q > 0);              // warp-uniform; surplus slots redo the last tile, unstored
-                    idx = min(idx, total - 1);
-                    int mt = first;
-                    while (idx >= CT - mt) { idx -= CT - mt; mt++; }
-                    const int nt = mt + idx;
-                    rowi[q] = 8 * mt + g8; coli[q] = 8 * nt + 2 * t4;
-                    const int rc = min(rowi[q], n - 1);
-                    c0[q] = T[(size_t)rc * W + min(coli[q], ncols - 1)];
-                    c1[q] = T[(size_t)rc * W + min(coli[q] + 1, ncols - 1)];
-                    const int am = min(8 * mt + g8, ncols - 1), bn = min(8 * nt + g8, ncols - 1);
-#pragma unroll
-                    for (int kt = 0; kt < 2; kt++) {
-                        const int k = kt * 4 + t4;
-                        const double* rowk = T + (size_t)(r0 + min(k, nb - 1)) * W;
-                        const double xa = rowk[am], xb = rowk[bn];
-                        af[q][kt] = k < nb ? -xa : 0.0;                    // A[m][k] = -U_j[k][8 mt + m]
-                        bfr[q][kt] = xb;                                   // B[k][nn] = U_j[k][8 nt + nn]
-                    }
+            const bool ahead = wrp == 0;
+            const int rest = total - 1;
+            int lo = ahead ? 0 : 1 + (int)(((long long)rest * (wrp - 1)) / (nwarps - 1));
+            const int hi = ahead ? 1 : 1 + (int)(((long long)rest * wrp) / (nwarps - 1));
+            int mt = first, nt, idx = lo;
+            while (idx >= CT - mt) { idx -= CT - mt; mt++; }
+            nt = mt + idx;
+            const double* rowk0 = T + (size_t)(r0 + min(t4, nb - 1)) * W;        // k = t4
+            const double* rowk1 = T + (size_t)(r0 + min(4 + t4, nb - 1)) * W;    // k = 4 + t4
+            const bool k0v = t4 < nb, k1v = 4 + t4 < nb;
+            int curMt = -1;
+            double a0 = 0.0, a1 = 0.0;
+            for (; lo < hi; lo++) {
+                if (mt != curMt) {
+                    const int am = min(8 * mt + g8, ncols - 1);
+                    const double x0 = rowk0[am], x1 = rowk1[am];
+                    a0 = k0v ? -x0 : 0.0; a1 = k1v ? -x1 : 0.0;                   // A[m][k] = -U_j[k][8 mt + m]
+                    curMt = mt;
                 }
-#pragma unroll
-                for (int kt = 0; kt < 2; kt++)
-#pragma unroll
-                    for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], af[q][kt], bfr[q][kt]);
-#pragma unroll
-                for (int q = 0; q < EK2_NI; q++)
-                    if (ok[q] && rowi[q] < n) { if (coli[q] < ncols) T[(size_t)rowi[q] * W + coli[q]] = c0[q]; if (coli[q] + 1 < ncols) T[(size_t)rowi[q] * W + coli[q] + 1] = c1[q]; }
+                const int rowi = 8 * mt + g8, coli = 8 * nt + 2 * t4, bn = min(8 * nt + g8, ncols - 1);
+                double* crow = T + (size_t)min(rowi, n - 1) * W;
+                double c0 = crow[min(coli, ncols - 1)], c1 = crow[min(coli + 1, ncols - 1)];
+                const double b0 = rowk0[bn], b1 = rowk1[bn];                       // B[k][nn] = U_j[k][8 nt + nn]
+                hv_dmma(c0, c1, a0, b0);
+                hv_dmma(c0, c1, a1, b1);
+                if (rowi < n) { if (coli < ncols) crow[coli] = c0; if (coli + 1 < ncols) crow[coli + 1] = c1; }
+                if (++nt == CT) { mt++; nt = mt; }
             }
             if (ahead) {
                 __syncwarp();
@@ -400,9 +431,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
 
     EK2_PHASE(1);
     // ---- phase A: HP[:, J_c] = H P[0:l, J_c] on the fp64 tensor cores (n x Bc x l)
-    ek2_dmma_gemm(n, Bc, l, wrp, lane,
-                  [&](int i, int k) { return Hs[i + (size_t)k * n]; },
-                  [&](int k, int j) { return PB[k + (size_t)j * LD]; },
+    ek2_dmma_gemm(n, Bc, l, wrp, lane, Hs, 1, n, PB, 1, LD,
                   [](int, int) { return 0.0; },
                   [&](int i, int j, double v0, double v1) { T[(size_t)i * W + n + j] = v0; if (j + 1 < Bc) T[(size_t)i * W + n + j + 1] = v1; });
     __syncthreads();
@@ -411,9 +440,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     // blocked elimination never reads S below its diagonal tiles
     {
         const int kc = max(0, min(Bc, l - J0));
-        ek2_dmma_gemm<true>(n, n, kc, wrp, lane,
-                      [&](int i, int k) { return T[(size_t)i * W + n + k]; },
-                      [&](int k, int j) { return Hs[j + (size_t)(J0 + k) * n]; },
+        ek2_dmma_gemm<true>(n, n, kc, wrp, lane, T + n, W, 1, Hs + (size_t)J0 * n, n, 1,
                       [](int, int) { return 0.0; },
                       [&](int i, int j, double v0, double v1) {
                           if (oneStage) { RS[i * n + j] = v0; if (j + 1 < n) RS[i * n + j + 1] = v1; }      // partial stays out of the tableau
@@ -509,17 +536,14 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     __syncthreads();
     EK2_PHASE(7);
     // P[:, J_c] -= Z' Z[:, J_c] on the fp64 tensor cores (N x Bc x n), in place in the shared-memory block
-    ek2_dmma_gemm(N, Bc, n, wrp, lane,
-                  [&](int i, int k) { return -Z[(size_t)k * LD + i]; },
-                  [&](int k, int j) { return Z[(size_t)k * LD + J0 + j]; },
-                  [&](int i, int j) { return PB[i + (size_t)j * LD]; },
-                  [&](int i, int j, double v0, double v1) { PB[i + (size_t)j * LD] = v0; if (j + 1 < Bc) PB[i + (size_t)(j + 1) * LD] = v1; });
+    // (accumulated as -P + Z'Z and negated on the way out: no per-step negation of an operand)
+    ek2_dmma_gemm(N, Bc, n, wrp, lane, Z, 1, LD, Z + J0, LD, 1,
+                  [&](int i, int j) { return -PB[i + (size_t)j * LD]; },
+                  [&](int i, int j, double v0, double v1) { PB[i + (size_t)j * LD] = -v0; if (j + 1 < Bc) PB[i + (size_t)(j + 1) * LD] = -v1; });
     // state mean: m += Z' z_v (CTA 0 owns the write-back; quaternion normalisation: updateCommon normalises the current
     // orientation only, the visual update and the augmentation all of them, ekf.cpp:31, 843, 874)
     if (c == 0) {
-        ek2_dmma_gemm(N, 1, n, wrp, lane,
-                      [&](int i, int k) { return Z[(size_t)k * LD + i]; },
-                      [&](int k, int) { return T[(size_t)k * W + vcol]; },
+        ek2_dmma_gemm(N, 1, n, wrp, lane, Z, 1, LD, T + vcol, W, 0,
                       [&](int i, int) { return s_m[i]; },
                       [&](int i, int, double v0, double) { s_m[i] = v0; });
         __syncthreads();

@@ -35,6 +35,19 @@ for n in (8, 20, 40, 84):
         print(line)
     ekf.symmetrize(); ekf.augment(-1)
 
+for rep in range(3):
+    ekf.symmetrize(); ekf.augment(-1)
+ekf.flush()
+w = np.zeros(32); lib.hv_ekf_debug_result_words(ekf.h, w.ctypes.data)
+ts = w[8:18]
+keys = [k for k in range(10) if ts[k] > 0]
+line = f"symmetrise+augment: total {(max(ts[keys]) - ts[0]) / 1e3:6.1f} us | "
+prev = ts[0]
+for k in keys[1:]:
+    if ts[k] >= prev:
+        line += f"{names[k]} {(ts[k] - prev) / 1e3:.1f} | "; prev = ts[k]
+print(line)
+
 t = 1.0
 for rep in range(3):
     for k in range(10):

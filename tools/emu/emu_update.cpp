@@ -59,6 +59,7 @@ int main(int argc, char** argv)
         double* m = arena.alloc<double>(N); double* P = arena.alloc<double>((size_t)N * N);
         double* H = arena.alloc<double>((size_t)cs.n * N); double* f = arena.alloc<double>(cs.n); double* y = arena.alloc<double>(cs.n);
         double* res = arena.alloc<double>(64);
+        double* cwork = arena.alloc<double>((size_t)N * N);
         {   // random SPD covariance (slightly asymmetric for the symmetrisation cases) and a plausible mean
             std::vector<double> Bm((size_t)N * N);
             for (auto& x : Bm) x = rnd();
@@ -77,7 +78,7 @@ int main(int argc, char** argv)
         for (int i = 0; i < cs.n; i++) { f[i] = 0.5 * gauss(); y[i] = f[i] + cs.yscale * gauss(); }
 
         EkfUpdateArgs a; memset(&a, 0, sizeof(a));
-        a.b.m = m; a.b.P = P; a.b.res = res; a.b.N = N; a.b.trail = cs.trail; a.b.mapDim = 0;
+        a.b.m = m; a.b.P = P; a.b.res = res; a.b.cwork = cwork; a.b.N = N; a.b.trail = cs.trail; a.b.mapDim = 0;
         a.op = cs.op; a.n = cs.n; a.l = cs.l; a.mode = cs.mode; a.noiseScale = noiseScale; a.rmseThr = -1.0;
         int ost = 0; double ochi2 = 0;
         const double r = 0.05;
