@@ -33,7 +33,7 @@
 #define EK2_PHASE(i) do { } while (0)
 #endif
 
-struct Ek2Geom { int C, B, X, W, T, PB, RS, EXTRA, oneStage, LD; };
+struct Ek2Geom { int C, B, X, W, T, PB, RS, EXTRA, SYM, oneStage, LD; };
 __host__ __device__ inline Ek2Geom ek2_geom(int n, int l, int N, bool joseph, int C)
 {
     Ek2Geom g;
@@ -51,13 +51,14 @@ __host__ __device__ inline Ek2Geom ek2_geom(int n, int l, int N, bool joseph, in
     // small S: every CTA leaves its partial in RS and sums all of them itself; else reduce-scatter (own slice in RS) + all-gather
     g.oneStage = n * n <= 1024 ? 1 : 0;
     g.RS = g.oneStage ? n * n : E;
-    g.EXTRA = joseph ? N * (EKF_POSE + 14 + 14) + N * g.B : 0;   // K | T1c | special columns of G | P'' block
+    g.EXTRA = joseph ? N * EKF_POSE + 2 * 21 * g.LD + N * g.B : 0;   // K | [G special | K] | [T1c | R K] | P'' block
+    g.SYM = n <= 8 ? N * g.B : 0;                           // transposition buffer of the symmetrisation (its users have n <= 7)
     return g;
 }
 __host__ __device__ inline size_t ek2_smem_bytes(int n, int l, int N, bool joseph, int C)
 {
     const Ek2Geom g = ek2_geom(n, l, N, joseph, C);
-    return ((size_t)g.X + g.T + g.PB + g.RS + g.EXTRA) * sizeof(double);
+    return ((size_t)g.X + g.T + g.PB + g.RS + g.EXTRA + g.SYM) * sizeof(double);
 }
 
 __device__ __forceinline__ void ek2_copy8(double* __restrict__ dst, const double* __restrict__ src, int count, int tid)
@@ -104,66 +105,78 @@ __host__ __device__ inline void ek2_upper_tile(int tu, int& mt, int& nt)
 // two loads off running pointers and one DMMA -- with only 256 FMAs per MMA the instruction count around it decides the
 // speed (the first version took its operands through index-clamping lambdas: ~15 instructions per MMA, and was issue-bound
 // at a third of the tensor-core rate).
+// One chunk of NI tiles of one warp (NI is exact: no padded tiles -- the kernel is bound by the tensor-core rate, 64 FMA per
+// clock per SM, so a padded slot costs as much as a real one)
+template <int NI, bool UPPER, class FCI, class FST>
+__device__ __forceinline__ void ek2_dmma_chunk(int M, int Nn, int K, int MT, int base, int stride, int lane, const double* A, int sAm, int sAk,
+                                               const double* B, int sBk, int sBn, FCI cinit, FST store)
+{
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int KF = K >> 2, tail = K & 3;                                  // full k-steps, leftover k's
+    const int dA = 4 * sAk, dB = 4 * sBk;
+    double c0[NI], c1[NI];
+    int row[NI], col[NI];
+    const double* pa[NI]; const double* pb[NI];
+#pragma unroll
+    for (int q = 0; q < NI; q++) {
+        const int tl = base + q * stride;
+        int mt, nt;
+        if (UPPER) ek2_upper_tile(tl, mt, nt); else { mt = tl % MT; nt = tl / MT; }
+        row[q] = mt * 8 + g8; col[q] = nt * 8 + 2 * t4;
+        const int rowc = min(row[q], M - 1), colbc = min(nt * 8 + g8, Nn - 1);   // rows / columns past the matrix: clamped, never stored
+        pa[q] = A + (size_t)rowc * sAm + (size_t)t4 * sAk;
+        pb[q] = B + (size_t)t4 * sBk + (size_t)colbc * sBn;
+        c0[q] = cinit(rowc, min(col[q], Nn - 1)); c1[q] = cinit(rowc, min(col[q] + 1, Nn - 1));
+    }
+    int kt = 0;
+    for (; kt + 2 <= KF; kt += 2) {
+        double a0[NI], b0[NI], a1[NI], b1[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) { a0[q] = pa[q][0]; b0[q] = pb[q][0]; a1[q] = pa[q][dA]; b1[q] = pb[q][dB]; pa[q] += 2 * dA; pb[q] += 2 * dB; }
+#pragma unroll
+        for (int q = 0; q < NI; q++) hv_dmma(c0[q], c1[q], a0[q], b0[q]);
+#pragma unroll
+        for (int q = 0; q < NI; q++) hv_dmma(c0[q], c1[q], a1[q], b1[q]);
+    }
+    if (kt < KF) {
+        double a0[NI], b0[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) { a0[q] = pa[q][0]; b0[q] = pb[q][0]; pa[q] += dA; pb[q] += dB; }
+#pragma unroll
+        for (int q = 0; q < NI; q++) hv_dmma(c0[q], c1[q], a0[q], b0[q]);
+    }
+    if (tail) {                                                           // k = 4 KF + t4 is valid for t4 < tail: others re-read k = 4 KF, zeroed
+        const bool kv = t4 < tail;
+        double a0[NI], b0[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) {
+            const double xa = kv ? pa[q][0] : pa[q][-(ptrdiff_t)t4 * sAk];
+            a0[q] = kv ? xa : 0.0;
+            b0[q] = kv ? pb[q][0] : pb[q][-(ptrdiff_t)t4 * sBk];
+        }
+#pragma unroll
+        for (int q = 0; q < NI; q++) hv_dmma(c0[q], c1[q], a0[q], b0[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NI; q++)
+        if (row[q] < M && col[q] < Nn) store(row[q], col[q], c0[q], c1[q]);
+}
+
 template <bool UPPER = false, class FCI, class FST>
 __device__ __forceinline__ void ek2_dmma_gemm(int M, int Nn, int K, int wrp, int lane, const double* A, int sAm, int sAk,
                                               const double* B, int sBk, int sBn, FCI cinit, FST store)
 {
-    const int g8 = lane >> 2, t4 = lane & 3;
     const int MT = (M + 7) >> 3, NT = (Nn + 7) >> 3, tiles = UPPER ? MT * (MT + 1) / 2 : MT * NT;
     const int nwarps = EK2_NT / 32;
     if (M <= 0 || Nn <= 0) return;
-    const int KF = K >> 2, tail = K & 3;                                  // full k-steps, leftover k's
-    const int dA = 4 * sAk, dB = 4 * sBk;
     for (int base = wrp; base < tiles; base += nwarps * EK2_NI) {
-        double c0[EK2_NI], c1[EK2_NI];
-        int row[EK2_NI], col[EK2_NI];
-        const double* pa[EK2_NI]; const double* pb[EK2_NI];
-        bool ok[EK2_NI];
-#pragma unroll
-        for (int q = 0; q < EK2_NI; q++) {
-            const int tile = base + q * nwarps;
-            ok[q] = tile < tiles;                                         // warp-uniform; surplus slots redo the last tile, unstored
-            const int tl = min(tile, tiles - 1);
-            int mt, nt;
-            if (UPPER) ek2_upper_tile(tl, mt, nt); else { mt = tl % MT; nt = tl / MT; }
-            row[q] = mt * 8 + g8; col[q] = nt * 8 + 2 * t4;
-            const int rowc = min(row[q], M - 1), colbc = min(nt * 8 + g8, Nn - 1);   // rows / columns past the matrix: clamped, never stored
-            pa[q] = A + (size_t)rowc * sAm + (size_t)t4 * sAk;
-            pb[q] = B + (size_t)t4 * sBk + (size_t)colbc * sBn;
-            c0[q] = cinit(rowc, min(col[q], Nn - 1)); c1[q] = cinit(rowc, min(col[q] + 1, Nn - 1));
+        const int cnt = min(EK2_NI, (tiles - base + nwarps - 1) / nwarps);      // tiles of this warp in this chunk (warp-uniform)
+        switch (cnt) {
+            case 1: ek2_dmma_chunk<1, UPPER>(M, Nn, K, MT, base, nwarps, lane, A, sAm, sAk, B, sBk, sBn, cinit, store); break;
+            case 2: ek2_dmma_chunk<2, UPPER>(M, Nn, K, MT, base, nwarps, lane, A, sAm, sAk, B, sBk, sBn, cinit, store); break;
+            case 3: ek2_dmma_chunk<3, UPPER>(M, Nn, K, MT, base, nwarps, lane, A, sAm, sAk, B, sBk, sBn, cinit, store); break;
+            default: ek2_dmma_chunk<4, UPPER>(M, Nn, K, MT, base, nwarps, lane, A, sAm, sAk, B, sBk, sBn, cinit, store); break;
         }
-        int kt = 0;
-        for (; kt + 2 <= KF; kt += 2) {
-            double a0[EK2_NI], b0[EK2_NI], a1[EK2_NI], b1[EK2_NI];
-#pragma unroll
-            for (int q = 0; q < EK2_NI; q++) { a0[q] = pa[q][0]; b0[q] = pb[q][0]; a1[q] = pa[q][dA]; b1[q] = pb[q][dB]; pa[q] += 2 * dA; pb[q] += 2 * dB; }
-#pragma unroll
-            for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], a0[q], b0[q]);
-#pragma unroll
-            for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], a1[q], b1[q]);
-        }
-        if (kt < KF) {
-            double a0[EK2_NI], b0[EK2_NI];
-#pragma unroll
-            for (int q = 0; q < EK2_NI; q++) { a0[q] = pa[q][0]; b0[q] = pb[q][0]; pa[q] += dA; pb[q] += dB; }
-#pragma unroll
-            for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], a0[q], b0[q]);
-        }
-        if (tail) {                                                       // k = 4 KF + t4 is valid for t4 < tail: others re-read k = 4 KF, zeroed
-            const bool kv = t4 < tail;
-            double a0[EK2_NI], b0[EK2_NI];
-#pragma unroll
-            for (int q = 0; q < EK2_NI; q++) {
-                const double xa = kv ? pa[q][0] : pa[q][-(ptrdiff_t)t4 * sAk];
-                a0[q] = kv ? xa : 0.0;
-                b0[q] = kv ? pb[q][0] : pb[q][-(ptrdiff_t)t4 * sBk];
-            }
-#pragma unroll
-            for (int q = 0; q < EK2_NI; q++) hv_dmma(c0[q], c1[q], a0[q], b0[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < EK2_NI; q++)
-            if (ok[q] && row[q] < M && col[q] < Nn) store(row[q], col[q], c0[q], c1[q]);
     }
 }
 
@@ -338,6 +351,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     double* PB = T + g.T;           // P[:, J_c]
     double* RS = PB + g.PB;         // reduced S
     double* EX = RS + g.RS;         // Joseph-form extras
+    double* SYMB = EX + g.EXTRA;    // symmetrisation: mirrored entries, transposed
     const int W = g.W, B = g.B, LD = g.LD;
     const int J0 = c * B, Bc = max(0, min(B, N - J0));
     const int vcol = n + B, cend = joseph ? vcol + n : vcol;
@@ -558,10 +572,12 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     int ldb = LD;                                     // ... and its leading dimension
     if (joseph) {
         // ---- Joseph form (ekf.cpp:35-50): P'' = G T1' + K R K', G = T1 P' = P' - Z'Z (in PB now), T1 = I - K visAugH
+        // As ONE product on the tensor cores: P''[:, J_c] = [G_special | K] (N x 21) * [T1c | R K]' (21 x Bc) + (G[:, J_c] on the
+        // non-special columns): the 14 special columns of G come from the CTAs that own them (distributed shared memory).
         double* Ks = EX;                              // N x 7
-        double* T1c = Ks + (size_t)N * EKF_POSE;      // N x 14
-        double* GS = T1c + (size_t)N * 14;            // N x 14: the special columns of G
-        double* P2 = GS + (size_t)N * 14;             // N x B: P'' block
+        double* AS = Ks + (size_t)N * EKF_POSE;       // N x 21, ld LD: [G special columns | K]
+        double* BS = AS + (size_t)21 * LD;            // N x 21, ld LD: [T1c | Rdiag K]
+        double* P2 = BS + (size_t)21 * LD;            // N x B: P'' block
         for (int t = tid; t < N * EKF_POSE; t += EK2_NT) {
             const int i = t % N, r = t / N;
             double s = 0.0;
@@ -569,42 +585,60 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
             Ks[t] = s;
         }
         __syncthreads();
-        for (int t = tid; t < N * 14; t += EK2_NT) {
+        for (int t = tid; t < N * 21; t += EK2_NT) {
             const int j = t % N, cc = t / N;
-            const double kv = cc < 7 ? -Ks[j + cc * N] : Ks[j + (cc - 7) * N];
-            T1c[t] = (j == ek2_special_col(cc) ? 1.0 : 0.0) + kv;
+            if (cc < 14) {
+                const double kv = cc < 7 ? -Ks[j + cc * N] : Ks[j + (cc - 7) * N];
+                BS[j + (size_t)cc * LD] = (j == ek2_special_col(cc) ? 1.0 : 0.0) + kv;          // T1 = I - K visAugH, its 14 columns
+            } else {
+                BS[j + (size_t)cc * LD] = a.Rdiag * Ks[j + (cc - 14) * N];
+                AS[j + (size_t)cc * LD] = Ks[j + (cc - 14) * N];
+            }
         }
         cluster.sync();                               // #4: all of G is final
         for (int t = tid; t < N * 14; t += EK2_NT) {
             const int i = t % N, cc = t / N;
             const int col = ek2_special_col(cc), r = col / B;
-            GS[t] = cluster.map_shared_rank(PB, r)[i + (size_t)(col - r * B) * LD];
+            AS[i + (size_t)cc * LD] = cluster.map_shared_rank(PB, r)[i + (size_t)(col - r * B) * LD];
         }
         __syncthreads();
-        for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
-            const int i = idx % N, j = J0 + idx / N;
-            const bool jsp = j < 3 || (j >= EKF_ORI && j < EKF_ORI + 4) || (j >= EKF_CAM && j < EKF_CAM + EKF_POSE);
-            double s = jsp ? 0.0 : PB[i + (size_t)(idx / N) * LD];
-#pragma unroll
-            for (int cc = 0; cc < 14; cc++) s += GS[i + cc * N] * T1c[j + cc * N];
-            double kr = 0.0;
-#pragma unroll
-            for (int r = 0; r < EKF_POSE; r++) kr += Ks[i + r * N] * (a.Rdiag * Ks[j + r * N]);
-            P2[idx] = s + kr;
-        }
+        ek2_dmma_gemm(N, Bc, 21, wrp, lane, AS, 1, LD, BS + J0, LD, 1,
+                      [&](int i, int jj) {
+                          const int j = J0 + jj;
+                          const bool jsp = j < 3 || (j >= EKF_ORI && j < EKF_ORI + 4) || (j >= EKF_CAM && j < EKF_CAM + EKF_POSE);
+                          return jsp ? 0.0 : PB[i + (size_t)jj * LD];
+                      },
+                      [&](int i, int jj, double v0, double v1) { P2[i + (size_t)jj * N] = v0; if (jj + 1 < Bc) P2[i + (size_t)(jj + 1) * N] = v1; });
         Pblk = P2; ldb = N;
     }
     if (a.symmetrize) {
         cluster.sync();                               // #5: every final block is in shared memory
-        for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
-            const int i = idx % N, j = J0 + idx / N;
-            double v = Pblk[i + (size_t)(idx / N) * ldb];
-            if (i != j) {
-                const int r = i / B;                  // owner of column i, which holds P(j, i)
-                const double w = cluster.map_shared_rank(Pblk, r)[j + (size_t)(i - r * B) * ldb];
-                v = i > j ? 0.5 * (v + w) : 0.5 * (w + v);      // same operand order as P(i>j) + P(j<i) on both sides
+        if (g.SYM) {
+            // mirrored entries P(j, i) live in the block of the CTA that owns column i: fetched with the row index j running
+            // fastest (contiguous in the owner's column), parked transposed, then combined and stored with i running fastest
+            for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
+                const int jj = idx % Bc, i = idx / Bc, j = J0 + jj, r = i / B;
+                SYMB[i + (size_t)jj * N] = i != j ? cluster.map_shared_rank(Pblk, r)[j + (size_t)(i - r * B) * ldb] : 0.0;
             }
-            P[i + (size_t)j * N] = v;
+            __syncthreads();
+            for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
+                const int i = idx % N, jj = idx / N, j = J0 + jj;
+                double v = Pblk[i + (size_t)jj * ldb];
+                const double w = SYMB[idx];
+                if (i != j) v = i > j ? 0.5 * (v + w) : 0.5 * (w + v);
+                P[i + (size_t)j * N] = v;
+            }
+        } else {
+            for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
+                const int i = idx % N, j = J0 + idx / N;
+                double v = Pblk[i + (size_t)(idx / N) * ldb];
+                if (i != j) {
+                    const int r = i / B;                  // owner of column i, which holds P(j, i)
+                    const double w = cluster.map_shared_rank(Pblk, r)[j + (size_t)(i - r * B) * ldb];
+                    v = i > j ? 0.5 * (v + w) : 0.5 * (w + v);      // same operand order as P(i>j) + P(j<i) on both sides
+                }
+                P[i + (size_t)j * N] = v;
+            }
         }
     } else {
         for (int idx = tid; idx < N * Bc; idx += EK2_NT) P[(size_t)J0 * N + idx] = Pblk[(idx % N) + (size_t)(idx / N) * ldb];

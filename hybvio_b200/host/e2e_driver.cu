@@ -88,6 +88,61 @@ static int e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, cons
     return rc;
 }
 
+// ---- device-resident loop (bench.py's `value`): the same frame as above with every input already in HBM and no host
+// synchronisation; tracker and EKF on their own streams with the real dependencies as events (LK(k) after EKF(k-1): the
+// flow predictor reads the EKF poses, src/tracker/tracker.cpp:59-63; visual updates(k) after LK(k)). A native caller keeps
+// the launch rate independent of the Python interpreter of the harness.
+typedef struct hv_dev_frame {
+    const uint8_t* left; const uint8_t* right;   // device gray images
+    size_t stride;
+    const float* d_init_xy;                      // device: predicted end points (n x 2)
+    const hv_ekf_op* ops;                        // the frame's EKF calls with DEVICE pointers; the first nimu ops are the IMU burst
+    int nops, nimu;
+} hv_dev_frame;
+
+int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const float* d_points, float* d_next, float* d_next2,
+               uint8_t* d_status, int32_t* d_ts, int n, const hv_dev_frame* frames, int nframes, float* elapsed_ms)
+{
+    hv_pyr* p[4] = {pyr[0], pyr[1], pyr[2], pyr[3]};
+    cudaStream_t sa = (cudaStream_t)hv_ctx_stream(trk), sb = (cudaStream_t)hv_ctx_stream(ekf_ctx);
+    cudaEvent_t e0, e1, evLk, evEkf;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventCreateWithFlags(&evLk, cudaEventDisableTiming); cudaEventCreateWithFlags(&evEkf, cudaEventDisableTiming);
+    hv_ctx_sync(trk); hv_ctx_sync(ekf_ctx);
+    cudaEventRecord(e0, sa);
+    cudaEventRecord(evEkf, sb);
+    int rc = HV_OK;
+    for (int k = 0; k < nframes && rc == HV_OK; k++) {
+        const hv_dev_frame& f = frames[k];
+        hv_pyr* cur[2] = {p[2], p[3]};
+        const uint8_t* img[2] = {f.left, f.right};
+        const size_t strides[2] = {f.stride, f.stride};
+        rc = hv_pyr_build_batch(cur, img, strides, 2, 1);                       // A: no dependency
+        if (rc != HV_OK) break;
+        rc = hv_ekf_run_device(ekf, f.ops, f.nimu);                            // B: IMU burst (queued) ...
+        if (rc == HV_OK) rc = hv_ekf_flush(ekf);                               // ... issued now: overlaps the tracker
+        if (rc != HV_OK) break;
+        cudaStreamWaitEvent(sa, evEkf, 0);                                     // flow predictor needs EKF(k-1)
+        cudaMemcpyAsync(d_next, f.d_init_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToDevice, sa);
+        rc = hv_lk_track_device(trk, p[0], cur[0], d_points, d_next, d_status, d_ts, n, 1, 20, 0.03, 1e-3);
+        if (rc == HV_OK) rc = hv_lk_track_device(trk, cur[0], cur[1], d_next, d_next2, d_status, d_ts, n, 0, 20, 0.03, 1e-3);
+        if (rc != HV_OK) break;
+        cudaEventRecord(evLk, sa);
+        cudaStreamWaitEvent(sb, evLk, 0);                                      // visual updates need the tracks
+        rc = hv_ekf_run_device(ekf, f.ops + f.nimu, f.nops - f.nimu);
+        if (rc == HV_OK) rc = hv_ekf_flush(ekf);
+        cudaEventRecord(evEkf, sb);
+        hv_pyr* q0 = p[0]; hv_pyr* q1 = p[1]; p[0] = p[2]; p[1] = p[3]; p[2] = q0; p[3] = q1;
+    }
+    cudaStreamWaitEvent(sa, evEkf, 0);
+    cudaEventRecord(e1, sa);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(elapsed_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(evLk); cudaEventDestroy(evEkf);
+    for (int i = 0; i < 4; i++) pyr[i] = p[i];
+    return rc;
+}
+
 int hv_e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const float* points, int n, const hv_e2e_frame* frames,
                int nframes, double* pose_out, float* elapsed_ms)
 {
