@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(EK2_NT) ekf_check_batch_cluster2_kernel(EkfUpd
     a.Rdiag = it.Rdiag; a.chi2Thr = it.chi2Thr; a.rmseThr = it.rmseThr; a.skipChi2 = it.skipChi2;
     a.b.res += (size_t)EKF_RES_STRIDE * inst;
     if (a.sig) a.sig += 4 * inst;
+    a.b.cwork += (size_t)inst * 10 * a.b.N * a.b.N;           // own exchange area (Z | reduced S | partial S)
     ek2_body(a, ek2_sm, cluster);
 }
 
@@ -51,9 +52,13 @@ static cudaError_t ek2_launch(K kernel, int C, int nclusters, size_t smem, cudaS
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C * nclusters); cfg.blockDim = dim3(EK2_NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at;
-    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = C; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-    cfg.attrs = &at; cfg.numAttrs = 1;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    // programmatic dependent launch: this kernel may start while the previous KERNEL of the stream is still running (it waits
+    // in griddepcontrol.wait before it reads the filter state); HV_EKF_NO_PDL=1 switches it off (A/B)
+    static const bool pdl = getenv("HV_EKF_NO_PDL") == nullptr;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 

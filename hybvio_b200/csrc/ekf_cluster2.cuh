@@ -285,10 +285,15 @@ __device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int
             int total = 0;
             for (int mt = first; mt < MT; mt++) total += CT - mt;
             const bool ahead = wrp == 0;
+            // Workers: the warps that do NOT share warp 0's scheduler / FP64 pipe (warp id mod 4 != 0). The pivot chain of the
+            // look-ahead factorisation is a sequence of dependent fp64 operations; every DMMA a sibling warp queues on the
+            // same pipe (16 cycles each) would sit in front of them.
+            const int nwork = nwarps - nwarps / 4, widx = wrp - wrp / 4 - 1;           // 12 workers, index 0..11
+            const bool worker = (wrp & 3) != 0;
             const int rest = total - 1;
-            int lo = ahead ? 0 : 1 + (int)(((long long)rest * (wrp - 1)) / (nwarps - 1));
-            const int hi = ahead ? 1 : 1 + (int)(((long long)rest * wrp) / (nwarps - 1));
-            int mt = first, nt, idx = lo;
+            int lo = ahead ? 0 : worker ? 1 + (int)(((long long)rest * widx) / nwork) : 0;
+            const int hi = ahead ? 1 : worker ? 1 + (int)(((long long)rest * (widx + 1)) / nwork) : 0;
+            int mt = first, nt, idx = min(lo, total - 1);
             while (idx >= CT - mt) { idx -= CT - mt; mt++; }
             nt = mt + idx;
             const double* rowk0 = T + (size_t)(r0 + min(t4, nb - 1)) * W;        // k = t4
@@ -320,6 +325,20 @@ __device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int
         }
     }
     return !*s_bad;
+}
+
+// Programmatic dependent launch (sm_90+): see ek2_body. No-ops on the host emulator.
+__device__ __forceinline__ void ek2_pdl_launch_dependents()
+{
+#ifndef HV_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void ek2_pdl_wait()
+{
+#ifndef HV_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 }
 
 // Result words (VuOutlierStatus, chi2, numeric flag): device copy + optional mapped-host copy with a sequence flag
@@ -356,9 +375,23 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     const int J0 = c * B, Bc = max(0, min(B, N - J0));
     const int vcol = n + B, cend = joseph ? vcol + n : vcol;
     const bool oneStage = g.oneStage != 0;
+    // S exchange: entries of the upper-triangular 8 x 8 tiles, tile by tile (ETOT of them). Large S goes through L2 (bulk remote
+    // shared-memory pulls run at less than half the L2 rate): a.b.cwork = [ Z (N^2) | reduced S (N^2) | C partial S (8 N^2) ]
+    const int MTs = (n + 7) >> 3, ETOT = 64 * (MTs * (MTs + 1) / 2);
+    const bool bigS = !oneStage && a.b.cwork != nullptr && (size_t)C * ETOT <= (size_t)8 * N * N;
+    double* const Sred = a.b.cwork ? a.b.cwork + (size_t)N * N : nullptr;
+    double* const Spart = a.b.cwork ? a.b.cwork + (size_t)2 * N * N : nullptr;
     double* const P = a.b.P;
 
     EK2_PHASE(0);
+    // Programmatic dependent launch: the next kernel of the stream may start now (its launch latency and the staging of its
+    // own measurement matrix overlap with this kernel); it will not touch the filter state before its own
+    // griddepcontrol.wait, which returns when this grid has completed and its writes are visible.
+    ek2_pdl_launch_dependents();
+    // ---- the measurement matrix does not depend on earlier kernels: stage it before waiting for them
+    if (a.op == EKF_OP_DENSE) ek2_copy8(X, a.H, n * l, tid);
+    else for (int i = tid; i < n * l; i += EK2_NT) X[i] = 0.0;
+    ek2_pdl_wait();
     // ---- stage the state mean and the own column block of P (augmentation: of A P A' + visAugQ, ekf.cpp:853-857)
     if (joseph) {
         const int drop = a.dropIdx;
@@ -389,10 +422,8 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     // ---- measurement model into shared memory (ld = n)
     double hspeed = 0.0;
     if (a.op == EKF_OP_DENSE) {
-        ek2_copy8(X, a.H, n * l, tid);
         __syncthreads();
     } else {
-        for (int i = tid; i < n * l; i += EK2_NT) X[i] = 0.0;
         __syncthreads();                                                  // s_m staged, X zeroed
         if (a.op == EKF_OP_PSEUDO_VELOCITY) {
             hspeed = sqrt(s_m[EKF_VEL] * s_m[EKF_VEL] + s_m[EKF_VEL + 1] * s_m[EKF_VEL + 1]);
@@ -458,14 +489,17 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
                       [](int, int) { return 0.0; },
                       [&](int i, int j, double v0, double v1) {
                           if (oneStage) { RS[i * n + j] = v0; if (j + 1 < n) RS[i * n + j + 1] = v1; }      // partial stays out of the tableau
-                          else { T[(size_t)i * W + j] = v0; if (j + 1 < n) T[(size_t)i * W + j + 1] = v1; }
+                          else if (bigS) {                                                                  // tile-ordered, through L2
+                              const int mt = i >> 3, nt = j >> 3;
+                              double* dst = Spart + (size_t)c * ETOT + 64 * (nt * (nt + 1) / 2 + mt) + 8 * (i & 7) + (j & 7);
+                              dst[0] = v0; dst[1] = v1;
+                          } else { T[(size_t)i * W + j] = v0; if (j + 1 < n) T[(size_t)i * W + j + 1] = v1; }
                       });
     }
     EK2_PHASE(3);
     cluster.sync();                                   // #1: every partial S is in place (and from here on shared memory is exposed)
     // ---- reduce S through distributed shared memory, fixed order r = 0 .. C-1 (+ R on the diagonal)
     {
-        const int MTs = (n + 7) >> 3, ETOT = 64 * (MTs * (MTs + 1) / 2);   // entries of the upper-triangular tiles, tile by tile
         auto entry = [&](int e, int& i, int& ip) { int mt, nt; ek2_upper_tile(e >> 6, mt, nt); i = 8 * mt + ((e >> 3) & 7); ip = 8 * nt + (e & 7); };
         if (oneStage) {
             for (int e = tid; e < ETOT; e += EK2_NT) {
@@ -484,16 +518,17 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
                 int i, ip; entry(e, i, ip);
                 double s = 0.0;
                 if (i < n && ip < n) {
-                    for (int r = 0; r < C; r++) s += cluster.map_shared_rank(T, r)[(size_t)i * W + ip];
+                    if (bigS) { for (int r = 0; r < C; r++) s += Spart[(size_t)r * ETOT + e]; }
+                    else { for (int r = 0; r < C; r++) s += cluster.map_shared_rank(T, r)[(size_t)i * W + ip]; }
                     if (i == ip) s += a.Rdiag;
                 }
-                RS[e - e0] = s;
+                if (bigS) Sred[e] = s; else RS[e - e0] = s;
             }
             cluster.sync();                               // #2: all slices reduced; nobody reads the partials any more
             for (int e = tid; e < ETOT; e += EK2_NT) {
                 int i, ip; entry(e, i, ip);
                 const int r = e / E;
-                if (i < n && ip < n) T[(size_t)i * W + ip] = cluster.map_shared_rank(RS, r)[e - r * E];
+                if (i < n && ip < n) T[(size_t)i * W + ip] = bigS ? Sred[e] : cluster.map_shared_rank(RS, r)[e - r * E];
             }
             __syncthreads();
         }

@@ -59,7 +59,7 @@ int main(int argc, char** argv)
         double* m = arena.alloc<double>(N); double* P = arena.alloc<double>((size_t)N * N);
         double* H = arena.alloc<double>((size_t)cs.n * N); double* f = arena.alloc<double>(cs.n); double* y = arena.alloc<double>(cs.n);
         double* res = arena.alloc<double>(64);
-        double* cwork = arena.alloc<double>((size_t)N * N);
+        double* cwork = arena.alloc<double>((size_t)10 * N * N);
         {   // random SPD covariance (slightly asymmetric for the symmetrisation cases) and a plausible mean
             std::vector<double> Bm((size_t)N * N);
             for (auto& x : Bm) x = rnd();

@@ -27,9 +27,10 @@ for it in range(reps):
     nxt.copy_(init)
     hv.lk_track_device(pyr[0], pyr[2], pts, nxt, st, ts, N, True)
     hv.lk_track_device(pyr[2], pyr[3], nxt, nxt2, st, ts, N, False)
-    for s in range(3):
+    for s in range(10):                      # one IMU burst: 10 x (predict + normalizeQuaternions(true)) -> one launch
         t += 0.005
-        ekf.predict(t, [0.01, 0.02, 0.2], [0.1, 0.2, 9.8])
+        ekf.predict(t, [0.01, 0.02, 0.2], [0.1, 0.2, 9.8]); ekf.normalize_quaternions(True)
+    ekf.flush()
     for n in (8, 20, 40, 84):
         l = min(160, 20 + 7 * max(1, n // 4))
         Hm = torch.from_numpy(np.asfortranarray(rng.normal(0, 0.1, (n, l))).ravel(order="F").copy()).cuda()
