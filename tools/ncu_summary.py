@@ -22,8 +22,11 @@ col = {h: i for i, h in enumerate(hdr)}
 BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 TIME = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3}
 kernels = []
+# the capture is a window of the periodic launch sequence of prof_kernels.py: align the labels on the first pyramid launch
+names = [r[col["Kernel Name"]] for r in data]
+first_pyr = next((i for i, nm in enumerate(names) if "hv_pyr" in nm and "hv_pyr" in names[(i + 1) % len(names)]), 0)
 for k, r in enumerate(data):
-    e = {"launch": LABELS[k % len(LABELS)] if len(data) % len(LABELS) == 0 else r[col["Kernel Name"]], "kernel": r[col["Kernel Name"]]}
+    e = {"launch": LABELS[(k - first_pyr) % len(LABELS)] if len(data) % len(LABELS) == 0 else r[col["Kernel Name"]], "kernel": r[col["Kernel Name"]]}
     for m in METRICS:
         if m in col and r[col[m]] not in ("", "n/a"):
             v = float(r[col[m]].replace(",", ""))
