@@ -382,17 +382,17 @@ def time_kernels(sess, reps=40):
         def upd(i, c=c):
             ops = sess.ops_dev[i % POOL_EKF]
             ekf.run_device(ctypes_slice(ops, IMU_OPS + c, 1), 1)
-        timed(f"ekf_update_cluster_kernel check+update #{c} (n={n},l={l})", upd, 2 * 8 * N * N + 8 * n * l, stream=B)
+        timed(f"ekf_update_cluster2_kernel check+update #{c} (n={n},l={l})", upd, 2 * 8 * N * N + 8 * n * l, stream=B)
         ekf.symmetrize(); ekf.augment(-1)
 
     def chk(i):
         ops = sess.ops_dev[i % POOL_EKF]
         ekf.run_device(ctypes_slice(ops, IMU_OPS + UPDATES, CHECKS - UPDATES), CHECKS - UPDATES)
-    timed(f"ekf_check_batch_cluster_kernel ({CHECKS - UPDATES} tracks, one cluster each)", chk,
+    timed(f"ekf_check_batch_cluster2_kernel ({CHECKS - UPDATES} tracks, one cluster each)", chk,
           sum(8 * N * N + 8 * n * l for n, l in (ekf_rows(c) for c in range(UPDATES, CHECKS))), stream=B)
     def sym_aug(i):
         ekf.symmetrize(); ekf.augment(-1)
-    timed("ekf_update_cluster_kernel symmetrise + augment (one launch)", sym_aug, 2 * 8 * N * N, stream=B)
+    timed("ekf_update_cluster2_kernel symmetrise + augment (one launch)", sym_aug, 2 * 8 * N * N, stream=B)
     return out
 
 
@@ -590,6 +590,14 @@ def run_ours(args):
                 "kernel_family_share_of_step": {k: round(v / tot, 3) for k, v in fam.items()},
                 "note": "achieved = algorithmic bytes (SURVEY.md 8(d)) / CUDA-event launch time of the largest launch of the kernel with the largest "
                         "share of the step; one VIO session is a chain of small dependent launches (latency-bound), see DESIGN.md 4 and kernels_batched"}
+        if "n=84" in dom:
+            # what actually bounds this kernel: fp64 tensor-core (DMMA) work on the 8 SMs of its cluster + the serial pivot chain
+            n_, l_, N_ = 84, 160, sess.ekf.N
+            fma = n_ * l_ * N_ + n_ * n_ * l_ / 2 + n_ ** 3 / 3 + n_ * n_ * (N_ + 1) / 2 + N_ * N_ * n_
+            gf = 2 * fma / kern[dom]["us_per_launch"] * 1e-3
+            peak8 = 64 * 2 * 1.965 * 8      # 64 FMA/clk/SM (tools/probe2.cu) x 2 flop x 1.965 GHz x 8 SMs, GFLOP/s
+            roof["fp64_tensor"] = {"fma_per_launch": int(fma), "achieved_gflops": round(gf, 1), "peak_gflops_of_the_8_sms_used": round(peak8, 1),
+                                   "frac": round(gf / peak8, 4), "note": "DMMA m8n8k4 measured at 64 FMA/clk/SM on B200; the kernel runs on one 8-CTA cluster"}
         for k in kern:
             kern[k]["frac_of_hbm_peak"] = round(kern[k]["gbs"] / peak, 5)
             kern[k]["share_of_step"] = round(shares[k] / tot, 3)
