@@ -32,6 +32,10 @@
 #ifndef EK2_PHASE
 #define EK2_PHASE(i) do { } while (0)
 #endif
+#ifndef EK2_ELIM_MARK                 // tools/ubench_elim2.cu: cycle stamps inside the blocked elimination
+#define EK2_ELIM_MARK(i) do { } while (0)
+#define EK2_ELIM_DECL
+#endif
 
 struct Ek2Geom { int C, B, X, W, T, PB, RS, EXTRA, SYM, oneStage, LD; };
 __host__ __device__ inline Ek2Geom ek2_geom(int n, int l, int N, bool joseph, int C)
@@ -211,21 +215,34 @@ __device__ __forceinline__ void ek2_diag_factor(const double* T, int W, int r0, 
         if (lane >= 16) x = 0.0;
         v[i] = x;
     }
-    // Row operations of the LDL' factorisation on [D | I] (rows stay unscaled on the dependent chain: per pivot one shuffle,
-    // one reciprocal, one multiply, one FMA); the D^-1/2 scaling that turns the rows into L' and L^-1 follows in parallel.
+    // Row operations of the LDL' factorisation on [D | I], TWO pivots per dependent step: the rows below a pivot pair
+    // (k, k+1) are eliminated with the inverse of its 2 x 2 block -- one reciprocal (of the determinant) per pair on the
+    // chain instead of one per pivot (measured: a pivot of the one-at-a-time version cost ~240 cycles, half of it the
+    // reciprocal's Newton steps). Eliminating row k+1 by row k, and the D^-1/2 scaling that turns the rows into L' and
+    // L^-1, are off the chain.
     bool ok = true;
-    double dsel = 1.0;                               // lane k keeps pivot k
+    double dsel = 1.0;                               // lane k (mod 8) keeps pivot d_k
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const double akk = __shfl_sync(0xffffffffu, v[k], k);
-        if (!(akk > 0.0)) ok = false;
-        if (cidx == k) dsel = akk;
-        double raw[8];
+    for (int k = 0; k < 8; k += 2) {
+        const double a = __shfl_sync(0xffffffffu, v[k], k), b = __shfl_sync(0xffffffffu, v[k], k + 1);
+        const double c = __shfl_sync(0xffffffffu, v[k + 1], k + 1);
+        double x1[8], x2[8];
 #pragma unroll
-        for (int i = k + 1; i < 8; i++) raw[i] = __shfl_sync(0xffffffffu, v[k], i);   // S is symmetric: a_ik = entry i of row k
-        const double rinv = ek2_rcp(akk);
+        for (int i = k + 2; i < 8; i++) { x1[i] = __shfl_sync(0xffffffffu, v[k], i); x2[i] = __shfl_sync(0xffffffffu, v[k + 1], i); }   // S symmetric: a_ik = entry i of row k
+        const double det = fma(a, c, -(b * b));
+        if (!(a > 0.0) || !(det > 0.0)) ok = false;
+        const double rdet = ek2_rcp(det);
+        const double ia = c * rdet, ib = -(b * rdet), ic = a * rdet;          // inverse of [[a, b], [b, c]]
 #pragma unroll
-        for (int i = k + 1; i < 8; i++) v[i] = fma(-(raw[i] * rinv), v[k], v[i]);
+        for (int i = k + 2; i < 8; i++) {
+            const double m1 = fma(x2[i], ib, x1[i] * ia), m2 = fma(x2[i], ic, x1[i] * ib);
+            v[i] = fma(-m2, v[k + 1], fma(-m1, v[k], v[i]));
+        }
+        // off the chain: row k+1 -= (b / a) row k; pivots d_k = a, d_k+1 = det / a
+        const double ra = ek2_rcp(a);
+        v[k + 1] = fma(-(b * ra), v[k], v[k + 1]);
+        if (cidx == k) dsel = a;
+        if (cidx == k + 1) dsel = det * ra;
     }
     const double rs = rsqrt(dsel);                   // lane k (mod 8): 1 / sqrt(d_k)
 #pragma unroll
@@ -250,6 +267,7 @@ __device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int
     const int g8 = lane >> 2, t4 = lane & 3;
     const int nwarps = EK2_NT / 32;
     const int MT = (n + 7) >> 3, CT = (ncols + 7) >> 3;
+    EK2_ELIM_DECL
     if (wrp == 0) {
         if (lane == 0) *s_bad = 0;
         __syncwarp();
@@ -260,6 +278,7 @@ __device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int
         if (*s_bad) return false;
         const int r0 = 8 * j, nb = min(8, n - r0);
         const double* linv = s_linv + (j & 1) * 64;
+        EK2_ELIM_MARK(0);
         // ---- a. rows of the block <- L_jj^-1 * rows, column tiles j .. CT-1 (loads clamped into the tableau: no branches)
         for (int ct = j + wrp; ct < CT; ct += nwarps) {
             double c0 = 0.0, c1 = 0.0;
@@ -276,7 +295,9 @@ __device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int
             const int col = 8 * ct + 2 * t4;
             if (g8 < nb) { if (col < ncols) T[(size_t)(r0 + g8) * W + col] = c0; if (col + 1 < ncols) T[(size_t)(r0 + g8) * W + col + 1] = c1; }
         }
+        EK2_ELIM_MARK(1);
         __syncthreads();
+        EK2_ELIM_MARK(2);
         // ---- b. trailing update: row tiles mt > j, column tiles nt >= mt (row-major list; entry 0 is the next diagonal tile).
         // Warp 0 takes entry 0 and then factors it; warps 1..15 walk contiguous ranges of the rest, reloading the A
         // fragment (-U_j[:, row tile]') only when the row tile changes.
@@ -293,35 +314,50 @@ __device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int
             const int rest = total - 1;
             int lo = ahead ? 0 : worker ? 1 + (int)(((long long)rest * widx) / nwork) : 0;
             const int hi = ahead ? 1 : worker ? 1 + (int)(((long long)rest * (widx + 1)) / nwork) : 0;
-            int mt = first, nt, idx = min(lo, total - 1);
-            while (idx >= CT - mt) { idx -= CT - mt; mt++; }
-            nt = mt + idx;
             const double* rowk0 = T + (size_t)(r0 + min(t4, nb - 1)) * W;        // k = t4
             const double* rowk1 = T + (size_t)(r0 + min(4 + t4, nb - 1)) * W;    // k = 4 + t4
             const bool k0v = t4 < nb, k1v = 4 + t4 < nb;
-            int curMt = -1;
-            double a0 = 0.0, a1 = 0.0;
-            for (; lo < hi; lo++) {
-                if (mt != curMt) {
-                    const int am = min(8 * mt + g8, ncols - 1);
-                    const double x0 = rowk0[am], x1 = rowk1[am];
-                    a0 = k0v ? -x0 : 0.0; a1 = k1v ? -x1 : 0.0;                   // A[m][k] = -U_j[k][8 mt + m]
-                    curMt = mt;
-                }
-                const int rowi = 8 * mt + g8, coli = 8 * nt + 2 * t4, bn = min(8 * nt + g8, ncols - 1);
+            if (ahead) {
+                // the next diagonal tile (first, first): A and B fragments are the same column block of U_j
+                const int cb = 8 * first, am = min(cb + g8, ncols - 1);
+                const double x0 = rowk0[am], x1 = rowk1[am];
+                const int rowi = cb + g8, coli = cb + 2 * t4;
                 double* crow = T + (size_t)min(rowi, n - 1) * W;
                 double c0 = crow[min(coli, ncols - 1)], c1 = crow[min(coli + 1, ncols - 1)];
-                const double b0 = rowk0[bn], b1 = rowk1[bn];                       // B[k][nn] = U_j[k][8 nt + nn]
-                hv_dmma(c0, c1, a0, b0);
-                hv_dmma(c0, c1, a1, b1);
+                hv_dmma(c0, c1, k0v ? -x0 : 0.0, x0);
+                hv_dmma(c0, c1, k1v ? -x1 : 0.0, x1);
                 if (rowi < n) { if (coli < ncols) crow[coli] = c0; if (coli + 1 < ncols) crow[coli + 1] = c1; }
-                if (++nt == CT) { mt++; nt = mt; }
+            } else if (worker) {
+                int mt = first, nt, idx = min(lo, total - 1);
+                while (idx >= CT - mt) { idx -= CT - mt; mt++; }
+                nt = mt + idx;
+                int curMt = -1;
+                double a0 = 0.0, a1 = 0.0;
+                for (; lo < hi; lo++) {
+                    if (mt != curMt) {
+                        const int am = min(8 * mt + g8, ncols - 1);
+                        const double x0 = rowk0[am], x1 = rowk1[am];
+                        a0 = k0v ? -x0 : 0.0; a1 = k1v ? -x1 : 0.0;                   // A[m][k] = -U_j[k][8 mt + m]
+                        curMt = mt;
+                    }
+                    const int rowi = 8 * mt + g8, coli = 8 * nt + 2 * t4, bn = min(8 * nt + g8, ncols - 1);
+                    double* crow = T + (size_t)min(rowi, n - 1) * W;
+                    double c0 = crow[min(coli, ncols - 1)], c1 = crow[min(coli + 1, ncols - 1)];
+                    const double b0 = rowk0[bn], b1 = rowk1[bn];                       // B[k][nn] = U_j[k][8 nt + nn]
+                    hv_dmma(c0, c1, a0, b0);
+                    hv_dmma(c0, c1, a1, b1);
+                    if (rowi < n) { if (coli < ncols) crow[coli] = c0; if (coli + 1 < ncols) crow[coli + 1] = c1; }
+                    if (++nt == CT) { mt++; nt = mt; }
+                }
             }
+            EK2_ELIM_MARK(3);
             if (ahead) {
                 __syncwarp();
                 ek2_diag_factor(T, W, 8 * first, min(8, n - 8 * first), lane, s_linv + (first & 1) * 64, s_bad);
             }
+            EK2_ELIM_MARK(4);
             __syncthreads();
+            EK2_ELIM_MARK(5);
         }
     }
     return !*s_bad;
