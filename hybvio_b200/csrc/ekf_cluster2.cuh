@@ -215,38 +215,25 @@ __device__ __forceinline__ void ek2_diag_factor(const double* T, int W, int r0, 
         if (lane >= 16) x = 0.0;
         v[i] = x;
     }
-    // Row operations of the LDL' factorisation on [D | I], TWO pivots per dependent step: the rows below a pivot pair
-    // (k, k+1) are eliminated with the inverse of its 2 x 2 block -- one reciprocal (of the determinant) per pair on the
-    // chain instead of one per pivot (measured: a pivot of the one-at-a-time version cost ~240 cycles, half of it the
-    // reciprocal's Newton steps). Eliminating row k+1 by row k, and the D^-1/2 scaling that turns the rows into L' and
-    // L^-1, are off the chain.
+    // Cholesky row operations on [D | I]. Dependent chain per pivot: broadcast a_kk (shuffle) -> rsqrt -> scale (own entry
+    // of the pivot row, and the multipliers of the rows below, whose RAW values were shuffled in beforehand: S is symmetric,
+    // a_ik = entry i of row k) -> one FMA. Measured alternatives on B200 (tools/ubench_elim2.cu, cycles per 8 x 8 block):
+    // shuffling the scaled row after the multiply ~1900, LDL' with rcp.approx + 2 Newton steps and a final scaling ~1950,
+    // 2 x 2 pivot blocks with one reciprocal of the determinant per pair ~1870.
     bool ok = true;
-    double dsel = 1.0;                               // lane k (mod 8) keeps pivot d_k
 #pragma unroll
-    for (int k = 0; k < 8; k += 2) {
-        const double a = __shfl_sync(0xffffffffu, v[k], k), b = __shfl_sync(0xffffffffu, v[k], k + 1);
-        const double c = __shfl_sync(0xffffffffu, v[k + 1], k + 1);
-        double x1[8], x2[8];
+    for (int k = 0; k < 8; k++) {
+        const double akk = __shfl_sync(0xffffffffu, v[k], k);
+        double raw[8];
 #pragma unroll
-        for (int i = k + 2; i < 8; i++) { x1[i] = __shfl_sync(0xffffffffu, v[k], i); x2[i] = __shfl_sync(0xffffffffu, v[k + 1], i); }   // S symmetric: a_ik = entry i of row k
-        const double det = fma(a, c, -(b * b));
-        if (!(a > 0.0) || !(det > 0.0)) ok = false;
-        const double rdet = ek2_rcp(det);
-        const double ia = c * rdet, ib = -(b * rdet), ic = a * rdet;          // inverse of [[a, b], [b, c]]
+        for (int i = k + 1; i < 8; i++) raw[i] = __shfl_sync(0xffffffffu, v[k], i);
+        if (!(akk > 0.0)) ok = false;
+        const double r = rsqrt(akk);
+        const double u = v[k] * r;                   // row k of L' (entry of this column)
+        v[k] = u;
 #pragma unroll
-        for (int i = k + 2; i < 8; i++) {
-            const double m1 = fma(x2[i], ib, x1[i] * ia), m2 = fma(x2[i], ic, x1[i] * ib);
-            v[i] = fma(-m2, v[k + 1], fma(-m1, v[k], v[i]));
-        }
-        // off the chain: row k+1 -= (b / a) row k; pivots d_k = a, d_k+1 = det / a
-        const double ra = ek2_rcp(a);
-        v[k + 1] = fma(-(b * ra), v[k], v[k + 1]);
-        if (cidx == k) dsel = a;
-        if (cidx == k + 1) dsel = det * ra;
+        for (int i = k + 1; i < 8; i++) v[i] = fma(-(raw[i] * r), u, v[i]);
     }
-    const double rs = rsqrt(dsel);                   // lane k (mod 8): 1 / sqrt(d_k)
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] *= __shfl_sync(0xffffffffu, rs, i);
     if (lane >= 8 && lane < 16) {
 #pragma unroll
         for (int i = 0; i < 8; i++) linv[i * 8 + (lane - 8)] = v[i];
