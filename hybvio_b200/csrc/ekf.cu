@@ -338,245 +338,13 @@ __global__ void __launch_bounds__(EKF_NT) ekf_update_kernel(EkfUpdateArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------ predict
-__device__ __forceinline__ void quat2rmat_d(const double* q, double* R /*row-major 3x3*/, double (*dR)[9])
-{
-    // src/odometry/util.cpp:10-47
-    R[0] = q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3]; R[1] = 2 * q[1] * q[2] - 2 * q[0] * q[3]; R[2] = 2 * q[1] * q[3] + 2 * q[0] * q[2];
-    R[3] = 2 * q[1] * q[2] + 2 * q[0] * q[3]; R[4] = q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3]; R[5] = 2 * q[2] * q[3] - 2 * q[0] * q[1];
-    R[6] = 2 * q[1] * q[3] - 2 * q[0] * q[2]; R[7] = 2 * q[2] * q[3] + 2 * q[0] * q[1]; R[8] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
-    const double a = 2 * q[0], b = 2 * q[1], c = 2 * q[2], d = 2 * q[3];
-    double* D0 = dR[0]; D0[0] = a; D0[1] = -d; D0[2] = c; D0[3] = d; D0[4] = a; D0[5] = -b; D0[6] = -c; D0[7] = b; D0[8] = a;
-    double* D1 = dR[1]; D1[0] = b; D1[1] = c; D1[2] = d; D1[3] = c; D1[4] = -b; D1[5] = -a; D1[6] = d; D1[7] = a; D1[8] = -b;
-    double* D2 = dR[2]; D2[0] = -c; D2[1] = b; D2[2] = a; D2[3] = b; D2[4] = c; D2[5] = d; D2[6] = -a; D2[7] = d; D2[8] = -c;
-    double* D3 = dR[3]; D3[0] = -d; D3[1] = -a; D3[2] = b; D3[3] = a; D3[4] = -d; D3[5] = c; D3[6] = b; D3[7] = c; D3[8] = d;
-}
-
 #ifdef HV_EKF_TIMING
 #define PMARK(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.b.res[8 + (i)] = (double)t_; } } while (0)
 #else
 #define PMARK(i) do { } while (0)
 #endif
-#define DX(i, j) s_dydx[(i) + (j) * 20]
-#define DQ(i, j) s_dydq[(i) + (j) * 20]
-// predict() for `count` consecutive IMU samples in ONE launch (ekf.cpp:320-514 applied count times).
-// Per sample only the 20-dimensional inertial part is touched: mean, Jacobians dydx (20x20) / dydq (20x12), the
-// P00 block and the running product Dacc = dydx_k ... dydx_1, all in shared memory. The two off-diagonal strips of P
-// are transformed ONCE at the end with Dacc: P[20:,0:20] Dacc' and Dacc P[0:20,20:]  -- algebraically the same as
-// applying every dydx in turn (fp64 differences are association-order rounding, ~1e-16 relative).
-// A dependent fp64 operation costs 24 cycles on B200, so the ~600-flop Jacobian sequence is cut into barrier-separated
-// stages whose independent pieces run in different warps / lanes.
-__global__ void __launch_bounds__(EKF_NT) ekf_predict_v1_kernel(EkfPredictArgs a)
-{
-    __shared__ double s_dydx[400], s_dydq[240], s_Q[144], s_P00[400], s_T1[400], s_G1[240], s_acc[400];
-    __shared__ double s_m[EKF_INER], s_A[16], s_qn[4], s_Tx[3], s_B[12];
-    const int tid = threadIdx.x, N = a.b.N;
-    const int lane = tid & 31, wrp = tid >> 5;
-    double* P = a.b.P;
-    PMARK(0);
-    for (int i = tid; i < 400; i += EKF_NT) { s_acc[i] = (i % 21 == 0) ? 1.0 : 0.0; s_P00[i] = P[(i % 20) + (size_t)(i / 20) * N]; }
-    for (int i = tid; i < 144; i += EKF_NT) s_Q[i] = a.b.Q[i];
-    if (tid < EKF_INER) s_m[tid] = a.b.m[tid];
-    __syncthreads();
-    PMARK(1);
-    for (int si = 0; si < a.count; si++) {
-        const EkfPredictSample& S = a.s[si];
-        const double dt = S.dt;
-        for (int i = tid; i < 400; i += EKF_NT) s_dydx[i] = (i % 21 == 0) ? 1.0 : 0.0;
-        for (int i = tid; i < 240; i += EKF_NT) s_dydq[i] = 0.0;
-        // mean-reverting random-walk blocks of Q are re-set for this dt (ekf.cpp:397-412); the change persists in Q
-        if (tid < 9) {
-            const int r = tid % 3, c = tid / 3;
-            if (S.qBaa >= 0.0) s_Q[(EKF_Q_BAA_DRIFT + r) + (EKF_Q_BAA_DRIFT + c) * 12] = r == c ? S.qBaa : 0.0;
-            if (S.qBga >= 0.0) s_Q[(EKF_Q_BGA_DRIFT + r) + (EKF_Q_BGA_DRIFT + c) * 12] = r == c ? S.qBga : 0.0;
-        }
-        __syncthreads();
-        // stage 1 (16 lanes): A = exp(S) = cos(th) I + sin(th)/th S, S = -dt/2 Omega(w)  (closed form of the reference's
-        // Pade S.exp(), ekf.cpp:414-425: Omega^2 = -|w|^2 I), th = |w| dt / 2
-        if (wrp == 0 && lane < 16) {
-            const double w0 = S.xg[0] - s_m[EKF_BGA], w1 = S.xg[1] - s_m[EKF_BGA + 1], w2 = S.xg[2] - s_m[EKF_BGA + 2];
-            const double c = -dt / 2;
-            const double th = sqrt(w0 * w0 + w1 * w1 + w2 * w2) * fabs(c);
-            const double ct = cos(th), sc = th < 1e-8 ? 1.0 - th * th / 6.0 : sin(th) / th;
-            // Omega row-major {0,-w0,-w1,-w2, w0,0,-w2,w1, w1,w2,0,-w0, w2,-w1,w0,0}: component (3 = zero) / sign per entry
-            const int comp = (0xC6396C93u >> (2 * lane)) & 3;
-            const bool neg = (0x284Eu >> lane) & 1;
-            double wv = comp == 0 ? w0 : comp == 1 ? w1 : comp == 2 ? w2 : 0.0;
-            if (neg) wv = -wv;
-            s_A[lane] = sc * (wv * c) + ((lane % 5 == 0) ? ct : 0.0);
-        }
-        if (wrp == 1 && lane < 3) s_Tx[lane] = s_m[EKF_BAT + lane] * S.xa[lane] - s_m[EKF_BAA + lane];
-        __syncthreads();
-        // stage 2: q_new = A q; d(orientation)/d(gyro noise) columns A dS_j q (ekf.cpp:470-476) and their negatives
-        if (wrp == 0 && lane < 4) {
-            double v = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) v += s_A[lane * 4 + j] * s_m[EKF_ORI + j];
-            s_qn[lane] = v;
-        }
-        if (wrp == 1 && lane < 3) {
-            const int j = lane;
-            const double h = dt / 2;
-            const double q0 = s_m[EKF_ORI], q1 = s_m[EKF_ORI + 1], q2 = s_m[EKF_ORI + 2], q3 = s_m[EKF_ORI + 3];
-            double t0, t1, t2, t3;                    // dS_j * q
-            if (j == 0) { t0 = h * q1; t1 = -h * q0; t2 = h * q3; t3 = -h * q2; }
-            else if (j == 1) { t0 = h * q2; t1 = -h * q3; t2 = -h * q0; t3 = h * q1; }
-            else { t0 = h * q3; t1 = h * q2; t2 = -h * q1; t3 = -h * q0; }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const double v = s_A[i * 4] * t0 + s_A[i * 4 + 1] * t1 + s_A[i * 4 + 2] * t2 + s_A[i * 4 + 3] * t3;
-                DQ(EKF_ORI + i, EKF_Q_GYRO + j) = v;
-                DX(EKF_ORI + i, EKF_BGA + j) = -v;   // ekf.cpp:492
-            }
-        }
-        if (wrp == 2 && lane < 16) DX(EKF_ORI + lane / 4, EKF_ORI + lane % 4) = s_A[lane];
-        if (wrp == 3 && lane < 3) {
-            DX(EKF_POS + lane, EKF_VEL + lane) = dt;
-            DQ(EKF_BGA + lane, EKF_Q_BGA_DRIFT + lane) = 1.0; DQ(EKF_BAA + lane, EKF_Q_BAA_DRIFT + lane) = 1.0;
-        }
-        __syncthreads();
-        // stage 3: rotation matrix of the NEW quaternion and its derivatives (src/odometry/util.cpp:10-47): one lane
-        // per quaternion component for B[:, qi] = dR[qi]' Txab dt, one lane for the R-dependent blocks and the mean
-        double mnew = 0.0; bool mset = false;     // each thread writes at most one mean entry, after the stage barrier
-        if (wrp == 0 && lane < 4) {
-            const double q0 = s_qn[0], q1 = s_qn[1], q2 = s_qn[2], q3 = s_qn[3];
-            const double a2 = 2 * q0, b2 = 2 * q1, c2 = 2 * q2, d2 = 2 * q3;
-            double D[9];
-            if (lane == 0) { D[0] = a2; D[1] = -d2; D[2] = c2; D[3] = d2; D[4] = a2; D[5] = -b2; D[6] = -c2; D[7] = b2; D[8] = a2; }
-            else if (lane == 1) { D[0] = b2; D[1] = c2; D[2] = d2; D[3] = c2; D[4] = -b2; D[5] = -a2; D[6] = d2; D[7] = a2; D[8] = -b2; }
-            else if (lane == 2) { D[0] = -c2; D[1] = b2; D[2] = a2; D[3] = b2; D[4] = c2; D[5] = d2; D[6] = -a2; D[7] = d2; D[8] = -c2; }
-            else { D[0] = -d2; D[1] = -a2; D[2] = b2; D[3] = a2; D[4] = -d2; D[5] = c2; D[6] = b2; D[7] = c2; D[8] = d2; }
-#pragma unroll
-            for (int i = 0; i < 3; i++) s_B[i * 4 + lane] = (D[i] * s_Tx[0] + D[3 + i] * s_Tx[1] + D[6 + i] * s_Tx[2]) * dt;
-        }
-        if (wrp == 1 && lane < 3) {
-            const double* q = s_qn;
-            const int i = lane;
-            double R[9];
-            R[0] = q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3]; R[1] = 2 * q[1] * q[2] - 2 * q[0] * q[3]; R[2] = 2 * q[1] * q[3] + 2 * q[0] * q[2];
-            R[3] = 2 * q[1] * q[2] + 2 * q[0] * q[3]; R[4] = q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3]; R[5] = 2 * q[2] * q[3] - 2 * q[0] * q[1];
-            R[6] = 2 * q[1] * q[3] - 2 * q[0] * q[2]; R[7] = 2 * q[2] * q[3] + 2 * q[0] * q[1]; R[8] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
-            const double gi = i == 2 ? -a.gravity : 0.0;
-            // velocity += (R' Txab + g) dt with the OLD biases (ekf.cpp:435-436)
-            mnew = s_m[EKF_VEL + i] + (R[i] * s_Tx[0] + R[3 + i] * s_Tx[1] + R[6 + i] * s_Tx[2] + gi) * dt; mset = true;
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                DQ(EKF_VEL + i, EKF_Q_ACC + j) = R[j * 3 + i] * dt;
-                DX(EKF_VEL + i, EKF_BAA + j) = -R[j * 3 + i] * dt;
-                DX(EKF_VEL + i, EKF_BAT + j) = R[j * 3 + i] * S.xa[j] * dt;
-            }
-        }
-        if (wrp == 2 && lane < 13) {
-            // position with the OLD velocity, orientation, mean-reverting biases (ekf.cpp:432, 440-448)
-            if (lane < 3) mnew = s_m[EKF_POS + lane] + s_m[EKF_VEL + lane] * dt;
-            else if (lane < 7) mnew = s_qn[lane - 3];
-            else if (lane < 10) mnew = s_m[EKF_BAA + lane - 7] * S.baaDecay;
-            else mnew = s_m[EKF_BGA + lane - 10] * S.bgaDecay;
-            mset = true;
-        }
-        __syncthreads();
-        if (mset) {
-            if (wrp == 1) s_m[EKF_VEL + lane] = mnew;
-            else s_m[lane < 3 ? EKF_POS + lane : lane < 7 ? EKF_ORI + lane - 3 : lane < 10 ? EKF_BAA + lane - 7 : EKF_BGA + lane - 10] = mnew;
-        }
-        // stage 4: d vel / d quat = B A  (ekf.cpp:458-461)
-        if (wrp == 0 && lane < 12) {
-            const int i = lane / 4, j = lane % 4;
-            double v = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) v += s_B[i * 4 + k] * s_A[k * 4 + j];
-            DX(EKF_VEL + i, EKF_ORI + j) = v;
-        }
-        __syncthreads();
-        // stage 5: d vel / d gyro noise and d vel / d gyro bias (ekf.cpp:486-489)
-        if (wrp == 0 && lane < 9) {
-            const int i = lane / 3, j = lane % 3;
-            double v = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) v += DX(EKF_VEL + i, EKF_ORI + k) * DQ(EKF_ORI + k, EKF_Q_GYRO + j);
-            DQ(EKF_VEL + i, EKF_Q_GYRO + j) = v;
-            DX(EKF_VEL + i, EKF_BGA + j) = -v;
-        }
-        __syncthreads();
-        // P00 = dydx P00 dydx' + dydq Q dydq'  and  Dacc = dydx Dacc   (4 interleaved partial sums per dot product)
-        double t1 = 0.0, accNew = 0.0, g1 = 0.0;
-        if (tid < 400) {
-            const int i = tid % 20, j = tid / 20;
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0, u0 = 0, u1 = 0, u2 = 0, u3 = 0;
-#pragma unroll
-            for (int k = 0; k < 20; k += 4) {
-                s0 += DX(i, k) * s_P00[k + j * 20]; s1 += DX(i, k + 1) * s_P00[k + 1 + j * 20]; s2 += DX(i, k + 2) * s_P00[k + 2 + j * 20]; s3 += DX(i, k + 3) * s_P00[k + 3 + j * 20];
-                u0 += DX(i, k) * s_acc[k + j * 20]; u1 += DX(i, k + 1) * s_acc[k + 1 + j * 20]; u2 += DX(i, k + 2) * s_acc[k + 2 + j * 20]; u3 += DX(i, k + 3) * s_acc[k + 3 + j * 20];
-            }
-            t1 = (s0 + s1) + (s2 + s3);
-            accNew = (u0 + u1) + (u2 + u3);
-        }
-        if (tid < 240) {
-            const int i = tid % 20, j = tid / 20;
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-            for (int k = 0; k < 12; k += 4) { s0 += DQ(i, k) * s_Q[k + j * 12]; s1 += DQ(i, k + 1) * s_Q[k + 1 + j * 12]; s2 += DQ(i, k + 2) * s_Q[k + 2 + j * 12]; s3 += DQ(i, k + 3) * s_Q[k + 3 + j * 12]; }
-            g1 = (s0 + s1) + (s2 + s3);
-        }
-        __syncthreads();
-        if (tid < 400) { s_T1[tid] = t1; s_acc[tid] = accNew; }
-        if (tid < 240) s_G1[tid] = g1;
-        __syncthreads();
-        if (tid < 400) {
-            const int i = tid % 20, j = tid / 20;
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0, g0 = 0, g1b = 0, g2 = 0, g3 = 0;
-#pragma unroll
-            for (int k = 0; k < 20; k += 4) { s0 += s_T1[i + k * 20] * DX(j, k); s1 += s_T1[i + (k + 1) * 20] * DX(j, k + 1); s2 += s_T1[i + (k + 2) * 20] * DX(j, k + 2); s3 += s_T1[i + (k + 3) * 20] * DX(j, k + 3); }
-#pragma unroll
-            for (int k = 0; k < 12; k += 4) { g0 += s_G1[i + k * 20] * DQ(j, k); g1b += s_G1[i + (k + 1) * 20] * DQ(j, k + 1); g2 += s_G1[i + (k + 2) * 20] * DQ(j, k + 2); g3 += s_G1[i + (k + 3) * 20] * DQ(j, k + 3); }
-            s_P00[tid] = ((s0 + s1) + (s2 + s3)) + ((g0 + g1b) + (g2 + g3));
-        }
-        __syncthreads();
-    }
-    PMARK(2);
-    // ---- write back the inertial block, then transform the two strips with the accumulated Jacobian
-    if (tid < EKF_INER) a.b.m[tid] = s_m[tid];
-    for (int i = tid; i < 400; i += EKF_NT) { a.b.dydx[i] = s_dydx[i]; P[(i % 20) + (size_t)(i / 20) * N] = s_P00[i]; }
-    for (int i = tid; i < 144; i += EKF_NT) a.b.Q[i] = s_Q[i];
-#define AC(i, j) s_acc[(i) + (j) * 20]
-    const int rest = N - EKF_INER;
-    for (int r = tid; r < 2 * rest; r += EKF_NT) {
-        if (r < rest) {                                     // P[20+r, 0:20] = P[20+r, 0:20] * Dacc'
-            const int i = EKF_INER + r;
-            double row[20], out[20];
-#pragma unroll
-            for (int k = 0; k < 20; k++) row[k] = P[i + (size_t)k * N];
-#pragma unroll
-            for (int j = 0; j < 20; j++) out[j] = 0.0;
-#pragma unroll
-            for (int k = 0; k < 20; k++) {
-                const double rk = row[k];
-#pragma unroll
-                for (int j = 0; j < 20; j++) out[j] += rk * AC(j, k);
-            }
-#pragma unroll
-            for (int j = 0; j < 20; j++) P[i + (size_t)j * N] = out[j];
-        } else {                                            // P[0:20, 20+c] = Dacc * P[0:20, 20+c]
-            double* colp = P + (size_t)(EKF_INER + r - rest) * N;
-            double col[20], out[20];
-#pragma unroll
-            for (int k = 0; k < 20; k++) col[k] = colp[k];
-#pragma unroll
-            for (int j = 0; j < 20; j++) out[j] = 0.0;
-#pragma unroll
-            for (int k = 0; k < 20; k++) {
-                const double ck = col[k];
-#pragma unroll
-                for (int j = 0; j < 20; j++) out[j] += AC(j, k) * ck;
-            }
-#pragma unroll
-            for (int j = 0; j < 20; j++) colp[j] = out[j];
-        }
-    }
-    PMARK(4);
-}
-
-// Current predict kernel: parallel-over-samples Jacobians + short sequential chains (ekf_predict.cuh). The kernel above
-// (one sample after the other, ~9 barriers per sample) is kept this round as an A/B switch: HV_EKF_PREDICT_V1=1.
+// predict() for `count` consecutive IMU samples in ONE launch (ekf.cpp:320-514 applied count times, with the
+// normalizeQuaternions(true) calls that follow them): see ekf_predict.cuh.
 #define EKF_PMARK(i) PMARK(i)
 #include "ekf_predict.cuh"
 __global__ void __launch_bounds__(EKF_NT) ekf_predict_kernel(EkfPredictArgs a)
@@ -793,8 +561,6 @@ cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s)
 }
 cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s)
 {
-    static const bool v1 = getenv("HV_EKF_PREDICT_V1") != nullptr;
-    if (v1) { ekf_predict_v1_kernel<<<1, EKF_NT, 0, s>>>(a); return cudaGetLastError(); }
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(ekf_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ekf_predict_smem_bytes(EKF_MAX_PREDICT));

@@ -637,8 +637,7 @@ int hv_ekf_symmetrize(hv_ekf* e)
 int hv_ekf_normalize_quaternions(hv_ekf* e, int onlyCurrent)
 {
     EKF_ENTER_LAZY(e, "hv_ekf_normalize_quaternions");
-    static const bool v1 = getenv("HV_EKF_PREDICT_V1") != nullptr;
-    if (onlyCurrent && !v1 && e->pend.count > 0 && !e->pend.s[e->pend.count - 1].normAfter) {
+    if (onlyCurrent && e->pend.count > 0 && !e->pend.s[e->pend.count - 1].normAfter) {
         e->pend.s[e->pend.count - 1].normAfter = 1;              // folded into the deferred predict launch
         return HV_OK;
     }
