@@ -281,8 +281,6 @@ static int lk_fill(LkLaunch& L, hv_ctx* c, int maxLevel, int maxIter, double eps
     L.eps2 = e * e;
     L.minEig = (float)minEig;
     L.doneCounter = nullptr; L.doneTarget = 0; L.seq = 0; L.hostFlag = nullptr;
-    static const bool prefetch = getenv("HV_LK_PREFETCH") != nullptr;      // A/B switch this round: off unless set
-    L.prefetch = prefetch ? 1 : 0;
     return HV_OK;
 }
 

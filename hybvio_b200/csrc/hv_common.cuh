@@ -60,7 +60,6 @@ struct LkLaunch {
     // Completion signal for the host-buffer API (single job, CTA-per-feature kernel): every CTA bumps *doneCounter after
     // its results are visible system-wide; the one that reaches doneTarget stores seq into *hostFlag (mapped pinned host
     // memory), which the host polls instead of a D2H copy + stream synchronisation. NULL: no signal.
-    int prefetch;               // CTA-per-feature kernel: template windows of all levels are fetched up front (one L2 round trip)
     unsigned* doneCounter;
     unsigned doneTarget, seq;
     volatile unsigned* hostFlag;

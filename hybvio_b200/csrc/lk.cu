@@ -279,40 +279,6 @@ __global__ void __launch_bounds__(LKC_NW * 32) hv_lk_cta_kernel(LkLaunch L)
     int status = 1;
     int Ipat[RPW], dIpat[RPW];
 
-    // The template windows depend only on the previous point, not on the iteration: fetch them for ALL levels now (one L2
-    // round trip instead of one per level). Each thread parks its own samples in shared memory (used as per-thread scratch:
-    // a level-indexed register array would live in local memory) and reads them back when the level comes up.
-    constexpr int PFL = 4;
-    __shared__ uint8_t s_tv[PFL][LKC_NW][RPW + 1][32];
-    __shared__ int s_td[PFL][LKC_NW][RPW + 1][32];
-    const bool pf = L.prefetch != 0;
-    if (pf) {
-        int tv[PFL][RPW + 1], td[PFL][RPW + 1];
-#pragma unroll
-        for (int lv = 0; lv < PFL; lv++) {
-            const HvLevel LI = PI.lv[min(lv, maxLevel)];
-            const float lscale = (float)(1. / (1 << lv));
-            const float px = __fsub_rn(__fmul_rn(prevPt.x, lscale), halfWin), py = __fsub_rn(__fmul_rn(prevPt.y, lscale), halfWin);
-            const int ipx = cv_floor(px), ipy = cv_floor(py);
-            const bool inwin = lv <= maxLevel && !(ipx < -WIN || ipx >= LI.w || ipy < -WIN || ipy >= LI.h);
-            const int cx = ipx + col;
-            const bool colOk = (unsigned)cx < (unsigned)LI.w;
-            const int cxr = inwin ? hv_reflect101(cx, LI.w) : 0;
-#pragma unroll
-            for (int y = 0; y <= RPW; y++) {
-                const int ry = ipy + r0 + min(y, nr);
-                const int ryr = inwin ? hv_reflect101(ry, LI.h) : 0;
-                tv[lv][y] = inwin ? (int)__ldg(LI.gray + (size_t)ryr * LI.gpitch + cxr) : 0;
-                td[lv][y] = (inwin && colOk && (unsigned)ry < (unsigned)LI.h)
-                                ? __ldg(reinterpret_cast<const int*>(LI.deriv + (size_t)ry * LI.dpitch + cx)) : 0;
-            }
-        }
-#pragma unroll
-        for (int lv = 0; lv < PFL; lv++)
-#pragma unroll
-            for (int y = 0; y <= RPW; y++) { s_tv[lv][wrp][y][lane] = (uint8_t)tv[lv][y]; s_td[lv][wrp][y][lane] = td[lv][y]; }
-    }
-
     for (int level = maxLevel; level >= 0; --level) {
         const HvLevel LI = PI.lv[level];
         const HvLevel LJ = PJ.lv[level];
@@ -341,18 +307,13 @@ __global__ void __launch_bounds__(LKC_NW * 32) hv_lk_cta_kernel(LkLaunch L)
             const bool colOk = (unsigned)cx < (unsigned)LI.w;
             const int cxr = hv_reflect101(cx, LI.w);
             int v[RPW + 1], d[RPW + 1];
-            if (pf && level < PFL) {
 #pragma unroll
-                for (int y = 0; y <= RPW; y++) { v[y] = s_tv[level][wrp][y][lane]; d[y] = s_td[level][wrp][y][lane]; }
-            } else {
-#pragma unroll
-                for (int y = 0; y <= RPW; y++) {
-                    const int ry = ipy + r0 + min(y, nr);
-                    const int ryr = hv_reflect101(ry, LI.h);
-                    v[y] = __ldg(LI.gray + (size_t)ryr * LI.gpitch + cxr);
-                    d[y] = (colOk && (unsigned)ry < (unsigned)LI.h)
-                               ? __ldg(reinterpret_cast<const int*>(LI.deriv + (size_t)ry * LI.dpitch + cx)) : 0;
-                }
+            for (int y = 0; y <= RPW; y++) {
+                const int ry = ipy + r0 + min(y, nr);
+                const int ryr = hv_reflect101(ry, LI.h);
+                v[y] = __ldg(LI.gray + (size_t)ryr * LI.gpitch + cxr);
+                d[y] = (colOk && (unsigned)ry < (unsigned)LI.h)
+                           ? __ldg(reinterpret_cast<const int*>(LI.deriv + (size_t)ry * LI.dpitch + cx)) : 0;
             }
             int vr0 = __shfl_down_sync(0xffffffffu, v[0], 1), dr0 = __shfl_down_sync(0xffffffffu, d[0], 1);
 #pragma unroll
