@@ -42,6 +42,14 @@ static int ek2_cluster_size()
     return C;
 }
 
+// Single (non-batched) measurements with at least HV_EKF_C16_MIN_N rows run on a 16-CTA cluster (non-portable size): the dense
+// products halve, the exchanges get a little slower. Off unless the variable is set (A/B switch this round).
+static int ek2_cluster_size_for(int n, bool batch)
+{
+    static const int minN = [] { const char* s = getenv("HV_EKF_C16_MIN_N"); return s ? atoi(s) : (1 << 30); }();
+    return (!batch && n >= minN) ? 16 : ek2_cluster_size();
+}
+
 bool ekf_cluster2_fits(int n, int l, int N, bool joseph)
 {
     return N <= EK2_MAXN && ek2_smem_bytes(n, l, N, joseph, ek2_cluster_size()) + EK2_STATIC_SMEM <= EK2_SMEM_LIMIT;
@@ -67,13 +75,13 @@ static cudaError_t ek2_prepare(K kernel, int C)
 {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EK2_SMEM_LIMIT - EK2_STATIC_SMEM));
     if (e != cudaSuccess) return e;
-    if (C > 8) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    return e;
+    (void)C;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
 }
 
 cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s)
 {
-    const int C = ek2_cluster_size();
+    const int C = ek2_cluster_size_for(a.n, false);
     static bool ready = false;
     if (!ready) { cudaError_t e = ek2_prepare(ekf_update_cluster2_kernel, C); if (e != cudaSuccess) return e; ready = true; }
     const size_t smem = ek2_smem_bytes(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT, C);
