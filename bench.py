@@ -471,6 +471,10 @@ def run_selftest_dist(args):
 
 
 def run_ours(args):
+    if args.sessions > 1:
+        # several sessions share the GPU: a dependent kernel that was launched early (programmatic dependent launch) would hold
+        # an SM and ~200 KB of shared memory while it waits for its predecessor -- SMs the other sessions could use
+        os.environ.setdefault("HV_EKF_NO_PDL", "1")
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))

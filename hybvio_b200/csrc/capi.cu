@@ -45,7 +45,8 @@ static int ctx_create(int device, cudaStream_t stream, bool own, hv_ctx** out)
     if (own) { HV_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
     else c->stream = stream;
     HV_CUDA(cudaMalloc(&c->d_table, sizeof(HvPyrDesc) * HV_TABLE_CAPACITY));
-    HV_CUDA(cudaMemset(c->d_table, 0, sizeof(HvPyrDesc) * HV_TABLE_CAPACITY));
+    HV_CUDA(cudaMemsetAsync(c->d_table, 0, sizeof(HvPyrDesc) * HV_TABLE_CAPACITY, c->stream));
+    HV_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = HV_TABLE_CAPACITY - 1; i >= 0; --i) c->freeSlots.push_back(i);
     *out = c;
     return HV_OK;
@@ -93,7 +94,8 @@ int hv_ctx_reserve_stage(hv_ctx* c, size_t bytes)
     HV_CUDA(cudaHostAlloc(&c->h_stage, cap + 64, cudaHostAllocMapped));          // + 64: the completion flag
     HV_CUDA(cudaHostGetDevicePointer(&c->hd_stage, c->h_stage, 0));
     memset(c->h_stage, 0, cap + 64);
-    if (!c->d_done) { HV_CUDA(cudaMalloc(&c->d_done, sizeof(unsigned))); HV_CUDA(cudaMemset(c->d_done, 0, sizeof(unsigned))); c->doneCount = 0; }
+    // (stream-ordered: the context's stream is non-blocking, a cudaMemset on the legacy stream could land after the first kernel's counts)
+    if (!c->d_done) { HV_CUDA(cudaMalloc(&c->d_done, sizeof(unsigned))); HV_CUDA(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned), c->stream)); c->doneCount = 0; }
     c->stageBytes = cap;
     return HV_OK;
 }
@@ -368,7 +370,7 @@ int hv_lk_track(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* prevXY, floa
         c->launches += 1;
         rc = hv_poll_flag(flag, L.seq, c->stream, "hv_lk_track");
         if (rc != HV_OK) {      // resynchronise the counter before anybody polls again
-            cudaStreamSynchronize(c->stream); cudaMemset(c->d_done, 0, sizeof(unsigned)); c->doneCount = 0;
+            cudaStreamSynchronize(c->stream); cudaMemsetAsync(c->d_done, 0, sizeof(unsigned), c->stream); cudaStreamSynchronize(c->stream); c->doneCount = 0;
             return rc;
         }
     } else {
