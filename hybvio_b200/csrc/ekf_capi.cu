@@ -18,6 +18,8 @@ struct hv_ekf {
     double* d_in = nullptr;       // staging for H, f, y uploads
     size_t inDoubles = 0;
     double* h_pin = nullptr;      // pinned host staging: [in (inDoubles) | out (N + 8)]
+    cudaEvent_t evStaged = nullptr;   // recorded after the H2D copy out of h_pin: the staging block may be refilled once it has fired
+    bool stagedPending = false;
     double* h_sig = nullptr;      // mapped pinned result words the kernels write for a polling host: 4 doubles per batch slot
     double* d_sig = nullptr;      // (device alias)
     double sigSeq = 0.0;
@@ -156,6 +158,7 @@ static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
     e->b.N = e->N; e->b.trail = e->trail; e->b.mapDim = e->mapDim;
     err = cudaMallocHost(&e->h_pin, (e->inDoubles + N + 8 + EKF_RES_STRIDE * EKF_MAX_BATCH) * sizeof(double));
     if (err != cudaSuccess) { cudaFree(e->d_block); delete e; hv_set_error("hv_ekf_create: cudaMallocHost failed"); return HV_ERR_OOM; }
+    if (cudaEventCreateWithFlags(&e->evStaged, cudaEventDisableTiming) != cudaSuccess) { cudaFree(e->d_block); cudaFreeHost(e->h_pin); delete e; hv_set_error("hv_ekf_create: cudaEventCreate failed"); return HV_ERR_CUDA; }
     err = cudaHostAlloc(&e->h_sig, 4 * sizeof(double) * (EKF_MAX_BATCH + 1), cudaHostAllocMapped);
     if (err == cudaSuccess) err = cudaHostGetDevicePointer(&e->d_sig, e->h_sig, 0);
     if (err != cudaSuccess) { cudaFree(e->d_block); cudaFreeHost(e->h_pin); delete e; hv_set_error("hv_ekf_create: mapped result buffer: %s", cudaGetErrorString(err)); return HV_ERR_OOM; }
@@ -211,6 +214,7 @@ int hv_ekf_destroy(hv_ekf* e)
     cudaFree(e->d_block);
     cudaFreeHost(e->h_pin);
     cudaFreeHost(e->h_sig);
+    if (e->evStaged) cudaEventDestroy(e->evStaged);
     delete e;
     return HV_OK;
 }
@@ -494,6 +498,20 @@ static int visual_args(hv_ekf* e, const char* who, int n, int l, double r, doubl
     return HV_OK;
 }
 
+// The pinned staging block is shared by all calls; an asynchronous call (updateVisualTrack) returns while its H2D copy may
+// still be queued, so the next call must not refill the block before that copy has read it.
+static int staging_acquire(hv_ekf* e)
+{
+    if (e->stagedPending) { HV_CUDA(cudaEventSynchronize(e->evStaged)); e->stagedPending = false; }
+    return HV_OK;
+}
+static int staging_release(hv_ekf* e)      // call right after the H2D copy has been enqueued
+{
+    HV_CUDA(cudaEventRecord(e->evStaged, e->ctx->stream));
+    e->stagedPending = true;
+    return HV_OK;
+}
+
 // Waits for `count` result slots of the mapped buffer to carry sequence number seq (kernels of ekf_cluster2.cuh).
 static int poll_results(hv_ekf* e, int count, double seq, const char* who)
 {
@@ -526,8 +544,12 @@ static int visual_host(hv_ekf* e, const char* who, const double* H, int n, int l
     cudaStream_t s = e->ctx->stream;
     const size_t nl = (size_t)n * l, inD = nl + 2 * (size_t)n;
     double* hin = e->h_pin;
+    rc = staging_acquire(e);
+    if (rc != HV_OK) return rc;
     memcpy(hin, H, nl * sizeof(double)); memcpy(hin + nl, f, n * sizeof(double)); memcpy(hin + nl + n, y, n * sizeof(double));
     HV_CUDA(cudaMemcpyAsync(e->d_in, hin, inD * sizeof(double), cudaMemcpyHostToDevice, s));
+    rc = staging_release(e);
+    if (rc != HV_OK) return rc;
     a.H = e->d_in; a.f = e->d_in + nl; a.y = e->d_in + nl + n;
     prep_update(e, a);
     const bool polled = ekf_polling() && mode != EKF_MODE_UPDATE && !mOut && ekf_update_uses_cluster2(a);
@@ -683,6 +705,7 @@ static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, b
     memset(&b, 0, sizeof(b));
     b.count = count;
     size_t off = 0;
+    if (host) { int rc = staging_acquire(e); if (rc != HV_OK) return rc; }
     for (int i = 0; i < count; i++) {
         const hv_ekf_op& o = ops[first + i];
         EkfUpdateArgs tmp;
@@ -700,7 +723,11 @@ static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, b
             off += nl + 2 * (size_t)o.n;
         } else { it.H = o.H; it.f = o.f; it.y = o.y; }
     }
-    if (host) HV_CUDA(cudaMemcpyAsync(e->d_in, e->h_pin, off * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (host) {
+        HV_CUDA(cudaMemcpyAsync(e->d_in, e->h_pin, off * sizeof(double), cudaMemcpyHostToDevice, s));
+        int rc = staging_release(e);
+        if (rc != HV_OK) return rc;
+    }
     a.b = e->b; a.noiseScale = e->noiseScale; a.useGlobalWork = 0;
     static const bool v1 = getenv("HV_EKF_CLUSTER_V1") != nullptr;
     bool fits2 = !v1;
