@@ -91,7 +91,8 @@ public:
         pyramid->pool = pool; pyramid->width = img->width; pyramid->height = img->height; pyramid->source = img;
         pyramid->pyr = pool->acquire(img->width, img->height, parameters.pyrLKWindowSize, parameters.pyrLKMaxLevel);
         // H2D copy + one fused kernel, asynchronous on the context stream (cv::buildOpticalFlowPyramid in the reference)
-        HV(hv_pyr_build(pyramid->pyr, cpu.getData<std::uint8_t>(), static_cast<size_t>(cpu.bytesPerRow())));
+        // (raw pointer: the reference's gray type is FixedPoint<uint8_t>, ImagePyramid::GrayType; getData<uint8_t>() would reject it)
+        HV(hv_pyr_build(pyramid->pyr, cpu.getDataRaw(), static_cast<size_t>(cpu.bytesPerRow())));
         return pyramid;
     }
 };

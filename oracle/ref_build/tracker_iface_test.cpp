@@ -1,0 +1,107 @@
+// TEST INFRASTRUCTURE: interface-level check of hybvio_b200/host/cuda_tracker_backends.cpp.
+// Drives the reference's OWN abstract interfaces -- tracker::ImagePyramid::Factory::compute and tracker::OpticalFlow::compute
+// (src/tracker/image_pyramid.hpp, optical_flow.hpp), exactly as tracker::Image::opticalFlow does (src/tracker/image.cpp:87-106)
+// -- once with the reference's CPU back ends (src/tracker/image_pyramid.cpp, optical_flow.cpp, compiled unmodified over the
+// vendored OpenCV) and once with the CUDA back ends, on the same accelerated::Image frames, and compares the outputs:
+// Feature::Status identical, end points <= 1e-3 px for >= 99 % and < 3e-2 px for all.
+//   tracker_iface_test ref    reference back ends only (no GPU needed; checks the harness)
+//   tracker_iface_test both   reference vs CUDA (needs a B200)
+#include "image_pyramid.hpp"
+#include "optical_flow.hpp"
+#include "parameters.hpp"
+#include <accelerated-arrays/cpu/image.hpp>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+
+namespace tracker {
+std::unique_ptr<ImagePyramid::Factory> buildCudaImagePyramidFactory(const odometry::ParametersTracker&);
+std::unique_ptr<OpticalFlow> buildCudaOpticalFlow(const odometry::ParametersTracker&);
+}
+
+namespace {
+constexpr int W = 752, H = 480;
+unsigned hash2(int x, int y, unsigned seed) { unsigned h = (unsigned)x * 374761393u + (unsigned)y * 668265263u + seed * 2246822519u; h = (h ^ (h >> 13)) * 1274126177u; return h ^ (h >> 16); }
+double valueNoise(double u, double v, int cell, unsigned seed)
+{
+    const double gx = u / cell, gy = v / cell;
+    const int x0 = (int)std::floor(gx), y0 = (int)std::floor(gy);
+    const double fx = gx - x0, fy = gy - y0;
+    auto g = [&](int x, int y) { return (hash2(x, y, seed) & 0xffff) / 65535.0 - 0.5; };
+    return (g(x0, y0) * (1 - fx) + g(x0 + 1, y0) * fx) * (1 - fy) + (g(x0, y0 + 1) * (1 - fx) + g(x0 + 1, y0 + 1) * fx) * fy;
+}
+std::shared_ptr<accelerated::Image> makeFrame(accelerated::Image::Factory& f, double dx, double dy)
+{
+    auto img = f.create<tracker::ImagePyramid::GrayType, 1>(W, H);
+    auto& cpu = accelerated::cpu::Image::castFrom(*img);
+    std::uint8_t* d = cpu.getDataRaw();
+    const std::size_t pitch = cpu.bytesPerRow();
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const double u = x + dx, v = y + dy;
+            double t = 128 + 140 * valueNoise(u, v, 6, 1) + 100 * valueNoise(u, v, 17, 2) + 70 * valueNoise(u, v, 48, 3);
+            if (u > 500 && u < 580 && v > 300 && v < 360) t = 90;          // flat patch: minimum-eigenvalue rejections
+            d[y * pitch + x] = (std::uint8_t)std::fmin(255.0, std::fmax(0.0, std::floor(t + 0.5)));
+        }
+    return std::shared_ptr<accelerated::Image>(std::move(img));
+}
+struct Result { std::vector<tracker::Feature::Point> pts; std::vector<tracker::Feature::Status> st; };
+Result run(tracker::ImagePyramid::Factory& fac, tracker::OpticalFlow& flow, std::shared_ptr<accelerated::Image> a, std::shared_ptr<accelerated::Image> b,
+           const std::vector<tracker::Feature::Point>& prev, const std::vector<tracker::Feature::Point>* init)
+{
+    auto pa = fac.compute(a), pb = fac.compute(b);
+    Result r;
+    if (init) r.pts = *init;
+    flow.compute(*pa, *pb, prev, r.pts, r.st, init != nullptr);
+    return r;
+}
+}
+
+int main(int argc, char** argv)
+{
+    const bool both = argc > 1 && !std::strcmp(argv[1], "both");
+    odometry::Parameters params;
+    const odometry::ParametersTracker& pt = params.tracker;
+    auto factory = accelerated::cpu::Image::createFactory();
+    const double dx = 2.6, dy = -1.3;
+    auto f0 = makeFrame(*factory, 0, 0), f1 = makeFrame(*factory, dx, dy);    // content moves by (-dx, -dy)
+    std::mt19937 rng(7);
+    std::uniform_real_distribution<float> ux(-5.f, W + 5.f), uy(-5.f, H + 5.f), un(-3.f, 3.f);
+    std::vector<tracker::Feature::Point> prev(400), init(400);
+    for (size_t i = 0; i < prev.size(); i++) {
+        prev[i].x = ux(rng); prev[i].y = uy(rng);
+        if (i % 10 == 0) { prev[i].x = 510.f + (i % 60); prev[i].y = 310.f + (i % 40); }     // on the flat patch
+        init[i].x = prev[i].x - (float)dx + un(rng); init[i].y = prev[i].y - (float)dy + un(rng);
+    }
+    auto refFac = tracker::ImagePyramid::Factory::buildOpenCv(pt);
+    auto refFlow = tracker::OpticalFlow::buildOpenCv(pt);
+    int fails = 0;
+    for (int useInit = 0; useInit < 2; useInit++) {
+        const Result r = run(*refFac, *refFlow, f0, f1, prev, useInit ? &init : nullptr);
+        int tracked = 0, failed = 0, oor = 0; double err = 0;
+        for (size_t i = 0; i < prev.size(); i++) {
+            if (r.st[i] == tracker::Feature::Status::TRACKED) { tracked++; err = std::fmax(err, std::hypot(r.pts[i].x - (prev[i].x - dx), r.pts[i].y - (prev[i].y - dy))); }
+            else if (r.st[i] == tracker::Feature::Status::FAILED_FLOW) failed++; else oor++;
+        }
+        std::printf("reference back ends, useInitialCorners=%d: %d TRACKED (max |end - truth| %.3f px), %d FAILED_FLOW, %d FLOW_OUT_OF_RANGE\n", useInit, tracked, err, failed, oor);
+        if (tracked < 150 || failed < 20) { std::printf("FAIL: implausible reference result (harness broken?)\n"); fails++; }
+        if (!both) continue;
+        auto cuFac = tracker::buildCudaImagePyramidFactory(pt);
+        auto cuFlow = tracker::buildCudaOpticalFlow(pt);
+        const Result c = run(*cuFac, *cuFlow, f0, f1, prev, useInit ? &init : nullptr);
+        int stDiff = 0, within = 0, cmp = 0; double worst = 0;
+        for (size_t i = 0; i < prev.size(); i++) {
+            if (c.st[i] != r.st[i]) { stDiff++; continue; }
+            if (r.st[i] != tracker::Feature::Status::TRACKED) continue;
+            const double d = std::hypot((double)c.pts[i].x - r.pts[i].x, (double)c.pts[i].y - r.pts[i].y);
+            worst = std::fmax(worst, d); cmp++; if (d <= 1e-3) within++;
+        }
+        const bool ok = stDiff == 0 && worst < 3e-2 && within >= 0.99 * cmp;
+        std::printf("CUDA back ends vs reference, useInitialCorners=%d: %d status differences, %d / %d end points within 1e-3 px, worst %.2e px: %s\n",
+                    useInit, stDiff, within, cmp, worst, ok ? "ok" : "FAIL");
+        fails += !ok;
+    }
+    std::printf(fails ? "tracker interface test FAILED\n" : "tracker interface test passed\n");
+    return fails;
+}
