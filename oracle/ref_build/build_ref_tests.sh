@@ -34,3 +34,21 @@ g++ -o "$OUT/run_ref_ekf_tests" $O/test_ekf.o $O/test_main.o $O/helpers.o $O/cud
     $OUT/obj_ekf/parameters.o $OUT/obj_ekf/odo_util.o $OUT/obj_ekf/timer.o $OUT/obj_ekf/util_util.o $OUT/obj_ekf/parameter_parser.o \
     -Wl,--gc-sections -L"$ROOT/hybvio_b200" -lhybvio_b200 -Wl,-rpath,'$ORIGIN/../../hybvio_b200' -lpthread
 echo built $OUT/run_ref_ekf_tests
+
+# Second suite: the reference's triangulation tests (test/triangulation.cpp: "visual", "stereo_visual", pinv, two-camera
+# triangulation and the derivative checks), which use odometry::EKF as the state store behind extractCameraPoseTrail /
+# prepareVisualUpdate (src/odometry/triangulation.cpp, unmodified) -- again linked against CudaEKF instead of ekf.cpp.
+mkdir -p "$OUT/inc/fake/tracker" "$OUT/inc/fake/odometry"
+ln -sfn "$OUT/gen/output/parameters.hpp" "$OUT/inc/fake/odometry/parameters.hpp"     # "../odometry/parameters.hpp" seen from src/tracker
+INC2="$INC -I$OUT/inc/fake/tracker -I$OCV/photo/include -I$OCV/dnn/include -I$OCV/ml/include -I$OCV/objdetect/include -I$OCV/stitching/include"
+[ -f "$OUT/obj_lk/video_lkpyramid.o" ] || make -C "$HERE" -f Makefile.lk -j8
+g++ $FL $INC2 -c "$REF/test/triangulation.cpp" -o $O/test_triangulation.o &
+g++ $FL $INC2 -c "$REF/src/odometry/triangulation.cpp" -o $O/ref_triangulation.o &
+g++ $FL $INC2 -c "$REF/src/tracker/camera.cpp" -o $O/ref_camera.o &
+g++ $FL $INC2 -c "$REF/src/tracker/util.cpp" -o $O/ref_tracker_util.o &
+wait
+OCVOBJ=$(ls $OUT/obj_lk/*.o $OUT/obj_lk/core_utils/*.o | grep -v shim.o)
+g++ -o "$OUT/run_ref_triangulation_tests" $O/test_triangulation.o $O/test_main.o $O/helpers.o $O/ref_triangulation.o $O/ref_camera.o $O/ref_tracker_util.o \
+    $O/cuda_ekf.o $OUT/obj_ekf/parameters.o $OUT/obj_ekf/odo_util.o $OUT/obj_ekf/timer.o $OUT/obj_ekf/util_util.o $OUT/obj_ekf/parameter_parser.o $OCVOBJ \
+    -Wl,--gc-sections -L"$ROOT/hybvio_b200" -lhybvio_b200 -Wl,-rpath,'$ORIGIN/../../hybvio_b200' -lpthread -ldl -lz
+echo built $OUT/run_ref_triangulation_tests

@@ -265,3 +265,18 @@ def test_deferred_work_is_flushed_by_every_reader(cuda):
     assert np.array_equal(ma, mb) and np.array_equal(Pa, Pb)
     for e in (a, b, ca, cb):
         e.close()
+
+
+def test_reference_triangulation_suite_against_cuda_ekf():
+    """The reference's OWN triangulation unit tests (test/triangulation.cpp: "visual", "stereo_visual", pinv, two-camera
+    triangulation, derivative checks -- 7 test cases) compiled unmodified together with src/odometry/triangulation.cpp and
+    src/tracker/camera.cpp, with odometry::EKF provided by hybvio_b200/host/cuda_ekf.cpp: extractCameraPoseTrail and
+    prepareVisualUpdate read the pose trail out of the CUDA filter (oracle/ref_build/build_ref_tests.sh)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "run_ref_triangulation_tests")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/run_ref_triangulation_tests not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], cwd=os.path.join(root, "oracle", "_ref"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "All tests passed" in r.stdout and "7 test cases" in r.stdout, r.stdout[-500:]
