@@ -54,3 +54,25 @@ def make_track(seed, trail=20, npose=6, stereo=True, noise=1e-3, depth=5.0, base
     ip = np.array(ip)
     vel = rng.normal(0, 0.05, ip.shape)
     return dict(m=m, trail=trail, stereo=stereo, idx=idx, T1=T1, T2=T2, ip=ip, vel=vel, pf_true=pf)
+
+
+def corrupt(t, kind, seed):
+    """Spoils a track so that the reference's failure branches are taken: a gross outlier, mirrored observations (point behind
+    the cameras), a static camera (no parallax -> BAD_COND), random observations."""
+    rng = np.random.RandomState(10000 + seed)
+    if kind == "outlier":
+        t["ip"][rng.randint(len(t["ip"]))] += rng.normal(0, 0.5, 2)
+    elif kind == "flip":
+        t["ip"] = -t["ip"] + rng.normal(0, 0.05, t["ip"].shape)
+    elif kind == "static":
+        m = t["m"]
+        for k in range(1, t["trail"] + 1):
+            o = 20 + 7 * (k - 1)
+            m[o:o + 3] = m[0:3] + rng.normal(0, 1e-7, 3)
+            m[o + 3:o + 7] = m[6:10]
+        t["ip"][:] = t["ip"][0] + rng.normal(0, 1e-6, t["ip"].shape)
+    elif kind == "garbage":
+        t["ip"] = rng.normal(0, 0.5, t["ip"].shape)
+    else:
+        assert kind == "none"
+    return t
