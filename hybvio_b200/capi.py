@@ -35,6 +35,23 @@ class EkfParams(ctypes.Structure):
     ]
 
 
+class CameraModel(ctypes.Structure):
+    """hv_camera_model (include/hybvio_b200.h)"""
+    _fields_ = [("imu_to_camera", c_double * 16), ("second_imu_to_camera", c_double * 16), ("use_stereo", c_int),
+                ("estimate_imu_camera_time_shift", c_int), ("gauss_newton_iterations", ctypes.c_uint),
+                ("convergence_threshold", c_double), ("convergence_r", c_double), ("rcond_threshold", c_double),
+                ("min_dist", c_double), ("max_dist", c_double)]
+
+
+class TrackObs(ctypes.Structure):
+    _fields_ = [("npose", c_int), ("pose_trail_index", c_void_p), ("ip", c_void_p), ("velocities", c_void_p)]
+
+
+class TrackModel(ctypes.Structure):
+    _fields_ = [("triangulator_status", c_int), ("prepare_vu_status", c_int), ("rows", c_int), ("cols", c_int),
+                ("pf", c_double * 3), ("depth", c_double), ("d_H", c_void_p), ("d_f", c_void_p), ("d_y", c_void_p)]
+
+
 class EkfOp(ctypes.Structure):
     _fields_ = [("kind", c_int), ("n", c_int), ("l", c_int), ("mode", c_int), ("index", c_int),
                 ("t", c_double), ("r", c_double), ("rmse_thr", c_double), ("gyro", c_double * 3), ("acc", c_double * 3),
@@ -122,6 +139,11 @@ def _bind_ekf(lib):
     lib.hv_ekf_visual_update.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double]
     lib.hv_ekf_visual_check_update.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double,
                                                ctypes.POINTER(c_int), dp, c_void_p]
+    lib.hv_camera_model_defaults.argtypes = [ctypes.POINTER(CameraModel)]
+    lib.hv_camera_model_defaults.restype = None
+    lib.hv_ekf_set_camera_model.argtypes = [c_void_p, ctypes.POINTER(CameraModel)]
+    lib.hv_ekf_track_models.argtypes = [c_void_p, ctypes.POINTER(TrackObs), c_int, ctypes.POINTER(TrackModel)]
+    lib.hv_ekf_track_model_download.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     lib.hv_ekf_visual_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p]
     lib.hv_ekf_augment.argtypes = [c_void_p, c_int]
     lib.hv_ekf_set_imu_batching.argtypes = [c_void_p, c_int]
@@ -367,6 +389,46 @@ class Ekf:
     def augment(self, drop=-1): check(self.lib.hv_ekf_augment(self.h, drop), "hv_ekf_augment")
     def unaugment(self): check(self.lib.hv_ekf_unaugment(self.h), "hv_ekf_unaugment")
     def symmetrize(self): check(self.lib.hv_ekf_symmetrize(self.h), "hv_ekf_symmetrize")
+    def set_camera_model(self, imu_to_camera, second_imu_to_camera=None, use_stereo=False, estimate_time_shift=True, **kw):
+        """hv_ekf_set_camera_model: 4x4 matrices as numpy (row, col); kw: other hv_camera_model fields."""
+        c = CameraModel()
+        self.lib.hv_camera_model_defaults(ctypes.byref(c))
+        c.imu_to_camera[:] = list(np.asarray(imu_to_camera, np.float64).flatten(order="F"))
+        if second_imu_to_camera is not None:
+            c.second_imu_to_camera[:] = list(np.asarray(second_imu_to_camera, np.float64).flatten(order="F"))
+        c.use_stereo = 1 if use_stereo else 0
+        c.estimate_imu_camera_time_shift = 1 if estimate_time_shift else 0
+        for k, v in kw.items():
+            setattr(c, k, v)
+        check(self.lib.hv_ekf_set_camera_model(self.h, ctypes.byref(c)), "hv_ekf_set_camera_model")
+        self._stereo = bool(use_stereo)
+
+    def track_models(self, tracks, download=True):
+        """hv_ekf_track_models. tracks: list of (pose_trail_index, ip, velocities). Returns one dict per track: tri_status,
+        vu_status, pf, depth, rows, cols, device pointers d_H / d_f / d_y and (download=True) H, f, dpf on the host."""
+        n = len(tracks)
+        obs = (TrackObs * n)()
+        keep = []
+        for k, (idx, ip, vel) in enumerate(tracks):
+            idx = np.ascontiguousarray(idx, np.int32); ip = _dd(np.asarray(ip).ravel()); vel = _dd(np.asarray(vel).ravel())
+            keep.append((idx, ip, vel))
+            obs[k].npose = len(idx); obs[k].pose_trail_index = idx.ctypes.data; obs[k].ip = ip.ctypes.data; obs[k].velocities = vel.ctypes.data
+        out = (TrackModel * n)()
+        check(self.lib.hv_ekf_track_models(self.h, obs, n, out), "hv_ekf_track_models")
+        res = []
+        for k in range(n):
+            o = out[k]
+            d = {"tri_status": o.triangulator_status, "vu_status": o.prepare_vu_status, "rows": o.rows, "cols": o.cols,
+                 "pf": np.array(o.pf[:]), "depth": o.depth, "d_H": o.d_H, "d_f": o.d_f, "d_y": o.d_y}
+            if download:
+                npose = len(keep[k][0])
+                H = np.zeros((o.rows, o.cols), order="F"); f = np.zeros(o.rows); dpf = np.zeros((3, 7 * npose + 1), order="F")
+                check(self.lib.hv_ekf_track_model_download(self.h, k, _ptr(H) if H.size else None, _ptr(f) if f.size else None, _ptr(dpf)),
+                      "hv_ekf_track_model_download")
+                d.update(H=H, f=f, dpf=dpf)
+            res.append(d)
+        return res
+
     def flush(self): check(self.lib.hv_ekf_flush(self.h), "hv_ekf_flush")
     def set_imu_batching(self, max_samples): check(self.lib.hv_ekf_set_imu_batching(self.h, int(max_samples)), "hv_ekf_set_imu_batching")
     def normalize_quaternions(self, only_current=False): check(self.lib.hv_ekf_normalize_quaternions(self.h, 1 if only_current else 0), "hv_ekf_normalize_quaternions")

@@ -3,6 +3,7 @@
 // src/odometry/ekf.cpp:145-151) lives here; m, P and all arithmetic on them live on the device (ekf.cu).
 #include "capi_internal.h"
 #include "ekf.cuh"
+#include "track_model.h"
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -38,6 +39,27 @@ struct hv_ekf {
     EkfPredictArgs pend;
     bool pendSym = false;
     int imuBatch = EKF_MAX_PREDICT;
+    struct TrackModels* tm = nullptr;    // per-track measurement model on the device (hv_ekf_track_models), created on first use
+};
+
+// Buffers of hv_ekf_track_models: inputs packed by the host into one pinned block, outputs in HBM (H, f, d pf) + a small
+// status block that travels back.
+struct TrackModels {
+    hv_camera_model cam;
+    bool camSet = false;
+    int cap = 0, last = 0;
+    std::vector<int> lastNpose;
+    char* d_in = nullptr;  char* h_in = nullptr;      // [npose int cap | idx int cap x MAXPOSE | ip | vel]
+    char* d_out = nullptr; char* h_out = nullptr;     // [status int 4 cap | pf double 4 cap]
+    double *d_dpf = nullptr, *d_H = nullptr, *d_f = nullptr;
+    static size_t inBytes(int c) { return (size_t)c * (sizeof(int) * (1 + TM_MAXPOSE + 1) + sizeof(double) * 4 * TM_MAXOBS); }   // +1 int: keeps the doubles 8-byte aligned
+    static size_t outBytes(int c) { return (size_t)c * (sizeof(int) * 4 + sizeof(double) * 4); }
+    static size_t hStride() { return (size_t)2 * TM_MAXOBS * TM_MAXN; }
+    void release()
+    {
+        cudaFree(d_in); cudaFree(d_out); cudaFree(d_dpf); cudaFree(d_H); cudaFree(d_f); cudaFreeHost(h_in); cudaFreeHost(h_out);
+        d_in = d_out = h_in = h_out = nullptr; d_dpf = d_H = d_f = nullptr; cap = 0;
+    }
 };
 
 // ---- chi-square 95% quantiles (the reference hard-codes the table odometry/util.hpp:23; recomputed here by
@@ -215,6 +237,7 @@ int hv_ekf_destroy(hv_ekf* e)
     cudaFreeHost(e->h_pin);
     cudaFreeHost(e->h_sig);
     if (e->evStaged) cudaEventDestroy(e->evStaged);
+    if (e->tm) { e->tm->release(); delete e->tm; }
     delete e;
     return HV_OK;
 }
@@ -238,6 +261,7 @@ int hv_ekf_clone(const hv_ekf* src, hv_ekf** out)
     e->time = src->time; e->ZUPTtime = src->ZUPTtime; e->ZRUPTtime = src->ZRUPTtime; e->initZUPTtime = src->initZUPTtime;
     e->wasStationary = src->wasStationary; e->prevSampleT = src->prevSampleT; e->firstSampleT = src->firstSampleT;
     e->firstSample = src->firstSample; e->chi2inv95 = src->chi2inv95; e->imuBatch = src->imuBatch;
+    if (src->tm && src->tm->camSet) { e->tm = new TrackModels(); e->tm->cam = src->tm->cam; e->tm->camSet = true; }
     *out = e;
     return HV_OK;
 }
@@ -816,6 +840,134 @@ int hv_ekf_debug_result_words(hv_ekf* e, double* out32)
     EKF_ENTER(e, "hv_ekf_debug_result_words");
     HV_CUDA(cudaMemcpyAsync(out32, e->b.res, 32 * sizeof(double), cudaMemcpyDeviceToHost, e->ctx->stream));
     HV_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    return HV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- per-track measurement model
+void hv_camera_model_defaults(hv_camera_model* c)
+{
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->estimate_imu_camera_time_shift = 1;
+    c->gauss_newton_iterations = 10; c->convergence_threshold = 1e-2; c->convergence_r = 11.0; c->rcond_threshold = 1e-8;
+    c->min_dist = 0.0; c->max_dist = 1e300;
+}
+
+int hv_ekf_set_camera_model(hv_ekf* e, const hv_camera_model* c)
+{
+    EKF_ENTER_LAZY(e, "hv_ekf_set_camera_model");
+    if (!c || c->gauss_newton_iterations < 1) { hv_set_error("hv_ekf_set_camera_model: invalid argument"); return HV_ERR_INVALID; }
+    bool zero = true;
+    for (int i = 0; i < 16; i++) zero = zero && c->imu_to_camera[i] == 0.0;
+    if (zero) { hv_set_error("hv_ekf_set_camera_model: imu_to_camera is the zero sentinel (triangulation.cpp:78-79)"); return HV_ERR_INVALID; }
+    if (!e->tm) e->tm = new TrackModels();
+    e->tm->cam = *c; e->tm->camSet = true;
+    return HV_OK;
+}
+
+static int tm_reserve(TrackModels* t, int n)
+{
+    if (n <= t->cap) return HV_OK;
+    int cap = t->cap ? t->cap : 64;
+    while (cap < n) cap *= 2;
+    t->release();
+    HV_CUDA(cudaMalloc(&t->d_in, TrackModels::inBytes(cap)));
+    HV_CUDA(cudaMalloc(&t->d_out, TrackModels::outBytes(cap)));
+    HV_CUDA(cudaMalloc(&t->d_dpf, sizeof(double) * cap * 3 * (7 * TM_MAXPOSE + 1)));
+    HV_CUDA(cudaMalloc(&t->d_H, sizeof(double) * cap * TrackModels::hStride()));
+    HV_CUDA(cudaMalloc(&t->d_f, sizeof(double) * cap * 2 * TM_MAXOBS));
+    HV_CUDA(cudaHostAlloc(&t->h_in, TrackModels::inBytes(cap), cudaHostAllocDefault));
+    HV_CUDA(cudaHostAlloc(&t->h_out, TrackModels::outBytes(cap), cudaHostAllocDefault));
+    t->cap = cap;
+    return HV_OK;
+}
+
+int hv_ekf_track_models(hv_ekf* e, const hv_track_obs* tracks, int ntracks, hv_track_model* out)
+{
+    EKF_ENTER(e, "hv_ekf_track_models");
+    TrackModels* t = e->tm;
+    if (!t || !t->camSet) { hv_set_error("hv_ekf_track_models: hv_ekf_set_camera_model has not been called"); return HV_ERR_STATE; }
+    if (!tracks || !out || ntracks < 1) { hv_set_error("hv_ekf_track_models: invalid argument"); return HV_ERR_INVALID; }
+    const int maxIndex = e->trail < TM_MAXPOSE - 1 ? e->trail : TM_MAXPOSE - 1;
+    const int ncam = t->cam.use_stereo ? 2 : 1;
+    for (int k = 0; k < ntracks; k++) {
+        const hv_track_obs& o = tracks[k];
+        if (o.npose < 2 || o.npose > TM_MAXPOSE || !o.pose_trail_index || !o.ip || !o.velocities) {
+            hv_set_error("hv_ekf_track_models: track %d: npose %d outside 2..%d or NULL arrays", k, o.npose, TM_MAXPOSE); return HV_ERR_INVALID;
+        }
+        for (int i = 0; i < o.npose; i++)
+            if (o.pose_trail_index[i] < 0 || o.pose_trail_index[i] > maxIndex) {
+                hv_set_error("hv_ekf_track_models: track %d: pose index %d outside 0..%d", k, o.pose_trail_index[i], maxIndex); return HV_ERR_INVALID;
+            }
+    }
+    int rc = tm_reserve(t, ntracks);
+    if (rc != HV_OK) return rc;
+    cudaStream_t s = e->ctx->stream;
+    // pack: the block layout is fixed by the capacity, so that one H2D copy moves everything
+    const int cap = t->cap;
+    int* h_np = (int*)t->h_in;
+    int* h_idx = h_np + cap;
+    double* h_ip = (double*)(t->h_in + sizeof(int) * (size_t)cap * (TM_MAXPOSE + 2));
+    double* h_vel = h_ip + (size_t)cap * 2 * TM_MAXOBS;
+    for (int k = 0; k < ntracks; k++) {
+        const hv_track_obs& o = tracks[k];
+        h_np[k] = o.npose;
+        memcpy(h_idx + (size_t)k * TM_MAXPOSE, o.pose_trail_index, sizeof(int) * o.npose);
+        memcpy(h_ip + (size_t)k * 2 * TM_MAXOBS, o.ip, sizeof(double) * 2 * o.npose * ncam);
+        memcpy(h_vel + (size_t)k * 2 * TM_MAXOBS, o.velocities, sizeof(double) * 2 * o.npose * ncam);
+    }
+    // three ranges are live: [npose | idx] up to track ntracks, ip, vel -- copy only what is used
+    HV_CUDA(cudaMemcpyAsync(t->d_in, t->h_in, sizeof(int) * ((size_t)cap + (size_t)ntracks * TM_MAXPOSE), cudaMemcpyHostToDevice, s));
+    const size_t ipOff = sizeof(int) * (size_t)cap * (TM_MAXPOSE + 2), velOff = ipOff + sizeof(double) * (size_t)cap * 2 * TM_MAXOBS;
+    HV_CUDA(cudaMemcpyAsync(t->d_in + ipOff, t->h_in + ipOff, sizeof(double) * (size_t)ntracks * 2 * TM_MAXOBS, cudaMemcpyHostToDevice, s));
+    HV_CUDA(cudaMemcpyAsync(t->d_in + velOff, t->h_in + velOff, sizeof(double) * (size_t)ntracks * 2 * TM_MAXOBS, cudaMemcpyHostToDevice, s));
+    TmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = e->b.m; a.N = e->N; a.stereo = t->cam.use_stereo ? 1 : 0; a.timeShift = t->cam.estimate_imu_camera_time_shift ? 1 : 0; a.ntracks = ntracks;
+    for (int c = 0; c < 2; c++) {
+        const double* T = c ? t->cam.second_imu_to_camera : t->cam.imu_to_camera;
+        for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) a.Rc[c][3 * r + k] = T[4 * k + r]; a.base[c][r] = T[12 + r]; }
+    }
+    a.gnIterations = t->cam.gauss_newton_iterations; a.convThreshold = t->cam.convergence_threshold; a.convR = t->cam.convergence_r;
+    a.rcondThreshold = t->cam.rcond_threshold; a.minDist = t->cam.min_dist; a.maxDist = t->cam.max_dist;
+    a.npose = (const int*)t->d_in; a.idx = a.npose + cap;
+    a.ip = (const double*)(t->d_in + ipOff); a.vel = (const double*)(t->d_in + velOff);
+    a.status = (int*)t->d_out; a.pf = (double*)(t->d_out + sizeof(int) * 4 * (size_t)cap);
+    a.dpf = t->d_dpf; a.H = t->d_H; a.f = t->d_f; a.Hstride = TrackModels::hStride();
+    HV_CUDA(tm_launch(a, s));
+    e->ctx->launches++;
+    HV_CUDA(cudaMemcpyAsync(t->h_out, t->d_out, sizeof(int) * 4 * (size_t)ntracks, cudaMemcpyDeviceToHost, s));
+    const size_t pfOff = sizeof(int) * 4 * (size_t)cap;
+    HV_CUDA(cudaMemcpyAsync(t->h_out + pfOff, t->d_out + pfOff, sizeof(double) * 4 * (size_t)ntracks, cudaMemcpyDeviceToHost, s));
+    HV_CUDA(cudaStreamSynchronize(s));
+    const int* st = (const int*)t->h_out;
+    const double* pf = (const double*)(t->h_out + pfOff);
+    t->last = ntracks; t->lastNpose.resize(ntracks);
+    for (int k = 0; k < ntracks; k++) {
+        hv_track_model& o = out[k];
+        o.triangulator_status = st[4 * k]; o.prepare_vu_status = st[4 * k + 1]; o.rows = st[4 * k + 2]; o.cols = st[4 * k + 3];
+        for (int r = 0; r < 3; r++) o.pf[r] = pf[4 * k + r];
+        o.depth = pf[4 * k + 3];
+        o.d_H = t->d_H + (size_t)k * TrackModels::hStride();
+        o.d_f = t->d_f + (size_t)k * 2 * TM_MAXOBS;
+        o.d_y = a.ip + (size_t)k * 2 * TM_MAXOBS;
+        t->lastNpose[k] = tracks[k].npose;
+    }
+    return HV_OK;
+}
+
+int hv_ekf_track_model_download(hv_ekf* e, int track, double* H, double* f, double* dpf)
+{
+    EKF_ENTER_LAZY(e, "hv_ekf_track_model_download");
+    TrackModels* t = e->tm;
+    if (!t || track < 0 || track >= t->last) { hv_set_error("hv_ekf_track_model_download: no such track"); return HV_ERR_INVALID; }
+    cudaStream_t s = e->ctx->stream;
+    const int* st = (const int*)t->h_out + 4 * track;
+    const size_t rows = st[2], cols = st[3];
+    if (H && rows * cols) HV_CUDA(cudaMemcpyAsync(H, t->d_H + (size_t)track * TrackModels::hStride(), sizeof(double) * rows * cols, cudaMemcpyDeviceToHost, s));
+    if (f && rows) HV_CUDA(cudaMemcpyAsync(f, t->d_f + (size_t)track * 2 * TM_MAXOBS, sizeof(double) * rows, cudaMemcpyDeviceToHost, s));
+    if (dpf) HV_CUDA(cudaMemcpyAsync(dpf, t->d_dpf + (size_t)track * 3 * (7 * TM_MAXPOSE + 1), sizeof(double) * 3 * (7 * t->lastNpose[track] + 1), cudaMemcpyDeviceToHost, s));
+    HV_CUDA(cudaStreamSynchronize(s));
     return HV_OK;
 }
 

@@ -220,6 +220,49 @@ int hv_ekf_transform_to(hv_ekf* ekf, const double pos[3], const double q[4], int
 int hv_ekf_insert_map_point(hv_ekf* ekf, int idx, const double pf[3]);   /* ekf.cpp:911-921 */
 int hv_ekf_condition_on_last_pose(hv_ekf* ekf);                /* ekf.cpp:928-942 */
 int hv_ekf_lock_biases(hv_ekf* ekf);                           /* ekf.cpp:944-947 */
+/* ---- Per-track measurement model on the device (next hot-path row) --------------------------------
+ * What Session::trackerVisualUpdate computes on the host for every track before it can call the EKF
+ * (src/odometry/backend.cpp:1050-1160): extractCameraPoseTrail (src/odometry/triangulation.cpp:65-103) ->
+ * Triangulator::triangulate with derivatives (:120-407, two-view start :610-710) -> per-pose sum of the two cameras
+ * (backend.cpp:1105-1116) -> prepareVisualUpdate(truncated) (:897-987). Here it runs on the device from the resident state
+ * mean; H, f (and the measurement vector y = the observations) stay in HBM, where hv_ekf_visual_device / hv_ekf_run_device
+ * read them, so H is neither built on nor uploaded from the host. */
+typedef struct hv_camera_model {
+    double imu_to_camera[16];            /* odometry::Parameters::imuToCamera, 4x4 column-major (Eigen) */
+    double second_imu_to_camera[16];     /* ...::secondImuToCamera (ignored unless use_stereo) */
+    int use_stereo;                      /* tracker.useStereo */
+    int estimate_imu_camera_time_shift;  /* odometry.estimateImuCameraTimeShift */
+    unsigned gauss_newton_iterations;    /* odometry.triangulationGaussNewtonIterations (10) */
+    double convergence_threshold;        /* odometry.triangulationConvergenceThreshold (1e-2) */
+    double convergence_r;                /* odometry.triangulationConvergenceR (11) */
+    double rcond_threshold;              /* odometry.triangulationRcondThreshold (1e-8) */
+    double min_dist, max_dist;           /* odometry.triangulationMinDist / MaxDist (0, 1e300): BAD_DEPTH gate, backend.cpp:1095-1098 */
+} hv_camera_model;
+void hv_camera_model_defaults(hv_camera_model* c);     /* the reference defaults above; the two matrices are zeroed */
+int hv_ekf_set_camera_model(hv_ekf* ekf, const hv_camera_model* c);
+#define HV_TRACK_MAX_POSES 21            /* pose-trail indices per track (cameraTrailLength 20 + the current pose) */
+typedef struct hv_track_obs {
+    int npose;                           /* 2 .. HV_TRACK_MAX_POSES */
+    const int* pose_trail_index;         /* npose indices as EkfStateIndex::createTrackIndex gives them: 0 = current pose, k = trail slot k - 1 */
+    const double* ip;                    /* normalised image points x,y: npose of the first camera [, npose of the second] */
+    const double* velocities;            /* their velocities, same layout (TriangulationArgsIn::featureVelocities) */
+} hv_track_obs;
+typedef struct hv_track_model {
+    int triangulator_status;             /* odometry::TriangulatorStatus (output.hpp:21-29): OK 0, BEHIND 2, BAD_COND 3, NO_CONVERGENCE 4, BAD_DEPTH 5, UNKNOWN_PROBLEM 6 */
+    int prepare_vu_status;               /* odometry::PrepareVuStatus (output.hpp:15-19), -1 if triangulation failed */
+    int rows, cols;                      /* of H: 2 n_obs x l (truncated at the last pose the track touches) */
+    double pf[3], depth;                 /* triangulated point, |pf - first camera| */
+    const double* d_H;                   /* DEVICE: rows x cols, column-major, ld = rows */
+    const double* d_f;                   /* DEVICE: predicted observations, rows */
+    const double* d_y;                   /* DEVICE: the observations, rows (the y of visualTrackOutlierCheck / updateVisualTrack) */
+} hv_track_model;
+/* All tracks are evaluated against the CURRENT state mean in one launch (one CTA per track); the device pointers in out[]
+ * stay valid until the next call on this ekf. Synchronises (the caller branches on the statuses). */
+int hv_ekf_track_models(hv_ekf* ekf, const hv_track_obs* tracks, int ntracks, hv_track_model* out);
+/* Test / debug: copies H (rows x cols), f (rows) and d pf / d (poses, t) (3 x (7 npose + 1), column-major, after the stereo
+ * sum) of track `track` of the last hv_ekf_track_models call to the host; any pointer may be NULL. */
+int hv_ekf_track_model_download(hv_ekf* ekf, int track, double* H, double* f, double* dpf);
+
 /* Debug: the 32 result words of the last update kernel ([0] status, [1] chi2, [2] flag, [8..] phase timestamps when
  * the library is built with -DHV_EKF_TIMING). */
 int hv_ekf_debug_result_words(hv_ekf* ekf, double* out32);

@@ -31,3 +31,18 @@ def test_cluster_update_kernel_body_on_host_emulator(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count(" ok") == 13 and "FAIL" not in out.stdout
+
+
+def test_track_model_kernel_body_on_host_emulator(tmp_path):
+    """track_model.cuh (triangulation + prepareVisualUpdate of one track per CTA) vs oracle/hv_oracle_tri.c: mono / stereo,
+    2..10 poses, time shift on / off, clean and spoiled tracks (OK, BEHIND, BAD_COND, NO_CONVERGENCE)."""
+    exe = str(tmp_path / "emu_track_model")
+    obj = str(tmp_path / "orc_tri.o")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", "hv_oracle_tri.c"), "-o", obj])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tools", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tools", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tools", "emu", "emu_track_model.cpp"), obj, "-lm", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("  ok") == 40 and "FAIL" not in out.stdout
+    assert "OK 30 BEHIND 6 BAD_COND 3 NO_CONVERGENCE 1" in out.stdout

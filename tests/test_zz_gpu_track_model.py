@@ -1,0 +1,138 @@
+"""GPU parity of the per-track measurement model on the device (hv_ekf_track_models: triangulation + prepareVisualUpdate,
+SURVEY.md 8(f) N1) against the C oracle (oracle/hv_oracle_tri.c, itself pinned against the compiled reference and its golden
+vectors in test_oracle_tri.py), through the C ABI. Statuses identical; pf, d pf, H, f within 1e-9 relative (fp64, different
+summation order). The file sorts after the other GPU tests on purpose: this row was added after the round's last GPU session
+and has so far only run on the host emulator (tests/test_emu_kernels.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import tri_common  # noqa: E402
+import make_golden_tri  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)) if b.size else 0.0
+
+
+@pytest.fixture(scope="module")
+def env():
+    from hybvio_b200 import capi
+    from oracle import tri_oracle
+    hv = capi.Context(0)
+    yield capi, hv, tri_oracle.OracleTri()
+    hv.close()
+
+
+def make_ekf(capi, hv, t):
+    import ctypes
+    p = capi.EkfParams()
+    capi.load().hv_ekf_default_params(ctypes.byref(p))
+    p.camera_trail_length = t["trail"]
+    e = capi.Ekf(hv, p)
+    e.upload(m=t["m"])
+    return e
+
+
+def compare(dev, orc, where):
+    assert (dev["tri_status"], dev["vu_status"]) == (orc["tri_status"], orc["vu_status"]), where
+    if orc["tri_status"] != 0:
+        assert dev["rows"] == 0 and not dev["dpf"].any(), where
+        return
+    tol = TOL if np.abs(orc["dpf"]).max() < 1e6 else 1e-6
+    assert dev["H"].shape == orc["H"].shape, where
+    for k in ("pf", "dpf", "H", "f"):
+        assert rel(dev[k], orc[k]) < tol, (where, k, rel(dev[k], orc[k]))
+    assert abs(dev["depth"] - orc["depth"]) < tol * max(1.0, orc["depth"]), where
+
+
+@pytest.mark.parametrize("stereo", [True, False])
+@pytest.mark.parametrize("time_shift", [True, False])
+def test_track_models_match_oracle(env, stereo, time_shift):
+    """One launch, many tracks against the same state: clean and spoiled tracks, 2..10 poses each."""
+    capi, hv, orc = env
+    base = tri_common.make_track(0, npose=4, stereo=stereo)
+    e = make_ekf(capi, hv, base)
+    e.set_camera_model(base["T1"], base["T2"], use_stereo=stereo, estimate_time_shift=time_shift)
+    tracks, expect = [], []
+    rng = np.random.RandomState(5)
+    for k in range(96):
+        # every track of a launch shares the state (and rig) of `base`: rebuild the observations of a new point from it
+        t = tri_common.make_track(0, npose=2 + k % 9, stereo=stereo, noise=[1e-3, 3e-3, 1e-2][k % 3], depth=[2, 5, 15, 40][k % 4])
+        assert np.array_equal(t["m"], base["m"])
+        idx = np.concatenate([[0], np.sort(rng.choice(np.arange(1, 21), len(t["idx"]) - 1, replace=False))]).astype(np.int32)
+        ip = tri_common.project(base["m"], idx, base["T1"], base["T2"], stereo, t["pf_true"] + rng.normal(0, 0.3, 3)) + rng.normal(0, 1e-3, (len(idx) * (2 if stereo else 1), 2))
+        t = dict(t, idx=idx, ip=ip, vel=rng.normal(0, 0.05, ip.shape))
+        tri_common.corrupt_observations(t, ["none", "none", "none", "outlier", "flip", "garbage"][k % 6], 100 + k)
+        tracks.append((t["idx"], t["ip"], t["vel"]))
+        expect.append(orc.track_model(base["m"], base["trail"], stereo, t["idx"], base["T1"], base["T2"], t["ip"], t["vel"], time_shift))
+    got = e.track_models(tracks)
+    seen = set()
+    for k, (g, o) in enumerate(zip(got, expect)):
+        compare(g, o, (stereo, time_shift, k))
+        seen.add(o["tri_status"])
+    assert {0, 2}.issubset(seen)
+    e.close()
+
+
+def test_track_models_match_reference_golden_vectors(env):
+    """The committed outputs of the reference's own triangulation.cpp (tests/golden/tri_golden.npz)."""
+    capi, hv, _ = env
+    g = np.load(os.path.join(HERE, "golden", "tri_golden.npz"))
+    seen = set()
+    for i, (seed, kw, cor) in enumerate(make_golden_tri.cases()):
+        t = make_golden_tri.build(seed, kw, cor)
+        e = make_ekf(capi, hv, t)
+        for ets in (1, 0):
+            p = f"c{i}_t{ets}_"
+            ref = {"tri_status": int(g[p + "status"][0]), "vu_status": int(g[p + "status"][1]), "pf": g[p + "pf"], "dpf": g[p + "dpf"],
+                   "depth": float(g[p + "depth"][0]), "H": g[p + "H"], "f": g[p + "f"]}
+            e.set_camera_model(t["T1"], t["T2"], use_stereo=t["stereo"], estimate_time_shift=bool(ets))
+            dev = e.track_models([(t["idx"], t["ip"], t["vel"])])[0]
+            compare(dev, ref, (i, seed, cor, ets))
+            seen.add(ref["tri_status"])
+        e.close()
+    assert seen == {0, 2, 3, 4}
+
+
+def test_device_H_feeds_the_outlier_check_and_update(env):
+    """H, f, y never leave the device: check + update from the pointers hv_ekf_track_models returns equals the same calls with
+    the oracle's H uploaded from the host."""
+    capi, hv, orc = env
+    t = tri_common.make_track(3, npose=6, stereo=True)
+    a, b = make_ekf(capi, hv, t), make_ekf(capi, hv, t)
+    a.set_camera_model(t["T1"], t["T2"], use_stereo=True)
+    d = a.track_models([(t["idx"], t["ip"], t["vel"])])[0]
+    o = orc.track_model(t["m"], t["trail"], True, t["idx"], t["T1"], t["T2"], t["ip"], t["vel"], True)
+    assert d["tri_status"] == 0 and d["vu_status"] == 0
+    import torch
+    res = torch.zeros(2, dtype=torch.float64, device="cuda")
+    a.visual_device(d["d_H"], d["rows"], d["cols"], d["d_f"], d["d_y"], 0.02, 5.0, 2, res)
+    st_b, chi2_b, _ = b.visual_check_update(o["H"], o["f"], t["ip"].ravel(), 0.02, 5.0)
+    ma, Pa = a.download(); mb, Pb = b.download()
+    torch.cuda.synchronize()
+    assert int(res[0].item()) == st_b and abs(res[1].item() - chi2_b) < 1e-9 * max(1.0, abs(chi2_b))
+    assert np.abs(ma - mb).max() < 1e-9 and np.abs(Pa - Pb).max() / np.abs(Pb).max() < 1e-9
+    a.close(); b.close()
+
+
+def test_track_models_reject_bad_input(env):
+    capi, hv, _ = env
+    t = tri_common.make_track(1, npose=4, stereo=False)
+    e = make_ekf(capi, hv, t)
+    with pytest.raises(RuntimeError):
+        e.track_models([(t["idx"], t["ip"], t["vel"])])                # camera model not set
+    e.set_camera_model(t["T1"], None, use_stereo=False)
+    with pytest.raises(RuntimeError):
+        e.track_models([(t["idx"][:1], t["ip"][:1], t["vel"][:1])])    # a single pose
+    with pytest.raises(RuntimeError):
+        e.track_models([(np.array([0, 25], np.int32), t["ip"][:2], t["vel"][:2])])   # index beyond the trail
+    e.close()

@@ -12,6 +12,25 @@ def quat2rmat(q):
                      [2 * q1 * q3 - 2 * q0 * q2, 2 * q2 * q3 + 2 * q0 * q1, q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3]])
 
 
+def project(m, idx, T1, T2, stereo, pf):
+    """Normalised image coordinates of the world point pf in the cameras of the poses idx (camera 0 poses, then camera 1)."""
+    ip = []
+    for T in ([T1, T2] if stereo else [T1]):
+        for i in idx:
+            o = 0 if i == 0 else 20 + 7 * (i - 1)
+            q = m[6:10] if i == 0 else m[o + 3:o + 7]
+            R = T[:3, :3] @ quat2rmat(q)
+            c = R @ (pf - (m[o:o + 3] - R.T @ T[:3, 3]))
+            ip.append(c[:2] / c[2])
+    return np.array(ip)
+
+
+def corrupt_observations(t, kind, seed):
+    """corrupt() restricted to the kinds that leave the state alone (tracks of one launch share it)."""
+    assert kind in ("none", "outlier", "flip", "garbage")
+    return corrupt(t, kind, seed)
+
+
 def make_track(seed, trail=20, npose=6, stereo=True, noise=1e-3, depth=5.0, baseline=0.11):
     rng = np.random.RandomState(seed)
     N = 20 + 7 * trail

@@ -1,0 +1,132 @@
+// tools/emu/emu_track_model.cpp -- runs the REAL body of hv_track_model_kernel (hybvio_b200/csrc/track_model.cuh) on the host
+// emulator and compares it with the C oracle (oracle/hv_oracle_tri.c: orc_track_model) on synthetic tracks.
+//   g++ -std=c++20 -O1 -pthread -Itools/emu/stubs -Itools/emu -Ihybvio_b200/csrc tools/emu/emu_track_model.cpp oracle/hv_oracle_tri.c -o build/emu_track_model
+#include <algorithm>
+#include "cuda_emu.h"
+#include "track_model.cuh"
+
+extern "C" int orc_track_model(const double* m, int trail, int useStereo, const int* poseTrailIndex, int npose, const double* imuToCam,
+                               const double* imuToCam2, const double* ip, const double* vel, int estimateTimeShift, int* triStatus, double* pf,
+                               double* dpf, double* depth, int* vuStatus, int* rows, int* cols, double* H, double* f);
+
+static double urand() { return rand() / (double)RAND_MAX; }
+static double nrand() { double s = 0; for (int i = 0; i < 12; i++) s += urand(); return s - 6.0; }
+static void quat2rmat(const double* q, double* R) { tm_quat_mat(q, -1, R); }
+
+struct Scene { std::vector<double> m, ip, vel; std::vector<int> idx; double T1[16], T2[16]; int npose, stereo, trail; };
+
+// the same construction as tests/tri_common.py: a smooth path, a stereo rig, one point projected into every observing camera
+static Scene make_scene(int seed, int npose, int stereo, double noise, double depth, int corrupt)
+{
+    srand(1000 + seed);
+    Scene s; s.trail = 20; s.npose = npose; s.stereo = stereo;
+    const int N = 20 + 7 * s.trail;
+    s.m.assign(N, 0.0);
+    for (int k = 0; k <= s.trail; k++) {
+        double pos[3] = {0.08 * k + 0.005 * nrand(), 0.02 * std::sin(0.7 * k) + 0.005 * nrand(), 0.01 * k + 0.005 * nrand()};
+        double ang[3] = {0.02 * k + 0.003 * nrand(), -0.015 * k + 0.003 * nrand(), 0.01 * std::sin((double)k) + 0.003 * nrand()};
+        double q[4] = {1.0, 0.5 * ang[0], 0.5 * ang[1], 0.5 * ang[2]};
+        const double qn = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        for (double& x : q) x /= qn;
+        const int o = k == 0 ? 0 : 20 + 7 * (k - 1);
+        for (int r = 0; r < 3; r++) s.m[o + r] = pos[r];
+        for (int r = 0; r < 4; r++) s.m[(k == 0 ? 6 : o + 3) + r] = q[r];
+    }
+    for (int r = 0; r < 3; r++) { s.m[3 + r] = 0.1 * nrand(); s.m[16 + r] = 1.0; }
+    double qc[4] = {1.0, 0.01 * nrand(), 0.01 * nrand(), 0.01 * nrand()};
+    const double qn = std::sqrt(qc[0] * qc[0] + qc[1] * qc[1] + qc[2] * qc[2] + qc[3] * qc[3]);
+    for (double& x : qc) x /= qn;
+    double Rc[9]; quat2rmat(qc, Rc);
+    memset(s.T1, 0, sizeof(s.T1));
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) s.T1[4 * c + r] = Rc[3 * r + c];
+    s.T1[12] = 0.01; s.T1[13] = -0.02; s.T1[14] = 0.005; s.T1[15] = 1.0;
+    memcpy(s.T2, s.T1, sizeof(s.T1)); s.T2[12] -= 0.11;
+    // pose indices: 0 plus npose - 1 distinct trail slots, increasing
+    std::vector<int> pool; for (int k = 1; k <= s.trail; k++) pool.push_back(k);
+    for (int k = 0; k < npose - 1; k++) { const int j = k + rand() % (int)(pool.size() - k); std::swap(pool[k], pool[j]); }
+    s.idx.assign(pool.begin(), pool.begin() + npose - 1); std::sort(s.idx.begin(), s.idx.end()); s.idx.insert(s.idx.begin(), 0);
+    auto cam = [&](int i, const double* T, double* pc, double* R) {
+        const int o = i == 0 ? 0 : 20 + 7 * (i - 1);
+        double Rq[9]; quat2rmat(&s.m[i == 0 ? 6 : o + 3], Rq);
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { double v = 0; for (int k = 0; k < 3; k++) v += T[4 * k + r] * Rq[3 * k + c]; R[3 * r + c] = v; }
+        for (int r = 0; r < 3; r++) pc[r] = s.m[o + r] - (R[r] * T[12] + R[3 + r] * T[13] + R[6 + r] * T[14]);
+    };
+    double p0[3], R0[9]; cam(0, s.T1, p0, R0);
+    const double local[3] = {(urand() * 0.6 - 0.3) * depth, (urand() * 0.4 - 0.2) * depth, depth};
+    double pf[3]; for (int r = 0; r < 3; r++) pf[r] = p0[r] + R0[r] * local[0] + R0[3 + r] * local[1] + R0[6 + r] * local[2];
+    for (int c = 0; c < (stereo ? 2 : 1); c++) for (int i : s.idx) {
+        double pc[3], R[9], d[3], x[3]; cam(i, c ? s.T2 : s.T1, pc, R);
+        for (int r = 0; r < 3; r++) d[r] = pf[r] - pc[r];
+        tm_mv(R, d, x);
+        s.ip.push_back(x[0] / x[2] + noise * nrand()); s.ip.push_back(x[1] / x[2] + noise * nrand());
+    }
+    for (size_t i = 0; i < s.ip.size(); i++) s.vel.push_back(0.05 * nrand());
+    if (corrupt == 1) { const int k = rand() % (int)(s.ip.size() / 2); s.ip[2 * k] += 0.5 * nrand(); s.ip[2 * k + 1] += 0.5 * nrand(); }     // outlier
+    if (corrupt == 2) for (double& v : s.ip) v = -v + 0.05 * nrand();                                                                          // behind
+    if (corrupt == 3) {                                                                                                                         // static camera
+        for (int k = 1; k <= s.trail; k++) { const int o = 20 + 7 * (k - 1); for (int r = 0; r < 3; r++) s.m[o + r] = s.m[r] + 1e-7 * nrand(); for (int r = 0; r < 4; r++) s.m[o + 3 + r] = s.m[6 + r]; }
+        for (size_t i = 2; i < s.ip.size(); i++) s.ip[i] = s.ip[i % 2] + 1e-6 * nrand();
+    }
+    if (corrupt == 4) for (double& v : s.ip) v = 0.5 * nrand();                                                                                // garbage
+    return s;
+}
+
+int main()
+{
+    int fails = 0, hist[8] = {0};
+    const int ncase = 40;
+    for (int cs = 0; cs < ncase; cs++) {
+        const int stereo = cs % 2 == 0, npose = 2 + cs % 9, corrupt = cs < 18 ? 0 : 1 + cs % 4, ets = cs % 5 != 3;
+        const double noises[3] = {1e-3, 3e-3, 1e-2}, depths[4] = {2, 5, 15, 40};
+        Scene s = make_scene(cs, npose, stereo, noises[cs % 3], depths[cs % 4], corrupt);
+        const int N = (int)s.m.size(), nobs = npose * (stereo ? 2 : 1);
+        // oracle
+        int tri, vu, rows, cols; double pf[3], depth;
+        std::vector<double> dpf(3 * (7 * npose + 1)), H((size_t)2 * nobs * N), f(2 * nobs);
+        orc_track_model(s.m.data(), s.trail, stereo, s.idx.data(), npose, s.T1, s.T2, s.ip.data(), s.vel.data(), ets, &tri, pf, dpf.data(), &depth, &vu, &rows, &cols, H.data(), f.data());
+        // kernel body, as track 1 of a 3-track launch (offsets)
+        const int T = 3, trk = 1;
+        TmArgs a; memset(&a, 0, sizeof(a));
+        a.m = s.m.data(); a.N = N; a.stereo = stereo; a.timeShift = ets; a.ntracks = T;
+        for (int c = 0; c < 2; c++) { const double* Tm = c ? s.T2 : s.T1; for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) a.Rc[c][3 * r + k] = Tm[4 * k + r]; a.base[c][r] = Tm[12 + r]; } }
+        a.gnIterations = 10; a.convThreshold = 1e-2; a.convR = 11.0; a.rcondThreshold = 1e-8; a.minDist = 0; a.maxDist = 1e300;
+        std::vector<int> np(T, npose), idx(T * TM_MAXPOSE, 0), st(4 * T, -7);
+        std::vector<double> ip(T * TM_MAXOBS * 2, 0.0), vel(T * TM_MAXOBS * 2, 0.0), opf(4 * T), odpf((size_t)T * 3 * (7 * TM_MAXPOSE + 1), 7.0), of(T * 2 * TM_MAXOBS);
+        const size_t Hs = (size_t)2 * TM_MAXOBS * TM_MAXN;
+        std::vector<double> oH(T * Hs, 7.0);
+        std::copy(s.idx.begin(), s.idx.end(), idx.begin() + trk * TM_MAXPOSE);
+        std::copy(s.ip.begin(), s.ip.end(), ip.begin() + trk * TM_MAXOBS * 2);
+        std::copy(s.vel.begin(), s.vel.end(), vel.begin() + trk * TM_MAXOBS * 2);
+        a.npose = np.data(); a.idx = idx.data(); a.ip = ip.data(); a.vel = vel.data(); a.status = st.data(); a.pf = opf.data(); a.dpf = odpf.data();
+        a.H = oH.data(); a.f = of.data(); a.Hstride = Hs;
+        std::vector<double> dyn(tm_smem_bytes() / 8, std::nan(""));      // shared memory is not zero on the device
+        gridDim.x = T;
+        emu::launch_cta(TM_NT, trk, [&] { tm_body(a, dyn.data()); });
+        // compare
+        const int* kst = &st[4 * trk];
+        bool ok = kst[0] == tri && kst[1] == vu;
+        double ep = 0, ed = 0, eh = 0, ef = 0, dmax = 1e-300, hmax = 1e-300;
+        if (ok && tri == 0) {
+            ok = kst[2] == rows && kst[3] == cols;
+            for (int r = 0; r < 3; r++) ep = std::fmax(ep, std::fabs(opf[4 * trk + r] - pf[r]) / std::fmax(1.0, std::fabs(pf[r])));
+            ep = std::fmax(ep, std::fabs(opf[4 * trk + 3] - depth) / std::fmax(1.0, depth));
+            const double* kd = &odpf[(size_t)trk * 3 * (7 * TM_MAXPOSE + 1)];
+            for (size_t i = 0; i < dpf.size(); i++) { ed = std::fmax(ed, std::fabs(kd[i] - dpf[i])); dmax = std::fmax(dmax, std::fabs(dpf[i])); }
+            if (ok && vu == 0) {
+                const double* kH = &oH[trk * Hs];
+                for (size_t i = 0; i < (size_t)rows * cols; i++) { eh = std::fmax(eh, std::fabs(kH[i] - H[i])); hmax = std::fmax(hmax, std::fabs(H[i])); }
+                for (int i = 0; i < rows; i++) ef = std::fmax(ef, std::fabs(of[trk * 2 * TM_MAXOBS + i] - f[i]));
+            }
+            const double tol = dmax < 1e6 ? 1e-9 : 1e-6;
+            ok = ok && ep < tol && ed / dmax < tol && eh / hmax < tol && ef < tol;
+        }
+        // neighbours untouched
+        ok = ok && st[0] == -7 && st[8] == -7 && oH[0] == 7.0 && oH[2 * Hs] == 7.0;
+        hist[tri & 7]++;
+        printf("case %2d %s npose=%d corrupt=%d ts=%d: status %d/%d (oracle %d/%d) H %dx%d  |dpf| %.2e |dH| %.2e |df| %.2e |dpf,depth| %.2e  %s\n", cs, stereo ? "stereo" : "mono  ", npose,
+               corrupt, ets, kst[0], kst[1], tri, vu, rows, cols, ed / dmax, eh / hmax, ef, ep, ok ? "ok" : "FAIL");
+        fails += !ok;
+    }
+    printf("statuses seen: OK %d BEHIND %d BAD_COND %d NO_CONVERGENCE %d\n", hist[0], hist[2], hist[3], hist[4]);
+    return fails;
+}
