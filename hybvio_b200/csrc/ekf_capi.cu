@@ -956,6 +956,42 @@ int hv_ekf_track_models(hv_ekf* e, const hv_track_obs* tracks, int ntracks, hv_t
     return HV_OK;
 }
 
+// Outlier check / update on a measurement model that is already on the device (hv_ekf_track_models): same launch and result
+// protocol as visual_host, without the staging copy.
+int hv_ekf_visual_track(hv_ekf* e, const hv_track_model* t, double r, double rmseThr, int mode, int* vuStatus, double* chi2)
+{
+    EKF_ENTER(e, "hv_ekf_visual_track");
+    const char* who = "hv_ekf_visual_track";
+    if (!t || !t->d_H || !t->d_f || !t->d_y || mode < 0 || mode > 2) { hv_set_error("%s: invalid argument", who); return HV_ERR_INVALID; }
+    if (t->triangulator_status != 0 || t->prepare_vu_status != 0) { hv_set_error("%s: the track has no valid measurement model", who); return HV_ERR_INVALID; }
+    EkfUpdateArgs a;
+    int rc = visual_args(e, who, t->rows, t->cols, r, rmseThr, mode, a);
+    if (rc != HV_OK) return rc;
+    a.H = t->d_H; a.f = t->d_f; a.y = t->d_y;
+    prep_update(e, a);
+    const bool polled = ekf_polling() && mode != EKF_MODE_UPDATE && ekf_update_uses_cluster2(a);
+    if (polled) { a.sig = e->d_sig; a.sigSeq = (e->sigSeq += 1.0); }
+    rc = launch_update(e, a);
+    if (rc != HV_OK) return rc;
+    if (mode == EKF_MODE_UPDATE) return HV_OK;                   // asynchronous
+    cudaStream_t s = e->ctx->stream;
+    double st[3];
+    if (polled) {
+        rc = poll_results(e, 1, a.sigSeq, who);
+        if (rc != HV_OK) return rc;
+        st[0] = e->h_sig[0]; st[1] = e->h_sig[1]; st[2] = e->h_sig[2];
+    } else {
+        double* hout = e->h_pin + e->inDoubles;
+        HV_CUDA(cudaMemcpyAsync(hout, e->b.res, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        HV_CUDA(cudaStreamSynchronize(s));
+        st[0] = hout[0]; st[1] = hout[1]; st[2] = hout[2];
+    }
+    if (vuStatus) *vuStatus = (int)st[0];
+    if (chi2) *chi2 = st[1];
+    if (st[2] != 0.0) { hv_set_error("%s: innovation covariance not positive definite", who); return HV_ERR_STATE; }
+    return HV_OK;
+}
+
 int hv_ekf_track_model_download(hv_ekf* e, int track, double* H, double* f, double* dpf)
 {
     EKF_ENTER_LAZY(e, "hv_ekf_track_model_download");

@@ -9,6 +9,7 @@
 #include "ekf.hpp"
 #include "parameters.hpp"
 #include "../../include/hybvio_b200.h"
+#include "cuda_track_model.hpp"
 
 #include <Eigen/Eigenvalues>
 #include <cstdio>
@@ -189,4 +190,71 @@ EKF::~EKF() = default;
 EKF::EKF(const EKF& other) = default;
 EKF::EKF() {}
 std::unique_ptr<EKF> EKF::build(const Parameters& parameters) { return std::unique_ptr<EKF>(new CudaEKF(parameters)); }
+
+// ---- cuda_track_model.hpp: the per-track measurement model on the device (backend.cpp:1050-1160)
+static CudaEKF& cudaEkf(EKF& ekf) {
+    CudaEKF* c = dynamic_cast<CudaEKF*>(&ekf);
+    if (!c) { std::fprintf(stderr, "hybvio_b200: the EKF was not built by the CUDA EKF::build\n"); std::abort(); }
+    return *c;
+}
+
+void cudaTrackModels(EKF& ekf, const Parameters& parameters, const std::vector<CudaTrackIn>& in, std::vector<CudaTrackOut>& out) {
+    CudaEKF& e = cudaEkf(ekf);
+    const ParametersOdometry& po = parameters.odometry;
+    hv_camera_model cam;
+    hv_camera_model_defaults(&cam);
+    Eigen::Map<Eigen::Matrix4d>(cam.imu_to_camera) = parameters.imuToCamera;
+    Eigen::Map<Eigen::Matrix4d>(cam.second_imu_to_camera) = parameters.secondImuToCamera;
+    cam.use_stereo = parameters.tracker.useStereo ? 1 : 0;
+    cam.estimate_imu_camera_time_shift = po.estimateImuCameraTimeShift ? 1 : 0;
+    cam.gauss_newton_iterations = po.triangulationGaussNewtonIterations;
+    cam.convergence_threshold = po.triangulationConvergenceThreshold; cam.convergence_r = po.triangulationConvergenceR;
+    cam.rcond_threshold = po.triangulationRcondThreshold; cam.min_dist = po.triangulationMinDist; cam.max_dist = po.triangulationMaxDist;
+    HV(hv_ekf_set_camera_model(e.h, &cam));
+    std::vector<hv_track_obs> obs(in.size());
+    for (size_t k = 0; k < in.size(); k++) {
+        obs[k].npose = (int)in[k].poseTrailIndex->size();
+        obs[k].pose_trail_index = in[k].poseTrailIndex->data();
+        obs[k].ip = in[k].imageFeatures->front().data();             // contiguous Vector2d storage: x0 y0 x1 y1 ...
+        obs[k].velocities = in[k].featureVelocities->front().data();
+    }
+    std::vector<hv_track_model> res(in.size());
+    HV(hv_ekf_track_models(e.h, obs.data(), (int)obs.size(), res.data()));
+    out.resize(in.size());
+    for (size_t k = 0; k < in.size(); k++) {
+        CudaTrackOut& o = out[k];
+        o.triangulateStatus = static_cast<TriangulatorStatus>(res[k].triangulator_status);
+        o.prepareVuStatus = static_cast<PrepareVuStatus>(res[k].prepare_vu_status < 0 ? 0 : res[k].prepare_vu_status);
+        o.pf = Eigen::Vector3d(res[k].pf[0], res[k].pf[1], res[k].pf[2]);
+        o.depth = res[k].depth; o.rows = res[k].rows; o.cols = res[k].cols;
+        o.dH = res[k].d_H; o.df = res[k].d_f; o.dy = res[k].d_y; o.index = (int)k;
+    }
+}
+
+static hv_track_model toAbi(const CudaTrackOut& t) {
+    hv_track_model m;
+    m.triangulator_status = static_cast<int>(t.triangulateStatus); m.prepare_vu_status = static_cast<int>(t.prepareVuStatus);
+    m.rows = t.rows; m.cols = t.cols; m.pf[0] = t.pf(0); m.pf[1] = t.pf(1); m.pf[2] = t.pf(2); m.depth = t.depth;
+    m.d_H = t.dH; m.d_f = t.df; m.d_y = t.dy;
+    return m;
+}
+
+VuOutlierStatus cudaVisualTrackOutlierCheck(EKF& ekf, const CudaTrackOut& track, double r, double trackRmseThreshold) {
+    const hv_track_model m = toAbi(track);
+    int st = 0;
+    HV(hv_ekf_visual_track(cudaEkf(ekf).h, &m, r, trackRmseThreshold, 0, &st, nullptr));
+    return static_cast<VuOutlierStatus>(st);
+}
+
+void cudaUpdateVisualTrack(EKF& ekf, const CudaTrackOut& track, double r) {
+    CudaEKF& e = cudaEkf(ekf);
+    const hv_track_model m = toAbi(track);
+    HV(hv_ekf_visual_track(e.h, &m, r, -1.0, 1, nullptr, nullptr));
+    e.touched();
+}
+
+void cudaTrackModelDownload(EKF& ekf, const CudaTrackOut& track, Eigen::MatrixXd& H, Eigen::VectorXd& f) {
+    H.resize(track.rows, track.cols); f.resize(track.rows);
+    HV(hv_ekf_track_model_download(cudaEkf(ekf).h, track.index, H.data(), f.data(), nullptr));
+}
 } // namespace odometry

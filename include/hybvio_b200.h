@@ -259,6 +259,13 @@ typedef struct hv_track_model {
 /* All tracks are evaluated against the CURRENT state mean in one launch (one CTA per track); the device pointers in out[]
  * stay valid until the next call on this ekf. Synchronises (the caller branches on the statuses). */
 int hv_ekf_track_models(hv_ekf* ekf, const hv_track_obs* tracks, int ntracks, hv_track_model* out);
+/* visualTrackOutlierCheck (mode 0) / updateVisualTrack (mode 1) / check then update-if-inlier (mode 2) (ekf.cpp:787-844) on
+ * the device-resident H, f, y of one track of the last hv_ekf_track_models call. Modes 0 and 2 return the VuOutlierStatus and
+ * chi2 (one host round trip, like hv_ekf_visual_check); mode 1 is asynchronous. Note that an update changes the state: the
+ * models of the other tracks of that call were evaluated against the state before it (as in the reference's batch mode,
+ * backend.cpp:1170-1183; per-track mode re-evaluates the next track with a new hv_ekf_track_models call). */
+int hv_ekf_visual_track(hv_ekf* ekf, const hv_track_model* t, double r, double track_rmse_threshold, int mode, int* vu_status,
+                        double* chi2);
 /* Test / debug: copies H (rows x cols), f (rows) and d pf / d (poses, t) (3 x (7 npose + 1), column-major, after the stereo
  * sum) of track `track` of the last hv_ekf_track_models call to the host; any pointer may be NULL. */
 int hv_ekf_track_model_download(hv_ekf* ekf, int track, double* H, double* f, double* dpf);

@@ -27,7 +27,7 @@ O=$OUT/obj_tests
 g++ $FL $INC -c "$REF/test/ekf.cpp" -o $O/test_ekf.o &
 g++ $FL $INC -c "$REF/test/test_main.cpp" -o $O/test_main.o &
 g++ $FL $INC -c "$REF/test/helpers.cpp" -o $O/helpers.o &
-g++ $FL $INC -c "$ROOT/hybvio_b200/host/cuda_ekf.cpp" -o $O/cuda_ekf.o &
+g++ $FL $INC -I"$ROOT/hybvio_b200/host" -c "$ROOT/hybvio_b200/host/cuda_ekf.cpp" -o $O/cuda_ekf.o &
 wait
 # parameters.o / odo_util.o ... come from build_ekf.sh (the reference's own support objects, minus ekf.o)
 g++ -o "$OUT/run_ref_ekf_tests" $O/test_ekf.o $O/test_main.o $O/helpers.o $O/cuda_ekf.o \
@@ -52,3 +52,11 @@ g++ -o "$OUT/run_ref_triangulation_tests" $O/test_triangulation.o $O/test_main.o
     $O/cuda_ekf.o $OUT/obj_ekf/parameters.o $OUT/obj_ekf/odo_util.o $OUT/obj_ekf/timer.o $OUT/obj_ekf/util_util.o $OUT/obj_ekf/parameter_parser.o $OCVOBJ \
     -Wl,--gc-sections -L"$ROOT/hybvio_b200" -lhybvio_b200 -Wl,-rpath,'$ORIGIN/../../hybvio_b200' -lpthread -ldl -lz
 echo built $OUT/run_ref_triangulation_tests
+
+# Third binary: the per-track measurement model through the reference's interfaces, host path (reference triangulation.cpp,
+# unmodified) against the device path (hybvio_b200/host/cuda_track_model.hpp), both on CudaEKF.
+g++ $FL $INC2 -I"$ROOT/hybvio_b200/host" -c "$HERE/track_model_iface_test.cpp" -o $O/track_model_iface_test.o
+g++ -o "$OUT/run_track_model_iface_test" $O/track_model_iface_test.o $O/ref_triangulation.o $O/ref_camera.o $O/ref_tracker_util.o \
+    $O/cuda_ekf.o $OUT/obj_ekf/parameters.o $OUT/obj_ekf/odo_util.o $OUT/obj_ekf/timer.o $OUT/obj_ekf/util_util.o $OUT/obj_ekf/parameter_parser.o $OCVOBJ \
+    -Wl,--gc-sections -L"$ROOT/hybvio_b200" -lhybvio_b200 -Wl,-rpath,'$ORIGIN/../../hybvio_b200' -lpthread -ldl -lz
+echo built $OUT/run_track_model_iface_test

@@ -136,3 +136,17 @@ def test_track_models_reject_bad_input(env):
     with pytest.raises(RuntimeError):
         e.track_models([(np.array([0, 25], np.int32), t["ip"][:2], t["vel"][:2])])   # index beyond the trail
     e.close()
+
+
+def test_track_model_through_the_reference_interfaces():
+    """oracle/ref_build/track_model_iface_test.cpp: the reference's unmodified extractCameraPoseTrail / Triangulator::triangulate /
+    prepareVisualUpdate / EKF::visualTrackOutlierCheck / updateVisualTrack (H built on the host) against cudaTrackModels /
+    cudaVisualTrackOutlierCheck / cudaUpdateVisualTrack (hybvio_b200/host/cuda_track_model.hpp), both on the CUDA EKF."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    exe = os.path.join(root, "oracle", "_ref", "run_track_model_iface_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/run_track_model_iface_test not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], cwd=os.path.join(root, "oracle", "_ref"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "track model interface: all ok" in r.stdout, r.stdout[-500:]
