@@ -631,6 +631,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(inputs, budget_s=args.cpu_budget)
+        if world == 1 and nsess == 1:
+            result["next_row_track_model"] = next_row_track_model()
     for x in sessions:
         x.ctx.sync(); x.ctx_b.sync()
     if world > 1:
@@ -638,6 +640,20 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         emit(json.dumps(result))
+
+
+def next_row_track_model():
+    """SURVEY.md 8(f) N1 (triangulation + prepareVisualUpdate on the device): measured and checked against the oracle by
+    tools/track_model_bench.py in a SEPARATE process after the headline measurement, so that nothing it does can disturb
+    the line above; not part of value / e2e."""
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "track_model_bench.py")], capture_output=True, text=True, timeout=180)
+        if r.returncode != 0:
+            return {"error": (r.stderr or r.stdout)[-400:]}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as ex:       # noqa: BLE001 -- a report-only extra must never take the bench line down
+        return {"error": repr(ex)[:400]}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm

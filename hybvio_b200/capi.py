@@ -144,6 +144,8 @@ def _bind_ekf(lib):
     lib.hv_ekf_set_camera_model.argtypes = [c_void_p, ctypes.POINTER(CameraModel)]
     lib.hv_ekf_track_models.argtypes = [c_void_p, ctypes.POINTER(TrackObs), c_int, ctypes.POINTER(TrackModel)]
     lib.hv_ekf_track_model_download.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    lib.hv_ekf_track_models_time.argtypes = [c_void_p, c_int, ctypes.POINTER(ctypes.c_float)]
+    lib.hv_ekf_visual_track.argtypes = [c_void_p, ctypes.POINTER(TrackModel), c_double, c_double, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double)]
     lib.hv_ekf_visual_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p]
     lib.hv_ekf_augment.argtypes = [c_void_p, c_int]
     lib.hv_ekf_set_imu_batching.argtypes = [c_void_p, c_int]
@@ -428,6 +430,21 @@ class Ekf:
                 d.update(H=H, f=f, dpf=dpf)
             res.append(d)
         return res
+
+    def track_models_time(self, reps=50):
+        """Average device time (us) of the kernel of the last track_models call."""
+        ms = ctypes.c_float(0)
+        check(self.lib.hv_ekf_track_models_time(self.h, reps, ctypes.byref(ms)), "hv_ekf_track_models_time")
+        return ms.value * 1e3
+
+    def visual_track(self, model, r, rmse_thr=-1.0, mode=0):
+        """hv_ekf_visual_track on one dict returned by track_models: (VuOutlierStatus, chi2), or None for mode 1 (asynchronous)."""
+        t = TrackModel()
+        t.triangulator_status, t.prepare_vu_status, t.rows, t.cols = model["tri_status"], model["vu_status"], model["rows"], model["cols"]
+        t.d_H, t.d_f, t.d_y = model["d_H"], model["d_f"], model["d_y"]
+        st, chi2 = c_int(-1), c_double(0.0)
+        check(self.lib.hv_ekf_visual_track(self.h, ctypes.byref(t), r, rmse_thr, mode, ctypes.byref(st), ctypes.byref(chi2)), "hv_ekf_visual_track")
+        return None if mode == 1 else (st.value, chi2.value)
 
     def flush(self): check(self.lib.hv_ekf_flush(self.h), "hv_ekf_flush")
     def set_imu_batching(self, max_samples): check(self.lib.hv_ekf_set_imu_batching(self.h, int(max_samples)), "hv_ekf_set_imu_batching")

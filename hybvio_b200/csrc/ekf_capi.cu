@@ -49,6 +49,7 @@ struct TrackModels {
     bool camSet = false;
     int cap = 0, last = 0;
     std::vector<int> lastNpose;
+    TmArgs lastArgs;
     char* d_in = nullptr;  char* h_in = nullptr;      // [npose int cap | idx int cap x MAXPOSE | ip | vel]
     char* d_out = nullptr; char* h_out = nullptr;     // [status int 4 cap | pf double 4 cap]
     double *d_dpf = nullptr, *d_H = nullptr, *d_f = nullptr;
@@ -936,6 +937,7 @@ int hv_ekf_track_models(hv_ekf* e, const hv_track_obs* tracks, int ntracks, hv_t
     a.dpf = t->d_dpf; a.H = t->d_H; a.f = t->d_f; a.Hstride = TrackModels::hStride();
     HV_CUDA(tm_launch(a, s));
     e->ctx->launches++;
+    t->lastArgs = a;
     HV_CUDA(cudaMemcpyAsync(t->h_out, t->d_out, sizeof(int) * 4 * (size_t)ntracks, cudaMemcpyDeviceToHost, s));
     const size_t pfOff = sizeof(int) * 4 * (size_t)cap;
     HV_CUDA(cudaMemcpyAsync(t->h_out + pfOff, t->d_out + pfOff, sizeof(double) * 4 * (size_t)ntracks, cudaMemcpyDeviceToHost, s));
@@ -989,6 +991,29 @@ int hv_ekf_visual_track(hv_ekf* e, const hv_track_model* t, double r, double rms
     if (vuStatus) *vuStatus = (int)st[0];
     if (chi2) *chi2 = st[1];
     if (st[2] != 0.0) { hv_set_error("%s: innovation covariance not positive definite", who); return HV_ERR_STATE; }
+    return HV_OK;
+}
+
+// Measurement aid: re-issues the kernel of the last hv_ekf_track_models call `reps` times between two CUDA events on the
+// context's stream (same inputs, same outputs) and returns the average device time per launch.
+int hv_ekf_track_models_time(hv_ekf* e, int reps, float* msPerLaunch)
+{
+    EKF_ENTER(e, "hv_ekf_track_models_time");
+    TrackModels* t = e->tm;
+    if (!t || t->last < 1 || reps < 1 || !msPerLaunch) { hv_set_error("hv_ekf_track_models_time: nothing to repeat"); return HV_ERR_INVALID; }
+    cudaStream_t s = e->ctx->stream;
+    cudaEvent_t a, b;
+    HV_CUDA(cudaEventCreate(&a)); HV_CUDA(cudaEventCreate(&b));
+    for (int i = 0; i < 3; i++) HV_CUDA(tm_launch(t->lastArgs, s));
+    HV_CUDA(cudaEventRecord(a, s));
+    for (int i = 0; i < reps; i++) HV_CUDA(tm_launch(t->lastArgs, s));
+    HV_CUDA(cudaEventRecord(b, s));
+    HV_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    HV_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    e->ctx->launches += reps + 3;
+    *msPerLaunch = ms / reps;
     return HV_OK;
 }
 

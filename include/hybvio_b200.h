@@ -270,6 +270,9 @@ int hv_ekf_visual_track(hv_ekf* ekf, const hv_track_model* t, double r, double t
  * sum) of track `track` of the last hv_ekf_track_models call to the host; any pointer may be NULL. */
 int hv_ekf_track_model_download(hv_ekf* ekf, int track, double* H, double* f, double* dpf);
 
+/* Measurement aid (bench): repeats the kernel of the last hv_ekf_track_models call `reps` times between two CUDA events on the
+ * context's stream and returns the average device time per launch in milliseconds. */
+int hv_ekf_track_models_time(hv_ekf* ekf, int reps, float* ms_per_launch);
 /* Debug: the 32 result words of the last update kernel ([0] status, [1] chi2, [2] flag, [8..] phase timestamps when
  * the library is built with -DHV_EKF_TIMING). */
 int hv_ekf_debug_result_words(hv_ekf* ekf, double* out32);

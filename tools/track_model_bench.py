@@ -1,0 +1,92 @@
+"""Measures the per-track measurement-model kernel (hv_track_model_kernel: triangulation + prepareVisualUpdate on the device,
+SURVEY.md 8(f) N1) on cuda:0 and checks it against the C oracle in the same run. Prints ONE JSON object. bench.py runs this as a
+separate process after its own measurement (a problem here cannot disturb the headline line); it can also be run by hand:
+    python tools/track_model_bench.py [--tracks 150] [--reps 50]
+Workload: the tracks of one EuRoC-shaped stereo frame (BASELINE config 2: 150 tracks, trail 20, stereo), 2..21 poses per track,
+all evaluated against one resident state in one launch (one CTA per track)."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tracks", type=int, default=150)
+    ap.add_argument("--reps", type=int, default=50)
+    args = ap.parse_args()
+    import tri_common
+    from hybvio_b200 import capi
+    from oracle import tri_oracle
+
+    base = tri_common.make_track(0, npose=4, stereo=True)
+    rng = np.random.RandomState(11)
+    tracks = []
+    for k in range(args.tracks):
+        npose = 2 + (k * 7) % 20                       # 2..21 poses: the whole range of a trail-20 filter
+        idx = np.concatenate([[0], np.sort(rng.choice(np.arange(1, 21), npose - 1, replace=False))]).astype(np.int32)
+        depth = [2.0, 4.0, 8.0, 16.0][k % 4]
+        pf = base["pf_true"] * depth / 5.0 + rng.normal(0, 0.2, 3)
+        ip = tri_common.project(base["m"], idx, base["T1"], base["T2"], True, pf) + rng.normal(0, 1e-3, (2 * npose, 2))
+        tracks.append((idx, ip, rng.normal(0, 0.05, ip.shape)))
+    hv = capi.Context(0)
+    p = capi.EkfParams()
+    capi.load().hv_ekf_default_params(ctypes.byref(p))
+    p.camera_trail_length = base["trail"]
+    ekf = capi.Ekf(hv, p)
+    ekf.upload(m=base["m"])
+    ekf.set_camera_model(base["T1"], base["T2"], use_stereo=True, estimate_time_shift=True)
+    got = ekf.track_models(tracks)                     # warm-up + results for the parity check
+    for _ in range(3):
+        ekf.track_models(tracks, download=False)
+    t0 = time.perf_counter()
+    for _ in range(args.reps):
+        ekf.track_models(tracks, download=False)
+    call_us = (time.perf_counter() - t0) / args.reps * 1e6
+    kernel_us = ekf.track_models_time(args.reps)
+    # parity against the oracle (checker only)
+    orc = tri_oracle.OracleTri()
+    worst, mism, ok_tracks, h_bytes, obs = 0.0, 0, 0, 0, 0
+    t0 = time.perf_counter()
+    exp = [orc.track_model(base["m"], base["trail"], True, i, base["T1"], base["T2"], ip, v, True) for i, ip, v in tracks]
+    port_us = (time.perf_counter() - t0) / len(tracks) * 1e6
+    for g, o in zip(got, exp):
+        if (g["tri_status"], g["vu_status"]) != (o["tri_status"], o["vu_status"]):
+            mism += 1
+            continue
+        if o["tri_status"] == 0:
+            ok_tracks += 1
+            h_bytes += 8 * o["H"].size
+            obs += o["H"].shape[0] // 2
+            for key in ("H", "f", "pf", "dpf"):
+                worst = max(worst, float(np.abs(g[key] - o[key]).max() / max(np.abs(o[key]).max(), 1e-300)))
+    out = {"kernel": "hv_track_model_kernel", "tracks": len(tracks), "stereo": True, "trail": base["trail"],
+           "kernel_us_per_launch": round(kernel_us, 2), "kernel_us_per_track": round(kernel_us / len(tracks), 3),
+           "tracks_per_s_kernel": round(len(tracks) / kernel_us * 1e6, 1),
+           "call_us": round(call_us, 2), "call_note": "hv_ekf_track_models through ctypes: pack + H2D of the observations, launch, D2H of statuses, synchronise",
+           "algo_bytes_per_launch": int(h_bytes + 8 * 160 * len(tracks) + 8 * 4 * obs),
+           "gbs": round((h_bytes + 8 * 160 * len(tracks) + 8 * 4 * obs) / kernel_us * 1e-3, 2),
+           "bytes_note": "H written (2 n_obs x l x 8 B per triangulated track) + state mean read per CTA + observations; the kernel is bound by the Gauss-Newton dependency chain, not by HBM",
+           "parity": {"checker": "oracle/hv_oracle_tri.c", "status_mismatches": mism, "triangulated": ok_tracks, "worst_relative_difference": worst},
+           "cpu_port_us_per_track": round(port_us, 2)}
+    if tri_oracle.have_ref():
+        ref = tri_oracle.RefTri()
+        t0 = time.perf_counter()
+        for i, ip, v in tracks:
+            ref.track_model(base["m"], base["trail"], True, i, base["T1"], base["T2"], ip, v, True)
+        out["cpu_reference_us_per_track"] = round((time.perf_counter() - t0) / len(tracks) * 1e6, 2)
+        out["cpu_reference_note"] = "the reference's own triangulation.cpp + prepareVisualUpdate (oracle/_ref/libref_tri.so), one host thread, incl. its EKF::build per call"
+    ekf.close(); hv.close()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
