@@ -113,14 +113,20 @@ def test_device_H_feeds_the_outlier_check_and_update(env):
     d = a.track_models([(t["idx"], t["ip"], t["vel"])])[0]
     o = orc.track_model(t["m"], t["trail"], True, t["idx"], t["T1"], t["T2"], t["ip"], t["vel"], True)
     assert d["tri_status"] == 0 and d["vu_status"] == 0
-    import torch
-    res = torch.zeros(2, dtype=torch.float64, device="cuda")
-    a.visual_device(d["d_H"], d["rows"], d["cols"], d["d_f"], d["d_y"], 0.02, 5.0, 2, res)
+    st_a, chi2_a = a.visual_track(d, 0.02, 5.0, mode=2)          # check, then update if inlier, on the device-resident H
     st_b, chi2_b, _ = b.visual_check_update(o["H"], o["f"], t["ip"].ravel(), 0.02, 5.0)
     ma, Pa = a.download(); mb, Pb = b.download()
-    torch.cuda.synchronize()
-    assert int(res[0].item()) == st_b and abs(res[1].item() - chi2_b) < 1e-9 * max(1.0, abs(chi2_b))
+    assert st_a == st_b and abs(chi2_a - chi2_b) < 1e-9 * max(1.0, abs(chi2_b))
     assert np.abs(ma - mb).max() < 1e-9 and np.abs(Pa - Pb).max() / np.abs(Pb).max() < 1e-9
+    # the asynchronous update-only mode on a second pair of filters
+    a2, b2 = make_ekf(capi, hv, t), make_ekf(capi, hv, t)
+    a2.set_camera_model(t["T1"], t["T2"], use_stereo=True)
+    d2 = a2.track_models([(t["idx"], t["ip"], t["vel"])], download=False)[0]
+    assert a2.visual_track(d2, 0.02, mode=1) is None
+    b2.visual_update(o["H"], o["f"], t["ip"].ravel(), 0.02)
+    m2a, P2a = a2.download(); m2b, P2b = b2.download()
+    assert np.abs(m2a - m2b).max() < 1e-9 and np.abs(P2a - P2b).max() / np.abs(P2b).max() < 1e-9
+    a2.close(); b2.close()
     a.close(); b.close()
 
 
