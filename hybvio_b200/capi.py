@@ -52,6 +52,16 @@ class TrackModel(ctypes.Structure):
                 ("pf", c_double * 3), ("depth", c_double), ("d_H", c_void_p), ("d_f", c_void_p), ("d_y", c_void_p)]
 
 
+class VisualUpdateParams(ctypes.Structure):
+    _fields_ = [("chi_outlier_r", c_double), ("track_rmse_threshold", c_double), ("visual_r", c_double),
+                ("max_successful_updates", c_int), ("lookahead", c_int)]
+
+
+class TrackResult(ctypes.Structure):
+    _fields_ = [("triangulator_status", c_int), ("prepare_vu_status", c_int), ("outlier_status", c_int), ("updated", c_int),
+                ("chi2", c_double), ("pf", c_double * 3), ("depth", c_double)]
+
+
 class EkfOp(ctypes.Structure):
     _fields_ = [("kind", c_int), ("n", c_int), ("l", c_int), ("mode", c_int), ("index", c_int),
                 ("t", c_double), ("r", c_double), ("rmse_thr", c_double), ("gyro", c_double * 3), ("acc", c_double * 3),
@@ -144,6 +154,8 @@ def _bind_ekf(lib):
     lib.hv_ekf_set_camera_model.argtypes = [c_void_p, ctypes.POINTER(CameraModel)]
     lib.hv_ekf_track_models.argtypes = [c_void_p, ctypes.POINTER(TrackObs), c_int, ctypes.POINTER(TrackModel)]
     lib.hv_ekf_track_model_download.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    lib.hv_ekf_visual_tracks.argtypes = [c_void_p, ctypes.POINTER(TrackObs), c_int, ctypes.POINTER(VisualUpdateParams), ctypes.POINTER(TrackResult),
+                                         ctypes.POINTER(c_int)]
     lib.hv_ekf_track_models_time.argtypes = [c_void_p, c_int, ctypes.POINTER(ctypes.c_float)]
     lib.hv_ekf_visual_track.argtypes = [c_void_p, ctypes.POINTER(TrackModel), c_double, c_double, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double)]
     lib.hv_ekf_visual_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p]
@@ -430,6 +442,28 @@ class Ekf:
                 d.update(H=H, f=f, dpf=dpf)
             res.append(d)
         return res
+
+    def _pack_tracks(self, tracks):
+        n = len(tracks)
+        obs = (TrackObs * n)()
+        keep = []
+        for k, (idx, ip, vel) in enumerate(tracks):
+            idx = np.ascontiguousarray(idx, np.int32); ip = _dd(np.asarray(ip).ravel()); vel = _dd(np.asarray(vel).ravel())
+            keep.append((idx, ip, vel))
+            obs[k].npose = len(idx); obs[k].pose_trail_index = idx.ctypes.data; obs[k].ip = ip.ctypes.data; obs[k].velocities = vel.ctypes.data
+        return obs, keep
+
+    def visual_tracks(self, tracks, chi_outlier_r, visual_r, track_rmse_threshold=-1.0, max_successful_updates=5, lookahead=0):
+        """hv_ekf_visual_tracks: the per-track model -> check -> update chain with the control flow on the device.
+        Returns (list of dicts per track, number of successful updates)."""
+        obs, keep = self._pack_tracks(tracks)
+        prm = VisualUpdateParams(chi_outlier_r, track_rmse_threshold, visual_r, max_successful_updates, lookahead)
+        out = (TrackResult * len(tracks))()
+        succ = c_int(0)
+        check(self.lib.hv_ekf_visual_tracks(self.h, obs, len(tracks), ctypes.byref(prm), out, ctypes.byref(succ)), "hv_ekf_visual_tracks")
+        res = [{"tri_status": o.triangulator_status, "vu_status": o.prepare_vu_status, "outlier_status": o.outlier_status, "updated": bool(o.updated),
+                "chi2": o.chi2, "pf": np.array(o.pf[:]), "depth": o.depth} for o in out]
+        return res, succ.value
 
     def track_models_time(self, reps=50):
         """Average device time (us) of the kernel of the last track_models call."""

@@ -80,6 +80,18 @@ struct EkfUpdateArgs {
     // mapped pinned host memory at decision time (a check+update continues with the update afterwards). NULL: none.
     double* sig;
     double sigSeq;
+    // Device-side control flow (ekf_cluster2.cuh only) for chains that are issued without host round trips
+    // (hv_ekf_visual_tracks): the kernel does its work only if
+    //   (gateI == NULL || *gateI == gateIExpect) && (gateD == NULL || *gateD == gateDExpect) && (counter == NULL || *counter < counterMax),
+    // otherwise it reports NOT_COMPUTED and leaves the filter alone. slot (3 doubles, device) receives the result words as well;
+    // *bump is incremented once an update has been applied. lateH: the measurement model is produced by the preceding kernel
+    // of the stream, so it may only be read after griddepcontrol.wait.
+    const int* gateI; int gateIExpect;
+    const double* gateD; double gateDExpect;
+    const int* counter; int counterMax;
+    int* bump;
+    double* slot;
+    int lateH, padGate;
 };
 
 // Independent outlier checks against the same (m, P): one launch, one 8-CTA cluster per measurement

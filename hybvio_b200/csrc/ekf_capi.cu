@@ -53,13 +53,16 @@ struct TrackModels {
     char* d_in = nullptr;  char* h_in = nullptr;      // [npose int cap | idx int cap x MAXPOSE | ip | vel]
     char* d_out = nullptr; char* h_out = nullptr;     // [status int 4 cap | pf double 4 cap]
     double *d_dpf = nullptr, *d_H = nullptr, *d_f = nullptr;
+    char* d_ctl = nullptr; char* h_ctl = nullptr; int ctlCap = 0;      // chains: [success counter int, pad to 16 B | 8 doubles per track]
+    static size_t ctlBytes(int c) { return 16 + (size_t)c * 64; }
     static size_t inBytes(int c) { return (size_t)c * (sizeof(int) * (1 + TM_MAXPOSE + 1) + sizeof(double) * 4 * TM_MAXOBS); }   // +1 int: keeps the doubles 8-byte aligned
     static size_t outBytes(int c) { return (size_t)c * (sizeof(int) * 4 + sizeof(double) * 4); }
     static size_t hStride() { return (size_t)2 * TM_MAXOBS * TM_MAXN; }
     void release()
     {
         cudaFree(d_in); cudaFree(d_out); cudaFree(d_dpf); cudaFree(d_H); cudaFree(d_f); cudaFreeHost(h_in); cudaFreeHost(h_out);
-        d_in = d_out = h_in = h_out = nullptr; d_dpf = d_H = d_f = nullptr; cap = 0;
+        cudaFree(d_ctl); cudaFreeHost(h_ctl);
+        d_in = d_out = h_in = h_out = d_ctl = h_ctl = nullptr; d_dpf = d_H = d_f = nullptr; cap = 0; ctlCap = 0;
     }
 };
 
@@ -883,28 +886,29 @@ static int tm_reserve(TrackModels* t, int n)
     return HV_OK;
 }
 
-int hv_ekf_track_models(hv_ekf* e, const hv_track_obs* tracks, int ntracks, hv_track_model* out)
+// Validates a batch of tracks, packs it into the pinned block, enqueues the H2D copies and fills the kernel arguments
+// (everything except ntracks / trackOffset / counter).
+static int tm_submit(hv_ekf* e, const char* who, const hv_track_obs* tracks, int ntracks, TmArgs& a)
 {
-    EKF_ENTER(e, "hv_ekf_track_models");
     TrackModels* t = e->tm;
-    if (!t || !t->camSet) { hv_set_error("hv_ekf_track_models: hv_ekf_set_camera_model has not been called"); return HV_ERR_STATE; }
-    if (!tracks || !out || ntracks < 1) { hv_set_error("hv_ekf_track_models: invalid argument"); return HV_ERR_INVALID; }
+    if (!t || !t->camSet) { hv_set_error("%s: hv_ekf_set_camera_model has not been called", who); return HV_ERR_STATE; }
+    if (!tracks || ntracks < 1) { hv_set_error("%s: invalid argument", who); return HV_ERR_INVALID; }
     const int maxIndex = e->trail < TM_MAXPOSE - 1 ? e->trail : TM_MAXPOSE - 1;
     const int ncam = t->cam.use_stereo ? 2 : 1;
     for (int k = 0; k < ntracks; k++) {
         const hv_track_obs& o = tracks[k];
         if (o.npose < 2 || o.npose > TM_MAXPOSE || !o.pose_trail_index || !o.ip || !o.velocities) {
-            hv_set_error("hv_ekf_track_models: track %d: npose %d outside 2..%d or NULL arrays", k, o.npose, TM_MAXPOSE); return HV_ERR_INVALID;
+            hv_set_error("%s: track %d: npose %d outside 2..%d or NULL arrays", who, k, o.npose, TM_MAXPOSE); return HV_ERR_INVALID;
         }
         for (int i = 0; i < o.npose; i++)
             if (o.pose_trail_index[i] < 0 || o.pose_trail_index[i] > maxIndex) {
-                hv_set_error("hv_ekf_track_models: track %d: pose index %d outside 0..%d", k, o.pose_trail_index[i], maxIndex); return HV_ERR_INVALID;
+                hv_set_error("%s: track %d: pose index %d outside 0..%d", who, k, o.pose_trail_index[i], maxIndex); return HV_ERR_INVALID;
             }
     }
     int rc = tm_reserve(t, ntracks);
     if (rc != HV_OK) return rc;
     cudaStream_t s = e->ctx->stream;
-    // pack: the block layout is fixed by the capacity, so that one H2D copy moves everything
+    // pack: the block layout is fixed by the capacity, so that the live ranges are three contiguous copies
     const int cap = t->cap;
     int* h_np = (int*)t->h_in;
     int* h_idx = h_np + cap;
@@ -917,12 +921,10 @@ int hv_ekf_track_models(hv_ekf* e, const hv_track_obs* tracks, int ntracks, hv_t
         memcpy(h_ip + (size_t)k * 2 * TM_MAXOBS, o.ip, sizeof(double) * 2 * o.npose * ncam);
         memcpy(h_vel + (size_t)k * 2 * TM_MAXOBS, o.velocities, sizeof(double) * 2 * o.npose * ncam);
     }
-    // three ranges are live: [npose | idx] up to track ntracks, ip, vel -- copy only what is used
     HV_CUDA(cudaMemcpyAsync(t->d_in, t->h_in, sizeof(int) * ((size_t)cap + (size_t)ntracks * TM_MAXPOSE), cudaMemcpyHostToDevice, s));
     const size_t ipOff = sizeof(int) * (size_t)cap * (TM_MAXPOSE + 2), velOff = ipOff + sizeof(double) * (size_t)cap * 2 * TM_MAXOBS;
     HV_CUDA(cudaMemcpyAsync(t->d_in + ipOff, t->h_in + ipOff, sizeof(double) * (size_t)ntracks * 2 * TM_MAXOBS, cudaMemcpyHostToDevice, s));
     HV_CUDA(cudaMemcpyAsync(t->d_in + velOff, t->h_in + velOff, sizeof(double) * (size_t)ntracks * 2 * TM_MAXOBS, cudaMemcpyHostToDevice, s));
-    TmArgs a;
     memset(&a, 0, sizeof(a));
     a.m = e->b.m; a.N = e->N; a.stereo = t->cam.use_stereo ? 1 : 0; a.timeShift = t->cam.estimate_imu_camera_time_shift ? 1 : 0; a.ntracks = ntracks;
     for (int c = 0; c < 2; c++) {
@@ -935,26 +937,138 @@ int hv_ekf_track_models(hv_ekf* e, const hv_track_obs* tracks, int ntracks, hv_t
     a.ip = (const double*)(t->d_in + ipOff); a.vel = (const double*)(t->d_in + velOff);
     a.status = (int*)t->d_out; a.pf = (double*)(t->d_out + sizeof(int) * 4 * (size_t)cap);
     a.dpf = t->d_dpf; a.H = t->d_H; a.f = t->d_f; a.Hstride = TrackModels::hStride();
+    t->last = ntracks; t->lastNpose.resize(ntracks);
+    for (int k = 0; k < ntracks; k++) t->lastNpose[k] = tracks[k].npose;
+    return HV_OK;
+}
+
+// D2H of the status / point words of tracks [first, first + count) (asynchronous)
+static int tm_fetch(hv_ekf* e, int first, int count)
+{
+    TrackModels* t = e->tm;
+    cudaStream_t s = e->ctx->stream;
+    const size_t pfOff = sizeof(int) * 4 * (size_t)t->cap;
+    HV_CUDA(cudaMemcpyAsync(t->h_out + sizeof(int) * 4 * (size_t)first, t->d_out + sizeof(int) * 4 * (size_t)first, sizeof(int) * 4 * (size_t)count, cudaMemcpyDeviceToHost, s));
+    HV_CUDA(cudaMemcpyAsync(t->h_out + pfOff + sizeof(double) * 4 * (size_t)first, t->d_out + pfOff + sizeof(double) * 4 * (size_t)first,
+                            sizeof(double) * 4 * (size_t)count, cudaMemcpyDeviceToHost, s));
+    return HV_OK;
+}
+
+static void tm_result(const hv_ekf* e, const TmArgs& a, int k, hv_track_model& o)
+{
+    const TrackModels* t = e->tm;
+    const int* st = (const int*)t->h_out;
+    const double* pf = (const double*)(t->h_out + sizeof(int) * 4 * (size_t)t->cap);
+    o.triangulator_status = st[4 * k]; o.prepare_vu_status = st[4 * k + 1]; o.rows = st[4 * k + 2]; o.cols = st[4 * k + 3];
+    for (int r = 0; r < 3; r++) o.pf[r] = pf[4 * k + r];
+    o.depth = pf[4 * k + 3];
+    o.d_H = t->d_H + (size_t)k * TrackModels::hStride();
+    o.d_f = t->d_f + (size_t)k * 2 * TM_MAXOBS;
+    o.d_y = a.ip + (size_t)k * 2 * TM_MAXOBS;
+}
+
+int hv_ekf_track_models(hv_ekf* e, const hv_track_obs* tracks, int ntracks, hv_track_model* out)
+{
+    EKF_ENTER(e, "hv_ekf_track_models");
+    if (!out) { hv_set_error("hv_ekf_track_models: invalid argument"); return HV_ERR_INVALID; }
+    TmArgs a;
+    int rc = tm_submit(e, "hv_ekf_track_models", tracks, ntracks, a);
+    if (rc != HV_OK) return rc;
+    cudaStream_t s = e->ctx->stream;
     HV_CUDA(tm_launch(a, s));
     e->ctx->launches++;
-    t->lastArgs = a;
-    HV_CUDA(cudaMemcpyAsync(t->h_out, t->d_out, sizeof(int) * 4 * (size_t)ntracks, cudaMemcpyDeviceToHost, s));
-    const size_t pfOff = sizeof(int) * 4 * (size_t)cap;
-    HV_CUDA(cudaMemcpyAsync(t->h_out + pfOff, t->d_out + pfOff, sizeof(double) * 4 * (size_t)ntracks, cudaMemcpyDeviceToHost, s));
+    e->tm->lastArgs = a;
+    rc = tm_fetch(e, 0, ntracks);
+    if (rc != HV_OK) return rc;
     HV_CUDA(cudaStreamSynchronize(s));
-    const int* st = (const int*)t->h_out;
-    const double* pf = (const double*)(t->h_out + pfOff);
-    t->last = ntracks; t->lastNpose.resize(ntracks);
-    for (int k = 0; k < ntracks; k++) {
-        hv_track_model& o = out[k];
-        o.triangulator_status = st[4 * k]; o.prepare_vu_status = st[4 * k + 1]; o.rows = st[4 * k + 2]; o.cols = st[4 * k + 3];
-        for (int r = 0; r < 3; r++) o.pf[r] = pf[4 * k + r];
-        o.depth = pf[4 * k + 3];
-        o.d_H = t->d_H + (size_t)k * TrackModels::hStride();
-        o.d_f = t->d_f + (size_t)k * 2 * TM_MAXOBS;
-        o.d_y = a.ip + (size_t)k * 2 * TM_MAXOBS;
-        t->lastNpose[k] = tracks[k].npose;
+    for (int k = 0; k < ntracks; k++) tm_result(e, a, k, out[k]);
+    return HV_OK;
+}
+
+// The per-track loop of Session::trackerVisualUpdate (src/odometry/backend.cpp:1012-1252, per-track mode) as ONE stream-ordered
+// chain with the control flow on the device: for every track  model(state) -> outlier check -> update if inlier,  each kernel
+// gated by words the previous ones wrote (model valid, fewer than max_successful_updates so far, check said INLIER). The host
+// synchronises once per `lookahead` tracks instead of twice per track.
+int hv_ekf_visual_tracks(hv_ekf* e, const hv_track_obs* tracks, int ntracks, const hv_visual_update_params* p, hv_track_result* out,
+                         int* successfulUpdates)
+{
+    EKF_ENTER(e, "hv_ekf_visual_tracks");
+    const char* who = "hv_ekf_visual_tracks";
+    if (!p || !out) { hv_set_error("%s: invalid argument", who); return HV_ERR_INVALID; }
+    TmArgs base;
+    int rc = tm_submit(e, who, tracks, ntracks, base);
+    if (rc != HV_OK) return rc;
+    TrackModels* t = e->tm;
+    cudaStream_t s = e->ctx->stream;
+    if (t->ctlCap < t->cap) {
+        cudaFree(t->d_ctl); cudaFreeHost(t->h_ctl); t->d_ctl = t->h_ctl = nullptr; t->ctlCap = 0;
+        HV_CUDA(cudaMalloc(&t->d_ctl, TrackModels::ctlBytes(t->cap)));
+        HV_CUDA(cudaHostAlloc(&t->h_ctl, TrackModels::ctlBytes(t->cap), cudaHostAllocDefault));
+        t->ctlCap = t->cap;
     }
+    int* d_counter = (int*)t->d_ctl;
+    double* d_slots = (double*)(t->d_ctl + 16);                       // per track: check (4 doubles), update (4 doubles)
+    HV_CUDA(cudaMemsetAsync(t->d_ctl, 0, 16, s));
+    const int maxSucc = p->max_successful_updates > 0 ? p->max_successful_updates : 0x7fffffff;
+    const int ncam = t->cam.use_stereo ? 2 : 1;
+    const int step = p->lookahead > 0 ? p->lookahead : ntracks;
+    int issued = 0, succ = 0;
+    while (issued < ntracks && succ < maxSucc) {
+        const int first = issued, count = ntracks - issued < step ? ntracks - issued : step;
+        for (int k = first; k < first + count; k++) {
+            TmArgs a = base;
+            a.ntracks = 1; a.trackOffset = k; a.counter = d_counter; a.counterMax = maxSucc;
+            HV_CUDA(tm_launch(a, s));
+            e->ctx->launches++;
+            const hv_track_obs& o = tracks[k];
+            const int n = 2 * o.npose * ncam;
+            int l = 0;                                                // truncation of prepareVisualUpdate (triangulation.cpp:909-921)
+            for (int i = 0; i < o.npose; i++) { const int x = o.pose_trail_index[i]; const int end = x == 0 ? 10 : 20 + 7 * (x - 1) + 7; if (end > l) l = end; }
+            double* slotC = d_slots + 8 * (size_t)k;
+            EkfUpdateArgs c;
+            rc = visual_args(e, who, n, l, p->chi_outlier_r, p->track_rmse_threshold, EKF_MODE_CHECK, c);
+            if (rc != HV_OK) return rc;
+            c.H = t->d_H + (size_t)k * TrackModels::hStride(); c.f = t->d_f + (size_t)k * 2 * TM_MAXOBS; c.y = base.ip + (size_t)k * 2 * TM_MAXOBS;
+            c.gateI = base.status + 4 * (size_t)k + 1; c.gateIExpect = 0; c.counter = d_counter; c.counterMax = maxSucc; c.slot = slotC; c.lateH = 1;
+            prep_update(e, c);
+            if (!ekf_update_uses_cluster2(c)) { hv_set_error("%s: track %d (n=%d, l=%d) does not fit the cluster kernel", who, k, n, l); return HV_ERR_INVALID; }
+            rc = launch_update(e, c);
+            if (rc != HV_OK) return rc;
+            EkfUpdateArgs u;
+            rc = visual_args(e, who, n, l, p->visual_r, -1.0, EKF_MODE_UPDATE, u);
+            if (rc != HV_OK) return rc;
+            u.H = c.H; u.f = c.f; u.y = c.y;
+            u.gateD = slotC; u.gateDExpect = 0.0;                     // VuOutlierStatus::INLIER
+            u.bump = d_counter; u.slot = slotC + 4; u.lateH = 1;
+            rc = launch_update(e, u);
+            if (rc != HV_OK) return rc;
+        }
+        rc = tm_fetch(e, first, count);
+        if (rc != HV_OK) return rc;
+        HV_CUDA(cudaMemcpyAsync(t->h_ctl, t->d_ctl, 16, cudaMemcpyDeviceToHost, s));
+        HV_CUDA(cudaMemcpyAsync(t->h_ctl + 16 + 64 * (size_t)first, t->d_ctl + 16 + 64 * (size_t)first, 64 * (size_t)count, cudaMemcpyDeviceToHost, s));
+        HV_CUDA(cudaStreamSynchronize(s));
+        succ = *(const int*)t->h_ctl;
+        issued += count;
+    }
+    const double* slots = (const double*)(t->h_ctl + 16);
+    bool numeric = false;
+    for (int k = 0; k < ntracks; k++) {
+        hv_track_result& o = out[k];
+        memset(&o, 0, sizeof(o));
+        if (k >= issued) { o.triangulator_status = TM_SKIPPED; o.prepare_vu_status = TM_VU_NOT_RUN; o.outlier_status = 1; continue; }
+        hv_track_model mdl;
+        tm_result(e, base, k, mdl);
+        o.triangulator_status = mdl.triangulator_status; o.prepare_vu_status = mdl.prepare_vu_status;
+        for (int r = 0; r < 3; r++) o.pf[r] = mdl.pf[r];
+        o.depth = mdl.depth;
+        const double* sc = slots + 8 * (size_t)k;
+        o.outlier_status = (int)sc[0]; o.chi2 = sc[1];
+        o.updated = (sc[0] == 0.0 && sc[4] == 0.0 && sc[6] == 0.0) ? 1 : 0;
+        numeric = numeric || sc[2] != 0.0 || sc[6] != 0.0;
+    }
+    if (successfulUpdates) *successfulUpdates = succ;
+    if (numeric) { hv_set_error("%s: innovation covariance not positive definite", who); return HV_ERR_STATE; }
     return HV_OK;
 }
 

@@ -368,6 +368,7 @@ __device__ __forceinline__ void ek2_pdl_wait()
 __device__ __forceinline__ void ek2_report(const EkfUpdateArgs& a, double st, double chi2, double flag)
 {
     a.b.res[0] = st; a.b.res[1] = chi2; a.b.res[2] = flag;
+    if (a.slot) { a.slot[0] = st; a.slot[1] = chi2; a.slot[2] = flag; }
     if (a.sig) {
         a.sig[0] = st; a.sig[1] = chi2; a.sig[2] = flag;
         __threadfence_system();
@@ -412,9 +413,20 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     // griddepcontrol.wait, which returns when this grid has completed and its writes are visible.
     ek2_pdl_launch_dependents();
     // ---- the measurement matrix does not depend on earlier kernels: stage it before waiting for them
-    if (a.op == EKF_OP_DENSE) ek2_copy8(X, a.H, n * l, tid);
+    const bool lateH = a.lateH != 0 && a.op == EKF_OP_DENSE;
+    if (a.op == EKF_OP_DENSE) { if (!lateH) ek2_copy8(X, a.H, n * l, tid); }
     else for (int i = tid; i < n * l; i += EK2_NT) X[i] = 0.0;
     ek2_pdl_wait();
+    // ---- device-side control flow of a chain issued without host round trips (EkfUpdateArgs): every thread of the cluster
+    // reads the same words, written by kernels that have completed
+    if (a.gateI || a.gateD || a.counter) {
+        bool run = true;
+        if (a.gateI && *(volatile const int*)a.gateI != a.gateIExpect) run = false;
+        if (a.gateD && *(volatile const double*)a.gateD != a.gateDExpect) run = false;
+        if (a.counter && *(volatile const int*)a.counter >= a.counterMax) run = false;
+        if (!run) { if (c == 0 && tid == 0) ek2_report(a, 1.0, 0.0, 0.0); return; }      // VuOutlierStatus::NOT_COMPUTED
+    }
+    if (lateH) ek2_copy8(X, a.H, n * l, tid);
     // ---- stage the state mean and the own column block of P (augmentation: of A P A' + visAugQ, ekf.cpp:853-857)
     if (joseph) {
         const int drop = a.dropIdx;
@@ -702,5 +714,6 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         for (int idx = tid; idx < N * Bc; idx += EK2_NT) P[(size_t)J0 * N + idx] = Pblk[(idx % N) + (size_t)(idx / N) * ldb];
     }
     EK2_PHASE(9);
+    if (a.bump && c == 0 && tid == 0) *a.bump = *a.bump + 1;          // one writer per grid; kernels of a chain are stream-ordered
     cluster.sync();                                   // nobody may leave while its shared memory can still be read
 }

@@ -258,7 +258,11 @@ __device__ __forceinline__ int tm_ori_index(int i) { return i == 0 ? TM_ORI : TM
 __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
 {
     __shared__ int s_colmap[TM_MAXN], s_flag[4], s_code[TM_MAXOBS];
-    const int tid = threadIdx.x, trk = blockIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int tid = threadIdx.x, trk = blockIdx.x + a.trackOffset, lane = tid & 31, wrp = tid >> 5;
+    if (a.counter && *(volatile const int*)a.counter >= a.counterMax) {      // uniform: written by a kernel that has completed
+        if (tid == 0) { int* st = a.status + 4 * (size_t)trk; st[0] = TM_SKIPPED; st[1] = TM_VU_NOT_RUN; st[2] = 0; st[3] = 0; }
+        return;
+    }
     const int npose = a.npose[trk], ncam = a.stereo ? 2 : 1, n = npose * ncam, dDim = 7 * n;
     const int* idx = a.idx + (size_t)trk * TM_MAXPOSE;
     const double* ip = a.ip + (size_t)trk * TM_MAXOBS * 2;

@@ -14,7 +14,8 @@
 #define TM_CAM 20
 
 enum { TM_OK = 0, TM_HYBRID, TM_BEHIND, TM_BAD_COND, TM_NO_CONVERGENCE, TM_BAD_DEPTH, TM_UNKNOWN_PROBLEM };   // TriangulatorStatus, output.hpp:21-29
-enum { TM_VU_OK = 0, TM_VU_ZERO_DEPTH = 1, TM_VU_BEHIND = 2, TM_VU_NOT_RUN = -1 };                              // PrepareVuStatus, output.hpp:15-19
+enum { TM_VU_OK = 0, TM_VU_ZERO_DEPTH = 1, TM_VU_BEHIND = 2, TM_VU_NOT_RUN = -1 };
+#define TM_SKIPPED (-1)                        // triangulation not attempted: the chain already has its successful updates (backend.cpp:1240-1247)                              // PrepareVuStatus, output.hpp:15-19
 
 struct TmArgs {
     const double* m;            // state mean (device), N entries
@@ -33,6 +34,9 @@ struct TmArgs {
     double* H;                  // [ntracks][Hstride]  rows x cols column-major, ld = rows
     double* f;                  // [ntracks][2 TM_MAXOBS]
     size_t Hstride;
+    int trackOffset;            // CTA b handles track b + trackOffset (chains launch one track at a time out of a packed batch)
+    int counterMax;             // with counter != NULL: skip (status TM_SKIPPED) once *counter >= counterMax
+    const int* counter;         // successful updates so far in a chain issued without host round trips (hv_ekf_visual_tracks)
 };
 
 #ifdef __CUDACC__

@@ -198,8 +198,7 @@ static CudaEKF& cudaEkf(EKF& ekf) {
     return *c;
 }
 
-void cudaTrackModels(EKF& ekf, const Parameters& parameters, const std::vector<CudaTrackIn>& in, std::vector<CudaTrackOut>& out) {
-    CudaEKF& e = cudaEkf(ekf);
+static void setCameraModel(CudaEKF& e, const Parameters& parameters) {
     const ParametersOdometry& po = parameters.odometry;
     hv_camera_model cam;
     hv_camera_model_defaults(&cam);
@@ -211,6 +210,9 @@ void cudaTrackModels(EKF& ekf, const Parameters& parameters, const std::vector<C
     cam.convergence_threshold = po.triangulationConvergenceThreshold; cam.convergence_r = po.triangulationConvergenceR;
     cam.rcond_threshold = po.triangulationRcondThreshold; cam.min_dist = po.triangulationMinDist; cam.max_dist = po.triangulationMaxDist;
     HV(hv_ekf_set_camera_model(e.h, &cam));
+}
+
+static std::vector<hv_track_obs> toObs(const std::vector<CudaTrackIn>& in) {
     std::vector<hv_track_obs> obs(in.size());
     for (size_t k = 0; k < in.size(); k++) {
         obs[k].npose = (int)in[k].poseTrailIndex->size();
@@ -218,6 +220,13 @@ void cudaTrackModels(EKF& ekf, const Parameters& parameters, const std::vector<C
         obs[k].ip = in[k].imageFeatures->front().data();             // contiguous Vector2d storage: x0 y0 x1 y1 ...
         obs[k].velocities = in[k].featureVelocities->front().data();
     }
+    return obs;
+}
+
+void cudaTrackModels(EKF& ekf, const Parameters& parameters, const std::vector<CudaTrackIn>& in, std::vector<CudaTrackOut>& out) {
+    CudaEKF& e = cudaEkf(ekf);
+    setCameraModel(e, parameters);
+    const std::vector<hv_track_obs> obs = toObs(in);
     std::vector<hv_track_model> res(in.size());
     HV(hv_ekf_track_models(e.h, obs.data(), (int)obs.size(), res.data()));
     out.resize(in.size());
@@ -229,6 +238,31 @@ void cudaTrackModels(EKF& ekf, const Parameters& parameters, const std::vector<C
         o.depth = res[k].depth; o.rows = res[k].rows; o.cols = res[k].cols;
         o.dH = res[k].d_H; o.df = res[k].d_f; o.dy = res[k].d_y; o.index = (int)k;
     }
+}
+
+int cudaVisualTracks(EKF& ekf, const Parameters& parameters, const std::vector<CudaTrackIn>& in, double chiOutlierR, double rmseThreshold,
+                     double visualR, int maxSuccessfulUpdates, int lookahead, std::vector<CudaTrackResult>& out) {
+    CudaEKF& e = cudaEkf(ekf);
+    setCameraModel(e, parameters);
+    const std::vector<hv_track_obs> obs = toObs(in);
+    hv_visual_update_params p;
+    p.chi_outlier_r = chiOutlierR; p.track_rmse_threshold = rmseThreshold; p.visual_r = visualR;
+    p.max_successful_updates = maxSuccessfulUpdates; p.lookahead = lookahead;
+    std::vector<hv_track_result> res(in.size());
+    int succ = 0;
+    HV(hv_ekf_visual_tracks(e.h, obs.data(), (int)obs.size(), &p, res.data(), &succ));
+    e.touched();
+    out.resize(in.size());
+    for (size_t k = 0; k < in.size(); k++) {
+        CudaTrackResult& o = out[k];
+        o.attempted = res[k].triangulator_status >= 0;
+        o.triangulateStatus = static_cast<TriangulatorStatus>(o.attempted ? res[k].triangulator_status : 0);
+        o.prepareVuStatus = static_cast<PrepareVuStatus>(res[k].prepare_vu_status < 0 ? 0 : res[k].prepare_vu_status);
+        o.outlierStatus = static_cast<VuOutlierStatus>(res[k].outlier_status);
+        o.updated = res[k].updated != 0; o.chi2 = res[k].chi2; o.depth = res[k].depth;
+        o.pf = Eigen::Vector3d(res[k].pf[0], res[k].pf[1], res[k].pf[2]);
+    }
+    return succ;
 }
 
 static hv_track_model toAbi(const CudaTrackOut& t) {

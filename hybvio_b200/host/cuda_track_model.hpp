@@ -35,6 +35,19 @@ void cudaTrackModels(EKF& ekf, const Parameters& parameters, const std::vector<C
 VuOutlierStatus cudaVisualTrackOutlierCheck(EKF& ekf, const CudaTrackOut& track, double r, double trackRmseThreshold);
 /// EKF::updateVisualTrack on the device-resident H of a track (ekf.cpp:829-844)
 void cudaUpdateVisualTrack(EKF& ekf, const CudaTrackOut& track, double r);
+/// The whole per-track loop (model -> visualTrackOutlierCheck -> updateVisualTrack if INLIER, at most maxSuccessfulUpdates
+/// updates; backend.cpp:1012-1252 in per-track mode) as one chain with the control flow on the device: one host
+/// synchronisation per `lookahead` tracks (0: one in total) instead of two per track.
+struct CudaTrackResult {
+    TriangulatorStatus triangulateStatus; bool attempted;   // attempted == false: the chain already had its successful updates
+    PrepareVuStatus prepareVuStatus;
+    VuOutlierStatus outlierStatus;
+    bool updated;
+    double chi2, depth;
+    Eigen::Vector3d pf;
+};
+int cudaVisualTracks(EKF& ekf, const Parameters& parameters, const std::vector<CudaTrackIn>& in, double chiOutlierR, double rmseThreshold,
+                     double visualR, int maxSuccessfulUpdates, int lookahead, std::vector<CudaTrackResult>& out);
 /// Host copies of H and f (viewers, tests)
 void cudaTrackModelDownload(EKF& ekf, const CudaTrackOut& track, Eigen::MatrixXd& H, Eigen::VectorXd& f);
 

@@ -266,6 +266,33 @@ int hv_ekf_track_models(hv_ekf* ekf, const hv_track_obs* tracks, int ntracks, hv
  * backend.cpp:1170-1183; per-track mode re-evaluates the next track with a new hv_ekf_track_models call). */
 int hv_ekf_visual_track(hv_ekf* ekf, const hv_track_model* t, double r, double track_rmse_threshold, int mode, int* vu_status,
                         double* chi2);
+/* The per-track loop of Session::trackerVisualUpdate in per-track mode (src/odometry/backend.cpp:1012-1252) as ONE chain on the
+ * stream, with the control flow on the device: for every track, in order,
+ *     measurement model against the CURRENT state (the previous track's update included)
+ *  -> visualTrackOutlierCheck(chi_outlier_r, track_rmse_threshold)       if the model is valid
+ *  -> updateVisualTrack(visual_r)                                         if the check says INLIER,
+ * and nothing more once max_successful_updates updates have been applied (backend.cpp:1240-1247). Each kernel is gated by
+ * words its predecessors wrote, so the host does not synchronise per track but once per `lookahead` tracks (0: once). The
+ * caller applies its own pre-filters (track score, trackMinFrames, blacklist, maxVisualUpdates: backend.cpp:1020-1047, 1241)
+ * by choosing which tracks to submit. Results are those of the per-track calls hv_ekf_track_models ->
+ * hv_ekf_visual_track(mode 0) -> hv_ekf_visual_track(mode 1) issued track by track.
+ * Not covered: trackOutlierThresholdGrowthFactor != 1 (the thresholds are fixed for the chain), hybrid map points. */
+typedef struct hv_visual_update_params {
+    double chi_outlier_r;            /* r of the check: odometry.trackChiTestOutlierR / focal length (backend.cpp:996) */
+    double track_rmse_threshold;     /* < 0: off (odometry.trackRmseThreshold) */
+    double visual_r;                 /* r of the update (odometry.visualR, backend.cpp:994-995) */
+    int max_successful_updates;      /* odometry.maxSuccessfulVisualUpdates; <= 0: unlimited */
+    int lookahead;                   /* tracks issued per host synchronisation; 0 = all */
+} hv_visual_update_params;
+typedef struct hv_track_result {
+    int triangulator_status;         /* odometry::TriangulatorStatus; -1: not attempted (enough successful updates before it) */
+    int prepare_vu_status;           /* odometry::PrepareVuStatus, -1 if triangulation failed / not attempted */
+    int outlier_status;              /* odometry::VuOutlierStatus (INLIER 0, NOT_COMPUTED 1, RMSE 2, CHI2 3) */
+    int updated;                     /* 1: updateVisualTrack was applied with this track */
+    double chi2, pf[3], depth;
+} hv_track_result;
+int hv_ekf_visual_tracks(hv_ekf* ekf, const hv_track_obs* tracks, int ntracks, const hv_visual_update_params* params,
+                         hv_track_result* out, int* successful_updates);
 /* Test / debug: copies H (rows x cols), f (rows) and d pf / d (poses, t) (3 x (7 npose + 1), column-major, after the stereo
  * sum) of track `track` of the last hv_ekf_track_models call to the host; any pointer may be NULL. */
 int hv_ekf_track_model_download(hv_ekf* ekf, int track, double* H, double* f, double* dpf);

@@ -130,6 +130,76 @@ def test_device_H_feeds_the_outlier_check_and_update(env):
     a.close(); b.close()
 
 
+def sequential_reference_flow(orc, okf, m0_tracks, base, chi_r, vis_r, max_succ):
+    """The per-track loop of Session::trackerVisualUpdate (backend.cpp:1012-1252, per-track mode) with the oracles: every track
+    is modelled against the state the previous track's update left behind."""
+    out, succ = [], 0
+    for idx, ip, vel in m0_tracks:
+        if succ >= max_succ:
+            out.append({"tri_status": -1, "vu_status": -1, "outlier_status": 1, "updated": False})
+            continue
+        m, _ = okf.download()
+        o = orc.track_model(m, base["trail"], base["stereo"], idx, base["T1"], base["T2"], ip, vel, True)
+        r = {"tri_status": o["tri_status"], "vu_status": o["vu_status"], "outlier_status": 1, "updated": False, "pf": o["pf"]}
+        if o["tri_status"] == 0 and o["vu_status"] == 0:
+            st, chi2 = okf.visual_check(o["H"], o["f"], np.asarray(ip).ravel(), chi_r, -1.0)
+            r["outlier_status"], r["chi2"] = st, chi2
+            if st == 0:
+                okf.visual_update(o["H"], o["f"], np.asarray(ip).ravel(), vis_r)
+                r["updated"] = True
+                succ += 1
+        out.append(r)
+    return out, succ
+
+
+def chain_tracks(base, count, seed):
+    rng = np.random.RandomState(seed)
+    tracks = []
+    for k in range(count):
+        npose = 4 + (k * 5) % 9
+        idx = np.concatenate([[0], np.sort(rng.choice(np.arange(1, 21), npose - 1, replace=False))]).astype(np.int32)
+        pf = base["pf_true"] + rng.normal(0, 0.4, 3)
+        ip = tri_common.project(base["m"], idx, base["T1"], base["T2"], base["stereo"], pf)
+        ip = ip + rng.normal(0, 2e-3, ip.shape)
+        if k % 4 == 1:
+            ip[rng.randint(len(ip))] += [0.08, -0.06]          # a gross outlier: rejected by the chi2 test (or by the triangulation)
+        if k % 7 == 3:
+            ip = -ip                                           # behind the cameras: no measurement model
+        tracks.append((idx, ip, rng.normal(0, 0.05, ip.shape)))
+    return tracks
+
+
+@pytest.mark.parametrize("lookahead", [0, 3])
+def test_device_gated_chain_equals_the_per_track_loop(env, lookahead):
+    """hv_ekf_visual_tracks (model -> check -> update if inlier, control flow on the device, one synchronisation per `lookahead`
+    tracks) against the same loop driven track by track with the oracles."""
+    capi, hv, orc = env
+    from oracle import ekf_oracle
+    base = tri_common.make_track(7, npose=4, stereo=True)
+    tracks = chain_tracks(base, 14, 21)
+    e = make_ekf(capi, hv, base)
+    okf = ekf_oracle.OracleEKF(e.params)
+    rngP = np.random.RandomState(3)
+    A = rngP.normal(0, 1, (e.N, e.N))
+    P0 = 1e-4 * (A @ A.T) / e.N + np.diag(np.full(e.N, 1e-4))
+    e.upload(m=base["m"], P=P0); okf.upload(m=base["m"], P=P0)
+    e.set_camera_model(base["T1"], base["T2"], use_stereo=True)
+    chi_r, vis_r, max_succ = 0.01, 0.004, 5
+    exp, exp_succ = sequential_reference_flow(orc, okf, tracks, base, chi_r, vis_r, max_succ)
+    got, succ = e.visual_tracks(tracks, chi_r, vis_r, max_successful_updates=max_succ, lookahead=lookahead)
+    assert succ == exp_succ
+    assert exp_succ == max_succ and any(x["outlier_status"] == 3 for x in exp) and any(x["tri_status"] == 2 for x in exp) and exp[-1]["tri_status"] == -1
+    for k, (g, x) in enumerate(zip(got, exp)):
+        assert (g["tri_status"], g["vu_status"], g["outlier_status"], g["updated"]) == (x["tri_status"], x["vu_status"], x["outlier_status"], x["updated"]), (k, g, x)
+        if x["tri_status"] == 0:
+            assert np.abs(g["pf"] - x["pf"]).max() < 1e-9 * max(1.0, np.abs(x["pf"]).max())
+        if "chi2" in x:
+            assert abs(g["chi2"] - x["chi2"]) < 1e-8 * max(1.0, abs(x["chi2"]))
+    ma, Pa = e.download(); mb, Pb = okf.download()
+    assert np.abs(ma - mb).max() < 1e-9 and np.abs(Pa - Pb).max() / np.abs(Pb).max() < 1e-9
+    e.close(); okf.close()
+
+
 def test_track_models_reject_bad_input(env):
     capi, hv, _ = env
     t = tri_common.make_track(1, npose=4, stereo=False)

@@ -100,8 +100,17 @@ int main()
         a.npose = np.data(); a.idx = idx.data(); a.ip = ip.data(); a.vel = vel.data(); a.status = st.data(); a.pf = opf.data(); a.dpf = odpf.data();
         a.H = oH.data(); a.f = of.data(); a.Hstride = Hs;
         std::vector<double> dyn(tm_smem_bytes() / 8, std::nan(""));      // shared memory is not zero on the device
-        gridDim.x = T;
-        emu::launch_cta(TM_NT, trk, [&] { tm_body(a, dyn.data()); });
+        gridDim.x = 1;
+        a.trackOffset = trk;                        // one CTA of a chain: track `trk` of the packed batch
+        int counter = cs % 7 == 6 ? 5 : 2;          // a few cases arrive after the chain has its 5 successful updates
+        a.counter = &counter; a.counterMax = 5;
+        emu::launch_cta(TM_NT, 0, [&] { tm_body(a, dyn.data()); });
+        if (counter == 5) {
+            const bool sk = st[4 * trk] == TM_SKIPPED && st[4 * trk + 1] == TM_VU_NOT_RUN && oH[trk * Hs] == 7.0 && st[0] == -7 && st[8] == -7;
+            printf("case %2d skipped by the success counter  %s\n", cs, sk ? "ok" : "FAIL");
+            fails += !sk;
+            continue;
+        }
         // compare
         const int* kst = &st[4 * trk];
         bool ok = kst[0] == tri && kst[1] == vu;

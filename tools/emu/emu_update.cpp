@@ -25,7 +25,8 @@ void orc_ekf_update_zupt(orc_ekf*, double);
 static double rnd() { return rand() / (double)RAND_MAX - 0.5; }
 static double gauss() { double s = 0; for (int i = 0; i < 12; i++) s += rand() / (double)RAND_MAX; return s - 6.0; }
 
-struct Case { const char* name; int trail, C, op, n, l, mode; double yscale; int symFirst, drop; };
+// gate: 0 none; 1 device-side gates present and satisfied (+ lateH, slot, bump); 2 / 3 / 4: gated off by the int flag / the counter / the double flag
+struct Case { const char* name; int trail, C, op, n, l, mode; double yscale; int symFirst, drop; int gate = 0; };
 
 int main(int argc, char** argv)
 {
@@ -43,6 +44,11 @@ int main(int argc, char** argv)
         {"zupt", 6, 8, EKF_OP_ZUPT, 3, 6, EKF_MODE_UPDATE, 0, 0, 0},
         {"dense n=120 update (batch visual update)", 30, 8, EKF_OP_DENSE, 120, 160, EKF_MODE_UPDATE, 0.02, 0, 0},
         {"dense n=13 check+update N=62 (odd sizes)", 6, 8, EKF_OP_DENSE, 13, 41, EKF_MODE_CHECK_UPDATE, 0.02, 0, 0},
+        {"gated chain link: gates open, late H, update", 20, 8, EKF_OP_DENSE, 24, 97, EKF_MODE_UPDATE, 0.02, 0, 0, 1},
+        {"gated chain link: gates open, check", 20, 8, EKF_OP_DENSE, 24, 97, EKF_MODE_CHECK, 0.02, 0, 0, 1},
+        {"gated off by the model flag", 20, 8, EKF_OP_DENSE, 24, 97, EKF_MODE_CHECK, 0.02, 0, 0, 2},
+        {"gated off by the success counter", 20, 8, EKF_OP_DENSE, 24, 97, EKF_MODE_CHECK, 0.02, 0, 0, 3},
+        {"update gated off by the check result", 20, 8, EKF_OP_DENSE, 24, 97, EKF_MODE_UPDATE, 0.02, 0, 0, 4},
     };
     const int only = argc > 1 ? atoi(argv[1]) : -1;
     int fails = 0, idx = -1;
@@ -82,11 +88,24 @@ int main(int argc, char** argv)
         a.op = cs.op; a.n = cs.n; a.l = cs.l; a.mode = cs.mode; a.noiseScale = noiseScale; a.rmseThr = -1.0;
         int ost = 0; double ochi2 = 0;
         const double r = 0.05;
+        int* gflag = arena.alloc<int>(4); double* gslot = arena.alloc<double>(8);      // [0] model flag, [1] counter; slots: [0..2] of this kernel, [4] the check result it is gated on
+        gflag[0] = 0; gflag[1] = 2; gslot[0] = gslot[1] = gslot[2] = -7.0; gslot[4] = 0.0;
+        const bool gatedOff = cs.gate >= 2;
+        if (cs.gate) {
+            a.gateI = &gflag[0]; a.gateIExpect = 0; a.counter = &gflag[1]; a.counterMax = 5; a.gateD = &gslot[4]; a.gateDExpect = 0.0;
+            a.bump = &gflag[1]; a.slot = gslot; a.lateH = 1;
+            if (cs.gate == 2) gflag[0] = 3;            // the model kernel reported a failure
+            if (cs.gate == 3) gflag[1] = 5;            // enough successful updates already
+            if (cs.gate == 4) gslot[4] = 3.0;          // the check said CHI2 outlier
+        }
         if (cs.op == EKF_OP_DENSE) {
             a.H = H; a.f = f; a.y = y; a.Rdiag = r * r * noiseScale; a.normalizeAll = 1;
             a.chi2Thr = cs.mode == EKF_MODE_UPDATE ? 0.0 : orc_chi2inv95(cs.n);
-            if (cs.mode != EKF_MODE_UPDATE) ost = orc_ekf_visual_check(o, H, cs.n, cs.l, f, y, r, -1.0, &ochi2);
-            if (cs.mode == EKF_MODE_UPDATE || (cs.mode == EKF_MODE_CHECK_UPDATE && ost == 0)) orc_ekf_visual_update(o, H, cs.n, cs.l, f, y, r);
+            if (gatedOff) ost = 1;                     // NOT_COMPUTED, filter untouched
+            else {
+                if (cs.mode != EKF_MODE_UPDATE) ost = orc_ekf_visual_check(o, H, cs.n, cs.l, f, y, r, -1.0, &ochi2);
+                if (cs.mode == EKF_MODE_UPDATE || (cs.mode == EKF_MODE_CHECK_UPDATE && ost == 0)) orc_ekf_visual_update(o, H, cs.n, cs.l, f, y, r);
+            }
         } else if (cs.op == EKF_OP_AUGMENT) {
             const int drop = cs.drop == -1 ? cs.trail - 1 : cs.drop;
             a.Rdiag = prm.v[17] * noiseScale; a.dropIdx = drop; a.symFirst = cs.symFirst;
@@ -111,7 +130,12 @@ int main(int argc, char** argv)
         for (size_t i = 0; i < oP.size(); i++) { eP = std::fmax(eP, std::fabs(oP[i] - P[i])); pmax = std::fmax(pmax, std::fabs(oP[i])); }
         if (a.symmetrize) for (int i = 0; i < N; i++) for (int j = 0; j < i; j++) asym = std::fmax(asym, std::fabs(P[i + (size_t)j * N] - P[j + (size_t)i * N]));
         bool ok = bad == 0 && em < 1e-9 && eP / pmax < 1e-9 && asym == 0.0;
-        if (cs.op == EKF_OP_DENSE && cs.mode != EKF_MODE_UPDATE) ok = ok && (int)res[0] == ost && std::fabs(res[1] - ochi2) <= 1e-9 * std::fmax(1.0, std::fabs(ochi2));
+        if (cs.op == EKF_OP_DENSE && (cs.mode != EKF_MODE_UPDATE || gatedOff)) ok = ok && (int)res[0] == ost && std::fabs(res[1] - ochi2) <= 1e-9 * std::fmax(1.0, std::fabs(ochi2));
+        if (cs.gate) {
+            ok = ok && gslot[0] == res[0] && gslot[1] == res[1] && gslot[2] == res[2];                     // the slot mirrors the result words
+            const int expectCounter = (cs.gate == 3 ? 5 : 2) + ((cs.gate == 1 && cs.mode == EKF_MODE_UPDATE) ? 1 : 0);
+            ok = ok && gflag[1] == expectCounter;                                                          // bumped only by an applied update
+        }
         printf("[%2d] %-42s N=%3d C=%2d smem %6.1f KB: status %d/%d chi2 %.6g/%.6g  max|dm| %.2e  max|dP|/max|P| %.2e  %s\n", idx, cs.name, N, cs.C, smem / 1024.0,
                (int)res[0], ost, res[1], ochi2, em, eP / pmax, ok ? "ok" : "FAIL");
         fflush(stdout);
