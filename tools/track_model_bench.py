@@ -18,6 +18,76 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def visual_update_loop(capi, hv, base, p, ntracks=20, reps=20):
+    """Session::trackerVisualUpdate's per-track loop (backend.cpp:1012-1252; 20 candidate tracks, at most 5 successful updates)
+    three ways through the C ABI, same tracks and start state: (a) device-gated chain hv_ekf_visual_tracks, one synchronisation;
+    (b) the same chain synchronising every 4 tracks; (c) track by track: hv_ekf_track_models -> hv_ekf_visual_track(check) ->
+    hv_ekf_visual_track(update), two synchronisations per track. Wall-clock per loop incl. ctypes; results must agree."""
+    import tri_common
+    rng = np.random.RandomState(5)
+    tracks = []
+    for k in range(ntracks):
+        npose = 4 + (k * 5) % 9
+        idx = np.concatenate([[0], np.sort(rng.choice(np.arange(1, 21), npose - 1, replace=False))]).astype(np.int32)
+        ip = tri_common.project(base["m"], idx, base["T1"], base["T2"], True, base["pf_true"] + rng.normal(0, 0.4, 3))
+        ip = ip + rng.normal(0, 2e-3, ip.shape)
+        if k % 3 == 1:
+            ip[rng.randint(len(ip))] += [0.08, -0.06]
+        tracks.append((idx, ip, rng.normal(0, 0.05, ip.shape)))
+    ekf = capi.Ekf(hv, p)
+    ekf.set_camera_model(base["T1"], base["T2"], use_stereo=True, estimate_time_shift=True)
+    A = np.random.RandomState(3).normal(0, 1, (ekf.N, ekf.N))
+    P0 = 1e-4 * (A @ A.T) / ekf.N + np.diag(np.full(ekf.N, 1e-4))
+    chi_r, vis_r = 0.01, 0.004
+
+    def reset():
+        ekf.upload(m=base["m"], P=P0)
+        ekf.flush()
+        hv.sync()
+
+    def chain(lookahead):
+        return ekf.visual_tracks(tracks, chi_r, vis_r, max_successful_updates=5, lookahead=lookahead)
+
+    def per_track():
+        succ, res = 0, []
+        for t in tracks:
+            if succ >= 5:
+                break
+            d = ekf.track_models([t], download=False)[0]
+            st = 1
+            if d["tri_status"] == 0 and d["vu_status"] == 0:
+                st, _ = ekf.visual_track(d, chi_r, mode=0)
+                if st == 0:
+                    ekf.visual_track(d, vis_r, mode=1)
+                    succ += 1
+            res.append((d["tri_status"], st))
+        return res, succ
+
+    def timed(fn):
+        best, state, ret = [], None, None
+        for i in range(reps + 2):
+            reset()
+            t0 = time.perf_counter()
+            ret = fn()
+            hv.sync()
+            dt = time.perf_counter() - t0
+            if i >= 2:
+                best.append(dt)
+            state = ekf.download()
+        return float(np.median(best)) * 1e6, state, ret
+
+    us_a, st_a, ret_a = timed(lambda: chain(0))
+    us_b, st_b, _ = timed(lambda: chain(4))
+    us_c, st_c, ret_c = timed(per_track)
+    seq = [(r["tri_status"], r["outlier_status"]) for r in ret_a[0]][:len(ret_c[0])]
+    ekf.close()
+    return {"tracks": ntracks, "max_successful_updates": 5, "successful_updates": ret_a[1],
+            "chain_one_sync_us": round(us_a, 1), "chain_sync_every_4_us": round(us_b, 1), "per_track_calls_us": round(us_c, 1),
+            "same_decisions": bool(seq == ret_c[0] and ret_a[1] == ret_c[1]),
+            "max_state_difference_chain_vs_per_track": float(max(np.abs(st_a[0] - st_c[0]).max(), np.abs(st_b[0] - st_c[0]).max())),
+            "note": "median wall-clock of the whole loop through ctypes, state re-uploaded before every repetition (outside the timed region)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tracks", type=int, default=150)
@@ -84,6 +154,10 @@ def main():
             ref.track_model(base["m"], base["trail"], True, i, base["T1"], base["T2"], ip, v, True)
         out["cpu_reference_us_per_track"] = round((time.perf_counter() - t0) / len(tracks) * 1e6, 2)
         out["cpu_reference_note"] = "the reference's own triangulation.cpp + prepareVisualUpdate (oracle/_ref/libref_tri.so), one host thread, incl. its EKF::build per call"
+    try:
+        out["visual_update_loop"] = visual_update_loop(capi, hv, base, p)
+    except Exception as ex:       # noqa: BLE001 -- keep the kernel numbers above even if the loop comparison fails
+        out["visual_update_loop"] = {"error": repr(ex)[:300]}
     ekf.close(); hv.close()
     print(json.dumps(out))
 
