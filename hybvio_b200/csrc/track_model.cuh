@@ -34,7 +34,7 @@
 
 // shared-memory carve (doubles)
 #define TM_S_POSE 0                                   // n x 48: p 3, R 9, dR 4 x 9
-#define TM_S_PP (TM_S_POSE + TM_MAXOBS * 48)          // n x 24: C 9, t 3, h 3, err 2, E 6
+#define TM_S_PP (TM_S_POSE + TM_MAXOBS * 48)          // n x 24: C 9, t 3, h 3, err 2, E 6, 1 / h_z
 #define TM_S_DQ (TM_S_PP + TM_MAXOBS * 24)            // (7n + 1) x 3: d pfi
 #define TM_S_EXO (TM_S_DQ + (TM_MAXCOL + 1) * 3)      // (7n + 1) x 6: explicit part of d(E'e) (3) and d(E'E) step (3), own-pose columns
 #define TM_S_P0 (TM_S_EXO + (TM_MAXCOL + 1) * 6)      // n x 7 x 6: pose-0 items
@@ -141,13 +141,13 @@ __device__ inline void tm_dpinv32(const double* A, const double* iA, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------------- 3x3 LDL^T (diagonal pivoting)
-struct TmLdlt { double M[9]; int tp[3]; double l1; };
+struct TmLdlt { double M[9]; double iD[3]; int tp[3]; double l1; };       // iD: reciprocal pivots (0 where the pivot is below DBL_MIN: pseudo-inverse of D)
 
 __device__ inline void tm_ldlt(const double* Ain, TmLdlt& X)
 {
     double* M = X.M;
     for (int i = 0; i < 9; i++) M[i] = Ain[i];
-    X.l1 = 0;
+    X.l1 = 0; X.iD[0] = X.iD[1] = X.iD[2] = 0.0;
     for (int c = 0; c < 3; c++) {
         double s = 0;
         for (int r = c; r < 3; r++) s += fabs(M[3 * r + c]);
@@ -170,7 +170,10 @@ __device__ inline void tm_ldlt(const double* Ain, TmLdlt& X)
         for (int r = k + 1; r < 3; r++) for (int c = 0; c < k; c++) M[3 * r + k] -= M[3 * r + c] * temp[c];
         const double akk = M[4 * k];
         if (k == 0 && !(fabs(akk) > 0)) { for (int j = 0; j < 3; j++) X.tp[j] = j; return; }
-        if (fabs(akk) > 0) for (int r = k + 1; r < 3; r++) M[3 * r + k] /= akk;
+        // one division per pivot; the multipliers and the solves use the reciprocal (1 ulp from the reference's divisions)
+        const double ia = fabs(akk) > 0 ? 1.0 / akk : 0.0;
+        X.iD[k] = fabs(akk) > DBL_MIN ? ia : 0.0;
+        if (fabs(akk) > 0) for (int r = k + 1; r < 3; r++) M[3 * r + k] *= ia;
     }
 }
 
@@ -180,7 +183,7 @@ __device__ inline void tm_solve(const TmLdlt& X, const double* rhs, double* x)
     double v[3] = {rhs[0], rhs[1], rhs[2]};
     for (int k = 0; k < 3; k++) if (X.tp[k] != k) { const double t = v[k]; v[k] = v[X.tp[k]]; v[X.tp[k]] = t; }
     for (int r = 1; r < 3; r++) for (int c = 0; c < r; c++) v[r] -= M[3 * r + c] * v[c];
-    for (int i = 0; i < 3; i++) v[i] = fabs(M[4 * i]) > DBL_MIN ? v[i] / M[4 * i] : 0.0;
+    for (int i = 0; i < 3; i++) v[i] *= X.iD[i];
     for (int r = 1; r >= 0; r--) for (int c = r + 1; c < 3; c++) v[r] -= M[3 * c + r] * v[c];
     for (int k = 2; k >= 0; k--) if (X.tp[k] != k) { const double t = v[k]; v[k] = v[X.tp[k]]; v[X.tp[k]] = t; }
     x[0] = v[0]; x[1] = v[1]; x[2] = v[2];
@@ -227,12 +230,12 @@ __device__ inline void tm_block_term(const double* pp, const double* pfi, const 
         if (dC) s += dC[3 * r] * pfi[0] + dC[3 * r + 1] * pfi[1] + dC[3 * r + 2] + pfi[2] * dt[r];
         dh[r] = s;
     }
-    const double ih2 = 1.0 / h[2], ih2sq = 1.0 / (h[2] * h[2]);
-    const double dih2 = -dh[2] / (h[2] * h[2]);
-    const double dih2sq = -2 * dh[2] * ih2sq / h[2];
+    const double ih2 = pp[23], ih2sq = ih2 * ih2;                      // 1 / h_z, computed once per observation and iteration
+    const double dih2 = -dh[2] * ih2sq;
+    const double dih2sq = -2 * dh[2] * ih2sq * ih2;
     double dErr[2], dE[6];
     for (int r = 0; r < 2; r++) {
-        dErr[r] = (extra ? extra[r] : 0.0) - dh[r] / h[2] - dih2 * h[r];
+        dErr[r] = (extra ? extra[r] : 0.0) - dh[r] * ih2 - dih2 * h[r];
         const double k1 = dh[r] * ih2sq + dih2sq * h[r];
         for (int c = 0; c < 2; c++) {
             double s = -dih2 * C[3 * r + c] + k1 * C[6 + c];
@@ -373,12 +376,13 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
                 for (int r = 0; r < 3; r++) dp[r] = p0[r] - cur[r];
                 tm_mv(cur + 3, dp, t);
                 for (int r = 0; r < 3; r++) h[r] = (C[3 * r] * pfi[0] + C[3 * r + 1] * pfi[1] + C[3 * r + 2]) + pfi[2] * t[r];
-                const double ih2sq = 1.0 / (h[2] * h[2]);
+                const double ih2 = 1.0 / h[2], ih2sq = ih2 * ih2;       // the only division of the block (the reference divides per term)
                 for (int r = 0; r < 2; r++) {
-                    err[r] = ip[2 * i + r] - h[r] / h[2];
-                    for (int c = 0; c < 2; c++) E[3 * r + c] = (-1 / h[2]) * C[3 * r + c] + h[r] * ih2sq * C[6 + c];
-                    E[3 * r + 2] = -t[r] / h[2] + h[r] * ih2sq * t[2];
+                    err[r] = ip[2 * i + r] - h[r] * ih2;
+                    for (int c = 0; c < 2; c++) E[3 * r + c] = -ih2 * C[3 * r + c] + h[r] * ih2sq * C[6 + c];
+                    E[3 * r + 2] = -t[r] * ih2 + h[r] * ih2sq * t[2];
                 }
+                pp[23] = ih2;
                 for (int r = 0; r < 9; r++) pp[r] = C[r];
                 for (int r = 0; r < 3; r++) { pp[9 + r] = t[r]; pp[12 + r] = h[r]; }
                 pp[15] = err[0]; pp[16] = err[1];
