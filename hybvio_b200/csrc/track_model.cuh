@@ -141,52 +141,50 @@ __device__ inline void tm_dpinv32(const double* A, const double* iA, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------------- 3x3 LDL^T (diagonal pivoting)
-struct TmLdlt { double M[9]; double iD[3]; int tp[3]; double l1; };       // iD: reciprocal pivots (0 where the pivot is below DBL_MIN: pseudo-inverse of D)
+// Eigen's LDLT (lower, unblocked, left-looking: the pivot of step k is the largest ORIGINAL diagonal entry among the remaining
+// ones, the Schur complement is applied afterwards) written out for 3x3 in scalars, so that it lives in registers: p0 in
+// {0,1,2} is the index exchanged with 0, p1 = 1 when indices 1 and 2 were exchanged in the second step.
+struct TmLdlt { double l10, l20, l21, i0, i1, i2, l1; int p0, p1; };     // i*: reciprocal pivots (0 below DBL_MIN: pseudo-inverse of D)
 
-__device__ inline void tm_ldlt(const double* Ain, TmLdlt& X)
+__device__ __forceinline__ void tm_swap(double& a, double& b) { const double t = a; a = b; b = t; }
+
+__device__ __forceinline__ void tm_ldlt(const double* A, TmLdlt& X)
 {
-    double* M = X.M;
-    for (int i = 0; i < 9; i++) M[i] = Ain[i];
-    X.l1 = 0; X.iD[0] = X.iD[1] = X.iD[2] = 0.0;
-    for (int c = 0; c < 3; c++) {
-        double s = 0;
-        for (int r = c; r < 3; r++) s += fabs(M[3 * r + c]);
-        for (int k = 0; k < c; k++) s += fabs(M[3 * c + k]);
-        if (s > X.l1) X.l1 = s;
-    }
-    for (int k = 0; k < 3; k++) {
-        int big = k;
-        for (int i = k + 1; i < 3; i++) if (fabs(M[4 * i]) > fabs(M[4 * big])) big = i;
-        X.tp[k] = big;
-        if (big != k) {
-            for (int c = 0; c < k; c++) { const double t = M[3 * k + c]; M[3 * k + c] = M[3 * big + c]; M[3 * big + c] = t; }
-            for (int r = big + 1; r < 3; r++) { const double t = M[3 * r + k]; M[3 * r + k] = M[3 * r + big]; M[3 * r + big] = t; }
-            { const double t = M[4 * k]; M[4 * k] = M[4 * big]; M[4 * big] = t; }
-            for (int i = k + 1; i < big; i++) { const double t = M[3 * i + k]; M[3 * i + k] = M[3 * big + i]; M[3 * big + i] = t; }
-        }
-        double temp[3];
-        for (int c = 0; c < k; c++) temp[c] = M[4 * c] * M[3 * k + c];
-        for (int c = 0; c < k; c++) M[4 * k] -= M[3 * k + c] * temp[c];
-        for (int r = k + 1; r < 3; r++) for (int c = 0; c < k; c++) M[3 * r + k] -= M[3 * r + c] * temp[c];
-        const double akk = M[4 * k];
-        if (k == 0 && !(fabs(akk) > 0)) { for (int j = 0; j < 3; j++) X.tp[j] = j; return; }
-        // one division per pivot; the multipliers and the solves use the reciprocal (1 ulp from the reference's divisions)
-        const double ia = fabs(akk) > 0 ? 1.0 / akk : 0.0;
-        X.iD[k] = fabs(akk) > DBL_MIN ? ia : 0.0;
-        if (fabs(akk) > 0) for (int r = k + 1; r < 3; r++) M[3 * r + k] *= ia;
-    }
+    double a00 = A[0], a10 = A[3], a11 = A[4], a20 = A[6], a21 = A[7], a22 = A[8];
+    const double c0 = fabs(a00) + fabs(a10) + fabs(a20), c1 = fabs(a10) + fabs(a11) + fabs(a21), c2 = fabs(a20) + fabs(a21) + fabs(a22);
+    X.l1 = fmax(c0, fmax(c1, c2));                     // max abs column sum of the self-adjoint matrix (lower triangle)
+    X.p0 = 0; X.p1 = 0;
+    if (fabs(a11) > fabs(a00) && fabs(a11) >= fabs(a22)) { X.p0 = 1; tm_swap(a00, a11); tm_swap(a20, a21); }
+    else if (fabs(a22) > fabs(a00) && fabs(a22) > fabs(a11)) { X.p0 = 2; tm_swap(a00, a22); tm_swap(a10, a21); }
+    X.l10 = X.l20 = X.l21 = 0.0; X.i0 = X.i1 = X.i2 = 0.0;
+    const double d0 = a00;
+    if (!(fabs(d0) > 0)) { X.p0 = 0; return; }        // zero matrix: Eigen stops here; every solve returns 0
+    const double r0 = 1.0 / d0;
+    X.i0 = fabs(d0) > DBL_MIN ? r0 : 0.0;
+    double l10 = a10 * r0, l20 = a20 * r0;
+    if (fabs(a22) > fabs(a11)) { X.p1 = 1; tm_swap(a11, a22); tm_swap(l10, l20); }
+    const double t0 = d0 * l10;
+    const double d1 = a11 - l10 * t0;
+    double l21 = a21 - l20 * t0;
+    if (fabs(d1) > 0) { const double r1 = 1.0 / d1; X.i1 = fabs(d1) > DBL_MIN ? r1 : 0.0; l21 *= r1; }
+    const double d2 = a22 - (l20 * (d0 * l20) + l21 * (d1 * l21));
+    if (fabs(d2) > DBL_MIN) X.i2 = 1.0 / d2;
+    X.l10 = l10; X.l20 = l20; X.l21 = l21;
 }
 
-__device__ inline void tm_solve(const TmLdlt& X, const double* rhs, double* x)
+__device__ __forceinline__ void tm_solve(const TmLdlt& X, const double* rhs, double* x)
 {
-    const double* M = X.M;
-    double v[3] = {rhs[0], rhs[1], rhs[2]};
-    for (int k = 0; k < 3; k++) if (X.tp[k] != k) { const double t = v[k]; v[k] = v[X.tp[k]]; v[X.tp[k]] = t; }
-    for (int r = 1; r < 3; r++) for (int c = 0; c < r; c++) v[r] -= M[3 * r + c] * v[c];
-    for (int i = 0; i < 3; i++) v[i] *= X.iD[i];
-    for (int r = 1; r >= 0; r--) for (int c = r + 1; c < 3; c++) v[r] -= M[3 * c + r] * v[c];
-    for (int k = 2; k >= 0; k--) if (X.tp[k] != k) { const double t = v[k]; v[k] = v[X.tp[k]]; v[X.tp[k]] = t; }
-    x[0] = v[0]; x[1] = v[1]; x[2] = v[2];
+    double v0 = rhs[0], v1 = rhs[1], v2 = rhs[2];
+    if (X.p0 == 1) tm_swap(v0, v1); else if (X.p0 == 2) tm_swap(v0, v2);
+    if (X.p1) tm_swap(v1, v2);
+    v1 -= X.l10 * v0;
+    v2 -= X.l20 * v0 + X.l21 * v1;
+    v0 *= X.i0; v1 *= X.i1; v2 *= X.i2;
+    v1 -= X.l21 * v2;
+    v0 -= X.l10 * v1 + X.l20 * v2;
+    if (X.p1) tm_swap(v1, v2);
+    if (X.p0 == 1) tm_swap(v0, v1); else if (X.p0 == 2) tm_swap(v0, v2);
+    x[0] = v0; x[1] = v1; x[2] = v2;
 }
 
 // Hager's 1-norm estimate of the inverse with Higham's alternating-sign safeguard, as Eigen's LDLT::rcond()

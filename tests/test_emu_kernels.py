@@ -48,3 +48,14 @@ def test_track_model_kernel_body_on_host_emulator(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("  ok") == 40 and "FAIL" not in out.stdout          # 35 compared with the oracle + 5 skipped by the success counter
     assert "OK 25 BEHIND 6 BAD_COND 3 NO_CONVERGENCE 1" in out.stdout
+
+
+def test_track_model_ldlt_matches_oracle(tmp_path):
+    """The register-resident 3x3 pivoted LDL^T of the track-model kernel vs the oracle's (Eigen's algorithm) on 200k random
+    symmetric matrices: same pivots, backward error at rounding level."""
+    exe = str(tmp_path / "emu_ldlt3")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fpermissive", "-w", "-I" + os.path.join(ROOT, "tools", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tools", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tools", "emu", "emu_ldlt3.cpp"), "-lm", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "pivot mismatches 0;" in out.stdout, out.stdout + out.stderr
