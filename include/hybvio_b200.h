@@ -279,8 +279,8 @@ int hv_ekf_visual_track(hv_ekf* ekf, const hv_track_model* t, double r, double t
  * Not covered: trackOutlierThresholdGrowthFactor != 1 (the thresholds are fixed for the chain), hybrid map points. */
 typedef struct hv_visual_update_params {
     double chi_outlier_r;            /* r of the check: odometry.trackChiTestOutlierR / focal length (backend.cpp:996) */
-    double track_rmse_threshold;     /* < 0: off (odometry.trackRmseThreshold) */
-    double visual_r;                 /* r of the update (odometry.visualR, backend.cpp:994-995) */
+    double track_rmse_threshold;     /* odometry.trackRmseThreshold / focal length (backend.cpp:995); < 0: off */
+    double visual_r;                 /* r of the update: odometry.visualR / focal length (backend.cpp:997) */
     int max_successful_updates;      /* odometry.maxSuccessfulVisualUpdates; <= 0: unlimited */
     int lookahead;                   /* tracks issued per host synchronisation; 0 = all */
 } hv_visual_update_params;
