@@ -8,6 +8,7 @@
 #include "ekf.hpp"
 #include "parameters.hpp"
 #include <cstring>
+#include <memory>
 
 extern "C" {
 
@@ -19,13 +20,20 @@ int ref_track_model(const double* m, int trail, int useStereo, const int* poseTr
                     const double* imuToCam2, const double* ip, const double* vel, int estimateTimeShift, int* triStatus, double* pf,
                     double* dpf, double* depth, int* vuStatus, int* rows, int* cols, double* H, double* f)
 {
-    odometry::Parameters params;
-    params.odometry.cameraTrailLength = trail;
+    // the filter is only the state store behind extractCameraPoseTrail: build it once per trail length (timing runs call this
+    // function per track; EKF::build allocates N x N matrices)
+    static odometry::Parameters params;
+    static std::unique_ptr<odometry::EKF> ekf;
+    static int builtTrail = -1;
     params.odometry.estimateImuCameraTimeShift = estimateTimeShift != 0;
     params.tracker.useStereo = useStereo != 0;
     params.imuToCamera = Eigen::Map<const Eigen::Matrix4d>(imuToCam);
     params.secondImuToCamera = Eigen::Map<const Eigen::Matrix4d>(imuToCam2);
-    auto ekf = odometry::EKF::build(params);
+    if (builtTrail != trail) {
+        params.odometry.cameraTrailLength = trail;
+        ekf = odometry::EKF::build(params);
+        builtTrail = trail;
+    }
     const int N = ekf->getStateDim();
     ekf->setState(Eigen::Map<const Eigen::VectorXd>(m, N));
     std::vector<int> idx(poseTrailIndex, poseTrailIndex + npose);

@@ -153,7 +153,7 @@ def main():
         for i, ip, v in tracks:
             ref.track_model(base["m"], base["trail"], True, i, base["T1"], base["T2"], ip, v, True)
         out["cpu_reference_us_per_track"] = round((time.perf_counter() - t0) / len(tracks) * 1e6, 2)
-        out["cpu_reference_note"] = "the reference's own triangulation.cpp + prepareVisualUpdate (oracle/_ref/libref_tri.so), one host thread, incl. its EKF::build per call"
+        out["cpu_reference_note"] = "the reference's own triangulation.cpp + prepareVisualUpdate (oracle/_ref/libref_tri.so), one host thread (-O2, as oracle/ref_build/build_tri.sh compiles it)"
     try:
         out["visual_update_loop"] = visual_update_loop(capi, hv, base, p)
     except Exception as ex:       # noqa: BLE001 -- keep the kernel numbers above even if the loop comparison fails
