@@ -59,3 +59,21 @@ def test_track_model_ldlt_matches_oracle(tmp_path):
                            os.path.join(ROOT, "tools", "emu", "emu_ldlt3.cpp"), "-lm", "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "pivot mismatches 0;" in out.stdout, out.stdout + out.stderr
+
+
+def test_device_gated_chain_on_host_emulator(tmp_path):
+    """The device side of hv_ekf_visual_tracks: per track tm_body -> ek2_body check -> ek2_body update, talking through the gate /
+    slot / counter words only (inlier, chi2 outlier, point behind the cameras, skipped after the last allowed update), against
+    the same loop driven through the C oracles; final filter state within 1e-9."""
+    exe = str(tmp_path / "emu_chain")
+    objs = []
+    for name in ("hv_oracle_ekf", "hv_oracle_tri"):
+        obj = str(tmp_path / (name + ".o"))
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", name + ".c"), "-o", obj])
+        objs.append(obj)
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tools", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tools", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tools", "emu", "emu_chain.cpp"), *objs, "-lm", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("  ok") == 10 and "FAIL" not in out.stdout and "chain: 3 updates (oracle 3)" in out.stdout
