@@ -583,21 +583,24 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
     const int rows = 2 * n;
     if (tid == 0) { st[0] = TM_OK; st[1] = vu; st[2] = rows; st[3] = end; }
     if (vu != TM_VU_OK) return;
-    // H(2i + r, c): every element written exactly once, consecutive threads along a column (coalesced)
+    // H(2i + r, c): every element written exactly once; a warp per column, lanes along the rows (contiguous in memory)
     double* H = a.H + (size_t)trk * a.Hstride;
-    for (int e = tid; e < rows * end; e += TM_NT) {
-        const int c = e / rows, rr = e % rows, i = rr >> 1, r = rr & 1;
+    for (int c = wrp; c < end; c += TM_NT / 32) {
         const int mc = s_colmap[c];
-        double v = 0.0;
-        const double* dr = DIPR + 6 * i + 3 * r;
-        if (mc >= 0) {
-            const double* d = DPF + 3 * mc;
-            v = dr[0] * d[0] + dr[1] * d[1] + dr[2] * d[2];
-            if (mc / 7 == i % npose) v = OWN[14 * i + 7 * r + mc % 7] + v;
-        } else if (c == TM_SFT && a.timeShift) {
-            const double* d = DPF + 3 * 7 * npose;
-            v = (dr[0] * d[0] + dr[1] * d[1] + dr[2] * d[2]) - vel[2 * i + r];
+        const bool sft = mc < 0 && c == TM_SFT && a.timeShift;
+        const double* d = mc >= 0 ? DPF + 3 * mc : DPF + 3 * 7 * npose;
+        const int ownPose = mc >= 0 ? mc / 7 : -1, comp = mc >= 0 ? mc % 7 : 0;
+        for (int rr = lane; rr < rows; rr += 32) {
+            const int i = rr >> 1, r = rr & 1;
+            const double* dr = DIPR + 6 * i + 3 * r;
+            double v = 0.0;
+            if (mc >= 0) {
+                v = dr[0] * d[0] + dr[1] * d[1] + dr[2] * d[2];
+                if (ownPose == (i >= npose ? i - npose : i)) v = OWN[14 * i + 7 * r + comp] + v;
+            } else if (sft) {
+                v = (dr[0] * d[0] + dr[1] * d[1] + dr[2] * d[2]) - vel[2 * i + r];
+            }
+            H[(size_t)c * rows + rr] = v;
         }
-        H[e] = v;
     }
 }
