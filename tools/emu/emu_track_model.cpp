@@ -74,9 +74,9 @@ static Scene make_scene(int seed, int npose, int stereo, double noise, double de
 int main()
 {
     int fails = 0, hist[8] = {0};
-    const int ncase = 40;
+    const int ncase = 44;                          // 40..43: the largest tracks the kernel accepts (21 poses, 42 observations in stereo)
     for (int cs = 0; cs < ncase; cs++) {
-        const int stereo = cs % 2 == 0, npose = 2 + cs % 9, corrupt = cs < 18 ? 0 : 1 + cs % 4, ets = cs % 5 != 3;
+        const int stereo = cs % 2 == 0, npose = cs >= 40 ? (cs < 42 ? TM_MAXPOSE : TM_MAXPOSE - 1) : 2 + cs % 9, corrupt = cs < 18 || cs >= 40 ? 0 : 1 + cs % 4, ets = cs % 5 != 3;
         const double noises[3] = {1e-3, 3e-3, 1e-2}, depths[4] = {2, 5, 15, 40};
         Scene s = make_scene(cs, npose, stereo, noises[cs % 3], depths[cs % 4], corrupt);
         const int N = (int)s.m.size(), nobs = npose * (stereo ? 2 : 1);
@@ -102,7 +102,7 @@ int main()
         std::vector<double> dyn(tm_smem_bytes() / 8, std::nan(""));      // shared memory is not zero on the device
         gridDim.x = 1;
         a.trackOffset = trk;                        // one CTA of a chain: track `trk` of the packed batch
-        int counter = cs % 7 == 6 ? 5 : 2;          // a few cases arrive after the chain has its 5 successful updates
+        int counter = (cs % 7 == 6 && cs < 40) ? 5 : 2;          // a few cases arrive after the chain has its 5 successful updates
         a.counter = &counter; a.counterMax = 5;
         emu::launch_cta(TM_NT, 0, [&] { tm_body(a, dyn.data()); });
         if (counter == 5) {
