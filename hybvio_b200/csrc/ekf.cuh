@@ -92,6 +92,10 @@ struct EkfUpdateArgs {
     int* bump;
     double* slot;
     int lateH, padGate;
+    // EKF_MODE_CHECK_UPDATE with two noise levels (ekf_cluster2.cuh only; 0: off): the outlier check uses Rdiag, the update that
+    // follows an INLIER decision uses Rdiag2 -- visualTrackOutlierCheck(trackChiTestOutlierR) then updateVisualTrack(visualR),
+    // backend.cpp:1158-1185, in one kernel: H P and S0 = H P H' are formed once, S0 + R is factorised twice.
+    double Rdiag2;
 };
 
 // Independent outlier checks against the same (m, P): one launch, one 8-CTA cluster per measurement

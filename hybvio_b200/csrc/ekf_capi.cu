@@ -1012,6 +1012,10 @@ int hv_ekf_visual_tracks(hv_ekf* e, const hv_track_obs* tracks, int ntracks, con
     const int maxSucc = p->max_successful_updates > 0 ? p->max_successful_updates : 0x7fffffff;
     const int ncam = t->cam.use_stereo ? 2 : 1;
     const int step = p->lookahead > 0 ? p->lookahead : ntracks;
+    // check and update of a track in ONE kernel (S0 = H P H' formed once, factorised with each of the two R); HV_CHAIN_SEPARATE=1
+    // issues them as two gated launches instead (A/B)
+    static const bool separate = getenv("HV_CHAIN_SEPARATE") != nullptr;
+    const bool fused = !separate && p->chi_outlier_r >= 0.0 && p->visual_r > 0.0;
     int issued = 0, succ = 0;
     while (issued < ntracks && succ < maxSucc) {
         const int first = issued, count = ntracks - issued < step ? ntracks - issued : step;
@@ -1026,14 +1030,16 @@ int hv_ekf_visual_tracks(hv_ekf* e, const hv_track_obs* tracks, int ntracks, con
             for (int i = 0; i < o.npose; i++) { const int x = o.pose_trail_index[i]; const int end = x == 0 ? 10 : 20 + 7 * (x - 1) + 7; if (end > l) l = end; }
             double* slotC = d_slots + 8 * (size_t)k;
             EkfUpdateArgs c;
-            rc = visual_args(e, who, n, l, p->chi_outlier_r, p->track_rmse_threshold, EKF_MODE_CHECK, c);
+            rc = visual_args(e, who, n, l, p->chi_outlier_r, p->track_rmse_threshold, fused ? EKF_MODE_CHECK_UPDATE : EKF_MODE_CHECK, c);
             if (rc != HV_OK) return rc;
             c.H = t->d_H + (size_t)k * TrackModels::hStride(); c.f = t->d_f + (size_t)k * 2 * TM_MAXOBS; c.y = base.ip + (size_t)k * 2 * TM_MAXOBS;
             c.gateI = base.status + 4 * (size_t)k + 1; c.gateIExpect = 0; c.counter = d_counter; c.counterMax = maxSucc; c.slot = slotC; c.lateH = 1;
+            if (fused) { c.Rdiag2 = (p->visual_r * p->visual_r) * e->noiseScale; c.bump = d_counter; }      // check with chi_outlier_r, update with visual_r, one kernel
             prep_update(e, c);
             if (!ekf_update_uses_cluster2(c)) { hv_set_error("%s: track %d (n=%d, l=%d) does not fit the cluster kernel", who, k, n, l); return HV_ERR_INVALID; }
             rc = launch_update(e, c);
             if (rc != HV_OK) return rc;
+            if (fused) continue;
             EkfUpdateArgs u;
             rc = visual_args(e, who, n, l, p->visual_r, -1.0, EKF_MODE_UPDATE, u);
             if (rc != HV_OK) return rc;
@@ -1064,8 +1070,8 @@ int hv_ekf_visual_tracks(hv_ekf* e, const hv_track_obs* tracks, int ntracks, con
         o.depth = mdl.depth;
         const double* sc = slots + 8 * (size_t)k;
         o.outlier_status = (int)sc[0]; o.chi2 = sc[1];
-        o.updated = (sc[0] == 0.0 && sc[4] == 0.0 && sc[6] == 0.0) ? 1 : 0;
-        numeric = numeric || sc[2] != 0.0 || sc[6] != 0.0;
+        o.updated = fused ? ((sc[0] == 0.0 && sc[2] == 0.0) ? 1 : 0) : ((sc[0] == 0.0 && sc[4] == 0.0 && sc[6] == 0.0) ? 1 : 0);
+        numeric = numeric || sc[2] != 0.0 || (!fused && sc[6] != 0.0);
     }
     if (successfulUpdates) *successfulUpdates = succ;
     if (numeric) { hv_set_error("%s: innovation covariance not positive definite", who); return HV_ERR_STATE; }

@@ -570,6 +570,38 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     }
 
     EK2_PHASE(4);
+    bool decided = false;
+    if (a.Rdiag2 > 0.0 && a.mode == EKF_MODE_CHECK_UPDATE && a.op == EKF_OP_DENSE && !a.skipChi2) {
+        // ---- check and update with different R: chi2 from a small tableau [S0 + R_check | v] in the region H occupied (dead since
+        // phase B, not exposed to the cluster), every CTA for itself; the big tableau gets S0 + R_update and is eliminated below
+        const int W2 = (n + 1) | 1;
+        double* Xc = X;
+        for (int e = tid; e < n * n; e += EK2_NT) Xc[(size_t)(e / n) * W2 + (e % n)] = T[(size_t)(e / n) * W + (e % n)];
+        for (int i = tid; i < n; i += EK2_NT) Xc[(size_t)i * W2 + n] = T[(size_t)i * W + vcol];
+        __syncthreads();
+        for (int i = tid; i < n; i += EK2_NT) T[(size_t)i * W + i] += a.Rdiag2 - a.Rdiag;
+        const bool bad2 = !ek2_block_eliminate(Xc, W2, n, n + 1, wrp, lane, s_linv, &s_bad);
+        if (bad2) {                                   // uniform over the cluster
+            if (c == 0 && tid == 0) ek2_report(a, 1.0, 0.0, 1.0);
+            cluster.sync();
+            return;
+        }
+        __syncthreads();
+        if (wrp == 0) {
+            double t = 0.0;
+            for (int k = lane; k < n; k += 32) { const double z = Xc[(size_t)k * W2 + n]; t += z * z; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_sync(0xffffffffu, t, lane ^ o);
+            if (lane == 0) s_scalar[1] = a.noiseScale * t;
+        }
+        __syncthreads();
+        const double chi2c = s_scalar[1];
+        const bool outlier = chi2c > a.chi2Thr;
+        if (c == 0 && tid == 0) ek2_report(a, outlier ? 3.0 : 0.0, chi2c, 0.0);
+        if (outlier) { cluster.sync(); return; }
+        decided = true;
+        __syncthreads();                              // s_scalar / s_linv are reused below
+    }
     // ---- blocked forward elimination of [S | HP_Jc | v | (I)]: the right part becomes Z = L^-1 (.)
     const bool bad = !ek2_block_eliminate(T, W, n, cend + 1, wrp, lane, s_linv, &s_bad);
     if (bad) {                                        // uniform over the cluster
@@ -588,7 +620,9 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     }
     __syncthreads();
     const double chi2 = s_scalar[1];
-    if (checking) {
+    if (decided) {
+        // INLIER under the check's R has been reported already; chi2 here belongs to the update's R and is not reported
+    } else if (checking) {
         const bool outlier = !a.skipChi2 && chi2 > a.chi2Thr;
         if (c == 0 && tid == 0) ek2_report(a, outlier ? 3.0 : 0.0, chi2, 0.0);
         if (outlier || a.mode == EKF_MODE_CHECK) { cluster.sync(); return; }

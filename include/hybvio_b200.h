@@ -271,7 +271,9 @@ int hv_ekf_visual_track(hv_ekf* ekf, const hv_track_model* t, double r, double t
  *     measurement model against the CURRENT state (the previous track's update included)
  *  -> visualTrackOutlierCheck(chi_outlier_r, track_rmse_threshold)       if the model is valid
  *  -> updateVisualTrack(visual_r)                                         if the check says INLIER,
- * and nothing more once max_successful_updates updates have been applied (backend.cpp:1240-1247). Each kernel is gated by
+ * and nothing more once max_successful_updates updates have been applied (backend.cpp:1240-1247). Check and update of a track
+ * run as ONE kernel (H P and H P H' formed once, factorised with each of the two noise levels; HV_CHAIN_SEPARATE=1 in the
+ * environment issues two gated launches instead), so a track costs two launches. Each kernel is gated by
  * words its predecessors wrote, so the host does not synchronise per track but once per `lookahead` tracks (0: once). The
  * caller applies its own pre-filters (track score, trackMinFrames, blacklist, maxVisualUpdates: backend.cpp:1020-1047, 1241)
  * by choosing which tracks to submit. Results are those of the per-track calls hv_ekf_track_models ->

@@ -22,8 +22,8 @@ def test_predict_kernel_body_on_host_emulator(tmp_path):
 def test_cluster_update_kernel_body_on_host_emulator(tmp_path):
     """ekf_cluster2.cuh (8 / 16 CTAs as forked processes, distributed shared memory as a shared mapping): dense check /
     update / check+update at n = 8..84, augmentation incl. the deferred symmetrisation, selector updates, and the device-side
-    gates of a chain issued without host round trips (open; closed by the model flag / the success counter / the check result);
-    vs the C oracle."""
+    gates of a chain issued without host round trips (open; closed by the model flag / the success counter / the check result),
+    check + update with two noise levels in one kernel; vs the C oracle."""
     exe = str(tmp_path / "emu_update")
     obj = str(tmp_path / "orc_ekf.o")
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", "hv_oracle_ekf.c"), "-o", obj])
@@ -32,7 +32,7 @@ def test_cluster_update_kernel_body_on_host_emulator(tmp_path):
                            os.path.join(ROOT, "tools", "emu", "emu_update.cpp"), obj, "-lm", "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count(" ok") == 18 and "FAIL" not in out.stdout
+    assert out.stdout.count(" ok") == 23 and "FAIL" not in out.stdout
 
 
 def test_track_model_kernel_body_on_host_emulator(tmp_path):
@@ -74,6 +74,7 @@ def test_device_gated_chain_on_host_emulator(tmp_path):
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tools", "emu", "stubs"),
                            "-I" + os.path.join(ROOT, "tools", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
                            os.path.join(ROOT, "tools", "emu", "emu_chain.cpp"), *objs, "-lm", "-o", exe])
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count("  ok") == 10 and "FAIL" not in out.stdout and "chain: 3 updates (oracle 3)" in out.stdout
+    for args, tag in (([], "chain: 3 updates (oracle 3)"), (["fused"], "chain (fused check+update): 3 updates (oracle 3)")):
+        out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert out.stdout.count("  ok") == 10 and "FAIL" not in out.stdout and tag in out.stdout

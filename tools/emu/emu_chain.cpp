@@ -30,8 +30,9 @@ int orc_track_model(const double* m, int trail, int useStereo, const int* poseTr
 static double urand() { return rand() / (double)RAND_MAX; }
 static double nrand() { double s = 0; for (int i = 0; i < 12; i++) s += urand(); return s - 6.0; }
 
-int main()
+int main(int argc, char**)
 {
+    const bool fused = argc > 1;        // any argument: check and update of a track in ONE kernel (two noise levels)
     srand(77);
     const int trail = 20, N = 20 + 7 * trail, ntracks = 9, maxSucc = 3, stereo = 1;
     const double chiR = 0.01, visR = 0.004;
@@ -138,11 +139,16 @@ int main()
         c.Rdiag = chiR * chiR * noiseScale; c.chi2Thr = orc_chi2inv95(n);
         c.gateI = status + 4 * t + 1; c.gateIExpect = 0; c.counter = counter; c.counterMax = maxSucc; c.slot = slots + 8 * t; c.lateH = 1;
         const size_t smem = ek2_smem_bytes(n, l, N, false, 8);
+        if (fused) { c.mode = EKF_MODE_CHECK_UPDATE; c.Rdiag2 = visR * visR * noiseScale; c.bump = counter; }
         int bad = emu::launch_cluster(arena, 8, EK2_NT, smem, [&](double* dyn) { EkfUpdateArgs aa = c; ek2_body(aa, dyn, cg::this_cluster()); });
-        EkfUpdateArgs u = c;
-        u.mode = EKF_MODE_UPDATE; u.Rdiag = visR * visR * noiseScale; u.chi2Thr = 0.0;
-        u.gateI = nullptr; u.counter = nullptr; u.gateD = slots + 8 * t; u.gateDExpect = 0.0; u.bump = counter; u.slot = slots + 8 * t + 4;
-        bad += emu::launch_cluster(arena, 8, EK2_NT, smem, [&](double* dyn) { EkfUpdateArgs aa = u; ek2_body(aa, dyn, cg::this_cluster()); });
+        if (!fused) {
+            EkfUpdateArgs u = c;
+            u.mode = EKF_MODE_UPDATE; u.Rdiag = visR * visR * noiseScale; u.chi2Thr = 0.0;
+            u.gateI = nullptr; u.counter = nullptr; u.gateD = slots + 8 * t; u.gateDExpect = 0.0; u.bump = counter; u.slot = slots + 8 * t + 4;
+            bad += emu::launch_cluster(arena, 8, EK2_NT, smem, [&](double* dyn) { EkfUpdateArgs aa = u; ek2_body(aa, dyn, cg::this_cluster()); });
+        } else {
+            slots[8 * t + 4] = (slots[8 * t] == 0.0 && slots[8 * t + 2] == 0.0) ? 0.0 : 1.0;      // "updated" as the host derives it in fused mode
+        }
         const int gTri = status[4 * t], gOut = (int)slots[8 * t], gUpd = slots[8 * t + 4] == 0.0 ? 1 : 0;
         const bool ok = bad == 0 && gTri == eTri[t] && gOut == eOut[t] && gUpd == eUpd[t];
         printf("track %d (n=%2d l=%3d): model %2d/%2d  check %d/%d  updated %d/%d  counter %d  %s\n", t, n, l, gTri, eTri[t], gOut, eOut[t], gUpd, eUpd[t], counter[0], ok ? "ok" : "FAIL");
@@ -155,7 +161,7 @@ int main()
     for (int i = 0; i < N; i++) em = std::fmax(em, std::fabs(om[i] - m[i]));
     for (size_t i = 0; i < oP.size(); i++) { eP = std::fmax(eP, std::fabs(oP[i] - P[i])); pmax = std::fmax(pmax, std::fabs(oP[i])); }
     const bool ok = counter[0] == succ && succ == maxSucc && em < 1e-9 && eP / pmax < 1e-9;
-    printf("chain: %d updates (oracle %d)  max|dm| %.2e  max|dP|/max|P| %.2e  %s\n", counter[0], succ, em, eP / pmax, ok ? "ok" : "FAIL");
+    printf("chain%s: %d updates (oracle %d)  max|dm| %.2e  max|dP|/max|P| %.2e  %s\n", fused ? " (fused check+update)" : "", counter[0], succ, em, eP / pmax, ok ? "ok" : "FAIL");
     fails += !ok;
     orc_ekf_destroy(o);
     return fails;

@@ -26,7 +26,7 @@ static double rnd() { return rand() / (double)RAND_MAX - 0.5; }
 static double gauss() { double s = 0; for (int i = 0; i < 12; i++) s += rand() / (double)RAND_MAX; return s - 6.0; }
 
 // gate: 0 none; 1 device-side gates present and satisfied (+ lateH, slot, bump); 2 / 3 / 4: gated off by the int flag / the counter / the double flag
-struct Case { const char* name; int trail, C, op, n, l, mode; double yscale; int symFirst, drop; int gate = 0; };
+struct Case { const char* name; int trail, C, op, n, l, mode; double yscale; int symFirst, drop; int gate = 0; double r2 = 0.0; };   // r2 > 0: the update uses its own noise level (two-R check+update)
 
 int main(int argc, char** argv)
 {
@@ -49,6 +49,11 @@ int main(int argc, char** argv)
         {"gated off by the model flag", 20, 8, EKF_OP_DENSE, 24, 97, EKF_MODE_CHECK, 0.02, 0, 0, 2},
         {"gated off by the success counter", 20, 8, EKF_OP_DENSE, 24, 97, EKF_MODE_CHECK, 0.02, 0, 0, 3},
         {"update gated off by the check result", 20, 8, EKF_OP_DENSE, 24, 97, EKF_MODE_UPDATE, 0.02, 0, 0, 4},
+        {"two-R check+update n=24 (inlier)", 20, 8, EKF_OP_DENSE, 24, 97, EKF_MODE_CHECK_UPDATE, 0.02, 0, 0, 0, 0.004},
+        {"two-R check+update n=24 (outlier)", 20, 8, EKF_OP_DENSE, 24, 97, EKF_MODE_CHECK_UPDATE, 40.0, 0, 0, 0, 0.004},
+        {"two-R check+update n=84 l=160", 20, 8, EKF_OP_DENSE, 84, 160, EKF_MODE_CHECK_UPDATE, 0.02, 0, 0, 0, 0.01},
+        {"two-R check+update n=8 (one-stage S), gated", 20, 8, EKF_OP_DENSE, 8, 34, EKF_MODE_CHECK_UPDATE, 0.02, 0, 0, 1, 0.2},
+        {"two-R check+update n=13 N=62", 6, 8, EKF_OP_DENSE, 13, 41, EKF_MODE_CHECK_UPDATE, 0.02, 0, 0, 0, 0.004},
     };
     const int only = argc > 1 ? atoi(argv[1]) : -1;
     int fails = 0, idx = -1;
@@ -104,8 +109,9 @@ int main(int argc, char** argv)
             if (gatedOff) ost = 1;                     // NOT_COMPUTED, filter untouched
             else {
                 if (cs.mode != EKF_MODE_UPDATE) ost = orc_ekf_visual_check(o, H, cs.n, cs.l, f, y, r, -1.0, &ochi2);
-                if (cs.mode == EKF_MODE_UPDATE || (cs.mode == EKF_MODE_CHECK_UPDATE && ost == 0)) orc_ekf_visual_update(o, H, cs.n, cs.l, f, y, r);
+                if (cs.mode == EKF_MODE_UPDATE || (cs.mode == EKF_MODE_CHECK_UPDATE && ost == 0)) orc_ekf_visual_update(o, H, cs.n, cs.l, f, y, cs.r2 > 0 ? cs.r2 : r);
             }
+            if (cs.r2 > 0) a.Rdiag2 = cs.r2 * cs.r2 * noiseScale;
         } else if (cs.op == EKF_OP_AUGMENT) {
             const int drop = cs.drop == -1 ? cs.trail - 1 : cs.drop;
             a.Rdiag = prm.v[17] * noiseScale; a.dropIdx = drop; a.symFirst = cs.symFirst;
@@ -133,7 +139,7 @@ int main(int argc, char** argv)
         if (cs.op == EKF_OP_DENSE && (cs.mode != EKF_MODE_UPDATE || gatedOff)) ok = ok && (int)res[0] == ost && std::fabs(res[1] - ochi2) <= 1e-9 * std::fmax(1.0, std::fabs(ochi2));
         if (cs.gate) {
             ok = ok && gslot[0] == res[0] && gslot[1] == res[1] && gslot[2] == res[2];                     // the slot mirrors the result words
-            const int expectCounter = (cs.gate == 3 ? 5 : 2) + ((cs.gate == 1 && cs.mode == EKF_MODE_UPDATE) ? 1 : 0);
+            const int expectCounter = (cs.gate == 3 ? 5 : 2) + ((cs.gate == 1 && (cs.mode == EKF_MODE_UPDATE || (cs.mode == EKF_MODE_CHECK_UPDATE && ost == 0))) ? 1 : 0);
             ok = ok && gflag[1] == expectCounter;                                                          // bumped only by an applied update
         }
         printf("[%2d] %-42s N=%3d C=%2d smem %6.1f KB: status %d/%d chi2 %.6g/%.6g  max|dm| %.2e  max|dP|/max|P| %.2e  %s\n", idx, cs.name, N, cs.C, smem / 1024.0,
