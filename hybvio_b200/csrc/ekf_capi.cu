@@ -1022,6 +1022,7 @@ int hv_ekf_visual_tracks(hv_ekf* e, const hv_track_obs* tracks, int ntracks, con
         for (int k = first; k < first + count; k++) {
             TmArgs a = base;
             a.ntracks = 1; a.trackOffset = k; a.counter = d_counter; a.counterMax = maxSucc;
+            a.pdl = k > first ? 1 : 0;                                // behind a cluster kernel of this chain: overlap the launch with its tail
             HV_CUDA(tm_launch(a, s));
             e->ctx->launches++;
             const hv_track_obs& o = tracks[k];

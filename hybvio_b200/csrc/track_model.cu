@@ -2,6 +2,7 @@
 // device (one CTA per track; body and algorithm notes in track_model.cuh). Replaces, for the EKF's visual updates, the host
 // sequence extractCameraPoseTrail -> Triangulator::triangulate -> prepareVisualUpdate of src/odometry/backend.cpp:1050-1160.
 #include "track_model.cuh"
+#include <stdlib.h>
 
 __global__ void __launch_bounds__(TM_NT, 2) hv_track_model_kernel(TmArgs a)
 {
@@ -17,6 +18,17 @@ cudaError_t tm_launch(const TmArgs& a, cudaStream_t s)
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    hv_track_model_kernel<<<a.ntracks, TM_NT, tm_smem_bytes(), s>>>(a);
+    static const bool pdlAllowed = getenv("HV_EKF_NO_PDL") == nullptr;
+    if (a.pdl && pdlAllowed) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(a.ntracks); cfg.blockDim = dim3(TM_NT); cfg.dynamicSmemBytes = tm_smem_bytes(); cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, hv_track_model_kernel, a);
+    }
+    TmArgs b = a;
+    b.pdl = 0;
+    hv_track_model_kernel<<<a.ntracks, TM_NT, tm_smem_bytes(), s>>>(b);
     return cudaGetLastError();
 }

@@ -260,6 +260,12 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
 {
     __shared__ int s_colmap[TM_MAXN], s_flag[4], s_code[TM_MAXOBS];
     const int tid = threadIdx.x, trk = blockIdx.x + a.trackOffset, lane = tid & 31, wrp = tid >> 5;
+#ifndef HV_EMU
+    if (a.pdl) {        // the next kernel of the chain may be scheduled now (it reads nothing of ours before its own wait); then wait for our predecessor
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+#endif
     if (a.counter && *(volatile const int*)a.counter >= a.counterMax) {      // uniform: written by a kernel that has completed
         if (tid == 0) { int* st = a.status + 4 * (size_t)trk; st[0] = TM_SKIPPED; st[1] = TM_VU_NOT_RUN; st[2] = 0; st[3] = 0; }
         return;

@@ -37,6 +37,8 @@ struct TmArgs {
     int trackOffset;            // CTA b handles track b + trackOffset (chains launch one track at a time out of a packed batch)
     int counterMax;             // with counter != NULL: skip (status TM_SKIPPED) once *counter >= counterMax
     const int* counter;         // successful updates so far in a chain issued without host round trips (hv_ekf_visual_tracks)
+    int pdl, padPdl;            // chain link: launched with programmatic stream serialisation (starts while the previous kernel of the
+                                // stream drains, waits in griddepcontrol.wait before it reads anything that kernel wrote)
 };
 
 #ifdef __CUDACC__
