@@ -123,6 +123,57 @@ int main()
             if (!ok) { fails++; std::printf("track %d (stereo %d): reference status %d, device %d  FAIL\n", t, stereo, (int)st, (int)dev[t].triangulateStatus); }
         }
         std::printf("stereo %d: %d tracks, %d triangulated, %d checks; worst |dH|/|H| %.2e |df| %.2e |dpf| %.2e\n", stereo, ntracks, nOk, nCheck, worstH, worstF, worstPf);
+        // ---- the whole per-track loop (backend.cpp:1012-1252, per-track mode): reference calls track by track on one copy of the
+        // filter, cudaVisualTracks (one device-gated chain) on another
+        {
+            const double chiR = 0.05, visR = 0.05; const int maxSucc = 5;
+            auto e1 = ekf->clone(), e2 = ekf->clone();
+            std::vector<int> rTri(ntracks, -1), rOut(ntracks, (int)VuOutlierStatus::NOT_COMPUTED), rUpd(ntracks, 0);
+            int succ = 0;
+            for (int t = 0; t < ntracks && succ < maxSucc; t++) {
+                CameraPoseTrail tr;
+                extractCameraPoseTrail(*e1, idx[t], params, stereo != 0, tr);
+                TriangulationArgsOut out;
+                const TriangulationArgsIn args { .imageFeatures = feats[t], .featureVelocities = vels[t], .trail = tr, .stereo = stereo != 0,
+                    .calculateDerivatives = true, .estimateImuCameraTimeShift = params.odometry.estimateImuCameraTimeShift };
+                TriangulatorStatus st = triangulator.triangulate(args, out);
+                rTri[t] = (int)st;
+                if (st != TriangulatorStatus::OK) continue;
+                if (stereo) {
+                    const size_t n = idx[t].size();
+                    for (size_t i = 0; i < n; ++i) { out.dpfdp[i] += out.dpfdp[i + n]; out.dpfdq[i] += out.dpfdq[i + n]; }
+                    out.dpfdp.resize(n); out.dpfdq.resize(n);
+                }
+                Eigen::MatrixXd H; Eigen::VectorXd f, y(2 * feats[t].size());
+                const PrepareVisualUpdateArgsIn pargs { .triangulationOut = out, .featureVelocities = vels[t], .trail = tr, .poseTrailIndex = idx[t],
+                    .stateDim = N, .useStereo = stereo != 0, .truncated = true, .mapPointOffset = -1,
+                    .estimateImuCameraTimeShift = params.odometry.estimateImuCameraTimeShift };
+                if (prepareVisualUpdate(pargs, H, f) != PREPARE_VU_OK) continue;
+                for (size_t i = 0; i < feats[t].size(); i++) y.segment<2>(2 * i) = feats[t][i];
+                const VuOutlierStatus os = e1->visualTrackOutlierCheck(H, f, y, chiR, -1.0);
+                rOut[t] = (int)os;
+                if (os == VuOutlierStatus::INLIER) { e1->updateVisualTrack(H, f, y, visR); rUpd[t] = 1; succ++; }
+            }
+            std::vector<CudaTrackResult> res;
+            const int dsucc = cudaVisualTracks(*e2, params, in, chiR, -1.0, visR, maxSucc, 0, res);
+            bool ok = dsucc == succ;
+            for (int t = 0; t < ntracks; t++) {
+                const int dTri = res[t].attempted ? (int)res[t].triangulateStatus : -1;
+                if (dTri != rTri[t] || (int)res[t].outlierStatus != rOut[t] || (int)res[t].updated != rUpd[t]) {
+                    ok = false;
+                    std::printf("  loop track %d: reference %d/%d/%d, chain %d/%d/%d  FAIL\n", t, rTri[t], rOut[t], rUpd[t], dTri, (int)res[t].outlierStatus, (int)res[t].updated);
+                }
+            }
+            const double em = (e1->getState() - e2->getState()).cwiseAbs().maxCoeff();
+            const double eP = (e1->getStateCovariance() - e2->getStateCovariance()).cwiseAbs().maxCoeff() / e1->getStateCovariance().cwiseAbs().maxCoeff();
+            // Five chained updates on the freshly built filter (prior variances noiseInitial^2 x noiseScale 1e4 against r = 0.05) are
+            // badly conditioned: rounding-level differences in H (1e-15) grow to 1e-8 in m -- also between two runs of the
+            // reference's own EKF fed with the two H (measured here on the CPU). Hence 1e-5 (the north-star gate is 1e-4 m); the
+            // 1e-9 bar is held by the single update above and, with a well-conditioned prior, by tests/test_zz_gpu_track_model.py.
+            ok = ok && em < 1e-5 && eP < 1e-6;
+            std::printf("  per-track loop vs device-gated chain: %d / %d updates, |dm| %.2e |dP|/|P| %.2e  %s\n", succ, dsucc, em, eP, ok ? "ok" : "FAIL");
+            fails += !ok;
+        }
     }
     std::printf(fails ? "FAILED (%d)\n" : "track model interface: all ok\n", fails);
     return fails;
