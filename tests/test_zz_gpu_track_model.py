@@ -109,6 +109,9 @@ def test_device_H_feeds_the_outlier_check_and_update(env):
     capi, hv, orc = env
     t = tri_common.make_track(3, npose=6, stereo=True)
     a, b = make_ekf(capi, hv, t), make_ekf(capi, hv, t)
+    A = np.random.RandomState(3).normal(0, 1, (a.N, a.N))
+    P0 = 1e-4 * (A @ A.T) / a.N + np.diag(np.full(a.N, 1e-4))          # a well-conditioned prior: the comparison is about H, not about the filter
+    a.upload(P=P0); b.upload(P=P0)
     a.set_camera_model(t["T1"], t["T2"], use_stereo=True)
     d = a.track_models([(t["idx"], t["ip"], t["vel"])])[0]
     o = orc.track_model(t["m"], t["trail"], True, t["idx"], t["T1"], t["T2"], t["ip"], t["vel"], True)
@@ -120,6 +123,7 @@ def test_device_H_feeds_the_outlier_check_and_update(env):
     assert np.abs(ma - mb).max() < 1e-9 and np.abs(Pa - Pb).max() / np.abs(Pb).max() < 1e-9
     # the asynchronous update-only mode on a second pair of filters
     a2, b2 = make_ekf(capi, hv, t), make_ekf(capi, hv, t)
+    a2.upload(P=P0); b2.upload(P=P0)
     a2.set_camera_model(t["T1"], t["T2"], use_stereo=True)
     d2 = a2.track_models([(t["idx"], t["ip"], t["vel"])], download=False)[0]
     assert a2.visual_track(d2, 0.02, mode=1) is None
