@@ -18,6 +18,36 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def cpu_reference_loop(tracks, base, p, P0, chi_r, vis_r, reps=3):
+    """The same loop with the reference's own code on the host: triangulation.cpp + prepareVisualUpdate (oracle/_ref/libref_tri.so)
+    and ekf.cpp (libref_ekf.so), one thread, as Session::trackerVisualUpdate runs it. None where oracle/_ref was not built."""
+    from oracle import ekf_oracle, tri_oracle
+    if not (tri_oracle.have_ref() and os.path.exists(ekf_oracle.REF_SO)):
+        return None
+    tri, best, dec = tri_oracle.RefTri(), [], []
+    for _ in range(reps):
+        kf = ekf_oracle.RefEKF(p)
+        kf.upload(m=base["m"], P=P0)
+        dec, succ = [], 0
+        t0 = time.perf_counter()
+        for idx, ip, vel in tracks:
+            if succ >= 5:
+                break
+            m, _P = kf.download()
+            o = tri.track_model(m, base["trail"], True, idx, base["T1"], base["T2"], ip, vel, True)
+            st = 1
+            if o["tri_status"] == 0 and o["vu_status"] == 0:
+                st, _ = kf.visual_check(o["H"], o["f"], np.asarray(ip).ravel(), chi_r, -1.0)
+                if st == 0:
+                    kf.visual_update(o["H"], o["f"], np.asarray(ip).ravel(), vis_r)
+                    succ += 1
+            dec.append((o["tri_status"], st))
+        best.append(time.perf_counter() - t0)
+        kf.close()
+    return {"us": round(float(np.median(best)) * 1e6, 1), "successful_updates": succ, "decisions": dec,
+            "note": "reference triangulation.cpp + ekf.cpp through ctypes, one host thread; includes a state download per track"}
+
+
 def visual_update_loop(capi, hv, base, p, ntracks=20, reps=20):
     """Session::trackerVisualUpdate's per-track loop (backend.cpp:1012-1252; 20 candidate tracks, at most 5 successful updates)
     three ways through the C ABI, same tracks and start state: (a) device-gated chain hv_ekf_visual_tracks, one synchronisation;
@@ -76,6 +106,7 @@ def visual_update_loop(capi, hv, base, p, ntracks=20, reps=20):
             state = ekf.download()
         return float(np.median(best)) * 1e6, state, ret
 
+    cpu = cpu_reference_loop(tracks, base, p, P0, chi_r, vis_r)
     us_a, st_a, ret_a = timed(lambda: chain(0))
     us_b, st_b, _ = timed(lambda: chain(4))
     us_c, st_c, ret_c = timed(per_track)
@@ -83,7 +114,9 @@ def visual_update_loop(capi, hv, base, p, ntracks=20, reps=20):
     ekf.close()
     return {"tracks": ntracks, "max_successful_updates": 5, "successful_updates": ret_a[1],
             "chain_one_sync_us": round(us_a, 1), "chain_sync_every_4_us": round(us_b, 1), "per_track_calls_us": round(us_c, 1),
+            "cpu_reference_loop": cpu,
             "same_decisions": bool(seq == ret_c[0] and ret_a[1] == ret_c[1]),
+            "same_decisions_as_cpu_reference": (None if cpu is None else bool([tuple(x) for x in cpu["decisions"]] == seq[:len(cpu["decisions"])])),
             "max_state_difference_chain_vs_per_track": float(max(np.abs(st_a[0] - st_c[0]).max(), np.abs(st_b[0] - st_c[0]).max())),
             "note": "median wall-clock of the whole loop through ctypes, state re-uploaded before every repetition (outside the timed region)"}
 
