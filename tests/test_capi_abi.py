@@ -37,3 +37,15 @@ def test_no_cpu_fallback_without_gpu():
 def test_version_string():
     from hybvio_b200 import capi
     assert b"sm_100a" in capi.load().hv_version()
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: include/hybvio_b200.h must compile as C (no C++-isms, no torch / CUDA types)."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "hybvio_b200.h"\nint main(void) { hv_camera_model c; hv_visual_update_params p; hv_track_result r; hv_ekf_op o; '
+                   '(void)c; (void)p; (void)r; (void)o; return 0; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"), "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
