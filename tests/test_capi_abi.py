@@ -49,3 +49,34 @@ def test_header_is_plain_c99(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"), "-fsyntax-only", str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """hybvio_b200/capi.py mirrors the structs of include/hybvio_b200.h by hand: sizes and field offsets must agree with what
+    the C compiler lays out."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from hybvio_b200 import capi
+    pairs = {"hv_camera_model": capi.CameraModel, "hv_track_obs": capi.TrackObs, "hv_track_model": capi.TrackModel,
+             "hv_visual_update_params": capi.VisualUpdateParams, "hv_track_result": capi.TrackResult, "hv_ekf_op": capi.EkfOp,
+             "hv_ekf_params": capi.EkfParams, "hv_lk_job": capi.LkJob}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hybvio_b200.h"', 'int main(void) {']
+    for cname, py in pairs.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in py._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0; }']
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(root, "include"), str(src), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        a, b, c = ln.split()
+        got[(a, b)] = int(c)
+    for cname, py in pairs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(py), cname
+        for fname, _ in py._fields_:
+            assert got[(cname, fname)] == getattr(py, fname).offset, (cname, fname)
