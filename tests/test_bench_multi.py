@@ -43,3 +43,20 @@ def test_workload_definition_matches_baseline_config():
     assert min(seen) == 0 and max(seen) == bench.POOL_FRAMES - 1
     pool_mb = bench.POOL_FRAMES * 2 * bench.W * bench.H / 1e6
     assert pool_mb + 40 > 126                                                   # inputs larger than L2
+
+
+def test_reference_arm_json_contract():
+    """`bench.py --impl reference` (the reference's own CPU path from oracle/_ref, or the C port where that is missing) runs on host
+    cores only and prints the contract's line: same metric / unit / config as the CUDA arm, impl = reference, e2e with zero copies."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("stereo frames/sec") and d["unit"] == "frames/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["value"] > 0
+    assert "workload" in d["config"] and d["data"] == "synthetic" and d["vs_baseline"] is None
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and abs(cb["value"] - d["value"]) < 1e-6 * d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["unit"] == "frames/s"
