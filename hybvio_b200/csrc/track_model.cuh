@@ -462,17 +462,18 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
             }
         }
         __syncthreads();
-        // C4: 63 sums over the observations: generic (18), pose-0 columns (42), time column (3)
-        if (tid < 63) {
-            const double* src; int stride;
-            if (tid < 18) { src = GEN + tid; stride = 18; }
-            else if (tid < 60) { src = P0 + (tid - 18); stride = 42; }
-            else { src = TMV + (tid - 60); stride = 3; }
-            double s0 = 0, s1 = 0;
-            int i = 0;
-            for (; i + 1 < n; i += 2) { s0 += src[(size_t)i * stride]; s1 += src[(size_t)(i + 1) * stride]; }
-            if (i < n) s0 += src[(size_t)i * stride];
-            RED[tid] = s0 + s1;
+        // C4: 63 sums over the observations: generic (18), pose-0 columns (42), time column (3); four lanes per sum
+        {
+            const int sidx = tid >> 2, part = tid & 3;
+            const double* src = GEN; int stride = 0;
+            if (sidx < 18) { src = GEN + sidx; stride = 18; }
+            else if (sidx < 60) { src = P0 + (sidx - 18); stride = 42; }
+            else if (sidx < 63) { src = TMV + (sidx - 60); stride = 3; }
+            double sacc = 0.0;
+            if (sidx < 63) for (int i = part; i < n; i += 4) sacc += src[(size_t)i * stride];
+            sacc += __shfl_sync(0xffffffffu, sacc, lane ^ 1);
+            sacc += __shfl_sync(0xffffffffu, sacc, lane ^ 2);
+            if (sidx < 63 && part == 0) RED[sidx] = sacc;
         }
         __syncthreads();
         // C5: d pfi_j += X^-1 (w_j - a_j)   (:322-327 with the two solves of the reference merged into one)
