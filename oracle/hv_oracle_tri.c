@@ -480,3 +480,15 @@ int orc_track_model(const double* m, int trail, int useStereo, const int* poseTr
     free(tr_); free(d);
     return 0;
 }
+
+/* Entry points for the reference's own known-answer tests of the helpers (test/triangulation.cpp:477-485 "pinv",
+ * :487-519 "triangulateWithTwoCameras"): row-major 3x2 -> 2x3; poses as p[3], R[9] row-major. */
+void orc_pinv32(const double* A, double* iA) { pinv32(A, iA); }
+void orc_two_cameras_point(const double* p0, const double* R0, const double* p1, const double* R1, const double* ip0, const double* ip1, double* pf)
+{
+    tri_pose a, b; double d[15][3];
+    memset(&a, 0, sizeof(a)); memset(&b, 0, sizeof(b));
+    memcpy(a.p, p0, sizeof(a.p)); memcpy(a.R, R0, sizeof(a.R)); memcpy(b.p, p1, sizeof(b.p)); memcpy(b.R, R1, sizeof(b.R));
+    const double zero[2] = {0, 0};
+    two_cameras(&a, &b, ip0, ip1, zero, zero, 0, pf, d);
+}

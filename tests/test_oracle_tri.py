@@ -60,6 +60,31 @@ def test_oracle_matches_reference_golden_vectors(orc):
     assert seen == {0, 2, 3, 4}        # OK, BEHIND, BAD_COND, NO_CONVERGENCE all exercised
 
 
+def test_known_answers_of_the_reference_test_suite(orc):
+    """The known-answer tests test/triangulation.cpp holds for this path: "visual" (Matlab-generated track, :56-167), "pinv"
+    (Matlab pinv, :477-485), "triangulateWithTwoCameras" (right triangle, :487-519); with the reference's own tolerances."""
+    import ctypes
+    k = tri_common.reference_visual_kat()
+    impls = [orc] + ([tri_oracle.RefTri()] if tri_oracle.have_ref() else [])
+    for impl in impls:
+        o = impl.track_model(k["m"], k["trail"], False, k["idx"], k["T1"], k["T2"], k["ip"], k["vel"], True)
+        assert o["tri_status"] == 0 and o["vu_status"] == 0
+        assert np.abs(o["pf"] - k["pf_expected"]).sum() < 1e-5
+        assert o["H"].shape == (20, 83)                       # 10 observations, truncated after trail slot 8 (CAM + 7 * 8 + 7)
+    L = orc.lib
+    A = np.array([[1.0, 4.0], [3.0, 2.0], [-1.0, -3.0]])      # = m.transpose() of the reference test
+    iA = np.zeros((2, 3))
+    L.orc_pinv32(A.ctypes.data_as(ctypes.c_void_p), iA.ctypes.data_as(ctypes.c_void_p))
+    expect = np.array([[-0.153333, 0.206667], [0.406667, -0.113333], [0.0666667, -0.133333]]).T
+    assert np.abs(iA - expect).sum() < 1e-5
+    assert np.abs(iA - np.linalg.pinv(A)).max() < 1e-14
+    pf = np.zeros(3)
+    eye = np.eye(3).ravel()
+    args = [np.array([1.0, 1.0, 0.0]), eye, np.array([1.0, 2.0, 0.0]), eye, np.array([0.0, 1.0]), np.array([0.0, 0.0]), pf]
+    L.orc_two_cameras_point(*[x.ctypes.data_as(ctypes.c_void_p) for x in args])
+    assert np.abs(pf - np.array([0.0, 1.0, 1.0])).sum() < 1e-5
+
+
 def test_measurement_model_is_consistent_with_the_scene(orc):
     """Independent of the reference: on a nearly clean track the triangulated point is the true point, the predicted observations
     are the observations, and H is the total derivative of the predictions w.r.t. the pose states, the re-triangulated point

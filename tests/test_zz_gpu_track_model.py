@@ -103,6 +103,20 @@ def test_track_models_match_reference_golden_vectors(env):
     assert seen == {0, 2, 3, 4}
 
 
+def test_known_answer_of_the_reference_test_suite(env):
+    """TEST_CASE "visual" of the reference's test/triangulation.cpp (:56-167): a Matlab-generated track; the reference requires
+    TriangulatorStatus::OK and sum |pf - pf_e| < 1e-5."""
+    capi, hv, orc = env
+    k = tri_common.reference_visual_kat()
+    e = make_ekf(capi, hv, k)
+    e.set_camera_model(k["T1"], None, use_stereo=False, estimate_time_shift=True)
+    d = e.track_models([(k["idx"], k["ip"], k["vel"])])[0]
+    assert d["tri_status"] == 0 and d["vu_status"] == 0 and d["H"].shape == (20, 83)
+    assert np.abs(d["pf"] - k["pf_expected"]).sum() < 1e-5
+    compare(d, orc.track_model(k["m"], k["trail"], False, k["idx"], k["T1"], k["T2"], k["ip"], k["vel"], True), "visual KAT")
+    e.close()
+
+
 def test_device_H_feeds_the_outlier_check_and_update(env):
     """H, f, y never leave the device: check + update from the pointers hv_ekf_track_models returns equals the same calls with
     the oracle's H uploaded from the host."""
