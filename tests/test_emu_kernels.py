@@ -46,8 +46,8 @@ def test_track_model_kernel_body_on_host_emulator(tmp_path):
                            os.path.join(ROOT, "tools", "emu", "emu_track_model.cpp"), obj, "-lm", "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count("  ok") == 44 and "FAIL" not in out.stdout          # 39 compared with the oracle (incl. 21-pose tracks) + 5 skipped by the success counter
-    assert "OK 29 BEHIND 6 BAD_COND 3 NO_CONVERGENCE 1" in out.stdout
+    assert out.stdout.count("  ok") == 45 and "FAIL" not in out.stdout          # 40 compared with the oracle (incl. 21-pose tracks, the reference's KAT) + 5 skipped by the success counter
+    assert "OK 30 BEHIND 6 BAD_COND 3 NO_CONVERGENCE 1" in out.stdout and 'reference KAT "visual"' in out.stdout
 
 
 def test_track_model_ldlt_matches_oracle(tmp_path):

@@ -71,14 +71,45 @@ static Scene make_scene(int seed, int npose, int stereo, double noise, double de
     return s;
 }
 
+// TEST_CASE "visual" of the reference's test/triangulation.cpp (:56-167): Matlab-generated poses and track, expected point
+static Scene kat_scene()
+{
+    static const double poses[70] = {
+        -1.115954259678003, -2.830379937574711, 0.360953864756080, 0.228275363465427, -0.064194730744503, -0.594104812214096, -0.772824444840030,
+        -1.080393253042482, -2.763692958718615, 0.332645073392916, 0.196322489942363, -0.083909476935720, -0.628312037667580, -0.752388564841313,
+        -1.053635192163148, -2.698599740902574, 0.304049959330811, 0.171347617609120, -0.090804163156838, -0.627022749727822, -0.749919482080305,
+        -1.031838101194812, -2.623526076445418, 0.281408008477340, 0.155625729177218, -0.090380891656242, -0.639892913358913, -0.737146980096418,
+        -1.009828260492951, -2.544268915819571, 0.273217018299048, 0.153209864083974, -0.090234014840705, -0.636707261073876, -0.737354342707954,
+        -0.986215006493242, -2.468647298253558, 0.272275808868746, 0.157856184323099, -0.083435652262512, -0.606327170014471, -0.761376924834563,
+        -0.961600705821358, -2.396757542411821, 0.267737813520921, 0.163130732364498, -0.079219306292358, -0.594278868691105, -0.765754228906657,
+        -0.933757923541281, -2.325217937044675, 0.255438002606821, 0.172957779390792, -0.084991869290214, -0.593937386185525, -0.762521999377893,
+        -0.898272888273739, -2.253889975199411, 0.239108878766994, 0.189256086747472, -0.090322497349436, -0.593833321653932, -0.758101862911017,
+        -0.858474881652736, -2.184122374378553, 0.228789583088852, 0.204536006494471, -0.092660683000154, -0.580153035798419, -0.761692686677209};
+    static const double uv[20] = {-0.182574266004879, -0.078574171780591, -0.158898685463446, -0.007691759819452, -0.131230597106084, -0.013212139610991,
+        -0.110637420135181, 0.020800938142075, -0.107508132406555, 0.002175057216783, -0.108465120810051, -0.080045047328712, -0.111911566078740, -0.103534929832195,
+        -0.135452929226407, -0.099277664417604, -0.165840298753357, -0.093731544303972, -0.188661852179662, -0.133908509900881};
+    Scene s; s.trail = 20; s.npose = 10; s.stereo = 0;
+    s.m.assign(160, 0.0);
+    for (int r = 0; r < 3; r++) s.m[r] = poses[r];
+    for (int r = 0; r < 4; r++) s.m[6 + r] = poses[3 + r];
+    for (int i = 0; i < 9; i++) for (int r = 0; r < 7; r++) s.m[20 + 7 * i + r] = poses[7 * (i + 1) + r];
+    memset(s.T1, 0, sizeof(s.T1)); s.T1[0] = 1; s.T1[5] = -1; s.T1[10] = -1; s.T1[15] = 1;      // diag(1, -1, -1, 1): the default imuToCameraMatrix
+    memcpy(s.T2, s.T1, sizeof(s.T1));
+    for (int i = 0; i < 10; i++) s.idx.push_back(i);
+    s.ip.assign(uv, uv + 20); s.vel.assign(20, 0.1);
+    return s;
+}
+
 int main()
 {
     int fails = 0, hist[8] = {0};
-    const int ncase = 44;                          // 40..43: the largest tracks the kernel accepts (21 poses, 42 observations in stereo)
+    const int ncase = 45;                          // 40..43: the largest tracks the kernel accepts (21 poses, 42 observations in stereo)
     for (int cs = 0; cs < ncase; cs++) {
-        const int stereo = cs % 2 == 0, npose = cs >= 40 ? (cs < 42 ? TM_MAXPOSE : TM_MAXPOSE - 1) : 2 + cs % 9, corrupt = cs < 18 || cs >= 40 ? 0 : 1 + cs % 4, ets = cs % 5 != 3;
+        const bool kat = cs == 44;                 // the reference's own known-answer track (mono, 10 poses, time shift on)
+        const int stereo = kat ? 0 : cs % 2 == 0, npose = kat ? 10 : cs >= 40 ? (cs < 42 ? TM_MAXPOSE : TM_MAXPOSE - 1) : 2 + cs % 9, corrupt = cs < 18 || cs >= 40 ? 0 : 1 + cs % 4,
+                  ets = kat ? 1 : cs % 5 != 3;
         const double noises[3] = {1e-3, 3e-3, 1e-2}, depths[4] = {2, 5, 15, 40};
-        Scene s = make_scene(cs, npose, stereo, noises[cs % 3], depths[cs % 4], corrupt);
+        Scene s = cs == 44 ? kat_scene() : make_scene(cs, npose, stereo, noises[cs % 3], depths[cs % 4], corrupt);
         const int N = (int)s.m.size(), nobs = npose * (stereo ? 2 : 1);
         // oracle
         int tri, vu, rows, cols; double pf[3], depth;
@@ -128,6 +159,12 @@ int main()
             }
             const double tol = dmax < 1e6 ? 1e-9 : 1e-6;
             ok = ok && ep < tol && ed / dmax < tol && eh / hmax < tol && ef < tol;
+        }
+        if (kat) {                                 // test/triangulation.cpp:92, 167: sum |pf - pf_e| < 1e-5
+            const double pfe[3] = {-2.32842, -8.02612, -0.619833};
+            const double dk = std::fabs(opf[4 * trk] - pfe[0]) + std::fabs(opf[4 * trk + 1] - pfe[1]) + std::fabs(opf[4 * trk + 2] - pfe[2]);
+            ok = ok && kst[0] == 0 && dk < 1e-5;
+            printf("reference KAT \"visual\": sum |pf - pf_e| = %.2e\n", dk);
         }
         // neighbours untouched
         ok = ok && st[0] == -7 && st[8] == -7 && oH[0] == 7.0 && oH[2 * Hs] == 7.0;
