@@ -492,3 +492,6 @@ void orc_two_cameras_point(const double* p0, const double* R0, const double* p1,
     const double zero[2] = {0, 0};
     two_cameras(&a, &b, ip0, ip1, zero, zero, 0, pf, d);
 }
+/* test/util.cpp:9-57 "quat2rmat", "quat2rmat_d"; :97-109 "cond" (rcond_ldlt of the identity is 1) */
+void orc_quat2rmat_d(const double* q, double* R, double* dR) { double d[4][9]; quat2rmat_d(q, R, d); memcpy(dR, d, sizeof(d)); }
+double orc_rcond_ldlt3(const double* A) { ldlt3 X; ldlt3_compute(A, &X); return ldlt3_rcond(&X); }

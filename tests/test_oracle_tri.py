@@ -78,6 +78,20 @@ def test_known_answers_of_the_reference_test_suite(orc):
     expect = np.array([[-0.153333, 0.206667], [0.406667, -0.113333], [0.0666667, -0.133333]]).T
     assert np.abs(iA - expect).sum() < 1e-5
     assert np.abs(iA - np.linalg.pinv(A)).max() < 1e-14
+    # test/util.cpp:9-57: quat2rmat / quat2rmat_d against Matlab (q = rotm2quat(rotx(15) roty(3) rotz(-5)))
+    q = np.array([0.990310843256666, 0.129225220713441, 0.031619820909086, -0.039817872689419])
+    R, dR = np.zeros(9), np.zeros(36)
+    L.orc_quat2rmat_d(q.ctypes.data_as(ctypes.c_void_p), R.ctypes.data_as(ctypes.c_void_p), dR.ctypes.data_as(ctypes.c_void_p))
+    rmat_e = np.array([0.994829447880333, 0.087036298831283, 0.052335956242944, -0.070691985487699, 0.963430758692103, -0.258464342596353,
+                       -0.072917849789463, 0.253428206582672, 0.964602058514480])
+    a, b, c, d = 1.980621686513332, 0.258450441426882, 0.063239641818172, 0.079635745378838
+    dR_e = np.array([[a, d, c, -d, a, -b, -c, b, a], [b, c, -d, c, -b, -a, -d, a, -b], [-c, b, a, b, c, -d, -a, -d, -c], [d, -a, b, a, d, c, b, c, -d]])
+    assert np.abs(R - rmat_e).sum() < 1e-5
+    for i in range(4):
+        assert np.abs(dR[9 * i:9 * i + 9] - dR_e[i]).sum() < 1e-5
+    # test/util.cpp:105-107: the LDLT-based reciprocal condition number of the identity is exactly 1
+    L.orc_rcond_ldlt3.restype = ctypes.c_double
+    assert L.orc_rcond_ldlt3(np.eye(3).ravel().ctypes.data_as(ctypes.c_void_p)) == 1.0
     pf = np.zeros(3)
     eye = np.eye(3).ravel()
     args = [np.array([1.0, 1.0, 0.0]), eye, np.array([1.0, 2.0, 0.0]), eye, np.array([0.0, 1.0]), np.array([0.0, 0.0]), pf]
