@@ -60,3 +60,12 @@ def test_reference_arm_json_contract():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and abs(cb["value"] - d["value"]) < 1e-6 * d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["unit"] == "frames/s"
+
+
+def test_next_row_report_cannot_take_the_bench_line_down():
+    """bench.py attaches the track-model measurement from a separate process; without a GPU (here) that process fails, and the hook
+    must come back with an error entry instead of raising."""
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.next_row_track_model()
+    assert isinstance(r, dict) and "error" in r and "hv_ctx_create" in r["error"]
