@@ -644,11 +644,11 @@ def run_ours(args):
 
 def next_row_track_model():
     """SURVEY.md 8(f) N1 (triangulation + prepareVisualUpdate on the device): measured and checked against the oracle by
-    tools/track_model_bench.py in a SEPARATE process after the headline measurement, so that nothing it does can disturb
+    tests/tools/track_model_bench.py in a SEPARATE process after the headline measurement, so that nothing it does can disturb
     the line above; not part of value / e2e."""
     import subprocess
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "track_model_bench.py")], capture_output=True, text=True, timeout=180)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "track_model_bench.py")], capture_output=True, text=True, timeout=180)
         if r.returncode != 0:
             return {"error": (r.stderr or r.stdout)[-400:]}
         return json.loads(r.stdout.strip().splitlines()[-1])

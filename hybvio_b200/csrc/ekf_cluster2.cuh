@@ -21,7 +21,7 @@
 // CTA takes the same branch; every path that leaves the kernel after the first exposure of shared memory to the
 // neighbours passes a final cluster barrier (a CTA must not exit while its shared memory may still be read).
 //
-// Written against the primitives tools/emu can run on the host (tools/emu/emu_update.cpp runs this body against the C
+// Written against the primitives tests/emu can run on the host (tests/emu/emu_update.cpp runs this body against the C
 // oracle without a GPU).
 #pragma once
 #include "ekf.cuh"

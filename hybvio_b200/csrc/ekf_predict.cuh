@@ -18,8 +18,8 @@
 // The two off-diagonal strips of P are transformed once at the end with Dacc = D_{c-1} ... D_0 (algebraically what
 // the reference does sample by sample; fp64 differences are association-order rounding, ~1e-16 relative).
 //
-// Written against the small set of CUDA primitives that tools/emu/ can run on the host (threads, __syncthreads,
-// __syncwarp, full-warp shuffles), so that the indexing logic is testable without a GPU (tools/emu/emu_predict.cpp).
+// Written against the small set of CUDA primitives that tests/emu/ can run on the host (threads, __syncthreads,
+// __syncwarp, full-warp shuffles), so that the indexing logic is testable without a GPU (tests/emu/emu_predict.cpp).
 #pragma once
 #include "ekf.cuh"
 #include "hv_dmma.cuh"

@@ -25,8 +25,8 @@
 // Every thread factorises the same 3x3 normal matrix itself (pivoted LDL^T as Eigen's LDLT, the rcond estimate of Eigen's
 // ConditionEstimator: the BAD_COND gate has to see the same number) instead of waiting for a broadcast.
 //
-// Written against the CUDA subset tools/emu runs on the host (threads, __syncthreads, full-warp shuffles):
-// tools/emu/emu_track_model.cpp runs this body against oracle/hv_oracle_tri.c without a GPU.
+// Written against the CUDA subset tests/emu runs on the host (threads, __syncthreads, full-warp shuffles):
+// tests/emu/emu_track_model.cpp runs this body against oracle/hv_oracle_tri.c without a GPU.
 #pragma once
 #include <float.h>
 #include <math.h>

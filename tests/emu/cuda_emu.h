@@ -1,4 +1,4 @@
-// tools/emu/cuda_emu.h -- a very small host emulation of the CUDA execution model, for testing kernel LOGIC without a
+// tests/emu/cuda_emu.h -- a very small host emulation of the CUDA execution model, for testing kernel LOGIC without a
 // GPU (this container has none; GPU minutes are scarce). Test infrastructure only -- never part of the product.
 //
 // Every CUDA thread of ONE CTA is an OS thread; __syncthreads / __syncwarp are std::barrier, full-warp shuffles go

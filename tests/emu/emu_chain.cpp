@@ -1,4 +1,4 @@
-// tools/emu/emu_chain.cpp -- the device side of hv_ekf_visual_tracks on the host emulator: for a list of tracks, in order,
+// tests/emu/emu_chain.cpp -- the device side of hv_ekf_visual_tracks on the host emulator: for a list of tracks, in order,
 //   tm_body (one CTA, counter gate)  ->  ek2_body check (gated by the model's status word and the success counter, H staged late)
 //   ->  ek2_body update (gated by the check's result word, bumps the counter),
 // all kernels talking through words in "global memory" (a shared mapping) exactly as the chain on the GPU does, and compares the

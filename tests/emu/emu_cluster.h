@@ -1,4 +1,4 @@
-// tools/emu/emu_cluster.h -- thread-block CLUSTER on the host emulator: one forked process per CTA (so that `static`
+// tests/emu/emu_cluster.h -- thread-block CLUSTER on the host emulator: one forked process per CTA (so that `static`
 // shared variables stay per-CTA), "global memory" and every CTA's dynamic shared memory in one MAP_SHARED arena mapped
 // before the fork (same addresses everywhere, hence cluster.map_shared_rank is pointer arithmetic), cluster.sync() on a
 // process-shared pthread barrier. Test infrastructure only.

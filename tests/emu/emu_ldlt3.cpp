@@ -1,4 +1,4 @@
-// tools/emu/emu_ldlt3.cpp -- the scalar 3x3 pivoted LDL^T / solve / rcond of track_model.cuh against the array version of the
+// tests/emu/emu_ldlt3.cpp -- the scalar 3x3 pivoted LDL^T / solve / rcond of track_model.cuh against the array version of the
 // oracle (oracle/hv_oracle_tri.c, included here for its static functions) on 200k random symmetric matrices: SPD, badly scaled,
 // tied diagonals, indefinite; all six pivot patterns occur. Test infrastructure.
 #include "cuda_emu.h"

@@ -1,6 +1,6 @@
-// tools/emu/emu_predict.cpp -- runs the REAL body of ekf_predict_kernel (hybvio_b200/csrc/ekf_predict.cuh) on the host
+// tests/emu/emu_predict.cpp -- runs the REAL body of ekf_predict_kernel (hybvio_b200/csrc/ekf_predict.cuh) on the host
 // emulator and compares it with the C oracle (oracle/hv_oracle_ekf.c: orc_ekf_predict, sample by sample).
-//   g++ -std=c++20 -O1 -pthread -Itools/emu/stubs -Itools/emu -Ihybvio_b200/csrc tools/emu/emu_predict.cpp oracle/hv_oracle_ekf.c -o build/emu_predict
+//   g++ -std=c++20 -O1 -pthread -Itests/emu/stubs -Itests/emu -Ihybvio_b200/csrc tests/emu/emu_predict.cpp oracle/hv_oracle_ekf.c -o build/emu_predict
 #include "cuda_emu.h"
 #define EKF_PMARK(i) do { } while (0)
 #include "ekf_predict.cuh"

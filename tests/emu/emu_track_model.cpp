@@ -1,6 +1,6 @@
-// tools/emu/emu_track_model.cpp -- runs the REAL body of hv_track_model_kernel (hybvio_b200/csrc/track_model.cuh) on the host
+// tests/emu/emu_track_model.cpp -- runs the REAL body of hv_track_model_kernel (hybvio_b200/csrc/track_model.cuh) on the host
 // emulator and compares it with the C oracle (oracle/hv_oracle_tri.c: orc_track_model) on synthetic tracks.
-//   g++ -std=c++20 -O1 -pthread -Itools/emu/stubs -Itools/emu -Ihybvio_b200/csrc tools/emu/emu_track_model.cpp oracle/hv_oracle_tri.c -o build/emu_track_model
+//   g++ -std=c++20 -O1 -pthread -Itests/emu/stubs -Itests/emu -Ihybvio_b200/csrc tests/emu/emu_track_model.cpp oracle/hv_oracle_tri.c -o build/emu_track_model
 #include <algorithm>
 #include "cuda_emu.h"
 #include "track_model.cuh"

@@ -1,4 +1,4 @@
-// tools/emu/emu_update.cpp -- runs the REAL body of the cluster update kernel (hybvio_b200/csrc/ekf_cluster2.cuh) on the
+// tests/emu/emu_update.cpp -- runs the REAL body of the cluster update kernel (hybvio_b200/csrc/ekf_cluster2.cuh) on the
 // host emulator (one process per CTA, distributed shared memory = a shared mapping) and compares it with the C oracle.
 #include "emu_cluster.h"
 #include "ekf_cluster2.cuh"

@@ -1,4 +1,4 @@
-// stub of <cuda_runtime.h> for the host emulation build (tools/emu)
+// stub of <cuda_runtime.h> for the host emulation build (tests/emu)
 #pragma once
 #include <cstddef>
 typedef void* cudaStream_t;

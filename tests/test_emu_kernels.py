@@ -1,5 +1,5 @@
 """CPU test: the REAL body of the fused predict kernel (hybvio_b200/csrc/ekf_predict.cuh) compiled for the host thread
-emulator (tools/emu) and compared with the C oracle -- catches indexing / staging / protocol mistakes without a GPU.
+emulator (tests/emu) and compared with the C oracle -- catches indexing / staging / protocol mistakes without a GPU.
 The GPU parity tests (test_gpu_ekf.py) remain the authority on the compiled sm_100a code."""
 import os
 import subprocess
@@ -11,9 +11,9 @@ def test_predict_kernel_body_on_host_emulator(tmp_path):
     exe = str(tmp_path / "emu_predict")
     obj = str(tmp_path / "orc_ekf.o")
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", "hv_oracle_ekf.c"), "-o", obj])
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tools", "emu", "stubs"),
-                           "-I" + os.path.join(ROOT, "tools", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
-                           os.path.join(ROOT, "tools", "emu", "emu_predict.cpp"), obj, "-lm", "-o", exe])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "emu", "emu_predict.cpp"), obj, "-lm", "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count(" ok") == 12 and "FAIL" not in out.stdout
@@ -27,9 +27,9 @@ def test_cluster_update_kernel_body_on_host_emulator(tmp_path):
     exe = str(tmp_path / "emu_update")
     obj = str(tmp_path / "orc_ekf.o")
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", "hv_oracle_ekf.c"), "-o", obj])
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tools", "emu", "stubs"),
-                           "-I" + os.path.join(ROOT, "tools", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
-                           os.path.join(ROOT, "tools", "emu", "emu_update.cpp"), obj, "-lm", "-o", exe])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "emu", "emu_update.cpp"), obj, "-lm", "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count(" ok") == 23 and "FAIL" not in out.stdout
@@ -41,9 +41,9 @@ def test_track_model_kernel_body_on_host_emulator(tmp_path):
     exe = str(tmp_path / "emu_track_model")
     obj = str(tmp_path / "orc_tri.o")
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", "hv_oracle_tri.c"), "-o", obj])
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tools", "emu", "stubs"),
-                           "-I" + os.path.join(ROOT, "tools", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
-                           os.path.join(ROOT, "tools", "emu", "emu_track_model.cpp"), obj, "-lm", "-o", exe])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "emu", "emu_track_model.cpp"), obj, "-lm", "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("  ok") == 45 and "FAIL" not in out.stdout          # 40 compared with the oracle (incl. 21-pose tracks, the reference's KAT) + 5 skipped by the success counter
@@ -54,9 +54,9 @@ def test_track_model_ldlt_matches_oracle(tmp_path):
     """The register-resident 3x3 pivoted LDL^T of the track-model kernel vs the oracle's (Eigen's algorithm) on 200k random
     symmetric matrices: same pivots, backward error at rounding level."""
     exe = str(tmp_path / "emu_ldlt3")
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fpermissive", "-w", "-I" + os.path.join(ROOT, "tools", "emu", "stubs"),
-                           "-I" + os.path.join(ROOT, "tools", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
-                           os.path.join(ROOT, "tools", "emu", "emu_ldlt3.cpp"), "-lm", "-o", exe])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fpermissive", "-w", "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "emu", "emu_ldlt3.cpp"), "-lm", "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "pivot mismatches 0;" in out.stdout, out.stdout + out.stderr
 
@@ -71,9 +71,9 @@ def test_device_gated_chain_on_host_emulator(tmp_path):
         obj = str(tmp_path / (name + ".o"))
         subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", name + ".c"), "-o", obj])
         objs.append(obj)
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tools", "emu", "stubs"),
-                           "-I" + os.path.join(ROOT, "tools", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
-                           os.path.join(ROOT, "tools", "emu", "emu_chain.cpp"), *objs, "-lm", "-o", exe])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "emu", "emu_chain.cpp"), *objs, "-lm", "-o", exe])
     for args, tag in (([], "chain: 3 updates (oracle 3)"), (["fused"], "chain (fused check+update): 3 updates (oracle 3)")):
         out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=900)
         assert out.returncode == 0, out.stdout + out.stderr

@@ -1,5 +1,5 @@
 import sys, os, ctypes, numpy as np
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import ekf_script, ekf_common as C
 from hybvio_b200 import capi
 from oracle import ekf_oracle

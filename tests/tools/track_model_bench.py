@@ -1,7 +1,7 @@
 """Measures the per-track measurement-model kernel (hv_track_model_kernel: triangulation + prepareVisualUpdate on the device,
 SURVEY.md 8(f) N1) on cuda:0 and checks it against the C oracle in the same run. Prints ONE JSON object. bench.py runs this as a
 separate process after its own measurement (a problem here cannot disturb the headline line); it can also be run by hand:
-    python tools/track_model_bench.py [--tracks 150] [--reps 50]
+    python tests/tools/track_model_bench.py [--tracks 150] [--reps 50]
 Workload: the tracks of one EuRoC-shaped stereo frame (BASELINE config 2: 150 tracks, trail 20, stereo), 2..21 poses per track,
 all evaluated against one resident state in one launch (one CTA per track)."""
 import argparse
@@ -13,7 +13,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
