@@ -69,3 +69,13 @@ def test_next_row_report_cannot_take_the_bench_line_down():
     import bench
     r = bench.next_row_track_model()
     assert isinstance(r, dict) and (("error" in r and "hv_ctx_create" in r["error"]) or "kernel" in r)      # "kernel": a GPU was present after all
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """N > 1: rank 0 alone runs the reference arm and prints it, the other ranks exit 0 without work."""
+    r = _torchrun(2, "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
