@@ -791,14 +791,52 @@ static bool batchable_check(const hv_ekf* e, const hv_ekf_op& o)
            ekf_cluster_smem_bytes(o.n, o.l, e->N, false) <= 216 * 1024;
 }
 
+// a dense visual measurement that changes the state (update / check+update) and fits the cluster kernel
+static bool persistable(hv_ekf* e, const hv_ekf_op& o)
+{
+    if (o.kind != HV_EKF_OP_VISUAL || (o.mode != EKF_MODE_UPDATE && o.mode != EKF_MODE_CHECK_UPDATE) || !o.H || !o.f || !o.y) return false;
+    if (o.n <= 0 || o.l <= 0 || o.l > e->N || o.n > e->N || o.n >= (int)e->chi2inv95.size()) return false;
+    static const bool off = getenv("HV_EKF_SINGLE_CTA") != nullptr || getenv("HV_EKF_CLUSTER_V1") != nullptr;
+    return !off && ekf_cluster2_fits(o.n, o.l, e->N, false);
+}
+
 static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vuStatus, double* chi2, double* mOut)
 {
     if (!ops || nops < 0) { hv_set_error("hv_ekf_run: invalid argument"); return HV_ERR_INVALID; }
     static const bool noBatch = getenv("HV_EKF_NO_BATCH") != nullptr;
+    static const bool persist = getenv("HV_EKF_PERSIST") != nullptr;
     for (int i = 0; i < nops; i++) {
         const hv_ekf_op& o = ops[i];
         int rc = HV_OK;
         if (o.kind == HV_EKF_OP_VISUAL) { rc = flush_pending(e); if (rc != HV_OK) return rc; }   // the other kinds enter through their own entry points
+        // consecutive check+update / update measurements with device-resident inputs: one persistent launch (the P blocks stay in
+        // shared memory between the measurements). Opt-in this round: HV_EKF_PERSIST=1.
+        if (persist && !host && persistable(e, o)) {
+            EkfMultiList list;
+            memset(&list, 0, sizeof(list));
+            EkfUpdateArgs first;
+            int cnt = 0;
+            while (i + cnt < nops && cnt < EKF_MAX_MULTI && persistable(e, ops[i + cnt])) {
+                const hv_ekf_op& q = ops[i + cnt];
+                EkfUpdateArgs t;
+                rc = visual_args(e, "hv_ekf_run_device", q.n, q.l, q.r, q.rmse_thr, q.mode, t);
+                if (rc != HV_OK) return rc;
+                EkfMultiItem& it = list.it[cnt];
+                it.H = q.H; it.f = q.f; it.y = q.y; it.n = q.n; it.l = q.l; it.mode = q.mode; it.skipChi2 = t.skipChi2;
+                it.Rdiag = t.Rdiag; it.Rdiag2 = 0.0; it.chi2Thr = t.chi2Thr; it.rmseThr = t.rmseThr; it.slot = nullptr;
+                list.count = cnt + 1;
+                if (!ekf_multi2_fits(list, e->N)) { list.count = cnt; break; }
+                if (cnt == 0) first = t;
+                cnt++;
+            }
+            if (cnt >= 2) {
+                prep_update(e, first);
+                HV_CUDA(ekf_launch_update_multi2(first, list, e->ctx->stream));
+                e->ctx->launches++;
+                i += cnt - 1;
+                continue;
+            }
+        }
         if (!noBatch && batchable_check(e, o)) {
             int cnt = 1;
             while (i + cnt < nops && cnt < EKF_MAX_BATCH && batchable_check(e, ops[i + cnt])) cnt++;

@@ -32,6 +32,15 @@ __global__ void __launch_bounds__(EK2_NT) ekf_check_batch_cluster2_kernel(EkfUpd
     ek2_body(a, ek2_sm, cluster);
 }
 
+// Persistent sequence: the measurements of the list are applied one after the other by the same cluster; the P column block of
+// every CTA stays in shared memory between them (no re-staging, no launch gap); m travels through global memory (CTA 0 writes it,
+// the final cluster barrier of a measurement orders it before the next one reads it).
+__global__ void __launch_bounds__(EK2_NT) ekf_update_multi_cluster2_kernel(EkfUpdateArgs a, EkfMultiList list)
+{
+    extern __shared__ __align__(16) double ek2_sm[];
+    ek2_multi_body(a, list, ek2_sm, cg::this_cluster());
+}
+
 #define EK2_STATIC_SMEM (sizeof(double) * (2 + 128 + 2 + EK2_MAXN) + 256)
 #define EK2_SMEM_LIMIT (227 * 1024)
 
@@ -86,6 +95,23 @@ cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s)
     if (!ready) { cudaError_t e = ek2_prepare(ekf_update_cluster2_kernel, C); if (e != cudaSuccess) return e; ready = true; }
     const size_t smem = ek2_smem_bytes(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT, C);
     return ek2_launch(ekf_update_cluster2_kernel, C, 1, smem, s, a);
+}
+
+bool ekf_multi2_fits(const EkfMultiList& m, int N)
+{
+    if (N > EK2_MAXN || m.count < 1 || m.count > EKF_MAX_MULTI) return false;
+    return ek2_multi_smem_bytes(m, N, ek2_cluster_size(), nullptr, nullptr) + EK2_STATIC_SMEM <= EK2_SMEM_LIMIT;
+}
+
+cudaError_t ekf_launch_update_multi2(const EkfUpdateArgs& a, const EkfMultiList& m, cudaStream_t s)
+{
+    const int C = ek2_cluster_size();
+    static bool ready = false;
+    if (!ready) { cudaError_t e = ek2_prepare(ekf_update_multi_cluster2_kernel, C); if (e != cudaSuccess) return e; ready = true; }
+    if (a.symmetrize || a.op != EKF_OP_DENSE) return cudaErrorInvalidValue;       // sequences are dense visual measurements
+    EkfUpdateArgs b = a;
+    const size_t smem = ek2_multi_smem_bytes(m, a.b.N, C, &b.xCap, &b.tCap);
+    return ek2_launch(ekf_update_multi_cluster2_kernel, C, 1, smem, s, b, m);
 }
 
 cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s)

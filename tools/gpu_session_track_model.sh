@@ -17,4 +17,5 @@ echo "== ncu --set full of the same launches"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:hv_track_model\|ekf_update_cluster2 -c 20 -o gpurun_out/tm_full -f \
     python tools/prof_track_model.py 1 >> gpurun_out/tm_prof.log 2>&1
 echo "== all GPU tests, bench"; timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -5 | tee gpurun_out/all_tests.log
+echo "== A/B: persistent sequence of updates"; HV_EKF_PERSIST=1 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_persist.json 2> gpurun_out/bench_persist.err; tail -c 600 gpurun_out/bench_persist.json
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 1500 gpurun_out/bench.json
