@@ -113,6 +113,12 @@ struct EkfMultiItem {
 };
 struct EkfMultiList { int count, pad; EkfMultiItem it[EKF_MAX_MULTI]; };
 
+// The whole per-track loop of a frame in ONE launch (ekf_chain_cluster2_kernel, HV_CHAIN_PERSIST=1): per track the measurement
+// model in CTA 0 of the cluster (track_model.cuh), then check + update with two noise levels on the cluster, P blocks resident.
+#define EKF_MAX_CHAIN 24
+struct EkfChainItem { int n, l; double chi2Thr; double* slot; };      // rows / columns of H (host-known), chi2inv95[n], result words
+struct EkfChainList { int count, first; double RdiagCheck, RdiagUpdate, rmseThr; EkfChainItem it[EKF_MAX_CHAIN]; };
+
 // Independent outlier checks against the same (m, P): one launch, one 8-CTA cluster per measurement
 #define EKF_MAX_BATCH 24
 #define EKF_RES_STRIDE 32
@@ -168,5 +174,8 @@ cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s);
 bool ekf_multi2_fits(const EkfMultiList& m, int N);
 cudaError_t ekf_launch_update_multi2(const EkfUpdateArgs& a, const EkfMultiList& m, cudaStream_t s);
+struct TmArgs;
+bool ekf_chain2_fits(const EkfChainList& c, int N);
+cudaError_t ekf_launch_chain2(const EkfUpdateArgs& a, const TmArgs& tm, const EkfChainList& c, cudaStream_t s);
 cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_elementwise(const EkfEwArgs& a, cudaStream_t s);

@@ -1054,10 +1054,41 @@ int hv_ekf_visual_tracks(hv_ekf* e, const hv_track_obs* tracks, int ntracks, con
     // issues them as two gated launches instead (A/B)
     static const bool separate = getenv("HV_CHAIN_SEPARATE") != nullptr;
     const bool fused = !separate && p->chi_outlier_r >= 0.0 && p->visual_r > 0.0;
+    static const bool persistChain = getenv("HV_CHAIN_PERSIST") != nullptr;
     int issued = 0, succ = 0;
     while (issued < ntracks && succ < maxSucc) {
         const int first = issued, count = ntracks - issued < step ? ntracks - issued : step;
-        for (int k = first; k < first + count; k++) {
+        // HV_CHAIN_PERSIST=1: the whole chunk as ONE launch (model in CTA 0 of the cluster, check + update on the cluster, P blocks
+        // resident in shared memory from track to track); opt-in until it has been measured
+        bool oneLaunch = false;
+        if (persistChain && fused && count <= EKF_MAX_CHAIN) {
+            EkfChainList list;
+            memset(&list, 0, sizeof(list));
+            list.count = count; list.first = first;
+            list.RdiagCheck = (p->chi_outlier_r * p->chi_outlier_r) * e->noiseScale; list.RdiagUpdate = (p->visual_r * p->visual_r) * e->noiseScale;
+            list.rmseThr = p->track_rmse_threshold;
+            bool okShape = true;
+            for (int k = first; k < first + count; k++) {
+                const hv_track_obs& o = tracks[k];
+                EkfChainItem& it = list.it[k - first];
+                it.n = 2 * o.npose * ncam; it.l = 0;
+                for (int i = 0; i < o.npose; i++) { const int x = o.pose_trail_index[i]; const int end = x == 0 ? 10 : 20 + 7 * (x - 1) + 7; if (end > it.l) it.l = end; }
+                if (it.n >= (int)e->chi2inv95.size() || it.l > e->N) { okShape = false; break; }
+                it.chi2Thr = e->chi2inv95[it.n]; it.slot = d_slots + 8 * (size_t)k;
+            }
+            if (okShape && ekf_chain2_fits(list, e->N)) {
+                EkfUpdateArgs c;
+                rc = visual_args(e, who, list.it[0].n, list.it[0].l, p->chi_outlier_r, p->track_rmse_threshold, EKF_MODE_CHECK_UPDATE, c);
+                if (rc != HV_OK) return rc;
+                prep_update(e, c);
+                TmArgs a = base;
+                a.ntracks = 1; a.counter = d_counter; a.counterMax = maxSucc;
+                HV_CUDA(ekf_launch_chain2(c, a, list, s));
+                e->ctx->launches++;
+                oneLaunch = true;
+            }
+        }
+        for (int k = first; k < first + count && !oneLaunch; k++) {
             TmArgs a = base;
             a.ntracks = 1; a.trackOffset = k; a.counter = d_counter; a.counterMax = maxSucc;
             a.pdl = k > first ? 1 : 0;                                // behind a cluster kernel of this chain: overlap the launch with its tail

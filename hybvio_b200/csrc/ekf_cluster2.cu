@@ -10,6 +10,7 @@ namespace cg = cooperative_groups;
 #define EK2_PHASE(i) do { if (c == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.b.res[8 + (i)] = (double)t_; } } while (0)
 #endif
 #include "ekf_cluster2.cuh"
+#include "ekf_chain2.cuh"
 
 __global__ void __launch_bounds__(EK2_NT) ekf_update_cluster2_kernel(EkfUpdateArgs a)
 {
@@ -41,7 +42,15 @@ __global__ void __launch_bounds__(EK2_NT) ekf_update_multi_cluster2_kernel(EkfUp
     ek2_multi_body(a, list, ek2_sm, cg::this_cluster());
 }
 
+// One launch for the whole visual-update loop of a frame (ekf_chain2.cuh)
+__global__ void __launch_bounds__(EK2_NT) ekf_chain_cluster2_kernel(EkfUpdateArgs a, TmArgs tm, EkfChainList list)
+{
+    extern __shared__ __align__(16) double ek2_sm[];
+    ek2_chain_body(a, tm, list, ek2_sm, cg::this_cluster());
+}
+
 #define EK2_STATIC_SMEM (sizeof(double) * (2 + 128 + 2 + EK2_MAXN) + 256)
+#define EK2_CHAIN_STATIC_SMEM (EK2_STATIC_SMEM + sizeof(int) * (TM_MAXN + 4 + TM_MAXOBS) + 64)
 #define EK2_SMEM_LIMIT (227 * 1024)
 
 // Cluster size: 8 (portable) unless HV_EKF_CLUSTER=16 asks for the non-portable size (A/B switch this round).
@@ -80,9 +89,9 @@ static cudaError_t ek2_launch(K kernel, int C, int nclusters, size_t smem, cudaS
 }
 
 template <class K>
-static cudaError_t ek2_prepare(K kernel, int C)
+static cudaError_t ek2_prepare(K kernel, int C, size_t staticSmem = EK2_STATIC_SMEM)
 {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EK2_SMEM_LIMIT - EK2_STATIC_SMEM));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EK2_SMEM_LIMIT - staticSmem));
     if (e != cudaSuccess) return e;
     (void)C;
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -112,6 +121,23 @@ cudaError_t ekf_launch_update_multi2(const EkfUpdateArgs& a, const EkfMultiList&
     EkfUpdateArgs b = a;
     const size_t smem = ek2_multi_smem_bytes(m, a.b.N, C, &b.xCap, &b.tCap);
     return ek2_launch(ekf_update_multi_cluster2_kernel, C, 1, smem, s, b, m);
+}
+
+bool ekf_chain2_fits(const EkfChainList& c, int N)
+{
+    if (N > EK2_MAXN || c.count < 1 || c.count > EKF_MAX_CHAIN) return false;
+    return ek2_chain_smem_bytes(c, N, ek2_cluster_size(), nullptr, nullptr) + EK2_CHAIN_STATIC_SMEM <= EK2_SMEM_LIMIT;
+}
+
+cudaError_t ekf_launch_chain2(const EkfUpdateArgs& a, const TmArgs& tm, const EkfChainList& c, cudaStream_t s)
+{
+    const int C = ek2_cluster_size();
+    static bool ready = false;
+    if (!ready) { cudaError_t e = ek2_prepare(ekf_chain_cluster2_kernel, C, EK2_CHAIN_STATIC_SMEM); if (e != cudaSuccess) return e; ready = true; }
+    if (a.symmetrize || a.op != EKF_OP_DENSE) return cudaErrorInvalidValue;
+    EkfUpdateArgs b = a;
+    const size_t smem = ek2_chain_smem_bytes(c, a.b.N, C, &b.xCap, &b.tCap);
+    return ek2_launch(ekf_chain_cluster2_kernel, C, 1, smem, s, b, tm, c);
 }
 
 cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s)

@@ -259,6 +259,9 @@ __device__ __forceinline__ int tm_ori_index(int i) { return i == 0 ? TM_ORI : TM
 __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
 {
     __shared__ int s_colmap[TM_MAXN], s_flag[4], s_code[TM_MAXOBS];
+    // NT threads (a multiple of 32, >= 256: the 4-lane reductions of stage C4 address 63 x 4 threads): TM_NT in its own kernel, the
+    // 512 threads of a cluster CTA when the persistent chain kernel runs the model in its CTA 0
+    const int NT = (int)blockDim.x;
     const int tid = threadIdx.x, trk = blockIdx.x + a.trackOffset, lane = tid & 31, wrp = tid >> 5;
 #ifndef HV_EMU
     if (a.pdl) {        // the next kernel of the chain may be scheduled now (it reads nothing of ours before its own wait); then wait for our predecessor
@@ -279,7 +282,7 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
     double *TMV = sm + TM_S_TMV, *RED = sm + TM_S_RED, *SC = sm + TM_S_SC;
 
     // ---- A: camera pose trail (triangulation.cpp:65-103): item = (pose, part), part 0: R and p, parts 1..4: dR/dq
-    for (int it = tid; it < 5 * n; it += TM_NT) {
+    for (int it = tid; it < 5 * n; it += NT) {
         const int k = it / 5, part = it % 5, cam = k / npose, i = idx[k % npose];
         const double* q = m + tm_ori_index(i);
         double Q[9], M[9];
@@ -295,7 +298,7 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
             for (int r = 0; r < 9; r++) o[12 + 9 * (part - 1) + r] = M[r];
         }
     }
-    for (int j = tid; j < 3 * (dDim + 1); j += TM_NT) DQ[j] = 0.0;
+    for (int j = tid; j < 3 * (dDim + 1); j += NT) DQ[j] = 0.0;
     if (tid < 4) s_flag[tid] = 0;
     __syncthreads();
 
@@ -412,7 +415,7 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
         tm_ldlt(ETE, X);
         tm_solve(X, Eerr, step);
         // C3: the 18 n block terms
-        for (int it = tid; it < 18 * n; it += TM_NT) {
+        for (int it = tid; it < 18 * n; it += NT) {
             double av[3], wv[3];
             if (it < 3 * n) {                                   // generic: d pfi = e_k
                 const int i = it / 3, k = it % 3;
@@ -477,7 +480,7 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
         }
         __syncthreads();
         // C5: d pfi_j += X^-1 (w_j - a_j)   (:322-327 with the two solves of the reference merged into one)
-        for (int j = tid; j <= dDim; j += TM_NT) {
+        for (int j = tid; j <= dDim; j += NT) {
             double* dq = DQ + 3 * j;
             double rhs[3], upd[3];
             for (int r = 0; r < 3; r++) {
@@ -516,7 +519,7 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
         else {
             for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R0T[3 * r + c] = R0[3 * c + r];
             tm_mm(R0T, dpf0, M);
-            for (int j = tid; j <= dDim; j += TM_NT) {
+            for (int j = tid; j <= dDim; j += NT) {
                 double x[3], y[3] = {0, 0, 0};
                 tm_mv(M, DQ + 3 * j, x);
                 if (j >= 3 && j < 7) tm_mtv(POSE + 12 + 9 * (j - 3), pf0, y);
@@ -541,7 +544,7 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
     double* dpfOut = a.dpf ? a.dpf + (size_t)trk * 3 * (7 * TM_MAXPOSE + 1) : nullptr;
     if (tri != TM_OK) {
         if (tid == 0) { st[0] = tri; st[1] = TM_VU_NOT_RUN; st[2] = 0; st[3] = 0; }
-        if (dpfOut) for (int j = tid; j < 3 * (7 * npose + 1); j += TM_NT) dpfOut[j] = 0.0;
+        if (dpfOut) for (int j = tid; j < 3 * (7 * npose + 1); j += NT) dpfOut[j] = 0.0;
         return;
     }
 
@@ -549,15 +552,15 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
     double *DPF = sm + TM_S_DPF, *OWN = sm + TM_S_OWN, *DIPR = sm + TM_S_DIPR;
     double held[2][3];                                  // DPF aliases EXO, not DQ: no hazard, but keep the sum in registers until the barrier for clarity
     int nheld = 0;
-    for (int j = tid; j < 7 * npose + 1; j += TM_NT, nheld++)
+    for (int j = tid; j < 7 * npose + 1; j += NT, nheld++)
         for (int r = 0; r < 3; r++)
             held[nheld][r] = j == 7 * npose ? DQ[3 * dDim + r] : DQ[3 * j + r] + (a.stereo ? DQ[3 * (7 * npose + j) + r] : 0.0);
     nheld = 0;
-    for (int j = tid; j < 7 * npose + 1; j += TM_NT, nheld++)
+    for (int j = tid; j < 7 * npose + 1; j += NT, nheld++)
         for (int r = 0; r < 3; r++) { DPF[3 * j + r] = held[nheld][r]; if (dpfOut) dpfOut[3 * j + r] = held[nheld][r]; }
     int end = 0;
     for (int k = 0; k < npose; k++) { const int e = tm_ori_index(idx[k]) + 4 > tm_pos_index(idx[k]) + 3 ? tm_ori_index(idx[k]) + 4 : tm_pos_index(idx[k]) + 3; if (e > end) end = e; }
-    for (int c = tid; c < end; c += TM_NT) s_colmap[c] = -1;
+    for (int c = tid; c < end; c += NT) s_colmap[c] = -1;
     __syncthreads();
     if (tid < npose) {
         const int pos = tm_pos_index(idx[tid]), ori = tm_ori_index(idx[tid]);
@@ -592,7 +595,7 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
     if (vu != TM_VU_OK) return;
     // H(2i + r, c): every element written exactly once; a warp per column, lanes along the rows (contiguous in memory)
     double* H = a.H + (size_t)trk * a.Hstride;
-    for (int c = wrp; c < end; c += TM_NT / 32) {
+    for (int c = wrp; c < end; c += NT / 32) {
         const int mc = s_colmap[c];
         const bool sft = mc < 0 && c == TM_SFT && a.timeShift;
         const double* d = mc >= 0 ? DPF + 3 * mc : DPF + 3 * 7 * npose;

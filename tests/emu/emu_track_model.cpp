@@ -135,7 +135,8 @@ int main()
         a.trackOffset = trk;                        // one CTA of a chain: track `trk` of the packed batch
         int counter = (cs % 7 == 6 && cs < 40) ? 5 : 2;          // a few cases arrive after the chain has its 5 successful updates
         a.counter = &counter; a.counterMax = 5;
-        emu::launch_cta(TM_NT, 0, [&] { tm_body(a, dyn.data()); });
+        static const int nthreads = getenv("EMU_NT") ? atoi(getenv("EMU_NT")) : TM_NT;      // 512: as CTA 0 of the persistent chain kernel runs it
+        emu::launch_cta(nthreads, 0, [&] { tm_body(a, dyn.data()); });
         if (counter == 5) {
             const bool sk = st[4 * trk] == TM_SKIPPED && st[4 * trk + 1] == TM_VU_NOT_RUN && oH[trk * Hs] == 7.0 && st[0] == -7 && st[8] == -7;
             printf("case %2d skipped by the success counter  %s\n", cs, sk ? "ok" : "FAIL");

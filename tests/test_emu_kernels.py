@@ -74,7 +74,8 @@ def test_device_gated_chain_on_host_emulator(tmp_path):
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
                            "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
                            os.path.join(ROOT, "tests", "emu", "emu_chain.cpp"), *objs, "-lm", "-o", exe])
-    for args, tag in (([], "chain: 3 updates (oracle 3)"), (["fused"], "chain (fused check+update): 3 updates (oracle 3)")):
+    for args, tag in (([], "chain: 3 updates (oracle 3)"), (["fused"], "chain (fused check+update): 3 updates (oracle 3)"),
+                      (["fused", "persist"], "chain (one persistent launch): 3 updates (oracle 3)")):
         out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=900)
         assert out.returncode == 0, out.stdout + out.stderr
         assert out.stdout.count("  ok") == 10 and "FAIL" not in out.stdout and tag in out.stdout

@@ -10,6 +10,7 @@ echo "== measurement tool"; timeout 300 python tests/tools/track_model_bench.py 
 echo "== A/B: separate check / update launches, no PDL"
 HV_CHAIN_SEPARATE=1 timeout 300 python tests/tools/track_model_bench.py > gpurun_out/tm_bench_separate.json 2>/dev/null
 HV_EKF_NO_PDL=1 timeout 300 python tests/tools/track_model_bench.py > gpurun_out/tm_bench_nopdl.json 2>/dev/null
+HV_CHAIN_PERSIST=1 timeout 300 python tests/tools/track_model_bench.py > gpurun_out/tm_bench_persist.json 2>/dev/null
 echo "== launch list of the model kernel and one chain"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:hv_track_model\|ekf_update_cluster2 -c 200 --csv --log-file gpurun_out/tm_launches.csv \
     python tools/prof_track_model.py 1 > gpurun_out/tm_prof.log 2>&1
