@@ -649,9 +649,13 @@ def next_row_track_model():
     import subprocess
     try:
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "track_model_bench.py")], capture_output=True, text=True, timeout=180)
-        if r.returncode != 0:
-            return {"error": (r.stderr or r.stdout)[-400:]}
-        return json.loads(r.stdout.strip().splitlines()[-1])
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if lines:                                         # the tool prints its line before it tears the context down
+            d = json.loads(lines[-1])
+            if r.returncode != 0:
+                d["exit_code"] = r.returncode
+            return d
+        return {"error": (r.stderr or r.stdout)[-400:]}
     except Exception as ex:       # noqa: BLE001 -- a report-only extra must never take the bench line down
         return {"error": repr(ex)[:400]}
 
