@@ -258,7 +258,7 @@ __device__ __forceinline__ int tm_ori_index(int i) { return i == 0 ? TM_ORI : TM
 // ---------------------------------------------------------------------------------------------------- the kernel body
 __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
 {
-    __shared__ int s_colmap[TM_MAXN], s_flag[4], s_code[TM_MAXOBS];
+    __shared__ int s_colmap[TM_MAXN], s_code[TM_MAXOBS];
     // NT threads (a multiple of 32, >= 256: the 4-lane reductions of stage C4 address 63 x 4 threads): TM_NT in its own kernel, the
     // 512 threads of a cluster CTA when the persistent chain kernel runs the model in its CTA 0
     const int NT = (int)blockDim.x;
@@ -299,7 +299,6 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
         }
     }
     for (int j = tid; j < 3 * (dDim + 1); j += NT) DQ[j] = 0.0;
-    if (tid < 4) s_flag[tid] = 0;
     __syncthreads();
 
     // ---- B: two-view start (triangulation.cpp:610-710) between observation 0 and the last one of camera 0 (:157-158)
@@ -530,12 +529,12 @@ __device__ __forceinline__ void tm_body(const TmArgs& a, double* sm)
                 double d[3], c3[3];
                 for (int r = 0; r < 3; r++) d[r] = pf[r] - cur[r];
                 tm_mv(cur + 3, d, c3);
-                if (c3[2] < 0) s_flag[0] = 1;
+                s_code[tid] = c3[2] < 0 ? 1 : 0;                    // one word per observation: no two threads write the same address
             }
         }
     }
     __syncthreads();
-    if (tri == TM_OK && s_flag[0]) tri = TM_BEHIND;
+    if (tri == TM_OK) { int behind = 0; for (int i = 0; i < n; i++) behind |= s_code[i]; if (behind) tri = TM_BEHIND; }
     const double depth = sqrt((pf[0] - p0[0]) * (pf[0] - p0[0]) + (pf[1] - p0[1]) * (pf[1] - p0[1]) + (pf[2] - p0[2]) * (pf[2] - p0[2]));
     if (depth < a.minDist || depth > a.maxDist) tri = TM_BAD_DEPTH;                                     // backend.cpp:1095-1098
 

@@ -93,3 +93,35 @@ def test_persistent_sequence_on_host_emulator(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("  ok") == 9 and "FAIL" not in out.stdout and "persistent sequence of 8 measurements" in out.stdout
+
+
+def test_kernel_bodies_are_race_free_under_thread_sanitizer(tmp_path):
+    """The emulator runs every CUDA thread as an OS thread and every barrier as a real barrier, so ThreadSanitizer sees a missing
+    __syncthreads / __syncwarp as a data race on the shared-memory arrays (inside a CTA; accesses between the CTAs of a cluster go
+    through a process-shared mapping and are not covered). All harnesses must come out without a report."""
+    probe = tmp_path / "probe.cpp"
+    probe.write_text("int main() { return 0; }\n")
+    if subprocess.run(["g++", "-fsanitize=thread", str(probe), "-o", str(tmp_path / "probe")], capture_output=True).returncode != 0:
+        import pytest
+        pytest.skip("g++ -fsanitize=thread is not available")
+    objs = {}
+    for name in ("hv_oracle_ekf", "hv_oracle_tri"):
+        objs[name] = str(tmp_path / (name + ".o"))
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", name + ".c"), "-o", objs[name]])
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
+    runs = [("emu_track_model", ["hv_oracle_tri"], [[]], {}), ("emu_track_model", ["hv_oracle_tri"], [[]], {"EMU_NT": "512"}),
+            ("emu_update", ["hv_oracle_ekf"], [["0"], ["3"], ["6"], ["14"], ["20"]], {}), ("emu_multi", ["hv_oracle_ekf"], [[]], {}),
+            ("emu_chain", ["hv_oracle_ekf", "hv_oracle_tri"], [[], ["fused", "persist"]], {}), ("emu_predict", ["hv_oracle_ekf"], [[]], {})]
+    built = {}
+    for src, deps, arglists, extra in runs:
+        if src not in built:
+            exe = str(tmp_path / (src + "_tsan"))
+            subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-pthread", "-w", "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
+                                   "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                                   os.path.join(ROOT, "tests", "emu", src + ".cpp"), *[objs[d] for d in deps], "-lm", "-o", exe])
+            built[src] = exe
+        for args in arglists:
+            out = subprocess.run([built[src], *args], capture_output=True, text=True, timeout=1500, env=dict(env, **extra))
+            text = out.stdout + out.stderr
+            assert "WARNING: ThreadSanitizer" not in text, (src, args, text[text.index("WARNING: ThreadSanitizer"):][:1500])
+            assert out.returncode == 0 and "FAIL" not in out.stdout, (src, args, out.stdout[-800:])
