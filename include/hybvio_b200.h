@@ -204,7 +204,9 @@ typedef struct hv_ekf_op {
     double gyro[3], acc[3];
     const double* H; const double* f; const double* y;
 } hv_ekf_op;
-/* H/f/y are DEVICE pointers; fully asynchronous. */
+/* H/f/y are DEVICE pointers; fully asynchronous. Consecutive independent outlier checks (mode 0) are issued as one launch, one
+ * cluster per measurement; with HV_EKF_PERSIST=1 in the environment consecutive update / check+update ops (modes 1, 2) become one
+ * persistent launch as well (the covariance blocks stay in shared memory between them; same results). */
 int hv_ekf_run_device(hv_ekf* ekf, const hv_ekf_op* ops, int nops);
 /* H/f/y are HOST pointers; every VISUAL op with mode 0 or 2 returns its VuOutlierStatus / chi2 into
  * vu_status[i] / chi2[i] (arrays of length nops, entries of other ops untouched) -- i.e. each such op is a host
