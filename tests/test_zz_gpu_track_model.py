@@ -218,6 +218,48 @@ def test_device_gated_chain_equals_the_per_track_loop(env, lookahead):
     e.close(); okf.close()
 
 
+def test_full_frame_properties(env):
+    """BASELINE config 2 size (150 stereo tracks, 2..21 poses, trail 20) through properties that need no oracle: a track's result does
+    not depend on its position in the batch (bitwise), H is zero in the columns of poses the track does not touch and its column
+    count is the truncation point of prepareVisualUpdate, f reproduces the observations to the noise level, repeated calls agree bitwise."""
+    capi, hv, _ = env
+    base = tri_common.make_track(0, npose=4, stereo=True)
+    rng = np.random.RandomState(11)
+    tracks = []
+    for k in range(150):
+        npose = 2 + (k * 7) % 20
+        idx = np.concatenate([[0], np.sort(rng.choice(np.arange(1, 21), npose - 1, replace=False))]).astype(np.int32)
+        pf = base["pf_true"] * [2.0, 4.0, 8.0, 16.0][k % 4] / 5.0 + rng.normal(0, 0.2, 3)
+        ip = tri_common.project(base["m"], idx, base["T1"], base["T2"], True, pf) + rng.normal(0, 1e-3, (2 * npose, 2))
+        tracks.append((idx, ip, rng.normal(0, 0.05, ip.shape)))
+    e = make_ekf(capi, hv, base)
+    e.set_camera_model(base["T1"], base["T2"], use_stereo=True)
+    a = e.track_models(tracks)
+    perm = rng.permutation(150)
+    b = e.track_models([tracks[i] for i in perm])
+    c = e.track_models(tracks)
+    ok = 0
+    for k in range(150):
+        x, y, z = a[k], b[int(np.where(perm == k)[0][0])], c[k]
+        for other in (y, z):
+            assert (x["tri_status"], x["vu_status"]) == (other["tri_status"], other["vu_status"])
+            assert np.array_equal(x["H"], other["H"]) and np.array_equal(x["f"], other["f"]) and np.array_equal(x["pf"], other["pf"])
+        if x["tri_status"] != 0:
+            continue
+        ok += 1
+        idx = tracks[k][0]
+        used = np.zeros(x["cols"], bool)
+        used[0:3] = used[6:10] = True
+        used[19] = True                                          # the time-shift column
+        for i in idx[1:]:
+            used[20 + 7 * (i - 1):20 + 7 * i] = True
+        assert x["cols"] == 20 + 7 * int(idx.max()) and x["rows"] == 4 * len(idx)
+        assert not x["H"][:, ~used].any() and np.abs(x["H"][:, used]).max() > 0
+        assert np.abs(x["f"] - tracks[k][1].ravel()).max() < 2e-2
+    assert ok >= 140
+    e.close()
+
+
 def test_track_models_reject_bad_input(env):
     capi, hv, _ = env
     t = tri_common.make_track(1, npose=4, stereo=False)
