@@ -89,3 +89,43 @@ inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 template <class T> inline T min(T a, T b) { return a < b ? a : b; }
 template <class T> inline T max(T a, T b) { return a > b ? a : b; }
 using std::fma;
+
+// ---- additions for the tracker kernels (lk.cu): vector types, read-only loads, rounding-mode intrinsics (the host FPU rounds to
+// nearest even; build with -ffp-contract=off so that no multiply-add is contracted), integer warp collectives, atomics
+#include <climits>
+#include <cfloat>
+struct float2 { float x, y; };
+struct short2 { short x, y; };
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline float __ll2float_rn(long long v) { return (float)v; }
+inline int __float2int_rn(float v) { return (int)std::lrintf(v); }
+inline int __float2int_rd(float v) { return (int)std::floor(v); }
+inline int __shfl_down_sync(unsigned, int v, int delta)
+{
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* slot = emu::cta->xch.data() + (size_t)w * 32;
+    slot[lane] = (double)v;
+    emu::cta->wbar[w]->arrive_and_wait();
+    const int r = lane + delta < 32 ? (int)slot[lane + delta] : v;
+    emu::cta->wbar[w]->arrive_and_wait();
+    return r;
+}
+inline int __reduce_add_sync(unsigned, int v)
+{
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* slot = emu::cta->xch.data() + (size_t)w * 32;
+    slot[lane] = (double)v;
+    emu::cta->wbar[w]->arrive_and_wait();
+    long long s = 0;
+    for (int i = 0; i < 32; i++) s += (long long)slot[i];
+    emu::cta->wbar[w]->arrive_and_wait();
+    return (int)s;
+}
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

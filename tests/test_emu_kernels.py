@@ -95,6 +95,31 @@ def test_persistent_sequence_on_host_emulator(tmp_path):
     assert out.stdout.count("  ok") == 9 and "FAIL" not in out.stdout and "persistent sequence of 8 measurements" in out.stdout
 
 
+def _lk_device_part(tmp_path):
+    """The device part of hybvio_b200/csrc/lk.cu (everything before the host launcher, which uses <<< >>>) as an includable file."""
+    src = open(os.path.join(ROOT, "hybvio_b200", "csrc", "lk.cu")).read()
+    cut = src.index("\ncudaError_t hv_launch_lk")
+    inc = tmp_path / "lk_device.inc"
+    inc.write_text(src[:cut] + "\n")
+    return str(tmp_path)
+
+
+def test_lk_kernel_bodies_on_host_emulator(tmp_path):
+    """hv_lk_cta_kernel<31> (CTA per feature) and hv_lk_kernel<31> (warp per feature) on the emulator: end points and statuses
+    bit-identical to the C oracle in the kernels' accumulation order, with and without initial flow, incl. points outside the image
+    and on a flat patch."""
+    exe = str(tmp_path / "emu_lk")
+    obj = str(tmp_path / "orc_lk.o")
+    incdir = _lk_device_part(tmp_path)
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", "hv_oracle_lk.c"), "-o", obj])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-w", "-I" + incdir, "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "emu", "emu_lk.cpp"), obj, "-lm", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("  ok") == 4 and "FAIL" not in out.stdout and "35 tracked" in out.stdout
+
+
 def test_kernel_bodies_are_race_free_under_thread_sanitizer(tmp_path):
     """The emulator runs every CUDA thread as an OS thread and every barrier as a real barrier, so ThreadSanitizer sees a missing
     __syncthreads / __syncwarp as a data race on the shared-memory arrays (inside a CTA; accesses between the CTAs of a cluster go
@@ -107,18 +132,21 @@ def test_kernel_bodies_are_race_free_under_thread_sanitizer(tmp_path):
     if subprocess.run([str(tmp_path / "probe")], capture_output=True).returncode != 0:
         pytest.skip("ThreadSanitizer binaries do not start here (address-space layout)")
     objs = {}
-    for name in ("hv_oracle_ekf", "hv_oracle_tri"):
+    incdir = _lk_device_part(tmp_path)
+    for name in ("hv_oracle_ekf", "hv_oracle_tri", "hv_oracle_lk"):
         objs[name] = str(tmp_path / (name + ".o"))
         subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", name + ".c"), "-o", objs[name]])
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
     runs = [("emu_track_model", ["hv_oracle_tri"], [[]], {}), ("emu_track_model", ["hv_oracle_tri"], [[]], {"EMU_NT": "512"}),
             ("emu_update", ["hv_oracle_ekf"], [["0"], ["3"], ["6"], ["14"], ["20"]], {}), ("emu_multi", ["hv_oracle_ekf"], [[]], {}),
-            ("emu_chain", ["hv_oracle_ekf", "hv_oracle_tri"], [[], ["fused", "persist"]], {}), ("emu_predict", ["hv_oracle_ekf"], [[]], {})]
+            ("emu_chain", ["hv_oracle_ekf", "hv_oracle_tri"], [[], ["fused", "persist"]], {}), ("emu_predict", ["hv_oracle_ekf"], [[]], {}),
+            ("emu_lk", ["hv_oracle_lk"], [[]], {})]
     built = {}
     for src, deps, arglists, extra in runs:
         if src not in built:
             exe = str(tmp_path / (src + "_tsan"))
-            subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-pthread", "-w", "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
+            subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-pthread", "-w", "-I" + incdir,
+                                   "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
                                    "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
                                    os.path.join(ROOT, "tests", "emu", src + ".cpp"), *[objs[d] for d in deps], "-lm", "-o", exe])
             built[src] = exe
