@@ -44,6 +44,7 @@ struct Cta {
     }
 };
 inline Cta* cta = nullptr;
+inline unsigned block_y = 0, block_z = 0;      // blockIdx.y / .z of the CTA launch_cta runs (kernels with 2-D / 3-D grids)
 
 template <class F>
 void launch_cta(int nthreads, unsigned bx, F&& body)
@@ -53,7 +54,7 @@ void launch_cta(int nthreads, unsigned bx, F&& body)
     blockDim.x = nthreads; blockDim.y = blockDim.z = 1;
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; t++)
-        th.emplace_back([&, t] { threadIdx.x = t; threadIdx.y = threadIdx.z = 0; blockIdx.x = bx; blockIdx.y = blockIdx.z = 0; body(); });
+        th.emplace_back([&, t] { threadIdx.x = t; threadIdx.y = threadIdx.z = 0; blockIdx.x = bx; blockIdx.y = block_y; blockIdx.z = block_z; body(); });
     for (auto& x : th) x.join();
     cta = nullptr;
 }
@@ -129,3 +130,7 @@ inline int __reduce_add_sync(unsigned, int v)
     return (int)s;
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+struct uchar4 { unsigned char x, y, z, w; };
+struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
+inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { return uchar4{x, y, z, w}; }
+inline unsigned char* emu_dynamic_smem = nullptr;   // stands in for `extern __shared__` arrays (set by the harness before a launch)

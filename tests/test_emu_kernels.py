@@ -120,6 +120,31 @@ def test_lk_kernel_bodies_on_host_emulator(tmp_path):
     assert out.stdout.count("  ok") == 4 and "FAIL" not in out.stdout and "35 tracked" in out.stdout
 
 
+def _pyr_device_part(tmp_path):
+    """The device part of hybvio_b200/csrc/pyramid.cu; its `extern __shared__` array becomes a pointer the harness sets."""
+    src = open(os.path.join(ROOT, "hybvio_b200", "csrc", "pyramid.cu")).read()
+    dev = src[:src.index("\ncudaError_t hv_launch_pyr_fused")]
+    decl = "extern __shared__ __align__(16) uint8_t smem[];"
+    assert decl in dev
+    (tmp_path / "pyr_device.inc").write_text(dev.replace(decl, "uint8_t* smem = emu_dynamic_smem;") + "\n")
+    return str(tmp_path)
+
+
+def test_pyramid_kernel_body_on_host_emulator(tmp_path):
+    """hv_pyr_fused_kernel on the emulator: gray and Scharr gradient images of every level bit-identical to the oracle (OpenCV's pyrDown
+    + Scharr arithmetic), 752 x 480 with 4 levels and ragged sizes, frame copied into level 0 or read from a separate buffer."""
+    exe = str(tmp_path / "emu_pyramid")
+    obj = str(tmp_path / "orc_lk.o")
+    incdir = _pyr_device_part(tmp_path)
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", "hv_oracle_lk.c"), "-o", obj])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-w", "-I" + incdir, "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
+                           "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "emu", "emu_pyramid.cpp"), obj, "-lm", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("  ok") == 5 and "FAIL" not in out.stdout and "752x480, 4 levels" in out.stdout
+
+
 def test_kernel_bodies_are_race_free_under_thread_sanitizer(tmp_path):
     """The emulator runs every CUDA thread as an OS thread and every barrier as a real barrier, so ThreadSanitizer sees a missing
     __syncthreads / __syncwarp as a data race on the shared-memory arrays (inside a CTA; accesses between the CTAs of a cluster go
@@ -133,6 +158,7 @@ def test_kernel_bodies_are_race_free_under_thread_sanitizer(tmp_path):
         pytest.skip("ThreadSanitizer binaries do not start here (address-space layout)")
     objs = {}
     incdir = _lk_device_part(tmp_path)
+    _pyr_device_part(tmp_path)
     for name in ("hv_oracle_ekf", "hv_oracle_tri", "hv_oracle_lk"):
         objs[name] = str(tmp_path / (name + ".o"))
         subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", name + ".c"), "-o", objs[name]])
@@ -140,7 +166,7 @@ def test_kernel_bodies_are_race_free_under_thread_sanitizer(tmp_path):
     runs = [("emu_track_model", ["hv_oracle_tri"], [[]], {}), ("emu_track_model", ["hv_oracle_tri"], [[]], {"EMU_NT": "512"}),
             ("emu_update", ["hv_oracle_ekf"], [["0"], ["3"], ["6"], ["14"], ["20"]], {}), ("emu_multi", ["hv_oracle_ekf"], [[]], {}),
             ("emu_chain", ["hv_oracle_ekf", "hv_oracle_tri"], [[], ["fused", "persist"]], {}), ("emu_predict", ["hv_oracle_ekf"], [[]], {}),
-            ("emu_lk", ["hv_oracle_lk"], [[]], {})]
+            ("emu_lk", ["hv_oracle_lk"], [[]], {}), ("emu_pyramid", ["hv_oracle_lk"], [[]], {})]
     built = {}
     for src, deps, arglists, extra in runs:
         if src not in built:
