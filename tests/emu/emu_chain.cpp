@@ -28,6 +28,13 @@ int orc_track_model(const double* m, int trail, int useStereo, const int* poseTr
                     double* dpf, double* depth, int* vuStatus, int* rows, int* cols, double* H, double* f);
 }
 
+struct ChainCtx { EkfUpdateArgs c; TmArgs ta; EkfChainList list; };
+#if !defined(EMU_CLUSTER_THREADS) || defined(EMU_AS_LIB)
+EMU_CLUSTER_BODY(emu_chain_update_body) { EkfUpdateArgs aa = *(const EkfUpdateArgs*)ctx; ek2_body(aa, dyn, cg::this_cluster()); }
+EMU_CLUSTER_BODY(emu_chain_persist_body) { const ChainCtx& c = *(const ChainCtx*)ctx; ek2_chain_body(c.c, c.ta, c.list, dyn, cg::this_cluster()); }
+#endif
+#ifndef EMU_AS_LIB
+
 static double urand() { return rand() / (double)RAND_MAX; }
 static double nrand() { double s = 0; for (int i = 0; i < 12; i++) s += urand(); return s - 6.0; }
 
@@ -140,7 +147,8 @@ int main(int argc, char**)
         c.b.m = m; c.b.P = P; c.b.res = res; c.b.cwork = cwork; c.b.N = N; c.b.trail = trail;
         c.op = EKF_OP_DENSE; c.noiseScale = noiseScale; c.normalizeAll = 1;
         const size_t smem = ek2_chain_smem_bytes(list, N, 8, &c.xCap, &c.tCap);
-        const int bad = emu::launch_cluster(arena, 8, EK2_NT, smem, [&](double* dyn) { ek2_chain_body(c, ta, list, dyn, cg::this_cluster()); });
+        ChainCtx cc{c, ta, list};
+        const int bad = EMU_LAUNCH_CLUSTER(arena, 8, EK2_NT, smem, emu_chain_persist_body, &cc);
         fails += bad;
         for (int t = 0; t < ntracks; t++) {
             const int gTri = status[4 * t], gOut = (int)slots[8 * t], gUpd = (slots[8 * t] == 0.0 && slots[8 * t + 2] == 0.0) ? 1 : 0;
@@ -164,12 +172,12 @@ int main(int argc, char**)
         c.gateI = status + 4 * t + 1; c.gateIExpect = 0; c.counter = counter; c.counterMax = maxSucc; c.slot = slots + 8 * t; c.lateH = 1;
         const size_t smem = ek2_smem_bytes(n, l, N, false, 8);
         if (fused) { c.mode = EKF_MODE_CHECK_UPDATE; c.Rdiag2 = visR * visR * noiseScale; c.bump = counter; }
-        int bad = emu::launch_cluster(arena, 8, EK2_NT, smem, [&](double* dyn) { EkfUpdateArgs aa = c; ek2_body(aa, dyn, cg::this_cluster()); });
+        int bad = EMU_LAUNCH_CLUSTER(arena, 8, EK2_NT, smem, emu_chain_update_body, &c);
         if (!fused) {
             EkfUpdateArgs u = c;
             u.mode = EKF_MODE_UPDATE; u.Rdiag = visR * visR * noiseScale; u.chi2Thr = 0.0;
             u.gateI = nullptr; u.counter = nullptr; u.gateD = slots + 8 * t; u.gateDExpect = 0.0; u.bump = counter; u.slot = slots + 8 * t + 4;
-            bad += emu::launch_cluster(arena, 8, EK2_NT, smem, [&](double* dyn) { EkfUpdateArgs aa = u; ek2_body(aa, dyn, cg::this_cluster()); });
+            bad += EMU_LAUNCH_CLUSTER(arena, 8, EK2_NT, smem, emu_chain_update_body, &u);
         } else {
             slots[8 * t + 4] = (slots[8 * t] == 0.0 && slots[8 * t + 2] == 0.0) ? 0.0 : 1.0;      // "updated" as the host derives it in fused mode
         }
@@ -190,3 +198,4 @@ int main(int argc, char**)
     orc_ekf_destroy(o);
     return fails;
 }
+#endif  // EMU_AS_LIB

@@ -60,6 +60,78 @@ int launch_cluster(Arena& arena, int nctas, int nthreads, size_t smemBytes, F&& 
     for (pid_t k : kids) { int st = 0; waitpid(k, &st, 0); if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) bad++; }
     return bad;
 }
+// ---- named cluster bodies ---------------------------------------------------------------------------------------------------
+// A harness writes the code one CTA runs as   EMU_CLUSTER_BODY(name) { ... uses ctx, dyn ... }   and launches it with
+// EMU_LAUNCH_CLUSTER(arena, nctas, nthreads, smemBytes, name, ctxPointer). Two ways to run it:
+//  * default: one forked process per CTA (launch_cluster above);
+//  * -DEMU_CLUSTER_THREADS: every CTA in the SAME process, so that ThreadSanitizer also sees the accesses between CTAs (distributed
+//    shared memory, exchanges through global memory). The static __shared__ variables still have to be per CTA, so the harness is
+//    compiled a second time as a shared library (-DEMU_AS_LIB -shared -fPIC -fvisibility=hidden), the executable copies that file
+//    once per CTA and dlopen()s every copy (own statics each); the executable itself contains no kernel body.
+typedef void (*emu_body_fn)(void* ctx, double* dyn);
+#define EMU_CLUSTER_BODY(name) extern "C" __attribute__((visibility("default"))) void name(void* ctx, double* dyn)
+
+#if defined(EMU_AS_LIB)
+}  // namespace emu
+extern "C" __attribute__((visibility("default"))) void emu_run_cta(emu::ClusterShared* sh, int rank, int nthreads, emu::emu_body_fn body, void* ctx)
+{
+    emu::cl = sh; emu::cl_rank = rank;
+    gridDim.x = sh->nctas; gridDim.y = gridDim.z = 1;
+    double* dyn = (double*)(sh->smemBase + (size_t)rank * sh->smemStride);
+    emu::launch_cta(nthreads, (unsigned)rank, [&] { body(ctx, dyn); });
+}
+namespace emu {
+#endif
+
+#if defined(EMU_CLUSTER_THREADS) && !defined(EMU_AS_LIB)
+}  // namespace emu
+#include <dlfcn.h>
+#include <fstream>
+#include <string>
+namespace emu {
+inline std::vector<void*>& cta_libs()
+{
+    static std::vector<void*> libs;
+    return libs;
+}
+inline void* cta_lib(int rank)
+{
+    auto& libs = cta_libs();
+    while ((int)libs.size() <= rank) {
+        const char* src = getenv("EMU_BODY_LIB");
+        if (!src) { fprintf(stderr, "EMU_BODY_LIB is not set\n"); exit(2); }
+        const std::string dst = std::string(src) + ".cta" + std::to_string(libs.size()) + "." + std::to_string((int)getpid()) + ".so";
+        { std::ifstream in(src, std::ios::binary); std::ofstream out(dst, std::ios::binary); out << in.rdbuf(); }
+        void* h = dlopen(dst.c_str(), RTLD_NOW | RTLD_LOCAL);
+        unlink(dst.c_str());
+        if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); exit(2); }
+        libs.push_back(h);
+    }
+    return libs[rank];
+}
+inline int launch_cluster_named(Arena& arena, int nctas, int nthreads, size_t smemBytes, const char* bodyName, void* ctx)
+{
+    ClusterShared* sh = arena.alloc<ClusterShared>(1);
+    sh->nctas = nctas; sh->smemStride = (smemBytes + 255) & ~(size_t)255;
+    sh->smemBase = arena.alloc<char>(sh->smemStride * nctas);
+    pthread_barrier_init(&sh->bar, nullptr, nctas);
+    typedef void (*run_fn)(ClusterShared*, int, int, emu_body_fn, void*);
+    std::vector<std::thread> th;
+    for (int c = 0; c < nctas; c++) {
+        void* h = cta_lib(c);
+        run_fn run = (run_fn)dlsym(h, "emu_run_cta");
+        emu_body_fn body = (emu_body_fn)dlsym(h, bodyName);
+        if (!run || !body) { fprintf(stderr, "emu: %s not found in the body library\n", bodyName); exit(2); }
+        th.emplace_back([=] { run(sh, c, nthreads, body, ctx); });
+    }
+    for (auto& t : th) t.join();
+    pthread_barrier_destroy(&sh->bar);
+    return 0;
+}
+#define EMU_LAUNCH_CLUSTER(arena, nctas, nthreads, smem, name, ctx) emu::launch_cluster_named(arena, nctas, nthreads, smem, #name, ctx)
+#else
+#define EMU_LAUNCH_CLUSTER(arena, nctas, nthreads, smem, name, ctx) emu::launch_cluster(arena, nctas, nthreads, smem, [&](double* dyn_) { name(ctx, dyn_); })
+#endif
 }  // namespace emu
 
 namespace cooperative_groups {

@@ -19,6 +19,12 @@ int orc_ekf_visual_check(const orc_ekf*, const double*, int, int, const double*,
 void orc_ekf_visual_update(orc_ekf*, const double*, int, int, const double*, const double*, double);
 }
 
+struct MultiCtx { EkfUpdateArgs a; EkfMultiList list; };
+#if !defined(EMU_CLUSTER_THREADS) || defined(EMU_AS_LIB)
+EMU_CLUSTER_BODY(emu_multi_body) { const MultiCtx& c = *(const MultiCtx*)ctx; ek2_multi_body(c.a, c.list, dyn, cg::this_cluster()); }
+#endif
+#ifndef EMU_AS_LIB
+
 static double rnd() { return rand() / (double)RAND_MAX - 0.5; }
 static double gauss() { double s = 0; for (int i = 0; i < 12; i++) s += rand() / (double)RAND_MAX; return s - 6.0; }
 
@@ -72,7 +78,8 @@ int main()
     a.b.m = m; a.b.P = P; a.b.res = res; a.b.cwork = cwork; a.b.N = N; a.b.trail = 20;
     a.op = EKF_OP_DENSE; a.noiseScale = noiseScale; a.normalizeAll = 1;
     const size_t smem = ek2_multi_smem_bytes(list, N, 8, &a.xCap, &a.tCap);
-    const int bad = emu::launch_cluster(arena, 8, EK2_NT, smem, [&](double* dyn) { ek2_multi_body(a, list, dyn, cg::this_cluster()); });
+    MultiCtx mc{a, list};
+    const int bad = EMU_LAUNCH_CLUSTER(arena, 8, EK2_NT, smem, emu_multi_body, &mc);
     int fails = bad;
     for (int k = 0; k < cnt; k++) {
         const bool checked = seq[k].mode != EKF_MODE_UPDATE;
@@ -92,3 +99,4 @@ int main()
     orc_ekf_destroy(o);
     return fails;
 }
+#endif  // EMU_AS_LIB

@@ -22,6 +22,12 @@ void orc_ekf_update_position(orc_ekf*, const double*, double);
 void orc_ekf_update_zupt(orc_ekf*, double);
 }
 
+// the code one CTA of the cluster runs (not compiled into the driver executable of the all-CTAs-in-one-process mode, emu_cluster.h)
+#if !defined(EMU_CLUSTER_THREADS) || defined(EMU_AS_LIB)
+EMU_CLUSTER_BODY(emu_update_body) { EkfUpdateArgs aa = *(const EkfUpdateArgs*)ctx; ek2_body(aa, dyn, cg::this_cluster()); }
+#endif
+#ifndef EMU_AS_LIB
+
 static double rnd() { return rand() / (double)RAND_MAX - 0.5; }
 static double gauss() { double s = 0; for (int i = 0; i < 12; i++) s += rand() / (double)RAND_MAX; return s - 6.0; }
 
@@ -128,7 +134,7 @@ int main(int argc, char** argv)
             orc_ekf_update_zupt(o, 1e-2);
         }
         const size_t smem = ek2_smem_bytes(cs.n, cs.l, N, cs.op == EKF_OP_AUGMENT, cs.C);
-        const int bad = emu::launch_cluster(arena, cs.C, EK2_NT, smem, [&](double* dyn) { EkfUpdateArgs aa = a; ek2_body(aa, dyn, cg::this_cluster()); });
+        const int bad = EMU_LAUNCH_CLUSTER(arena, cs.C, EK2_NT, smem, emu_update_body, &a);
         std::vector<double> om(N), oP((size_t)N * N);
         orc_ekf_download(o, om.data(), oP.data());
         double em = 0, eP = 0, pmax = 0, asym = 0;
@@ -151,3 +157,4 @@ int main(int argc, char** argv)
     }
     return fails;
 }
+#endif  // EMU_AS_LIB

@@ -147,37 +147,48 @@ def test_pyramid_kernel_body_on_host_emulator(tmp_path):
 
 def test_kernel_bodies_are_race_free_under_thread_sanitizer(tmp_path):
     """The emulator runs every CUDA thread as an OS thread and every barrier as a real barrier, so ThreadSanitizer sees a missing
-    __syncthreads / __syncwarp as a data race on the shared-memory arrays (inside a CTA; accesses between the CTAs of a cluster go
-    through a process-shared mapping and are not covered). All harnesses must come out without a report."""
+    __syncthreads / __syncwarp / cluster.sync as a data race. Single-CTA kernels run as they are; the cluster kernels run in the
+    all-CTAs-in-one-process mode of emu_cluster.h (every CTA out of its own copy of the harness's shared library), so that accesses
+    between CTAs -- distributed shared memory, exchanges through global memory -- are covered as well. No report allowed."""
+    import pytest
     probe = tmp_path / "probe.cpp"
     probe.write_text("int main() { return 0; }\n")
-    import pytest
     if subprocess.run(["g++", "-fsanitize=thread", str(probe), "-o", str(tmp_path / "probe")], capture_output=True).returncode != 0:
         pytest.skip("g++ -fsanitize=thread is not available")
     if subprocess.run([str(tmp_path / "probe")], capture_output=True).returncode != 0:
         pytest.skip("ThreadSanitizer binaries do not start here (address-space layout)")
-    objs = {}
     incdir = _lk_device_part(tmp_path)
     _pyr_device_part(tmp_path)
+    objs = {}
     for name in ("hv_oracle_ekf", "hv_oracle_tri", "hv_oracle_lk"):
         objs[name] = str(tmp_path / (name + ".o"))
         subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", name + ".c"), "-o", objs[name]])
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
-    runs = [("emu_track_model", ["hv_oracle_tri"], [[]], {}), ("emu_track_model", ["hv_oracle_tri"], [[]], {"EMU_NT": "512"}),
-            ("emu_update", ["hv_oracle_ekf"], [["0"], ["3"], ["6"], ["14"], ["20"]], {}), ("emu_multi", ["hv_oracle_ekf"], [[]], {}),
-            ("emu_chain", ["hv_oracle_ekf", "hv_oracle_tri"], [[], ["fused", "persist"]], {}), ("emu_predict", ["hv_oracle_ekf"], [[]], {}),
-            ("emu_lk", ["hv_oracle_lk"], [[]], {}), ("emu_pyramid", ["hv_oracle_lk"], [[]], {})]
+    flags = ["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-pthread", "-w", "-I" + incdir,
+             "-I" + os.path.join(ROOT, "tests", "emu", "stubs"), "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc")]
+    # (harness, oracle objects, argument lists, extra environment, cluster kernel?)
+    runs = [("emu_track_model", ["hv_oracle_tri"], [[]], {}, False), ("emu_track_model", ["hv_oracle_tri"], [[]], {"EMU_NT": "512"}, False),
+            ("emu_predict", ["hv_oracle_ekf"], [[]], {}, False), ("emu_lk", ["hv_oracle_lk"], [[]], {}, False), ("emu_pyramid", ["hv_oracle_lk"], [[]], {}, False),
+            ("emu_update", ["hv_oracle_ekf"], [["0"], ["3"], ["5"], ["6"], ["14"], ["20"]], {}, True), ("emu_multi", ["hv_oracle_ekf"], [[]], {}, True),
+            ("emu_chain", ["hv_oracle_ekf", "hv_oracle_tri"], [[], ["fused", "persist"]], {}, True)]
     built = {}
-    for src, deps, arglists, extra in runs:
+    for src, deps, arglists, extra, cluster in runs:
         if src not in built:
             exe = str(tmp_path / (src + "_tsan"))
-            subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-pthread", "-w", "-I" + incdir,
-                                   "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
-                                   "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
-                                   os.path.join(ROOT, "tests", "emu", src + ".cpp"), *[objs[d] for d in deps], "-lm", "-o", exe])
-            built[src] = exe
+            cpp = os.path.join(ROOT, "tests", "emu", src + ".cpp")
+            mode = ["-DEMU_CLUSTER_THREADS"] if cluster else []
+            subprocess.check_call(flags + mode + [cpp, *[objs[d] for d in deps], "-lm", "-ldl", "-o", exe])
+            lib = None
+            if cluster:
+                lib = str(tmp_path / ("lib" + src + "_body.so"))
+                subprocess.check_call(flags + mode + ["-DEMU_AS_LIB", "-shared", "-fPIC", "-fvisibility=hidden", cpp, "-o", lib])
+            built[src] = (exe, lib)
+        exe, lib = built[src]
         for args in arglists:
-            out = subprocess.run([built[src], *args], capture_output=True, text=True, timeout=1500, env=dict(env, **extra))
+            e = dict(env, **extra)
+            if lib:
+                e["EMU_BODY_LIB"] = lib
+            out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=1500, env=e)
             text = out.stdout + out.stderr
             assert "WARNING: ThreadSanitizer" not in text, (src, args, text[text.index("WARNING: ThreadSanitizer"):][:1500])
-            assert out.returncode == 0 and "FAIL" not in out.stdout, (src, args, out.stdout[-800:])
+            assert out.returncode == 0 and "FAIL" not in out.stdout and " ok" in out.stdout, (src, args, out.stdout[-800:] + out.stderr[-400:])
