@@ -300,36 +300,90 @@ class Session:
     D2H_BYTES = 2 * NFEAT * 13 + CHECKS * 24 + 8 * (20 + 7 * TRAIL)
 
 
+def gpu_uuid(torch, index):
+    """UUID of CUDA device `index` (CUDA_VISIBLE_DEVICES may renumber devices; NVML always sees all of them)."""
+    try:
+        return str(torch.cuda.get_device_properties(index).uuid)
+    except Exception:
+        return None
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe). The timed region of the default run
+    is ~100 ms, shorter than the start-up of an `nvidia-smi -lms` child (which is why earlier lines carried 0 samples), so the
+    sampler polls NVML in-process every 2 ms from a thread (the native timed loop releases the GIL); `nvidia-smi` is the
+    fallback when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, uuid=None):
+        self.rows, self.proc, self.nv, self.th = [], None, None, None
+        self.mask, self.sm, self.mx, self.source = 0, [], None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(uuid if str(uuid).startswith("GPU-") else f"GPU-{uuid}")
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(index)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)       # fail here rather than in the thread
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nv, self.h, self.source = nv, h, "nvml"
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while True:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(reasons(self.h))
+            except Exception:
+                pass
+            if self._stop.wait(0.002):
+                return
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self._stop.set()
+            self.th.join(timeout=1.0)
+            nv = self.nv
+            bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+            reasons = sorted(n for n, b in zip(self.NAMES, bits) if self.mask & int(b))
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                    "samples": len(self.sm), "source": "nvml, 2 ms poll"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
         time.sleep(0.15)
         self.proc.terminate()
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        reasons = sorted({self.NAMES[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def time_kernels(sess, reps=40):
@@ -521,7 +575,7 @@ def run_ours(args):
         for _ in range(warmup):
             step()
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
+        sampler = ClockSampler(local, gpu_uuid(torch, local)) if rank == 0 else None
         launches0 = sess.ctx.launches + sess.ctx_b.launches
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(sess.stream)
@@ -544,7 +598,7 @@ def run_ours(args):
         ms_dev_py, _, _ = timed_loop(sess.step_device, min(args.steps, 100), args.warmup)
         run_parallel("run_dev_native", args.warmup)
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
+        sampler = ClockSampler(local, gpu_uuid(torch, local)) if rank == 0 else None
         launches0 = launch_count()
         ms_local = run_parallel("run_dev_native", args.steps)
         launches = launch_count() - launches0

@@ -81,3 +81,40 @@ def test_reference_arm_under_torchrun_prints_one_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+
+
+def test_clock_sampler_polls_nvml_in_process_and_reports_throttle_reasons(monkeypatch):
+    """The timed region (~100 ms) is shorter than the start-up of an nvidia-smi child: the sampler must poll NVML itself.
+    A stand-in NVML module provides the clock and the reason bit mask."""
+    import time
+    import types
+    import pynvml as real
+    sys.path.insert(0, ROOT)
+    import bench
+    fake = types.ModuleType("pynvml")
+    for n in dir(real):
+        if n.startswith("nvmlClocks") or n.startswith("NVML_CLOCK"):
+            setattr(fake, n, getattr(real, n))
+    seen = {}
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByUUID = lambda u: seen.setdefault("uuid", u) and "h"
+    fake.nvmlDeviceGetHandleByIndex = lambda i: "h"
+    fake.nvmlDeviceGetClockInfo = lambda h, c: 1920
+    fake.nvmlDeviceGetMaxClockInfo = lambda h, c: 1965
+    fake.nvmlDeviceGetCurrentClocksEventReasons = lambda h: real.nvmlClocksThrottleReasonSwPowerCap | real.nvmlClocksThrottleReasonGpuIdle
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    c = bench.ClockSampler(0, "1234-abcd")
+    time.sleep(0.05)
+    d = c.stop()
+    assert seen["uuid"] == "GPU-1234-abcd"
+    assert d["sm_mhz"] == 1920.0 and d["sm_max_mhz"] == 1965.0 and d["samples"] >= 5
+    assert d["reasons"] == ["sw_power_cap"]                 # gpu_idle is not a slowdown reason
+
+
+def test_clock_sampler_degrades_without_nvml_and_nvidia_smi(monkeypatch):
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setitem(sys.modules, "pynvml", None)        # import fails
+    monkeypatch.setenv("PATH", "/nonexistent")
+    d = bench.ClockSampler(0).stop()
+    assert d["sm_mhz"] is None and d["samples"] == 0 and d["reasons"]
