@@ -80,3 +80,53 @@ def test_ctypes_structs_match_the_header(tmp_path):
         assert got[(cname, "size")] == ctypes.sizeof(py), cname
         for fname, _ in py._fields_:
             assert got[(cname, fname)] == getattr(py, fname).offset, (cname, fname)
+
+
+def _c_category(decl, is_return=False):
+    d = decl.strip()
+    if "*" in d or "[" in d:
+        return "ptr"
+    toks = re.sub(r"\bconst\b", "", d).split()
+    if not is_return and len(toks) > 1:
+        toks = toks[:-1]                                    # parameter name
+    return {"int": "int", "unsigned": "int", "double": "f64", "float": "f32", "size_t": "size", "long long": "i64", "void": "void"}[" ".join(toks)]
+
+
+def _ctypes_category(t):
+    if t is None:
+        return "void"
+    table = {ctypes.c_int: "int", ctypes.c_uint: "int", ctypes.c_double: "f64", ctypes.c_float: "f32", ctypes.c_size_t: "size",
+             ctypes.c_longlong: "i64", ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr"}
+    if t in table:
+        return table[t]
+    assert issubclass(t, (ctypes._Pointer, ctypes.Array)) or hasattr(t, "from_param"), t
+    return "ptr"
+
+
+def test_ctypes_prototypes_match_the_header():
+    """Every prototype of include/hybvio_b200.h against the argtypes / restype hybvio_b200/capi.py binds: same number of
+    arguments, same class (pointer, int, double, float, size_t, long long) at every position. A mismatch only shows up as a
+    crash or a garbage argument on the GPU box, so it is checked here."""
+    from hybvio_b200 import capi
+    lib = capi.load()
+    src = open(os.path.join(ROOT, "include", "hybvio_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = re.findall(r"^\s*((?:const\s+)?(?:long long|[A-Za-z_]\w*)\s*\**)\s*(hv_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.M)
+    assert len(protos) >= 70
+    assert sorted(p[1] for p in protos) == declared_symbols()
+    bad = []
+    for ret, name, args in protos:
+        f = getattr(lib, name)
+        want = [] if args.strip() in ("", "void") else [_c_category(a) for a in args.split(",")]
+        if f.argtypes is None:
+            if want:
+                bad.append((name, "no argtypes", want))
+            continue
+        got = [_ctypes_category(t) for t in f.argtypes]
+        if got != want:
+            bad.append((name, got, want))
+        # ctypes' default restype is c_int
+        if _ctypes_category(f.restype) != _c_category(ret, is_return=True):
+            bad.append((name, "restype", f.restype, ret))
+    assert not bad, bad
