@@ -28,6 +28,13 @@ import time
 
 import numpy as np
 
+T_PROCESS_START = time.monotonic()
+# Report-only extras (child processes, after the headline measurement): none is started later than EXTRAS_START_BY seconds into the
+# run and none gets more than EXTRAS_TIMEOUT seconds, so that the default `python bench.py` stays within a few minutes even if an
+# extra hangs (they exercise opt-in kernels). HV_BENCH_NO_EXTRAS=1 switches them off.
+EXTRAS_START_BY = 240.0
+EXTRAS_TIMEOUT = 150.0
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -686,8 +693,15 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(inputs, budget_s=args.cpu_budget)
         if world == 1 and nsess == 1 and not os.environ.get("HV_BENCH_CHILD"):
-            result["next_row_track_model"] = next_row_track_model()
-            result["persistent_updates_ab"] = persistent_updates_ab()
+            for key, extra in (("next_row_track_model", next_row_track_model), ("pyramid_gen2_ab", pyramid_gen2_ab),
+                               ("persistent_updates_ab", persistent_updates_ab)):
+                elapsed = time.monotonic() - T_PROCESS_START
+                if os.environ.get("HV_BENCH_NO_EXTRAS"):
+                    result[key] = {"skipped": "HV_BENCH_NO_EXTRAS"}
+                elif elapsed > EXTRAS_START_BY:
+                    result[key] = {"skipped": f"time budget: {elapsed:.0f} s into the run (limit {EXTRAS_START_BY:.0f} s)"}
+                else:
+                    result[key] = extra()
     for x in sessions:
         x.ctx.sync(); x.ctx_b.sync()
     if world > 1:
@@ -703,7 +717,7 @@ def next_row_track_model():
     the line above; not part of value / e2e."""
     import subprocess
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "track_model_bench.py")], capture_output=True, text=True, timeout=180)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "track_model_bench.py")], capture_output=True, text=True, timeout=EXTRAS_TIMEOUT)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if lines:                                         # the tool prints its line before it tears the context down
             d = json.loads(lines[-1])
@@ -722,7 +736,7 @@ def persistent_updates_ab():
     try:
         env = dict(os.environ, HV_EKF_PERSIST="1", HV_BENCH_CHILD="1")
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", "200", "--warmup", "20", "--e2e-steps", "50", "--no-cpu-baseline"],
-                           capture_output=True, text=True, timeout=300, env=env)
+                           capture_output=True, text=True, timeout=EXTRAS_TIMEOUT, env=env)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if not lines:
             return {"error": (r.stderr or r.stdout)[-400:]}
@@ -730,6 +744,26 @@ def persistent_updates_ab():
         return {"switch": "HV_EKF_PERSIST=1", "value": d.get("value"), "ms_per_step": d.get("ms_per_step"), "e2e": d.get("e2e", {}).get("value"),
                 "gpu_launches_per_step": d.get("gpu_launches_per_step"), "ekf_healthy_after_run": d.get("config", {}).get("ekf_healthy_after_run"),
                 "steps": d.get("steps")}
+    except Exception as ex:       # noqa: BLE001 -- report only
+        return {"error": repr(ex)[:400]}
+
+
+def pyramid_gen2_ab():
+    """A/B of the opt-in second-generation pyramid kernel (HV_PYR_V2=1: hv_pyr_fused2_kernel -- strips, two 16-bit lanes per register,
+    separable pyrDown; ~5x fewer instructions, bit-exact on the host emulator): the same bench in a child process with the switch set.
+    Report only -- value / e2e / roofline above are measured with the default kernel."""
+    try:
+        env = dict(os.environ, HV_PYR_V2="1", HV_BENCH_CHILD="1")
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", "200", "--warmup", "20", "--e2e-steps", "50", "--no-cpu-baseline"],
+                           capture_output=True, text=True, timeout=EXTRAS_TIMEOUT, env=env)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if not lines:
+            return {"error": (r.stderr or r.stdout)[-400:]}
+        d = json.loads(lines[-1])
+        pick = lambda table: {k: {"us_per_launch": v.get("us_per_launch"), "gbs": v.get("gbs"), "frac_of_hbm_peak": v.get("frac_of_hbm_peak")}
+                              for k, v in (d.get(table) or {}).items() if "pyr" in k}
+        return {"switch": "HV_PYR_V2=1", "value": d.get("value"), "ms_per_step": d.get("ms_per_step"), "e2e": d.get("e2e", {}).get("value"),
+                "kernels": pick("kernels"), "kernels_batched": pick("kernels_batched"), "steps": d.get("steps")}
     except Exception as ex:       # noqa: BLE001 -- report only
         return {"error": repr(ex)[:400]}
 

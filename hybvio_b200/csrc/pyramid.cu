@@ -17,7 +17,18 @@
 // HBM traffic per 752x480 image, maxLevel 3 (the algorithmic bytes of SURVEY.md 8(d)): read 360,960 +
 // write gray L1-3 118,440 + write deriv L0-3 1,917,600 = 2,397,000 B. Halo re-reads hit L2 (the whole input
 // is 361 KB).
+//
+// Two bodies share the geometry. hv_pyr_fused_kernel (first generation) evaluates every output pixel on its own: 18 byte loads
+// with a reflect-101 per tap for a Scharr item, 25 for a pyrDown pixel -- 36,000 warp instructions per CTA (ncu), i.e. the kernel
+// is issue-bound (8 % of the HBM roofline at 32 images per launch). hv_pyr_fused2_kernel keeps the data flow and removes the
+// instructions: a thread walks DOWN a 4-pixel-wide strip with the three input rows rolling through registers (one aligned 32-bit
+// + two byte loads per row instead of 18 byte loads), the Scharr arithmetic runs on two 16-bit lanes per register with biases
+// chosen so that every lane stays in [0, 65535] and the bias is exactly 0x8000 (removed by one XOR), pyrDown is separable along a
+// vertical strip of outputs (5 loads per source row shared by the outputs of the strip), reflection is one abs + one min
+// (levels of at least 8 x 8 pixels; smaller levels and partial 4-pixel items take the first-generation code), and the Scharr
+// pass of level k shares its barrier interval with the pyrDown pass that produces level k + 1.
 #include "hv_common.cuh"
+#include <stdlib.h>
 
 #ifndef PYR_NT
 #define PYR_NT 256
@@ -51,15 +62,11 @@ __device__ __forceinline__ void span_close(Span& s, int a, int b, int len)
 __device__ __forceinline__ int halo_of(int k, int top) { int h = 1; for (int i = top; i > k; --i) h = 2 * h + 2; return h; }
 
 // Scharr + store for the owned tile of level k. buf holds the stored region [sx.s0a.., sy.s0..] with pitch bp.
-__device__ __forceinline__ void emit_level(const HvLevel& L, const uint8_t* buf, int bp, int bx0, int by0,
-                                           const Span& sx, const Span& sy, bool writeGray, int itemW)
+__device__ __forceinline__ void emit_item(const HvLevel& L, const uint8_t* buf, int bp, int bx0, int by0,
+                                          const Span& sx, const Span& sy, bool writeGray, int itemW, int ix, int iy)
 {
     const int w = L.w, h = L.h;
-    const int tw = sx.o1 - sx.o0, th = sy.o1 - sy.o0;
-    const int itemsX = (tw + itemW - 1) / itemW;
-    const int nItems = itemsX * th;
-    for (int it = threadIdx.x; it < nItems; it += PYR_NT) {
-        const int iy = it / itemsX, ix = it - iy * itemsX;
+    {
         const int y = sy.o0 + iy, gx = sx.o0 + ix * itemW;
         const uint8_t* r0 = buf + (hv_reflect101(y - 1, h) - by0) * bp - bx0;
         const uint8_t* r1 = buf + (y - by0) * bp - bx0;
@@ -100,9 +107,199 @@ __device__ __forceinline__ void emit_level(const HvLevel& L, const uint8_t* buf,
     }
 }
 
-__global__ void __launch_bounds__(PYR_NT) hv_pyr_fused_kernel(PyrBuildList list)
+__device__ __forceinline__ void emit_level(const HvLevel& L, const uint8_t* buf, int bp, int bx0, int by0,
+                                           const Span& sx, const Span& sy, bool writeGray, int itemW)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    const int tw = sx.o1 - sx.o0, th = sy.o1 - sy.o0;
+    const int itemsX = (tw + itemW - 1) / itemW;
+    const int nItems = itemsX * th;
+    for (int it = threadIdx.x; it < nItems; it += PYR_NT) {
+        const int iy = it / itemsX, ix = it - iy * itemsX;
+        emit_item(L, buf, bp, bx0, by0, sx, sy, writeGray, itemW, ix, iy);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ second generation
+#ifdef HV_EMU
+#define PYR_ALIGNED(p, n) do { if (((uintptr_t)(p)) % (n)) { fprintf(stderr, "misaligned %d-byte access\n", (int)(n)); abort(); } } while (0)
+#else
+#define PYR_ALIGNED(p, n) do { } while (0)
+#endif
+
+// BORDER_REFLECT_101 for -len < p < 2 len - 1 (one reflection), len >= 2
+__device__ __forceinline__ int pyr_reflect1(int p, int len) { p = abs(p); return min(p, 2 * len - 2 - p); }
+
+// Scharr of a strip of the owned tile: columns gx .. gx + 3 (all owned; gx - bx0 is a multiple of 4), rows y0 .. y0 + RB - 1
+// (those below sy.o1 are skipped). Per register two 16-bit lanes = two neighbouring columns:
+//   A = (gx - 1, gx), B = (gx + 1, gx + 2), C = (gx + 3, gx + 4);   t0 = 3 (above + below) + 10 centre  (<= 4080),
+//   t1 = below - above + 2048  (in [1793, 2303]);   Ix = t0[i + 2] - t0[i] + 0x8000,   Iy = 3 (t1[i] + t1[i + 2]) + 10 t1[i + 1]
+//   = Iy_true + 16 * 2048 = Iy_true + 0x8000: both in [28688, 36848], and x + 0x8000 mod 2^16 = x ^ 0x8000.
+template <int RB>
+__device__ __forceinline__ void emit_strip(const HvLevel& L, const uint8_t* buf, int bp, int bx0, int by0, const Span& sx, const Span& sy,
+                                           bool writeGray, int ix, int iy)
+{
+    const int w = L.w, h = L.h;
+    const int gx = sx.o0 + 4 * ix, y0 = sy.o0 + RB * iy;
+    const int xc = gx - bx0, xl = pyr_reflect1(gx - 1, w) - bx0, xr = pyr_reflect1(gx + 4, w) - bx0;
+    uint32_t a[3], b[3], d[3], wb = 0, wd = 0;
+    auto load = [&](int y, uint32_t (&v)[3], uint32_t& word) {
+        const uint8_t* row = buf + (pyr_reflect1(y, h) - by0) * bp;
+        PYR_ALIGNED(row + xc, 4);
+        word = *reinterpret_cast<const uint32_t*>(row + xc);
+        const uint32_t l = row[xl], r = row[xr];
+        v[0] = __byte_perm(word, l, 0x5054);      // (l, c0)
+        v[1] = __byte_perm(word, 0u, 0x4241);     // (c1, c2)
+        v[2] = __byte_perm(word, r, 0x5453);      // (c3, r)
+    };
+    load(y0 - 1, a, wd);
+    load(y0, b, wb);
+    short2* drow = L.deriv + (size_t)y0 * L.dpitch + gx;
+    uint8_t* grow = L.gray + (size_t)y0 * L.gpitch + gx;
+    const int dpitch = L.dpitch, gpitch = L.gpitch;
+    PYR_ALIGNED(drow, 16); PYR_ALIGNED(L.deriv + dpitch, 16);
+    PYR_ALIGNED(grow, 4); PYR_ALIGNED(L.gray + gpitch, 4);
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        const int y = y0 + r;
+        if (y >= sy.o1) break;
+        load(y + 1, d, wd);
+        uint32_t t0[3], t1[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            t0[i] = (a[i] + d[i]) * 3u + b[i] * 10u;
+            t1[i] = d[i] + 0x08000800u - a[i];
+        }
+        const uint32_t gx01 = (t0[1] + 0x80008000u - t0[0]) ^ 0x80008000u;
+        const uint32_t gx23 = (t0[2] + 0x80008000u - t0[1]) ^ 0x80008000u;
+        const uint32_t m01 = __byte_perm(t1[0], t1[1], 0x5432), m23 = __byte_perm(t1[1], t1[2], 0x5432);
+        const uint32_t gy01 = ((t1[0] + t1[1]) * 3u + m01 * 10u) ^ 0x80008000u;
+        const uint32_t gy23 = ((t1[1] + t1[2]) * 3u + m23 * 10u) ^ 0x80008000u;
+        int4 v;
+        v.x = (int)__byte_perm(gx01, gy01, 0x5410); v.y = (int)__byte_perm(gx01, gy01, 0x7632);
+        v.z = (int)__byte_perm(gx23, gy23, 0x5410); v.w = (int)__byte_perm(gx23, gy23, 0x7632);
+        *reinterpret_cast<int4*>(drow) = v;
+        if (writeGray) *reinterpret_cast<uint32_t*>(grow) = wb;
+        drow += dpitch; grow += gpitch;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { a[i] = b[i]; b[i] = d[i]; }
+        wb = wd;
+    }
+}
+
+// pyrDown (5x5 [1 4 6 4 1]^2, (sum + 128) >> 8) of RS vertically adjacent outputs (cx, cy0 .. cy0 + RS - 1), rows >= cyEnd skipped:
+// the horizontal sums of the 2 RS + 3 source rows are formed once and shared. A vertical sum is at most 65,280.
+template <int RS>
+__device__ __forceinline__ void pyrdown_strip(const uint8_t* src, int sp, int sx0, int sy0, int sw, int sh, uint8_t* dst, int dp, int dx0, int dy0,
+                                              int cx, int cy0, int cyEnd)
+{
+    int xs[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) xs[i] = pyr_reflect1(2 * cx - 2 + i, sw) - sx0;
+    int hs[2 * RS + 3];
+#pragma unroll
+    for (int j = 0; j < 2 * RS + 3; j++) {
+        const int yy = min(2 * cy0 - 2 + j, 2 * cyEnd);       // rows past the last output's window: clamped, results unused
+        const uint8_t* row = src + (pyr_reflect1(yy, sh) - sy0) * sp;
+        hs[j] = row[xs[2]] * 6 + (row[xs[1]] + row[xs[3]]) * 4 + row[xs[0]] + row[xs[4]];
+    }
+    uint8_t* out = dst + (cy0 - dy0) * dp + (cx - dx0);
+#pragma unroll
+    for (int r = 0; r < RS; r++)
+        if (cy0 + r < cyEnd)
+            out[r * dp] = (uint8_t)((hs[2 * r] + hs[2 * r + 4] + (hs[2 * r + 1] + hs[2 * r + 3]) * 4 + hs[2 * r + 2] * 6 + 128) >> 8);
+}
+
+// pyrDown of the stored region of level k, one output pixel per work item (first generation; any level size)
+__device__ __forceinline__ void pyrdown_generic(const uint8_t* src, int sp, int sx0, int sy0, int sw, int sh, uint8_t* dst, int dp, int dx0,
+                                                const Span& dsx, const Span& dsy)
+{
+    const int cw = dsx.s1 - dsx.s0 + 1, ch = dsy.s1 - dsy.s0 + 1;
+    for (int it = threadIdx.x; it < cw * ch; it += PYR_NT) {
+        const int iy = it / cw, ix = it - iy * cw;
+        const int cx = dsx.s0 + ix, cy = dsy.s0 + iy;
+        int xs[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) xs[i] = hv_reflect101(2 * cx - 2 + i, sw) - sx0;
+        int acc = 0;
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const uint8_t* row = src + (hv_reflect101(2 * cy - 2 + j, sh) - sy0) * sp;
+            int hsum = row[xs[2]] * 6 + (row[xs[1]] + row[xs[3]]) * 4 + row[xs[0]] + row[xs[4]];
+            acc += hsum * (j == 2 ? 6 : (j == 1 || j == 3) ? 4 : 1);
+        }
+        dst[iy * dp + cx - dx0] = (uint8_t)((acc + 128) >> 8);
+    }
+}
+
+// The same for TWO neighbouring outputs (cx odd, cx + 1) whose 7 source columns 2 cx - 2 .. 2 cx + 4 need no reflection: they are the
+// first 7 bytes of two aligned 32-bit words q0..q7 (the buffer origin and 2 cx - 2 are multiples of 4), and the horizontal pass runs on
+// two 16-bit lanes (lo = cx, hi = cx + 1): 1 q0 + 4 q1 + 6 q2 + 4 q3 + 1 q4 | 1 q2 + 4 q3 + 6 q4 + 4 q5 + 1 q6 (<= 4080 per lane), the
+// vertical pass as well (<= 65,408 with the rounding term: no carry between the lanes).
+template <int RS>
+__device__ __forceinline__ void pyrdown_pair(const uint8_t* src, int sp, int sx0, int sy0, int sh, uint8_t* dst, int dp, int dx0, int dy0,
+                                             int cx, int cy0, int cyEnd)
+{
+    const int xo = 2 * cx - 2 - sx0;
+    uint32_t hs[2 * RS + 3];
+#pragma unroll
+    for (int j = 0; j < 2 * RS + 3; j++) {
+        const int yy = min(2 * cy0 - 2 + j, 2 * cyEnd);
+        const uint8_t* row = src + (pyr_reflect1(yy, sh) - sy0) * sp + xo;
+        PYR_ALIGNED(row, 4);
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row), w1 = *reinterpret_cast<const uint32_t*>(row + 4);
+        const uint32_t e0 = __byte_perm(w0, 0u, 0x4240), o0 = __byte_perm(w0, 0u, 0x4341);     // (q0, q2), (q1, q3)
+        const uint32_t e1 = __byte_perm(w1, 0u, 0x4240), o1 = __byte_perm(w1, 0u, 0x4341);     // (q4, q6), (q5, q7)
+        const uint32_t t2 = __byte_perm(e0, e1, 0x5432), t3 = __byte_perm(o0, o1, 0x5432);     // (q2, q4), (q3, q5)
+        hs[j] = e0 + e1 + (o0 + t3) * 4u + t2 * 6u;
+    }
+    uint8_t* out = dst + (cy0 - dy0) * dp + (cx - dx0);
+#pragma unroll
+    for (int r = 0; r < RS; r++)
+        if (cy0 + r < cyEnd) {
+            const uint32_t v = hs[2 * r] + hs[2 * r + 4] + (hs[2 * r + 1] + hs[2 * r + 3]) * 4u + hs[2 * r + 2] * 6u + 0x00800080u;
+            out[r * dp] = (uint8_t)(v >> 8);
+            out[r * dp + 1] = (uint8_t)(v >> 24);
+        }
+}
+
+// pyrDown of the stored region of level k, second generation: work item = (pair of columns (2 p + 1, 2 p + 2), strip of RS rows)
+template <int RS>
+__device__ __forceinline__ void pyrdown_fast(const uint8_t* src, int sp, int sx0, int sy0, int sw, int sh, uint8_t* dst, int dp, int dx0,
+                                             const Span& dsx, const Span& dsy)
+{
+    const int p0 = (dsx.s0 - 1) >> 1, np = ((dsx.s1 - 1) >> 1) - p0 + 1;
+    const int ch = dsy.s1 - dsy.s0 + 1, ns = (ch + RS - 1) / RS;
+    for (int it = threadIdx.x; it < np * ns; it += PYR_NT) {
+        const int is = it / np, ip = it - is * np;
+        const int ca = 2 * (p0 + ip) + 1, cy0 = dsy.s0 + RS * is;
+        const bool va = ca >= dsx.s0, vb = ca + 1 <= dsx.s1;
+        if (va && vb && ca >= 1 && 2 * ca + 4 <= sw - 1) {
+            pyrdown_pair<RS>(src, sp, sx0, sy0, sh, dst, dp, dx0, dsy.s0, ca, cy0, dsy.s1 + 1);
+        } else {
+            if (va) pyrdown_strip<RS>(src, sp, sx0, sy0, sw, sh, dst, dp, dx0, dsy.s0, ca, cy0, dsy.s1 + 1);
+            if (vb) pyrdown_strip<RS>(src, sp, sx0, sy0, sw, sh, dst, dp, dx0, dsy.s0, ca + 1, cy0, dsy.s1 + 1);
+        }
+    }
+}
+
+// Scharr pass of the second generation: full 4-pixel items as strips of RB rows, a partial item column (level width not a multiple
+// of 4 at the right image border) through the first-generation item
+template <int RB>
+__device__ __forceinline__ void emit_fast(const HvLevel& L, const uint8_t* buf, int bp, int bx0, int by0, const Span& sx, const Span& sy, bool writeGray)
+{
+    const int tw = sx.o1 - sx.o0, th = sy.o1 - sy.o0;
+    const int full = tw >> 2, ns = (th + RB - 1) / RB;
+    for (int it = threadIdx.x; it < full * ns; it += PYR_NT) {
+        const int iy = it / full, ix = it - iy * full;
+        emit_strip<RB>(L, buf, bp, bx0, by0, sx, sy, writeGray, ix, iy);
+    }
+    if (tw & 3)
+        for (int iy = threadIdx.x; iy < th; iy += PYR_NT) emit_item(L, buf, bp, bx0, by0, sx, sy, writeGray, 4, full, iy);
+}
+
+template <bool FAST>
+__device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem)
+{
     const HvPyrDesc& P = list.table[list.idx[blockIdx.z]];
     const int nl = P.nlevels, top = nl - 1;
     const int tx = blockIdx.x, ty = blockIdx.y;
@@ -111,6 +308,7 @@ __global__ void __launch_bounds__(PYR_NT) hv_pyr_fused_kernel(PyrBuildList list)
     // ---- geometry (identical in every thread)
     Span sx[HV_MAX_LEVELS], sy[HV_MAX_LEVELS];
     int bufOff[HV_MAX_LEVELS], bufPitch[HV_MAX_LEVELS];
+    int ox[HV_MAX_LEVELS];      // level coordinate of column 0 of the level's shared-memory buffer
     {
         int off = 0;
         for (int k = 0; k < nl; k++) {
@@ -129,6 +327,8 @@ __global__ void __launch_bounds__(PYR_NT) hv_pyr_fused_kernel(PyrBuildList list)
             span_close(sx[k], nax, nbx, w);
             span_close(sy[k], nay, nby, h);
             ax = sx[k].s0; bx = sx[k].s1; ay = sy[k].s0; by = sy[k].s1;
+            // second generation: the owned tile starts on a 4-byte boundary of the buffer (32-bit shared-memory loads of the strips)
+            ox[k] = FAST ? sx[k].s0 - ((sx[k].s0 - sx[k].o0) & 3) : sx[k].s0;
         }
     }
 
@@ -157,37 +357,59 @@ __global__ void __launch_bounds__(PYR_NT) hv_pyr_fused_kernel(PyrBuildList list)
                 for (int c = lane; c < nbytes; c += 32) b0[r * bp + c] = __ldg(src + c);
             }
         }
-        sx[0].s0 = x0a;   // stored origin is the aligned one
+        sx[0].s0 = x0a;   // stored origin is the aligned one (o0 is a multiple of the tile size, so this is ox[0] as well)
+        ox[0] = x0a;
     }
     __syncthreads();
-    emit_level(P.lv[0], smem + bufOff[0], bufPitch[0], sx[0].s0, sy[0].s0, sx[0], sy[0], ext != nullptr, 4);
 
-    // ---- coarser levels: 5x5 [1 4 6 4 1]^2, (sum+128)>>8, reflect-101 inside the finer level
-    for (int k = 1; k < nl; k++) {
-        const uint8_t* src = smem + bufOff[k - 1];
-        const int sp = bufPitch[k - 1], sx0 = sx[k - 1].s0, sy0 = sy[k - 1].s0;
-        const int sw = P.lv[k - 1].w, sh = P.lv[k - 1].h;
-        uint8_t* dst = smem + bufOff[k];
-        const int dp = bufPitch[k];
-        const int cw = sx[k].s1 - sx[k].s0 + 1, ch = sy[k].s1 - sy[k].s0 + 1;
-        for (int it = threadIdx.x; it < cw * ch; it += PYR_NT) {
-            const int iy = it / cw, ix = it - iy * cw;
-            const int cx = sx[k].s0 + ix, cy = sy[k].s0 + iy;
-            int xs[5];
-#pragma unroll
-            for (int i = 0; i < 5; i++) xs[i] = hv_reflect101(2 * cx - 2 + i, sw) - sx0;
-            int acc = 0;
-#pragma unroll
-            for (int j = 0; j < 5; j++) {
-                const uint8_t* row = src + (hv_reflect101(2 * cy - 2 + j, sh) - sy0) * sp;
-                int hsum = row[xs[2]] * 6 + (row[xs[1]] + row[xs[3]]) * 4 + row[xs[0]] + row[xs[4]];
-                acc += hsum * (j == 2 ? 6 : (j == 1 || j == 3) ? 4 : 1);
-            }
-            dst[iy * dp + ix] = (uint8_t)((acc + 128) >> 8);
+    if (!FAST) {
+        emit_level(P.lv[0], smem + bufOff[0], bufPitch[0], sx[0].s0, sy[0].s0, sx[0], sy[0], ext != nullptr, 4);
+        // ---- coarser levels: 5x5 [1 4 6 4 1]^2, (sum+128)>>8, reflect-101 inside the finer level
+        for (int k = 1; k < nl; k++) {
+            uint8_t* dst = smem + bufOff[k];
+            pyrdown_generic(smem + bufOff[k - 1], bufPitch[k - 1], sx[k - 1].s0, sy[k - 1].s0, P.lv[k - 1].w, P.lv[k - 1].h, dst, bufPitch[k], sx[k].s0, sx[k], sy[k]);
+            __syncthreads();
+            emit_level(P.lv[k], dst, bufPitch[k], sx[k].s0, sy[k].s0, sx[k], sy[k], true, min(4, HV_PYR_TILE >> k));
+        }
+        return;
+    }
+
+    // ---- second generation: between two barriers, the Scharr pass of level k and the pyrDown pass that produces level k + 1
+    // (both only read the buffer of level k)
+    for (int k = 0; k < nl; k++) {
+        const HvLevel L = P.lv[k];      // by value: the stores below go through generic pointers and would force re-loads of the table
+        const uint8_t* buf = smem + bufOff[k];
+        const int bp = bufPitch[k];
+        const bool writeGray = k > 0 || ext != nullptr;
+        if ((HV_PYR_TILE >> k) >= 4 && L.w >= 8 && L.h >= 8) {
+            if (k == 0) emit_fast<4>(L, buf, bp, ox[k], sy[k].s0, sx[k], sy[k], writeGray);
+            else if (k == 1) emit_fast<2>(L, buf, bp, ox[k], sy[k].s0, sx[k], sy[k], writeGray);
+            else emit_fast<1>(L, buf, bp, ox[k], sy[k].s0, sx[k], sy[k], writeGray);
+        } else {
+            emit_level(L, buf, bp, ox[k], sy[k].s0, sx[k], sy[k], writeGray, min(4, HV_PYR_TILE >> k));
+        }
+        if (k + 1 == nl) break;
+        uint8_t* dst = smem + bufOff[k + 1];
+        if (L.w >= 8 && L.h >= 8) {
+            if (k == 0) pyrdown_fast<4>(buf, bp, ox[k], sy[k].s0, L.w, L.h, dst, bufPitch[k + 1], ox[k + 1], sx[k + 1], sy[k + 1]);
+            else pyrdown_fast<2>(buf, bp, ox[k], sy[k].s0, L.w, L.h, dst, bufPitch[k + 1], ox[k + 1], sx[k + 1], sy[k + 1]);
+        } else {
+            pyrdown_generic(buf, bp, ox[k], sy[k].s0, L.w, L.h, dst, bufPitch[k + 1], ox[k + 1], sx[k + 1], sy[k + 1]);
         }
         __syncthreads();
-        emit_level(P.lv[k], dst, dp, sx[k].s0, sy[k].s0, sx[k], sy[k], true, min(4, HV_PYR_TILE >> k));
     }
+}
+
+__global__ void __launch_bounds__(PYR_NT) hv_pyr_fused_kernel(PyrBuildList list)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    pyr_body<false>(list, smem);
+}
+
+__global__ void __launch_bounds__(PYR_NT) hv_pyr_fused2_kernel(PyrBuildList list)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    pyr_body<true>(list, smem);
 }
 
 // Host-side launch helper (called from capi.cu). Shared memory is sized for the deepest pyramid in the list.
@@ -206,9 +428,13 @@ cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* id
                                 int n, int w0, int h0, int maxNlevels, cudaStream_t stream)
 {
     static bool attrSet = false;
+    // HV_PYR_V2=1: the second-generation body (strips, two 16-bit lanes per register); opt-in until it has been timed on a B200
+    static const bool gen2 = getenv("HV_PYR_V2") != nullptr && getenv("HV_PYR_V2")[0] != '0';
     size_t smem = hv_pyr_smem_bytes(maxNlevels);
     if (!attrSet) {
         cudaError_t e = cudaFuncSetAttribute(hv_pyr_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(hv_pyr_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attrSet = true;
     }
@@ -221,7 +447,8 @@ cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* id
             list.srcPitch[i] = src ? srcPitch[base + i] : 0;
         }
         dim3 grid((w0 + HV_PYR_TILE - 1) / HV_PYR_TILE, (h0 + HV_PYR_TILE - 1) / HV_PYR_TILE, list.n);
-        hv_pyr_fused_kernel<<<grid, PYR_NT, smem, stream>>>(list);
+        if (gen2) hv_pyr_fused2_kernel<<<grid, PYR_NT, smem, stream>>>(list);
+        else hv_pyr_fused_kernel<<<grid, PYR_NT, smem, stream>>>(list);
     }
     return cudaGetLastError();
 }

@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A GPU test that hangs (a kernel that never finishes blocks its caller inside the CUDA runtime, where no Python signal handler
+    runs) must not hold the GPU box until the session limit: with pytest-timeout present every gpu test gets a 15-minute limit
+    enforced from a watchdog thread (stack dump + exit)."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for it in items:
+        if it.get_closest_marker("gpu") and not it.get_closest_marker("timeout"):
+            it.add_marker(pytest.mark.timeout(900, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def oracle_lk():
     """The plain-C restatement (oracle/hv_oracle_lk.c); built on demand."""

@@ -133,4 +133,17 @@ inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p
 struct uchar4 { unsigned char x, y, z, w; };
 struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
 inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { return uchar4{x, y, z, w}; }
+// prmt.b32 in its default mode: selector nibble n picks byte (n & 7) of {b, a} (a = bytes 0-3, b = bytes 4-7); bit 3 replicates the sign
+inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
+{
+    const unsigned long long src = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        const unsigned n = (sel >> (4 * i)) & 0xf;
+        unsigned byte = (unsigned)(src >> (8 * (n & 7))) & 0xff;
+        if (n & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
 inline unsigned char* emu_dynamic_smem = nullptr;   // stands in for `extern __shared__` arrays (set by the harness before a launch)

@@ -17,11 +17,14 @@ void orc_pyr_free(orc_pyramid* p);
 
 static unsigned hash2(int x, int y) { unsigned h = (unsigned)x * 374761393u + (unsigned)y * 668265263u; h = (h ^ (h >> 13)) * 1274126177u; return h ^ (h >> 16); }
 
-static int run(int W, int H, int maxLevel, bool fromSrc)
+static int g_win = 31;        // buildOpticalFlowPyramid stops at the first level that is not larger than the window
+static int g_pattern = 0;     // 1: only 0 and 255 (largest gradients: the 16-bit lanes of the second generation at their limits)
+
+static int run(int W, int H, int maxLevel, bool fromSrc, bool gen2)
 {
-    const int WIN = 31;
+    const int WIN = g_win;
     std::vector<uint8_t> img((size_t)W * H);
-    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) img[(size_t)y * W + x] = (uint8_t)((hash2(x / 3, y / 5) & 0x7f) + (hash2(x, y) & 0x7f));
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) img[(size_t)y * W + x] = g_pattern ? (uint8_t)((hash2(x / 2, y / 2) & 1) ? 255 : 0) : (uint8_t)((hash2(x / 3, y / 5) & 0x7f) + (hash2(x, y) & 0x7f));
     orc_pyramid* po = orc_pyr_create(img.data(), W, H, W, WIN, maxLevel);
     const int nl = orc_pyr_levels(po);
     HvPyrDesc desc; memset(&desc, 0, sizeof(desc));
@@ -43,7 +46,7 @@ static int run(int W, int H, int maxLevel, bool fromSrc)
     gridDim.x = gx; gridDim.y = gy; gridDim.z = 1;
     for (int ty = 0; ty < gy; ty++) for (int tx = 0; tx < gx; tx++) {
         emu::block_y = ty; emu::block_z = 0;
-        emu::launch_cta(PYR_NT, (unsigned)tx, [&] { hv_pyr_fused_kernel(list); });
+        emu::launch_cta(PYR_NT, (unsigned)tx, [&] { if (gen2) hv_pyr_fused2_kernel(list); else hv_pyr_fused_kernel(list); });
     }
     emu::block_y = 0;
     long long badG = 0, badD = 0, pix = 0;
@@ -60,7 +63,7 @@ static int run(int W, int H, int maxLevel, bool fromSrc)
             pix++;
         }
     }
-    printf("%dx%d, %d levels, frame %s: %lld pixels, %lld gray / %lld gradient differences  %s\n", W, H, nl, fromSrc ? "read from a separate buffer" : "copied into level 0", pix, badG, badD,
+    printf("%s %dx%d, %d levels, frame %s: %lld pixels, %lld gray / %lld gradient differences  %s\n", gen2 ? "gen2" : "gen1", W, H, nl, fromSrc ? "read from a separate buffer" : "copied into level 0", pix, badG, badD,
            badG + badD == 0 ? "ok" : "FAIL");
     for (int lv = 0; lv < nl; lv++) { free(gbuf[lv]); free(dbuf[lv]); }
     orc_pyr_free(po);
@@ -70,10 +73,27 @@ static int run(int W, int H, int maxLevel, bool fromSrc)
 int main()
 {
     int fails = 0;
-    fails += run(320, 240, 3, false);
-    fails += run(320, 240, 3, true);
-    fails += run(188, 120, 2, false);          // widths that are not multiples of the tile, odd level sizes
-    fails += run(150, 101, 3, true);
-    fails += run(752, 480, 3, false);          // BASELINE config 2: 4 levels
+    for (int gen2 = 0; gen2 < 2; gen2++) {
+        fails += run(320, 240, 3, false, gen2);
+        fails += run(320, 240, 3, true, gen2);
+        fails += run(188, 120, 2, false, gen2);          // widths that are not multiples of the tile, odd level sizes
+        fails += run(150, 101, 3, true, gen2);
+        fails += run(752, 480, 3, false, gen2);          // BASELINE config 2: 4 levels
+    }
+    // second generation only: level widths that are not multiples of 4 (partial items), levels below 8 pixels (first-generation
+    // fallback inside the kernel), deeper pyramids (tiles of 4 and 2 pixels at levels 4 and 5), a single tile, TUM-VI's 512 x 512
+    fails += run(203, 77, 3, false, true);
+    fails += run(67, 66, 3, true, true);
+    fails += run(40, 24, 3, false, true);
+    fails += run(130, 70, 5, false, true);
+    fails += run(512, 512, 3, false, true);
+    g_win = 3;
+    fails += run(130, 70, 5, false, false);
+    fails += run(130, 70, 5, false, true);
+    fails += run(97, 45, 4, true, true);
+    g_win = 31;
+    g_pattern = 1;
+    fails += run(320, 240, 3, false, true);
+    fails += run(203, 77, 3, true, true);
     return fails;
 }

@@ -1,5 +1,6 @@
-"""Times hv_pyr_fused_kernel (2 images 752x480, device-resident frames) for the library named by HV_LIB_PATH and checks
-one pyramid against the C oracle (bit-exact)."""
+"""Times the fused pyramid kernel (2 images 752x480 per launch, and 32 per launch; device-resident frames) for the library named by
+HV_LIB_PATH and checks one pyramid against the C oracle (bit-exact). HV_PYR_V2=1 selects hv_pyr_fused2_kernel:
+    python tests/tools/pyr_time.py; HV_PYR_V2=1 python tests/tools/pyr_time.py"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -32,3 +33,17 @@ for lv in range(o.levels):
     og, od = o.download(lv, padded=False)
     ok = ok and np.array_equal(g, og) and np.array_equal(d, od)
 print(f"{os.path.basename(capi.LIB_PATH)}: pyramid pair {s.elapsed_time(e) * 1e3 / 200:.2f} us per launch, bit-exact vs oracle: {ok}")
+# 32 images per launch (the kernels_batched line of bench.py): 16 stereo pairs, every image into its own pyramid
+big = [hv.pyramid(W, H) for _ in range(32)]
+imgs = [frames[i % 16, i // 16] for i in range(32)]
+for i in range(3):
+    hv.build_pyramids(big, imgs, device=True)
+hv.sync()
+with torch.cuda.stream(st):
+    s.record(st)
+    for i in range(50):
+        hv.build_pyramids(big, imgs, device=True)
+    e.record(st)
+e.synchronize()
+us = s.elapsed_time(e) * 1e3 / 50
+print(f"{'hv_pyr_fused2_kernel' if os.environ.get('HV_PYR_V2') else 'hv_pyr_fused_kernel'}: 32 images per launch {us:.2f} us = {32 * 2397000 / us * 1e-3:.0f} GB/s algorithmic")
