@@ -328,7 +328,11 @@ int hv_lk_track_batch_device(hv_ctx* c, const hv_lk_job* jobs, int njobs, int ma
 int hv_lk_track_device(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* dPrev, float* dNext, uint8_t* dStatus,
                        int32_t* dTs, int n, int useInitial, int maxIter, double eps, double minEig)
 {
-    if (n == 0) return HV_OK;
+    if (!c || n < 0) { hv_set_error("hv_lk_track_device: invalid argument"); return HV_ERR_INVALID; }
+    if (n == 0) {                 // optical_flow.cpp:41-44: empty input, empty output (the pyramids are still validated)
+        int rc = lk_check_pair("hv_lk_track_device", c, prev, next);
+        return rc;
+    }
     hv_lk_job j; j.prev = prev; j.next = next; j.d_prev_xy = dPrev; j.d_next_xy = dNext; j.d_status = dStatus;
     j.d_track_status = dTs; j.n = n; j.use_initial = useInitial;
     return hv_lk_track_batch_device(c, &j, 1, maxIter, eps, minEig);

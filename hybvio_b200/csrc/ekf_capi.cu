@@ -150,6 +150,7 @@ extern "C" {
 
 void hv_ekf_default_params(hv_ekf_params* p)
 {
+    if (!p) return;
     // codegen/parameter_definitions.c:68-160
     p->camera_trail_length = 20; p->hybrid_map_size = 0;
     p->noise_scale = 100; p->gravity = 9.819;

@@ -130,3 +130,40 @@ def test_ctypes_prototypes_match_the_header():
         if _ctypes_category(f.restype) != _c_category(ret, is_return=True):
             bad.append((name, "restype", f.restype, ret))
     assert not bad, bad
+
+
+_NULL_PROBE = r"""
+import ctypes, sys
+sys.path.insert(0, {root!r})
+from hybvio_b200 import capi
+lib = capi.load()
+for name in {names!r}:
+    f = getattr(lib, name)
+    args = []
+    for t in (f.argtypes or []):
+        if t in (ctypes.c_int, ctypes.c_uint, ctypes.c_size_t, ctypes.c_longlong):
+            args.append(0)
+        elif t in (ctypes.c_double, ctypes.c_float):
+            args.append(0.0)
+        else:
+            args.append(None)
+    print(name, flush=True)
+    r = f(*args)
+    print(name, "->", r, flush=True)
+print("probe complete")
+"""
+
+
+def test_every_entry_point_survives_null_arguments():
+    """No exceptions and no crashes across the boundary: every function of the header called with NULL handles / NULL pointers / zeros
+    (in a child process, so that a crash is a test failure with the function's name and not the end of the test run). Functions that
+    return a status must not report success for a NULL handle (destroy / release of NULL are no-ops, like free)."""
+    import subprocess
+    import sys
+    names = declared_symbols()
+    r = subprocess.run([sys.executable, "-c", _NULL_PROBE.format(root=ROOT, names=names)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "probe complete" in r.stdout, "crashed in " + r.stdout.strip().splitlines()[-1] + "\n" + r.stderr[-500:]
+    results = dict(l.split(" -> ") for l in r.stdout.splitlines() if " -> " in l)
+    noop_ok = {"hv_ctx_destroy", "hv_ekf_destroy", "hv_pyr_release", "hv_device_count", "hv_ctx_launch_count", "hv_ekf_was_stationary"}
+    wrong = [n for n, v in results.items() if v.lstrip("-").isdigit() and int(v) >= 0 and n not in noop_ok]
+    assert not wrong, f"status 0 for NULL arguments: {wrong}"
