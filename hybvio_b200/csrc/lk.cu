@@ -462,7 +462,9 @@ cudaError_t hv_launch_lk(const LkLaunch& L, int win, cudaStream_t stream)
     static const bool forceWarp = getenv("HV_LK_WARP_PER_FEATURE") != nullptr;
     long long total = 0;
     for (int i = 0; i < L.njobs; i++) total += L.jobs[i].n;
-    if (!forceWarp && total <= 640) {
+    // HV_LK_CTA_MAX=n moves the switch-over point (A/B of the batched launches: 8 sessions = 1200 features)
+    static const long long ctaMax = getenv("HV_LK_CTA_MAX") ? atoll(getenv("HV_LK_CTA_MAX")) : 640;
+    if (!forceWarp && total <= ctaMax) {
         dim3 grid(maxN, L.njobs), block(LKC_NW * 32);
         switch (win) {
             case 31: hv_lk_cta_kernel<31><<<grid, block, 0, stream>>>(L); break;
