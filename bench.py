@@ -693,7 +693,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(inputs, budget_s=args.cpu_budget)
         if world == 1 and nsess == 1 and not os.environ.get("HV_BENCH_CHILD"):
-            for key, extra in (("next_row_track_model", next_row_track_model), ("pyramid_gen2_ab", pyramid_gen2_ab),
+            for key, extra in (("next_row_track_model", next_row_track_model), ("tracker_variants_ab", tracker_variants_ab),
                                ("persistent_updates_ab", persistent_updates_ab)):
                 elapsed = time.monotonic() - T_PROCESS_START
                 if os.environ.get("HV_BENCH_NO_EXTRAS"):
@@ -748,12 +748,14 @@ def persistent_updates_ab():
         return {"error": repr(ex)[:400]}
 
 
-def pyramid_gen2_ab():
-    """A/B of the opt-in second-generation pyramid kernel (HV_PYR_V2=1: hv_pyr_fused2_kernel -- strips, two 16-bit lanes per register,
-    separable pyrDown; ~5x fewer instructions, bit-exact on the host emulator): the same bench in a child process with the switch set.
-    Report only -- value / e2e / roofline above are measured with the default kernel."""
+def tracker_variants_ab():
+    """A/B of the two opt-in tracker kernels, both bit-exact on the host emulator: HV_PYR_V2=1 (hv_pyr_fused2_kernel -- strips, two 16-bit
+    lanes per register, separable pyrDown; ~5x fewer instructions; the pyramid is not on the critical path of a single session, so look at
+    its kernel rows) and HV_LK_CTA_WARPS=8 (8 instead of 4 warps per feature in hv_lk_cta_kernel<31>: half the window rows on the
+    dependent chain of an iteration; LK IS on the critical path, so `value` moves with it). The same bench in a child process with both
+    switches set. Report only -- value / e2e / roofline above are measured with the default kernels."""
     try:
-        env = dict(os.environ, HV_PYR_V2="1", HV_BENCH_CHILD="1")
+        env = dict(os.environ, HV_PYR_V2="1", HV_LK_CTA_WARPS="8", HV_BENCH_CHILD="1")
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", "200", "--warmup", "20", "--e2e-steps", "50", "--no-cpu-baseline"],
                            capture_output=True, text=True, timeout=EXTRAS_TIMEOUT, env=env)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -761,8 +763,8 @@ def pyramid_gen2_ab():
             return {"error": (r.stderr or r.stdout)[-400:]}
         d = json.loads(lines[-1])
         pick = lambda table: {k: {"us_per_launch": v.get("us_per_launch"), "gbs": v.get("gbs"), "frac_of_hbm_peak": v.get("frac_of_hbm_peak")}
-                              for k, v in (d.get(table) or {}).items() if "pyr" in k}
-        return {"switch": "HV_PYR_V2=1", "value": d.get("value"), "ms_per_step": d.get("ms_per_step"), "e2e": d.get("e2e", {}).get("value"),
+                              for k, v in (d.get(table) or {}).items() if "pyr" in k or "lk" in k}
+        return {"switches": "HV_PYR_V2=1 HV_LK_CTA_WARPS=8", "value": d.get("value"), "ms_per_step": d.get("ms_per_step"), "e2e": d.get("e2e", {}).get("value"),
                 "kernels": pick("kernels"), "kernels_batched": pick("kernels_batched"), "steps": d.get("steps")}
     except Exception as ex:       # noqa: BLE001 -- report only
         return {"error": repr(ex)[:400]}

@@ -252,18 +252,19 @@ __global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32) hv_lk_kernel(LkLaunch L
 // iteration, double-buffered). Because the sums are exact integers, the result is BIT-IDENTICAL to the warp-per-feature
 // kernel above for any split. Used when the launch has few features (one VIO session: 150 features on 148 SMs), where
 // latency, not throughput, is what counts.
-#define LKC_NW 4
-template <int WIN>
-__global__ void __launch_bounds__(LKC_NW * 32) hv_lk_cta_kernel(LkLaunch L)
+#define LKC_NW 4      // default warps per feature; HV_LK_CTA_WARPS=8 selects the 8-warp instantiation (window 31 only): half the rows
+                      // per warp on the dependent chain of an iteration, twice the partial sums to add (A/B pending)
+template <int WIN, int NW = LKC_NW>
+__global__ void __launch_bounds__(NW * 32) hv_lk_cta_kernel(LkLaunch L)
 {
-    constexpr int RPW = (WIN + LKC_NW - 1) / LKC_NW;      // window rows per warp
+    constexpr int RPW = (WIN + NW - 1) / NW;      // window rows per warp
     const LkJob& job = L.jobs[blockIdx.y];
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, tid = threadIdx.x;
     const int f = blockIdx.x;
     if (f >= job.n) return;
     __shared__ __align__(16) uint8_t reg[LK_REG_H * LK_REG_W];
-    __shared__ long long s_pa[LKC_NW][3];
-    __shared__ long long s_pb[2][LKC_NW][2];
+    __shared__ long long s_pa[NW][3];
+    __shared__ long long s_pb[2][NW][2];
 
     const HvPyrDesc& PI = L.table[job.prevIdx];
     const HvPyrDesc& PJ = L.table[job.nextIdx];
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(LKC_NW * 32) hv_lk_cta_kernel(LkLaunch L)
         }
         long long tA11 = 0, tA12 = 0, tA22 = 0;
 #pragma unroll
-        for (int w = 0; w < LKC_NW; w++) { tA11 += s_pa[w][0]; tA12 += s_pa[w][1]; tA22 += s_pa[w][2]; }
+        for (int w = 0; w < NW; w++) { tA11 += s_pa[w][0]; tA12 += s_pa[w][1]; tA22 += s_pa[w][2]; }
         const float A11 = __fmul_rn(__ll2float_rn(tA11), FLT_SCALE);
         const float A12 = __fmul_rn(__ll2float_rn(tA12), FLT_SCALE);
         const float A22 = __fmul_rn(__ll2float_rn(tA22), FLT_SCALE);
@@ -373,8 +374,8 @@ __global__ void __launch_bounds__(LKC_NW * 32) hv_lk_cta_kernel(LkLaunch L)
                 if (rx0 >= 0 && rx0 + LK_REG_W <= LJ.w && ry0 >= 0 && ry0 + LK_REG_H <= LJ.h) {
                     const uint8_t* g0 = LJ.gray + (size_t)ry0 * LJ.gpitch + rx0;
 #pragma unroll
-                    for (int u = 0; u < (LK_REG_H * (LK_REG_W / 4) + LKC_NW * 32 - 1) / (LKC_NW * 32); u++) {
-                        const int idx = tid + u * LKC_NW * 32;
+                    for (int u = 0; u < (LK_REG_H * (LK_REG_W / 4) + NW * 32 - 1) / (NW * 32); u++) {
+                        const int idx = tid + u * NW * 32;
                         if (idx < LK_REG_H * (LK_REG_W / 4)) {
                             const int row = idx / (LK_REG_W / 4), wd = idx - row * (LK_REG_W / 4);
                             reinterpret_cast<uint32_t*>(reg)[idx] = __ldg(reinterpret_cast<const uint32_t*>(g0 + (size_t)row * LJ.gpitch) + wd);
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(LKC_NW * 32) hv_lk_cta_kernel(LkLaunch L)
                     const bool hasB = lane + 32 < LK_REG_W;
                     const int cB = hv_reflect101(rx0 + (hasB ? lane + 32 : lane), LJ.w);
 #pragma unroll 4
-                    for (int row = wrp; row < LK_REG_H; row += LKC_NW) {
+                    for (int row = wrp; row < LK_REG_H; row += NW) {
                         const uint8_t* grow = LJ.gray + (size_t)hv_reflect101(ry0 + row, LJ.h) * LJ.gpitch;
                         const uint8_t a0 = __ldg(grow + cA), b0 = __ldg(grow + cB);
                         reg[row * LK_REG_W + lane] = a0;
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(LKC_NW * 32) hv_lk_cta_kernel(LkLaunch L)
             __syncthreads();
             long long tb1 = 0, tb2 = 0;
 #pragma unroll
-            for (int w = 0; w < LKC_NW; w++) { tb1 += s_pb[j & 1][w][0]; tb2 += s_pb[j & 1][w][1]; }
+            for (int w = 0; w < NW; w++) { tb1 += s_pb[j & 1][w][0]; tb2 += s_pb[j & 1][w][1]; }
             const float fb1 = __fmul_rn(__ll2float_rn(tb1), FLT_SCALE);
             const float fb2 = __fmul_rn(__ll2float_rn(tb2), FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
@@ -466,6 +467,11 @@ cudaError_t hv_launch_lk(const LkLaunch& L, int win, cudaStream_t stream)
     static const long long ctaMax = getenv("HV_LK_CTA_MAX") ? atoll(getenv("HV_LK_CTA_MAX")) : 640;
     if (!forceWarp && total <= ctaMax) {
         dim3 grid(maxN, L.njobs), block(LKC_NW * 32);
+        static const bool eightWarps = getenv("HV_LK_CTA_WARPS") != nullptr && atoi(getenv("HV_LK_CTA_WARPS")) == 8;
+        if (eightWarps && win == 31) {
+            hv_lk_cta_kernel<31, 8><<<grid, dim3(8 * 32), 0, stream>>>(L);
+            return cudaGetLastError();
+        }
         switch (win) {
             case 31: hv_lk_cta_kernel<31><<<grid, block, 0, stream>>>(L); break;
             case 21: hv_lk_cta_kernel<21><<<grid, block, 0, stream>>>(L); break;

@@ -76,7 +76,7 @@ int main()
         init[2 * i] = prev[2 * i] + 2.3f + (float)((rand() / (double)RAND_MAX) * 6 - 3); init[2 * i + 1] = prev[2 * i + 1] - 1.7f + (float)((rand() / (double)RAND_MAX) * 6 - 3);
     }
     int fails = 0;
-    for (int useInitial = 0; useInitial < 2; useInitial++) for (int variant = 0; variant < 2; variant++) {
+    for (int useInitial = 0; useInitial < 2; useInitial++) for (int variant = 0; variant < 3; variant++) {
         std::vector<float> onext = init, knext = init; std::vector<uint8_t> ost(N), kst(N, 7); std::vector<int32_t> kts(N, -1);
         orc_lk(pa, pb, prev.data(), onext.data(), ost.data(), N, MAXL, 20, 0.03, useInitial, 1e-3, 1);
         LkLaunch L; memset(&L, 0, sizeof(L));
@@ -86,6 +86,9 @@ int main()
         if (variant == 0) {
             gridDim.x = N; gridDim.y = 1;
             for (int f = 0; f < N; f++) emu::launch_cta(LKC_NW * 32, (unsigned)f, [&] { hv_lk_cta_kernel<31>(L); });
+        } else if (variant == 2) {                                    // 8 warps per feature (HV_LK_CTA_WARPS=8): 4 window rows per warp, the last warp owns 3
+            gridDim.x = N; gridDim.y = 1;
+            for (int f = 0; f < N; f++) emu::launch_cta(8 * 32, (unsigned)f, [&] { hv_lk_cta_kernel<31, 8>(L); });
         } else {
             const int ctas = (N + LK_WARPS_PER_CTA - 1) / LK_WARPS_PER_CTA;
             gridDim.x = ctas; gridDim.y = 1;
@@ -97,7 +100,7 @@ int main()
             const bool same = kst[i] == ost[i] && memcmp(&knext[2 * i], &onext[2 * i], 8) == 0;
             if (!same) { bad++; if (bad < 4) printf("  feature %d: kernel (%g, %g) st %d, oracle (%g, %g) st %d\n", i, knext[2 * i], knext[2 * i + 1], kst[i], onext[2 * i], onext[2 * i + 1], ost[i]); }
         }
-        printf("%s, useInitial=%d: %d features, %d tracked, %d differ from the oracle (bit-exact end points + status)  %s\n", variant == 0 ? "hv_lk_cta_kernel<31>" : "hv_lk_kernel<31>    ",
+        printf("%s, useInitial=%d: %d features, %d tracked, %d differ from the oracle (bit-exact end points + status)  %s\n", variant == 0 ? "hv_lk_cta_kernel<31>" : variant == 2 ? "hv_lk_cta_kernel<31, 8>" : "hv_lk_kernel<31>    ",
                useInitial, N, tracked, bad, bad == 0 ? "ok" : "FAIL");
         fails += bad != 0;
     }
