@@ -296,7 +296,7 @@ def test_chain_with_separate_check_and_update_launches():
     if os.environ.get("HV_CHAIN_SEPARATE") or os.environ.get("HV_CHAIN_PERSIST"):
         pytest.skip("this is a child run")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-k", "device_gated_chain", "-p", "no:cacheprovider"],
-                       env={**os.environ, "HV_CHAIN_SEPARATE": "1"}, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=600)
+                       env={**os.environ, "HV_CHAIN_SEPARATE": "1", "HV_GPU_FIRST_RUN_STRICT": "1"}, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]
 
 
@@ -307,5 +307,5 @@ def test_chain_as_one_persistent_launch():
     if os.environ.get("HV_CHAIN_PERSIST") or os.environ.get("HV_CHAIN_SEPARATE"):
         pytest.skip("this is a child run")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-k", "device_gated_chain", "-p", "no:cacheprovider"],
-                       env={**os.environ, "HV_CHAIN_PERSIST": "1"}, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=600)
+                       env={**os.environ, "HV_CHAIN_PERSIST": "1", "HV_GPU_FIRST_RUN_STRICT": "1"}, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]

@@ -5,6 +5,7 @@
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
+export HV_GPU_FIRST_RUN_STRICT=1      # plain pass / fail for the tests that have not run on hardware yet (tests/conftest.py)
 echo "== new GPU tests"; timeout 900 python -m pytest tests/test_zz_gpu_track_model.py -q -m gpu -x 2>&1 | tail -15 | tee gpurun_out/tm_tests.log
 echo "== measurement tool"; timeout 300 python tests/tools/track_model_bench.py > gpurun_out/tm_bench.json 2> gpurun_out/tm_bench.err; tail -c 3000 gpurun_out/tm_bench.json
 echo "== A/B: separate check / update launches, no PDL"

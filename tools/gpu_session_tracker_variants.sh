@@ -5,6 +5,7 @@
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
+export HV_GPU_FIRST_RUN_STRICT=1      # plain pass / fail for the tests that have not run on hardware yet (tests/conftest.py)
 echo "== parity: every pyramid + LK GPU test with HV_PYR_V2=1"
 timeout 900 python -m pytest tests/test_zzz_gpu_tracker_variants.py -q -m gpu -x 2>&1 | tail -8 | tee gpurun_out/pyr2_tests.log
 echo "== timing A/B (CUDA events, 2 images and 32 images per launch)"
