@@ -344,7 +344,27 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
         const bool aligned = ext == nullptr || ((((size_t)ext) | (size_t)list.srcPitch[blockIdx.z]) & 3) == 0;
         const uint8_t* base = ext ? ext : L0.gray;
         const int pitch = ext ? list.srcPitch[blockIdx.z] : L0.gpitch;
-        if (aligned && (ext == nullptr || x0a + words * 4 <= pitch)) {
+        if (FAST && aligned && (ext == nullptr || x0a + words * 4 <= pitch)) {
+            // four rows per warp in flight: the loads of a staging pass are independent, but one load -> store pair per iteration
+            // costs a full L2 / HBM round trip per row (13 per warp for the 108 rows of a 4-level tile)
+            constexpr int NW = PYR_NT / 32;
+            for (int c0 = 0; c0 < words; c0 += 32) {
+                const int c = c0 + lane;
+                for (int r = wrp; r < rows; r += 4 * NW) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int rr = r + u * NW;
+                        v[u] = (rr < rows && c < words) ? __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)(sy[0].s0 + rr) * pitch + x0a) + c) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int rr = r + u * NW;
+                        if (rr < rows && c < words) reinterpret_cast<uint32_t*>(b0 + rr * bp)[c] = v[u];
+                    }
+                }
+            }
+        } else if (aligned && (ext == nullptr || x0a + words * 4 <= pitch)) {
             for (int r = wrp; r < rows; r += PYR_NT / 32) {
                 const uint32_t* src = reinterpret_cast<const uint32_t*>(base + (size_t)(sy[0].s0 + r) * pitch + x0a);
                 uint32_t* dst = reinterpret_cast<uint32_t*>(b0 + r * bp);
