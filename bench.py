@@ -32,8 +32,8 @@ T_PROCESS_START = time.monotonic()
 # Report-only extras (child processes, after the headline measurement): none is started later than EXTRAS_START_BY seconds into the
 # run and none gets more than EXTRAS_TIMEOUT seconds, so that the default `python bench.py` stays within a few minutes even if an
 # extra hangs (they exercise opt-in kernels). HV_BENCH_NO_EXTRAS=1 switches them off.
-EXTRAS_START_BY = 240.0
-EXTRAS_TIMEOUT = 150.0
+EXTRAS_START_BY = 180.0
+EXTRAS_TIMEOUT = 120.0
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
