@@ -318,7 +318,7 @@ def gpu_uuid(torch, index):
 class ClockSampler:
     """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe). The timed region of the default run
     is ~100 ms, shorter than the start-up of an `nvidia-smi -lms` child (which is why earlier lines carried 0 samples), so the
-    sampler polls NVML in-process every 2 ms from a thread (the native timed loop releases the GIL); `nvidia-smi` is the
+    sampler polls NVML in-process every 10 ms from a thread (the native timed loop releases the GIL); `nvidia-smi` is the
     fallback when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -365,7 +365,7 @@ class ClockSampler:
                 self.mask |= int(reasons(self.h))
             except Exception:
                 pass
-            if self._stop.wait(0.002):
+            if self._stop.wait(0.010):
                 return
 
     def _read(self):
@@ -381,7 +381,7 @@ class ClockSampler:
                     nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
             reasons = sorted(n for n, b in zip(self.NAMES, bits) if self.mask & int(b))
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
-                    "samples": len(self.sm), "source": "nvml, 2 ms poll"}
+                    "samples": len(self.sm), "source": "nvml, 10 ms poll"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
         time.sleep(0.15)

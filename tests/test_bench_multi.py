@@ -106,10 +106,10 @@ def test_clock_sampler_polls_nvml_in_process_and_reports_throttle_reasons(monkey
     fake.nvmlDeviceGetCurrentClocksEventReasons = lambda h: real.nvmlClocksThrottleReasonSwPowerCap | real.nvmlClocksThrottleReasonGpuIdle
     monkeypatch.setitem(sys.modules, "pynvml", fake)
     c = bench.ClockSampler(0, "1234-abcd")
-    time.sleep(0.05)
+    time.sleep(0.08)
     d = c.stop()
     assert seen["uuid"] == "GPU-1234-abcd"
-    assert d["sm_mhz"] == 1920.0 and d["sm_max_mhz"] == 1965.0 and d["samples"] >= 5
+    assert d["sm_mhz"] == 1920.0 and d["sm_max_mhz"] == 1965.0 and d["samples"] >= 3
     assert d["reasons"] == ["sw_power_cap"]                 # gpu_idle is not a slowdown reason
 
 
