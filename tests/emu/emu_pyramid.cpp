@@ -17,6 +17,7 @@ void orc_pyr_free(orc_pyramid* p);
 
 static unsigned hash2(int x, int y) { unsigned h = (unsigned)x * 374761393u + (unsigned)y * 668265263u; h = (h ^ (h >> 13)) * 1274126177u; return h ^ (h >> 16); }
 
+static int g_fill = 0x00;      // initial content of the shared-memory arena: a result that depends on bytes no thread wrote changes with it
 static int g_win = 31;        // buildOpticalFlowPyramid stops at the first level that is not larger than the window
 static int g_pattern = 0;     // 1: only 0 and 255 (largest gradients: the 16-bit lanes of the second generation at their limits)
 
@@ -40,7 +41,7 @@ static int run(int W, int H, int maxLevel, bool fromSrc, bool gen2)
     if (!fromSrc) for (int y = 0; y < H; y++) memcpy(gbuf[0] + (size_t)y * desc.lv[0].gpitch, img.data() + (size_t)y * W, W);       // the frame was copied into level 0
     PyrBuildList list; memset(&list, 0, sizeof(list));
     list.table = &desc; list.n = 1; list.idx[0] = 0; list.src[0] = fromSrc ? img.data() : nullptr; list.srcPitch[0] = fromSrc ? W : 0;
-    std::vector<unsigned char> smem(hv_pyr_smem_bytes(nl) + 64);
+    std::vector<unsigned char> smem(hv_pyr_smem_bytes(nl) + 64, (unsigned char)g_fill);
     emu_dynamic_smem = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     const int gx = (W + HV_PYR_TILE - 1) / HV_PYR_TILE, gy = (H + HV_PYR_TILE - 1) / HV_PYR_TILE;
     gridDim.x = gx; gridDim.y = gy; gridDim.z = 1;
@@ -92,6 +93,11 @@ int main()
     fails += run(130, 70, 5, false, true);
     fails += run(97, 45, 4, true, true);
     g_win = 31;
+    g_fill = 0xFF;                                      // the packed pyrDown reads one byte past its 7 taps: must not reach a result
+    fails += run(752, 480, 3, false, true);
+    fails += run(203, 77, 3, true, true);
+    fails += run(130, 70, 5, false, true);
+    g_fill = 0x00;
     g_pattern = 1;
     fails += run(320, 240, 3, false, true);
     fails += run(203, 77, 3, true, true);
