@@ -134,7 +134,9 @@ __device__ __forceinline__ int pyr_reflect1(int p, int len) { p = abs(p); return
 //   A = (gx - 1, gx), B = (gx + 1, gx + 2), C = (gx + 3, gx + 4);   t0 = 3 (above + below) + 10 centre  (<= 4080),
 //   t1 = below - above + 2048  (in [1793, 2303]);   Ix = t0[i + 2] - t0[i] + 0x8000,   Iy = 3 (t1[i] + t1[i + 2]) + 10 t1[i + 1]
 //   = Iy_true + 16 * 2048 = Iy_true + 0x8000: both in [28688, 36848], and x + 0x8000 mod 2^16 = x ^ 0x8000.
-template <int RB>
+// PLAIN: all RB + 2 input rows lie inside the image and all RB output rows are owned -- no reflection, no row test, the row
+// addresses are compile-time multiples of the pitch off one base.
+template <int RB, bool PLAIN>
 __device__ __forceinline__ void emit_strip(const HvLevel& L, const uint8_t* buf, int bp, int bx0, int by0, const Span& sx, const Span& sy,
                                            bool writeGray, int ix, int iy)
 {
@@ -142,8 +144,9 @@ __device__ __forceinline__ void emit_strip(const HvLevel& L, const uint8_t* buf,
     const int gx = sx.o0 + 4 * ix, y0 = sy.o0 + RB * iy;
     const int xc = gx - bx0, xl = pyr_reflect1(gx - 1, w) - bx0, xr = pyr_reflect1(gx + 4, w) - bx0;
     uint32_t a[3], b[3], d[3], wb = 0, wd = 0;
+    const uint8_t* base = buf + (y0 - 1 - by0) * bp;                   // row y0 - 1 (PLAIN)
     auto load = [&](int y, uint32_t (&v)[3], uint32_t& word) {
-        const uint8_t* row = buf + (pyr_reflect1(y, h) - by0) * bp;
+        const uint8_t* row = PLAIN ? base + (y - (y0 - 1)) * bp : buf + (pyr_reflect1(y, h) - by0) * bp;
         PYR_ALIGNED(row + xc, 4);
         word = *reinterpret_cast<const uint32_t*>(row + xc);
         const uint32_t l = row[xl], r = row[xr];
@@ -161,7 +164,7 @@ __device__ __forceinline__ void emit_strip(const HvLevel& L, const uint8_t* buf,
 #pragma unroll
     for (int r = 0; r < RB; r++) {
         const int y = y0 + r;
-        if (y >= sy.o1) break;
+        if (!PLAIN && y >= sy.o1) break;
         load(y + 1, d, wd);
         uint32_t t0[3], t1[3];
 #pragma unroll
@@ -235,16 +238,17 @@ __device__ __forceinline__ void pyrdown_generic(const uint8_t* src, int sp, int 
 // first 7 bytes of two aligned 32-bit words q0..q7 (the buffer origin and 2 cx - 2 are multiples of 4), and the horizontal pass runs on
 // two 16-bit lanes (lo = cx, hi = cx + 1): 1 q0 + 4 q1 + 6 q2 + 4 q3 + 1 q4 | 1 q2 + 4 q3 + 6 q4 + 4 q5 + 1 q6 (<= 4080 per lane), the
 // vertical pass as well (<= 65,408 with the rounding term: no carry between the lanes).
-template <int RS>
+template <int RS, bool PLAIN>
 __device__ __forceinline__ void pyrdown_pair(const uint8_t* src, int sp, int sx0, int sy0, int sh, uint8_t* dst, int dp, int dx0, int dy0,
                                              int cx, int cy0, int cyEnd)
 {
     const int xo = 2 * cx - 2 - sx0;
+    const uint8_t* base = src + (2 * cy0 - 2 - sy0) * sp + xo;        // PLAIN: all 2 RS + 3 source rows inside the image, all RS outputs wanted
     uint32_t hs[2 * RS + 3];
 #pragma unroll
     for (int j = 0; j < 2 * RS + 3; j++) {
         const int yy = min(2 * cy0 - 2 + j, 2 * cyEnd);
-        const uint8_t* row = src + (pyr_reflect1(yy, sh) - sy0) * sp + xo;
+        const uint8_t* row = PLAIN ? base + j * sp : src + (pyr_reflect1(yy, sh) - sy0) * sp + xo;
         PYR_ALIGNED(row, 4);
         const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row), w1 = *reinterpret_cast<const uint32_t*>(row + 4);
         const uint32_t e0 = __byte_perm(w0, 0u, 0x4240), o0 = __byte_perm(w0, 0u, 0x4341);     // (q0, q2), (q1, q3)
@@ -255,7 +259,7 @@ __device__ __forceinline__ void pyrdown_pair(const uint8_t* src, int sp, int sx0
     uint8_t* out = dst + (cy0 - dy0) * dp + (cx - dx0);
 #pragma unroll
     for (int r = 0; r < RS; r++)
-        if (cy0 + r < cyEnd) {
+        if (PLAIN || cy0 + r < cyEnd) {
             const uint32_t v = hs[2 * r] + hs[2 * r + 4] + (hs[2 * r + 1] + hs[2 * r + 3]) * 4u + hs[2 * r + 2] * 6u + 0x00800080u;
             out[r * dp] = (uint8_t)(v >> 8);
             out[r * dp + 1] = (uint8_t)(v >> 24);
@@ -274,7 +278,8 @@ __device__ __forceinline__ void pyrdown_fast(const uint8_t* src, int sp, int sx0
         const int ca = 2 * (p0 + ip) + 1, cy0 = dsy.s0 + RS * is;
         const bool va = ca >= dsx.s0, vb = ca + 1 <= dsx.s1;
         if (va && vb && ca >= 1 && 2 * ca + 4 <= sw - 1) {
-            pyrdown_pair<RS>(src, sp, sx0, sy0, sh, dst, dp, dx0, dsy.s0, ca, cy0, dsy.s1 + 1);
+            if (cy0 >= 1 && 2 * cy0 + 2 * RS <= sh - 1 && cy0 + RS <= dsy.s1 + 1) pyrdown_pair<RS, true>(src, sp, sx0, sy0, sh, dst, dp, dx0, dsy.s0, ca, cy0, dsy.s1 + 1);
+            else pyrdown_pair<RS, false>(src, sp, sx0, sy0, sh, dst, dp, dx0, dsy.s0, ca, cy0, dsy.s1 + 1);
         } else {
             if (va) pyrdown_strip<RS>(src, sp, sx0, sy0, sw, sh, dst, dp, dx0, dsy.s0, ca, cy0, dsy.s1 + 1);
             if (vb) pyrdown_strip<RS>(src, sp, sx0, sy0, sw, sh, dst, dp, dx0, dsy.s0, ca + 1, cy0, dsy.s1 + 1);
@@ -291,7 +296,9 @@ __device__ __forceinline__ void emit_fast(const HvLevel& L, const uint8_t* buf, 
     const int full = tw >> 2, ns = (th + RB - 1) / RB;
     for (int it = threadIdx.x; it < full * ns; it += PYR_NT) {
         const int iy = it / full, ix = it - iy * full;
-        emit_strip<RB>(L, buf, bp, bx0, by0, sx, sy, writeGray, ix, iy);
+        const int y0 = sy.o0 + RB * iy;
+        if (y0 >= 1 && y0 + RB <= L.h - 1 && y0 + RB <= sy.o1) emit_strip<RB, true>(L, buf, bp, bx0, by0, sx, sy, writeGray, ix, iy);
+        else emit_strip<RB, false>(L, buf, bp, bx0, by0, sx, sy, writeGray, ix, iy);
     }
     if (tw & 3)
         for (int iy = threadIdx.x; iy < th; iy += PYR_NT) emit_item(L, buf, bp, bx0, by0, sx, sy, writeGray, 4, full, iy);
@@ -460,7 +467,7 @@ __global__ void __launch_bounds__(PYR_NT) hv_pyr_fused_kernel(PyrBuildList list)
     pyr_body<false>(list, smem);
 }
 
-__global__ void __launch_bounds__(PYR_NT) hv_pyr_fused2_kernel(PyrBuildList list)
+__global__ void __launch_bounds__(PYR_NT, 4) hv_pyr_fused2_kernel(PyrBuildList list)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     pyr_body<true>(list, smem);
