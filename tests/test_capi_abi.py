@@ -167,3 +167,18 @@ def test_every_entry_point_survives_null_arguments():
     noop_ok = {"hv_ctx_destroy", "hv_ekf_destroy", "hv_pyr_release", "hv_device_count", "hv_ctx_launch_count", "hv_ekf_was_stationary"}
     wrong = [n for n, v in results.items() if v.lstrip("-").isdigit() and int(v) >= 0 and n not in noop_ok]
     assert not wrong, f"status 0 for NULL arguments: {wrong}"
+
+
+def test_every_environment_switch_of_the_library_is_documented():
+    """Every getenv("HV_...") of the library / adapters appears in INTEGRATION.md's table of switches."""
+    import glob
+    names = set()
+    for pat in ("hybvio_b200/csrc/*.cu", "hybvio_b200/csrc/*.cuh", "hybvio_b200/host/*.cpp", "hybvio_b200/host/*.cu", "hybvio_b200/*.py"):
+        for f in glob.glob(os.path.join(ROOT, pat)):
+            src = open(f).read()
+            names |= set(re.findall(r'getenv\("(HV_[A-Z0-9_]+)"\)', src))
+            names |= set(re.findall(r'environ(?:\.get\(|\[)"(HV_[A-Z0-9_]+)"', src))
+    assert len(names) >= 10
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, f"not documented in INTEGRATION.md: {missing}"
