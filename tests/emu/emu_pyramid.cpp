@@ -92,6 +92,8 @@ int main()
     fails += run(130, 70, 5, false, false);
     fails += run(130, 70, 5, false, true);
     fails += run(97, 45, 4, true, true);
+    fails += run(400, 300, 5, false, true);             // 6 levels, 94-pixel halo at level 0: staged rows of more than 32 words
+    fails += run(400, 300, 5, false, false);
     g_win = 31;
     g_fill = 0xFF;                                      // the packed pyrDown reads one byte past its 7 taps: must not reach a result
     fails += run(752, 480, 3, false, true);

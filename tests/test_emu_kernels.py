@@ -144,7 +144,7 @@ def test_pyramid_kernel_body_on_host_emulator(tmp_path):
                            os.path.join(ROOT, "tests", "emu", "emu_pyramid.cpp"), obj, "-lm", "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count("  ok") == 23 and "FAIL" not in out.stdout
+    assert out.stdout.count("  ok") == 25 and "FAIL" not in out.stdout
     assert "gen1 752x480, 4 levels" in out.stdout and "gen2 752x480, 4 levels" in out.stdout and "gen2 130x70, 5 levels" in out.stdout
 
 
