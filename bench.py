@@ -799,7 +799,20 @@ class RefSession:
         self.t, self.k, self.prev_j = 0.0, 0, 0
         self.ekf.initialize_orientation(inputs.imu[0, 3:])
 
-    def step(self):
+    STAGES = ("pyramid", "lk", "ekf_predict", "ekf_check", "ekf_update", "ekf_augment")
+
+    def step(self, stage_s=None):
+        """One stereo frame. stage_s: optional dict that accumulates wall-clock seconds per stage (SURVEY.md 8(d) per-stage rows)."""
+        clock = time.perf_counter
+        t_ = clock()
+
+        def lap(name):
+            nonlocal t_
+            if stage_s is not None:
+                now = clock()
+                stage_s[name] = stage_s.get(name, 0.0) + now - t_
+                t_ = now
+
         self.k += 1
         j = frame_index(self.k)
         inp = self.inp
@@ -811,23 +824,29 @@ class RefSession:
                 q.free()
             cur = [self.lk.pyramid(self.frames[j, 0], WIN, MAXLEVEL), self.lk.pyramid(self.frames[j, 1], WIN, MAXLEVEL)]
             self.pyr[2:4] = cur
+        lap("pyramid")
         nxt, st, ts = self.lk.lk(self.pyr[0], cur[0], inp.points, inp.init_guess(self.prev_j, j), max_level=MAXLEVEL)
         nxt2, st2, ts2 = self.lk.lk(cur[0], cur[1], nxt, None, max_level=MAXLEVEL)
+        lap("lk")
         fr = self.k % POOL_EKF
         for s in range(PREDICTS):
             self.t += 0.005
             u = inp.imu[fr * PREDICTS + s]
             self.ekf.predict(self.t, u[:3], u[3:])
             self.ekf.normalize_quaternions(True)
+        lap("ekf_predict")
         row = inp.ekf_pool[fr]
         for c, (o, n, l) in enumerate(inp.ekf_off):
             Hm = row[o:o + n * l].reshape((n, l), order="F")
             f, y = row[o + n * l:o + n * l + n], row[o + n * l + n:o + n * l + 2 * n]
             st_, _ = self.ekf.visual_check(Hm, f, y, VISUAL_R)
+            lap("ekf_check")
             if c < UPDATES and st_ == 0:
                 self.ekf.visual_update(Hm, f, y, VISUAL_R)
+                lap("ekf_update")
         self.ekf.symmetrize()
         self.ekf.augment(-1)
+        lap("ekf_augment")
         self.pyr = self.pyr[2:4] + self.pyr[0:2]
         self.prev_j = j
 
@@ -845,9 +864,16 @@ def cpu_baseline(inputs, budget_s=12.0):
     for _ in range(n):
         rs.step()
     dt = time.perf_counter() - t0
+    # per-stage rows: a short instrumented pass after the timed one, so that the timers are not inside `value`
+    stage_s, m = {}, max(10, min(100, n // 10))
+    for _ in range(m):
+        rs.step(stage_s)
+    stages = {k: round(stage_s.get(k, 0.0) / m * 1e3, 4) for k in RefSession.STAGES}
+    stages["frame_total"] = round(sum(stage_s.values()) / m * 1e3, 4)
     return {"value": round(n / dt, 2), "unit": "frames/s", "cores": rs.cores, "kind": rs.kind, "host_cores": os.cpu_count(),
             "sample": f"{n} consecutive stereo frames of the same workload ({dt:.1f} s); pyramid+LK on {rs.cores} OpenCV threads, EKF on 1 thread "
-                      f"(reference builds Eigen with EIGEN_DONT_PARALLELIZE)"}
+                      f"(reference builds Eigen with EIGEN_DONT_PARALLELIZE)",
+            "stage_ms_per_frame": stages, "stage_sample": f"{m} instrumented frames after the timed ones"}
 
 
 def run_reference(args):
