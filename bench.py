@@ -870,10 +870,23 @@ def cpu_baseline(inputs, budget_s=12.0):
         rs.step(stage_s)
     stages = {k: round(stage_s.get(k, 0.0) / m * 1e3, 4) for k in RefSession.STAGES}
     stages["frame_total"] = round(sum(stage_s.values()) / m * 1e3, 4)
+    one_thread = None
+    if rs.kind == "reference" and hasattr(rs.lk, "set_threads"):       # the cv::setNumThreads(1) row of SURVEY.md 8(d)
+        all_threads = rs.cores
+        try:
+            rs.lk.set_threads(1)
+            s1, m1 = {}, max(5, m // 2)
+            for _ in range(m1):
+                rs.step(s1)
+            one_thread = {"pyramid": round(s1.get("pyramid", 0.0) / m1 * 1e3, 4), "lk": round(s1.get("lk", 0.0) / m1 * 1e3, 4),
+                          "frame_total": round(sum(s1.values()) / m1 * 1e3, 4)}
+        finally:
+            rs.lk.set_threads(all_threads)
     return {"value": round(n / dt, 2), "unit": "frames/s", "cores": rs.cores, "kind": rs.kind, "host_cores": os.cpu_count(),
             "sample": f"{n} consecutive stereo frames of the same workload ({dt:.1f} s); pyramid+LK on {rs.cores} OpenCV threads, EKF on 1 thread "
                       f"(reference builds Eigen with EIGEN_DONT_PARALLELIZE)",
-            "stage_ms_per_frame": stages, "stage_sample": f"{m} instrumented frames after the timed ones"}
+            "stage_ms_per_frame": stages, "stage_ms_per_frame_one_opencv_thread": one_thread,
+            "stage_sample": f"{m} instrumented frames after the timed ones"}
 
 
 def run_reference(args):
