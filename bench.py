@@ -905,13 +905,17 @@ def run_reference(args):
         rs.step()
     dt = time.perf_counter() - t0
     v = args.steps / dt
+    stage_s, m = {}, max(5, min(50, args.steps))              # per-stage rows from a few instrumented frames AFTER the timed ones
+    for _ in range(m):
+        rs.step(stage_s)
+    stages = {k: round(stage_s.get(k, 0.0) / m * 1e3, 4) for k in RefSession.STAGES}
     emit(json.dumps({
         "impl": "reference", "metric": "stereo frames/sec (752x480, 150 tracks)", "value": round(v, 2), "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(dt / args.steps * 1e3, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16 fixed-point + f32 (pyramid, LK), f64 (EKF)", "data": "synthetic",
         "config": {"workload": "BASELINE config 2 (same step as the CUDA arm) on the host CPU; one session"},
         "cpu_baseline": {"value": round(v, 2), "unit": "frames/s", "cores": rs.cores, "kind": rs.kind, "host_cores": os.cpu_count(),
-                         "sample": f"{args.steps} stereo frames"},
+                         "sample": f"{args.steps} stereo frames", "stage_ms_per_frame": stages},
         "e2e": {"value": round(v, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
