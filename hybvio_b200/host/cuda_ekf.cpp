@@ -9,6 +9,7 @@
 #include "ekf.hpp"
 #include "parameters.hpp"
 #include "../../include/hybvio_b200.h"
+#include "cuda_context.hpp"
 #include "cuda_track_model.hpp"
 
 #include <Eigen/Eigenvalues>
@@ -20,22 +21,12 @@
 namespace {
 using namespace odometry;
 
-[[noreturn]] void fail(const char* what) {
-    std::fprintf(stderr, "hybvio_b200: %s failed: %s\n", what, hv_last_error());
-    std::abort();
-}
-#define HV(call) do { if ((call) != HV_OK) fail(#call); } while (0)
+using hybvio_b200::sharedContext;   // ONE context / stream per process, shared with the tracker back ends (cuda_context.hpp)
 
-// One context (stream) per process is enough for the reference's single-threaded Session; HV_DEVICE selects the GPU.
-hv_ctx* sharedContext() {
-    static hv_ctx* ctx = [] {
-        hv_ctx* c = nullptr;
-        const char* dev = std::getenv("HV_DEVICE");
-        if (hv_ctx_create(dev ? std::atoi(dev) : 0, &c) != HV_OK) fail("hv_ctx_create");
-        return c;
-    }();
-    return ctx;
-}
+[[noreturn]] void fail(const char* what) { hybvio_b200::hvFail(what); }
+// Programming errors and CUDA errors abort (the reference asserts in the same places); NUMERICAL conditions do not:
+// see visualTrackOutlierCheck / updateVisualTrack below.
+#define HV(call) do { if ((call) != HV_OK) fail(#call); } while (0)
 
 struct CudaEKF : public EKF {
     const Parameters& parameters;
@@ -106,11 +97,20 @@ struct CudaEKF : public EKF {
     VuOutlierStatus visualTrackOutlierCheck(const Eigen::MatrixXd& visH, const Eigen::VectorXd& f, const Eigen::VectorXd& y, double r,
                                             double trackRmseThreshold) final {
         int st = 0;
-        HV(hv_ekf_visual_check(h, visH.data(), (int)visH.rows(), (int)visH.cols(), f.data(), y.data(), r, trackRmseThreshold, &st, nullptr));
+        const int rc = hv_ekf_visual_check(h, visH.data(), (int)visH.rows(), (int)visH.cols(), f.data(), y.data(), r, trackRmseThreshold, &st, nullptr);
+        if (rc == HV_ERR_STATE) {
+            // innovation covariance not positive definite: the reference's pivoted LDLT carries on with whatever it gets
+            // (ekf.cpp:787-819); here the track is simply not used this frame instead of killing the host process
+            std::fprintf(stderr, "hybvio_b200: visualTrackOutlierCheck: %s -> NOT_COMPUTED\n", hv_last_error());
+            return VuOutlierStatus::NOT_COMPUTED;
+        }
+        if (rc != HV_OK) fail("hv_ekf_visual_check");
         return static_cast<VuOutlierStatus>(st);
     }
     void updateVisualTrack(const Eigen::MatrixXd& visH, const Eigen::VectorXd& f, const Eigen::VectorXd& y, double r) final {
-        HV(hv_ekf_visual_update(h, visH.data(), (int)visH.rows(), (int)visH.cols(), f.data(), y.data(), r));
+        const int rc = hv_ekf_visual_update(h, visH.data(), (int)visH.rows(), (int)visH.cols(), f.data(), y.data(), r);
+        if (rc == HV_ERR_STATE) { std::fprintf(stderr, "hybvio_b200: updateVisualTrack skipped: %s\n", hv_last_error()); return; }
+        if (rc != HV_OK) fail("hv_ekf_visual_update");
         touched();
     }
     void updateVisualPoseAugmentation(int discardedPoseIndex = -1) final { HV(hv_ekf_augment(h, discardedPoseIndex)); touched(); }
@@ -189,7 +189,12 @@ namespace odometry {
 EKF::~EKF() = default;
 EKF::EKF(const EKF& other) = default;
 EKF::EKF() {}
-std::unique_ptr<EKF> EKF::build(const Parameters& parameters) { return std::unique_ptr<EKF>(new CudaEKF(parameters)); }
+std::unique_ptr<EKF> buildCudaEKF(const Parameters& parameters) { return std::unique_ptr<EKF>(new CudaEKF(parameters)); }
+#ifndef HV_PIPELINE_HARNESS
+// compiled INSTEAD of src/odometry/ekf.cpp: the reference's factory symbol. (The parity harness oracle/ref_build/pipeline defines
+// HV_PIPELINE_HARNESS and provides its own EKF::build that chooses between the reference, this class and a lock-step pair.)
+std::unique_ptr<EKF> EKF::build(const Parameters& parameters) { return buildCudaEKF(parameters); }
+#endif
 
 // ---- cuda_track_model.hpp: the per-track measurement model on the device (backend.cpp:1050-1160)
 static CudaEKF& cudaEkf(EKF& ekf) {

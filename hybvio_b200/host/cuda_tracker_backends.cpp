@@ -14,6 +14,7 @@
 #include "optical_flow.hpp"
 #include "parameters.hpp"
 #include "../../include/hybvio_b200.h"
+#include "cuda_context.hpp"
 
 #include <accelerated-arrays/cpu/image.hpp>
 #include <cassert>
@@ -26,21 +27,9 @@ namespace cv { class Mat; }
 
 namespace tracker {
 namespace {
-[[noreturn]] void fail(const char* what) {
-    std::fprintf(stderr, "hybvio_b200: %s failed: %s\n", what, hv_last_error());
-    std::abort();
-}
+using hybvio_b200::sharedContext;   // ONE context / stream per process, shared with CudaEKF (cuda_context.hpp)
+[[noreturn]] void fail(const char* what) { hybvio_b200::hvFail(what); }
 #define HV(call) do { if ((call) != HV_OK) fail(#call); } while (0)
-
-hv_ctx* sharedContext() {
-    static hv_ctx* ctx = [] {
-        hv_ctx* c = nullptr;
-        const char* dev = std::getenv("HV_DEVICE");
-        if (hv_ctx_create(dev ? std::atoi(dev) : 0, &c) != HV_OK) fail("hv_ctx_create");
-        return c;
-    }();
-    return ctx;
-}
 
 // Pool of device pyramids, recycled like the reference's util::Allocator ring (image_pyramid.cpp:31,37): a pyramid
 // returns to the pool when the last tracker::Image holding it dies (prevImage, SLAM queue, ...).
@@ -131,6 +120,9 @@ std::unique_ptr<ImagePyramid::Factory> buildCudaImagePyramidFactory(const odomet
 std::unique_ptr<OpticalFlow> buildCudaOpticalFlow(const odometry::ParametersTracker& p) {
     return std::unique_ptr<OpticalFlow>(new CudaOpticalFlow(p));
 }
+
+// test harnesses only (oracle/ref_build/pipeline): the device pyramid behind a tracker::ImagePyramid built by this file
+hv_pyr* cudaPyramidHandle(ImagePyramid& p) { return static_cast<CudaImagePyramid&>(p).pyr; }
 
 #ifdef HV_REPLACE_OPENCV_BACKENDS
 // compiled INSTEAD of src/tracker/image_pyramid.cpp and optical_flow.cpp: same symbols, CUDA back ends
