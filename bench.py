@@ -417,7 +417,7 @@ def time_kernels(sess, reps=40):
     inp, ctx, ekf, capi = sess.inp, sess.ctx, sess.ekf, sess.capi
     cur = sess.pyr[2:4]
     N = ekf.N
-    timed("hv_pyr_fused_kernel (2 images)", lambda i: ctx.build_pyramids(cur, [sess.d_frames[(7 * i) % POOL_FRAMES, 0], sess.d_frames[(7 * i) % POOL_FRAMES, 1]], device=True),
+    timed("hv_pyr_fused2_kernel (2 images)", lambda i: ctx.build_pyramids(cur, [sess.d_frames[(7 * i) % POOL_FRAMES, 0], sess.d_frames[(7 * i) % POOL_FRAMES, 1]], device=True),
           2 * PYR_BYTES)
     ctx.build_pyramids(cur, [sess.d_frames[1, 0], sess.d_frames[1, 1]], device=True)
     ctx.build_pyramids(sess.pyr[0:2], [sess.d_frames[0, 0], sess.d_frames[0, 1]], device=True)
@@ -483,7 +483,7 @@ def time_batched(sess, reps=20):
         e.synchronize()
         us = s.elapsed_time(e) * 1e3 / reps
         out[name] = {"us_per_launch": round(us, 2), "algo_bytes": algo, "gbs": round(algo / us * 1e-3, 1)}
-    run("hv_pyr_fused_kernel (32 images, one launch)", lambda: ctx.build_pyramids(pyrs, imgs, device=True), 32 * PYR_BYTES)
+    run("hv_pyr_fused2_kernel (32 images, one launch)", lambda: ctx.build_pyramids(pyrs, imgs, device=True), 32 * PYR_BYTES)
     capi = sess.capi
     jobs = (capi.LkJob * 8)()
     bufs = []
@@ -693,8 +693,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(inputs, budget_s=args.cpu_budget)
         if world == 1 and nsess == 1 and not os.environ.get("HV_BENCH_CHILD"):
-            for key, extra in (("next_row_track_model", next_row_track_model), ("tracker_variants_ab", tracker_variants_ab),
-                               ("persistent_updates_ab", persistent_updates_ab)):
+            for key, extra in (("next_row_track_model", next_row_track_model), ("persistent_updates_ab", persistent_updates_ab)):
                 elapsed = time.monotonic() - T_PROCESS_START
                 if os.environ.get("HV_BENCH_NO_EXTRAS"):
                     result[key] = {"skipped": "HV_BENCH_NO_EXTRAS"}
@@ -744,28 +743,6 @@ def persistent_updates_ab():
         return {"switch": "HV_EKF_PERSIST=1", "value": d.get("value"), "ms_per_step": d.get("ms_per_step"), "e2e": d.get("e2e", {}).get("value"),
                 "gpu_launches_per_step": d.get("gpu_launches_per_step"), "ekf_healthy_after_run": d.get("config", {}).get("ekf_healthy_after_run"),
                 "steps": d.get("steps")}
-    except Exception as ex:       # noqa: BLE001 -- report only
-        return {"error": repr(ex)[:400]}
-
-
-def tracker_variants_ab():
-    """A/B of the two opt-in tracker kernels, both bit-exact on the host emulator: HV_PYR_V2=1 (hv_pyr_fused2_kernel -- strips, two 16-bit
-    lanes per register, separable pyrDown; ~5x fewer instructions; the pyramid is not on the critical path of a single session, so look at
-    its kernel rows) and HV_LK_CTA_WARPS=8 (8 instead of 4 warps per feature in hv_lk_cta_kernel<31>: half the window rows on the
-    dependent chain of an iteration; LK IS on the critical path, so `value` moves with it). The same bench in a child process with both
-    switches set. Report only -- value / e2e / roofline above are measured with the default kernels."""
-    try:
-        env = dict(os.environ, HV_PYR_V2="1", HV_LK_CTA_WARPS="8", HV_BENCH_CHILD="1")
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", "200", "--warmup", "20", "--e2e-steps", "50", "--no-cpu-baseline"],
-                           capture_output=True, text=True, timeout=EXTRAS_TIMEOUT, env=env)
-        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
-        if not lines:
-            return {"error": (r.stderr or r.stdout)[-400:]}
-        d = json.loads(lines[-1])
-        pick = lambda table: {k: {"us_per_launch": v.get("us_per_launch"), "gbs": v.get("gbs"), "frac_of_hbm_peak": v.get("frac_of_hbm_peak")}
-                              for k, v in (d.get(table) or {}).items() if "pyr" in k or "lk" in k}
-        return {"switches": "HV_PYR_V2=1 HV_LK_CTA_WARPS=8", "value": d.get("value"), "ms_per_step": d.get("ms_per_step"), "e2e": d.get("e2e", {}).get("value"),
-                "kernels": pick("kernels"), "kernels_batched": pick("kernels_batched"), "steps": d.get("steps")}
     except Exception as ex:       # noqa: BLE001 -- report only
         return {"error": repr(ex)[:400]}
 

@@ -353,8 +353,7 @@ int hv_lk_track(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* prevXY, floa
     uint8_t* hs = (uint8_t*)c->h_stage; uint8_t* ds = (uint8_t*)c->d_stage;
     memcpy(hs + oPrev, prevXY, 8 * (size_t)n);
     if (useInitial) memcpy(hs + oNext, nextXY, 8 * (size_t)n);
-    static const bool warpKernel = getenv("HV_LK_WARP_PER_FEATURE") != nullptr;    // that kernel does not signal
-    if (hv_polling_enabled() && !warpKernel && n <= 640) {
+    if (hv_polling_enabled() && hv_lk_uses_cta_kernel(n)) {     // only the CTA-per-feature kernel raises the host flag
         // The kernel reads the points from and writes the results to the mapped pinned block itself (a few KB over PCIe) and
         // raises a flag there when the last feature is done: no H2D / D2H copy calls, no stream synchronisation.
         uint8_t* hd = (uint8_t*)c->hd_stage;

@@ -533,22 +533,14 @@ static size_t ekf_augment_smem_bytes(int N)
 
 bool ekf_update_uses_cluster2(const EkfUpdateArgs& a)
 {
-    static const bool forceSingle = getenv("HV_EKF_SINGLE_CTA") != nullptr, v1 = getenv("HV_EKF_CLUSTER_V1") != nullptr;
-    return !forceSingle && !v1 && !a.useGlobalWork && ekf_cluster2_fits(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT);
+    return !a.useGlobalWork && ekf_cluster2_fits(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT);
 }
 
 cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s)
 {
-    // 8-CTA cluster kernel whenever its shared-memory working set fits (n <= 84 at N = 160); the single-CTA kernel
-    // below remains for oversized batch updates (n up to N) and as an A/B switch (HV_EKF_SINGLE_CTA=1).
-    static const bool forceSingle = getenv("HV_EKF_SINGLE_CTA") != nullptr;
-    // second generation (ekf_cluster2.cuh: P blocks resident in shared memory, DSMEM exchanges); HV_EKF_CLUSTER_V1=1 selects
-    // the first generation (exchanges through L2) for A/B runs
-    static const bool v1 = getenv("HV_EKF_CLUSTER_V1") != nullptr;
-    if (!forceSingle && !v1 && !a.useGlobalWork && ekf_cluster2_fits(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT))
-        return ekf_launch_update_cluster2(a, s);
-    if (!forceSingle && !a.useGlobalWork && ekf_cluster_smem_bytes(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT) <= 216 * 1024)
-        return ekf_launch_update_cluster(a, s);
+    // 8-CTA cluster kernel (ekf_cluster2.cuh) whenever its shared-memory working set fits (n <= 84 at N = 160); the single-CTA
+    // kernel below only for oversized measurements (batch updates with n up to N, tableau in global memory).
+    if (ekf_update_uses_cluster2(a)) return ekf_launch_update_cluster2(a, s);
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(ekf_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);

@@ -165,9 +165,6 @@ struct EkfEwArgs {
 
 size_t ekf_update_smem_bytes(int n, int N);
 cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s);
-size_t ekf_cluster_smem_bytes(int n, int l, int N, bool joseph);
-cudaError_t ekf_launch_update_cluster(const EkfUpdateArgs& a, cudaStream_t s);
-cudaError_t ekf_launch_check_batch(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s);
 bool ekf_cluster2_fits(int n, int l, int N, bool joseph);
 bool ekf_update_uses_cluster2(const EkfUpdateArgs& a);    // the kernel ekf_launch_update will pick reports through a.sig
 cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s);

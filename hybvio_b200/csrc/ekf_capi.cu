@@ -344,6 +344,7 @@ int hv_ekf_set_process_noise(hv_ekf* e, const double* Q)
 int hv_ekf_get_dydx(hv_ekf* e, double* d)
 {
     EKF_ENTER(e, "hv_ekf_get_dydx");
+    if (!d) { hv_set_error("hv_ekf_get_dydx: NULL output"); return HV_ERR_INVALID; }
     HV_CUDA(cudaMemcpyAsync(d, e->b.dydx, sizeof(double) * 400, cudaMemcpyDeviceToHost, e->ctx->stream));
     HV_CUDA(cudaStreamSynchronize(e->ctx->stream));
     return HV_OK;
@@ -650,8 +651,14 @@ int hv_ekf_augment(hv_ekf* e, int discarded)
     if (discarded == -1) discarded = e->trail - 1;               // ekf.cpp:849
     if (discarded < 0 || discarded >= e->trail) { hv_set_error("hv_ekf_augment: pose index %d out of range", discarded); return HV_ERR_INVALID; }
     EkfUpdateArgs a; fill_small(a, EKF_OP_AUGMENT, EKF_POSE, EKF_CAM + EKF_POSE, e->prm.augment_r * e->noiseScale);
-    a.symFirst = e->pendSym ? 1 : 0;                             // a deferred symmetrisation rides along (cluster kernel)
-    e->pendSym = false;
+    a.b = e->b;
+    if (ekf_update_uses_cluster2(a)) {                           // a deferred symmetrisation rides along (cluster kernel only)
+        a.symFirst = e->pendSym ? 1 : 0;
+        e->pendSym = false;
+    } else {                                                     // the single-CTA kernel has no fused variant: issue it first
+        int rcs = flush_sym(e);
+        if (rcs != HV_OK) return rcs;
+    }
     a.dropIdx = discarded;
     a.augNoisePos = pow2(e->prm.noise_initial_pos_trail) * e->noiseScale;
     a.augNoiseOri = pow2(e->prm.noise_initial_ori_trail) * e->noiseScale;
@@ -678,10 +685,7 @@ int hv_ekf_unaugment(hv_ekf* e)
 int hv_ekf_symmetrize(hv_ekf* e)
 {
     EKF_ENTER(e, "hv_ekf_symmetrize");
-    // deferred: rides along with a directly following augmentation, otherwise issued by the next call. The single-CTA
-    // A/B path (HV_EKF_SINGLE_CTA) has no fused variant.
-    static const bool eager = getenv("HV_EKF_SINGLE_CTA") != nullptr || getenv("HV_EKF_EAGER") != nullptr;
-    if (eager) return launch_ew(e, EKF_EW_SYMMETRIZE);
+    // deferred: rides along with a directly following augmentation (cluster kernel), otherwise issued by the next call
     e->pendSym = true;
     return HV_OK;
 }
@@ -758,12 +762,9 @@ static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, b
         if (rc != HV_OK) return rc;
     }
     a.b = e->b; a.noiseScale = e->noiseScale; a.useGlobalWork = 0;
-    static const bool v1 = getenv("HV_EKF_CLUSTER_V1") != nullptr;
-    bool fits2 = !v1;
-    for (int i = 0; i < count && fits2; i++) fits2 = ekf_cluster2_fits(b.it[i].n, b.it[i].l, e->N, false);
-    const bool polled = host && fits2 && ekf_polling();
+    const bool polled = host && ekf_polling();           // every item fits the cluster kernel (batchable_check)
     if (polled) { a.sig = e->d_sig; a.sigSeq = (e->sigSeq += 1.0); }
-    HV_CUDA(fits2 ? ekf_launch_check_batch2(a, b, s) : ekf_launch_check_batch(a, b, s));
+    HV_CUDA(ekf_launch_check_batch2(a, b, s));
     e->ctx->launches++;
     if (polled) {
         int rc = poll_results(e, count, a.sigSeq, "hv_ekf_run");
@@ -789,7 +790,7 @@ static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, b
 static bool batchable_check(const hv_ekf* e, const hv_ekf_op& o)
 {
     return o.kind == HV_EKF_OP_VISUAL && o.mode == 0 && o.n > 0 && o.l > 0 && o.l <= e->N && o.n <= e->N &&
-           ekf_cluster_smem_bytes(o.n, o.l, e->N, false) <= 216 * 1024;
+           ekf_cluster2_fits(o.n, o.l, e->N, false);
 }
 
 // a dense visual measurement that changes the state (update / check+update) and fits the cluster kernel
@@ -797,14 +798,12 @@ static bool persistable(hv_ekf* e, const hv_ekf_op& o)
 {
     if (o.kind != HV_EKF_OP_VISUAL || (o.mode != EKF_MODE_UPDATE && o.mode != EKF_MODE_CHECK_UPDATE) || !o.H || !o.f || !o.y) return false;
     if (o.n <= 0 || o.l <= 0 || o.l > e->N || o.n > e->N || o.n >= (int)e->chi2inv95.size()) return false;
-    static const bool off = getenv("HV_EKF_SINGLE_CTA") != nullptr || getenv("HV_EKF_CLUSTER_V1") != nullptr;
-    return !off && ekf_cluster2_fits(o.n, o.l, e->N, false);
+    return ekf_cluster2_fits(o.n, o.l, e->N, false);
 }
 
 static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vuStatus, double* chi2, double* mOut)
 {
     if (!ops || nops < 0) { hv_set_error("hv_ekf_run: invalid argument"); return HV_ERR_INVALID; }
-    static const bool noBatch = getenv("HV_EKF_NO_BATCH") != nullptr;
     static const bool persist = getenv("HV_EKF_PERSIST") != nullptr;
     for (int i = 0; i < nops; i++) {
         const hv_ekf_op& o = ops[i];
@@ -838,7 +837,7 @@ static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vu
                 continue;
             }
         }
-        if (!noBatch && batchable_check(e, o)) {
+        if (batchable_check(e, o)) {
             int cnt = 1;
             while (i + cnt < nops && cnt < EKF_MAX_BATCH && batchable_check(e, ops[i + cnt])) cnt++;
             rc = flush_checks(e, ops, i, cnt, host, vuStatus, chi2);
@@ -881,6 +880,7 @@ int hv_ekf_run_host(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vuStatus, do
 int hv_ekf_debug_result_words(hv_ekf* e, double* out32)
 {
     EKF_ENTER(e, "hv_ekf_debug_result_words");
+    if (!out32) { hv_set_error("hv_ekf_debug_result_words: NULL output"); return HV_ERR_INVALID; }
     HV_CUDA(cudaMemcpyAsync(out32, e->b.res, 32 * sizeof(double), cudaMemcpyDeviceToHost, e->ctx->stream));
     HV_CUDA(cudaStreamSynchronize(e->ctx->stream));
     return HV_OK;

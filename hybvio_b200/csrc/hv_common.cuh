@@ -66,4 +66,7 @@ struct LkLaunch {
 };
 
 
+// Kernel choice of hv_launch_lk: up to 640 features in a launch (one session) a CTA of 4 warps per feature (minimal latency; the
+// only kernel that raises the host flag of the polled path), above that a warp per feature (throughput). Both produce identical bits.
+inline bool hv_lk_uses_cta_kernel(long long totalFeatures) { return totalFeatures <= 640; }
 cudaError_t hv_launch_lk(const LkLaunch& L, int win, cudaStream_t stream);

@@ -252,8 +252,7 @@ __global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32) hv_lk_kernel(LkLaunch L
 // iteration, double-buffered). Because the sums are exact integers, the result is BIT-IDENTICAL to the warp-per-feature
 // kernel above for any split. Used when the launch has few features (one VIO session: 150 features on 148 SMs), where
 // latency, not throughput, is what counts.
-#define LKC_NW 4      // default warps per feature; HV_LK_CTA_WARPS=8 selects the 8-warp instantiation (window 31 only): half the rows
-                      // per warp on the dependent chain of an iteration, twice the partial sums to add (A/B pending)
+#define LKC_NW 4      // warps per feature (an 8-warp instantiation measured no better on B200: 19.9 / 18.6 us against 19.7 / 16.5; removed)
 template <int WIN, int NW = LKC_NW>
 __global__ void __launch_bounds__(NW * 32) hv_lk_cta_kernel(LkLaunch L)
 {
@@ -460,18 +459,10 @@ cudaError_t hv_launch_lk(const LkLaunch& L, int win, cudaStream_t stream)
     if (maxN == 0) return cudaSuccess;
     // few features (one session): a CTA of 4 warps per feature minimises latency; many features: a warp per feature
     // maximises throughput. Both kernels produce identical bits (exact integer accumulation).
-    static const bool forceWarp = getenv("HV_LK_WARP_PER_FEATURE") != nullptr;
     long long total = 0;
     for (int i = 0; i < L.njobs; i++) total += L.jobs[i].n;
-    // HV_LK_CTA_MAX=n moves the switch-over point (A/B of the batched launches: 8 sessions = 1200 features)
-    static const long long ctaMax = getenv("HV_LK_CTA_MAX") ? atoll(getenv("HV_LK_CTA_MAX")) : 640;
-    if (!forceWarp && total <= ctaMax) {
+    if (hv_lk_uses_cta_kernel(total)) {          // the one predicate hv_lk_track's polling path relies on too (capi_internal.h)
         dim3 grid(maxN, L.njobs), block(LKC_NW * 32);
-        static const bool eightWarps = getenv("HV_LK_CTA_WARPS") != nullptr && atoi(getenv("HV_LK_CTA_WARPS")) == 8;
-        if (eightWarps && win == 31) {
-            hv_lk_cta_kernel<31, 8><<<grid, dim3(8 * 32), 0, stream>>>(L);
-            return cudaGetLastError();
-        }
         switch (win) {
             case 31: hv_lk_cta_kernel<31><<<grid, block, 0, stream>>>(L); break;
             case 21: hv_lk_cta_kernel<21><<<grid, block, 0, stream>>>(L); break;

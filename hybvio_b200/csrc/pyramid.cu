@@ -18,10 +18,10 @@
 // write gray L1-3 118,440 + write deriv L0-3 1,917,600 = 2,397,000 B. Halo re-reads hit L2 (the whole input
 // is 361 KB).
 //
-// Two bodies share the geometry. hv_pyr_fused_kernel (first generation) evaluates every output pixel on its own: 18 byte loads
-// with a reflect-101 per tap for a Scharr item, 25 for a pyrDown pixel -- 36,000 warp instructions per CTA (ncu), i.e. the kernel
-// is issue-bound (8 % of the HBM roofline at 32 images per launch). hv_pyr_fused2_kernel keeps the data flow and removes the
-// instructions: a thread walks DOWN a 4-pixel-wide strip with the three input rows rolling through registers (one aligned 32-bit
+// The first generation of this kernel (round 1, removed) evaluated every output pixel on its own: 18 byte loads with a reflect-101
+// per tap for a Scharr item, 25 for a pyrDown pixel -- 36,000 warp instructions per CTA (ncu), i.e. issue-bound (8 % of the HBM
+// roofline at 32 images per launch; 24.9 us per stereo pair against 16.8 us for this one). hv_pyr_fused2_kernel keeps the data flow and
+// removes the instructions: a thread walks DOWN a 4-pixel-wide strip with the three input rows rolling through registers (one aligned 32-bit
 // + two byte loads per row instead of 18 byte loads), the Scharr arithmetic runs on two 16-bit lanes per register with biases
 // chosen so that every lane stays in [0, 65535] and the bias is exactly 0x8000 (removed by one XOR), pyrDown is separable along a
 // vertical strip of outputs (5 loads per source row shared by the outputs of the strip), reflection is one abs + one min
@@ -304,7 +304,6 @@ __device__ __forceinline__ void emit_fast(const HvLevel& L, const uint8_t* buf, 
         for (int iy = threadIdx.x; iy < th; iy += PYR_NT) emit_item(L, buf, bp, bx0, by0, sx, sy, writeGray, 4, full, iy);
 }
 
-template <bool FAST>
 __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem)
 {
     const HvPyrDesc& P = list.table[list.idx[blockIdx.z]];
@@ -316,7 +315,7 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
     Span sx[HV_MAX_LEVELS], sy[HV_MAX_LEVELS];
     int bufOff[HV_MAX_LEVELS], bufPitch[HV_MAX_LEVELS];
     int ox[HV_MAX_LEVELS];      // level coordinate of column 0 of the level's shared-memory buffer
-    if (FAST) {
+    {
         // ~450 instructions when every thread derives it for itself: a tenth of the first generation's work, but more than a third of
         // the second generation's. One thread per axis and one for the buffer layout, handed to the others through shared memory.
         __shared__ Span g_sx[HV_MAX_LEVELS], g_sy[HV_MAX_LEVELS];
@@ -351,26 +350,6 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
             // the owned tile starts on a 4-byte boundary of the buffer (32-bit shared-memory loads of the strips)
             ox[k] = sx[k].s0 - ((sx[k].s0 - sx[k].o0) & 3);
         }
-    } else {
-        int off = 0;
-        for (int k = 0; k < nl; k++) {
-            int rw = (HV_PYR_TILE >> k) + 2 * halo_of(k, top) + 4;   // +4: slack for 4-byte aligned start
-            rw = (rw + 3) & ~3;
-            bufOff[k] = off; bufPitch[k] = rw;
-            off += rw * rw; off = (off + 15) & ~15;
-        }
-        int ax = 0, bx = 0, ay = 0, by = 0;
-        for (int k = top; k >= 0; k--) {
-            const int w = P.lv[k].w, h = P.lv[k].h;
-            sx[k].o0 = (tx * HV_PYR_TILE) >> k; sx[k].o1 = min(w, ((tx + 1) * HV_PYR_TILE) >> k);
-            sy[k].o0 = (ty * HV_PYR_TILE) >> k; sy[k].o1 = min(h, ((ty + 1) * HV_PYR_TILE) >> k);
-            int nax = sx[k].o0 - 1, nbx = sx[k].o1, nay = sy[k].o0 - 1, nby = sy[k].o1;
-            if (k < top) { nax = min(nax, 2 * ax - 2); nbx = max(nbx, 2 * bx + 2); nay = min(nay, 2 * ay - 2); nby = max(nby, 2 * by + 2); }
-            span_close(sx[k], nax, nbx, w);
-            span_close(sy[k], nay, nby, h);
-            ax = sx[k].s0; bx = sx[k].s1; ay = sy[k].s0; by = sy[k].s1;
-            ox[k] = sx[k].s0;
-        }
     }
 
     // ---- stage the level-0 region with 32-bit loads (gpitch is a multiple of 4: rows are 4-byte aligned)
@@ -385,7 +364,7 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
         const bool aligned = ext == nullptr || ((((size_t)ext) | (size_t)list.srcPitch[blockIdx.z]) & 3) == 0;
         const uint8_t* base = ext ? ext : L0.gray;
         const int pitch = ext ? list.srcPitch[blockIdx.z] : L0.gpitch;
-        if (FAST && aligned && (ext == nullptr || x0a + words * 4 <= pitch)) {
+        if (aligned && (ext == nullptr || x0a + words * 4 <= pitch)) {
             // four rows per warp in flight: the loads of a staging pass are independent, but one load -> store pair per iteration
             // costs a full L2 / HBM round trip per row (13 per warp for the 108 rows of a 4-level tile)
             constexpr int NW = PYR_NT / 32;
@@ -405,12 +384,6 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
                     }
                 }
             }
-        } else if (aligned && (ext == nullptr || x0a + words * 4 <= pitch)) {
-            for (int r = wrp; r < rows; r += PYR_NT / 32) {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(base + (size_t)(sy[0].s0 + r) * pitch + x0a);
-                uint32_t* dst = reinterpret_cast<uint32_t*>(b0 + r * bp);
-                for (int c = lane; c < words; c += 32) dst[c] = __ldg(src + c);
-            }
         } else {   // arbitrary external pitch / alignment: byte loads, never past the last image column
             const int nbytes = min(words * 4, L0.w - x0a);
             for (int r = wrp; r < rows; r += PYR_NT / 32) {
@@ -422,18 +395,6 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
         ox[0] = x0a;
     }
     __syncthreads();
-
-    if (!FAST) {
-        emit_level(P.lv[0], smem + bufOff[0], bufPitch[0], sx[0].s0, sy[0].s0, sx[0], sy[0], ext != nullptr, 4);
-        // ---- coarser levels: 5x5 [1 4 6 4 1]^2, (sum+128)>>8, reflect-101 inside the finer level
-        for (int k = 1; k < nl; k++) {
-            uint8_t* dst = smem + bufOff[k];
-            pyrdown_generic(smem + bufOff[k - 1], bufPitch[k - 1], sx[k - 1].s0, sy[k - 1].s0, P.lv[k - 1].w, P.lv[k - 1].h, dst, bufPitch[k], sx[k].s0, sx[k], sy[k]);
-            __syncthreads();
-            emit_level(P.lv[k], dst, bufPitch[k], sx[k].s0, sy[k].s0, sx[k], sy[k], true, min(4, HV_PYR_TILE >> k));
-        }
-        return;
-    }
 
     // ---- second generation: between two barriers, the Scharr pass of level k and the pyrDown pass that produces level k + 1
     // (both only read the buffer of level k)
@@ -461,16 +422,10 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
     }
 }
 
-__global__ void __launch_bounds__(PYR_NT) hv_pyr_fused_kernel(PyrBuildList list)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    pyr_body<false>(list, smem);
-}
-
 __global__ void __launch_bounds__(PYR_NT, 4) hv_pyr_fused2_kernel(PyrBuildList list)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    pyr_body<true>(list, smem);
+    pyr_body(list, smem);
 }
 
 // Host-side launch helper (called from capi.cu). Shared memory is sized for the deepest pyramid in the list.
@@ -489,13 +444,9 @@ cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* id
                                 int n, int w0, int h0, int maxNlevels, cudaStream_t stream)
 {
     static bool attrSet = false;
-    // HV_PYR_V2=1: the second-generation body (strips, two 16-bit lanes per register); opt-in until it has been timed on a B200
-    static const bool gen2 = getenv("HV_PYR_V2") != nullptr && getenv("HV_PYR_V2")[0] != '0';
     size_t smem = hv_pyr_smem_bytes(maxNlevels);
     if (!attrSet) {
-        cudaError_t e = cudaFuncSetAttribute(hv_pyr_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(hv_pyr_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(hv_pyr_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attrSet = true;
     }
@@ -508,8 +459,7 @@ cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* id
             list.srcPitch[i] = src ? srcPitch[base + i] : 0;
         }
         dim3 grid((w0 + HV_PYR_TILE - 1) / HV_PYR_TILE, (h0 + HV_PYR_TILE - 1) / HV_PYR_TILE, list.n);
-        if (gen2) hv_pyr_fused2_kernel<<<grid, PYR_NT, smem, stream>>>(list);
-        else hv_pyr_fused_kernel<<<grid, PYR_NT, smem, stream>>>(list);
+        hv_pyr_fused2_kernel<<<grid, PYR_NT, smem, stream>>>(list);
     }
     return cudaGetLastError();
 }

@@ -97,7 +97,7 @@ int main(int argc, char** argv)
             const double d = std::hypot((double)c.pts[i].x - r.pts[i].x, (double)c.pts[i].y - r.pts[i].y);
             worst = std::fmax(worst, d); cmp++; if (d <= 1e-3) within++;
         }
-        const bool ok = stDiff == 0 && worst < 3e-2 && within >= 0.99 * cmp;
+        const bool ok = stDiff == 0 && worst < 3e-2 && within >= cmp - (cmp + 999) / 1000;      // >= 99.9 %: at most ceil(cmp / 1000) flipped stop tests
         std::printf("CUDA back ends vs reference, useInitialCorners=%d: %d status differences, %d / %d end points within 1e-3 px, worst %.2e px: %s\n",
                     useInit, stDiff, within, cmp, worst, ok ? "ok" : "FAIL");
         fails += !ok;

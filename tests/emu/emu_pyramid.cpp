@@ -1,4 +1,4 @@
-// tests/emu/emu_pyramid.cpp -- the REAL body of hv_pyr_fused_kernel (device part of hybvio_b200/csrc/pyramid.cu: all levels of an image in
+// tests/emu/emu_pyramid.cpp -- the REAL body of hv_pyr_fused2_kernel (device part of hybvio_b200/csrc/pyramid.cu: all levels of an image in
 // one launch, 64 x 64 level-0 tile per CTA, coarser levels from shared memory) on the host emulator against the C oracle
 // (oracle/hv_oracle_lk.c: pyrDown + Scharr as OpenCV computes them): every level's gray and gradient images bit-identical.
 // "pyr_device.inc" is cut out of pyramid.cu by the test that builds this file (the `extern __shared__` array becomes a pointer).
@@ -47,7 +47,7 @@ static int run(int W, int H, int maxLevel, bool fromSrc, bool gen2)
     gridDim.x = gx; gridDim.y = gy; gridDim.z = 1;
     for (int ty = 0; ty < gy; ty++) for (int tx = 0; tx < gx; tx++) {
         emu::block_y = ty; emu::block_z = 0;
-        emu::launch_cta(PYR_NT, (unsigned)tx, [&] { if (gen2) hv_pyr_fused2_kernel(list); else hv_pyr_fused_kernel(list); });
+        emu::launch_cta(PYR_NT, (unsigned)tx, [&] { hv_pyr_fused2_kernel(list); });
     }
     emu::block_y = 0;
     long long badG = 0, badD = 0, pix = 0;
@@ -74,14 +74,15 @@ static int run(int W, int H, int maxLevel, bool fromSrc, bool gen2)
 int main()
 {
     int fails = 0;
-    for (int gen2 = 0; gen2 < 2; gen2++) {
+    {
+        const bool gen2 = true;
         fails += run(320, 240, 3, false, gen2);
         fails += run(320, 240, 3, true, gen2);
         fails += run(188, 120, 2, false, gen2);          // widths that are not multiples of the tile, odd level sizes
         fails += run(150, 101, 3, true, gen2);
         fails += run(752, 480, 3, false, gen2);          // BASELINE config 2: 4 levels
     }
-    // second generation only: level widths that are not multiples of 4 (partial items), levels below 8 pixels (first-generation
+    // level widths that are not multiples of 4 (partial items), levels below 8 pixels (per-pixel
     // fallback inside the kernel), deeper pyramids (tiles of 4 and 2 pixels at levels 4 and 5), a single tile, TUM-VI's 512 x 512
     fails += run(203, 77, 3, false, true);
     fails += run(67, 66, 3, true, true);
@@ -89,11 +90,9 @@ int main()
     fails += run(130, 70, 5, false, true);
     fails += run(512, 512, 3, false, true);
     g_win = 3;
-    fails += run(130, 70, 5, false, false);
     fails += run(130, 70, 5, false, true);
     fails += run(97, 45, 4, true, true);
     fails += run(400, 300, 5, false, true);             // 6 levels, 94-pixel halo at level 0: staged rows of more than 32 words
-    fails += run(400, 300, 5, false, false);
     g_win = 31;
     g_fill = 0xFF;                                      // the packed pyrDown reads one byte past its 7 taps: must not reach a result
     fails += run(752, 480, 3, false, true);

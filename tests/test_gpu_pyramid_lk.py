@@ -5,7 +5,7 @@ Tolerances (BASELINE.json north_star / SURVEY.md 8(c)):
   * pyramid gray + Scharr levels: bit-exact (incl. the reference's padding, reconstructed by the accessor)
   * LK vs the oracle in accum_mode 1 (the kernel's own exact-integer arithmetic): bit-exact end points + status
   * LK vs the reference (golden vectors / accum_mode 0): status and track status identical; end points <= 1e-3 px
-    for >= 99% of tracked points and < 3e-2 px for all (a flipped stop test moves a point by at most one step).
+    for >= 99.9% of tracked points (outliers listed) and < 3e-2 px for all (a flipped stop test moves a point by at most one step).
 """
 import hashlib
 import os
@@ -41,8 +41,13 @@ def assert_lk_close(n_gpu, ts_gpu, n_ref, ts_ref, what):
     ok = ts_ref == 0
     d = np.abs(n_gpu - n_ref).max(axis=1)[ok]
     if d.size:
-        frac = (d <= TOL_PX).mean()
-        assert frac >= 0.99, f"{what}: only {frac:.4f} of end points within {TOL_PX} px (max {d.max():.3e})"
+        # >= 99.9 % of the end points within 1e-3 px (a flipped stop test moves a point by one step: at most
+        # ceil(n / 1000) such points), every point within 3e-2 px; the outliers are listed
+        idx = np.nonzero(ok)[0][d > TOL_PX]
+        outliers = [(int(i), float(np.abs(n_gpu[i] - n_ref[i]).max())) for i in idx]
+        if outliers:
+            print(f"{what}: {len(outliers)} of {d.size} end points differ by more than {TOL_PX} px: {outliers[:20]}")
+        assert len(outliers) <= -(-d.size // 1000), f"{what}: {len(outliers)} of {d.size} end points off by more than {TOL_PX} px: {outliers[:20]}"
         assert d.max() < TOL_FLIP_PX, f"{what}: end point off by {d.max():.3e} px"
 
 

@@ -2,7 +2,7 @@
 interfaces tracker::ImagePyramid::Factory::compute / tracker::OpticalFlow::compute are driven once with the reference's CPU back
 ends (src/tracker/image_pyramid.cpp, optical_flow.cpp, compiled unmodified over the vendored OpenCV) and once with the CUDA back
 ends on the same accelerated::Image frames (oracle/ref_build/tracker_iface_test.cpp, built by build_tracker_iface.sh).
-Tolerance: Feature::Status identical; end points <= 1e-3 px for >= 99 %, < 3e-2 px for all."""
+Tolerance: Feature::Status identical; end points <= 1e-3 px for >= 99.9 %, < 3e-2 px for all."""
 import os
 import subprocess
 

@@ -85,7 +85,7 @@ def test_oracle_exact_integer_mode_is_within_tolerance_of_reference_order(oracle
     n1, s1, _ = oracle_lk.lk(pa, pb, gold["A_pts"], gold["A_init"], accum_mode=1)
     assert np.array_equal(s0, s1)
     d = np.abs(n0 - n1).max(axis=1)[s0 > 0]
-    assert (d <= 1e-3).mean() >= 0.99 and d.max() < 3e-2
+    assert (d > 1e-3).sum() <= -(-d.size // 1000) and d.max() < 3e-2
 
 
 @pytest.mark.parametrize("w,h,max_level,n,use_init,seed", [
