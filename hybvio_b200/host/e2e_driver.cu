@@ -13,7 +13,7 @@
 extern "C" {
 
 typedef struct hv_e2e_frame {
-    const uint8_t* left; const uint8_t* right;   // host (pinned) gray images
+    const uint8_t* left; const uint8_t* right;   // host (pinned) gray images; right == NULL: mono (BASELINE config 1)
     size_t stride;
     const float* init_xy;                        // predicted end points for the temporal LK call (n x 2)
     const hv_ekf_op* ops;                        // the frame's EKF calls, HOST pointers (predicts, checks/updates, symmetrise, augment)
@@ -50,7 +50,7 @@ static int e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, cons
     auto submit = [&](int k, hv_pyr* const* dst) {
         const uint8_t* img[2] = {frames[k].left, frames[k].right};
         const size_t strides[2] = {frames[k].stride, frames[k].stride};
-        return hv_pyr_build_batch(dst, img, strides, 2, 0);                                 // H2D + one kernel, asynchronous
+        return hv_pyr_build_batch(dst, img, strides, frames[k].right ? 2 : 1, 0);           // H2D + one kernel, asynchronous
     };
     {
         const auto t0 = clk::now();
@@ -66,7 +66,7 @@ static int e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, cons
         rc = hv_lk_track(trk, p[0], cur[0], points, nxt.data(), st.data(), ts.data(), n, 1, 20, 0.03, 1e-3);   // sync
         if (rc != HV_OK) break;
         const auto t2 = clk::now();
-        rc = hv_lk_track(trk, cur[0], cur[1], nxt.data(), nxt2.data(), st.data(), ts.data(), n, 0, 20, 0.03, 1e-3);
+        if (f.right) rc = hv_lk_track(trk, cur[0], cur[1], nxt.data(), nxt2.data(), st.data(), ts.data(), n, 0, 20, 0.03, 1e-3);
         if (rc != HV_OK) break;
         const auto t3 = clk::now();
         if (k + 1 < nframes) { hv_pyr* nxtp[2] = {p[0], p[1]}; rc = submit(k + 1, nxtp); if (rc != HV_OK) break; }
@@ -117,7 +117,7 @@ int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
         hv_pyr* cur[2] = {p[2], p[3]};
         const uint8_t* img[2] = {f.left, f.right};
         const size_t strides[2] = {f.stride, f.stride};
-        rc = hv_pyr_build_batch(cur, img, strides, 2, 1);                       // A: no dependency
+        rc = hv_pyr_build_batch(cur, img, strides, f.right ? 2 : 1, 1);          // A: no dependency
         if (rc != HV_OK) break;
         rc = hv_ekf_run_device(ekf, f.ops, f.nimu);                            // B: IMU burst (queued) ...
         if (rc == HV_OK) rc = hv_ekf_flush(ekf);                               // ... issued now: overlaps the tracker
@@ -125,7 +125,7 @@ int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
         cudaStreamWaitEvent(sa, evEkf, 0);                                     // flow predictor needs EKF(k-1)
         cudaMemcpyAsync(d_next, f.d_init_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToDevice, sa);
         rc = hv_lk_track_device(trk, p[0], cur[0], d_points, d_next, d_status, d_ts, n, 1, 20, 0.03, 1e-3);
-        if (rc == HV_OK) rc = hv_lk_track_device(trk, cur[0], cur[1], d_next, d_next2, d_status, d_ts, n, 0, 20, 0.03, 1e-3);
+        if (rc == HV_OK && f.right) rc = hv_lk_track_device(trk, cur[0], cur[1], d_next, d_next2, d_status, d_ts, n, 0, 20, 0.03, 1e-3);
         if (rc != HV_OK) break;
         cudaEventRecord(evLk, sa);
         cudaStreamWaitEvent(sb, evLk, 0);                                      // visual updates need the tracks
