@@ -108,6 +108,9 @@ def load():
     lib.hv_lk_track.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double]
     lib.hv_lk_track_device.argtypes = lib.hv_lk_track.argtypes
     lib.hv_lk_track_batch_device.argtypes = [c_void_p, ctypes.POINTER(LkJob), c_int, c_int, c_double, c_double]
+    lib.hv_gftt_cells.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    lib.hv_gftt_detect.argtypes = [c_void_p, c_void_p, c_int, c_int, ctypes.c_float, c_void_p]
+    lib.hv_gftt_detect_device.argtypes = [c_void_p, c_void_p, c_int, c_int, ctypes.c_float, c_void_p]
     _bind_ekf(lib)
     _lib = lib
     return lib
@@ -280,6 +283,21 @@ class Pyramid:
         fn = self.lib.hv_pyr_download_level_padded if padded else self.lib.hv_pyr_download_level
         check(fn(self.h, level, _ptr(g), _ptr(d)), "hv_pyr_download_level")
         return g, d
+
+    def gftt_cells(self, cell=32):
+        cx, cy = c_int(), c_int()
+        check(self.lib.hv_gftt_cells(self.h, cell, ctypes.byref(cx), ctypes.byref(cy)), "hv_gftt_cells")
+        return cx.value, cy.value
+
+    def gftt_detect(self, block_size=3, cell=32, min_response=1e-3):
+        """Device part of tracker::FeatureDetector::detect on the level-0 image of this pyramid: (cells, 3) float32 (x, y, response)."""
+        cx, cy = self.gftt_cells(cell)
+        kp = np.zeros((cx * cy, 3), np.float32)
+        check(self.lib.hv_gftt_detect(self.ctx.h, self.h, block_size, cell, min_response, _ptr(kp)), "hv_gftt_detect")
+        return kp
+
+    def gftt_detect_device(self, d_kp, block_size=3, cell=32, min_response=1e-3):
+        check(self.lib.hv_gftt_detect_device(self.ctx.h, self.h, block_size, cell, min_response, d_kp), "hv_gftt_detect_device")
 
     def release(self):
         if self.h:

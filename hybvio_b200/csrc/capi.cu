@@ -390,4 +390,76 @@ int hv_lk_track(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* prevXY, floa
     return HV_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ corner detection (N2)
+static int gftt_args(const char* who, hv_ctx* c, hv_pyr* pyr, int blockSize, int cell, float minResponse, GfttArgs& a)
+{
+    if (!c || !pyr || pyr->ctx != c) { hv_set_error("%s: invalid context / pyramid", who); return HV_ERR_INVALID; }
+    if (blockSize != 3) { hv_set_error("%s: gfttBlockSize %d unsupported (3 only)", who, blockSize); return HV_ERR_UNSUPPORTED; }
+    if (cell < 2 || cell > 32) { hv_set_error("%s: cell size %d unsupported (2..32)", who, cell); return HV_ERR_UNSUPPORTED; }
+    const HvLevel& L = pyr->desc.lv[0];
+    memset(&a, 0, sizeof(a));
+    a.gray = L.gray; a.pitch = L.gpitch; a.w = L.w; a.h = L.h; a.cell = cell; a.minResponse = minResponse;
+    const double scale = 1.0 / ((double)(1 << 2) * blockSize * 255.0);          // OCV/imgproc/src/corner.cpp:246-251
+    a.k1 = (float)(1.0 * scale); a.k0 = (float)(2.0 * scale);
+    return HV_OK;
+}
+
+int hv_gftt_cells(const hv_pyr* pyr, int cell, int* cellsX, int* cellsY)
+{
+    if (!pyr || cell <= 0) { hv_set_error("hv_gftt_cells: invalid argument"); return HV_ERR_INVALID; }
+    if (cellsX) *cellsX = pyr->w / cell;
+    if (cellsY) *cellsY = pyr->h / cell;
+    return HV_OK;
+}
+
+int hv_gftt_detect_device(hv_ctx* c, hv_pyr* pyr, int blockSize, int cell, float minResponse, float* dKp)
+{
+    GfttArgs a;
+    int rc = gftt_args("hv_gftt_detect_device", c, pyr, blockSize, cell, minResponse, a);
+    if (rc != HV_OK) return rc;
+    if (!dKp) { hv_set_error("hv_gftt_detect_device: NULL output"); return HV_ERR_INVALID; }
+    HV_CUDA(cudaSetDevice(c->device));
+    a.kp = dKp;
+    HV_CUDA(hv_launch_gftt(a, c->stream));
+    c->launches += 1;
+    return HV_OK;
+}
+
+int hv_gftt_detect(hv_ctx* c, hv_pyr* pyr, int blockSize, int cell, float minResponse, float* kp)
+{
+    GfttArgs a;
+    int rc = gftt_args("hv_gftt_detect", c, pyr, blockSize, cell, minResponse, a);
+    if (rc != HV_OK) return rc;
+    if (!kp) { hv_set_error("hv_gftt_detect: NULL output"); return HV_ERR_INVALID; }
+    const int cells = (a.w / cell) * (a.h / cell);
+    if (cells == 0) return HV_OK;
+    HV_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)cells * 3 * sizeof(float);
+    rc = hv_ctx_reserve_stage(c, bytes);
+    if (rc != HV_OK) return rc;
+    uint8_t* hs = (uint8_t*)c->h_stage;
+    if (hv_polling_enabled()) {
+        // the kernel writes the key points straight into the mapped pinned block and the last cell raises the flag (as the LK kernel does)
+        a.kp = (float*)c->hd_stage;
+        volatile unsigned* flag = (volatile unsigned*)(hs + c->stageBytes);
+        a.doneCounter = c->d_done; c->doneCount += (unsigned)cells; a.doneTarget = c->doneCount;
+        a.seq = ++c->seq; a.hostFlag = (volatile unsigned*)((uint8_t*)c->hd_stage + c->stageBytes);
+        HV_CUDA(hv_launch_gftt(a, c->stream));
+        c->launches += 1;
+        rc = hv_poll_flag(flag, a.seq, c->stream, "hv_gftt_detect");
+        if (rc != HV_OK) {
+            cudaStreamSynchronize(c->stream); cudaMemsetAsync(c->d_done, 0, sizeof(unsigned), c->stream); cudaStreamSynchronize(c->stream); c->doneCount = 0;
+            return rc;
+        }
+    } else {
+        a.kp = (float*)c->d_stage;
+        HV_CUDA(hv_launch_gftt(a, c->stream));
+        c->launches += 1;
+        HV_CUDA(cudaMemcpyAsync(hs, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+        HV_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    memcpy(kp, hs, bytes);
+    return HV_OK;
+}
+
 } // extern "C"

@@ -70,3 +70,15 @@ struct LkLaunch {
 // only kernel that raises the host flag of the polled path), above that a warp per feature (throughput). Both produce identical bits.
 inline bool hv_lk_uses_cta_kernel(long long totalFeatures) { return totalFeatures <= 640; }
 cudaError_t hv_launch_lk(const LkLaunch& L, int win, cudaStream_t stream);
+
+// ---- corner detection launch description (gftt.cu)
+struct GfttArgs {
+    const uint8_t* gray; int pitch, w, h;
+    int cell;                 // bs
+    float k0, k1;             // [1 2 1] * scale as the fp32 kernel OpenCV builds (k0 = 2 s, k1 = s)
+    float minResponse;
+    float* kp;                // cellsX * cellsY * (x, y, response * 16); may be mapped pinned host memory
+    unsigned* doneCounter; unsigned doneTarget, seq; volatile unsigned* hostFlag;      // polled completion (like the LK kernel), optional
+};
+
+cudaError_t hv_launch_gftt(const GfttArgs& a, cudaStream_t stream);

@@ -54,13 +54,31 @@ struct PyramidPool {
     }
 };
 
+// Which device pyramid holds a given host image (key: address of the image data): lets the corner detector adapter
+// (cuda_feature_detector.cpp) run on the level-0 image that is already in HBM instead of uploading the frame a second time. The
+// tracker builds an image's pyramid (optical flow, tracker.cpp:395-438) before it detects new features on it (tracker.cpp:531).
+struct PyramidRegistry {
+    std::mutex mutex;
+    std::vector<std::pair<const void*, hv_pyr*>> entries;
+    void add(const void* key, hv_pyr* p) { std::lock_guard<std::mutex> l(mutex); remove_locked(key); entries.emplace_back(key, p); }
+    void remove(const void* key, hv_pyr* p) {
+        std::lock_guard<std::mutex> l(mutex);
+        for (size_t i = 0; i < entries.size(); i++) if (entries[i].first == key && entries[i].second == p) { entries.erase(entries.begin() + i); return; }
+    }
+    hv_pyr* find(const void* key) { std::lock_guard<std::mutex> l(mutex); for (auto& e : entries) if (e.first == key) return e.second; return nullptr; }
+private:
+    void remove_locked(const void* key) { for (size_t i = 0; i < entries.size(); i++) if (entries[i].first == key) { entries.erase(entries.begin() + i); return; } }
+};
+PyramidRegistry& registry() { static PyramidRegistry r; return r; }
+
 struct CudaImagePyramid : ImagePyramid {
     std::shared_ptr<PyramidPool> pool;
     hv_pyr* pyr = nullptr;
     int width = 0, height = 0;
+    const void* key = nullptr;
     std::shared_ptr<accelerated::Image> source;   // keeps the host gray image alive until the async H2D has been consumed
 
-    ~CudaImagePyramid() override { if (pyr) pool->release(pyr, width, height); }
+    ~CudaImagePyramid() override { if (pyr) { registry().remove(key, pyr); pool->release(pyr, width, height); } }
     // The device layout is not an accelerated::Image; like the reference's CPU pyramid (image_pyramid.cpp:17-25) these
     // two accessors are not used by any caller.
     accelerated::Image& getGrayLevel(std::size_t) final { assert(false && "device-resident pyramid"); std::abort(); }
@@ -82,6 +100,8 @@ public:
         // H2D copy + one fused kernel, asynchronous on the context stream (cv::buildOpticalFlowPyramid in the reference)
         // (raw pointer: the reference's gray type is FixedPoint<uint8_t>, ImagePyramid::GrayType; getData<uint8_t>() would reject it)
         HV(hv_pyr_build(pyramid->pyr, cpu.getDataRaw(), static_cast<size_t>(cpu.bytesPerRow())));
+        pyramid->key = cpu.getDataRaw();
+        registry().add(pyramid->key, pyramid->pyr);
         return pyramid;
     }
 };
@@ -120,6 +140,9 @@ std::unique_ptr<ImagePyramid::Factory> buildCudaImagePyramidFactory(const odomet
 std::unique_ptr<OpticalFlow> buildCudaOpticalFlow(const odometry::ParametersTracker& p) {
     return std::unique_ptr<OpticalFlow>(new CudaOpticalFlow(p));
 }
+
+// the device pyramid whose level 0 is the host image at `data`, or NULL (cuda_feature_detector.cpp)
+hv_pyr* cudaPyramidOfHostImage(const void* data) { return registry().find(data); }
 
 // test harnesses only (oracle/ref_build/pipeline): the device pyramid behind a tracker::ImagePyramid built by this file
 hv_pyr* cudaPyramidHandle(ImagePyramid& p) { return static_cast<CudaImagePyramid&>(p).pyr; }

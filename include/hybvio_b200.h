@@ -106,6 +106,21 @@ typedef struct hv_lk_job {
 } hv_lk_job;
 int hv_lk_track_batch_device(hv_ctx* ctx, const hv_lk_job* jobs, int njobs, int max_iter, double eps, double min_eig);
 
+/* ---------------------------------------------------------------- corner detection ---- */
+/* Device part of tracker::FeatureDetector::detect on CPU images (src/tracker/feature_detector.cpp:566-682, the default "GPU-GFTT"
+ * detector without OpenGL images): CpuCornerResponse = cv::cornerMinEigenVal(gray, block_size, 3) (feature_detector.cpp:281-310,
+ * OCV/imgproc/src/corner.cpp:238-320) and CollectMax::cpuImplementation (feature_detector.cpp:393-417: the best response of every
+ * cell x cell block, x GAIN 16, kept if > min_response), on the level-0 gray image of `pyr`, which hv_pyr_build has already put into
+ * HBM. cell = the detector's block size (32 for tracker.gfttMinDistance >= 32, feature_detector.cpp:425-433), block_size =
+ * tracker.gfttBlockSize (3), min_response = tracker.gfttMinResponse.
+ *   kp    (w / cell) * (h / cell) x (x, y, response) float32 in row-major cell order; a cell without a qualifying pixel reports
+ *         (0, 0, -1e10) exactly as the reference does. The sort by response, the reference's resize quirk and applyMinDistance
+ *         (feature_detector.cpp:625-638) stay on the host: hybvio_b200/host/cuda_feature_detector.cpp.
+ * hv_gftt_detect: host output, synchronises. hv_gftt_detect_device: device output, no synchronisation. */
+int hv_gftt_cells(const hv_pyr* pyr, int cell, int* cells_x, int* cells_y);
+int hv_gftt_detect(hv_ctx* ctx, hv_pyr* pyr, int block_size, int cell, float min_response, float* kp);
+int hv_gftt_detect_device(hv_ctx* ctx, hv_pyr* pyr, int block_size, int cell, float min_response, float* d_kp);
+
 /* ---------------------------------------------------------------- EKF ----------------------------------- */
 /* Replaces odometry::EKF / EKFImplementation (src/odometry/ekf.hpp:62-174, ekf.cpp). State m (N) and
  * covariance P (N x N) are fp64 and live in HBM; N = 20 + 7*trail + 3*map (ekf.cpp:156-158). */

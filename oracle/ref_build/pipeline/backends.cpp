@@ -8,6 +8,7 @@
 #include "backends.hpp"
 
 #include "ekf.hpp"
+#include "feature_detector.hpp"
 #include "image.hpp"
 #include "image_pyramid.hpp"
 #include "optical_flow.hpp"
@@ -35,6 +36,7 @@ namespace tracker {
 std::unique_ptr<ImagePyramid::Factory> buildCudaImagePyramidFactory(const odometry::ParametersTracker&);
 std::unique_ptr<OpticalFlow> buildCudaOpticalFlow(const odometry::ParametersTracker&);
 hv_pyr* cudaPyramidHandle(ImagePyramid&);
+std::unique_ptr<FeatureDetector> buildCudaFeatureDetector(int w, int h, const odometry::ParametersTracker&);
 }
 namespace odometry { std::unique_ptr<EKF> buildCudaEKF(const Parameters&); }
 
@@ -45,6 +47,9 @@ int g_frame = -1;
 Stats g_stats;
 std::unordered_map<tracker::Image*, std::shared_ptr<tracker::Image>> g_shadow;
 }
+bool g_cudaDetector = true;
+void setUseCudaDetector(bool on) { g_cudaDetector = on; }
+bool useCudaDetector() { return g_cudaDetector; }
 void setFlavour(Flavour f) { g_flavour = f; }
 Flavour flavour() { return g_flavour; }
 void setFrameIndex(int f) { g_frame = f; }
@@ -124,6 +129,34 @@ struct DualOpticalFlow : OpticalFlow {
             if (!(e <= 1e-3)) { s.lkOver1e3++; s.lkOutliers.push_back({g_frame, call, (int)i, dx, dy}); }
         }
     }
+};
+
+// ------------------------------------------------------------------------------------------------ corner detector, lock-step
+struct DualDetector : FeatureDetector {
+    std::unique_ptr<FeatureDetector> ref, cuda;
+    std::vector<Feature::Point> cornersC;
+    DualDetector(const odometry::ParametersTracker& p, std::unique_ptr<FeatureDetector> r, std::unique_ptr<FeatureDetector> c)
+        : FeatureDetector(p), ref(std::move(r)), cuda(std::move(c)) {}
+    void compare(const std::vector<Feature::Point>& a, const std::vector<Feature::Point>& b) {
+        Stats& s = g_stats;
+        s.detCalls++; s.detCorners += (long)a.size();
+        if (a.size() != b.size()) { s.detMismatch += 1 + (long)std::max(a.size(), b.size()) - (long)std::min(a.size(), b.size()); if (s.detFirstMismatchFrame < 0) s.detFirstMismatchFrame = g_frame; return; }
+        for (size_t i = 0; i < a.size(); i++)
+            if (a[i].x != b[i].x || a[i].y != b[i].y) { s.detMismatch++; if (s.detFirstMismatchFrame < 0) s.detFirstMismatchFrame = g_frame; }
+    }
+    void detect(Image& image, std::vector<Feature::Point>& corners, const std::vector<Feature::Point>& prev, int maskRadius) final {
+        ref->detect(image, corners, prev, maskRadius);
+        cuda->detect(image, cornersC, prev, maskRadius);
+        compare(corners, cornersC);
+    }
+    accelerated::Future detect(accelerated::Image& image, std::vector<Feature::Point>& corners, const std::vector<Feature::Point>& prev, int maskRadius) final {
+        ref->detect(image, corners, prev, maskRadius).wait();
+        cuda->detect(image, cornersC, prev, maskRadius).wait();
+        compare(corners, cornersC);
+        return accelerated::Future::instantlyResolved();
+    }
+    bool supportsAsync() const final { return false; }
+    void debugVisualize(cv::Mat& m) final { ref->debugVisualize(m); }
 };
 
 // ------------------------------------------------------------------------------------------------ EKF, lock-step
@@ -339,6 +372,23 @@ std::unique_ptr<EKF> EKF::build(const Parameters& parameters) {
     }
 }
 } // namespace odometry
+
+// tracker::FeatureDetector::build (src/tracker/image.cpp:52), intercepted with -Wl,--wrap as well: reference detector, CUDA detector
+// (hybvio_b200/host/cuda_feature_detector.cpp) or both with the corner lists compared
+extern "C" {
+#define FD_BUILD _ZN7tracker15FeatureDetector5buildEiiRN11accelerated9ProcessorERNS1_5Image7FactoryERNS1_10operations15StandardFactoryERKN8odometry17ParametersTrackerE
+#define FD_CAT2(a, b) a##b
+#define FD_CAT(a, b) FD_CAT2(a, b)
+std::unique_ptr<tracker::FeatureDetector> FD_CAT(__real_, FD_BUILD)(int, int, accelerated::Processor&, accelerated::Image::Factory&,
+                                                                    accelerated::operations::StandardFactory&, const odometry::ParametersTracker&);
+std::unique_ptr<tracker::FeatureDetector> FD_CAT(__wrap_, FD_BUILD)(int w, int h, accelerated::Processor& proc, accelerated::Image::Factory& ifac,
+                                                                    accelerated::operations::StandardFactory& ofac, const odometry::ParametersTracker& p) {
+    using namespace harness;
+    if (flavour() == Flavour::REF || !useCudaDetector() || p.featureDetector != "GPU-GFTT") return FD_CAT(__real_, FD_BUILD)(w, h, proc, ifac, ofac, p);
+    if (flavour() == Flavour::CUDA) return tracker::buildCudaFeatureDetector(w, h, p);
+    return std::unique_ptr<tracker::FeatureDetector>(new DualDetector(p, FD_CAT(__real_, FD_BUILD)(w, h, proc, ifac, ofac, p), tracker::buildCudaFeatureDetector(w, h, p)));
+}
+}
 
 // tracker::Tracker::build, intercepted with  -Wl,--wrap=_ZN7tracker7Tracker5buildERKN8odometry10ParametersE
 extern "C" {

@@ -18,6 +18,8 @@ enum class Flavour { REF, CUDA, DUAL };
 void setFlavour(Flavour f);
 Flavour flavour();
 void setFrameIndex(int frame);
+void setUseCudaDetector(bool on);      // CUDA / DUAL flavours: corner detector on the device too; default on
+bool useCudaDetector();
 void setRefThreads(int n);
 int refThreads();
 
@@ -40,6 +42,9 @@ struct Stats {
     long ekfChecks = 0, ekfCheckMismatch = 0, ekfCompares = 0;
     double ekfMaxPos = 0, ekfMaxM = 0, ekfMaxPrel = 0;
     std::vector<double> framePos, framePrel;          // running maximum within each frame
+    // corner detector (DUAL): corner lists of FeatureDetector::detect, reference against CUDA
+    long detCalls = 0, detCorners = 0, detMismatch = 0;
+    int detFirstMismatchFrame = -1;
     // tracker (DUAL): reference-driven tracker against the CUDA-driven shadow tracker
     long trkFrames = 0, trkTracks = 0, trkIdMismatch = 0, trkStatusMismatch = 0, trkSizeMismatch = 0, trkKeyframeMismatch = 0;
     double trkMaxPointDiff = 0;

@@ -55,7 +55,8 @@ void fillParameters(odometry::Parameters& p, const Config& c) {
     t.focalLength = c.f; t.principalPointX = 0.5 * (c.w - 1); t.principalPointY = 0.5 * (c.h - 1);
     t.maxTracks = c.maxTracks; t.pyrLKMaxLevel = c.maxLevel;
     t.useStereo = c.stereo;
-    t.featureDetector = "GFTT";                       // the reference's CPU detector (no OpenGL in this build)
+    // featureDetector stays at its default "GPU-GFTT": with CPU images that is CpuCornerResponse + CollectMax::cpuImplementation
+    // (src/tracker/feature_detector.cpp:666-669), the path the CUDA detector replaces
     t.targetFps = 20;
     o.cameraTrailLength = c.trail;
     if (c.trail < 10) o.cameraTrailHanoiLength = 2;
@@ -119,6 +120,7 @@ int main(int argc, char** argv) {
         else if (arg("--still")) still = std::atof(argv[++i]);
         else if (arg("--motion")) motion = std::atof(argv[++i]);
         else if (arg("--keep-cov")) keepP = std::atoi(argv[++i]);
+        else if (arg("--cuda-detector")) harness::setUseCudaDetector(std::atoi(argv[++i]) != 0);
         else { std::fprintf(stderr, "usage: run_pipeline --mode ref|cuda|lockstep|free [--config 2|4|1] [--frames N] [--out file.json] [--threads T]\n"); return 2; }
     }
     const Config cfg = makeConfig(configId);
@@ -272,6 +274,7 @@ int main(int argc, char** argv) {
         bool first = true;
         for (const auto& kv : S.ekfOps) { js << (first ? "" : ", ") << "\"" << kv.first << "\": {\"calls\": " << kv.second.calls << ", \"pos\": " << kv.second.maxPos << ", \"m\": " << kv.second.maxM << ", \"P_rel\": " << kv.second.maxPrel << "}"; first = false; }
         js << "},\n   \"position_diff_by_frame\": " << jsonVec(S.framePos) << ",\n   \"cov_rel_diff_by_frame\": " << jsonVec(S.framePrel) << "},\n"
+           << "  \"detector\": {\"calls\": " << S.detCalls << ", \"corners\": " << S.detCorners << ", \"mismatch\": " << S.detMismatch << ", \"first_mismatch_frame\": " << S.detFirstMismatchFrame << "},\n"
            << "  \"tracker\": {\"frames\": " << S.trkFrames << ", \"tracks\": " << S.trkTracks << ", \"id_mismatch\": " << S.trkIdMismatch << ", \"status_mismatch\": " << S.trkStatusMismatch
            << ", \"size_mismatch\": " << S.trkSizeMismatch << ", \"keyframe_mismatch\": " << S.trkKeyframeMismatch << ", \"first_mismatch_frame\": " << S.trkFirstMismatchFrame
            << ", \"max_point_diff_px\": " << S.trkMaxPointDiff << "}\n }";

@@ -6,6 +6,7 @@ UNMODIFIED (oracle/ref_build/Makefile.pipeline) and driven at odometry::Control 
 
 Gates (lock-step mode, every frame of the run):
   * every pyramid level, gray and gradients: bit-exact
+  * every FeatureDetector::detect call (default detector on CPU images: cornerMinEigenVal + per-cell maxima): identical corner lists
   * every LK call: Feature::Status identical; end points <= 1e-3 px for >= 99.9 % of the tracked points, the rest listed and < 3e-2 px
   * Tracker::Output of a TrackerImplementation running on CUDA-flavoured images against the reference-driven one: track IDs and
     statuses bit-equal, points <= 1e-3 px (same 99.9 % rule through the LK gate)
@@ -55,7 +56,7 @@ def test_lockstep_parity_through_the_unmodified_reference_core(config, frames):
     d, err = run("lockstep", config, frames)
     p = d["pipelines"][0]
     L = d["lockstep"]
-    print(json.dumps({k: L[k] for k in ("pyramid", "lk", "tracker")}), json.dumps({k: v for k, v in L["ekf"].items() if not k.endswith("by_frame")}))
+    print(json.dumps({k: L[k] for k in ("pyramid", "lk", "detector", "tracker")}), json.dumps({k: v for k, v in L["ekf"].items() if not k.endswith("by_frame")}))
     assert p["frames_tracking"] >= frames // 2, "the reference pipeline did not reach TRACKING"
     # pyramids: bit-exact
     assert L["pyramid"]["pyramids"] >= frames and L["pyramid"]["mismatching_bytes"] == 0
@@ -65,6 +66,10 @@ def test_lockstep_parity_through_the_unmodified_reference_core(config, frames):
     assert lk["status_mismatch"] == 0, lk["outliers"][:10]
     assert lk["over_1e-3_px"] <= -(-lk["tracked"] // 1000), lk["outliers"][:20]
     assert lk["max_diff_px"] < TOL_FLIP_PX
+    # corner detector (N2): the corner lists of FeatureDetector::detect (reference CPU detector against the device kernel + host half)
+    det = L["detector"]
+    assert det["calls"] >= 1 and det["corners"] > 100
+    assert det["mismatch"] == 0, det
     # Tracker::Output: IDs / statuses bit-equal
     t = L["tracker"]
     assert t["frames"] >= frames - 5 and t["tracks"] > 30 * frames
