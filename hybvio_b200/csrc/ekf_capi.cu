@@ -9,6 +9,8 @@
 #include <cstring>
 #include <vector>
 
+#define HV_RUN_MAX_OPS 256       // ops of one hv_ekf_run_host list that can report through the mapped result area
+
 struct hv_ekf {
     hv_ctx* ctx = nullptr;
     hv_ekf_params prm;
@@ -23,6 +25,8 @@ struct hv_ekf {
     bool stagedPending = false;
     double* h_sig = nullptr;      // mapped pinned result words the kernels write for a polling host: 4 doubles per batch slot
     double* d_sig = nullptr;      // (device alias)
+    double* h_run = nullptr;      // mapped pinned result words of hv_ekf_run_host: 4 doubles per op of the list (HV_RUN_MAX_OPS)
+    double* d_run = nullptr;      // (device alias)
     double sigSeq = 0.0;
     // host bookkeeping, exactly the members of EKFImplementation (ekf.cpp:145-151)
     int augmentCount = 0;
@@ -190,6 +194,10 @@ static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
     if (err == cudaSuccess) err = cudaHostGetDevicePointer(&e->d_sig, e->h_sig, 0);
     if (err != cudaSuccess) { cudaFree(e->d_block); cudaFreeHost(e->h_pin); delete e; hv_set_error("hv_ekf_create: mapped result buffer: %s", cudaGetErrorString(err)); return HV_ERR_OOM; }
     memset(e->h_sig, 0, 4 * sizeof(double) * (EKF_MAX_BATCH + 1));
+    err = cudaHostAlloc(&e->h_run, 4 * sizeof(double) * HV_RUN_MAX_OPS, cudaHostAllocMapped);
+    if (err == cudaSuccess) err = cudaHostGetDevicePointer(&e->d_run, e->h_run, 0);
+    if (err != cudaSuccess) { cudaFree(e->d_block); cudaFreeHost(e->h_pin); cudaFreeHost(e->h_sig); delete e; hv_set_error("hv_ekf_create: mapped result buffer: %s", cudaGetErrorString(err)); return HV_ERR_OOM; }
+    memset(e->h_run, 0, 4 * sizeof(double) * HV_RUN_MAX_OPS);
     *out = e;
     return HV_OK;
 }
@@ -241,6 +249,7 @@ int hv_ekf_destroy(hv_ekf* e)
     cudaFree(e->d_block);
     cudaFreeHost(e->h_pin);
     cudaFreeHost(e->h_sig);
+    cudaFreeHost(e->h_run);
     if (e->evStaged) cudaEventDestroy(e->evStaged);
     if (e->tm) { e->tm->release(); delete e->tm; }
     delete e;
@@ -865,6 +874,101 @@ static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vu
     return HV_OK;
 }
 
+// hv_ekf_run_host without a round trip per measurement: the list is known up front and a check+update decides on the device whether
+// its update is applied, so nothing the host would do depends on an intermediate result. Every measurement gets its own slice of the
+// pinned staging block (the host stages and issues op i+1 while the GPU works on op i), the kernels write their result words into a
+// mapped pinned area (one 4-double slot per op), and the ONE synchronisation at the end also covers the state read-back.
+// Returns 1 if the list cannot be handled here (too long, staging too small, a measurement that needs the single-CTA kernel).
+static int run_ops_host_async(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vuStatus, double* chi2, double* mOut, int* handled)
+{
+    *handled = 0;
+    if (nops > HV_RUN_MAX_OPS) return HV_OK;
+    size_t need = 0;
+    for (int i = 0; i < nops; i++) {
+        const hv_ekf_op& o = ops[i];
+        if (o.kind != HV_EKF_OP_VISUAL) continue;
+        if (o.mode < 0 || o.mode > 2 || !o.H || !o.f || !o.y || o.n <= 0 || o.l <= 0 || o.l > e->N || o.n > e->N || !ekf_cluster2_fits(o.n, o.l, e->N, false)) return HV_OK;
+        need += (size_t)o.n * o.l + 2 * (size_t)o.n;
+    }
+    if (need > e->inDoubles) return HV_OK;
+    *handled = 1;
+    cudaStream_t s = e->ctx->stream;
+    int rc = staging_acquire(e);
+    if (rc != HV_OK) return rc;
+    const double seq = (e->sigSeq += 1.0);
+    size_t off = 0;
+    bool staged = false;
+    for (int i = 0; i < nops; i++) {
+        const hv_ekf_op& o = ops[i];
+        rc = HV_OK;
+        if (o.kind == HV_EKF_OP_VISUAL) {
+            rc = flush_pending(e);
+            if (rc != HV_OK) return rc;
+            // consecutive pure checks: one launch (one cluster per track), one H2D copy
+            int cnt = 1;
+            if (o.mode == EKF_MODE_CHECK) while (i + cnt < nops && cnt < EKF_MAX_BATCH && ops[i + cnt].kind == HV_EKF_OP_VISUAL && ops[i + cnt].mode == EKF_MODE_CHECK) cnt++;
+            const size_t off0 = off;
+            EkfUpdateArgs a; EkfCheckBatch b;
+            memset(&b, 0, sizeof(b));
+            b.count = cnt;
+            for (int j = 0; j < cnt; j++) {
+                const hv_ekf_op& q = ops[i + j];
+                EkfUpdateArgs t;
+                rc = visual_args(e, "hv_ekf_run_host", q.n, q.l, q.r, q.rmse_thr, q.mode, t);
+                if (rc != HV_OK) return rc;
+                const size_t nl = (size_t)q.n * q.l;
+                double* hin = e->h_pin + off;
+                memcpy(hin, q.H, nl * sizeof(double)); memcpy(hin + nl, q.f, q.n * sizeof(double)); memcpy(hin + nl + q.n, q.y, q.n * sizeof(double));
+                t.H = e->d_in + off; t.f = e->d_in + off + nl; t.y = e->d_in + off + nl + q.n;
+                off += nl + 2 * (size_t)q.n;
+                if (j == 0) a = t;
+                EkfCheckItem& it = b.it[j];
+                it.n = q.n; it.l = q.l; it.Rdiag = t.Rdiag; it.chi2Thr = t.chi2Thr; it.rmseThr = t.rmseThr; it.skipChi2 = t.skipChi2;
+                it.H = t.H; it.f = t.f; it.y = t.y;
+            }
+            HV_CUDA(cudaMemcpyAsync(e->d_in + off0, e->h_pin + off0, (off - off0) * sizeof(double), cudaMemcpyHostToDevice, s));
+            staged = true;
+            a.sig = e->d_run + 4 * i; a.sigSeq = seq;
+            if (cnt > 1) {
+                a.b = e->b; a.noiseScale = e->noiseScale; a.useGlobalWork = 0;
+                HV_CUDA(ekf_launch_check_batch2(a, b, s));
+                e->ctx->launches++;
+            } else {
+                rc = launch_update(e, a);
+                if (rc != HV_OK) return rc;
+            }
+            i += cnt - 1;
+            continue;
+        }
+        switch (o.kind) {
+            case HV_EKF_OP_PREDICT: rc = hv_ekf_predict(e, o.t, o.gyro, o.acc); break;
+            case HV_EKF_OP_SYMMETRIZE: rc = hv_ekf_symmetrize(e); break;
+            case HV_EKF_OP_AUGMENT: rc = hv_ekf_augment(e, o.index); break;
+            case HV_EKF_OP_UNAUGMENT: rc = hv_ekf_unaugment(e); break;
+            case HV_EKF_OP_NORMALIZE: rc = hv_ekf_normalize_quaternions(e, o.index); break;
+            default: hv_set_error("hv_ekf_run: op %d: unknown kind %d", i, o.kind); return HV_ERR_INVALID;
+        }
+        if (rc != HV_OK) return rc;
+    }
+    if (staged) { rc = staging_release(e); if (rc != HV_OK) return rc; }
+    rc = flush_pending(e);
+    if (rc != HV_OK) return rc;
+    double* hout = e->h_pin + e->inDoubles;
+    if (mOut) HV_CUDA(cudaMemcpyAsync(hout + 8, e->b.m, e->N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    HV_CUDA(cudaStreamSynchronize(s));                           // the only synchronisation of the list
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    if (mOut) memcpy(mOut, hout + 8, e->N * sizeof(double));
+    for (int i = 0; i < nops; i++) {
+        if (ops[i].kind != HV_EKF_OP_VISUAL) continue;
+        const volatile double* w = e->h_run + 4 * i;
+        if (w[3] != seq) { hv_set_error("hv_ekf_run_host: op %d did not report its result", i); return HV_ERR_STATE; }
+        if (vuStatus) vuStatus[i] = (int)w[0];
+        if (chi2) chi2[i] = w[1];
+        if (w[2] != 0.0) { hv_set_error("hv_ekf_run: op %d: innovation covariance not positive definite", i); return HV_ERR_STATE; }
+    }
+    return HV_OK;
+}
+
 int hv_ekf_run_device(hv_ekf* e, const hv_ekf_op* ops, int nops)
 {
     EKF_ENTER(e, "hv_ekf_run_device");
@@ -874,6 +978,12 @@ int hv_ekf_run_device(hv_ekf* e, const hv_ekf_op* ops, int nops)
 int hv_ekf_run_host(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vuStatus, double* chi2, double* mOut)
 {
     EKF_ENTER(e, "hv_ekf_run_host");
+    if (!ops || nops < 0) { hv_set_error("hv_ekf_run: invalid argument"); return HV_ERR_INVALID; }
+    if (ekf_polling()) {          // HV_NO_POLL=1: the per-op path (one round trip per measurement) instead, for A/B
+        int handled = 0;
+        const int rc = run_ops_host_async(e, ops, nops, vuStatus, chi2, mOut, &handled);
+        if (handled || rc != HV_OK) return rc;
+    }
     return run_ops(e, ops, nops, true, vuStatus, chi2, mOut);
 }
 
