@@ -202,7 +202,8 @@ int hv_pyr_build_batch(hv_pyr* const* pyrs, const uint8_t* const* gray, const si
     HV_CUDA(cudaSetDevice(c->device));
     std::vector<unsigned short> idx(n);
     std::vector<const uint8_t*> src(n);
-    std::vector<int> srcPitch(n);
+    std::vector<int> srcPitch(n), l0Pitch(n), nls(n);
+    std::vector<const uint8_t*> l0(n);
     int maxNl = 0;
     for (int i = 0; i < n; i++) {
         hv_pyr* p = pyrs[i];
@@ -221,10 +222,12 @@ int hv_pyr_build_batch(hv_pyr* const* pyrs, const uint8_t* const* gray, const si
             src[i] = nullptr; srcPitch[i] = 0;
         }
         idx[i] = (unsigned short)p->slot;
+        l0[i] = L0.gray; l0Pitch[i] = L0.gpitch; nls[i] = p->nlevels;
         if (p->nlevels > maxNl) maxNl = p->nlevels;
     }
-    HV_CUDA(hv_launch_pyr_fused(c->d_table, idx.data(), src.data(), srcPitch.data(), n, pyrs[0]->w, pyrs[0]->h, maxNl, c->stream));
-    c->launches += (n + 59) / 60;
+    HV_CUDA(hv_launch_pyr_fused(c->d_table, idx.data(), src.data(), srcPitch.data(), l0.data(), l0Pitch.data(), nls.data(), n, pyrs[0]->w, pyrs[0]->h,
+                                maxNl, c->stream));
+    c->launches += (n + 31) / 32;
     return HV_OK;
 }
 

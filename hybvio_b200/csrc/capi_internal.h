@@ -49,4 +49,5 @@ bool hv_polling_enabled();
 
 // kernels (pyramid.cu, lk.cu)
 cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* idx, const uint8_t* const* src, const int* srcPitch,
+                                const uint8_t* const* level0, const int* level0Pitch, const int* nlevels,
                                 int n, int w0, int h0, int maxNlevels, cudaStream_t stream);

@@ -29,12 +29,15 @@
 // pass of level k shares its barrier interval with the pyrDown pass that produces level k + 1.
 #include "hv_common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 #ifndef PYR_NT
 #define PYR_NT 256
 #endif
 
-#define PYR_MAX_BATCH 60
+#define PYR_MAX_BATCH 32
+// 128-byte TMA descriptor (CUtensorMap) as an opaque blob, so that the device part also compiles on the host emulator
+struct alignas(64) HvTmap { unsigned long long q[16]; };
 struct PyrBuildList {
     const HvPyrDesc* table;   // device-resident descriptors of all pyramids of the context
     int n;                    // images in this launch
@@ -44,7 +47,35 @@ struct PyrBuildList {
     // straight into the level-0 buffer, which is then read in place.
     const uint8_t* src[PYR_MAX_BATCH];
     int srcPitch[PYR_MAX_BATCH];
+    // TMA staging of the level-0 region (cp.async.bulk.tensor.2d + mbarrier): one descriptor per image over its level-0 source (u8,
+    // w x h, row pitch a multiple of 16 bytes), box = (pitch of the level-0 shared-memory buffer) x (tile + 2 halo rows). useTma[z] == 0:
+    // the source does not meet TMA's alignment rules (or HV_PYR_NO_TMA=1): staged with 32-bit loads instead.
+    unsigned char useTma[PYR_MAX_BATCH];
+    HvTmap tmap[PYR_MAX_BATCH];
 };
+
+#ifndef HV_EMU
+__device__ __forceinline__ unsigned pyr_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pyr_mbar_init(unsigned long long* bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(pyr_smem_u32(bar)) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // the init must be visible to the async (TMA) proxy
+}
+__device__ __forceinline__ void pyr_tma_load_2d(void* dst, const HvTmap* map, int x, int y, unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(pyr_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(pyr_smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(pyr_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pyr_mbar_wait(unsigned long long* bar, unsigned phase)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(pyr_smem_u32(bar)), "r"(phase) : "memory");
+    } while (!done);
+}
+#endif
 
 struct Span { int o0, o1;   // owned output range [o0, o1) at this level
               int s0, s1; };  // stored (shared-memory) range [s0, s1] inclusive, in level coordinates
@@ -311,6 +342,10 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
     const int tx = blockIdx.x, ty = blockIdx.y;
     if (tx * HV_PYR_TILE >= P.lv[0].w || ty * HV_PYR_TILE >= P.lv[0].h) return;
 
+#ifndef HV_EMU
+    __shared__ __align__(8) unsigned long long s_bar;
+    if (list.useTma[blockIdx.z] && threadIdx.x == 0) pyr_mbar_init(&s_bar);      // made visible to the others by the geometry barrier below
+#endif
     // ---- geometry (identical in every thread)
     Span sx[HV_MAX_LEVELS], sy[HV_MAX_LEVELS];
     int bufOff[HV_MAX_LEVELS], bufPitch[HV_MAX_LEVELS];
@@ -340,8 +375,9 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
             for (int k = 0; k < nl; k++) {
                 int rw = (HV_PYR_TILE >> k) + 2 * halo_of(k, top) + 4;
                 rw = (rw + 3) & ~3;
-                g_off[k] = off; g_pitch[k] = rw;
-                off += rw * rw; off = (off + 15) & ~15;
+                const int pitch = k == 0 ? (rw + 15) & ~15 : rw;       // level 0: the TMA box is as wide as the buffer (multiple of 16 bytes)
+                g_off[k] = off; g_pitch[k] = pitch;
+                off += pitch * rw; off = (off + 127) & ~127;
             }
         }
         __syncthreads();
@@ -364,6 +400,14 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
         const bool aligned = ext == nullptr || ((((size_t)ext) | (size_t)list.srcPitch[blockIdx.z]) & 3) == 0;
         const uint8_t* base = ext ? ext : L0.gray;
         const int pitch = ext ? list.srcPitch[blockIdx.z] : L0.gpitch;
+#ifndef HV_EMU
+        if (list.useTma[blockIdx.z]) {
+            // ONE bulk tensor copy for the whole region: rows below / columns right of the image arrive as zeros (they are never read:
+            // the spans are closed under reflection inside the image), the box is as wide as the buffer pitch
+            if (threadIdx.x == 0) pyr_tma_load_2d(b0, &list.tmap[blockIdx.z], x0a, sy[0].s0, &s_bar, (unsigned)(bp * (HV_PYR_TILE + 2 * halo_of(0, top))));
+            pyr_mbar_wait(&s_bar, 0);
+        } else
+#endif
         if (aligned && (ext == nullptr || x0a + words * 4 <= pitch)) {
             // four rows per warp in flight: the loads of a staging pass are independent, but one load -> store pair per iteration
             // costs a full L2 / HBM round trip per row (13 per warp for the 108 rows of a 4-level tile)
@@ -394,6 +438,9 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
         sx[0].s0 = x0a;   // stored origin is the aligned one (o0 is a multiple of the tile size, so this is ox[0] as well)
         ox[0] = x0a;
     }
+#ifndef HV_EMU
+    if (!list.useTma[blockIdx.z])
+#endif
     __syncthreads();
 
     // ---- second generation: between two barriers, the Scharr pass of level k and the pyrDown pass that produces level k + 1
@@ -422,9 +469,9 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
     }
 }
 
-__global__ void __launch_bounds__(PYR_NT, 4) hv_pyr_fused2_kernel(PyrBuildList list)
+__global__ void __launch_bounds__(PYR_NT, 4) hv_pyr_fused2_kernel(const __grid_constant__ PyrBuildList list)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     pyr_body(list, smem);
 }
 
@@ -435,12 +482,45 @@ size_t hv_pyr_smem_bytes(int nlevels)
     for (int k = 0; k < nlevels; k++) {
         int h = 1; for (int i = nlevels - 1; i > k; --i) h = 2 * h + 2;
         int rw = (HV_PYR_TILE >> k) + 2 * h + 4; rw = (rw + 3) & ~3;
-        off += (size_t)rw * rw; off = (off + 15) & ~(size_t)15;
+        const int pitch = k == 0 ? (rw + 15) & ~15 : rw;
+        off += (size_t)pitch * rw; off = (off + 127) & ~(size_t)127;
     }
     return off;
 }
 
+// ---- TMA descriptors (host): cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
+#include <cuda.h>
+typedef CUresult (*PyrEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PyrEncodeFn pyr_encode_fn()
+{
+    static PyrEncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (getenv("HV_PYR_NO_TMA")) return (PyrEncodeFn) nullptr;          // A/B switch: stage with 32-bit loads instead
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (PyrEncodeFn)p;
+    }();
+    return fn;
+}
+// Level-0 source `base` (u8, w x h, `pitch` bytes per row) as a 2-D tensor with a (boxW x boxH) box; false if TMA's rules are not met
+static bool pyr_make_tmap(HvTmap& out, const uint8_t* base, int w, int h, int pitch, int boxW, int boxH)
+{
+    static_assert(sizeof(CUtensorMap) == sizeof(HvTmap), "CUtensorMap is 128 bytes");
+    PyrEncodeFn enc = pyr_encode_fn();
+    if (!enc || (((size_t)base) & 15) || (pitch & 15) || boxW > 256 || boxH > 256 || (boxW & 15)) return false;
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)boxW, (cuuint32_t)boxH}, estr[2] = {1, 1};
+    if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    memcpy(&out, &m, sizeof(m));
+    return true;
+}
+
 cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* idx, const uint8_t* const* src, const int* srcPitch,
+                                const uint8_t* const* level0, const int* level0Pitch, const int* nlevels,
                                 int n, int w0, int h0, int maxNlevels, cudaStream_t stream)
 {
     static bool attrSet = false;
@@ -457,6 +537,13 @@ cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* id
             list.idx[i] = idx[base + i];
             list.src[i] = src ? src[base + i] : nullptr;
             list.srcPitch[i] = src ? srcPitch[base + i] : 0;
+            // TMA descriptor over the image the CTAs stage from: the external frame if there is one, else the level-0 buffer
+            const int nl = nlevels[base + i];
+            int halo = 1; for (int q = nl - 1; q > 0; --q) halo = 2 * halo + 2;
+            int rw = HV_PYR_TILE + 2 * halo + 4; rw = (rw + 3) & ~3; rw = (rw + 15) & ~15;
+            const uint8_t* img = list.src[i] ? list.src[i] : level0[base + i];
+            const int pitch = list.src[i] ? list.srcPitch[i] : level0Pitch[base + i];
+            list.useTma[i] = pyr_make_tmap(list.tmap[i], img, w0, h0, pitch, rw, HV_PYR_TILE + 2 * halo) ? 1 : 0;
         }
         dim3 grid((w0 + HV_PYR_TILE - 1) / HV_PYR_TILE, (h0 + HV_PYR_TILE - 1) / HV_PYR_TILE, list.n);
         hv_pyr_fused2_kernel<<<grid, PYR_NT, smem, stream>>>(list);

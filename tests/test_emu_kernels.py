@@ -123,8 +123,8 @@ def test_lk_kernel_bodies_on_host_emulator(tmp_path):
 def _pyr_device_part(tmp_path):
     """The device part of hybvio_b200/csrc/pyramid.cu; its `extern __shared__` array becomes a pointer the harness sets."""
     src = open(os.path.join(ROOT, "hybvio_b200", "csrc", "pyramid.cu")).read()
-    dev = src[:src.index("\ncudaError_t hv_launch_pyr_fused")]
-    decl = "extern __shared__ __align__(16) uint8_t smem[];"
+    dev = src[:src.index("\n// ---- TMA descriptors (host)")]
+    decl = "extern __shared__ __align__(128) uint8_t smem[];"
     assert decl in dev
     (tmp_path / "pyr_device.inc").write_text(dev.replace(decl, "uint8_t* smem = emu_dynamic_smem;") + "\n")
     return str(tmp_path)
