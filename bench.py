@@ -825,7 +825,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(inputs, budget_s=args.cpu_budget)
         if world == 1 and nsess == 1 and CONFIG_ID == 2 and not os.environ.get("HV_BENCH_CHILD"):
-            for key, extra in (("next_row_track_model", next_row_track_model), ("persistent_updates_ab", persistent_updates_ab)):
+            for key, extra in (("next_row_track_model", next_row_track_model),):
                 elapsed = time.monotonic() - T_PROCESS_START
                 if os.environ.get("HV_BENCH_NO_EXTRAS"):
                     result[key] = {"skipped": "HV_BENCH_NO_EXTRAS"}
@@ -857,25 +857,6 @@ def next_row_track_model():
             return d
         return {"error": (r.stderr or r.stdout)[-400:]}
     except Exception as ex:       # noqa: BLE001 -- a report-only extra must never take the bench line down
-        return {"error": repr(ex)[:400]}
-
-
-def persistent_updates_ab():
-    """A/B of the opt-in persistent sequence of updates (HV_EKF_PERSIST=1: the five check+update launches of a frame become one,
-    the covariance blocks stay in shared memory): the same bench in a child process with the switch set, shorter
-    loops, no CPU baseline. Report only -- value / e2e above are measured with the default path."""
-    try:
-        env = dict(os.environ, HV_EKF_PERSIST="1", HV_BENCH_CHILD="1")
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", "200", "--warmup", "20", "--e2e-steps", "50", "--no-cpu-baseline"],
-                           capture_output=True, text=True, timeout=EXTRAS_TIMEOUT, env=env)
-        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
-        if not lines:
-            return {"error": (r.stderr or r.stdout)[-400:]}
-        d = json.loads(lines[-1])
-        return {"switch": "HV_EKF_PERSIST=1", "value": d.get("value"), "ms_per_step": d.get("ms_per_step"), "e2e": d.get("e2e", {}).get("value"),
-                "gpu_launches_per_step": d.get("gpu_launches_per_step"), "ekf_healthy_after_run": d.get("config", {}).get("ekf_healthy_after_run"),
-                "steps": d.get("steps")}
-    except Exception as ex:       # noqa: BLE001 -- report only
         return {"error": repr(ex)[:400]}
 
 

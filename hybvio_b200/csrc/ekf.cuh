@@ -96,28 +96,7 @@ struct EkfUpdateArgs {
     // follows an INLIER decision uses Rdiag2 -- visualTrackOutlierCheck(trackChiTestOutlierR) then updateVisualTrack(visualR),
     // backend.cpp:1158-1185, in one kernel: H P and S0 = H P H' are formed once, S0 + R is factorised twice.
     double Rdiag2;
-    // Persistent sequence of measurements in ONE launch (ekf_update_multi_cluster2_kernel): the kernel body is run once per
-    // measurement with the P column block of every CTA staying in shared memory in between. xCap / tCap: capacities (doubles) of
-    // the H / tableau regions, so that the P block sits at the same shared-memory offset for every measurement of the sequence
-    // (0: sized for this measurement alone); keepBlock: the block is already in shared memory (not the first measurement).
-    int xCap, tCap, keepBlock, padMulti;
 };
-
-// Consecutive dense visual measurements of hv_ekf_run_device issued as one persistent launch (HV_EKF_PERSIST=1)
-#define EKF_MAX_MULTI 8
-struct EkfMultiItem {
-    const double* H; const double* f; const double* y;   // device
-    int n, l, mode, skipChi2;
-    double Rdiag, Rdiag2, chi2Thr, rmseThr;
-    double* slot;                                        // optional per-measurement result words (3 doubles)
-};
-struct EkfMultiList { int count, pad; EkfMultiItem it[EKF_MAX_MULTI]; };
-
-// The whole per-track loop of a frame in ONE launch (ekf_chain_cluster2_kernel, HV_CHAIN_PERSIST=1): per track the measurement
-// model in CTA 0 of the cluster (track_model.cuh), then check + update with two noise levels on the cluster, P blocks resident.
-#define EKF_MAX_CHAIN 24
-struct EkfChainItem { int n, l; double chi2Thr; double* slot; };      // rows / columns of H (host-known), chi2inv95[n], result words
-struct EkfChainList { int count, first; double RdiagCheck, RdiagUpdate, rmseThr; EkfChainItem it[EKF_MAX_CHAIN]; };
 
 // Independent outlier checks against the same (m, P): one launch, one 8-CTA cluster per measurement
 #define EKF_MAX_BATCH 24
@@ -169,10 +148,6 @@ bool ekf_cluster2_fits(int n, int l, int N, bool joseph);
 bool ekf_update_uses_cluster2(const EkfUpdateArgs& a);    // the kernel ekf_launch_update will pick reports through a.sig
 cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s);
-bool ekf_multi2_fits(const EkfMultiList& m, int N);
-cudaError_t ekf_launch_update_multi2(const EkfUpdateArgs& a, const EkfMultiList& m, cudaStream_t s);
 struct TmArgs;
-bool ekf_chain2_fits(const EkfChainList& c, int N);
-cudaError_t ekf_launch_chain2(const EkfUpdateArgs& a, const TmArgs& tm, const EkfChainList& c, cudaStream_t s);
 cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_elementwise(const EkfEwArgs& a, cudaStream_t s);

@@ -802,50 +802,13 @@ static bool batchable_check(const hv_ekf* e, const hv_ekf_op& o)
            ekf_cluster2_fits(o.n, o.l, e->N, false);
 }
 
-// a dense visual measurement that changes the state (update / check+update) and fits the cluster kernel
-static bool persistable(hv_ekf* e, const hv_ekf_op& o)
-{
-    if (o.kind != HV_EKF_OP_VISUAL || (o.mode != EKF_MODE_UPDATE && o.mode != EKF_MODE_CHECK_UPDATE) || !o.H || !o.f || !o.y) return false;
-    if (o.n <= 0 || o.l <= 0 || o.l > e->N || o.n > e->N || o.n >= (int)e->chi2inv95.size()) return false;
-    return ekf_cluster2_fits(o.n, o.l, e->N, false);
-}
-
 static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vuStatus, double* chi2, double* mOut)
 {
     if (!ops || nops < 0) { hv_set_error("hv_ekf_run: invalid argument"); return HV_ERR_INVALID; }
-    static const bool persist = getenv("HV_EKF_PERSIST") != nullptr;
     for (int i = 0; i < nops; i++) {
         const hv_ekf_op& o = ops[i];
         int rc = HV_OK;
         if (o.kind == HV_EKF_OP_VISUAL) { rc = flush_pending(e); if (rc != HV_OK) return rc; }   // the other kinds enter through their own entry points
-        // consecutive check+update / update measurements with device-resident inputs: one persistent launch (the P blocks stay in
-        // shared memory between the measurements). Opt-in this round: HV_EKF_PERSIST=1.
-        if (persist && !host && persistable(e, o)) {
-            EkfMultiList list;
-            memset(&list, 0, sizeof(list));
-            EkfUpdateArgs first;
-            int cnt = 0;
-            while (i + cnt < nops && cnt < EKF_MAX_MULTI && persistable(e, ops[i + cnt])) {
-                const hv_ekf_op& q = ops[i + cnt];
-                EkfUpdateArgs t;
-                rc = visual_args(e, "hv_ekf_run_device", q.n, q.l, q.r, q.rmse_thr, q.mode, t);
-                if (rc != HV_OK) return rc;
-                EkfMultiItem& it = list.it[cnt];
-                it.H = q.H; it.f = q.f; it.y = q.y; it.n = q.n; it.l = q.l; it.mode = q.mode; it.skipChi2 = t.skipChi2;
-                it.Rdiag = t.Rdiag; it.Rdiag2 = 0.0; it.chi2Thr = t.chi2Thr; it.rmseThr = t.rmseThr; it.slot = nullptr;
-                list.count = cnt + 1;
-                if (!ekf_multi2_fits(list, e->N)) { list.count = cnt; break; }
-                if (cnt == 0) first = t;
-                cnt++;
-            }
-            if (cnt >= 2) {
-                prep_update(e, first);
-                HV_CUDA(ekf_launch_update_multi2(first, list, e->ctx->stream));
-                e->ctx->launches++;
-                i += cnt - 1;
-                continue;
-            }
-        }
         if (batchable_check(e, o)) {
             int cnt = 1;
             while (i + cnt < nops && cnt < EKF_MAX_BATCH && batchable_check(e, ops[i + cnt])) cnt++;
@@ -1161,45 +1124,14 @@ int hv_ekf_visual_tracks(hv_ekf* e, const hv_track_obs* tracks, int ntracks, con
     const int maxSucc = p->max_successful_updates > 0 ? p->max_successful_updates : 0x7fffffff;
     const int ncam = t->cam.use_stereo ? 2 : 1;
     const int step = p->lookahead > 0 ? p->lookahead : ntracks;
-    // check and update of a track in ONE kernel (S0 = H P H' formed once, factorised with each of the two R); HV_CHAIN_SEPARATE=1
-    // issues them as two gated launches instead (A/B)
-    static const bool separate = getenv("HV_CHAIN_SEPARATE") != nullptr;
-    const bool fused = !separate && p->chi_outlier_r >= 0.0 && p->visual_r > 0.0;
-    static const bool persistChain = getenv("HV_CHAIN_PERSIST") != nullptr;
+    // check and update of a track in ONE kernel (S0 = H P H' formed once, factorised with each of the two R). Measured on B200 (round 2,
+    // 20 candidate tracks, 5 updates): 537 us for the loop against 593 us with separate gated check / update launches and 651 us with
+    // one persistent launch per chunk (model in CTA 0 + check / update on the cluster) -- both alternatives removed.
+    const bool fused = p->chi_outlier_r >= 0.0 && p->visual_r > 0.0;
     int issued = 0, succ = 0;
     while (issued < ntracks && succ < maxSucc) {
         const int first = issued, count = ntracks - issued < step ? ntracks - issued : step;
-        // HV_CHAIN_PERSIST=1: the whole chunk as ONE launch (model in CTA 0 of the cluster, check + update on the cluster, P blocks
-        // resident in shared memory from track to track); opt-in until it has been measured
-        bool oneLaunch = false;
-        if (persistChain && fused && count <= EKF_MAX_CHAIN) {
-            EkfChainList list;
-            memset(&list, 0, sizeof(list));
-            list.count = count; list.first = first;
-            list.RdiagCheck = (p->chi_outlier_r * p->chi_outlier_r) * e->noiseScale; list.RdiagUpdate = (p->visual_r * p->visual_r) * e->noiseScale;
-            list.rmseThr = p->track_rmse_threshold;
-            bool okShape = true;
-            for (int k = first; k < first + count; k++) {
-                const hv_track_obs& o = tracks[k];
-                EkfChainItem& it = list.it[k - first];
-                it.n = 2 * o.npose * ncam; it.l = 0;
-                for (int i = 0; i < o.npose; i++) { const int x = o.pose_trail_index[i]; const int end = x == 0 ? 10 : 20 + 7 * (x - 1) + 7; if (end > it.l) it.l = end; }
-                if (it.n >= (int)e->chi2inv95.size() || it.l > e->N) { okShape = false; break; }
-                it.chi2Thr = e->chi2inv95[it.n]; it.slot = d_slots + 8 * (size_t)k;
-            }
-            if (okShape && ekf_chain2_fits(list, e->N)) {
-                EkfUpdateArgs c;
-                rc = visual_args(e, who, list.it[0].n, list.it[0].l, p->chi_outlier_r, p->track_rmse_threshold, EKF_MODE_CHECK_UPDATE, c);
-                if (rc != HV_OK) return rc;
-                prep_update(e, c);
-                TmArgs a = base;
-                a.ntracks = 1; a.counter = d_counter; a.counterMax = maxSucc;
-                HV_CUDA(ekf_launch_chain2(c, a, list, s));
-                e->ctx->launches++;
-                oneLaunch = true;
-            }
-        }
-        for (int k = first; k < first + count && !oneLaunch; k++) {
+        for (int k = first; k < first + count; k++) {
             TmArgs a = base;
             a.ntracks = 1; a.trackOffset = k; a.counter = d_counter; a.counterMax = maxSucc;
             a.pdl = k > first ? 1 : 0;                                // behind a cluster kernel of this chain: overlap the launch with its tail

@@ -10,7 +10,6 @@ namespace cg = cooperative_groups;
 #define EK2_PHASE(i) do { if (c == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.b.res[8 + (i)] = (double)t_; } } while (0)
 #endif
 #include "ekf_cluster2.cuh"
-#include "ekf_chain2.cuh"
 
 __global__ void __launch_bounds__(EK2_NT) ekf_update_cluster2_kernel(EkfUpdateArgs a)
 {
@@ -33,40 +32,13 @@ __global__ void __launch_bounds__(EK2_NT) ekf_check_batch_cluster2_kernel(EkfUpd
     ek2_body(a, ek2_sm, cluster);
 }
 
-// Persistent sequence: the measurements of the list are applied one after the other by the same cluster; the P column block of
-// every CTA stays in shared memory between them (no re-staging, no launch gap); m travels through global memory (CTA 0 writes it,
-// the final cluster barrier of a measurement orders it before the next one reads it).
-__global__ void __launch_bounds__(EK2_NT) ekf_update_multi_cluster2_kernel(EkfUpdateArgs a, EkfMultiList list)
-{
-    extern __shared__ __align__(16) double ek2_sm[];
-    ek2_multi_body(a, list, ek2_sm, cg::this_cluster());
-}
-
-// One launch for the whole visual-update loop of a frame (ekf_chain2.cuh)
-__global__ void __launch_bounds__(EK2_NT) ekf_chain_cluster2_kernel(EkfUpdateArgs a, TmArgs tm, EkfChainList list)
-{
-    extern __shared__ __align__(16) double ek2_sm[];
-    ek2_chain_body(a, tm, list, ek2_sm, cg::this_cluster());
-}
-
 #define EK2_STATIC_SMEM (sizeof(double) * (2 + 128 + 2 + EK2_MAXN) + 256)
-#define EK2_CHAIN_STATIC_SMEM (EK2_STATIC_SMEM + sizeof(int) * (TM_MAXN + 4 + TM_MAXOBS) + 64)
 #define EK2_SMEM_LIMIT (227 * 1024)
 
-// Cluster size: 8 (portable) unless HV_EKF_CLUSTER=16 asks for the non-portable size (A/B switch this round).
-static int ek2_cluster_size()
-{
-    static const int C = [] { const char* s = getenv("HV_EKF_CLUSTER"); const int v = s ? atoi(s) : 8; return (v == 16 || v == 4 || v == 2) ? v : 8; }();
-    return C;
-}
-
-// Single (non-batched) measurements with at least HV_EKF_C16_MIN_N rows run on a 16-CTA cluster (non-portable size): the dense
-// products halve, the exchanges get a little slower. Off unless the variable is set (A/B switch this round).
-static int ek2_cluster_size_for(int n, bool batch)
-{
-    static const int minN = [] { const char* s = getenv("HV_EKF_C16_MIN_N"); return s ? atoi(s) : (1 << 30); }();
-    return (!batch && n >= minN) ? 16 : ek2_cluster_size();
-}
+// Cluster size 8 (the portable maximum). Measured on B200 (round 2, profiles/r02_ab_settled.md): a 16-CTA cluster (non-portable size)
+// was slower for the frame as a whole (3755 against 4152 frames/s): the dense products halve but every exchange gets slower.
+static int ek2_cluster_size() { return 8; }
+static int ek2_cluster_size_for(int, bool) { return 8; }
 
 bool ekf_cluster2_fits(int n, int l, int N, bool joseph)
 {
@@ -104,40 +76,6 @@ cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s)
     if (!ready) { cudaError_t e = ek2_prepare(ekf_update_cluster2_kernel, C); if (e != cudaSuccess) return e; ready = true; }
     const size_t smem = ek2_smem_bytes(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT, C);
     return ek2_launch(ekf_update_cluster2_kernel, C, 1, smem, s, a);
-}
-
-bool ekf_multi2_fits(const EkfMultiList& m, int N)
-{
-    if (N > EK2_MAXN || m.count < 1 || m.count > EKF_MAX_MULTI) return false;
-    return ek2_multi_smem_bytes(m, N, ek2_cluster_size(), nullptr, nullptr) + EK2_STATIC_SMEM <= EK2_SMEM_LIMIT;
-}
-
-cudaError_t ekf_launch_update_multi2(const EkfUpdateArgs& a, const EkfMultiList& m, cudaStream_t s)
-{
-    const int C = ek2_cluster_size();
-    static bool ready = false;
-    if (!ready) { cudaError_t e = ek2_prepare(ekf_update_multi_cluster2_kernel, C); if (e != cudaSuccess) return e; ready = true; }
-    if (a.symmetrize || a.op != EKF_OP_DENSE) return cudaErrorInvalidValue;       // sequences are dense visual measurements
-    EkfUpdateArgs b = a;
-    const size_t smem = ek2_multi_smem_bytes(m, a.b.N, C, &b.xCap, &b.tCap);
-    return ek2_launch(ekf_update_multi_cluster2_kernel, C, 1, smem, s, b, m);
-}
-
-bool ekf_chain2_fits(const EkfChainList& c, int N)
-{
-    if (N > EK2_MAXN || c.count < 1 || c.count > EKF_MAX_CHAIN) return false;
-    return ek2_chain_smem_bytes(c, N, ek2_cluster_size(), nullptr, nullptr) + EK2_CHAIN_STATIC_SMEM <= EK2_SMEM_LIMIT;
-}
-
-cudaError_t ekf_launch_chain2(const EkfUpdateArgs& a, const TmArgs& tm, const EkfChainList& c, cudaStream_t s)
-{
-    const int C = ek2_cluster_size();
-    static bool ready = false;
-    if (!ready) { cudaError_t e = ek2_prepare(ekf_chain_cluster2_kernel, C, EK2_CHAIN_STATIC_SMEM); if (e != cudaSuccess) return e; ready = true; }
-    if (a.symmetrize || a.op != EKF_OP_DENSE) return cudaErrorInvalidValue;
-    EkfUpdateArgs b = a;
-    const size_t smem = ek2_chain_smem_bytes(c, a.b.N, C, &b.xCap, &b.tCap);
-    return ek2_launch(ekf_chain_cluster2_kernel, C, 1, smem, s, b, tm, c);
 }
 
 cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s)

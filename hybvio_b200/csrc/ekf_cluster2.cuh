@@ -65,22 +65,6 @@ __host__ __device__ inline size_t ek2_smem_bytes(int n, int l, int N, bool josep
     return ((size_t)g.X + g.T + g.PB + g.RS + g.EXTRA + g.SYM) * sizeof(double);
 }
 
-// Shared memory of a persistent sequence: H / tableau regions sized for the largest measurement, one P block, the rest per measurement
-__host__ __device__ inline size_t ek2_multi_smem_bytes(const EkfMultiList& m, int N, int C, int* xCap, int* tCap)
-{
-    int X = 0, T = 0, rest = 0, PB = 0;
-    for (int i = 0; i < m.count; i++) {
-        const Ek2Geom g = ek2_geom(m.it[i].n, m.it[i].l, N, false, C);
-        if (g.X > X) X = g.X;
-        if (g.T > T) T = g.T;
-        if (g.RS > rest) rest = g.RS;                   // no symmetrisation buffer: the measurements of a sequence are visual updates (a.symmetrize == 0)
-        PB = g.PB;
-    }
-    if (xCap) *xCap = X;
-    if (tCap) *tCap = T;
-    return ((size_t)X + T + PB + rest) * sizeof(double);
-}
-
 __device__ __forceinline__ void ek2_copy8(double* __restrict__ dst, const double* __restrict__ src, int count, int tid)
 {
     for (int base = 0; base < count; base += 8 * EK2_NT) {
@@ -406,8 +390,8 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     const bool joseph = a.op == EKF_OP_AUGMENT;
     const Ek2Geom g = ek2_geom(n, l, N, joseph, C);
     double* X = sm;                 // H, later Z
-    double* T = X + (a.xCap ? a.xCap : g.X);            // tableau
-    double* PB = T + (a.tCap ? a.tCap : g.T);           // P[:, J_c] (same offset for every measurement of a persistent sequence)
+    double* T = X + g.X;                                // tableau
+    double* PB = T + g.T;                               // P[:, J_c]
     double* RS = PB + g.PB;         // reduced S
     double* EX = RS + g.RS;         // Joseph-form extras
     double* SYMB = EX + g.EXTRA;    // symmetrisation: mirrored entries, transposed
@@ -427,12 +411,12 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     // Programmatic dependent launch: the next kernel of the stream may start now (its launch latency and the staging of its
     // own measurement matrix overlap with this kernel); it will not touch the filter state before its own
     // griddepcontrol.wait, which returns when this grid has completed and its writes are visible.
-    if (!a.keepBlock) ek2_pdl_launch_dependents();
+    ek2_pdl_launch_dependents();
     // ---- the measurement matrix does not depend on earlier kernels: stage it before waiting for them
     const bool lateH = a.lateH != 0 && a.op == EKF_OP_DENSE;
     if (a.op == EKF_OP_DENSE) { if (!lateH) ek2_copy8(X, a.H, n * l, tid); }
     else for (int i = tid; i < n * l; i += EK2_NT) X[i] = 0.0;
-    if (!a.keepBlock) ek2_pdl_wait();
+    ek2_pdl_wait();
     // ---- device-side control flow of a chain issued without host round trips (EkfUpdateArgs): every thread of the cluster
     // reads the same words, written by kernels that have completed
     if (a.gateI || a.gateD || a.counter) {
@@ -458,10 +442,9 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         }
     } else {
         for (int i = tid; i < N; i += EK2_NT) s_m[i] = a.b.m[i];
-        // whole columns: one contiguous block of global memory, 8 loads in flight per thread (skipped when the block is still in
-        // shared memory from the previous measurement of a persistent sequence)
+        // whole columns: one contiguous block of global memory, 8 loads in flight per thread
         const double* src = P + (size_t)J0 * N;
-        const int count = a.keepBlock ? 0 : N * Bc;
+        const int count = N * Bc;
         for (int base = 0; base < count; base += 8 * EK2_NT) {
             double r[8];
 #pragma unroll
@@ -767,21 +750,4 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     EK2_PHASE(9);
     if (a.bump && c == 0 && tid == 0) *a.bump = *a.bump + 1;          // one writer per grid; kernels of a chain are stream-ordered
     cluster.sync();                                   // nobody may leave while its shared memory can still be read
-}
-
-// Persistent sequence (ekf_update_multi_cluster2_kernel): the measurements of the list one after the other on the same cluster;
-// the P column block of every CTA stays in shared memory in between (a.xCap / a.tCap fix its offset), the state mean travels
-// through global memory (CTA 0 writes it; the final cluster barrier of a measurement orders it before the next one reads it).
-template <class Cluster>
-__device__ __forceinline__ void ek2_multi_body(const EkfUpdateArgs& a, const EkfMultiList& list, double* sm, Cluster cluster)
-{
-    for (int i = 0; i < list.count; i++) {
-        const EkfMultiItem& it = list.it[i];
-        EkfUpdateArgs b = a;
-        b.H = it.H; b.f = it.f; b.y = it.y; b.n = it.n; b.l = it.l; b.mode = it.mode; b.skipChi2 = it.skipChi2;
-        b.Rdiag = it.Rdiag; b.Rdiag2 = it.Rdiag2; b.chi2Thr = it.chi2Thr; b.rmseThr = it.rmseThr; b.slot = it.slot;
-        b.keepBlock = i > 0 ? 1 : 0;
-        ek2_body(b, sm, cluster);
-        __syncthreads();                                  // the static shared words of the body are reused by the next measurement
-    }
 }

@@ -8,7 +8,6 @@
 #include "emu_cluster.h"
 #include "ekf_cluster2.cuh"
 #include "track_model.cuh"
-#include "ekf_chain2.cuh"
 namespace cg = cooperative_groups;
 
 extern "C" {
@@ -28,10 +27,8 @@ int orc_track_model(const double* m, int trail, int useStereo, const int* poseTr
                     double* dpf, double* depth, int* vuStatus, int* rows, int* cols, double* H, double* f);
 }
 
-struct ChainCtx { EkfUpdateArgs c; TmArgs ta; EkfChainList list; };
 #if !defined(EMU_CLUSTER_THREADS) || defined(EMU_AS_LIB)
 EMU_CLUSTER_BODY(emu_chain_update_body) { EkfUpdateArgs aa = *(const EkfUpdateArgs*)ctx; ek2_body(aa, dyn, cg::this_cluster()); }
-EMU_CLUSTER_BODY(emu_chain_persist_body) { const ChainCtx& c = *(const ChainCtx*)ctx; ek2_chain_body(c.c, c.ta, c.list, dyn, cg::this_cluster()); }
 #endif
 #ifndef EMU_AS_LIB
 
@@ -41,7 +38,6 @@ static double nrand() { double s = 0; for (int i = 0; i < 12; i++) s += urand();
 int main(int argc, char**)
 {
     const bool fused = argc > 1;        // any argument: check and update of a track in ONE kernel (two noise levels)
-    const bool persist = argc > 2;      // two arguments: the whole loop in ONE launch (ek2_chain_body: model in CTA 0, P blocks resident)
     srand(77);
     const int trail = 20, N = 20 + 7 * trail, ntracks = 9, maxSucc = 3, stereo = 1;
     const double chiR = 0.01, visR = 0.004;
@@ -135,29 +131,7 @@ int main(int argc, char**)
     ta.counter = counter; ta.counterMax = maxSucc;
     std::vector<double> tmDyn(tm_smem_bytes() / 8, std::nan(""));
     int fails = 0;
-    if (persist) {
-        EkfChainList list; memset(&list, 0, sizeof(list));
-        list.count = ntracks; list.first = 0; list.RdiagCheck = chiR * chiR * noiseScale; list.RdiagUpdate = visR * visR * noiseScale; list.rmseThr = -1.0;
-        for (int t = 0; t < ntracks; t++) {
-            const int n = 2 * npose[t] * 2;
-            int l = 0; for (int k = 0; k < npose[t]; k++) { const int x = idx[t * TM_MAXPOSE + k]; l = std::max(l, x == 0 ? 10 : 20 + 7 * (x - 1) + 7); }
-            list.it[t].n = n; list.it[t].l = l; list.it[t].chi2Thr = orc_chi2inv95(n); list.it[t].slot = slots + 8 * t;
-        }
-        EkfUpdateArgs c; memset(&c, 0, sizeof(c));
-        c.b.m = m; c.b.P = P; c.b.res = res; c.b.cwork = cwork; c.b.N = N; c.b.trail = trail;
-        c.op = EKF_OP_DENSE; c.noiseScale = noiseScale; c.normalizeAll = 1;
-        const size_t smem = ek2_chain_smem_bytes(list, N, 8, &c.xCap, &c.tCap);
-        ChainCtx cc{c, ta, list};
-        const int bad = EMU_LAUNCH_CLUSTER(arena, 8, EK2_NT, smem, emu_chain_persist_body, &cc);
-        fails += bad;
-        for (int t = 0; t < ntracks; t++) {
-            const int gTri = status[4 * t], gOut = (int)slots[8 * t], gUpd = (slots[8 * t] == 0.0 && slots[8 * t + 2] == 0.0) ? 1 : 0;
-            const bool ok = gTri == eTri[t] && gOut == eOut[t] && gUpd == eUpd[t];
-            printf("track %d: model %2d/%2d  check %d/%d  updated %d/%d  %s\n", t, gTri, eTri[t], gOut, eOut[t], gUpd, eUpd[t], ok ? "ok" : "FAIL");
-            fails += !ok;
-        }
-        printf("one launch, %.1f KB of shared memory per CTA\n", smem / 1024.0);
-    } else
+
     for (int t = 0; t < ntracks; t++) {
         TmArgs a1 = ta; a1.trackOffset = t;
         gridDim.x = 1;
@@ -193,7 +167,7 @@ int main(int argc, char**)
     for (int i = 0; i < N; i++) em = std::fmax(em, std::fabs(om[i] - m[i]));
     for (size_t i = 0; i < oP.size(); i++) { eP = std::fmax(eP, std::fabs(oP[i] - P[i])); pmax = std::fmax(pmax, std::fabs(oP[i])); }
     const bool ok = counter[0] == succ && succ == maxSucc && em < 1e-9 && eP / pmax < 1e-9;
-    printf("chain%s: %d updates (oracle %d)  max|dm| %.2e  max|dP|/max|P| %.2e  %s\n", persist ? " (one persistent launch)" : fused ? " (fused check+update)" : "", counter[0], succ, em, eP / pmax, ok ? "ok" : "FAIL");
+    printf("chain%s: %d updates (oracle %d)  max|dm| %.2e  max|dP|/max|P| %.2e  %s\n", fused ? " (fused check+update)" : "", counter[0], succ, em, eP / pmax, ok ? "ok" : "FAIL");
     fails += !ok;
     orc_ekf_destroy(o);
     return fails;

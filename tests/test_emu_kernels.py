@@ -74,25 +74,10 @@ def test_device_gated_chain_on_host_emulator(tmp_path):
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
                            "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
                            os.path.join(ROOT, "tests", "emu", "emu_chain.cpp"), *objs, "-lm", "-o", exe])
-    for args, tag in (([], "chain: 3 updates (oracle 3)"), (["fused"], "chain (fused check+update): 3 updates (oracle 3)"),
-                      (["fused", "persist"], "chain (one persistent launch): 3 updates (oracle 3)")):
+    for args, tag in (([], "chain: 3 updates (oracle 3)"), (["fused"], "chain (fused check+update): 3 updates (oracle 3)")):
         out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=900)
         assert out.returncode == 0, out.stdout + out.stderr
         assert out.stdout.count("  ok") == 10 and "FAIL" not in out.stdout and tag in out.stdout
-
-
-def test_persistent_sequence_on_host_emulator(tmp_path):
-    """ek2_multi_body: eight measurements (check+update incl. an outlier, check only, update only, two noise levels; n = 8..84) in
-    ONE emulated launch with the P blocks staying in shared memory, against the same measurements applied one by one by the oracle."""
-    exe = str(tmp_path / "emu_multi")
-    obj = str(tmp_path / "orc_ekf.o")
-    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", "hv_oracle_ekf.c"), "-o", obj])
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I" + os.path.join(ROOT, "tests", "emu", "stubs"),
-                           "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + os.path.join(ROOT, "hybvio_b200", "csrc"),
-                           os.path.join(ROOT, "tests", "emu", "emu_multi.cpp"), obj, "-lm", "-o", exe])
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count("  ok") == 9 and "FAIL" not in out.stdout and "persistent sequence of 8 measurements" in out.stdout
 
 
 def _lk_device_part(tmp_path):
@@ -172,8 +157,8 @@ def test_kernel_bodies_are_race_free_under_thread_sanitizer(tmp_path):
     # (harness, oracle objects, argument lists, extra environment, cluster kernel?)
     runs = [("emu_track_model", ["hv_oracle_tri"], [[]], {}, False), ("emu_track_model", ["hv_oracle_tri"], [[]], {"EMU_NT": "512"}, False),
             ("emu_predict", ["hv_oracle_ekf"], [[]], {}, False), ("emu_lk", ["hv_oracle_lk"], [[]], {}, False), ("emu_pyramid", ["hv_oracle_lk"], [[]], {}, False),
-            ("emu_update", ["hv_oracle_ekf"], [["0"], ["3"], ["5"], ["6"], ["14"], ["20"]], {}, True), ("emu_multi", ["hv_oracle_ekf"], [[]], {}, True),
-            ("emu_chain", ["hv_oracle_ekf", "hv_oracle_tri"], [[], ["fused", "persist"]], {}, True)]
+            ("emu_update", ["hv_oracle_ekf"], [["0"], ["3"], ["5"], ["6"], ["14"], ["20"]], {}, True),
+            ("emu_chain", ["hv_oracle_ekf", "hv_oracle_tri"], [[], ["fused"]], {}, True)]
     built = {}
     for src, deps, arglists, extra, cluster in runs:
         if src not in built:

@@ -286,26 +286,3 @@ def test_track_model_through_the_reference_interfaces():
     r = subprocess.run([exe], cwd=os.path.join(root, "oracle", "_ref"), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "track model interface: all ok" in r.stdout, r.stdout[-500:]
-
-
-# ---- A/B variants of the chain (environment switches, read once per process: child runs); last on purpose
-def test_chain_with_separate_check_and_update_launches():
-    """HV_CHAIN_SEPARATE=1: the chain issues check and update as two gated launches instead of the fused two-noise-level kernel
-    (read once per process, hence the child process)."""
-    import subprocess
-    if os.environ.get("HV_CHAIN_SEPARATE") or os.environ.get("HV_CHAIN_PERSIST"):
-        pytest.skip("this is a child run")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-k", "device_gated_chain", "-p", "no:cacheprovider"],
-                       env={**os.environ, "HV_CHAIN_SEPARATE": "1", "HV_GPU_FIRST_RUN_STRICT": "1"}, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]
-
-
-def test_chain_as_one_persistent_launch():
-    """HV_CHAIN_PERSIST=1: the whole chunk of tracks is ONE launch (model in CTA 0 of the cluster, check + update on the cluster, P
-    blocks resident in shared memory); same expectations as the multi-launch chain."""
-    import subprocess
-    if os.environ.get("HV_CHAIN_PERSIST") or os.environ.get("HV_CHAIN_SEPARATE"):
-        pytest.skip("this is a child run")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-k", "device_gated_chain", "-p", "no:cacheprovider"],
-                       env={**os.environ, "HV_CHAIN_PERSIST": "1", "HV_GPU_FIRST_RUN_STRICT": "1"}, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]

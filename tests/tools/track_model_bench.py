@@ -129,7 +129,7 @@ def visual_update_loop(capi, hv, base, p, ntracks=20, reps=20):
     out = {"tracks": ntracks, "max_successful_updates": 5,
            "chain_one_sync_us": None if us_a is None else round(us_a, 1), "chain_sync_every_4_us": None if us_b is None else round(us_b, 1),
            "per_track_calls_us": None if us_c is None else round(us_c, 1), "cpu_reference_loop": cpu,
-           "variant": "one persistent launch per chunk" if os.environ.get("HV_CHAIN_PERSIST") else "separate check / update launches" if os.environ.get("HV_CHAIN_SEPARATE") else "model + fused check/update per track",
+           "variant": "model + fused check/update per track",
            "note": "median wall-clock of the whole loop through ctypes, state re-uploaded before every repetition (outside the timed region)"}
     if ret_a is not None:
         out["successful_updates"] = ret_a[1]
