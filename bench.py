@@ -173,12 +173,14 @@ class Session:
             self.d_ts = torch.zeros(NFEAT, dtype=torch.int32, device=self.dev)
             self.d_ekf_pool = torch.from_numpy(inputs.ekf_pool).to(self.dev)
             self.d_res = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        # host copy of the measurement pool in page-locked memory (the e2e contract: inputs come from pinned host memory)
+        self.h_ekf_pool = torch.from_numpy(inputs.ekf_pool).pin_memory()
         # per-frame EKF op lists (hv_ekf_run_*: one crossing of the language boundary per frame)
         self.ops_dev, self.ops_host = [], []
         nops = IMU_OPS + CHECKS + 2
         for fr in range(POOL_EKF):
             od, oh = (capi.EkfOp * nops)(), (capi.EkfOp * nops)()
-            for ops, base in ((od, self.d_ekf_pool[fr].data_ptr()), (oh, inputs.ekf_pool[fr].ctypes.data)):
+            for ops, base in ((od, self.d_ekf_pool[fr].data_ptr()), (oh, self.h_ekf_pool[fr].data_ptr())):
                 for s_ in range(PREDICTS):
                     u = inputs.imu[fr * PREDICTS + s_]
                     ops[2 * s_].kind = capi.OP_PREDICT

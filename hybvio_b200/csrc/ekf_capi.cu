@@ -27,6 +27,8 @@ struct hv_ekf {
     double* d_sig = nullptr;      // (device alias)
     double* h_run = nullptr;      // mapped pinned result words of hv_ekf_run_host: 4 doubles per op of the list (HV_RUN_MAX_OPS)
     double* d_run = nullptr;      // (device alias)
+    cudaStream_t copyStream = nullptr;            // hv_ekf_run_host: the measurement inputs travel on their own stream, ahead of the kernels
+    std::vector<cudaEvent_t> copyEvents;          // one per measurement group of a list (created on demand)
     double sigSeq = 0.0;
     // host bookkeeping, exactly the members of EKFImplementation (ekf.cpp:145-151)
     int augmentCount = 0;
@@ -250,6 +252,8 @@ int hv_ekf_destroy(hv_ekf* e)
     cudaFreeHost(e->h_pin);
     cudaFreeHost(e->h_sig);
     cudaFreeHost(e->h_run);
+    for (cudaEvent_t ev : e->copyEvents) cudaEventDestroy(ev);
+    if (e->copyStream) cudaStreamDestroy(e->copyStream);
     if (e->evStaged) cudaEventDestroy(e->evStaged);
     if (e->tm) { e->tm->release(); delete e->tm; }
     delete e;
@@ -856,21 +860,26 @@ static int run_ops_host_async(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vu
     if (need > e->inDoubles) return HV_OK;
     *handled = 1;
     cudaStream_t s = e->ctx->stream;
+    if (!e->copyStream) HV_CUDA(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+    cudaStream_t cs = e->copyStream;
     int rc = staging_acquire(e);
     if (rc != HV_OK) return rc;
+    // kernels queued by earlier asynchronous calls (updateVisualTrack) may still read the device input block: the copies start behind them
+    HV_CUDA(cudaEventRecord(e->evStaged, s));
+    HV_CUDA(cudaStreamWaitEvent(cs, e->evStaged, 0));
     const double seq = (e->sigSeq += 1.0);
     size_t off = 0;
     bool staged = false;
+    int group = 0;
     for (int i = 0; i < nops; i++) {
         const hv_ekf_op& o = ops[i];
         rc = HV_OK;
         if (o.kind == HV_EKF_OP_VISUAL) {
             rc = flush_pending(e);
             if (rc != HV_OK) return rc;
-            // consecutive pure checks: one launch (one cluster per track), one H2D copy
+            // consecutive pure checks: one launch (one cluster per track)
             int cnt = 1;
             if (o.mode == EKF_MODE_CHECK) while (i + cnt < nops && cnt < EKF_MAX_BATCH && ops[i + cnt].kind == HV_EKF_OP_VISUAL && ops[i + cnt].mode == EKF_MODE_CHECK) cnt++;
-            const size_t off0 = off;
             EkfUpdateArgs a; EkfCheckBatch b;
             memset(&b, 0, sizeof(b));
             b.count = cnt;
@@ -879,18 +888,34 @@ static int run_ops_host_async(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vu
                 EkfUpdateArgs t;
                 rc = visual_args(e, "hv_ekf_run_host", q.n, q.l, q.r, q.rmse_thr, q.mode, t);
                 if (rc != HV_OK) return rc;
-                const size_t nl = (size_t)q.n * q.l;
-                double* hin = e->h_pin + off;
-                memcpy(hin, q.H, nl * sizeof(double)); memcpy(hin + nl, q.f, q.n * sizeof(double)); memcpy(hin + nl + q.n, q.y, q.n * sizeof(double));
+                const size_t nl = (size_t)q.n * q.l, tot = nl + 2 * (size_t)q.n;
+                // The inputs go to the device on the COPY stream (they depend on nothing the kernels produce), so that they run ahead of
+                // the kernels instead of sitting between them. A packed measurement (f = H + n l, y = f + n) in page-locked memory is
+                // copied straight from the caller's buffer; anything else is packed into the pinned staging block first.
+                bool direct = false;
+                if (q.f == q.H + nl && q.y == q.f + q.n) {
+                    cudaPointerAttributes at;
+                    if (cudaPointerGetAttributes(&at, q.H) == cudaSuccess && at.type == cudaMemoryTypeHost) direct = true;
+                    else cudaGetLastError();
+                }
+                if (direct) HV_CUDA(cudaMemcpyAsync(e->d_in + off, q.H, tot * sizeof(double), cudaMemcpyHostToDevice, cs));
+                else {
+                    double* hin = e->h_pin + off;
+                    memcpy(hin, q.H, nl * sizeof(double)); memcpy(hin + nl, q.f, q.n * sizeof(double)); memcpy(hin + nl + q.n, q.y, q.n * sizeof(double));
+                    HV_CUDA(cudaMemcpyAsync(e->d_in + off, hin, tot * sizeof(double), cudaMemcpyHostToDevice, cs));
+                    staged = true;
+                }
                 t.H = e->d_in + off; t.f = e->d_in + off + nl; t.y = e->d_in + off + nl + q.n;
-                off += nl + 2 * (size_t)q.n;
+                off += tot;
                 if (j == 0) a = t;
                 EkfCheckItem& it = b.it[j];
                 it.n = q.n; it.l = q.l; it.Rdiag = t.Rdiag; it.chi2Thr = t.chi2Thr; it.rmseThr = t.rmseThr; it.skipChi2 = t.skipChi2;
                 it.H = t.H; it.f = t.f; it.y = t.y;
             }
-            HV_CUDA(cudaMemcpyAsync(e->d_in + off0, e->h_pin + off0, (off - off0) * sizeof(double), cudaMemcpyHostToDevice, s));
-            staged = true;
+            if ((int)e->copyEvents.size() <= group) { cudaEvent_t ev; HV_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->copyEvents.push_back(ev); }
+            HV_CUDA(cudaEventRecord(e->copyEvents[group], cs));
+            HV_CUDA(cudaStreamWaitEvent(s, e->copyEvents[group], 0));
+            group++;
             a.sig = e->d_run + 4 * i; a.sigSeq = seq;
             if (cnt > 1) {
                 a.b = e->b; a.noiseScale = e->noiseScale; a.useGlobalWork = 0;
@@ -913,7 +938,7 @@ static int run_ops_host_async(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vu
         }
         if (rc != HV_OK) return rc;
     }
-    if (staged) { rc = staging_release(e); if (rc != HV_OK) return rc; }
+    (void)staged;            // the staging block is free again after the synchronisation below (the copies precede the kernels that wait for them)
     rc = flush_pending(e);
     if (rc != HV_OK) return rc;
     double* hout = e->h_pin + e->inDoubles;

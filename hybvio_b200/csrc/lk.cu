@@ -252,6 +252,23 @@ __global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32) hv_lk_kernel(LkLaunch L
 // iteration, double-buffered). Because the sums are exact integers, the result is BIT-IDENTICAL to the warp-per-feature
 // kernel above for any split. Used when the launch has few features (one VIO session: 150 features on 148 SMs), where
 // latency, not throughput, is what counts.
+// Asynchronous global -> shared copies (LDGSTS): the search region of a level is requested before the template patch is loaded, so that
+// the two dependent L2 round trips of a level become one (no registers in between). Plain copies on the host emulator.
+__device__ __forceinline__ void lk_cp_async4(void* smemDst, const void* gsrc)
+{
+#ifdef HV_EMU
+    *reinterpret_cast<uint32_t*>(smemDst) = *reinterpret_cast<const uint32_t*>(gsrc);
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void lk_cp_async_wait_all()
+{
+#ifndef HV_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 #define LKC_NW 4      // warps per feature (an 8-warp instantiation measured no better on B200: 19.9 / 18.6 us against 19.7 / 16.5; removed)
 template <int WIN, int NW = LKC_NW>
 __global__ void __launch_bounds__(NW * 32) hv_lk_cta_kernel(LkLaunch L)
@@ -300,6 +317,31 @@ __global__ void __launch_bounds__(NW * 32) hv_lk_cta_kernel(LkLaunch L)
         int w00, w01, w10, w11;
         bilin_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
 
+        // ---- search region of the first iteration, requested NOW with cp.async (it only depends on the starting point of the level):
+        // it arrives while the template patch below is being loaded and reduced. Same rx0 / ry0 as the iteration loop would choose.
+        bool rgOk = false;
+        int rx0 = 0, ry0 = 0;
+        {
+            lk_cp_async_wait_all();                          // a request of a level that was skipped after it was issued
+            __syncthreads();
+            const int inx0 = cv_floor(__fsub_rn(nx, halfWin)), iny0 = cv_floor(__fsub_rn(ny, halfWin));
+            if (!(inx0 < -WIN || inx0 >= LJ.w || iny0 < -WIN || iny0 >= LJ.h)) {
+                const int qx = (inx0 - LK_REG_M) & ~3, qy = iny0 - LK_REG_M;
+                if (qx >= 0 && qx + LK_REG_W <= LJ.w && qy >= 0 && qy + LK_REG_H <= LJ.h) {
+                    const uint8_t* g0 = LJ.gray + (size_t)qy * LJ.gpitch + qx;
+#pragma unroll
+                    for (int u = 0; u < (LK_REG_H * (LK_REG_W / 4) + NW * 32 - 1) / (NW * 32); u++) {
+                        const int idx = tid + u * NW * 32;
+                        if (idx < LK_REG_H * (LK_REG_W / 4)) {
+                            const int row = idx / (LK_REG_W / 4), wd = idx - row * (LK_REG_W / 4);
+                            lk_cp_async4(reinterpret_cast<uint32_t*>(reg) + idx, reinterpret_cast<const uint32_t*>(g0 + (size_t)row * LJ.gpitch) + wd);
+                        }
+                    }
+                    rgOk = true; rx0 = qx; ry0 = qy;
+                }
+            }
+        }
+
         // ---- template patch rows r0 .. r0+nr-1 of this warp (+1 row for the bilinear tap)
         int a11 = 0, a12 = 0, a22 = 0;
         {
@@ -335,6 +377,7 @@ __global__ void __launch_bounds__(NW * 32) hv_lk_cta_kernel(LkLaunch L)
         }
         {
             const long long sa11 = warp_sum_exact(a11), sa12 = warp_sum_exact(a12), sa22 = warp_sum_exact(a22);
+            lk_cp_async_wait_all();                          // own part of the search region has landed; the barrier publishes it
             __syncthreads();                                 // previous readers of s_pa are done
             if (lane == 0) { s_pa[wrp][0] = sa11; s_pa[wrp][1] = sa12; s_pa[wrp][2] = sa22; }
             __syncthreads();
@@ -358,8 +401,6 @@ __global__ void __launch_bounds__(NW * 32) hv_lk_cta_kernel(LkLaunch L)
 
         nx = __fsub_rn(nx, halfWin); ny = __fsub_rn(ny, halfWin);
         float pdx = 0.f, pdy = 0.f;
-        bool rgOk = false;
-        int rx0 = 0, ry0 = 0;
         for (int j = 0; j < L.maxIter; j++) {
             const int inx = cv_floor(nx), iny = cv_floor(ny);
             if (inx < -WIN || inx >= LJ.w || iny < -WIN || iny >= LJ.h) {

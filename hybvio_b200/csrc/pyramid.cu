@@ -64,7 +64,8 @@ __device__ __forceinline__ void pyr_mbar_init(unsigned long long* bar)
 __device__ __forceinline__ void pyr_tma_load_2d(void* dst, const HvTmap* map, int x, int y, unsigned long long* bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(pyr_smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+    // (destination state space .shared::cluster: the .shared::cta form assembles for sm_100a but traps as an illegal instruction on B200)
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  :: "r"(pyr_smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(pyr_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void pyr_mbar_wait(unsigned long long* bar, unsigned phase)
