@@ -108,6 +108,10 @@ def load():
     lib.hv_lk_track.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double]
     lib.hv_lk_track_device.argtypes = lib.hv_lk_track.argtypes
     lib.hv_lk_track_batch_device.argtypes = [c_void_p, ctypes.POINTER(LkJob), c_int, c_int, c_double, c_double]
+    lib.hv_ingest_create.argtypes = [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p)]
+    lib.hv_ingest_destroy.argtypes = [c_void_p]
+    lib.hv_ingest_set_remap.argtypes = [c_void_p, c_void_p]
+    lib.hv_ingest_frame.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p]
     lib.hv_gftt_cells.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
     lib.hv_gftt_detect.argtypes = [c_void_p, c_void_p, c_int, c_int, ctypes.c_float, c_void_p]
     lib.hv_gftt_detect_device.argtypes = [c_void_p, c_void_p, c_int, c_int, ctypes.c_float, c_void_p]
@@ -303,6 +307,38 @@ class Pyramid:
         if self.h:
             self.lib.hv_pyr_release(self.h)
             self.h = None
+
+
+class Ingest:
+    """hv_ingest: device part of tracker::Image::Factory::build (colour -> gray, undistortion / rectification) feeding a pyramid."""
+
+    def __init__(self, ctx, width, height):
+        self.ctx, self.lib, self.w, self.h = ctx, ctx.lib, width, height
+        h = c_void_p()
+        check(self.lib.hv_ingest_create(ctx.h, width, height, ctypes.byref(h)), "hv_ingest_create")
+        self.h_ = h
+
+    def set_remap(self, table):
+        if table is None:
+            check(self.lib.hv_ingest_set_remap(self.h_, None), "hv_ingest_set_remap")
+            return
+        assert table.dtype.itemsize == 12 and table.size == self.w * self.h
+        check(self.lib.hv_ingest_set_remap(self.h_, _ptr(np.ascontiguousarray(table))), "hv_ingest_set_remap")
+
+    def frame(self, img, pyr, coeff=None, want_gray=True):
+        img = np.ascontiguousarray(img, np.uint8)
+        channels = 1 if img.ndim == 2 else img.shape[2]
+        out = np.zeros((self.h, self.w), np.uint8) if want_gray else None
+        cf = None if coeff is None else np.ascontiguousarray(list(coeff) + [0.0] * (4 - len(coeff)), np.float64)
+        check(self.lib.hv_ingest_frame(self.h_, _ptr(img), img.strides[0], channels, None if cf is None else _ptr(cf), pyr.h, None if out is None else _ptr(out)),
+              "hv_ingest_frame")
+        self.ctx.sync()
+        return out
+
+    def close(self):
+        if self.h_:
+            self.lib.hv_ingest_destroy(self.h_)
+            self.h_ = None
 
 
 def _dd(a):

@@ -465,4 +465,83 @@ int hv_gftt_detect(hv_ctx* c, hv_pyr* pyr, int blockSize, int cell, float minRes
     return HV_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ frame ingest (N4)
+struct hv_ingest {
+    hv_ctx* ctx = nullptr;
+    int w = 0, h = 0;
+    uint8_t* d_raw = nullptr; size_t rawBytes = 0;     // the frame as it arrived (device)
+    uint8_t* d_gray = nullptr;                          // gray before the remap (w x h, pitch w rounded up to 4)
+    HvRemapEntry* d_table = nullptr;
+};
+
+int hv_ingest_create(hv_ctx* c, int w, int h, hv_ingest** out)
+{
+    if (!c || !out || w <= 0 || h <= 0 || w > 32767 || h > 32767) { hv_set_error("hv_ingest_create: invalid argument"); return HV_ERR_INVALID; }
+    HV_CUDA(cudaSetDevice(c->device));
+    hv_ingest* g = new hv_ingest;
+    g->ctx = c; g->w = w; g->h = h;
+    const size_t gp = (size_t)((w + 3) & ~3);
+    cudaError_t e = cudaMalloc(&g->d_gray, gp * h);
+    if (e != cudaSuccess) { delete g; hv_set_error("hv_ingest_create: %s", cudaGetErrorString(e)); return HV_ERR_OOM; }
+    *out = g;
+    return HV_OK;
+}
+int hv_ingest_destroy(hv_ingest* g)
+{
+    if (!g) return HV_OK;
+    cudaStreamSynchronize(g->ctx->stream);
+    cudaFree(g->d_raw); cudaFree(g->d_gray); cudaFree(g->d_table);
+    delete g;
+    return HV_OK;
+}
+int hv_ingest_set_remap(hv_ingest* g, const hv_remap_entry* table)
+{
+    if (!g) { hv_set_error("hv_ingest_set_remap: NULL handle"); return HV_ERR_INVALID; }
+    static_assert(sizeof(hv_remap_entry) == sizeof(HvRemapEntry) && sizeof(HvRemapEntry) == 12, "remap entry layout");
+    HV_CUDA(cudaSetDevice(g->ctx->device));
+    HV_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    if (!table) { cudaFree(g->d_table); g->d_table = nullptr; return HV_OK; }
+    const size_t bytes = sizeof(HvRemapEntry) * (size_t)g->w * g->h;
+    if (!g->d_table) HV_CUDA(cudaMalloc(&g->d_table, bytes));
+    HV_CUDA(cudaMemcpy(g->d_table, table, bytes, cudaMemcpyHostToDevice));
+    return HV_OK;
+}
+int hv_ingest_frame(hv_ingest* g, const uint8_t* src, size_t stride, int channels, const double* coeff, hv_pyr* dst, uint8_t* grayOut)
+{
+    if (!g || !src || !dst || channels < 1 || channels > 4 || dst->ctx != g->ctx || dst->w != g->w || dst->h != g->h || stride < (size_t)g->w * channels) {
+        hv_set_error("hv_ingest_frame: invalid argument"); return HV_ERR_INVALID;
+    }
+    hv_ctx* c = g->ctx;
+    HV_CUDA(cudaSetDevice(c->device));
+    const int w = g->w, h = g->h;
+    const HvLevel& L0 = dst->desc.lv[0];
+    const int gp = (w + 3) & ~3;
+    const bool colour = channels > 1, remap = g->d_table != nullptr;
+    if (!colour && !remap) {                                     // plain gray frame: exactly hv_pyr_build
+        int rc = hv_pyr_build(dst, src, stride);
+        if (rc != HV_OK) return rc;
+    } else {
+        const size_t need = stride * h;
+        if (need > g->rawBytes) { cudaStreamSynchronize(c->stream); cudaFree(g->d_raw); g->d_raw = nullptr; g->rawBytes = 0; HV_CUDA(cudaMalloc(&g->d_raw, need)); g->rawBytes = need; }
+        HV_CUDA(cudaMemcpyAsync(g->d_raw, src, need, cudaMemcpyHostToDevice, c->stream));          // the only trip of the frame over PCIe
+        const uint8_t* cur = g->d_raw; int curPitch = (int)stride;
+        if (colour) {
+            float cf[4] = {0.299f, 0.587f, 0.114f, 0.0f};                                          // image.cpp:360-366
+            if (coeff) for (int i = 0; i < 4; i++) cf[i] = i < channels ? (float)coeff[i] : 0.0f;
+            uint8_t* out = remap ? g->d_gray : L0.gray; const int op = remap ? gp : L0.gpitch;
+            HV_CUDA(hv_launch_gray(cur, curPitch, channels, w, h, cf, out, op, c->stream));
+            c->launches += 1;
+            cur = out; curPitch = op;
+        }
+        if (remap) { HV_CUDA(hv_launch_remap(cur, curPitch, w, h, g->d_table, L0.gray, L0.gpitch, c->stream)); c->launches += 1; }
+        // level 0 of the pyramid now holds the ingested image: build the rest in place (no second copy of the frame)
+        unsigned short idx = (unsigned short)dst->slot;
+        const uint8_t* l0 = L0.gray; const int l0p = L0.gpitch, nl = dst->nlevels;
+        HV_CUDA(hv_launch_pyr_fused(c->d_table, &idx, nullptr, nullptr, &l0, &l0p, &nl, 1, w, h, nl, c->stream));
+        c->launches += 1;
+    }
+    if (grayOut) HV_CUDA(cudaMemcpy2DAsync(grayOut, (size_t)w, L0.gray, (size_t)L0.gpitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToHost, c->stream));
+    return HV_OK;
+}
+
 } // extern "C"

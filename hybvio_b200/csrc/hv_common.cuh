@@ -82,3 +82,9 @@ struct GfttArgs {
 };
 
 cudaError_t hv_launch_gftt(const GfttArgs& a, cudaStream_t stream);
+
+// ---- frame ingest (ingest.cu)
+#define HV_REMAP_INVALID (-32768)
+struct HvRemapEntry { short x0, y0; float xfrac, yfrac; };      // 12 bytes per output pixel (hv_remap_entry of the C ABI)
+cudaError_t hv_launch_gray(const uint8_t* src, int srcPitch, int channels, int w, int h, const float coeff[4], uint8_t* dst, int dstPitch, cudaStream_t s);
+cudaError_t hv_launch_remap(const uint8_t* src, int srcPitch, int w, int h, const HvRemapEntry* table, uint8_t* dst, int dstPitch, cudaStream_t s);

@@ -86,9 +86,32 @@ struct CudaImagePyramid : ImagePyramid {
     const std::vector<cv::Mat>& getOpenCv() final { assert(false && "device-resident pyramid: no cv::Mat view"); std::abort(); }
 };
 
+// One pool per process (the adapters share one context): the pyramid factory and the ingest adapter (cuda_undistorter.cpp) draw from it.
+std::shared_ptr<PyramidPool> globalPool() { static std::shared_ptr<PyramidPool> p = std::make_shared<PyramidPool>(); return p; }
+
+// Pyramids that the frame ingest has ALREADY built on the device (the frame was undistorted there and never needs to be uploaded again),
+// keyed by the address of the host copy of the ingested image; taken over by the pyramid factory when the tracker asks for that image's
+// pyramid. At most 8 wait here: a frame whose pyramid is never requested goes back to the pool.
+struct PrebuiltPyramids {
+    std::mutex mutex;
+    std::vector<std::pair<const void*, hv_pyr*>> entries;
+    void add(const void* key, hv_pyr* p, int w, int h) {
+        std::lock_guard<std::mutex> l(mutex);
+        for (size_t i = 0; i < entries.size(); i++) if (entries[i].first == key) { globalPool()->release(entries[i].second, w, h); entries.erase(entries.begin() + i); break; }
+        if (entries.size() >= 8) { globalPool()->release(entries.front().second, w, h); entries.erase(entries.begin()); }
+        entries.emplace_back(key, p);
+    }
+    hv_pyr* take(const void* key) {
+        std::lock_guard<std::mutex> l(mutex);
+        for (size_t i = 0; i < entries.size(); i++) if (entries[i].first == key) { hv_pyr* p = entries[i].second; entries.erase(entries.begin() + i); return p; }
+        return nullptr;
+    }
+};
+PrebuiltPyramids& prebuilt() { static PrebuiltPyramids p; return p; }
+
 class CudaImagePyramidFactory : public ImagePyramid::Factory {
     const odometry::ParametersTracker& parameters;
-    std::shared_ptr<PyramidPool> pool = std::make_shared<PyramidPool>();
+    std::shared_ptr<PyramidPool> pool = globalPool();
 public:
     explicit CudaImagePyramidFactory(const odometry::ParametersTracker& p) : parameters(p) {}
     std::shared_ptr<ImagePyramid> compute(std::shared_ptr<accelerated::Image> img) final {
@@ -96,11 +119,15 @@ public:
         auto& cpu = accelerated::cpu::Image::castFrom(*img);
         auto pyramid = std::make_shared<CudaImagePyramid>();
         pyramid->pool = pool; pyramid->width = img->width; pyramid->height = img->height; pyramid->source = img;
-        pyramid->pyr = pool->acquire(img->width, img->height, parameters.pyrLKWindowSize, parameters.pyrLKMaxLevel);
-        // H2D copy + one fused kernel, asynchronous on the context stream (cv::buildOpticalFlowPyramid in the reference)
-        // (raw pointer: the reference's gray type is FixedPoint<uint8_t>, ImagePyramid::GrayType; getData<uint8_t>() would reject it)
-        HV(hv_pyr_build(pyramid->pyr, cpu.getDataRaw(), static_cast<size_t>(cpu.bytesPerRow())));
         pyramid->key = cpu.getDataRaw();
+        if (hv_pyr* pre = prebuilt().take(pyramid->key)) {
+            pyramid->pyr = pre;                 // built on the device by the frame ingest (cuda_undistorter.cpp): nothing to copy, nothing to launch
+        } else {
+            pyramid->pyr = pool->acquire(img->width, img->height, parameters.pyrLKWindowSize, parameters.pyrLKMaxLevel);
+            // H2D copy + one fused kernel, asynchronous on the context stream (cv::buildOpticalFlowPyramid in the reference)
+            // (raw pointer: the reference's gray type is FixedPoint<uint8_t>, ImagePyramid::GrayType; getData<uint8_t>() would reject it)
+            HV(hv_pyr_build(pyramid->pyr, cpu.getDataRaw(), static_cast<size_t>(cpu.bytesPerRow())));
+        }
         registry().add(pyramid->key, pyramid->pyr);
         return pyramid;
     }
@@ -140,6 +167,10 @@ std::unique_ptr<ImagePyramid::Factory> buildCudaImagePyramidFactory(const odomet
 std::unique_ptr<OpticalFlow> buildCudaOpticalFlow(const odometry::ParametersTracker& p) {
     return std::unique_ptr<OpticalFlow>(new CudaOpticalFlow(p));
 }
+
+// frame ingest (cuda_undistorter.cpp): a pyramid from the shared pool / hand-over of a pyramid already built from the image at `hostData`
+hv_pyr* cudaAcquirePyramid(int w, int h, int win, int maxLevel) { return globalPool()->acquire(w, h, win, maxLevel); }
+void cudaRegisterPrebuiltPyramid(const void* hostData, hv_pyr* p, int w, int h) { prebuilt().add(hostData, p, w, h); }
 
 // the device pyramid whose level 0 is the host image at `data`, or NULL (cuda_feature_detector.cpp)
 hv_pyr* cudaPyramidOfHostImage(const void* data) { return registry().find(data); }

@@ -121,6 +121,28 @@ int hv_gftt_cells(const hv_pyr* pyr, int cell, int* cells_x, int* cells_y);
 int hv_gftt_detect(hv_ctx* ctx, hv_pyr* pyr, int block_size, int cell, float min_response, float* kp);
 int hv_gftt_detect_device(hv_ctx* ctx, hv_pyr* pyr, int block_size, int cell, float min_response, float* d_kp);
 
+/* ---------------------------------------------------------------- frame ingest -------- */
+/* Device part of tracker::Image::Factory::build / buildStereo (src/tracker/image.cpp:243-308): colour -> gray
+ * (accelerated-arrays pixelwiseAffine, image.cpp:360-366) and undistortion / rectification (UndistorterImplementation::undistort,
+ * src/tracker/undistorter.cpp:77-118), with the result written straight into level 0 of the frame's pyramid, followed by the fused
+ * pyramid kernel -- the frame crosses PCIe once, as it arrives.
+ *   hv_remap_entry: per OUTPUT pixel the source position the reference's cameras map it to, as undistorter.cpp:93-94 forms it:
+ *   x0 = floor(px), y0 = floor(py), xfrac = (float)(px - x0), yfrac = (float)(py - y0); x0 = HV_REMAP_INVALID_X0 where pixelToRay /
+ *   rayToPixel fail or (px, py) lies outside [0, w) x [0, h). The table belongs to a (rectified camera, original camera) pair and is
+ *   computed once by the adapter with the reference's own Camera classes (hybvio_b200/host/cuda_undistorter.cpp).
+ * hv_ingest_frame: src = HOST frame (w x h, `channels` interleaved 8-bit channels, row stride in bytes). channels > 1: gray =
+ * sum_j coeff[j] * channel_j in the reference's fixed-point arithmetic (coeff NULL: 0.299, 0.587, 0.114, 0). table (device handle from
+ * hv_ingest_set_remap) optional. dst: the pyramid to build from the ingested frame. gray_out (host, optional, w x h, tightly packed)
+ * receives the ingested gray image (the tracker::Image keeps it on the host for cornerSubPix / SLAM); asynchronous like hv_pyr_build:
+ * synchronise (hv_ctx_sync or any synchronising call) before reading it. */
+#define HV_REMAP_INVALID_X0 (-32768)
+typedef struct hv_remap_entry { int16_t x0, y0; float xfrac, yfrac; } hv_remap_entry;
+typedef struct hv_ingest hv_ingest;
+int hv_ingest_create(hv_ctx* ctx, int width, int height, hv_ingest** out);
+int hv_ingest_destroy(hv_ingest* ing);
+int hv_ingest_set_remap(hv_ingest* ing, const hv_remap_entry* table);     /* width * height entries, host; NULL removes the table */
+int hv_ingest_frame(hv_ingest* ing, const uint8_t* src, size_t stride_bytes, int channels, const double* coeff, hv_pyr* dst, uint8_t* gray_out);
+
 /* ---------------------------------------------------------------- EKF ----------------------------------- */
 /* Replaces odometry::EKF / EKFImplementation (src/odometry/ekf.hpp:62-174, ekf.cpp). State m (N) and
  * covariance P (N x N) are fp64 and live in HBM; N = 20 + 7*trail + 3*map (ekf.cpp:156-158). */

@@ -121,3 +121,45 @@ int orc_gftt_corners(const float* kp_xyr, int nkp, const float* prev_xy, int npr
     }
     return out;
 }
+
+/* ---- frame ingest, same test-infrastructure status as above -------------------------------------------------------
+ * orc_gray: accelerated-arrays pixelwiseAffineUnary<FixedPoint<uint8_t>> (AA/cpu/operations.cpp:145-177, AA/fixed_point.hpp:16-36) as
+ *           src/tracker/image.cpp:360-366 uses it: v = 0; v += coeff[j] * float(in[j]) in fp32 (channel order), out = T(v).
+ * orc_remap: UndistorterImplementation::undistort, CPU branch (src/tracker/undistorter.cpp:84-112), with the camera mapping given as a
+ *           table {x0, y0, xfrac, yfrac} per output pixel (x0 = -32768: no source pixel); taps beyond the last column / row read the
+ *           linear address like cv::Mat::at does, clamped to the last byte of the image. */
+typedef struct { int16_t x0, y0; float xfrac, yfrac; } orc_remap_entry;
+
+void orc_gray(const uint8_t* src, int stride, int channels, int w, int h, const float* coeff, uint8_t* dst)
+{
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t* p = src + (size_t)y * stride + (size_t)x * channels;
+            float v = 0.0f;
+            for (int j = 0; j < channels; j++) { const float in = (float)((double)p[j] / 255.0); v += coeff[j] * in; }
+            double d = (double)v;
+            d = d < 0.0 ? 0.0 : d > 1.0 ? 1.0 : d;
+            dst[(size_t)y * w + x] = (uint8_t)(255.0 * d + 0.5);
+        }
+}
+
+void orc_remap(const uint8_t* src, int stride, int w, int h, const orc_remap_entry* table, uint8_t* dst)
+{
+    const long long last = (long long)(h - 1) * stride + (w - 1);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const orc_remap_entry e = table[(size_t)y * w + x];
+            float out = 0.0f;
+            if (e.x0 != -32768)
+                for (int iy = 0; iy < 2; iy++) {
+                    const float wy = iy > 0 ? e.yfrac : (1 - e.yfrac);
+                    for (int ix = 0; ix < 2; ix++) {
+                        const float wx = ix > 0 ? e.xfrac : (1 - e.xfrac);
+                        long long a = (long long)(e.y0 + iy) * stride + (e.x0 + ix);
+                        if (a > last) a = last;
+                        out += src[a] * wx * wy;
+                    }
+                }
+            dst[(size_t)y * w + x] = (uint8_t)(int)(out + 0.5);
+        }
+}

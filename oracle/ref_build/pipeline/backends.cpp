@@ -14,7 +14,11 @@
 #include "optical_flow.hpp"
 #include "parameters.hpp"
 #include "tracker.hpp"
+#include "undistorter.hpp"
+#include "camera.hpp"
 #include "hybvio_b200.h"
+#include "undistort_table.hpp"
+#include <accelerated-arrays/cpu/image.hpp>
 
 #include <opencv2/core.hpp>
 #include <algorithm>
@@ -37,6 +41,8 @@ std::unique_ptr<ImagePyramid::Factory> buildCudaImagePyramidFactory(const odomet
 std::unique_ptr<OpticalFlow> buildCudaOpticalFlow(const odometry::ParametersTracker&);
 hv_pyr* cudaPyramidHandle(ImagePyramid&);
 std::unique_ptr<FeatureDetector> buildCudaFeatureDetector(int w, int h, const odometry::ParametersTracker&);
+std::unique_ptr<Undistorter> buildCudaUndistorter(int w, int h, std::shared_ptr<const Camera> rectifiedCamera, accelerated::Image::Factory& ifac,
+                                                  const odometry::ParametersTracker& p);
 }
 namespace odometry { std::unique_ptr<EKF> buildCudaEKF(const Parameters&); }
 
@@ -157,6 +163,37 @@ struct DualDetector : FeatureDetector {
     }
     bool supportsAsync() const final { return false; }
     void debugVisualize(cv::Mat& m) final { ref->debugVisualize(m); }
+};
+
+// ------------------------------------------------------------------------------------------------ undistortion / rectification, lock-step
+// Both run on the same input; the images must be bit-identical wherever the reference's own bilinear taps stay inside its image buffer
+// (it reads a tap right of the last column / below the last row without a bounds check, undistorter.cpp:101: those pixels are undefined in
+// the reference itself and are counted separately).
+struct DualUndistorter : Undistorter {
+    std::unique_ptr<Undistorter> ref, cuda;
+    std::shared_ptr<const Camera> rectified;
+    int w, h;
+    std::vector<hv_remap_entry> table;
+    std::string tableFor;
+    Result undistort(accelerated::Image& image, std::shared_ptr<const Camera> camera) final {
+        Result a = ref->undistort(image, camera);
+        Result b = cuda->undistort(image, camera);
+        a.future.wait(); b.future.wait();
+        if (camera->serialize() != tableFor) { hybvio_b200::buildUndistortTable(*a.camera, *camera, w, h, table); tableFor = camera->serialize(); }
+        const uint8_t* pa = accelerated::cpu::Image::castFrom(*a.image).getDataRaw();
+        const uint8_t* pb = accelerated::cpu::Image::castFrom(*b.image).getDataRaw();
+        Stats& s = g_stats;
+        s.undCalls++;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                const hv_remap_entry& e = table[(size_t)y * w + x];
+                const bool defined = e.x0 == HV_REMAP_INVALID_X0 || (e.x0 + 1 < w && e.y0 + 1 < h);
+                if (!defined) { s.undUndefined++; continue; }
+                s.undPixels++;
+                if (pa[(size_t)y * w + x] != pb[(size_t)y * w + x]) s.undMismatch++;
+            }
+        return a;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------ EKF, lock-step
@@ -387,6 +424,23 @@ std::unique_ptr<tracker::FeatureDetector> FD_CAT(__wrap_, FD_BUILD)(int w, int h
     if (flavour() == Flavour::REF || !useCudaDetector() || p.featureDetector != "GPU-GFTT") return FD_CAT(__real_, FD_BUILD)(w, h, proc, ifac, ofac, p);
     if (flavour() == Flavour::CUDA) return tracker::buildCudaFeatureDetector(w, h, p);
     return std::unique_ptr<tracker::FeatureDetector>(new DualDetector(p, FD_CAT(__real_, FD_BUILD)(w, h, proc, ifac, ofac, p), tracker::buildCudaFeatureDetector(w, h, p)));
+}
+}
+
+// tracker::Undistorter::buildRectified / buildMono (src/tracker/image.cpp:323-336), intercepted with -Wl,--wrap
+extern "C" {
+#define UR_BUILD _ZN7tracker11Undistorter14buildRectifiedEiiSt10shared_ptrIKNS_6CameraEERN11accelerated5Image7FactoryERNS5_10operations15StandardFactoryERKN8odometry17ParametersTrackerE
+std::unique_ptr<tracker::Undistorter> FD_CAT(__real_, UR_BUILD)(int, int, std::shared_ptr<const tracker::Camera>, accelerated::Image::Factory&,
+                                                                accelerated::operations::StandardFactory&, const odometry::ParametersTracker&);
+std::unique_ptr<tracker::Undistorter> FD_CAT(__wrap_, UR_BUILD)(int w, int h, std::shared_ptr<const tracker::Camera> cam, accelerated::Image::Factory& ifac,
+                                                                accelerated::operations::StandardFactory& ofac, const odometry::ParametersTracker& p) {
+    using namespace harness;
+    auto real = FD_CAT(__real_, UR_BUILD)(w, h, cam, ifac, ofac, p);
+    if (!real || flavour() == Flavour::REF) return real;
+    if (flavour() == Flavour::CUDA) return tracker::buildCudaUndistorter(w, h, cam, ifac, p);
+    auto d = std::make_unique<DualUndistorter>();
+    d->ref = std::move(real); d->cuda = tracker::buildCudaUndistorter(w, h, cam, ifac, p); d->rectified = cam; d->w = w; d->h = h;
+    return d;
 }
 }
 

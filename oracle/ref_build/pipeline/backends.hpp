@@ -45,6 +45,8 @@ struct Stats {
     // corner detector (DUAL): corner lists of FeatureDetector::detect, reference against CUDA
     long detCalls = 0, detCorners = 0, detMismatch = 0;
     int detFirstMismatchFrame = -1;
+    // undistortion / rectification (DUAL): output images of Undistorter::undistort, reference against CUDA
+    long undCalls = 0, undPixels = 0, undMismatch = 0, undUndefined = 0;
     // tracker (DUAL): reference-driven tracker against the CUDA-driven shadow tracker
     long trkFrames = 0, trkTracks = 0, trkIdMismatch = 0, trkStatusMismatch = 0, trkSizeMismatch = 0, trkKeyframeMismatch = 0;
     double trkMaxPointDiff = 0;

@@ -108,7 +108,7 @@ std::string jsonVec(const std::vector<double>& v) {
 
 int main(int argc, char** argv) {
     std::string mode = "ref", outPath;
-    int configId = 2, frames = 120, threads = 0, keepP = 0;
+    int configId = 2, frames = 120, threads = 0, keepP = 0, rectify = 0;
     double still = 1.0, motion = 1.0;
     for (int i = 1; i < argc; i++) {
         auto arg = [&](const char* k) { return !std::strcmp(argv[i], k) && i + 1 < argc; };
@@ -121,11 +121,15 @@ int main(int argc, char** argv) {
         else if (arg("--motion")) motion = std::atof(argv[++i]);
         else if (arg("--keep-cov")) keepP = std::atoi(argv[++i]);
         else if (arg("--cuda-detector")) harness::setUseCudaDetector(std::atoi(argv[++i]) != 0);
+        else if (arg("--rectify")) rectify = std::atoi(argv[++i]);
         else { std::fprintf(stderr, "usage: run_pipeline --mode ref|cuda|lockstep|free [--config 2|4|1] [--frames N] [--out file.json] [--threads T]\n"); return 2; }
     }
     const Config cfg = makeConfig(configId);
     odometry::Parameters params;
     fillParameters(params, cfg);
+    // --rectify 1: stereo rectification on (tracker.useRectification): every frame goes through StereoRectifier + Undistorter
+    // (src/tracker/image.cpp:316-332), i.e. through the frame-ingest row N4
+    if (rectify) { params.tracker.useRectification = true; }
     if (threads > 0) harness::setRefThreads(threads);
 
     synth::Room room;
@@ -275,6 +279,7 @@ int main(int argc, char** argv) {
         for (const auto& kv : S.ekfOps) { js << (first ? "" : ", ") << "\"" << kv.first << "\": {\"calls\": " << kv.second.calls << ", \"pos\": " << kv.second.maxPos << ", \"m\": " << kv.second.maxM << ", \"P_rel\": " << kv.second.maxPrel << "}"; first = false; }
         js << "},\n   \"position_diff_by_frame\": " << jsonVec(S.framePos) << ",\n   \"cov_rel_diff_by_frame\": " << jsonVec(S.framePrel) << "},\n"
            << "  \"detector\": {\"calls\": " << S.detCalls << ", \"corners\": " << S.detCorners << ", \"mismatch\": " << S.detMismatch << ", \"first_mismatch_frame\": " << S.detFirstMismatchFrame << "},\n"
+           << "  \"undistorter\": {\"calls\": " << S.undCalls << ", \"pixels\": " << S.undPixels << ", \"mismatch\": " << S.undMismatch << ", \"undefined_in_reference\": " << S.undUndefined << "},\n"
            << "  \"tracker\": {\"frames\": " << S.trkFrames << ", \"tracks\": " << S.trkTracks << ", \"id_mismatch\": " << S.trkIdMismatch << ", \"status_mismatch\": " << S.trkStatusMismatch
            << ", \"size_mismatch\": " << S.trkSizeMismatch << ", \"keyframe_mismatch\": " << S.trkKeyframeMismatch << ", \"first_mismatch_frame\": " << S.trkFirstMismatchFrame
            << ", \"max_point_diff_px\": " << S.trkMaxPointDiff << "}\n }";

@@ -36,7 +36,7 @@ def run(mode, config, frames, extra=()):
     if not os.path.exists(EXE):
         pytest.skip("oracle/_ref/run_pipeline not built (needs /root/reference at build time: oracle/ref_build/Makefile.pipeline)")
     os.makedirs(OUT, exist_ok=True)
-    path = os.path.join(OUT, f"pipeline_{mode}_config{config}.json")
+    path = os.path.join(OUT, f"pipeline_{mode}_config{config}{'_rectified' if extra else ''}.json")
     r = subprocess.run([EXE, "--mode", mode, "--config", str(config), "--frames", str(frames), "--out", path, *extra],
                        cwd=os.path.join(ROOT, "oracle", "_ref"), capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
@@ -85,6 +85,34 @@ def test_lockstep_parity_through_the_unmodified_reference_core(config, frames):
     assert e["decision_mismatch"] == 0
     assert e["max_position_diff_m"] <= TOL_POS_M, e["ops"]
     assert e["max_cov_rel_diff"] <= TOL_P_REL, e["ops"]
+
+
+@pytest.mark.gpu
+def test_lockstep_with_stereo_rectification_on_the_device():
+    """tracker.useRectification = true: every frame goes through StereoRectifier + Undistorter (src/tracker/image.cpp:316-332), i.e. through
+    the frame-ingest row N4. Lock-step: Undistorter::undistort of the reference (CPU branch of undistorter.cpp) and of the CUDA adapter
+    (hybvio_b200/host/cuda_undistorter.cpp: table from the reference's own cameras, interpolation on the device) on the same frames,
+    bit-identical wherever the reference's taps stay inside its buffer; everything downstream as in the other lock-step runs."""
+    d, _ = run("lockstep", 2, 120, ("--rectify", "1"))
+    L = d["lockstep"]
+    print(json.dumps({k: L[k] for k in ("undistorter", "pyramid", "lk", "detector", "tracker")}))
+    u = L["undistorter"]
+    assert u["calls"] >= 2 * 115 and u["pixels"] > 100 * 752 * 470
+    assert u["mismatch"] == 0, u
+    assert L["pyramid"]["mismatching_bytes"] == 0 and L["lk"]["status_mismatch"] == 0 and L["detector"]["mismatch"] == 0
+    assert L["tracker"]["id_mismatch"] == 0 and L["tracker"]["status_mismatch"] == 0
+    assert L["ekf"]["decision_mismatch"] == 0 and L["ekf"]["max_position_diff_m"] <= TOL_POS_M and L["ekf"]["max_cov_rel_diff"] <= TOL_P_REL
+
+
+@pytest.mark.gpu
+def test_cuda_pipeline_with_rectification_uses_the_prebuilt_pyramids():
+    """CUDA flavour with rectification: the ingest adapter builds the pyramid of every frame on the device and hands it to the pyramid
+    factory (no second upload); the pipeline must track as well as the reference does on the same stream."""
+    d, _ = run("free", 2, 120, ("--rectify", "1"))
+    ref, cu = d["pipelines"]
+    assert cu["frames_tracking"] >= 80 and ref["frames_tracking"] >= 80
+    assert abs(cu["position_error_vs_ground_truth_m"] - ref["position_error_vs_ground_truth_m"]) < 0.02
+    assert max(d["free_running"]["position_diff_m_by_frame"][:40]) <= TOL_POS_M
 
 
 @pytest.mark.gpu
