@@ -164,7 +164,7 @@ def test_every_entry_point_survives_null_arguments():
     r = subprocess.run([sys.executable, "-c", _NULL_PROBE.format(root=ROOT, names=names)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "probe complete" in r.stdout, "crashed in " + r.stdout.strip().splitlines()[-1] + "\n" + r.stderr[-500:]
     results = dict(l.split(" -> ") for l in r.stdout.splitlines() if " -> " in l)
-    noop_ok = {"hv_ctx_destroy", "hv_ekf_destroy", "hv_pyr_release", "hv_device_count", "hv_ctx_launch_count", "hv_ekf_was_stationary"}
+    noop_ok = {"hv_ctx_destroy", "hv_ekf_destroy", "hv_pyr_release", "hv_ingest_destroy", "hv_device_count", "hv_ctx_launch_count", "hv_ekf_was_stationary"}
     wrong = [n for n, v in results.items() if v.lstrip("-").isdigit() and int(v) >= 0 and n not in noop_ok]
     assert not wrong, f"status 0 for NULL arguments: {wrong}"
 
