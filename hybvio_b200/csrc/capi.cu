@@ -42,11 +42,18 @@ static int ctx_create(int device, cudaStream_t stream, bool own, hv_ctx** out)
     HV_CUDA(cudaSetDevice(device));
     hv_ctx* c = new hv_ctx;
     c->device = device;
-    if (own) { HV_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
+    // every failure below releases what has been created so far (hv_ctx_destroy tolerates a partly initialised context)
+    auto fail = [&](cudaError_t e, const char* what) {
+        hv_set_error("hv_ctx_create: %s failed: %s", what, cudaGetErrorString(e));
+        hv_ctx_destroy(c);
+        return e == cudaErrorMemoryAllocation ? HV_ERR_OOM : HV_ERR_CUDA;
+    };
+    cudaError_t e = cudaSuccess;
+    if (own) { e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); if (e != cudaSuccess) { c->stream = nullptr; return fail(e, "cudaStreamCreate"); } c->ownStream = true; }
     else c->stream = stream;
-    HV_CUDA(cudaMalloc(&c->d_table, sizeof(HvPyrDesc) * HV_TABLE_CAPACITY));
-    HV_CUDA(cudaMemsetAsync(c->d_table, 0, sizeof(HvPyrDesc) * HV_TABLE_CAPACITY, c->stream));
-    HV_CUDA(cudaStreamSynchronize(c->stream));
+    if ((e = cudaMalloc(&c->d_table, sizeof(HvPyrDesc) * HV_TABLE_CAPACITY)) != cudaSuccess) { c->d_table = nullptr; return fail(e, "cudaMalloc"); }
+    if ((e = cudaMemsetAsync(c->d_table, 0, sizeof(HvPyrDesc) * HV_TABLE_CAPACITY, c->stream)) != cudaSuccess) return fail(e, "cudaMemsetAsync");
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
     for (int i = HV_TABLE_CAPACITY - 1; i >= 0; --i) c->freeSlots.push_back(i);
     *out = c;
     return HV_OK;
@@ -59,14 +66,14 @@ int hv_ctx_destroy(hv_ctx* c)
 {
     if (!c) return HV_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream || !c->ownStream) cudaStreamSynchronize(c->stream);
     if (c->d_table) cudaFree(c->d_table);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_done) cudaFree(c->d_done);
     if (c->d_ekfStage) cudaFree(c->d_ekfStage);
     if (c->h_ekfStage) cudaFreeHost(c->h_ekfStage);
-    if (c->ownStream) cudaStreamDestroy(c->stream);
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return HV_OK;
 }

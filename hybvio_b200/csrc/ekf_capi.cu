@@ -641,19 +641,28 @@ int hv_ekf_visual_check_update(hv_ekf* e, const double* H, int n, int l, const d
     return visual_host(e, "hv_ekf_visual_check_update", H, n, l, f, y, r, rmseThr, EKF_MODE_CHECK_UPDATE, vuStatus, chi2, mOut);
 }
 
-int hv_ekf_visual_device(hv_ekf* e, const double* dH, int n, int l, const double* df, const double* dy, double r, double rmseThr,
-                         int mode, double* dResult)
+static int visual_device(hv_ekf* e, const double* dH, int n, int l, const double* df, const double* dy, double r, double rmseThr,
+                         int mode, double* dResult, int lateH)
 {
-    EKF_ENTER(e, "hv_ekf_visual_device");
     if (!dH || !df || !dy || mode < 0 || mode > 2) { hv_set_error("hv_ekf_visual_device: invalid argument"); return HV_ERR_INVALID; }
     EkfUpdateArgs a;
     int rc = visual_args(e, "hv_ekf_visual_device", n, l, r, rmseThr, mode, a);
     if (rc != HV_OK) return rc;
     a.H = dH; a.f = df; a.y = dy;
+    // caller-owned device pointers: H may have been produced by the caller's previous kernel on this stream (hv_ctx_create_on_stream),
+    // so it is staged AFTER griddepcontrol.wait; early staging is kept for H that arrived through the library's own H2D copy
+    a.lateH = lateH;
     rc = launch_update(e, a);
     if (rc != HV_OK) return rc;
     if (dResult) HV_CUDA(cudaMemcpyAsync(dResult, e->b.res, 2 * sizeof(double), cudaMemcpyDeviceToDevice, e->ctx->stream));
     return HV_OK;
+}
+
+int hv_ekf_visual_device(hv_ekf* e, const double* dH, int n, int l, const double* df, const double* dy, double r, double rmseThr,
+                         int mode, double* dResult)
+{
+    EKF_ENTER(e, "hv_ekf_visual_device");
+    return visual_device(e, dH, n, l, df, dy, r, rmseThr, mode, dResult, 1);
 }
 
 int hv_ekf_augment(hv_ekf* e, int discarded)
@@ -827,7 +836,7 @@ static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vu
                 if (o.mode < 0 || o.mode > 2) { hv_set_error("hv_ekf_run: op %d: bad mode", i); return HV_ERR_INVALID; }
                 if (host) rc = visual_host(e, "hv_ekf_run_host", o.H, o.n, o.l, o.f, o.y, o.r, o.rmse_thr, o.mode,
                                            vuStatus ? vuStatus + i : nullptr, chi2 ? chi2 + i : nullptr, nullptr);
-                else rc = hv_ekf_visual_device(e, o.H, o.n, o.l, o.f, o.y, o.r, o.rmse_thr, o.mode, nullptr);
+                else rc = visual_device(e, o.H, o.n, o.l, o.f, o.y, o.r, o.rmse_thr, o.mode, nullptr, 0);    // prepared inputs (see the header): staged early
                 break;
             case HV_EKF_OP_SYMMETRIZE: rc = hv_ekf_symmetrize(e); break;
             case HV_EKF_OP_AUGMENT: rc = hv_ekf_augment(e, o.index); break;

@@ -242,8 +242,10 @@ typedef struct hv_ekf_op {
     const double* H; const double* f; const double* y;
 } hv_ekf_op;
 /* H/f/y are DEVICE pointers; fully asynchronous. Consecutive independent outlier checks (mode 0) are issued as one launch, one
- * cluster per measurement; with HV_EKF_PERSIST=1 in the environment consecutive update / check+update ops (modes 1, 2) become one
- * persistent launch as well (the covariance blocks stay in shared memory between them; same results). */
+ * cluster per measurement. The measurement inputs of a list are PREPARED inputs: the kernels read them while their predecessor on the
+ * stream may still be running (programmatic dependent launch), so they must not be produced by work queued on this stream after that
+ * predecessor. For H produced by the caller's own kernel right before the call use hv_ekf_visual_device, which reads its inputs only
+ * after the dependency on all earlier work of the stream has been resolved. */
 int hv_ekf_run_device(hv_ekf* ekf, const hv_ekf_op* ops, int nops);
 /* H/f/y are HOST pointers; every VISUAL op with mode 0 or 2 returns its VuOutlierStatus / chi2 into
  * vu_status[i] / chi2[i] (arrays of length nops, entries of other ops untouched) -- i.e. each such op is a host
