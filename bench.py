@@ -407,6 +407,22 @@ def adapter_e2e(inputs, h_frames, which, nframes, warmup):
                     f"{UPDATES} inliers, H / f / y as caller-owned Eigen objects per call, host frames in, pose out; wall clock of the calling thread"}
 
 
+def pin_to_numa_node(node):
+    """Pins this process to the host cores of NUMA node `node` (best effort); returns the node or None."""
+    try:
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def pin_to_gpu_numa_node(torch, local):
     """Pins this process to the host cores of the NUMA node its GPU hangs off (the end-to-end numbers are host-latency bound: a rank on
     the far socket pays for every one of its ~30 synchronous round trips per frame). Best effort; returns the node or None."""
@@ -1017,6 +1033,10 @@ def run_reference(args):
         return
     import torch
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
+    # The reference gets the same host placement as our arm: the cores of ONE NUMA node (the GPU's, or node 0). Measured on the 2-socket B200
+    # hosts: OpenCV's thread pool spread over both sockets needs 3.5 ms per pyramid pair and 4.9 ms per LK pair, pinned to one socket 0.67 /
+    # 0.32 ms -- unpinned the reference arm ran at 80 frames/s, pinned at 139.
+    numa_node = pin_to_gpu_numa_node(torch, int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else pin_to_numa_node(0)
     inputs = Inputs(dev, seed=0)       # torch is only the synthetic-input generator here; the timed path is pure CPU
     rs = RefSession(inputs)
     # >= 50 warm-up frames whatever --warmup says: OpenCV's thread pool, the page cache of the frame pool and the CPU clocks need them
@@ -1039,7 +1059,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": ref_warmup, "ms_per_step": round(dt / args.steps * 1e3, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16 fixed-point + f32 (pyramid, LK), f64 (EKF)", "data": "synthetic",
         "config": {"workload": CONFIG_NAME + " (same step as the CUDA arm) on the host CPU; ONE session on rank 0 whatever --gpus says",
-                   "baseline_config": CONFIG_ID},
+                   "baseline_config": CONFIG_ID, "host_numa_node_pinned": numa_node},
         "sessions": 1,
         "e2e_adapter": ad or {"unavailable": "oracle/_ref/libref_adapter_e2e.so not built"},
         "cpu_baseline": {"value": round(v, 2), "unit": "frames/s", "cores": rs.cores, "kind": rs.kind, "host_cores": os.cpu_count(),

@@ -92,6 +92,10 @@ struct EkfUpdateArgs {
     int* bump;
     double* slot;
     int lateH, padGate;
+    // Speculative update (ekf_cluster2.cuh, dense check+update only; NULL: off): the updated covariance blocks and state mean are written
+    // to specP / specM instead of P / m, which stay untouched -- the host adopts them by swapping pointers if the caller's
+    // updateVisualTrack(H, f, y, r) really follows the INLIER check with the same measurement (hv_ekf_visual_update).
+    double* specP; double* specM;
     // EKF_MODE_CHECK_UPDATE with two noise levels (ekf_cluster2.cuh only; 0: off): the outlier check uses Rdiag, the update that
     // follows an INLIER decision uses Rdiag2 -- visualTrackOutlierCheck(trackChiTestOutlierR) then updateVisualTrack(visualR),
     // backend.cpp:1158-1185, in one kernel: H P and S0 = H P H' are formed once, S0 + R is factorised twice.

@@ -27,6 +27,12 @@ struct hv_ekf {
     double* d_sig = nullptr;      // (device alias)
     double* h_run = nullptr;      // mapped pinned result words of hv_ekf_run_host: 4 doubles per op of the list (HV_RUN_MAX_OPS)
     double* d_run = nullptr;      // (device alias)
+    // Speculative update behind an INLIER check (visual_host): results wait in P2 / m2 until hv_ekf_visual_update adopts them
+    double* m2 = nullptr;                   // second state mean (device)
+    unsigned long long epoch = 0;           // bumped by everything that changes the filter state on the device
+    struct { bool valid = false; unsigned long long epoch = 0; int n = 0, l = 0; } spec;
+    double specR = -1.0;                    // noise level of the last updateVisualTrack (what the next check speculates with); < 0: none yet
+    bool specEnabled = false;               // the caller follows INLIER checks with updates (switched off by the first speculation nobody adopts)
     cudaStream_t copyStream = nullptr;            // hv_ekf_run_host: the measurement inputs travel on their own stream, ahead of the kernels
     std::vector<cudaEvent_t> copyEvents;          // one per measurement group of a list (created on demand)
     double sigSeq = 0.0;
@@ -128,6 +134,7 @@ static void prep_update(hv_ekf* e, EkfUpdateArgs& a)
 }
 static int launch_update(hv_ekf* e, EkfUpdateArgs& a)
 {
+    e->epoch++;
     prep_update(e, a);
     HV_CUDA(ekf_launch_update(a, e->ctx->stream));
     e->ctx->launches++;
@@ -143,6 +150,7 @@ static void fill_small(EkfUpdateArgs& a, int op, int n, int l, double Rdiag, int
 static int launch_ew(hv_ekf* e, int op, int ival0 = 0, const double* dv = nullptr, int ndv = 0)
 {
     EkfEwArgs a; memset(&a, 0, sizeof(a));
+    e->epoch++;
     a.b = e->b; a.op = op; a.ival0 = ival0;
     for (int i = 0; i < ndv; i++) a.dval[i] = dv[i];
     HV_CUDA(ekf_launch_elementwise(a, e->ctx->stream));
@@ -180,14 +188,15 @@ static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
     const size_t workD = N * (2 * N + 4);
     const size_t cworkD = (size_t)EKF_MAX_BATCH * 10 * NN;
     e->inDoubles = (size_t)EKF_MAX_BATCH * (NN + 2 * N);
-    const size_t total = N + NN + NN + workD + cworkD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + EKF_RES_STRIDE * (EKF_MAX_BATCH + 1) + e->inDoubles;
+    const size_t total = N + NN + NN + workD + cworkD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + EKF_RES_STRIDE * (EKF_MAX_BATCH + 1) + e->inDoubles + N;
     cudaError_t err = cudaMalloc(&e->d_block, total * sizeof(double));
     if (err != cudaSuccess) { delete e; hv_set_error("hv_ekf_create: cudaMalloc failed: %s", cudaGetErrorString(err)); return HV_ERR_OOM; }
     cudaMemsetAsync(e->d_block, 0, total * sizeof(double), c->stream);
     double* p = e->d_block;
     e->b.m = p; p += N; e->b.P = p; p += NN; e->b.P2 = p; p += NN; e->b.work = p; p += workD; e->b.cwork = p; p += cworkD;
     e->b.Hs = p; p += EKF_SMALL_MAXN * EKF_SMALL_MAXL; e->b.Q = p; p += 144; e->b.dydx = p; p += 400; e->b.res = p; p += EKF_RES_STRIDE * (EKF_MAX_BATCH + 1);
-    e->d_in = p;
+    e->d_in = p; p += e->inDoubles;
+    e->m2 = p;
     e->b.N = e->N; e->b.trail = e->trail; e->b.mapDim = e->mapDim;
     err = cudaMallocHost(&e->h_pin, (e->inDoubles + N + 8 + EKF_RES_STRIDE * EKF_MAX_BATCH) * sizeof(double));
     if (err != cudaSuccess) { cudaFree(e->d_block); delete e; hv_set_error("hv_ekf_create: cudaMallocHost failed"); return HV_ERR_OOM; }
@@ -306,6 +315,7 @@ int hv_ekf_set_first_sample_time(hv_ekf* e, double t)
 int hv_ekf_upload(hv_ekf* e, const double* m, const double* P)
 {
     EKF_ENTER(e, "hv_ekf_upload");
+    e->epoch++;
     const size_t N = e->N;
     if (m) HV_CUDA(cudaMemcpyAsync(e->b.m, m, sizeof(double) * N, cudaMemcpyHostToDevice, e->ctx->stream));
     if (P) HV_CUDA(cudaMemcpyAsync(e->b.P, P, sizeof(double) * N * N, cudaMemcpyHostToDevice, e->ctx->stream));
@@ -337,6 +347,7 @@ int hv_ekf_set_inertial_state(hv_ekf* e, const double* m20, const double* P20)
 {
     EKF_ENTER(e, "hv_ekf_set_inertial_state");
     if (!m20 || !P20) { hv_set_error("hv_ekf_set_inertial_state: NULL"); return HV_ERR_INVALID; }
+    e->epoch++;
     HV_CUDA(cudaMemcpyAsync(e->b.m, m20, sizeof(double) * 20, cudaMemcpyHostToDevice, e->ctx->stream));
     HV_CUDA(cudaMemcpy2DAsync(e->b.P, e->N * sizeof(double), P20, 20 * sizeof(double), 20 * sizeof(double), 20,
                               cudaMemcpyHostToDevice, e->ctx->stream));
@@ -417,6 +428,7 @@ static int predict_launch(hv_ekf* e, EkfPredictArgs& a)
 {
     if (a.count == 0) return HV_OK;
     a.b = e->b; a.gravity = e->prm.gravity;
+    e->epoch++;
     HV_CUDA(ekf_launch_predict(a, e->ctx->stream));
     e->ctx->launches++;
     a.count = 0;
@@ -587,6 +599,22 @@ static int visual_host(hv_ekf* e, const char* who, const double* H, int n, int l
     cudaStream_t s = e->ctx->stream;
     const size_t nl = (size_t)n * l, inD = nl + 2 * (size_t)n;
     double* hin = e->h_pin;
+    if (mode == EKF_MODE_UPDATE && !mOut && e->spec.valid) {
+        // updateVisualTrack right behind an INLIER visualTrackOutlierCheck of the SAME measurement (the reference's per-track loop,
+        // backend.cpp:1158-1185): the check kernel has already produced the updated state with this noise level in P2 / m2 -- adopt it.
+        const bool same = e->spec.epoch == e->epoch && e->spec.n == n && e->spec.l == l && r == e->specR &&
+                          memcmp(hin, H, nl * sizeof(double)) == 0 && memcmp(hin + nl, f, n * sizeof(double)) == 0 && memcmp(hin + nl + n, y, n * sizeof(double)) == 0;
+        e->spec.valid = false;
+        if (same) {
+            double* t = e->b.P; e->b.P = e->b.P2; e->b.P2 = t;
+            t = e->b.m; e->b.m = e->m2; e->m2 = t;
+            e->epoch++;
+            return HV_OK;
+        }
+    }
+    if (e->spec.valid) e->specEnabled = false;     // an INLIER check that was NOT followed by its update: stop speculating until an update call comes again
+    e->spec.valid = false;
+    if (mode == EKF_MODE_UPDATE) { e->specR = r; e->specEnabled = true; }
     rc = staging_acquire(e);
     if (rc != HV_OK) return rc;
     memcpy(hin, H, nl * sizeof(double)); memcpy(hin + nl, f, n * sizeof(double)); memcpy(hin + nl + n, y, n * sizeof(double));
@@ -597,6 +625,13 @@ static int visual_host(hv_ekf* e, const char* who, const double* H, int n, int l
     prep_update(e, a);
     const bool polled = ekf_polling() && mode != EKF_MODE_UPDATE && !mOut && ekf_update_uses_cluster2(a);
     if (polled) { a.sig = e->d_sig; a.sigSeq = (e->sigSeq += 1.0); }
+    // A pure check speculates: the same kernel goes on to compute the update the reference issues for an INLIER (with the noise level of the
+    // previous updateVisualTrack) into P2 / m2, while the host already has the decision; P and m stay as they are.
+    const bool speculate = polled && mode == EKF_MODE_CHECK && e->specEnabled && e->specR > 0.0 && !a.skipChi2 && a.rmseThr < 0.0 && r > 0.0;
+    if (speculate) {
+        a.mode = EKF_MODE_CHECK_UPDATE; a.Rdiag2 = (e->specR * e->specR) * e->noiseScale;
+        a.specP = e->b.P2; a.specM = e->m2;
+    }
     rc = launch_update(e, a);
     if (rc != HV_OK) return rc;
     if (mode == EKF_MODE_UPDATE && !mOut) return HV_OK;          // asynchronous
@@ -608,6 +643,7 @@ static int visual_host(hv_ekf* e, const char* who, const double* H, int n, int l
         if (vuStatus) *vuStatus = (int)e->h_sig[0];
         if (chi2) *chi2 = e->h_sig[1];
         if (e->h_sig[2] != 0.0) { hv_set_error("%s: innovation covariance not positive definite", who); return HV_ERR_STATE; }
+        if (speculate && e->h_sig[0] == 0.0) { e->spec.valid = true; e->spec.epoch = e->epoch; e->spec.n = n; e->spec.l = l; }
         return HV_OK;
     }
     double* hout = e->h_pin + e->inDoubles;

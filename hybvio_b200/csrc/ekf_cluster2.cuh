@@ -606,6 +606,12 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     const bool bad = !ek2_block_eliminate(T, W, n, cend + 1, wrp, lane, s_linv, &s_bad);
     if (bad) {                                        // uniform over the cluster
         if (c == 0 && tid == 0) ek2_report(a, 1.0, 0.0, 1.0);
+        if (a.specP && !joseph) {
+            // speculative update that cannot be computed: leave the UNCHANGED state in the speculative buffers, so that adopting them
+            // equals a skipped update (what the non-speculative path does when this elimination fails)
+            for (int idx = tid; idx < N * Bc; idx += EK2_NT) a.specP[(size_t)J0 * N + idx] = P[(size_t)J0 * N + idx];
+            if (c == 0) for (int i = tid; i < N; i += EK2_NT) a.specM[i] = a.b.m[i];
+        }
         cluster.sync();
         return;
     }
@@ -668,7 +674,8 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         for (int q = tid; q < (a.normalizeAll ? a.b.trail + 1 : 1); q += EK2_NT)
             ek2_normalize_quat(q == 0 ? s_m + EKF_ORI : s_m + EKF_CAM + EKF_POSE * (q - 1) + 3);
         __syncthreads();
-        for (int i = tid; i < N; i += EK2_NT) a.b.m[i] = s_m[i];
+        double* const mDst = (a.specM && !joseph) ? a.specM : a.b.m;
+        for (int i = tid; i < N; i += EK2_NT) mDst[i] = s_m[i];
     } else __syncthreads();
     EK2_PHASE(8);
 
@@ -745,7 +752,8 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
             }
         }
     } else {
-        for (int idx = tid; idx < N * Bc; idx += EK2_NT) P[(size_t)J0 * N + idx] = Pblk[(idx % N) + (size_t)(idx / N) * ldb];
+        double* const Pdst = (a.specP && !joseph) ? a.specP : P;
+        for (int idx = tid; idx < N * Bc; idx += EK2_NT) Pdst[(size_t)J0 * N + idx] = Pblk[(idx % N) + (size_t)(idx / N) * ldb];
     }
     EK2_PHASE(9);
     if (a.bump && c == 0 && tid == 0) *a.bump = *a.bump + 1;          // one writer per grid; kernels of a chain are stream-ordered

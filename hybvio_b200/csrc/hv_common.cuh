@@ -63,6 +63,7 @@ struct LkLaunch {
     unsigned* doneCounter;
     unsigned doneTarget, seq;
     volatile unsigned* hostFlag;
+    int prefetch;               // CTA-per-feature kernel: request the search region of a level with cp.async before the template patch is loaded
 };
 
 

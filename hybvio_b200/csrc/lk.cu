@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(NW * 32) hv_lk_cta_kernel(LkLaunch L)
             lk_cp_async_wait_all();                          // a request of a level that was skipped after it was issued
             __syncthreads();
             const int inx0 = cv_floor(__fsub_rn(nx, halfWin)), iny0 = cv_floor(__fsub_rn(ny, halfWin));
-            if (!(inx0 < -WIN || inx0 >= LJ.w || iny0 < -WIN || iny0 >= LJ.h)) {
+            if (L.prefetch && !(inx0 < -WIN || inx0 >= LJ.w || iny0 < -WIN || iny0 >= LJ.h)) {
                 const int qx = (inx0 - LK_REG_M) & ~3, qy = iny0 - LK_REG_M;
                 if (qx >= 0 && qx + LK_REG_W <= LJ.w && qy >= 0 && qy + LK_REG_H <= LJ.h) {
                     const uint8_t* g0 = LJ.gray + (size_t)qy * LJ.gpitch + qx;

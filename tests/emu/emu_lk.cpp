@@ -80,7 +80,7 @@ int main()
         std::vector<float> onext = init, knext = init; std::vector<uint8_t> ost(N), kst(N, 7); std::vector<int32_t> kts(N, -1);
         orc_lk(pa, pb, prev.data(), onext.data(), ost.data(), N, MAXL, 20, 0.03, useInitial, 1e-3, 1);
         LkLaunch L; memset(&L, 0, sizeof(L));
-        L.table = table; L.njobs = 1; L.maxLevel = MAXL; L.maxIter = 20; L.eps2 = 0.03 * 0.03; L.minEig = 1e-3f;
+        L.table = table; L.njobs = 1; L.prefetch = 1; L.maxLevel = MAXL; L.maxIter = 20; L.eps2 = 0.03 * 0.03; L.minEig = 1e-3f;
         L.jobs[0].prevIdx = 0; L.jobs[0].nextIdx = 1; L.jobs[0].n = N; L.jobs[0].useInitial = useInitial;
         L.jobs[0].prevPts = (const float2*)prev.data(); L.jobs[0].nextPts = (float2*)knext.data(); L.jobs[0].status = kst.data(); L.jobs[0].trackStatus = kts.data();
         if (variant == 0) {
