@@ -570,6 +570,29 @@ def time_kernels(sess, reps=40):
     if STEREO:
         timed("hv_lk_kernel stereo", lambda i: ctx.lk_track_device(cur[0], cur[1], sess.d_next, sess.d_next2, sess.d_status, sess.d_ts, NFEAT, False), LK_BYTES)
 
+    # ---- rows beyond the step: reported with per_step = 0, i.e. outside `value` and the roofline shares
+    cx_, cy_ = cur[0].gftt_cells(32)
+    d_kp = torch.zeros((max(1, cx_ * cy_), 3), dtype=torch.float32, device=sess.dev)
+    timed("hv_gftt_kernel (N2 corner detection on level 0; runs when tracks are missing, tracker.cpp:686; not in the step)",
+          lambda i: cur[0].gftt_detect_device(d_kp.data_ptr()), W * H + 12 * cx_ * cy_, per_step=0)
+    try:
+        ing = capi.Ingest(ctx, W, H)
+        tab = np.zeros(W * H, np.dtype([("x0", np.int16), ("y0", np.int16), ("xfrac", np.float32), ("yfrac", np.float32)]))
+        yy, xx = np.mgrid[0:H, 0:W]
+        tab["x0"] = np.clip(xx.ravel(), 0, W - 2); tab["y0"] = np.clip(yy.ravel(), 0, H - 2); tab["xfrac"] = 0.25; tab["yfrac"] = 0.5
+        ing.set_remap(tab)
+        rgba = torch.from_numpy(np.repeat(sess.h_frames[0, 0].numpy()[:, :, None], 4, axis=2).copy()).pin_memory()
+        lib_ = capi.load()
+
+        def ingest(i):
+            capi.check(lib_.hv_ingest_frame(ing.h_, rgba.data_ptr(), 4 * W, 4, None, cur[0].h, None), "hv_ingest_frame")
+        timed("hv_ingest_frame (N4: RGBA frame H2D + hv_gray_kernel + hv_remap_kernel + pyramid in place; not in the step)", ingest,
+              4 * W * H + 5 * W * H + 14 * W * H + PYR_BYTES, per_step=0)
+        ctx.sync(); ing.close()
+        ctx.build_pyramids(cur[:NCAM], [sess.d_frames[1, c] for c in range(NCAM)], device=True)
+    except Exception as ex:      # noqa: BLE001 -- report-only row
+        out["hv_ingest_frame (N4)"] = {"error": repr(ex)[:200], "per_step": 0, "us_per_launch": 0.0, "algo_bytes": 0, "gbs": 0.0}
+
     def pred(i):
         ops = sess.ops_dev[i % POOL_EKF]
         for s_ in range(PREDICTS):
