@@ -92,9 +92,10 @@ struct EkfUpdateArgs {
     int* bump;
     double* slot;
     int lateH, padGate;
-    // Speculative update (ekf_cluster2.cuh, dense check+update only; NULL: off): the updated covariance blocks and state mean are written
-    // to specP / specM instead of P / m, which stay untouched -- the host adopts them by swapping pointers if the caller's
-    // updateVisualTrack(H, f, y, r) really follows the INLIER check with the same measurement (hv_ekf_visual_update).
+    // Results into the second buffers (ekf_cluster2.cuh; NULL: off): the updated covariance blocks and state mean are written to
+    // specP / specM instead of P / m, which stay untouched -- the host adopts them by swapping pointers. Used by the speculative
+    // update (dense check+update: adopted if the caller's updateVisualTrack(H, f, y, r) really follows the INLIER check with the same
+    // measurement, hv_ekf_visual_update) and by the augmentation that shares a launch with outlier checks reading (m, P).
     double* specP; double* specM;
     // EKF_MODE_CHECK_UPDATE with two noise levels (ekf_cluster2.cuh only; 0: off): the outlier check uses Rdiag, the update that
     // follows an INLIER decision uses Rdiag2 -- visualTrackOutlierCheck(trackChiTestOutlierR) then updateVisualTrack(visualR),
@@ -151,7 +152,8 @@ cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s);
 bool ekf_cluster2_fits(int n, int l, int N, bool joseph);
 bool ekf_update_uses_cluster2(const EkfUpdateArgs& a);    // the kernel ekf_launch_update will pick reports through a.sig
 cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s);
-cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s);
+// aug != NULL: one more cluster of the same launch runs the augmentation *aug (results into aug->specP / aug->specM)
+cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s, const EkfUpdateArgs* aug = nullptr);
 struct TmArgs;
 cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s);
 cudaError_t ekf_launch_elementwise(const EkfEwArgs& a, cudaStream_t s);

@@ -186,7 +186,7 @@ static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
     e->noiseScale = prm->noise_scale * prm->noise_scale;
     const size_t N = e->N, NN = N * N;
     const size_t workD = N * (2 * N + 4);
-    const size_t cworkD = (size_t)EKF_MAX_BATCH * 10 * NN;
+    const size_t cworkD = (size_t)(EKF_MAX_BATCH + 1) * 10 * NN;       // one exchange area per cluster of a check batch (+ its augmentation)
     e->inDoubles = (size_t)EKF_MAX_BATCH * (NN + 2 * N);
     const size_t total = N + NN + NN + workD + cworkD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + EKF_RES_STRIDE * (EKF_MAX_BATCH + 1) + e->inDoubles + N;
     cudaError_t err = cudaMalloc(&e->d_block, total * sizeof(double));
@@ -701,6 +701,24 @@ int hv_ekf_visual_device(hv_ekf* e, const double* dH, int n, int l, const double
     return visual_device(e, dH, n, l, df, dy, r, rmseThr, mode, dResult, 1);
 }
 
+// Argument block of the pose augmentation (ekf.cpp:848-885); symFirst: a deferred maintainPositiveSemiDefinite() rides along
+static void augment_args(hv_ekf* e, int discarded, bool symFirst, EkfUpdateArgs& a)
+{
+    fill_small(a, EKF_OP_AUGMENT, EKF_POSE, EKF_CAM + EKF_POSE, e->prm.augment_r * e->noiseScale);
+    a.b = e->b;
+    a.symFirst = symFirst ? 1 : 0;
+    a.dropIdx = discarded;
+    a.augNoisePos = pow2(e->prm.noise_initial_pos_trail) * e->noiseScale;
+    a.augNoiseOri = pow2(e->prm.noise_initial_ori_trail) * e->noiseScale;
+    a.normalizeAll = 1; a.symmetrize = 1;
+}
+static void augment_done(hv_ekf* e)
+{
+    e->augmentTimes.push_back(hv_ekf_platform_time(e));          // ekf.cpp:876-884
+    if (e->augmentCount < e->trail) e->augmentCount++;
+    else e->augmentTimes.erase(e->augmentTimes.begin());
+}
+
 int hv_ekf_augment(hv_ekf* e, int discarded)
 {
     EKF_ENTER_LAZY(e, "hv_ekf_augment");
@@ -708,8 +726,7 @@ int hv_ekf_augment(hv_ekf* e, int discarded)
     if (rcf != HV_OK) return rcf;
     if (discarded == -1) discarded = e->trail - 1;               // ekf.cpp:849
     if (discarded < 0 || discarded >= e->trail) { hv_set_error("hv_ekf_augment: pose index %d out of range", discarded); return HV_ERR_INVALID; }
-    EkfUpdateArgs a; fill_small(a, EKF_OP_AUGMENT, EKF_POSE, EKF_CAM + EKF_POSE, e->prm.augment_r * e->noiseScale);
-    a.b = e->b;
+    EkfUpdateArgs a; augment_args(e, discarded, false, a);
     if (ekf_update_uses_cluster2(a)) {                           // a deferred symmetrisation rides along (cluster kernel only)
         a.symFirst = e->pendSym ? 1 : 0;
         e->pendSym = false;
@@ -717,15 +734,9 @@ int hv_ekf_augment(hv_ekf* e, int discarded)
         int rcs = flush_sym(e);
         if (rcs != HV_OK) return rcs;
     }
-    a.dropIdx = discarded;
-    a.augNoisePos = pow2(e->prm.noise_initial_pos_trail) * e->noiseScale;
-    a.augNoiseOri = pow2(e->prm.noise_initial_ori_trail) * e->noiseScale;
-    a.normalizeAll = 1; a.symmetrize = 1;
     int rc = launch_update(e, a);   // shift into P2, update there, Joseph product back into P: no swap
     if (rc != HV_OK) return rc;
-    e->augmentTimes.push_back(hv_ekf_platform_time(e));          // ekf.cpp:876-884
-    if (e->augmentCount < e->trail) e->augmentCount++;
-    else e->augmentTimes.erase(e->augmentTimes.begin());
+    augment_done(e);
     return HV_OK;
 }
 
@@ -786,9 +797,33 @@ int hv_ekf_condition_on_last_pose(hv_ekf* e)
     return launch_ew(e, EKF_EW_CONDITION_LAST_POSE);
 }
 
+// An op list that continues "[SYMMETRIZE,] AUGMENT" behind a run of outlier checks (the end of a frame, backend.cpp): the augmentation does
+// not depend on the checks and the checks only read (m, P), so it is issued as one more cluster of the same launch, writing into the
+// second buffers (P2 / m2), which are swapped in afterwards. Returns the number of ops consumed behind the checks (0: no fusion).
+static int augment_follows(const hv_ekf* e, const hv_ekf_op* ops, int nops, int k, int* discarded, bool* symFirst)
+{
+    int used = 0;
+    *symFirst = false;
+    if (k < nops && ops[k].kind == HV_EKF_OP_SYMMETRIZE) { *symFirst = true; used = 1; }
+    if (k + used >= nops || ops[k + used].kind != HV_EKF_OP_AUGMENT) return 0;
+    int d = ops[k + used].index;
+    if (d == -1) d = e->trail - 1;
+    if (d < 0 || d >= e->trail) return 0;                        // the plain path reports the error
+    if (!ekf_cluster2_fits(EKF_POSE, EKF_CAM + EKF_POSE, e->N, true)) return 0;
+    *discarded = d;
+    return used + 1;
+}
+static void adopt_second_buffers(hv_ekf* e)
+{
+    swap_P(e);
+    double* t = e->b.m; e->b.m = e->m2; e->m2 = t;
+    e->epoch++;
+    e->spec.valid = false;
+}
+
 // A run of consecutive check-only VISUAL ops (mode 0) reads the same (m, P) and is therefore issued as ONE launch
 // (one cluster per measurement); with host buffers it is also one H2D copy, one D2H copy and one synchronisation.
-static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, bool host, int* vuStatus, double* chi2)
+static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, bool host, int* vuStatus, double* chi2, int augDiscarded = -1, bool augSym = false)
 {
     if (count == 0) return HV_OK;
     cudaStream_t s = e->ctx->stream;
@@ -822,7 +857,13 @@ static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, b
     a.b = e->b; a.noiseScale = e->noiseScale; a.useGlobalWork = 0;
     const bool polled = host && ekf_polling();           // every item fits the cluster kernel (batchable_check)
     if (polled) { a.sig = e->d_sig; a.sigSeq = (e->sigSeq += 1.0); }
-    HV_CUDA(ekf_launch_check_batch2(a, b, s));
+    if (augDiscarded >= 0) {
+        EkfUpdateArgs aug; augment_args(e, augDiscarded, augSym, aug);
+        aug.noiseScale = e->noiseScale; aug.specP = e->b.P2; aug.specM = e->m2;
+        HV_CUDA(ekf_launch_check_batch2(a, b, s, &aug));
+        adopt_second_buffers(e);
+        augment_done(e);
+    } else HV_CUDA(ekf_launch_check_batch2(a, b, s));
     e->ctx->launches++;
     if (polled) {
         int rc = poll_results(e, count, a.sigSeq, "hv_ekf_run");
@@ -861,9 +902,11 @@ static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vu
         if (batchable_check(e, o)) {
             int cnt = 1;
             while (i + cnt < nops && cnt < EKF_MAX_BATCH && batchable_check(e, ops[i + cnt])) cnt++;
-            rc = flush_checks(e, ops, i, cnt, host, vuStatus, chi2);
+            int disc = -1; bool sym = false;
+            const int extra = augment_follows(e, ops, nops, i + cnt, &disc, &sym);
+            rc = flush_checks(e, ops, i, cnt, host, vuStatus, chi2, extra ? disc : -1, sym);
             if (rc != HV_OK) return rc;
-            i += cnt - 1;
+            i += cnt - 1 + extra;
             continue;
         }
         switch (o.kind) {
@@ -962,15 +1005,23 @@ static int run_ops_host_async(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vu
             HV_CUDA(cudaStreamWaitEvent(s, e->copyEvents[group], 0));
             group++;
             a.sig = e->d_run + 4 * i; a.sigSeq = seq;
-            if (cnt > 1) {
+            int disc = -1; bool sym = false;
+            const int extra = o.mode == EKF_MODE_CHECK ? augment_follows(e, ops, nops, i + cnt, &disc, &sym) : 0;
+            if (cnt > 1 || extra) {
                 a.b = e->b; a.noiseScale = e->noiseScale; a.useGlobalWork = 0;
-                HV_CUDA(ekf_launch_check_batch2(a, b, s));
+                if (extra) {
+                    EkfUpdateArgs aug; augment_args(e, disc, sym, aug);
+                    aug.noiseScale = e->noiseScale; aug.specP = e->b.P2; aug.specM = e->m2;
+                    HV_CUDA(ekf_launch_check_batch2(a, b, s, &aug));
+                    adopt_second_buffers(e);
+                    augment_done(e);
+                } else HV_CUDA(ekf_launch_check_batch2(a, b, s));
                 e->ctx->launches++;
             } else {
                 rc = launch_update(e, a);
                 if (rc != HV_OK) return rc;
             }
-            i += cnt - 1;
+            i += cnt - 1 + extra;
             continue;
         }
         switch (o.kind) {

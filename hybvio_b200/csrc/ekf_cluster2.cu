@@ -18,21 +18,27 @@ __global__ void __launch_bounds__(EK2_NT) ekf_update_cluster2_kernel(EkfUpdateAr
 }
 
 // Batched outlier checks: cluster i works on measurement i against the same state (read-only), with its own result words.
-__global__ void __launch_bounds__(EK2_NT) ekf_check_batch_cluster2_kernel(EkfUpdateArgs a, EkfCheckBatch b)
+// b.withAugment: one more cluster runs the pose augmentation that FOLLOWS the checks in the caller's sequence (aug: its argument block).
+// The checks only read (m, P) and the augmentation writes its result to the second buffers (aug.specP / aug.specM, adopted by the
+// host with a pointer swap), so the two are independent and share the launch instead of queueing behind each other.
+__global__ void __launch_bounds__(EK2_NT) ekf_check_batch_cluster2_kernel(EkfUpdateArgs a, EkfCheckBatch b, EkfUpdateArgs aug)
 {
     extern __shared__ __align__(16) double ek2_sm[];
     cg::cluster_group cluster = cg::this_cluster();
     const int inst = blockIdx.x / (int)cluster.num_blocks();
-    const EkfCheckItem& it = b.it[inst];
-    a.H = it.H; a.f = it.f; a.y = it.y; a.n = it.n; a.l = it.l;
-    a.Rdiag = it.Rdiag; a.chi2Thr = it.chi2Thr; a.rmseThr = it.rmseThr; a.skipChi2 = it.skipChi2;
+    if (inst >= b.count) a = aug;                               // (one call of the body: its code is 340 KB)
+    else {
+        const EkfCheckItem& it = b.it[inst];
+        a.H = it.H; a.f = it.f; a.y = it.y; a.n = it.n; a.l = it.l;
+        a.Rdiag = it.Rdiag; a.chi2Thr = it.chi2Thr; a.rmseThr = it.rmseThr; a.skipChi2 = it.skipChi2;
+        if (a.sig) a.sig += 4 * inst;
+    }
     a.b.res += (size_t)EKF_RES_STRIDE * inst;
-    if (a.sig) a.sig += 4 * inst;
     a.b.cwork += (size_t)inst * 10 * a.b.N * a.b.N;           // own exchange area (Z | reduced S | partial S)
     ek2_body(a, ek2_sm, cluster);
 }
 
-#define EK2_STATIC_SMEM (sizeof(double) * (2 + 128 + 2 + EK2_MAXN) + 256)
+#define EK2_STATIC_SMEM (sizeof(double) * (2 + 2 * EK2_EB * EK2_EB + 2 + EK2_MAXN) + 256)
 #define EK2_SMEM_LIMIT (227 * 1024)
 
 // Cluster size 8 (the portable maximum). Measured on B200 (round 2, profiles/r02_ab_settled.md): a 16-CTA cluster (non-portable size)
@@ -78,12 +84,13 @@ cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s)
     return ek2_launch(ekf_update_cluster2_kernel, C, 1, smem, s, a);
 }
 
-cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s)
+cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s, const EkfUpdateArgs* aug)
 {
     const int C = ek2_cluster_size();
     static bool ready = false;
     if (!ready) { cudaError_t e = ek2_prepare(ekf_check_batch_cluster2_kernel, C); if (e != cudaSuccess) return e; ready = true; }
     size_t smem = 0;
     for (int i = 0; i < b.count; i++) { const size_t v = ek2_smem_bytes(b.it[i].n, b.it[i].l, a.b.N, false, C); if (v > smem) smem = v; }
-    return ek2_launch(ekf_check_batch_cluster2_kernel, C, b.count, smem, s, a, b);
+    if (aug) { const size_t v = ek2_smem_bytes(aug->n, aug->l, a.b.N, true, C); if (v > smem) smem = v; }
+    return ek2_launch(ekf_check_batch_cluster2_kernel, C, b.count + (aug ? 1 : 0), smem, s, a, b, aug ? *aug : a);
 }

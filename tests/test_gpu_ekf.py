@@ -186,6 +186,53 @@ def test_batch_submission_matches_single_calls(cuda, oracle_lk, trail):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("trail", [6, 20])
+def test_device_op_list_matches_oracle(cuda, oracle_lk, trail):
+    """hv_ekf_run_device (measurements resident in HBM, nothing returned to the host): the frame's list -- IMU burst, check+update,
+    a run of checks whose launch also carries the augmentation that follows them (results into the second buffers, swapped in) --
+    against the oracle issuing the same calls one by one."""
+    import torch
+    from hybvio_b200 import capi
+    from oracle import ekf_oracle
+    p = C.params_with(default_params, trail)
+    a, b = cuda(p), ekf_oracle.OracleEKF(p)
+    rng, irng = np.random.RandomState(5), np.random.RandomState(13)
+    acc0 = ekf_script.imu_sample(np.random.RandomState(1), 0)[1]
+    a.initialize_orientation(acc0); b.initialize_orientation(acc0)
+    t = 0.0
+    for frame in range(4):
+        keep = []
+        ops, nops, meas, t = _frame_ops(capi, rng, irng, a.N, t, (8, 20, 40, 84) if trail == 20 else (8, 20), keep)
+        dev = []
+        for i, mm in enumerate(meas):
+            if mm[0] != "visual":
+                continue
+            H, f, y = mm[1], mm[2], mm[3]
+            d = torch.from_numpy(np.concatenate([H.ravel(order="F"), f, y])).cuda()
+            dev.append(d)
+            n, l = H.shape
+            ops[i].H, ops[i].f, ops[i].y = d.data_ptr(), d.data_ptr() + 8 * n * l, d.data_ptr() + 8 * (n * l + n)
+        torch.cuda.synchronize()
+        a.run_device(ops, nops)
+        for mm in meas:
+            if mm[0] == "predict":
+                b.predict(mm[1], mm[2], mm[3])
+            elif mm[0] == "visual":
+                s_, _ = b.visual_check(mm[1], mm[2], mm[3], ekf_script.VISUAL_R)
+                if mm[4] == 2 and s_ == 0:
+                    b.visual_update(mm[1], mm[2], mm[3], ekf_script.VISUAL_R)
+            elif mm[0] == "sym":
+                b.symmetrize()
+            else:
+                b.augment(-1)
+        mb, Pb = b.download()
+        ma, Pa = a.download()
+        assert np.abs(ma - mb).max() < C.TOL_M and ekf_script.rel_err(Pa, Pb) < C.TOL_P_REL, f"frame {frame}"
+        assert abs(a.platform_time() - b.platform_time()) < 1e-12 and a.pose_count() == b.pose_count()
+        del dev
+    a.close(); b.close()
+
+
 def test_reference_catch2_suite_against_cuda_ekf():
     """The reference's OWN unit tests (test/ekf.cpp: chi-squared KAT, der_predict, tranformTo with test/data/P.csv,
     m.csv), compiled unmodified but linked against hybvio_b200/host/cuda_ekf.cpp instead of src/odometry/ekf.cpp
