@@ -778,6 +778,11 @@ def run_ours(args):
         clocks = sampler.stop() if sampler else None
         barrier()
         ms_dev = aggregate_ms(ms_local, sess.dev, world)
+        if args.step_only:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC(), "value": round(frames_per_second(world * nsess, args.steps, ms_dev), 2), "steps": args.steps,
+                                  "warmup": args.warmup, "gpu_launches": launches, "note": "--step-only: device-resident loop only, no e2e / kernel rows"}))
+            return
         e2e_steps = max(3, min(args.steps, args.e2e_steps))
         # e2e: native caller of the host-buffer C ABI (hybvio_b200/host/e2e_driver.cu); the Python-driven variant of the
         # same calls (step_e2e) is reported next to it as e2e.python_harness
@@ -1121,6 +1126,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config: 2 (default, the headline), 4 (512x512, 200 features, N=62), 1 (mono)")
+    ap.add_argument("--step-only", action="store_true", help="only the device-resident timed loop (for `ncu` launch lists of the step: profiles/README.md)")
     ap.add_argument("--selftest-dist", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

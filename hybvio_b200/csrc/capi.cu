@@ -287,8 +287,7 @@ static int lk_fill(LkLaunch& L, hv_ctx* c, int maxLevel, int maxIter, double eps
 {
     // criteria clamp of SparsePyrLKOpticalFlowImpl::calc (lkpyramid.cpp:1361-1369)
     L.table = c->d_table;
-    static const bool noPrefetch = getenv("HV_LK_NO_PREFETCH") != nullptr;      // A/B switch
-    L.prefetch = noPrefetch ? 0 : 1;
+    L.prefetch = 1;
     L.maxLevel = maxLevel;
     L.maxIter = maxIter < 0 ? 0 : (maxIter > 100 ? 100 : maxIter);
     double e = eps < 0. ? 0. : (eps > 10. ? 10. : eps);

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(EK2_NT) ekf_check_batch_cluster2_kernel(EkfUpd
     ek2_body(a, ek2_sm, cluster);
 }
 
-#define EK2_STATIC_SMEM (sizeof(double) * (2 + 2 * EK2_EB * EK2_EB + 2 + EK2_MAXN) + 256)
+#define EK2_STATIC_SMEM (sizeof(double) * (2 + EK2_LINV_DOUBLES + 2 + EK2_MAXN) + 256)
 #define EK2_SMEM_LIMIT (227 * 1024)
 
 // Cluster size 8 (the portable maximum). Measured on B200 (round 2, profiles/r02_ab_settled.md): a 16-CTA cluster (non-portable size)

@@ -64,7 +64,6 @@ __device__ __forceinline__ void pyr_mbar_init(unsigned long long* bar)
 __device__ __forceinline__ void pyr_tma_load_2d(void* dst, const HvTmap* map, int x, int y, unsigned long long* bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(pyr_smem_u32(bar)), "r"(bytes) : "memory");
-    // (destination state space .shared::cluster: the .shared::cta form assembles for sm_100a but traps as an illegal instruction on B200)
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  :: "r"(pyr_smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(pyr_smem_u32(bar)) : "memory");
 }
@@ -376,7 +375,10 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
             for (int k = 0; k < nl; k++) {
                 int rw = (HV_PYR_TILE >> k) + 2 * halo_of(k, top) + 4;
                 rw = (rw + 3) & ~3;
-                const int pitch = k == 0 ? (rw + 15) & ~15 : rw;       // level 0: the TMA box is as wide as the buffer (multiple of 16 bytes)
+                // level 0: the TMA box is as wide as the buffer (multiple of 16 bytes) and starts on a 16-byte boundary of the image row,
+                // up to 12 bytes left of the 4-byte-aligned origin the staging by loads uses: 16 spare columns (+16: the row pitch stays
+                // off a multiple of 128 bytes)
+                const int pitch = k == 0 ? ((rw + 15) & ~15) + 32 : rw;
                 g_off[k] = off; g_pitch[k] = pitch;
                 off += pitch * rw; off = (off + 127) & ~127;
             }
@@ -401,11 +403,15 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
         const bool aligned = ext == nullptr || ((((size_t)ext) | (size_t)list.srcPitch[blockIdx.z]) & 3) == 0;
         const uint8_t* base = ext ? ext : L0.gray;
         const int pitch = ext ? list.srcPitch[blockIdx.z] : L0.gpitch;
+        int xorg = x0a;                               // image column of buffer column 0
 #ifndef HV_EMU
         if (list.useTma[blockIdx.z]) {
             // ONE bulk tensor copy for the whole region: rows below / columns right of the image arrive as zeros (they are never read:
-            // the spans are closed under reflection inside the image), the box is as wide as the buffer pitch
-            if (threadIdx.x == 0) pyr_tma_load_2d(b0, &list.tmap[blockIdx.z], x0a, sy[0].s0, &s_bar, (unsigned)(bp * (HV_PYR_TILE + 2 * halo_of(0, top))));
+            // the spans are closed under reflection inside the image), the box is as wide as the buffer pitch. The box must start on a
+            // 16-BYTE boundary of the row: with u8 elements any other inner coordinate traps as an illegal instruction on B200
+            // (tools/tma_probe.cu, profiles/r02_tma_probe.md), so the region begins up to 12 columns further left.
+            xorg = x0a & ~15;
+            if (threadIdx.x == 0) pyr_tma_load_2d(b0, &list.tmap[blockIdx.z], xorg, sy[0].s0, &s_bar, (unsigned)(bp * (HV_PYR_TILE + 2 * halo_of(0, top))));
             pyr_mbar_wait(&s_bar, 0);
         } else
 #endif
@@ -436,8 +442,8 @@ __device__ __forceinline__ void pyr_body(const PyrBuildList& list, uint8_t* smem
                 for (int c = lane; c < nbytes; c += 32) b0[r * bp + c] = __ldg(src + c);
             }
         }
-        sx[0].s0 = x0a;   // stored origin is the aligned one (o0 is a multiple of the tile size, so this is ox[0] as well)
-        ox[0] = x0a;
+        sx[0].s0 = xorg;  // stored origin is the aligned one (o0 is a multiple of the tile size, so this is ox[0] as well)
+        ox[0] = xorg;
     }
 #ifndef HV_EMU
     if (!list.useTma[blockIdx.z])
@@ -483,7 +489,7 @@ size_t hv_pyr_smem_bytes(int nlevels)
     for (int k = 0; k < nlevels; k++) {
         int h = 1; for (int i = nlevels - 1; i > k; --i) h = 2 * h + 2;
         int rw = (HV_PYR_TILE >> k) + 2 * h + 4; rw = (rw + 3) & ~3;
-        const int pitch = k == 0 ? (rw + 15) & ~15 : rw;
+        const int pitch = k == 0 ? ((rw + 15) & ~15) + 32 : rw;
         off += (size_t)pitch * rw; off = (off + 127) & ~(size_t)127;
     }
     return off;
@@ -541,7 +547,7 @@ cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* id
             // TMA descriptor over the image the CTAs stage from: the external frame if there is one, else the level-0 buffer
             const int nl = nlevels[base + i];
             int halo = 1; for (int q = nl - 1; q > 0; --q) halo = 2 * halo + 2;
-            int rw = HV_PYR_TILE + 2 * halo + 4; rw = (rw + 3) & ~3; rw = (rw + 15) & ~15;
+            int rw = HV_PYR_TILE + 2 * halo + 4; rw = (rw + 3) & ~3; rw = ((rw + 15) & ~15) + 32;       // = pitch of the level-0 shared-memory buffer
             const uint8_t* img = list.src[i] ? list.src[i] : level0[base + i];
             const int pitch = list.src[i] ? list.srcPitch[i] : level0Pitch[base + i];
             list.useTma[i] = pyr_make_tmap(list.tmap[i], img, w0, h0, pitch, rw, HV_PYR_TILE + 2 * halo) ? 1 : 0;

@@ -32,7 +32,7 @@ static double rnd() { return rand() / (double)RAND_MAX - 0.5; }
 static double gauss() { double s = 0; for (int i = 0; i < 12; i++) s += rand() / (double)RAND_MAX; return s - 6.0; }
 
 // gate: 0 none; 1 device-side gates present and satisfied (+ lateH, slot, bump); 2 / 3 / 4: gated off by the int flag / the counter / the double flag
-struct Case { const char* name; int trail, C, op, n, l, mode; double yscale; int symFirst, drop; int gate = 0; double r2 = 0.0; };   // r2 > 0: the update uses its own noise level (two-R check+update)
+struct Case { const char* name; int trail, C, op, n, l, mode; double yscale; int symFirst, drop; int gate = 0; double r2 = 0.0; int second = 0; };   // second: results into specP / specM, P and m untouched   // r2 > 0: the update uses its own noise level (two-R check+update)
 
 int main(int argc, char** argv)
 {
@@ -60,6 +60,9 @@ int main(int argc, char** argv)
         {"two-R check+update n=84 l=160", 20, 8, EKF_OP_DENSE, 84, 160, EKF_MODE_CHECK_UPDATE, 0.02, 0, 0, 0, 0.01},
         {"two-R check+update n=8 (one-stage S), gated", 20, 8, EKF_OP_DENSE, 8, 34, EKF_MODE_CHECK_UPDATE, 0.02, 0, 0, 1, 0.2},
         {"two-R check+update n=13 N=62", 6, 8, EKF_OP_DENSE, 13, 41, EKF_MODE_CHECK_UPDATE, 0.02, 0, 0, 0, 0.004},
+        {"augment + deferred symmetrise into the second buffers", 20, 8, EKF_OP_AUGMENT, 7, 27, EKF_MODE_UPDATE, 0, 1, -1, 0, 0.0, 1},
+        {"augment drop 2 N=62 into the second buffers", 6, 8, EKF_OP_AUGMENT, 7, 27, EKF_MODE_UPDATE, 0, 0, 2, 0, 0.0, 1},
+        {"two-R check+update n=40 into the second buffers", 20, 8, EKF_OP_DENSE, 40, 90, EKF_MODE_CHECK_UPDATE, 0.02, 0, 0, 0, 0.004, 1},
     };
     const int only = argc > 1 ? atoi(argv[1]) : -1;
     int fails = 0, idx = -1;
@@ -134,7 +137,20 @@ int main(int argc, char** argv)
             orc_ekf_update_zupt(o, 1e-2);
         }
         const size_t smem = ek2_smem_bytes(cs.n, cs.l, N, cs.op == EKF_OP_AUGMENT, cs.C);
-        const int bad = EMU_LAUNCH_CLUSTER(arena, cs.C, EK2_NT, smem, emu_update_body, &a);
+        double* P2 = nullptr; double* m2 = nullptr;
+        std::vector<double> P0, m0;
+        if (cs.second) {
+            P2 = arena.alloc<double>((size_t)N * N); m2 = arena.alloc<double>(N);
+            for (size_t i = 0; i < (size_t)N * N; i++) P2[i] = -3.0;
+            for (int i = 0; i < N; i++) m2[i] = -3.0;
+            a.specP = P2; a.specM = m2;
+            P0.assign(P, P + (size_t)N * N); m0.assign(m, m + N);
+        }
+        int bad = EMU_LAUNCH_CLUSTER(arena, cs.C, EK2_NT, smem, emu_update_body, &a);
+        if (cs.second) {                                                   // the first buffers must be untouched; compare the second ones
+            if (memcmp(P0.data(), P, sizeof(double) * (size_t)N * N) != 0 || memcmp(m0.data(), m, sizeof(double) * N) != 0) bad |= 64;
+            P = P2; m = m2;
+        }
         std::vector<double> om(N), oP((size_t)N * N);
         orc_ekf_download(o, om.data(), oP.data());
         double em = 0, eP = 0, pmax = 0, asym = 0;

@@ -15,7 +15,7 @@ __device__ unsigned long long g_acc[8][16];       // [mark transition][warp]; ac
 __global__ void __launch_bounds__(512) k_elim(const double* Tin, double* Tout, int n, int ncols, int W, long long* total)
 {
     extern __shared__ double T[];
-    __shared__ double s_linv[2 * EK2_EB * EK2_EB];
+    __shared__ double s_linv[EK2_LINV_DOUBLES];
     __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     for (int i = tid; i < n * W; i += 512) T[i] = Tin[i];
@@ -62,7 +62,7 @@ int main()
             for (int i = 0; i < n; i++) worst = fmax(worst, fabs(z[i] - R[(size_t)i * W + c]));
         }
         printf("max |L^-1 Y - host| = %.3e  ", worst);
-        const int MT = (n + EK2_EB - 1) / EK2_EB;
+        const int MT = (n + EK2_EB - 1) / EK2_EB;      // blocks
         printf("n=%2d (%2d blocks): total %6lld cyc = %5.2f us @1.965GHz (%s, ok=%lld) | per block step, warp 0: rows-solve %llu | wait barrier %llu | look-ahead tile %llu | diag factor %llu | wait barrier %llu | loop top %llu"
                "  || warp 5 (worker): rows-solve %llu | barrier %llu | trailing tiles %llu | idle until barrier %llu\n",
                n, MT, h[0], h[0] / 1965.0, cudaGetErrorString(e), h[1],
