@@ -226,8 +226,9 @@ class Session:
         if not self.overlap:
             A.wait_stream(B); B.wait_stream(A)
         self.ekf.run_device(ops, IMU_OPS)                                                          # B: IMU burst (queued) ...
-        self.ekf.flush()                                                                           # ... issued now: overlaps the tracker
-        A.wait_event(self.ev_ekf)                                                                  # flow predictor needs EKF(k-1)
+        self.ekf.flush()                                                                           # ... issued now
+        self.ev_ekf.record(B)
+        A.wait_event(self.ev_ekf)                                                                  # the flow predictor reads the state propagated to this frame
         init = self.d_init[0, j - 1] if j > self.prev_j else self.d_init[1, j]
         with self.torch.cuda.stream(A):
             self.d_next.copy_(init)                               # predicted flow (host callback in the reference)
@@ -237,7 +238,6 @@ class Session:
         self.ev_lk.record(A)
         B.wait_event(self.ev_lk)                                                                   # visual updates need the tracks
         self.ekf.run_device(ctypes_slice(ops, IMU_OPS, self.nops - IMU_OPS), self.nops - IMU_OPS)
-        self.ev_ekf.record(B)
         self.pyr = self.pyr[2:4] + self.pyr[0:2]
         self.prev_j = j
 
@@ -754,6 +754,7 @@ def run_ours(args):
         s.record(sess.stream)
         for _ in range(steps):
             step()
+        sess.ctx_b.sync()                          # EKF stream and the library's side stream (outlier checks of the last frames)
         sess.stream.wait_stream(sess.stream_b)
         e.record(sess.stream)
         e.synchronize()
@@ -854,7 +855,7 @@ def run_ours(args):
                                    f"20 checks (5 with update, n = {'/'.join(map(str, N_ROWS))} rows) + symmetrise + augment; independent sessions, " + str(nsess) + " per GPU",
                        "baseline_config": CONFIG_ID, "host_numa_node_pinned": numa_node,
                        "sessions_per_gpu": nsess,
-                       "streams": "2 per session (tracker / EKF) with event dependencies: LK(k) after EKF(k-1), visual updates(k) after LK(k)",
+                       "streams": "2 per session (tracker / EKF) with event dependencies: LK(k) after the IMU burst of frame k (the flow predictor reads the propagated state), visual updates(k) after LK(k); outlier checks that precede the augmentation on the library side stream",
                        "l2": f"inputs cycled through pools larger than L2 (frames {POOL_FRAMES * 2 * W * H / 1e6:.0f} MB + EKF inputs "
                              f"{POOL_EKF * inputs.ekf_stride * 8 / 1e6:.0f} MB > 126 MB); no explicit flush",
                        "ekf_healthy_after_run": healthy},

@@ -170,6 +170,7 @@ def _bind_ekf(lib):
     lib.hv_ekf_augment.argtypes = [c_void_p, c_int]
     lib.hv_ekf_set_imu_batching.argtypes = [c_void_p, c_int]
     lib.hv_ekf_run_device.argtypes = [c_void_p, ctypes.POINTER(EkfOp), c_int]
+    lib.hv_ekf_run_device_results.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double)]
     lib.hv_ekf_run_host.argtypes = [c_void_p, ctypes.POINTER(EkfOp), c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double), c_void_p]
     lib.hv_ekf_normalize_quaternions.argtypes = [c_void_p, c_int]
     lib.hv_ekf_translate_to.argtypes = [c_void_p, c_void_p]
@@ -446,6 +447,13 @@ class Ekf:
     def run_device(self, ops, nops):
         """ops: (EkfOp * k) array with DEVICE pointers; asynchronous."""
         check(self.lib.hv_ekf_run_device(self.h, ops, nops), "hv_ekf_run_device")
+
+    def run_device_results(self, nops):
+        """(vu_status, chi2) arrays of the last run_device list (entries of non-VISUAL ops: -1 / nan); waits for the list."""
+        st = np.full(nops, -1, dtype=np.int32); chi2 = np.full(nops, np.nan)
+        check(self.lib.hv_ekf_run_device_results(self.h, nops, st.ctypes.data_as(ctypes.POINTER(c_int)), chi2.ctypes.data_as(ctypes.POINTER(c_double))),
+              "hv_ekf_run_device_results")
+        return st, chi2
 
     def run_host(self, ops, nops, want_m=False):
         """ops with HOST pointers; returns (vu_status int32[nops], chi2 float64[nops], m or None)."""

@@ -67,6 +67,7 @@ int hv_ctx_destroy(hv_ctx* c)
     if (!c) return HV_OK;
     cudaSetDevice(c->device);
     if (c->stream || !c->ownStream) cudaStreamSynchronize(c->stream);
+    if (c->sideStream) { cudaStreamSynchronize(c->sideStream); cudaStreamDestroy(c->sideStream); }
     if (c->d_table) cudaFree(c->d_table);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -82,6 +83,7 @@ int hv_ctx_sync(hv_ctx* c)
 {
     if (!c) { hv_set_error("hv_ctx_sync: NULL ctx"); return HV_ERR_INVALID; }
     HV_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->sideStream) HV_CUDA(cudaStreamSynchronize(c->sideStream));
     return HV_OK;
 }
 void* hv_ctx_stream(hv_ctx* c) { return c ? (void*)c->stream : nullptr; }

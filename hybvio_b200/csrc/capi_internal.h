@@ -31,6 +31,9 @@ struct hv_ctx {
     unsigned doneCount = 0, seq = 0;   // host mirror of the counter / sequence number of the last polled launch
     // EKF staging
     void* h_ekfStage = nullptr; void* d_ekfStage = nullptr; size_t ekfStageBytes = 0;
+    // Side stream for work that the main stream need not wait for (created on first use; ekf_capi.cu: outlier checks of a device-resident
+    // op list). hv_ctx_sync waits for both.
+    cudaStream_t sideStream = nullptr;
 };
 
 struct hv_pyr {

@@ -36,6 +36,15 @@ struct hv_ekf {
     cudaStream_t copyStream = nullptr;            // hv_ekf_run_host: the measurement inputs travel on their own stream, ahead of the kernels
     std::vector<cudaEvent_t> copyEvents;          // one per measurement group of a list (created on demand)
     double sigSeq = 0.0;
+    // hv_ekf_run_device: a run of outlier checks that is followed by the pose augmentation goes to a SIDE stream (the checks only read
+    // the state, the augmentation writes the second buffers, so nothing that follows on the main stream has to wait for them);
+    // they are joined before the next writer of the second buffers and before anything that hands results to the host
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;       // (the stream itself belongs to the context: hv_ctx::sideStream)
+    bool sideBusy = false;
+    double* cworkSide = nullptr;            // exchange areas and result words of the clusters on the side stream
+    double* resSide = nullptr;
+    double* d_opres = nullptr;              // hv_ekf_run_device: result words per op of the list (4 doubles each, HV_RUN_MAX_OPS)
+    std::vector<unsigned char> lastVisual;  // per op of the last hv_ekf_run_device list: 1 = VISUAL (has result words)
     // host bookkeeping, exactly the members of EKFImplementation (ekf.cpp:145-151)
     int augmentCount = 0;
     std::vector<double> augmentTimes;
@@ -119,6 +128,7 @@ static int ekf_check(const hv_ekf* e, const char* who)
 }
 
 extern "C" { static int flush_pending(hv_ekf* e); }
+static int join_side(hv_ekf* e);
 // EKF_ENTER_LAZY: entry points that only extend the deferred queue; EKF_ENTER: everything else issues the queue first
 #define EKF_ENTER_LAZY(e, who)                         \
     do { int rc_ = ekf_check(e, who); if (rc_ != HV_OK) return rc_; HV_CUDA(cudaSetDevice((e)->ctx->device)); } while (0)
@@ -150,6 +160,7 @@ static void fill_small(EkfUpdateArgs& a, int op, int n, int l, double Rdiag, int
 static int launch_ew(hv_ekf* e, int op, int ival0 = 0, const double* dv = nullptr, int ndv = 0)
 {
     EkfEwArgs a; memset(&a, 0, sizeof(a));
+    if (op == EKF_EW_UNAUGMENT || op == EKF_EW_TRANSFORM) { int rcj = join_side(e); if (rcj != HV_OK) return rcj; }   // out of place into P2
     e->epoch++;
     a.b = e->b; a.op = op; a.ival0 = ival0;
     for (int i = 0; i < ndv; i++) a.dval[i] = dv[i];
@@ -159,6 +170,14 @@ static int launch_ew(hv_ekf* e, int op, int ival0 = 0, const double* dv = nullpt
 }
 
 static void swap_P(hv_ekf* e) { double* t = e->b.P; e->b.P = e->b.P2; e->b.P2 = t; }
+// Outlier checks still running on the side stream read what are now the SECOND buffers: every writer of P2 / m2 waits for them first
+static int join_side(hv_ekf* e)
+{
+    if (!e->sideBusy) return HV_OK;
+    HV_CUDA(cudaStreamWaitEvent(e->ctx->stream, e->evJoin, 0));
+    e->sideBusy = false;
+    return HV_OK;
+}
 
 extern "C" {
 
@@ -188,7 +207,8 @@ static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
     const size_t workD = N * (2 * N + 4);
     const size_t cworkD = (size_t)(EKF_MAX_BATCH + 1) * 10 * NN;       // one exchange area per cluster of a check batch (+ its augmentation)
     e->inDoubles = (size_t)EKF_MAX_BATCH * (NN + 2 * N);
-    const size_t total = N + NN + NN + workD + cworkD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + EKF_RES_STRIDE * (EKF_MAX_BATCH + 1) + e->inDoubles + N;
+    const size_t resD = (size_t)EKF_RES_STRIDE * (EKF_MAX_BATCH + 1);
+    const size_t total = N + NN + NN + workD + 2 * cworkD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + 2 * resD + e->inDoubles + N + 4 * HV_RUN_MAX_OPS;
     cudaError_t err = cudaMalloc(&e->d_block, total * sizeof(double));
     if (err != cudaSuccess) { delete e; hv_set_error("hv_ekf_create: cudaMalloc failed: %s", cudaGetErrorString(err)); return HV_ERR_OOM; }
     cudaMemsetAsync(e->d_block, 0, total * sizeof(double), c->stream);
@@ -196,7 +216,8 @@ static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
     e->b.m = p; p += N; e->b.P = p; p += NN; e->b.P2 = p; p += NN; e->b.work = p; p += workD; e->b.cwork = p; p += cworkD;
     e->b.Hs = p; p += EKF_SMALL_MAXN * EKF_SMALL_MAXL; e->b.Q = p; p += 144; e->b.dydx = p; p += 400; e->b.res = p; p += EKF_RES_STRIDE * (EKF_MAX_BATCH + 1);
     e->d_in = p; p += e->inDoubles;
-    e->m2 = p;
+    e->m2 = p; p += N;
+    e->cworkSide = p; p += cworkD; e->resSide = p; p += resD; e->d_opres = p;
     e->b.N = e->N; e->b.trail = e->trail; e->b.mapDim = e->mapDim;
     err = cudaMallocHost(&e->h_pin, (e->inDoubles + N + 8 + EKF_RES_STRIDE * EKF_MAX_BATCH) * sizeof(double));
     if (err != cudaSuccess) { cudaFree(e->d_block); delete e; hv_set_error("hv_ekf_create: cudaMallocHost failed"); return HV_ERR_OOM; }
@@ -263,6 +284,9 @@ int hv_ekf_destroy(hv_ekf* e)
     cudaFreeHost(e->h_run);
     for (cudaEvent_t ev : e->copyEvents) cudaEventDestroy(ev);
     if (e->copyStream) cudaStreamDestroy(e->copyStream);
+    if (e->ctx->sideStream) cudaStreamSynchronize(e->ctx->sideStream);
+    if (e->evFork) cudaEventDestroy(e->evFork);
+    if (e->evJoin) cudaEventDestroy(e->evJoin);
     if (e->evStaged) cudaEventDestroy(e->evStaged);
     if (e->tm) { e->tm->release(); delete e->tm; }
     delete e;
@@ -629,6 +653,8 @@ static int visual_host(hv_ekf* e, const char* who, const double* H, int n, int l
     // previous updateVisualTrack) into P2 / m2, while the host already has the decision; P and m stay as they are.
     const bool speculate = polled && mode == EKF_MODE_CHECK && e->specEnabled && e->specR > 0.0 && !a.skipChi2 && a.rmseThr < 0.0 && r > 0.0;
     if (speculate) {
+        int rcj = join_side(e);
+        if (rcj != HV_OK) return rcj;
         a.mode = EKF_MODE_CHECK_UPDATE; a.Rdiag2 = (e->specR * e->specR) * e->noiseScale;
         a.specP = e->b.P2; a.specM = e->m2;
     }
@@ -678,7 +704,7 @@ int hv_ekf_visual_check_update(hv_ekf* e, const double* H, int n, int l, const d
 }
 
 static int visual_device(hv_ekf* e, const double* dH, int n, int l, const double* df, const double* dy, double r, double rmseThr,
-                         int mode, double* dResult, int lateH)
+                         int mode, double* dResult, int lateH, double* slot = nullptr)
 {
     if (!dH || !df || !dy || mode < 0 || mode > 2) { hv_set_error("hv_ekf_visual_device: invalid argument"); return HV_ERR_INVALID; }
     EkfUpdateArgs a;
@@ -688,9 +714,13 @@ static int visual_device(hv_ekf* e, const double* dH, int n, int l, const double
     // caller-owned device pointers: H may have been produced by the caller's previous kernel on this stream (hv_ctx_create_on_stream),
     // so it is staged AFTER griddepcontrol.wait; early staging is kept for H that arrived through the library's own H2D copy
     a.lateH = lateH;
+    prep_update(e, a);
+    const bool ownSlot = slot && ekf_update_uses_cluster2(a);      // the cluster kernel writes its result words into the slot itself
+    if (ownSlot) a.slot = slot;
     rc = launch_update(e, a);
     if (rc != HV_OK) return rc;
     if (dResult) HV_CUDA(cudaMemcpyAsync(dResult, e->b.res, 2 * sizeof(double), cudaMemcpyDeviceToDevice, e->ctx->stream));
+    if (slot && !ownSlot) HV_CUDA(cudaMemcpyAsync(slot, e->b.res, 3 * sizeof(double), cudaMemcpyDeviceToDevice, e->ctx->stream));
     return HV_OK;
 }
 
@@ -727,6 +757,7 @@ int hv_ekf_augment(hv_ekf* e, int discarded)
     if (discarded == -1) discarded = e->trail - 1;               // ekf.cpp:849
     if (discarded < 0 || discarded >= e->trail) { hv_set_error("hv_ekf_augment: pose index %d out of range", discarded); return HV_ERR_INVALID; }
     EkfUpdateArgs a; augment_args(e, discarded, false, a);
+    if (!ekf_update_uses_cluster2(a)) { int rcj = join_side(e); if (rcj != HV_OK) return rcj; }      // the single-CTA kernel shifts into P2
     if (ekf_update_uses_cluster2(a)) {                           // a deferred symmetrisation rides along (cluster kernel only)
         a.symFirst = e->pendSym ? 1 : 0;
         e->pendSym = false;
@@ -857,10 +888,34 @@ static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, b
     a.b = e->b; a.noiseScale = e->noiseScale; a.useGlobalWork = 0;
     const bool polled = host && ekf_polling();           // every item fits the cluster kernel (batchable_check)
     if (polled) { a.sig = e->d_sig; a.sigSeq = (e->sigSeq += 1.0); }
+    if (!host && first + count <= HV_RUN_MAX_OPS) a.slot = e->d_opres + 4 * first;      // hv_ekf_run_device_results
     if (augDiscarded >= 0) {
+        int rcj = join_side(e);                            // (checks of the previous list read the buffers this augmentation writes)
+        if (rcj != HV_OK) return rcj;
         EkfUpdateArgs aug; augment_args(e, augDiscarded, augSym, aug);
         aug.noiseScale = e->noiseScale; aug.specP = e->b.P2; aug.specM = e->m2;
-        HV_CUDA(ekf_launch_check_batch2(a, b, s, &aug));
+        if (host) {
+            // results are wanted now: the augmentation is one more cluster of the checks' launch
+            HV_CUDA(ekf_launch_check_batch2(a, b, s, &aug));
+        } else {
+            // nothing goes back to the host: the checks leave the main stream altogether (fork -> side stream), the augmentation and
+            // whatever follows it (the next frame's IMU burst, its visual updates) run beside them
+            if (!e->ctx->sideStream) HV_CUDA(cudaStreamCreateWithFlags(&e->ctx->sideStream, cudaStreamNonBlocking));
+            if (!e->evFork) {
+                HV_CUDA(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
+                HV_CUDA(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
+            }
+            cudaStream_t side = e->ctx->sideStream;
+            HV_CUDA(cudaEventRecord(e->evFork, s));
+            HV_CUDA(cudaStreamWaitEvent(side, e->evFork, 0));
+            a.b.cwork = e->cworkSide; a.b.res = e->resSide;
+            HV_CUDA(ekf_launch_check_batch2(a, b, side));
+            HV_CUDA(cudaEventRecord(e->evJoin, side));
+            e->sideBusy = true;
+            e->ctx->launches++;
+            aug.useGlobalWork = 0;
+            HV_CUDA(ekf_launch_update(aug, s));
+        }
         adopt_second_buffers(e);
         augment_done(e);
     } else HV_CUDA(ekf_launch_check_batch2(a, b, s));
@@ -895,6 +950,10 @@ static bool batchable_check(const hv_ekf* e, const hv_ekf_op& o)
 static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vuStatus, double* chi2, double* mOut)
 {
     if (!ops || nops < 0) { hv_set_error("hv_ekf_run: invalid argument"); return HV_ERR_INVALID; }
+    if (!host) {                                                  // which slots of d_opres this list fills (hv_ekf_run_device_results)
+        e->lastVisual.assign(nops, 0);
+        for (int i = 0; i < nops && i < HV_RUN_MAX_OPS; i++) if (ops[i].kind == HV_EKF_OP_VISUAL) e->lastVisual[i] = 1;
+    }
     for (int i = 0; i < nops; i++) {
         const hv_ekf_op& o = ops[i];
         int rc = HV_OK;
@@ -915,7 +974,8 @@ static int run_ops(hv_ekf* e, const hv_ekf_op* ops, int nops, bool host, int* vu
                 if (o.mode < 0 || o.mode > 2) { hv_set_error("hv_ekf_run: op %d: bad mode", i); return HV_ERR_INVALID; }
                 if (host) rc = visual_host(e, "hv_ekf_run_host", o.H, o.n, o.l, o.f, o.y, o.r, o.rmse_thr, o.mode,
                                            vuStatus ? vuStatus + i : nullptr, chi2 ? chi2 + i : nullptr, nullptr);
-                else rc = visual_device(e, o.H, o.n, o.l, o.f, o.y, o.r, o.rmse_thr, o.mode, nullptr, 0);    // prepared inputs (see the header): staged early
+                else rc = visual_device(e, o.H, o.n, o.l, o.f, o.y, o.r, o.rmse_thr, o.mode, nullptr, 0,       // prepared inputs (see the header): staged early
+                                        i < HV_RUN_MAX_OPS ? e->d_opres + 4 * i : nullptr);
                 break;
             case HV_EKF_OP_SYMMETRIZE: rc = hv_ekf_symmetrize(e); break;
             case HV_EKF_OP_AUGMENT: rc = hv_ekf_augment(e, o.index); break;
@@ -1010,6 +1070,8 @@ static int run_ops_host_async(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vu
             if (cnt > 1 || extra) {
                 a.b = e->b; a.noiseScale = e->noiseScale; a.useGlobalWork = 0;
                 if (extra) {
+                    rc = join_side(e);
+                    if (rc != HV_OK) return rc;
                     EkfUpdateArgs aug; augment_args(e, disc, sym, aug);
                     aug.noiseScale = e->noiseScale; aug.specP = e->b.P2; aug.specM = e->m2;
                     HV_CUDA(ekf_launch_check_batch2(a, b, s, &aug));
@@ -1057,6 +1119,26 @@ int hv_ekf_run_device(hv_ekf* e, const hv_ekf_op* ops, int nops)
 {
     EKF_ENTER(e, "hv_ekf_run_device");
     return run_ops(e, ops, nops, false, nullptr, nullptr, nullptr);
+}
+
+int hv_ekf_run_device_results(hv_ekf* e, int nops, int* vuStatus, double* chi2)
+{
+    EKF_ENTER(e, "hv_ekf_run_device_results");
+    if (nops < 0 || nops > (int)e->lastVisual.size() || nops > HV_RUN_MAX_OPS) { hv_set_error("hv_ekf_run_device_results: the last list had %d ops (at most %d report)", (int)e->lastVisual.size(), HV_RUN_MAX_OPS); return HV_ERR_INVALID; }
+    int rc = join_side(e);
+    if (rc != HV_OK) return rc;
+    int rca = staging_acquire(e);
+    if (rca != HV_OK) return rca;
+    double* hout = e->h_pin;                                      // (inDoubles >= 4 HV_RUN_MAX_OPS for every state size)
+    HV_CUDA(cudaMemcpyAsync(hout, e->d_opres, sizeof(double) * 4 * nops, cudaMemcpyDeviceToHost, e->ctx->stream));
+    HV_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    for (int i = 0; i < nops; i++) {
+        if (!e->lastVisual[i]) continue;
+        if (vuStatus) vuStatus[i] = (int)hout[4 * i];
+        if (chi2) chi2[i] = hout[4 * i + 1];
+        if (hout[4 * i + 2] != 0.0) { hv_set_error("hv_ekf_run_device_results: op %d: innovation covariance not positive definite", i); return HV_ERR_STATE; }
+    }
+    return HV_OK;
 }
 
 int hv_ekf_run_host(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vuStatus, double* chi2, double* mOut)

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(EK2_NT) ekf_check_batch_cluster2_kernel(EkfUpd
         a.H = it.H; a.f = it.f; a.y = it.y; a.n = it.n; a.l = it.l;
         a.Rdiag = it.Rdiag; a.chi2Thr = it.chi2Thr; a.rmseThr = it.rmseThr; a.skipChi2 = it.skipChi2;
         if (a.sig) a.sig += 4 * inst;
+        if (a.slot) a.slot += 4 * inst;
     }
     a.b.res += (size_t)EKF_RES_STRIDE * inst;
     a.b.cwork += (size_t)inst * 10 * a.b.N * a.b.N;           // own exchange area (Z | reduced S | partial S)

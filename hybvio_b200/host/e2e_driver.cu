@@ -89,9 +89,9 @@ static int e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, cons
 }
 
 // ---- device-resident loop (bench.py's `value`): the same frame as above with every input already in HBM and no host
-// synchronisation; tracker and EKF on their own streams with the real dependencies as events (LK(k) after EKF(k-1): the
-// flow predictor reads the EKF poses, src/tracker/tracker.cpp:59-63; visual updates(k) after LK(k)). A native caller keeps
-// the launch rate independent of the Python interpreter of the harness.
+// synchronisation; tracker and EKF on their own streams with the real dependencies as events (LK(k) after the IMU burst of frame k:
+// the flow predictor reads the propagated pose and the pose trail, src/odometry/backend.cpp:547-600 via src/tracker/tracker.cpp:59-63;
+// visual updates(k) after LK(k)). A native caller keeps the launch rate independent of the Python interpreter of the harness.
 typedef struct hv_dev_frame {
     const uint8_t* left; const uint8_t* right;   // device gray images
     size_t stride;
@@ -110,8 +110,7 @@ int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
     cudaEventCreateWithFlags(&evLk, cudaEventDisableTiming); cudaEventCreateWithFlags(&evEkf, cudaEventDisableTiming);
     hv_ctx_sync(trk); hv_ctx_sync(ekf_ctx);
     cudaEventRecord(e0, sa);
-    cudaEventRecord(evEkf, sb);
-    int rc = HV_OK;
+    int rc = HV_OK, lastOps = 0;
     for (int k = 0; k < nframes && rc == HV_OK; k++) {
         const hv_dev_frame& f = frames[k];
         hv_pyr* cur[2] = {p[2], p[3]};
@@ -120,9 +119,10 @@ int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
         rc = hv_pyr_build_batch(cur, img, strides, f.right ? 2 : 1, 1);          // A: no dependency
         if (rc != HV_OK) break;
         rc = hv_ekf_run_device(ekf, f.ops, f.nimu);                            // B: IMU burst (queued) ...
-        if (rc == HV_OK) rc = hv_ekf_flush(ekf);                               // ... issued now: overlaps the tracker
+        if (rc == HV_OK) rc = hv_ekf_flush(ekf);                               // ... issued now
         if (rc != HV_OK) break;
-        cudaStreamWaitEvent(sa, evEkf, 0);                                     // flow predictor needs EKF(k-1)
+        cudaEventRecord(evEkf, sb);
+        cudaStreamWaitEvent(sa, evEkf, 0);                                     // the flow predictor reads the state propagated to this frame
         cudaMemcpyAsync(d_next, f.d_init_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToDevice, sa);
         rc = hv_lk_track_device(trk, p[0], cur[0], d_points, d_next, d_status, d_ts, n, 1, 20, 0.03, 1e-3);
         if (rc == HV_OK && f.right) rc = hv_lk_track_device(trk, cur[0], cur[1], d_next, d_next2, d_status, d_ts, n, 0, 20, 0.03, 1e-3);
@@ -131,9 +131,12 @@ int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
         cudaStreamWaitEvent(sb, evLk, 0);                                      // visual updates need the tracks
         rc = hv_ekf_run_device(ekf, f.ops + f.nimu, f.nops - f.nimu);
         if (rc == HV_OK) rc = hv_ekf_flush(ekf);
-        cudaEventRecord(evEkf, sb);
+        lastOps = f.nops - f.nimu;
         hv_pyr* q0 = p[0]; hv_pyr* q1 = p[1]; p[0] = p[2]; p[1] = p[3]; p[2] = q0; p[3] = q1;
     }
+    // the last frame's decisions come back to the host (this also waits for the outlier checks the library issued on its side stream)
+    if (rc == HV_OK && lastOps > 0) { std::vector<int> vu(lastOps); std::vector<double> chi2(lastOps); rc = hv_ekf_run_device_results(ekf, lastOps, vu.data(), chi2.data()); }
+    cudaEventRecord(evEkf, sb);
     cudaStreamWaitEvent(sa, evEkf, 0);
     cudaEventRecord(e1, sa);
     cudaEventSynchronize(e1);

@@ -48,6 +48,7 @@ int hv_ctx_create(int device, hv_ctx** out);
 /* Same, but issues all work on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream). */
 int hv_ctx_create_on_stream(int device, void* cuda_stream, hv_ctx** out);
 int hv_ctx_destroy(hv_ctx* ctx);
+/* Waits for everything issued through the context: its stream and the library's side stream (hv_ekf_run_device_results). */
 int hv_ctx_sync(hv_ctx* ctx);
 /* The stream as a cudaStream_t (for event timing by the caller). */
 void* hv_ctx_stream(hv_ctx* ctx);
@@ -245,8 +246,15 @@ typedef struct hv_ekf_op {
  * cluster per measurement. The measurement inputs of a list are PREPARED inputs: the kernels read them while their predecessor on the
  * stream may still be running (programmatic dependent launch), so they must not be produced by work queued on this stream after that
  * predecessor. For H produced by the caller's own kernel right before the call use hv_ekf_visual_device, which reads its inputs only
- * after the dependency on all earlier work of the stream has been resolved. */
+ * after the dependency on all earlier work of the stream has been resolved. The inputs must stay valid until hv_ctx_sync or
+ * hv_ekf_run_device_results has returned (synchronising the context's STREAM alone is not enough, see below). */
 int hv_ekf_run_device(hv_ekf* ekf, const hv_ekf_op* ops, int nops);
+/* What the VISUAL ops of the most recent hv_ekf_run_device list decided: VuOutlierStatus / chi2 into vu_status[i] / chi2[i] for the ops
+ * [0, nops) of that list (entries of other ops untouched; lists of up to 256 ops report). The list itself returns nothing and does not
+ * wait: a run of outlier checks that is followed by the pose augmentation (the end of a frame, backend.cpp:1012-1270) is issued on a side
+ * stream of the library -- the checks only read the state and the augmentation writes second buffers that are swapped in -- so that
+ * the augmentation, the next IMU burst and the next visual updates do not queue behind them. This call waits for all of it. */
+int hv_ekf_run_device_results(hv_ekf* ekf, int nops, int* vu_status, double* chi2);
 /* H/f/y are HOST pointers; every VISUAL op with mode 0 or 2 returns its VuOutlierStatus / chi2 into
  * vu_status[i] / chi2[i] (arrays of length nops, entries of other ops untouched) -- i.e. each such op is a host
  * round trip, as in the reference interface. m_out (optional, N doubles) receives the final state mean. */

@@ -214,21 +214,31 @@ def test_device_op_list_matches_oracle(cuda, oracle_lk, trail):
             ops[i].H, ops[i].f, ops[i].y = d.data_ptr(), d.data_ptr() + 8 * n * l, d.data_ptr() + 8 * (n * l + n)
         torch.cuda.synchronize()
         a.run_device(ops, nops)
-        for mm in meas:
+        exp = []
+        for i, mm in enumerate(meas):
             if mm[0] == "predict":
                 b.predict(mm[1], mm[2], mm[3])
             elif mm[0] == "visual":
-                s_, _ = b.visual_check(mm[1], mm[2], mm[3], ekf_script.VISUAL_R)
+                s_, c_ = b.visual_check(mm[1], mm[2], mm[3], ekf_script.VISUAL_R)
+                exp.append((i, s_, c_))
                 if mm[4] == 2 and s_ == 0:
                     b.visual_update(mm[1], mm[2], mm[3], ekf_script.VISUAL_R)
             elif mm[0] == "sym":
                 b.symmetrize()
             else:
                 b.augment(-1)
+        if frame % 2 == 0:                  # every other frame: fetch what the list decided (waits for the side stream)
+            st, chi2 = a.run_device_results(nops)
+            for i, s_, c_ in exp:
+                assert st[i] == s_, f"frame {frame} op {i}: status {st[i]} != {s_}"
+                assert abs(chi2[i] - c_) <= 1e-8 * max(1.0, abs(c_)), f"frame {frame} op {i}: chi2 {chi2[i]} != {c_}"
+            assert all(st[i] == -1 for i in range(nops) if i not in {j for j, _, _ in exp})
         mb, Pb = b.download()
         ma, Pa = a.download()
         assert np.abs(ma - mb).max() < C.TOL_M and ekf_script.rel_err(Pa, Pb) < C.TOL_P_REL, f"frame {frame}"
         assert abs(a.platform_time() - b.platform_time()) < 1e-12 and a.pose_count() == b.pose_count()
+        if frame % 2 == 1:
+            torch.cuda.synchronize()
         del dev
     a.close(); b.close()
 
