@@ -173,6 +173,7 @@ class Session:
             self.d_ts = torch.zeros(NFEAT, dtype=torch.int32, device=self.dev)
             self.d_ekf_pool = torch.from_numpy(inputs.ekf_pool).to(self.dev)
             self.d_res = torch.zeros(2, dtype=torch.float64, device=self.dev)
+            self.d_mean = torch.zeros(20, dtype=torch.float64, device=self.dev)
         # host copy of the measurement pool in page-locked memory (the e2e contract: inputs come from pinned host memory)
         self.h_ekf_pool = torch.from_numpy(inputs.ekf_pool).pin_memory()
         # per-frame EKF op lists (hv_ekf_run_*: one crossing of the language boundary per frame)
@@ -226,9 +227,10 @@ class Session:
         if not self.overlap:
             A.wait_stream(B); B.wait_stream(A)
         self.ekf.run_device(ops, IMU_OPS)                                                          # B: IMU burst (queued) ...
-        self.ekf.flush()                                                                           # ... issued now
+        self.ekf.predicted_mean_device(self.d_mean.data_ptr())                                     # ... its mean part first: all the flow predictor reads
         self.ev_ekf.record(B)
-        A.wait_event(self.ev_ekf)                                                                  # the flow predictor reads the state propagated to this frame
+        self.ekf.flush()                                                                           # ... then the full launch, beside the tracker
+        A.wait_event(self.ev_ekf)                                                                  # the flow predictor reads the pose propagated to this frame
         init = self.d_init[0, j - 1] if j > self.prev_j else self.d_init[1, j]
         with self.torch.cuda.stream(A):
             self.d_next.copy_(init)                               # predicted flow (host callback in the reference)

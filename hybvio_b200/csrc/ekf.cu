@@ -559,8 +559,15 @@ cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s)
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    ekf_predict_kernel<<<1, EKF_NT, ekf_predict_smem_bytes(a.count), s>>>(a);
-    return cudaGetLastError();
+    // programmatic dependent launch (see ekf_cluster2.cu): the kernel may be scheduled while its predecessor on the stream still runs; it
+    // waits in griddepcontrol.wait before it reads the state. HV_EKF_NO_PDL=1 switches it off.
+    static const bool pdl = getenv("HV_EKF_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(EKF_NT); cfg.dynamicSmemBytes = ekf_predict_smem_bytes(a.count); cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, ekf_predict_kernel, a);
 }
 cudaError_t ekf_launch_elementwise(const EkfEwArgs& a, cudaStream_t s)
 {

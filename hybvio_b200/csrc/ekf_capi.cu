@@ -485,6 +485,24 @@ int hv_ekf_predict(hv_ekf* e, double t, const double xg[3], const double xa[3])
     return HV_OK;
 }
 
+int hv_ekf_predicted_mean_device(hv_ekf* e, double* dMean20)
+{
+    EKF_ENTER_LAZY(e, "hv_ekf_predicted_mean_device");
+    if (!dMean20) { hv_set_error("hv_ekf_predicted_mean_device: NULL output"); return HV_ERR_INVALID; }
+    int rc = flush_sym(e);
+    if (rc != HV_OK) return rc;
+    cudaStream_t s = e->ctx->stream;
+    if (e->pend.count == 0) {                                     // nothing queued: the state as it is
+        HV_CUDA(cudaMemcpyAsync(dMean20, e->b.m, sizeof(double) * EKF_INER, cudaMemcpyDeviceToDevice, s));
+        return HV_OK;
+    }
+    EkfPredictArgs a = e->pend;                                   // the queue stays: the full launch follows with the next call that needs P
+    a.b = e->b; a.gravity = e->prm.gravity; a.meanOut = dMean20;
+    HV_CUDA(ekf_launch_predict(a, s));
+    e->ctx->launches++;
+    return HV_OK;
+}
+
 int hv_ekf_flush(hv_ekf* e)
 {
     EKF_ENTER(e, "hv_ekf_flush");

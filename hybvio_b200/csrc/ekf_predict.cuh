@@ -49,6 +49,20 @@ __device__ __forceinline__ double ps_qval(const double* s_Q, int a, int b, doubl
     return s_Q[a + b * 12];
 }
 
+// Programmatic dependent launch (sm_90+); no-ops on the host emulator
+__device__ __forceinline__ void ekf_pdl_launch_dependents()
+{
+#ifndef HV_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void ekf_pdl_wait()
+{
+#ifndef HV_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double* dyn)
 {
     __shared__ double s_Q[144], s_P00[400], s_T1[400];
@@ -58,9 +72,14 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
     const int tid = threadIdx.x, N = a.b.N, cnt = a.count;
     const int lane = tid & 31, wrp = tid >> 5;
     double* P = a.b.P;
+    const bool meanOnly = a.meanOut != nullptr;
     EKF_PMARK(0);
-    for (int i = tid; i < 400; i += EKF_NT) s_P00[i] = P[(i % 20) + (size_t)(i / 20) * N];
-    for (int i = tid; i < 144; i += EKF_NT) s_Q[i] = a.b.Q[i];
+    ekf_pdl_launch_dependents();                      // programmatic dependent launch, as in ekf_cluster2.cuh: nothing of the filter
+    ekf_pdl_wait();                                   // state is read before the previous kernel of the stream has completed
+    if (!meanOnly) {
+        for (int i = tid; i < 400; i += EKF_NT) s_P00[i] = P[(i % 20) + (size_t)(i / 20) * N];
+        for (int i = tid; i < 144; i += EKF_NT) s_Q[i] = a.b.Q[i];
+    }
     if (tid < EKF_INER) s_m[tid] = a.b.m[tid];
     __syncthreads();
     EKF_PMARK(1);
@@ -71,8 +90,10 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
         const EkfPredictSample& S = a.s[k];
         double* smp = dyn + (size_t)k * PS_STRIDE;
         double* D = smp + PS_D; double* G = smp + PS_G;
-        for (int i = lane; i < 400; i += 32) D[i] = (i % 21 == 0) ? 1.0 : 0.0;
-        for (int i = lane; i < 240; i += 32) G[i] = 0.0;
+        if (!meanOnly) {
+            for (int i = lane; i < 400; i += 32) D[i] = (i % 21 == 0) ? 1.0 : 0.0;
+            for (int i = lane; i < 240; i += 32) G[i] = 0.0;
+        }
         double bg0 = s_m[EKF_BGA], bg1 = s_m[EKF_BGA + 1], bg2 = s_m[EKF_BGA + 2];
         double ba = s_m[EKF_BAA + (lane % 3)];
         for (int j = 0; j < k; j++) { const double dg = a.s[j].bgaDecay, da = a.s[j].baaDecay; bg0 *= dg; bg1 *= dg; bg2 *= dg; ba *= da; }
@@ -153,6 +174,19 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
         const double dt = S.dt;
         const double* qo = s_q + k * 4;           // orientation before the sample
         const double* qn = s_qn + k * 4;          // and after (before a normalizeQuaternions that may follow)
+        if (meanOnly) {                           // velocity increment only: the same expression as below, in the same order
+            if (lane >= 8 && lane < 11) {
+                const double* q = qn;
+                const int i = lane - 8;
+                double R[9];
+                R[0] = q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3]; R[1] = 2 * q[1] * q[2] - 2 * q[0] * q[3]; R[2] = 2 * q[1] * q[3] + 2 * q[0] * q[2];
+                R[3] = 2 * q[1] * q[2] + 2 * q[0] * q[3]; R[4] = q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3]; R[5] = 2 * q[2] * q[3] - 2 * q[0] * q[1];
+                R[6] = 2 * q[1] * q[3] - 2 * q[0] * q[2]; R[7] = 2 * q[2] * q[3] + 2 * q[0] * q[1]; R[8] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
+                const double gi = i == 2 ? -a.gravity : 0.0;
+                smp[PS_DV + i] = (R[i] * Tx[0] + R[3 + i] * Tx[1] + R[6 + i] * Tx[2] + gi) * dt;
+            }
+            continue;
+        }
         if (lane < 3) {
             // d(orientation)/d(gyro noise) columns A dS_j q (ekf.cpp:470-476) and their negatives (ekf.cpp:492)
             const int j = lane;
@@ -269,6 +303,12 @@ __device__ __forceinline__ void ekf_predict_body(const EkfPredictArgs& a, double
         else if (lane < 10) { double b = s_m[EKF_BAA + lane - 7]; for (int k = 0; k < cnt; k++) b *= a.s[k].baaDecay; s_mfinal[EKF_BAA + lane - 7] = b; }
         else if (lane < 13) { double b = s_m[EKF_BGA + lane - 10]; for (int k = 0; k < cnt; k++) b *= a.s[k].bgaDecay; s_mfinal[EKF_BGA + lane - 10] = b; }
         else if (lane < 17) s_mfinal[EKF_BAT + lane - 13] = s_m[EKF_BAT + lane - 13];     // BAT (3) and SFT (1) are constant
+    }
+
+    if (meanOnly) {
+        __syncthreads();
+        if (tid < EKF_INER) a.meanOut[tid] = s_mfinal[tid];
+        return;
     }
 
     // ---- covariance recursion on the fp64 tensor cores: T1 = D P00 and Dacc' = D Dacc (one 8 x 8 tile of each per warp,

@@ -274,6 +274,12 @@ template <int WIN, int NW = LKC_NW>
 __global__ void __launch_bounds__(NW * 32) hv_lk_cta_kernel(LkLaunch L)
 {
     constexpr int RPW = (WIN + NW - 1) / NW;      // window rows per warp
+#ifndef HV_EMU
+    // Programmatic dependent launch: the next kernel of the stream (the stereo call behind the temporal one) may be scheduled now; this
+    // one reads nothing (points, pyramids) before its predecessor has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     const LkJob& job = L.jobs[blockIdx.y];
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, tid = threadIdx.x;
     const int f = blockIdx.x;
@@ -503,15 +509,19 @@ cudaError_t hv_launch_lk(const LkLaunch& L, int win, cudaStream_t stream)
     long long total = 0;
     for (int i = 0; i < L.njobs; i++) total += L.jobs[i].n;
     if (hv_lk_uses_cta_kernel(total)) {          // the one predicate hv_lk_track's polling path relies on too (capi_internal.h)
-        dim3 grid(maxN, L.njobs), block(LKC_NW * 32);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(maxN, L.njobs); cfg.blockDim = dim3(LKC_NW * 32); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        static const bool pdl = getenv("HV_EKF_NO_PDL") == nullptr;       // one switch for every programmatic dependent launch of the library
+        cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
         switch (win) {
-            case 31: hv_lk_cta_kernel<31><<<grid, block, 0, stream>>>(L); break;
-            case 21: hv_lk_cta_kernel<21><<<grid, block, 0, stream>>>(L); break;
-            case 15: hv_lk_cta_kernel<15><<<grid, block, 0, stream>>>(L); break;
-            case 11: hv_lk_cta_kernel<11><<<grid, block, 0, stream>>>(L); break;
+            case 31: return cudaLaunchKernelEx(&cfg, hv_lk_cta_kernel<31>, L);
+            case 21: return cudaLaunchKernelEx(&cfg, hv_lk_cta_kernel<21>, L);
+            case 15: return cudaLaunchKernelEx(&cfg, hv_lk_cta_kernel<15>, L);
+            case 11: return cudaLaunchKernelEx(&cfg, hv_lk_cta_kernel<11>, L);
             default: return cudaErrorInvalidValue;
         }
-        return cudaGetLastError();
     }
     dim3 grid((maxN + LK_WARPS_PER_CTA - 1) / LK_WARPS_PER_CTA, L.njobs);
     dim3 block(LK_WARPS_PER_CTA * 32);

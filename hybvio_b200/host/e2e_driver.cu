@@ -109,6 +109,8 @@ int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventCreateWithFlags(&evLk, cudaEventDisableTiming); cudaEventCreateWithFlags(&evEkf, cudaEventDisableTiming);
     hv_ctx_sync(trk); hv_ctx_sync(ekf_ctx);
+    double* d_mean = nullptr;
+    if (cudaMalloc(&d_mean, 20 * sizeof(double)) != cudaSuccess) return HV_ERR_OOM;
     cudaEventRecord(e0, sa);
     int rc = HV_OK, lastOps = 0;
     for (int k = 0; k < nframes && rc == HV_OK; k++) {
@@ -119,10 +121,12 @@ int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
         rc = hv_pyr_build_batch(cur, img, strides, f.right ? 2 : 1, 1);          // A: no dependency
         if (rc != HV_OK) break;
         rc = hv_ekf_run_device(ekf, f.ops, f.nimu);                            // B: IMU burst (queued) ...
-        if (rc == HV_OK) rc = hv_ekf_flush(ekf);                               // ... issued now
+        if (rc == HV_OK) rc = hv_ekf_predicted_mean_device(ekf, d_mean);       // ... its mean part first: all the flow predictor reads
         if (rc != HV_OK) break;
         cudaEventRecord(evEkf, sb);
-        cudaStreamWaitEvent(sa, evEkf, 0);                                     // the flow predictor reads the state propagated to this frame
+        rc = hv_ekf_flush(ekf);                                                // ... then the full launch (covariance), beside the tracker
+        if (rc != HV_OK) break;
+        cudaStreamWaitEvent(sa, evEkf, 0);                                     // the flow predictor reads the pose propagated to this frame
         cudaMemcpyAsync(d_next, f.d_init_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToDevice, sa);
         rc = hv_lk_track_device(trk, p[0], cur[0], d_points, d_next, d_status, d_ts, n, 1, 20, 0.03, 1e-3);
         if (rc == HV_OK && f.right) rc = hv_lk_track_device(trk, cur[0], cur[1], d_next, d_next2, d_status, d_ts, n, 0, 20, 0.03, 1e-3);
@@ -142,6 +146,7 @@ int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(elapsed_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(evLk); cudaEventDestroy(evEkf);
+    cudaFree(d_mean);
     for (int i = 0; i < 4; i++) pyr[i] = p[i];
     return rc;
 }

@@ -194,6 +194,12 @@ int hv_ekf_predict(hv_ekf* ekf, double t, const double gyro[3], const double acc
  * to issuing every sample on its own (max_samples = 1). Likewise hv_ekf_symmetrize directly followed by hv_ekf_augment
  * (backend.cpp:1267 -> 805) is one launch. */
 int hv_ekf_flush(hv_ekf* ekf);
+/* The 20 inertial states (position, velocity, orientation, biases: ekf.hpp:26-50) that the QUEUED IMU samples lead to, written to
+ * d_mean20 (device, 20 doubles) by a small launch of its own on the context's stream -- the mean part of predict() alone, a quarter of
+ * the full launch, which stays queued. For consumers that need the propagated pose but not the covariance: the optical-flow predictor
+ * (src/odometry/backend.cpp:547-600 reads ekf->position() / orientation() and the pose trail, which predict() does not change), so that
+ * the tracker can start while the covariance is still being propagated. Bit-identical to what the full launch leaves in the state. */
+int hv_ekf_predicted_mean_device(hv_ekf* ekf, double* d_mean20);
 int hv_ekf_set_imu_batching(hv_ekf* ekf, int max_samples);
 
 /* The fixed-H updates (ekf.cpp:573-677); rate limits and early-outs as in the reference. Asynchronous. */

@@ -67,14 +67,19 @@ int main()
             if (s.normAfter) orc_ekf_normalize_quaternions(o, 1);
         }
         std::vector<double> dyn(ekf_predict_smem_bytes(cnt) / 8);
+        // mean-only launch first (hv_ekf_predicted_mean_device): must leave the state alone and produce the bits the full launch will
+        std::vector<double> mean(20, -7.0), m0 = dm, P0 = dP;
+        { EkfPredictArgs am = a; am.meanOut = mean.data(); emu::launch_cta(EKF_NT, 0, [&] { ekf_predict_body(am, dyn.data()); }); }
+        bool meanOk = dm == m0 && dP == P0;
         emu::launch_cta(EKF_NT, 0, [&] { ekf_predict_body(a, dyn.data()); });
+        for (int i = 0; i < 20; i++) meanOk = meanOk && mean[i] == dm[i];
         std::vector<double> om(N), oP((size_t)N * N), od(400);
         orc_ekf_download(o, om.data(), oP.data()); orc_ekf_get_dydx(o, od.data());
         double em = 0, eP = 0, pmax = 0, ed = 0;
         for (int i = 0; i < N; i++) em = std::fmax(em, std::fabs(om[i] - dm[i]));
         for (size_t i = 0; i < oP.size(); i++) { eP = std::fmax(eP, std::fabs(oP[i] - dP[i])); pmax = std::fmax(pmax, std::fabs(oP[i])); }
         for (int i = 0; i < 400; i++) ed = std::fmax(ed, std::fabs(od[i] - ddydx[i]));
-        const bool ok = em < 1e-12 && eP / pmax < 1e-12 && ed < 1e-12;
+        const bool ok = em < 1e-12 && eP / pmax < 1e-12 && ed < 1e-12 && meanOk;
         printf("trial %d N=%d cnt=%d: max|dm| %.3e  max|dP|/max|P| %.3e  max|d dydx| %.3e  %s\n", trial, N, cnt, em, eP / pmax, ed, ok ? "ok" : "FAIL");
         fails += !ok;
     }

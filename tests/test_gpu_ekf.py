@@ -243,6 +243,36 @@ def test_device_op_list_matches_oracle(cuda, oracle_lk, trail):
     a.close(); b.close()
 
 
+def test_predicted_mean_launch_matches_full_predict(cuda):
+    """hv_ekf_predicted_mean_device: the mean part of the queued IMU burst as its own small launch -- leaves state and queue alone and
+    produces exactly the 20 inertial states the full launch writes afterwards."""
+    import torch
+    p = C.params_with(default_params, 20)
+    a = cuda(p)
+    rng = np.random.RandomState(21)
+    a.initialize_orientation(ekf_script.imu_sample(np.random.RandomState(1), 0)[1])
+    t = 0.0
+    d = torch.full((20,), -5.0, dtype=torch.float64, device="cuda")
+    for burst in range(3):
+        m0, P0 = a.download()
+        for s_ in range(10):
+            t += 0.005
+            g, acc = ekf_script.imu_sample(rng, s_ + 1)
+            a.predict(t, g, acc)
+            if burst != 1:
+                a.normalize_quaternions(True)
+        a.predicted_mean_device(d.data_ptr())
+        torch.cuda.synchronize()
+        pred = d.cpu().numpy().copy()
+        m1, P1 = a.download()                   # issues the queued full launch
+        assert np.array_equal(pred, m1[:20]), np.abs(pred - m1[:20]).max()
+        assert not np.array_equal(m0[:10], m1[:10]) and not np.array_equal(P0, P1)
+    a.predicted_mean_device(d.data_ptr())       # nothing queued: the state as it is
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy(), a.download()[0][:20])
+    a.close()
+
+
 def test_reference_catch2_suite_against_cuda_ekf():
     """The reference's OWN unit tests (test/ekf.cpp: chi-squared KAT, der_predict, tranformTo with test/data/P.csv,
     m.csv), compiled unmodified but linked against hybvio_b200/host/cuda_ekf.cpp instead of src/odometry/ekf.cpp
