@@ -1118,6 +1118,7 @@ static int run_ops_host_async(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vu
     rc = flush_pending(e);
     if (rc != HV_OK) return rc;
     double* hout = e->h_pin + e->inDoubles;
+    if (!mOut && need == 0) return HV_OK;                        // nothing to hand back (e.g. the IMU burst of a frame): fully asynchronous
     if (mOut) HV_CUDA(cudaMemcpyAsync(hout + 8, e->b.m, e->N * sizeof(double), cudaMemcpyDeviceToHost, s));
     HV_CUDA(cudaStreamSynchronize(s));                           // the only synchronisation of the list
     __atomic_thread_fence(__ATOMIC_ACQUIRE);

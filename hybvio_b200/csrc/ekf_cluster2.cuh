@@ -718,6 +718,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
             Ks[t] = s;
         }
         __syncthreads();
+        EK2_PHASE(10);
         for (int t = tid; t < N * 21; t += EK2_NT) {
             const int j = t % N, cc = t / N;
             if (cc < 14) {
@@ -728,13 +729,16 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
                 AS[j + (size_t)cc * LD] = Ks[j + (cc - 14) * N];
             }
         }
+        EK2_PHASE(11);
         cluster.sync();                               // #4: all of G is final
+        EK2_PHASE(12);
         for (int t = tid; t < N * 14; t += EK2_NT) {
             const int i = t % N, cc = t / N;
             const int col = ek2_special_col(cc), r = col / B;
             AS[i + (size_t)cc * LD] = cluster.map_shared_rank(PB, r)[i + (size_t)(col - r * B) * LD];
         }
         __syncthreads();
+        EK2_PHASE(13);
         ek2_dmma_gemm(N, Bc, 21, wrp, lane, AS, 1, LD, BS + J0, LD, 1,
                       [&](int i, int jj) {
                           const int j = J0 + jj;
@@ -743,10 +747,12 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
                       },
                       [&](int i, int jj, double v0, double v1) { P2[i + (size_t)jj * N] = v0; if (jj + 1 < Bc) P2[i + (size_t)(jj + 1) * N] = v1; });
         Pblk = P2; ldb = N;
+        EK2_PHASE(14);
     }
     double* const Pdst = a.specP ? a.specP : P;
     if (a.symmetrize) {
         cluster.sync();                               // #5: every final block is in shared memory
+        EK2_PHASE(15);
         if (g.SYM) {
             // mirrored entries P(j, i) live in the block of the CTA that owns column i: fetched with the row index j running
             // fastest (contiguous in the owner's column), parked transposed, then combined and stored with i running fastest
@@ -755,6 +761,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
                 SYMB[i + (size_t)jj * N] = i != j ? cluster.map_shared_rank(Pblk, r)[j + (size_t)(i - r * B) * ldb] : 0.0;
             }
             __syncthreads();
+            EK2_PHASE(16);
             for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
                 const int i = idx % N, jj = idx / N, j = J0 + jj;
                 double v = Pblk[i + (size_t)jj * ldb];

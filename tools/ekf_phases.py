@@ -16,7 +16,9 @@ if os.environ.get("HV_EKF_CLUSTER_V1"):
              7: "elimination", 8: "chi2/decision", 9: "Z exchange + P/m update"}
 else:   # ekf_cluster2.cuh
     names = {0: "start", 1: "P block + H staged, residual", 2: "HP", 3: "partial S", 4: "S reduced (DSMEM)", 5: "elimination", 6: "chi2/decision",
-             7: "Z gathered (DSMEM)", 8: "P block downdate + m", 9: "stores (+Joseph/symmetrise)"}
+             7: "Z gathered (DSMEM)", 8: "P block downdate + m", 9: "stores",
+             10: "Joseph: K", 11: "T1 columns", 12: "cluster.sync", 13: "special columns of G gathered (DSMEM)", 14: "Joseph product", 15: "cluster.sync",
+             16: "mirrored entries fetched (DSMEM)"}
 for n in (8, 20, 40, 84):
     l = min(160, 20 + 7 * max(1, n // 4))
     Hm = torch.from_numpy(np.asfortranarray(rng.normal(0, 0.1, (n, l))).ravel(order="F").copy()).cuda()
@@ -39,13 +41,12 @@ for rep in range(3):
     ekf.symmetrize(); ekf.augment(-1)
 ekf.flush()
 w = np.zeros(32); lib.hv_ekf_debug_result_words(ekf.h, w.ctypes.data)
-ts = w[8:18]
-keys = [k for k in range(10) if ts[k] > 0]
+ts = w[8:25]
+keys = sorted([k for k in range(17) if ts[k] > 0], key=lambda k: ts[k])
 line = f"symmetrise+augment: total {(max(ts[keys]) - ts[0]) / 1e3:6.1f} us | "
 prev = ts[0]
 for k in keys[1:]:
-    if ts[k] >= prev:
-        line += f"{names[k]} {(ts[k] - prev) / 1e3:.1f} | "; prev = ts[k]
+    line += f"{names[k]} {(ts[k] - prev) / 1e3:.1f} | "; prev = ts[k]
 print(line)
 
 t = 1.0
