@@ -49,7 +49,7 @@ __host__ __device__ inline Ek2Geom ek2_geom(int n, int l, int N, bool joseph, in
     g.LD = N + (((20 - (N & 15)) & 15) ? ((20 - (N & 15)) & 15) : 16);
     g.X = n * (l > g.LD ? l : g.LD);                        // H (n x l, ld n), later the gathered Z (n x N, ld LD)
     g.W = (n + g.B + 1 + (joseph ? n : 0)) | 1;             // tableau row: [S | HP_J | v | (I)]
-    g.T = n * g.W;
+    g.T = (n * g.W + 1) & ~1;                               // even: the P block behind the tableau starts on a 16-byte boundary (bulk copies)
     g.PB = g.LD * g.B;                                      // own column block of P, ld LD
     const int MTn = (n + 7) >> 3;
     const int E = (64 * (MTn * (MTn + 1) / 2) + C - 1) / C;    // two-stage: entries of the upper-triangular 8 x 8 tiles of S
@@ -387,6 +387,78 @@ __device__ __forceinline__ void ek2_report(const EkfUpdateArgs& a, double st, do
     }
 }
 
+// ---- bulk asynchronous copies (TMA, non-tensor form: cp.async.bulk) between global and shared memory, completion on an mbarrier.
+// One instruction moves a whole column / row / block: no register staging, no load -> store loop per thread. Addresses and sizes must
+// be multiples of 16 bytes (ek2_body checks and keeps the loops otherwise). On the host emulator: memcpy by the issuing thread.
+__device__ __forceinline__ void ek2_bar_init(unsigned long long* bar, int count)
+{
+#ifdef HV_EMU
+    *bar = 0; (void)count;
+#else
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void ek2_bar_expect(unsigned long long* bar, unsigned bytes)   // one arrival + the bytes it announces (0: plain arrival)
+{
+#ifdef HV_EMU
+    (void)bar; (void)bytes;
+#else
+    if (bytes) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+#endif
+}
+__device__ __forceinline__ void ek2_bar_wait(unsigned long long* bar, unsigned phase)
+{
+#ifdef HV_EMU
+    (void)bar; (void)phase;                           // (every use is followed by a barrier of the CTA)
+#else
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(phase) : "memory");
+    } while (!done);
+#endif
+}
+__device__ __forceinline__ void ek2_bulk_g2s(double* dst, const double* src, unsigned bytes, unsigned long long* bar)
+{
+#ifdef HV_EMU
+    if ((((size_t)dst) | ((size_t)src) | bytes) & 15) { fprintf(stderr, "emu: misaligned bulk copy (global -> shared)\n"); abort(); }
+    memcpy(dst, src, bytes); (void)bar;
+#else
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+#endif
+}
+__device__ __forceinline__ void ek2_bulk_s2g(double* dst, const double* src, unsigned bytes)
+{
+#ifdef HV_EMU
+    if ((((size_t)dst) | ((size_t)src) | bytes) & 15) { fprintf(stderr, "emu: misaligned bulk copy (shared -> global)\n"); abort(); }
+    memcpy(dst, src, bytes);
+#else
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"((unsigned)__cvta_generic_to_shared(src)), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void ek2_bulk_store_done()        // by the thread that issued the stores: committed and complete
+{
+#ifndef HV_EMU
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void ek2_fence_async_smem()       // generic-proxy writes to shared memory -> visible to the bulk-copy engine
+{
+#ifndef HV_EMU
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void ek2_fence_async_all()        // ... to global memory (a slice published for the neighbours' bulk reads)
+{
+#ifndef HV_EMU
+    asm volatile("fence.proxy.async;" ::: "memory");
+#endif
+}
+
 // `Cluster` is cooperative_groups::cluster_group (or the emulator's stand-in).
 template <class Cluster>
 __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster cluster)
@@ -394,7 +466,8 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     __shared__ double s_scalar[2];
     __shared__ double s_linv[EK2_LINV_DOUBLES];
     __shared__ int s_bad;
-    __shared__ double s_m[EK2_MAXN];
+    __shared__ __align__(16) double s_m[EK2_MAXN];
+    __shared__ __align__(8) unsigned long long s_bar[2];      // [0] staging (two arrivals: H, then P block + mean), [1] Z gather
     const int c = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, nwarps = EK2_NT / 32;
     const int N = a.b.N, n = a.n, l = a.l;
@@ -423,10 +496,20 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     // own measurement matrix overlap with this kernel); it will not touch the filter state before its own
     // griddepcontrol.wait, which returns when this grid has completed and its writes are visible.
     ek2_pdl_launch_dependents();
+    // Bulk copies need 16-byte aligned addresses and sizes: an even state dimension and aligned buffers (ek2_geom keeps the shared-memory
+    // side aligned); otherwise the loops below do the same work.
+    const bool bulk = (N & 1) == 0 && ((((size_t)P) | ((size_t)a.b.m) | ((size_t)a.b.cwork) | ((size_t)a.specP) | ((size_t)a.specM) | ((size_t)sm)) & 15) == 0;
+    const bool bulkH = bulk && a.op == EKF_OP_DENSE && ((n * l) & 1) == 0 && (((size_t)a.H) & 15) == 0;
+    if (tid == 0) { ek2_bar_init(&s_bar[0], 2); ek2_bar_init(&s_bar[1], 1); }
+    if (bulk) __syncthreads();                        // the barriers exist before anybody waits on them
     // ---- the measurement matrix does not depend on earlier kernels: stage it before waiting for them
     const bool lateH = a.lateH != 0 && a.op == EKF_OP_DENSE;
-    if (a.op == EKF_OP_DENSE) { if (!lateH) ek2_copy8(X, a.H, n * l, tid); }
-    else for (int i = tid; i < n * l; i += EK2_NT) X[i] = 0.0;
+    if (a.op == EKF_OP_DENSE) {
+        if (!lateH) {
+            if (bulkH) { if (tid == 0) { ek2_bar_expect(&s_bar[0], (unsigned)(n * l * 8)); ek2_bulk_g2s(X, a.H, (unsigned)(n * l * 8), &s_bar[0]); } }
+            else ek2_copy8(X, a.H, n * l, tid);
+        }
+    } else for (int i = tid; i < n * l; i += EK2_NT) X[i] = 0.0;
     ek2_pdl_wait();
     // ---- device-side control flow of a chain issued without host round trips (EkfUpdateArgs): every thread of the cluster
     // reads the same words, written by kernels that have completed
@@ -435,9 +518,21 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         if (a.gateI && *(volatile const int*)a.gateI != a.gateIExpect) run = false;
         if (a.gateD && *(volatile const double*)a.gateD != a.gateDExpect) run = false;
         if (a.counter && *(volatile const int*)a.counter >= a.counterMax) run = false;
-        if (!run) { if (c == 0 && tid == 0) ek2_report(a, 1.0, 0.0, 0.0); return; }      // VuOutlierStatus::NOT_COMPUTED
+        if (!run) {                                                                        // VuOutlierStatus::NOT_COMPUTED
+            if (bulk) {                               // a bulk copy of H may be in flight: complete the staging barrier and wait for it
+                const int arrived = (bulkH && !lateH) ? 1 : 0;
+                if (tid == 0) for (int q = arrived; q < 2; q++) ek2_bar_expect(&s_bar[0], 0);
+                ek2_bar_wait(&s_bar[0], 0);
+            }
+            if (c == 0 && tid == 0) ek2_report(a, 1.0, 0.0, 0.0);
+            return;
+        }
     }
-    if (lateH) ek2_copy8(X, a.H, n * l, tid);
+    if (lateH) {
+        if (bulkH) { if (tid == 0) { ek2_bar_expect(&s_bar[0], (unsigned)(n * l * 8)); ek2_bulk_g2s(X, a.H, (unsigned)(n * l * 8), &s_bar[0]); } }
+        else ek2_copy8(X, a.H, n * l, tid);
+    }
+    if (bulk && !bulkH && tid == 0) ek2_bar_expect(&s_bar[0], 0);        // the first of the two arrivals of the staging barrier
     // ---- stage the state mean and the own column block of P (augmentation: of A P A' + visAugQ, ekf.cpp:853-857)
     if (joseph) {
         const int drop = a.dropIdx;
@@ -450,6 +545,15 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
             if (a.symFirst && si >= 0 && sj >= 0 && si != sj) v = 0.5 * (v + P[sj + (size_t)si * N]);
             if (i == j && i >= EKF_CAM && i < EKF_CAM + EKF_POSE) v += (i - EKF_CAM) < 3 ? a.augNoisePos : a.augNoiseOri;
             PB[i + (size_t)(idx / N) * LD] = v;
+        }
+        if (bulk && tid == 0) ek2_bar_expect(&s_bar[0], 0);
+    } else if (bulk) {
+        // one bulk copy per column of the block (N doubles each, into the padded leading dimension) + one for the state mean
+        if (wrp == 0) {
+            if (lane == 0) ek2_bar_expect(&s_bar[0], (unsigned)((N * Bc + N) * 8));
+            __syncwarp();
+            for (int j = lane; j < Bc; j += 32) ek2_bulk_g2s(PB + (size_t)j * LD, P + (size_t)(J0 + j) * N, (unsigned)(N * 8), &s_bar[0]);
+            if (lane == 31) ek2_bulk_g2s(s_m, a.b.m, (unsigned)(N * 8), &s_bar[0]);
         }
     } else {
         for (int i = tid; i < N; i += EK2_NT) s_m[i] = a.b.m[i];
@@ -465,6 +569,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         }
     }
 
+    if (bulk) ek2_bar_wait(&s_bar[0], 0);             // H, the P block and the mean have landed
     // ---- measurement model into shared memory (ld = n)
     double hspeed = 0.0;
     if (a.op == EKF_OP_DENSE) {
@@ -657,7 +762,17 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         // at ~34 B/clk); every CTA publishes its slice, cluster barrier (release / acquire covers global memory), bulk read
         double* Zg = a.b.cwork;
         for (int t = tid; t < n * Bc; t += EK2_NT) { const int k = t / Bc, jj = t - k * Bc; Zg[(size_t)k * N + J0 + jj] = T[(size_t)k * W + n + jj]; }
+        if (bulk) ek2_fence_async_all();              // the slice is read by the neighbours' bulk copies (async proxy)
         cluster.sync();                               // #3
+        if (bulk) {
+            // one bulk copy per row of Z (N doubles into the padded leading dimension), issued by warp 0
+            if (wrp == 0) {
+                if (lane == 0) ek2_bar_expect(&s_bar[1], (unsigned)(n * N * 8));
+                __syncwarp();
+                for (int k = lane; k < n; k += 32) ek2_bulk_g2s(Z + (size_t)k * LD, Zg + (size_t)k * N, (unsigned)(N * 8), &s_bar[1]);
+            }
+            ek2_bar_wait(&s_bar[1], 0);
+        } else
         for (int base = 0; base < n * N; base += 8 * EK2_NT) {
             double r[8];
 #pragma unroll
@@ -691,13 +806,16 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     }
     // quaternion normalisation: updateCommon normalises the current orientation only, the visual update and the augmentation all of
     // them (ekf.cpp:31, 843, 874)
+    if (bulk) ek2_fence_async_smem();                 // the block just written leaves by bulk copies (below)
     __syncthreads();
     if (c == cm) {
         for (int q = tid; q < (a.normalizeAll ? a.b.trail + 1 : 1); q += EK2_NT)
             ek2_normalize_quat(q == 0 ? s_m + EKF_ORI : s_m + EKF_CAM + EKF_POSE * (q - 1) + 3);
+        ek2_fence_async_smem();
         __syncthreads();
         double* const mDst = a.specM ? a.specM : a.b.m;
-        for (int i = tid; i < N; i += EK2_NT) mDst[i] = s_m[i];
+        if (bulk) { if (tid == 32) { ek2_bulk_s2g(mDst, s_m, (unsigned)(N * 8)); ek2_bulk_store_done(); } }
+        else for (int i = tid; i < N; i += EK2_NT) mDst[i] = s_m[i];
     }
     EK2_PHASE(8);
 
@@ -780,6 +898,12 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
                 }
                 Pdst[i + (size_t)j * N] = v;
             }
+        }
+    } else if (bulk) {
+        // (the downdate wrote the block with ordinary stores: fenced towards the bulk-copy engine right after it, a CTA barrier since)
+        if (wrp == 0) {
+            for (int j = lane; j < Bc; j += 32) ek2_bulk_s2g(Pdst + (size_t)(J0 + j) * N, Pblk + (size_t)j * ldb, (unsigned)(N * 8));
+            ek2_bulk_store_done();
         }
     } else {
         for (int idx = tid; idx < N * Bc; idx += EK2_NT) Pdst[(size_t)J0 * N + idx] = Pblk[(idx % N) + (size_t)(idx / N) * ldb];
