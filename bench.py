@@ -302,6 +302,9 @@ class Session:
         capi.check(drv.hv_e2e_run_phases(self.ctx.h, self.ctx_b.h, P, self.ekf.h, self.inp.points.ctypes.data, NFEAT, frames, nframes, pose,
                                          ctypes.byref(ms), phases), "hv_e2e_run")
         self.e2e_host_phase_us = {k: round(phases[i] / nframes, 2) for i, k in enumerate(("pyramids_submit", "lk_temporal", "lk_stereo", "ekf_ops"))}
+        ht = (ctypes.c_double * 4)()
+        if capi.load().hv_ekf_debug_host_times(self.ekf.h, ht) == 0:      # the LAST frame's measurement list: issue / wait split of its host time
+            self.e2e_host_phase_us["ekf_list_last_frame"] = {"issue_us": round(ht[0], 1), "wait_us": round(ht[1], 1), "total_us": round(ht[2], 1), "ops": int(ht[3])}
         by_handle = {p.h.value: p for p in self.pyr}
         self.pyr = [by_handle[P[i]] for i in range(4)]
         return float(ms.value), np.array(pose)

@@ -165,6 +165,7 @@ def _bind_ekf(lib):
                                          ctypes.POINTER(c_int)]
     lib.hv_ekf_track_models_time.argtypes = [c_void_p, c_int, ctypes.POINTER(ctypes.c_float)]
     lib.hv_ekf_debug_result_words.argtypes = [c_void_p, c_void_p]
+    lib.hv_ekf_debug_host_times.argtypes = [c_void_p, c_void_p]
     lib.hv_ekf_visual_track.argtypes = [c_void_p, ctypes.POINTER(TrackModel), c_double, c_double, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double)]
     lib.hv_ekf_visual_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p]
     lib.hv_ekf_augment.argtypes = [c_void_p, c_int]

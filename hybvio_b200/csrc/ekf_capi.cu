@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <chrono>
 
 #define HV_RUN_MAX_OPS 256       // ops of one hv_ekf_run_host list that can report through the mapped result area
 
@@ -45,6 +46,7 @@ struct hv_ekf {
     double* resSide = nullptr;
     double* d_opres = nullptr;              // hv_ekf_run_device: result words per op of the list (4 doubles each, HV_RUN_MAX_OPS)
     std::vector<unsigned char> lastVisual;  // per op of the last hv_ekf_run_device list: 1 = VISUAL (has result words)
+    double hostTimes[4] = {0, 0, 0, 0};     // last hv_ekf_run_host list: {issue, wait, total} in us, number of ops (hv_ekf_debug_host_times)
     // host bookkeeping, exactly the members of EKFImplementation (ekf.cpp:145-151)
     int augmentCount = 0;
     std::vector<double> augmentTimes;
@@ -1025,6 +1027,7 @@ static int run_ops_host_async(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vu
     }
     if (need > e->inDoubles) return HV_OK;
     *handled = 1;
+    const auto tHost0 = std::chrono::steady_clock::now();
     cudaStream_t s = e->ctx->stream;
     if (!e->copyStream) HV_CUDA(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
     cudaStream_t cs = e->copyStream;
@@ -1120,7 +1123,13 @@ static int run_ops_host_async(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vu
     double* hout = e->h_pin + e->inDoubles;
     if (!mOut && need == 0) return HV_OK;                        // nothing to hand back (e.g. the IMU burst of a frame): fully asynchronous
     if (mOut) HV_CUDA(cudaMemcpyAsync(hout + 8, e->b.m, e->N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    const auto tHost1 = std::chrono::steady_clock::now();
     HV_CUDA(cudaStreamSynchronize(s));                           // the only synchronisation of the list
+    {
+        const auto tHost2 = std::chrono::steady_clock::now();
+        auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        e->hostTimes[0] = us(tHost0, tHost1); e->hostTimes[1] = us(tHost1, tHost2); e->hostTimes[2] = us(tHost0, tHost2); e->hostTimes[3] = nops;
+    }
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
     if (mOut) memcpy(mOut, hout + 8, e->N * sizeof(double));
     for (int i = 0; i < nops; i++) {
@@ -1170,6 +1179,13 @@ int hv_ekf_run_host(hv_ekf* e, const hv_ekf_op* ops, int nops, int* vuStatus, do
         if (handled || rc != HV_OK) return rc;
     }
     return run_ops(e, ops, nops, true, vuStatus, chi2, mOut);
+}
+
+int hv_ekf_debug_host_times(hv_ekf* e, double* out4)
+{
+    if (!e || !out4) { hv_set_error("hv_ekf_debug_host_times: NULL"); return HV_ERR_INVALID; }
+    for (int i = 0; i < 4; i++) out4[i] = e->hostTimes[i];
+    return HV_OK;
 }
 
 int hv_ekf_debug_result_words(hv_ekf* e, double* out32)

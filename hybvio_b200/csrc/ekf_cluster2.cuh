@@ -804,6 +804,17 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
                           if (j + 1 < Bc) PB[i + (size_t)(j + 1) * LD] = -v1; else if (j + 1 == Bc && own) s_m[i] = v1;
                       });
     }
+    // Joseph form, first step: the gain K = Z' (L^-1 I) (N x 7) needs the gathered Z and the eliminated identity columns only, so it
+    // shares the barrier of the downdate
+    if (joseph) {
+        double* Ks = EX;
+        for (int t = tid; t < N * EKF_POSE; t += EK2_NT) {
+            const int i = t % N, r = t / N;
+            double s = 0.0;
+            for (int k = 0; k < n; k++) s += Z[(size_t)k * LD + i] * T[(size_t)k * W + vcol + 1 + r];
+            Ks[t] = s;
+        }
+    }
     // quaternion normalisation: updateCommon normalises the current orientation only, the visual update and the augmentation all of
     // them (ekf.cpp:31, 843, 874)
     if (bulk) ek2_fence_async_smem();                 // the block just written leaves by bulk copies (below)
@@ -829,14 +840,19 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         double* AS = Ks + (size_t)N * EKF_POSE;       // N x 21, ld LD: [G special columns | K]
         double* BS = AS + (size_t)21 * LD;            // N x 21, ld LD: [T1c | Rdiag K]
         double* P2 = BS + (size_t)21 * LD;            // N x B: P'' block
-        for (int t = tid; t < N * EKF_POSE; t += EK2_NT) {
-            const int i = t % N, r = t / N;
-            double s = 0.0;
-            for (int k = 0; k < n; k++) s += Z[(size_t)k * LD + i] * T[(size_t)k * W + vcol + 1 + r];
-            Ks[t] = s;
-        }
-        __syncthreads();
         EK2_PHASE(10);
+        // the special columns of G = P' - Z'Z that this CTA owns go to EVERY CTA's operand block (remote stores: fire and forget, they
+        // are complete at the cluster barrier below) -- the first version had every CTA fetch them after the barrier, a dependent
+        // round trip per element on everybody's path
+        {
+            int own[14], nown = 0;
+#pragma unroll
+            for (int cc = 0; cc < 14; cc++) { const int col = ek2_special_col(cc); if (col >= J0 && col < J0 + Bc) own[nown++] = cc; }
+            for (int t = tid; t < nown * C * N; t += EK2_NT) {
+                const int i = t % N, rest = t / N, q = rest % C, cc = own[rest / C];
+                cluster.map_shared_rank(AS, q)[i + (size_t)cc * LD] = PB[i + (size_t)(ek2_special_col(cc) - J0) * LD];
+            }
+        }
         for (int t = tid; t < N * 21; t += EK2_NT) {
             const int j = t % N, cc = t / N;
             if (cc < 14) {
@@ -850,13 +866,6 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         EK2_PHASE(11);
         cluster.sync();                               // #4: all of G is final
         EK2_PHASE(12);
-        for (int t = tid; t < N * 14; t += EK2_NT) {
-            const int i = t % N, cc = t / N;
-            const int col = ek2_special_col(cc), r = col / B;
-            AS[i + (size_t)cc * LD] = cluster.map_shared_rank(PB, r)[i + (size_t)(col - r * B) * LD];
-        }
-        __syncthreads();
-        EK2_PHASE(13);
         ek2_dmma_gemm(N, Bc, 21, wrp, lane, AS, 1, LD, BS + J0, LD, 1,
                       [&](int i, int jj) {
                           const int j = J0 + jj;
@@ -869,17 +878,19 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     }
     double* const Pdst = a.specP ? a.specP : P;
     if (a.symmetrize) {
-        cluster.sync();                               // #5: every final block is in shared memory
+        if (g.SYM) {
+            // the mirrored entry of P(i, j) is P(j, i), held by the CTA that owns column i: every CTA SENDS the entries of its block to the
+            // owners of their mirror images (row j of the own column i -> slot (i, j) of the owner of column j), remote stores that are
+            // complete at the cluster barrier; the first version fetched them after the barrier (a dependent round trip per element)
+            if (joseph) __syncthreads();              // the Joseph product above wrote the block
+            for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
+                const int jrow = idx % N, icol = idx / N, r = jrow / B;
+                cluster.map_shared_rank(SYMB, r)[(J0 + icol) + (size_t)(jrow - r * B) * N] = Pblk[jrow + (size_t)icol * ldb];
+            }
+        }
+        cluster.sync();                               // #5: every final block is in shared memory, every mirror image has arrived
         EK2_PHASE(15);
         if (g.SYM) {
-            // mirrored entries P(j, i) live in the block of the CTA that owns column i: fetched with the row index j running
-            // fastest (contiguous in the owner's column), parked transposed, then combined and stored with i running fastest
-            for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
-                const int jj = idx % Bc, i = idx / Bc, j = J0 + jj, r = i / B;
-                SYMB[i + (size_t)jj * N] = i != j ? cluster.map_shared_rank(Pblk, r)[j + (size_t)(i - r * B) * ldb] : 0.0;
-            }
-            __syncthreads();
-            EK2_PHASE(16);
             for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
                 const int i = idx % N, jj = idx / N, j = J0 + jj;
                 double v = Pblk[i + (size_t)jj * ldb];

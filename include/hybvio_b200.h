@@ -360,6 +360,9 @@ int hv_ekf_track_models_time(hv_ekf* ekf, int reps, float* ms_per_launch);
 /* Debug: the 32 result words of the last update kernel ([0] status, [1] chi2, [2] flag, [8..] phase timestamps when
  * the library is built with -DHV_EKF_TIMING). */
 int hv_ekf_debug_result_words(hv_ekf* ekf, double* out32);
+/* Host wall time of the most recent hv_ekf_run_host list that had something to hand back: out4 = {issuing the list, waiting in its one
+ * synchronisation, total} in microseconds and the number of ops (bench.py reports them next to `e2e`). */
+int hv_ekf_debug_host_times(hv_ekf* ekf, double* out4);
 
 #ifdef __cplusplus
 }
