@@ -841,18 +841,6 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         double* BS = AS + (size_t)21 * LD;            // N x 21, ld LD: [T1c | Rdiag K]
         double* P2 = BS + (size_t)21 * LD;            // N x B: P'' block
         EK2_PHASE(10);
-        // the special columns of G = P' - Z'Z that this CTA owns go to EVERY CTA's operand block (remote stores: fire and forget, they
-        // are complete at the cluster barrier below) -- the first version had every CTA fetch them after the barrier, a dependent
-        // round trip per element on everybody's path
-        {
-            int own[14], nown = 0;
-#pragma unroll
-            for (int cc = 0; cc < 14; cc++) { const int col = ek2_special_col(cc); if (col >= J0 && col < J0 + Bc) own[nown++] = cc; }
-            for (int t = tid; t < nown * C * N; t += EK2_NT) {
-                const int i = t % N, rest = t / N, q = rest % C, cc = own[rest / C];
-                cluster.map_shared_rank(AS, q)[i + (size_t)cc * LD] = PB[i + (size_t)(ek2_special_col(cc) - J0) * LD];
-            }
-        }
         for (int t = tid; t < N * 21; t += EK2_NT) {
             const int j = t % N, cc = t / N;
             if (cc < 14) {
@@ -866,6 +854,15 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
         EK2_PHASE(11);
         cluster.sync();                               // #4: all of G is final
         EK2_PHASE(12);
+        // (fetched by every CTA: letting the two owners PUSH their 7 columns each to all eight CTAs was measured slower, 4.6 us of remote
+        // stores on two CTAs against 1.0 us of remote loads on all of them, profiles/r02_ekf_phases_session_l.txt)
+        for (int t = tid; t < N * 14; t += EK2_NT) {
+            const int i = t % N, cc = t / N;
+            const int col = ek2_special_col(cc), r = col / B;
+            AS[i + (size_t)cc * LD] = cluster.map_shared_rank(PB, r)[i + (size_t)(col - r * B) * LD];
+        }
+        __syncthreads();
+        EK2_PHASE(13);
         ek2_dmma_gemm(N, Bc, 21, wrp, lane, AS, 1, LD, BS + J0, LD, 1,
                       [&](int i, int jj) {
                           const int j = J0 + jj;
