@@ -914,8 +914,10 @@ static int flush_checks(hv_ekf* e, const hv_ekf_op* ops, int first, int count, b
         if (rcj != HV_OK) return rcj;
         EkfUpdateArgs aug; augment_args(e, augDiscarded, augSym, aug);
         aug.noiseScale = e->noiseScale; aug.specP = e->b.P2; aug.specM = e->m2;
-        if (host) {
-            // results are wanted now: the augmentation is one more cluster of the checks' launch
+        // HV_EKF_NO_PDL=1 (throughput mode, many sessions per GPU): nothing is launched early or beside the main stream
+        static const bool latencyMode = getenv("HV_EKF_NO_PDL") == nullptr;
+        if (host || !latencyMode) {
+            // results are wanted now (or: one stream per session): the augmentation is one more cluster of the checks' launch
             HV_CUDA(ekf_launch_check_batch2(a, b, s, &aug));
         } else {
             // nothing goes back to the host: the checks leave the main stream altogether (fork -> side stream), the augmentation and

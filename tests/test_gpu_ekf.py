@@ -273,6 +273,20 @@ def test_predicted_mean_launch_matches_full_predict(cuda):
     a.close()
 
 
+def test_device_op_list_in_throughput_mode():
+    """HV_EKF_NO_PDL=1 (many sessions per GPU: nothing launched early, no side stream): the outlier checks of a device-resident list stay on
+    the main stream with the augmentation as one more cluster of their launch. Same list, same oracle comparison, in a child process
+    (the switch is read once per process)."""
+    import subprocess, sys
+    if os.environ.get("HV_EKF_NO_PDL"):
+        pytest.skip("already the child")
+    env = dict(os.environ, HV_EKF_NO_PDL="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "-m", "gpu", __file__, "-k",
+                          "test_device_op_list_matches_oracle or test_batch_submission_matches_single_calls or test_predicted_mean_launch"],
+                         capture_output=True, text=True, timeout=900, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-1500:] + out.stderr[-500:]
+
+
 def test_reference_catch2_suite_against_cuda_ekf():
     """The reference's OWN unit tests (test/ekf.cpp: chi-squared KAT, der_predict, tranformTo with test/data/P.csv,
     m.csv), compiled unmodified but linked against hybvio_b200/host/cuda_ekf.cpp instead of src/odometry/ekf.cpp
