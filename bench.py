@@ -717,6 +717,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device. hybvio_b200 has no CPU fallback; use --impl reference for the CPU arm.")
     torch.cuda.set_device(local)
+    os.environ["HV_DEVICE"] = str(local)              # the C++ adapters (e2e_adapter) work on this rank's GPU, not on GPU 0
     numa_node = pin_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -22,6 +22,7 @@
 // with the sparse 7 x 27 visAugH + symmetrisation: O(N^2) instead of the reference's O(N^3).
 // fp64 differences to the reference are rounding-order only (tests: relative 1e-9 on P, 1e-10 on m).
 #include "ekf.cuh"
+#include "hv_device_once.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -541,11 +542,10 @@ cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s)
     // 8-CTA cluster kernel (ekf_cluster2.cuh) whenever its shared-memory working set fits (n <= 84 at N = 160); the single-CTA
     // kernel below only for oversized measurements (batch updates with n up to N, tableau in global memory).
     if (ekf_update_uses_cluster2(a)) return ekf_launch_update_cluster2(a, s);
-    static bool attr = false;
-    if (!attr) {
+    static bool seen[64];                             // per device: function attributes belong to the device's context
+    if (hv_first_use_on_device(seen)) {
         cudaError_t e = cudaFuncSetAttribute(ekf_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     const size_t smem = a.op == EKF_OP_AUGMENT ? ekf_augment_smem_bytes(a.b.N) : a.useGlobalWork ? 0 : ekf_update_smem_bytes(a.n, a.b.N);
     ekf_update_kernel<<<1, EKF_NT, smem, s>>>(a);
@@ -553,11 +553,10 @@ cudaError_t ekf_launch_update(const EkfUpdateArgs& a, cudaStream_t s)
 }
 cudaError_t ekf_launch_predict(const EkfPredictArgs& a, cudaStream_t s)
 {
-    static bool attr = false;
-    if (!attr) {
+    static bool seen[64];
+    if (hv_first_use_on_device(seen)) {
         cudaError_t e = cudaFuncSetAttribute(ekf_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ekf_predict_smem_bytes(EKF_MAX_PREDICT));
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     // programmatic dependent launch (see ekf_cluster2.cu): the kernel may be scheduled while its predecessor on the stream still runs; it
     // waits in griddepcontrol.wait before it reads the state. HV_EKF_NO_PDL=1 switches it off.

@@ -1,6 +1,7 @@
 // hybvio_b200/csrc/ekf_cluster2.cu -- kernels and launchers of the second-generation cluster update (ekf_cluster2.cuh):
 // P column blocks resident in shared memory, all inter-CTA exchanges through distributed shared memory.
 #include <cooperative_groups.h>
+#include "hv_device_once.cuh"
 #include <math.h>
 #include <stdlib.h>
 namespace cg = cooperative_groups;
@@ -79,8 +80,8 @@ static cudaError_t ek2_prepare(K kernel, int C, size_t staticSmem = EK2_STATIC_S
 cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s)
 {
     const int C = ek2_cluster_size_for(a.n, false);
-    static bool ready = false;
-    if (!ready) { cudaError_t e = ek2_prepare(ekf_update_cluster2_kernel, C); if (e != cudaSuccess) return e; ready = true; }
+    static bool seen[64];                             // per device (hv_common.cuh)
+    if (hv_first_use_on_device(seen)) { cudaError_t e = ek2_prepare(ekf_update_cluster2_kernel, C); if (e != cudaSuccess) return e; }
     const size_t smem = ek2_smem_bytes(a.n, a.l, a.b.N, a.op == EKF_OP_AUGMENT, C);
     return ek2_launch(ekf_update_cluster2_kernel, C, 1, smem, s, a);
 }
@@ -88,8 +89,8 @@ cudaError_t ekf_launch_update_cluster2(const EkfUpdateArgs& a, cudaStream_t s)
 cudaError_t ekf_launch_check_batch2(const EkfUpdateArgs& a, const EkfCheckBatch& b, cudaStream_t s, const EkfUpdateArgs* aug)
 {
     const int C = ek2_cluster_size();
-    static bool ready = false;
-    if (!ready) { cudaError_t e = ek2_prepare(ekf_check_batch_cluster2_kernel, C); if (e != cudaSuccess) return e; ready = true; }
+    static bool seen[64];
+    if (hv_first_use_on_device(seen)) { cudaError_t e = ek2_prepare(ekf_check_batch_cluster2_kernel, C); if (e != cudaSuccess) return e; }
     size_t smem = 0;
     for (int i = 0; i < b.count; i++) { const size_t v = ek2_smem_bytes(b.it[i].n, b.it[i].l, a.b.N, false, C); if (v > smem) smem = v; }
     if (aug) { const size_t v = ek2_smem_bytes(aug->n, aug->l, a.b.N, true, C); if (v > smem) smem = v; }

@@ -496,6 +496,7 @@ size_t hv_pyr_smem_bytes(int nlevels)
 }
 
 // ---- TMA descriptors (host): cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
+#include "hv_device_once.cuh"
 #include <cuda.h>
 typedef CUresult (*PyrEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -530,12 +531,11 @@ cudaError_t hv_launch_pyr_fused(const HvPyrDesc* table, const unsigned short* id
                                 const uint8_t* const* level0, const int* level0Pitch, const int* nlevels,
                                 int n, int w0, int h0, int maxNlevels, cudaStream_t stream)
 {
-    static bool attrSet = false;
+    static bool seen[64];                             // per device (hv_common.cuh)
     size_t smem = hv_pyr_smem_bytes(maxNlevels);
-    if (!attrSet) {
+    if (hv_first_use_on_device(seen)) {
         cudaError_t e = cudaFuncSetAttribute(hv_pyr_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attrSet = true;
     }
     for (int base = 0; base < n; base += PYR_MAX_BATCH) {
         PyrBuildList list;

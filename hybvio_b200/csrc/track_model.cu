@@ -2,6 +2,7 @@
 // device (one CTA per track; body and algorithm notes in track_model.cuh). Replaces, for the EKF's visual updates, the host
 // sequence extractCameraPoseTrail -> Triangulator::triangulate -> prepareVisualUpdate of src/odometry/backend.cpp:1050-1160.
 #include "track_model.cuh"
+#include "hv_device_once.cuh"
 #include <stdlib.h>
 
 __global__ void __launch_bounds__(TM_NT, 2) hv_track_model_kernel(TmArgs a)
@@ -12,11 +13,10 @@ __global__ void __launch_bounds__(TM_NT, 2) hv_track_model_kernel(TmArgs a)
 
 cudaError_t tm_launch(const TmArgs& a, cudaStream_t s)
 {
-    static bool attr = false;
-    if (!attr) {
+    static bool seen[64];                             // per device (hv_common.cuh)
+    if (hv_first_use_on_device(seen)) {
         cudaError_t e = cudaFuncSetAttribute(hv_track_model_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm_smem_bytes());
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     static const bool pdlAllowed = getenv("HV_EKF_NO_PDL") == nullptr;
     if (a.pdl && pdlAllowed) {
