@@ -287,6 +287,30 @@ def test_device_op_list_in_throughput_mode():
     assert out.returncode == 0 and " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-1500:] + out.stderr[-500:]
 
 
+def test_second_device_gets_its_own_function_attributes():
+    """Kernel function attributes (dynamic shared memory limit, cluster size) belong to a device's context: a process that uses the filter
+    on GPU 0 and then on GPU 1 must set them again (round 2: a torchrun rank failed its first launch on the second device). Needs 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from hybvio_b200 import capi
+    p = C.params_with(default_params, 20)
+    rng = np.random.RandomState(3)
+    H, f, y = ekf_script.visual_measurement(rng, 20, 160, 0.02)
+    results = []
+    for dev in (0, 1):
+        hv = capi.Context(dev)
+        e = capi.Ekf(hv, p)
+        e.initialize_orientation([0.1, 0.2, 9.8])
+        for s_ in range(10):
+            e.predict(0.005 * (s_ + 1), [0.01, 0.02, 0.2], [0.1, 0.2, 9.8]); e.normalize_quaternions(True)
+        e.visual_update(np.asfortranarray(H), f, y, ekf_script.VISUAL_R)
+        e.symmetrize(); e.augment(-1)
+        results.append(e.download())
+        e.close(); hv.close()
+    assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][1], results[1][1])
+
+
 def test_reference_catch2_suite_against_cuda_ekf():
     """The reference's OWN unit tests (test/ekf.cpp: chi-squared KAT, der_predict, tranformTo with test/data/P.csv,
     m.csv), compiled unmodified but linked against hybvio_b200/host/cuda_ekf.cpp instead of src/odometry/ekf.cpp
