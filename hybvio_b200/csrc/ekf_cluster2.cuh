@@ -38,6 +38,11 @@
 #endif
 
 struct Ek2Geom { int C, B, X, W, T, PB, RS, EXTRA, SYM, oneStage, LD; };
+#ifndef EK2_ODD_W                                     // (tools/: -DEK2_ODD_W measures the former layout)
+__host__ __device__ inline int ek2_pad4mod16(int w) { return w + ((20 - (w & 15)) & 15); }
+#else
+__host__ __device__ inline int ek2_pad4mod16(int w) { return w | 1; }
+#endif
 __host__ __device__ inline Ek2Geom ek2_geom(int n, int l, int N, bool joseph, int C)
 {
     Ek2Geom g;
@@ -48,7 +53,11 @@ __host__ __device__ inline Ek2Geom ek2_geom(int n, int l, int N, bool joseph, in
     // (never N itself: column N of the gathered Z holds z_v for the CTA that updates the state mean)
     g.LD = N + (((20 - (N & 15)) & 15) ? ((20 - (N & 15)) & 15) : 16);
     g.X = n * (l > g.LD ? l : g.LD);                        // H (n x l, ld n), later the gathered Z (n x N, ld LD)
-    g.W = (n + g.B + 1 + (joseph ? n : 0)) | 1;             // tableau row: [S | HP_J | v | (I)]
+    // tableau row [S | HP_J | v | (I)], padded to = 4 (mod 16) doubles like LD: every fragment load of the products that read the
+    // tableau (8 rows x 4 consecutive columns, or 4 rows x 8 columns, per half-warp) then touches 16 distinct 8-byte banks. Round 1
+    // used an odd width: 2- to 3-way conflicts, and the partial S product (A operand = the HP part of the tableau) ran at a third
+    // of the tensor rate (tools/ubench_gemm.cu)
+    g.W = ek2_pad4mod16(n + g.B + 1 + (joseph ? n : 0));
     g.T = (n * g.W + 1) & ~1;                               // even: the P block behind the tableau starts on a 16-byte boundary (bulk copies)
     g.PB = g.LD * g.B;                                      // own column block of P, ld LD
     const int MTn = (n + 7) >> 3;
@@ -694,7 +703,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     if (a.Rdiag2 > 0.0 && a.mode == EKF_MODE_CHECK_UPDATE && a.op == EKF_OP_DENSE && !a.skipChi2) {
         // ---- check and update with different R: chi2 from a small tableau [S0 + R_check | v] in the region H occupied (dead since
         // phase B, not exposed to the cluster), every CTA for itself; the big tableau gets S0 + R_update and is eliminated below
-        const int W2 = (n + 1) | 1;
+        const int W2 = min(ek2_pad4mod16(n + 1), max(l, LD));       // (fits the region H occupied: n rows of max(l, LD) doubles)
         double* Xc = X;
         for (int e = tid; e < n * n; e += EK2_NT) Xc[(size_t)(e / n) * W2 + (e % n)] = T[(size_t)(e / n) * W + (e % n)];
         for (int i = tid; i < n; i += EK2_NT) Xc[(size_t)i * W2 + n] = T[(size_t)i * W + vcol];

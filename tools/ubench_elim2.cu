@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(512) k_elim(const double* Tin, double* Tout, i
 int main()
 {
     for (int n : {8, 20, 40, 84}) {
-        const int B = 20, ncols = n + B + 1, W = ncols | 1;
+        const int B = 20, ncols = n + B + 1, W = ek2_pad4mod16(ncols);
         std::vector<double> M((size_t)n * n), T((size_t)n * W, 0.0);
         srand(1);
         for (auto& x : M) x = rand() / (double)RAND_MAX - 0.5;
