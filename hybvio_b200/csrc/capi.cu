@@ -68,6 +68,7 @@ int hv_ctx_destroy(hv_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream || !c->ownStream) cudaStreamSynchronize(c->stream);
     if (c->sideStream) { cudaStreamSynchronize(c->sideStream); cudaStreamDestroy(c->sideStream); }
+    if (c->covStream) { cudaStreamSynchronize(c->covStream); cudaStreamDestroy(c->covStream); }
     if (c->d_table) cudaFree(c->d_table);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -84,6 +85,7 @@ int hv_ctx_sync(hv_ctx* c)
     if (!c) { hv_set_error("hv_ctx_sync: NULL ctx"); return HV_ERR_INVALID; }
     HV_CUDA(cudaStreamSynchronize(c->stream));
     if (c->sideStream) HV_CUDA(cudaStreamSynchronize(c->sideStream));
+    if (c->covStream) HV_CUDA(cudaStreamSynchronize(c->covStream));
     return HV_OK;
 }
 void* hv_ctx_stream(hv_ctx* c) { return c ? (void*)c->stream : nullptr; }
@@ -306,7 +308,7 @@ static int lk_check_pair(const char* who, hv_ctx* c, hv_pyr* a, hv_pyr* b)
     return HV_OK;
 }
 
-int hv_lk_track_batch_device(hv_ctx* c, const hv_lk_job* jobs, int njobs, int maxIter, double eps, double minEig)
+static int lk_track_batch_device_on(hv_ctx* c, cudaStream_t stream, const hv_lk_job* jobs, int njobs, int maxIter, double eps, double minEig)
 {
     if (!c || !jobs || njobs < 0) { hv_set_error("hv_lk_track_batch_device: invalid argument"); return HV_ERR_INVALID; }
     HV_CUDA(cudaSetDevice(c->device));
@@ -330,16 +332,20 @@ int hv_lk_track_batch_device(hv_ctx* c, const hv_lk_job* jobs, int njobs, int ma
         }
         L.njobs = cnt;
         lk_fill(L, c, maxLevel, maxIter, eps, minEig);
-        cudaError_t e = hv_launch_lk(L, win, c->stream);
+        cudaError_t e = hv_launch_lk(L, win, stream);
         if (e == cudaErrorInvalidValue) { hv_set_error("hv_lk_track: window size %d unsupported (supported: 11, 15, 21, 31)", win); return HV_ERR_UNSUPPORTED; }
         HV_CUDA(e);
         c->launches += 1;
     }
     return HV_OK;
 }
+int hv_lk_track_batch_device(hv_ctx* c, const hv_lk_job* jobs, int njobs, int maxIter, double eps, double minEig)
+{
+    return lk_track_batch_device_on(c, c ? c->stream : nullptr, jobs, njobs, maxIter, eps, minEig);
+}
 
-int hv_lk_track_device(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* dPrev, float* dNext, uint8_t* dStatus,
-                       int32_t* dTs, int n, int useInitial, int maxIter, double eps, double minEig)
+static int lk_track_device_on(hv_ctx* c, cudaStream_t stream, hv_pyr* prev, hv_pyr* next, const float* dPrev, float* dNext, uint8_t* dStatus,
+                              int32_t* dTs, int n, int useInitial, int maxIter, double eps, double minEig)
 {
     if (!c || n < 0) { hv_set_error("hv_lk_track_device: invalid argument"); return HV_ERR_INVALID; }
     if (n == 0) {                 // optical_flow.cpp:41-44: empty input, empty output (the pyramids are still validated)
@@ -348,7 +354,17 @@ int hv_lk_track_device(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* dPrev
     }
     hv_lk_job j; j.prev = prev; j.next = next; j.d_prev_xy = dPrev; j.d_next_xy = dNext; j.d_status = dStatus;
     j.d_track_status = dTs; j.n = n; j.use_initial = useInitial;
-    return hv_lk_track_batch_device(c, &j, 1, maxIter, eps, minEig);
+    return lk_track_batch_device_on(c, stream, &j, 1, maxIter, eps, minEig);
+}
+int hv_lk_track_device(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* dPrev, float* dNext, uint8_t* dStatus,
+                       int32_t* dTs, int n, int useInitial, int maxIter, double eps, double minEig)
+{
+    return lk_track_device_on(c, c ? c->stream : nullptr, prev, next, dPrev, dNext, dStatus, dTs, n, useInitial, maxIter, eps, minEig);
+}
+int hv_lk_track_device_on_stream(hv_ctx* c, void* cudaStream, hv_pyr* prev, hv_pyr* next, const float* dPrev, float* dNext, uint8_t* dStatus,
+                                 int32_t* dTs, int n, int useInitial, int maxIter, double eps, double minEig)
+{
+    return lk_track_device_on(c, (cudaStream_t)cudaStream, prev, next, dPrev, dNext, dStatus, dTs, n, useInitial, maxIter, eps, minEig);
 }
 
 int hv_lk_track(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* prevXY, float* nextXY, uint8_t* status,

@@ -34,6 +34,7 @@ struct hv_ctx {
     // Side stream for work that the main stream need not wait for (created on first use; ekf_capi.cu: outlier checks of a device-resident
     // op list). hv_ctx_sync waits for both.
     cudaStream_t sideStream = nullptr;
+    cudaStream_t covStream = nullptr;   // full launch of an IMU burst whose mean part went ahead (ekf_capi.cu: predict_launch)
 };
 
 struct hv_pyr {

@@ -41,6 +41,11 @@ struct hv_ekf {
     // the state, the augmentation writes the second buffers, so nothing that follows on the main stream has to wait for them);
     // they are joined before the next writer of the second buffers and before anything that hands results to the host
     cudaEvent_t evFork = nullptr, evJoin = nullptr;       // (the stream itself belongs to the context: hv_ctx::sideStream)
+    // After hv_ekf_predicted_mean_device the full launch of the IMU burst (covariance) goes to a stream of its own (hv_ctx::covStream):
+    // whatever the caller issues next on the context's stream without touching the filter (the optical flow, when tracker and filter
+    // share a stream) does not queue behind it; the next call that touches the filter joins it
+    cudaEvent_t evCovFork = nullptr, evCov = nullptr;
+    bool covBusy = false, meanIssued = false;
     bool sideBusy = false;
     double* cworkSide = nullptr;            // exchange areas and result words of the clusters on the side stream
     double* resSide = nullptr;
@@ -287,6 +292,9 @@ int hv_ekf_destroy(hv_ekf* e)
     for (cudaEvent_t ev : e->copyEvents) cudaEventDestroy(ev);
     if (e->copyStream) cudaStreamDestroy(e->copyStream);
     if (e->ctx->sideStream) cudaStreamSynchronize(e->ctx->sideStream);
+    if (e->ctx->covStream) cudaStreamSynchronize(e->ctx->covStream);
+    if (e->evCovFork) cudaEventDestroy(e->evCovFork);
+    if (e->evCov) cudaEventDestroy(e->evCov);
     if (e->evFork) cudaEventDestroy(e->evFork);
     if (e->evJoin) cudaEventDestroy(e->evJoin);
     if (e->evStaged) cudaEventDestroy(e->evStaged);
@@ -450,12 +458,38 @@ static void predict_bookkeep(hv_ekf* e, double t, const double xg[3], const doub
     }
 }
 
+static int join_cov(hv_ekf* e)
+{
+    if (!e->covBusy) return HV_OK;
+    HV_CUDA(cudaStreamWaitEvent(e->ctx->stream, e->evCov, 0));
+    e->covBusy = false;
+    return HV_OK;
+}
 static int predict_launch(hv_ekf* e, EkfPredictArgs& a)
 {
     if (a.count == 0) return HV_OK;
     a.b = e->b; a.gravity = e->prm.gravity;
     e->epoch++;
-    HV_CUDA(ekf_launch_predict(a, e->ctx->stream));
+    static const bool latencyMode = getenv("HV_EKF_NO_PDL") == nullptr;
+    if (e->meanIssued && latencyMode) {
+        // the mean of this burst is out already (hv_ekf_predicted_mean_device): the full launch runs beside the context's stream
+        hv_ctx* c = e->ctx;
+        if (!c->covStream) HV_CUDA(cudaStreamCreateWithFlags(&c->covStream, cudaStreamNonBlocking));
+        if (!e->evCov) {
+            HV_CUDA(cudaEventCreateWithFlags(&e->evCovFork, cudaEventDisableTiming));
+            HV_CUDA(cudaEventCreateWithFlags(&e->evCov, cudaEventDisableTiming));
+        }
+        HV_CUDA(cudaEventRecord(e->evCovFork, c->stream));        // behind everything issued so far (earlier filter work, the mean launch)
+        HV_CUDA(cudaStreamWaitEvent(c->covStream, e->evCovFork, 0));
+        HV_CUDA(ekf_launch_predict(a, c->covStream));
+        HV_CUDA(cudaEventRecord(e->evCov, c->covStream));
+        e->covBusy = true;
+    } else {
+        int rc = join_cov(e);
+        if (rc != HV_OK) return rc;
+        HV_CUDA(ekf_launch_predict(a, e->ctx->stream));
+    }
+    e->meanIssued = false;
     e->ctx->launches++;
     a.count = 0;
     return HV_OK;
@@ -466,6 +500,8 @@ static int flush_sym(hv_ekf* e)
 {
     if (!e->pendSym) return HV_OK;
     e->pendSym = false;
+    int rc = join_cov(e);
+    if (rc != HV_OK) return rc;
     return launch_ew(e, EKF_EW_SYMMETRIZE);
 }
 // At most one kind of work is pending at a time (predict() issues a pending symmetrisation first, symmetrize() issues
@@ -473,6 +509,8 @@ static int flush_sym(hv_ekf* e)
 static int flush_pending(hv_ekf* e)
 {
     int rc = flush_predicts(e);
+    if (rc != HV_OK) return rc;
+    rc = join_cov(e);                                  // the caller is about to touch the filter on the context's stream
     if (rc != HV_OK) return rc;
     return flush_sym(e);
 }
@@ -491,7 +529,9 @@ int hv_ekf_predicted_mean_device(hv_ekf* e, double* dMean20)
 {
     EKF_ENTER_LAZY(e, "hv_ekf_predicted_mean_device");
     if (!dMean20) { hv_set_error("hv_ekf_predicted_mean_device: NULL output"); return HV_ERR_INVALID; }
-    int rc = flush_sym(e);
+    int rc = join_cov(e);                                         // (a covariance launch of an earlier burst writes the mean as well)
+    if (rc != HV_OK) return rc;
+    rc = flush_sym(e);
     if (rc != HV_OK) return rc;
     cudaStream_t s = e->ctx->stream;
     if (e->pend.count == 0) {                                     // nothing queued: the state as it is
@@ -502,12 +542,16 @@ int hv_ekf_predicted_mean_device(hv_ekf* e, double* dMean20)
     a.b = e->b; a.gravity = e->prm.gravity; a.meanOut = dMean20;
     HV_CUDA(ekf_launch_predict(a, s));
     e->ctx->launches++;
+    e->meanIssued = true;
     return HV_OK;
 }
 
 int hv_ekf_flush(hv_ekf* e)
 {
-    EKF_ENTER(e, "hv_ekf_flush");
+    EKF_ENTER_LAZY(e, "hv_ekf_flush");
+    int rc = flush_predicts(e);                        // (may go to the covariance stream: not joined here, see join_cov)
+    if (rc != HV_OK) return rc;
+    if (e->pendSym) { rc = join_cov(e); if (rc != HV_OK) return rc; return flush_sym(e); }
     return HV_OK;
 }
 
@@ -773,6 +817,7 @@ int hv_ekf_augment(hv_ekf* e, int discarded)
 {
     EKF_ENTER_LAZY(e, "hv_ekf_augment");
     int rcf = flush_predicts(e);
+    if (rcf == HV_OK) rcf = join_cov(e);
     if (rcf != HV_OK) return rcf;
     if (discarded == -1) discarded = e->trail - 1;               // ekf.cpp:849
     if (discarded < 0 || discarded >= e->trail) { hv_set_error("hv_ekf_augment: pose index %d out of range", discarded); return HV_ERR_INVALID; }

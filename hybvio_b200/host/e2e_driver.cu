@@ -97,9 +97,10 @@ static int e2e_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, cons
 }
 
 // ---- device-resident loop (bench.py's `value`): the same frame as above with every input already in HBM and no host
-// synchronisation; tracker and EKF on their own streams with the real dependencies as events (LK(k) after the IMU burst of frame k:
-// the flow predictor reads the propagated pose and the pose trail, src/odometry/backend.cpp:547-600 via src/tracker/tracker.cpp:59-63;
-// visual updates(k) after LK(k)). A native caller keeps the launch rate independent of the Python interpreter of the harness.
+// synchronisation. Dependencies (LK(k) after the mean propagation of frame k: the flow predictor reads the propagated pose and the pose
+// trail, src/odometry/backend.cpp:547-600 via src/tracker/tracker.cpp:59-63; visual updates(k) after LK(k); next propagation after the
+// augmentation) are stream order on ONE stream; what does not depend on them runs beside it. A native caller keeps the launch rate
+// independent of the Python interpreter of the harness.
 typedef struct hv_dev_frame {
     const uint8_t* left; const uint8_t* right;   // device gray images
     size_t stride;
@@ -111,49 +112,52 @@ typedef struct hv_dev_frame {
 int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const float* d_points, float* d_next, float* d_next2,
                uint8_t* d_status, int32_t* d_ts, int n, const hv_dev_frame* frames, int nframes, float* elapsed_ms)
 {
+    // Stream sa (the tracker context's): pyramid builds only. Stream sb (the filter context's): the WHOLE dependent chain of a frame --
+    // mean propagation -> optical flow (hv_lk_track_device_on_stream) -> visual updates -> augmentation -- so that no step of it waits
+    // for a cross-stream event that has not fired long ago. Beside it, on streams of the library: the covariance part of the IMU burst
+    // and the outlier checks that precede the augmentation.
     hv_pyr* p[4] = {pyr[0], pyr[1], pyr[2], pyr[3]};
     cudaStream_t sa = (cudaStream_t)hv_ctx_stream(trk), sb = (cudaStream_t)hv_ctx_stream(ekf_ctx);
-    cudaEvent_t e0, e1, evLk, evEkf;
+    cudaEvent_t e0, e1, evPyr, evLk;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventCreateWithFlags(&evLk, cudaEventDisableTiming); cudaEventCreateWithFlags(&evEkf, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&evPyr, cudaEventDisableTiming); cudaEventCreateWithFlags(&evLk, cudaEventDisableTiming);
     hv_ctx_sync(trk); hv_ctx_sync(ekf_ctx);
     double* d_mean = nullptr;
     if (cudaMalloc(&d_mean, 20 * sizeof(double)) != cudaSuccess) return HV_ERR_OOM;
-    cudaEventRecord(e0, sa);
+    cudaEventRecord(e0, sb);
+    cudaEventRecord(evLk, sb);
     int rc = HV_OK, lastOps = 0;
     for (int k = 0; k < nframes && rc == HV_OK; k++) {
         const hv_dev_frame& f = frames[k];
         hv_pyr* cur[2] = {p[2], p[3]};
         const uint8_t* img[2] = {f.left, f.right};
         const size_t strides[2] = {f.stride, f.stride};
-        rc = hv_pyr_build_batch(cur, img, strides, f.right ? 2 : 1, 1);          // A: no dependency
+        cudaStreamWaitEvent(sa, evLk, 0);                                      // the pyramids about to be rebuilt were read by the previous frame's optical flow
+        rc = hv_pyr_build_batch(cur, img, strides, f.right ? 2 : 1, 1);          // A: depends on nothing else
         if (rc != HV_OK) break;
+        cudaEventRecord(evPyr, sa);
         rc = hv_ekf_run_device(ekf, f.ops, f.nimu);                            // B: IMU burst (queued) ...
-        if (rc == HV_OK) rc = hv_ekf_predicted_mean_device(ekf, d_mean);       // ... its mean part first: all the flow predictor reads
+        if (rc == HV_OK) rc = hv_ekf_predicted_mean_device(ekf, d_mean);       // ... its mean part first: all the flow predictor reads ...
+        if (rc == HV_OK) rc = hv_ekf_flush(ekf);                               // ... the full launch (covariance) on the library's own stream
         if (rc != HV_OK) break;
-        cudaEventRecord(evEkf, sb);
-        rc = hv_ekf_flush(ekf);                                                // ... then the full launch (covariance), beside the tracker
+        cudaMemcpyAsync(d_next, f.d_init_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToDevice, sb);     // (the predictor's output)
+        cudaStreamWaitEvent(sb, evPyr, 0);                                     // issued a whole frame of filter work ago: has fired
+        rc = hv_lk_track_device_on_stream(trk, sb, p[0], cur[0], d_points, d_next, d_status, d_ts, n, 1, 20, 0.03, 1e-3);
+        if (rc == HV_OK && f.right) rc = hv_lk_track_device_on_stream(trk, sb, cur[0], cur[1], d_next, d_next2, d_status, d_ts, n, 0, 20, 0.03, 1e-3);
         if (rc != HV_OK) break;
-        cudaStreamWaitEvent(sa, evEkf, 0);                                     // the flow predictor reads the pose propagated to this frame
-        cudaMemcpyAsync(d_next, f.d_init_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToDevice, sa);
-        rc = hv_lk_track_device(trk, p[0], cur[0], d_points, d_next, d_status, d_ts, n, 1, 20, 0.03, 1e-3);
-        if (rc == HV_OK && f.right) rc = hv_lk_track_device(trk, cur[0], cur[1], d_next, d_next2, d_status, d_ts, n, 0, 20, 0.03, 1e-3);
-        if (rc != HV_OK) break;
-        cudaEventRecord(evLk, sa);
-        cudaStreamWaitEvent(sb, evLk, 0);                                      // visual updates need the tracks
-        rc = hv_ekf_run_device(ekf, f.ops + f.nimu, f.nops - f.nimu);
+        cudaEventRecord(evLk, sb);
+        rc = hv_ekf_run_device(ekf, f.ops + f.nimu, f.nops - f.nimu);         // joins the covariance launch, then the visual updates
         if (rc == HV_OK) rc = hv_ekf_flush(ekf);
         lastOps = f.nops - f.nimu;
         hv_pyr* q0 = p[0]; hv_pyr* q1 = p[1]; p[0] = p[2]; p[1] = p[3]; p[2] = q0; p[3] = q1;
     }
     // the last frame's decisions come back to the host (this also waits for the outlier checks the library issued on its side stream)
     if (rc == HV_OK && lastOps > 0) { std::vector<int> vu(lastOps); std::vector<double> chi2(lastOps); rc = hv_ekf_run_device_results(ekf, lastOps, vu.data(), chi2.data()); }
-    cudaEventRecord(evEkf, sb);
-    cudaStreamWaitEvent(sa, evEkf, 0);
-    cudaEventRecord(e1, sa);
+    cudaStreamWaitEvent(sb, evPyr, 0);
+    cudaEventRecord(e1, sb);
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(elapsed_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(evLk); cudaEventDestroy(evEkf);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(evLk); cudaEventDestroy(evPyr);
     cudaFree(d_mean);
     for (int i = 0; i < 4; i++) pyr[i] = p[i];
     return rc;

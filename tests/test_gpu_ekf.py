@@ -264,13 +264,29 @@ def test_predicted_mean_launch_matches_full_predict(cuda):
         a.predicted_mean_device(d.data_ptr())
         torch.cuda.synchronize()
         pred = d.cpu().numpy().copy()
-        m1, P1 = a.download()                   # issues the queued full launch
+        if burst == 2:
+            a.flush()                           # the full launch goes to the covariance stream; the download below joins it
+        m1, P1 = a.download()                   # issues the queued full launch (or waits for it)
         assert np.array_equal(pred, m1[:20]), np.abs(pred - m1[:20]).max()
         assert not np.array_equal(m0[:10], m1[:10]) and not np.array_equal(P0, P1)
     a.predicted_mean_device(d.data_ptr())       # nothing queued: the state as it is
     torch.cuda.synchronize()
     assert np.array_equal(d.cpu().numpy(), a.download()[0][:20])
-    a.close()
+    # the same bursts without the mean launch must leave the same state (covariance stream or not: one result)
+    b = cuda(p)
+    b.initialize_orientation(ekf_script.imu_sample(np.random.RandomState(1), 0)[1])
+    rng2, t2 = np.random.RandomState(21), 0.0
+    for burst in range(3):
+        for s_ in range(10):
+            t2 += 0.005
+            g, acc = ekf_script.imu_sample(rng2, s_ + 1)
+            b.predict(t2, g, acc)
+            if burst != 1:
+                b.normalize_quaternions(True)
+        b.flush()
+    ma, Pa = a.download(); mb, Pb = b.download()
+    assert np.array_equal(ma, mb) and np.array_equal(Pa, Pb)
+    a.close(); b.close()
 
 
 def test_device_op_list_in_throughput_mode():
