@@ -864,7 +864,7 @@ def run_ours(args):
                                    f"20 checks (5 with update, n = {'/'.join(map(str, N_ROWS))} rows) + symmetrise + augment; independent sessions, " + str(nsess) + " per GPU",
                        "baseline_config": CONFIG_ID, "host_numa_node_pinned": numa_node,
                        "sessions_per_gpu": nsess,
-                       "streams": "2 per session (tracker / EKF) with event dependencies: LK(k) after the IMU burst of frame k (the flow predictor reads the propagated state), visual updates(k) after LK(k); outlier checks that precede the augmentation on the library side stream",
+                       "streams": "per session: pyramid builds on the tracker stream; mean propagation -> LK(k) -> visual updates(k) -> augmentation in stream order on the filter stream (the flow predictor reads the propagated pose); covariance propagation and the outlier checks that precede the augmentation on streams of the library",
                        "l2": f"inputs cycled through pools larger than L2 (frames {POOL_FRAMES * 2 * W * H / 1e6:.0f} MB + EKF inputs "
                              f"{POOL_EKF * inputs.ekf_stride * 8 / 1e6:.0f} MB > 126 MB); no explicit flush",
                        "ekf_healthy_after_run": healthy},
