@@ -327,6 +327,114 @@ def test_second_device_gets_its_own_function_attributes():
     assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][1], results[1][1])
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_mix_of_asynchronous_paths_matches_oracle(cuda, oracle_lk, seed):
+    """Everything that runs beside the context's stream in one randomised sequence -- mean launches with the covariance on its own stream,
+    device lists whose outlier checks go to the side stream while the augmentation writes the second buffers, host lists (augmentation in
+    the checks' launch), speculative updates behind single checks, un-augmentation / transformTo (writers of the second buffers), clone,
+    per-op results -- against the oracle issuing the same calls one by one."""
+    import torch
+    from hybvio_b200 import capi
+    from oracle import ekf_oracle
+    p = C.params_with(default_params, 6)
+    a, b = cuda(p), ekf_oracle.OracleEKF(p)
+    rng, irng = np.random.RandomState(100 + seed), np.random.RandomState(200 + seed)
+    acc0 = ekf_script.imu_sample(np.random.RandomState(1), 0)[1]
+    a.initialize_orientation(acc0); b.initialize_orientation(acc0)
+    N, t = a.N, 0.0
+    d_mean = torch.zeros(20, dtype=torch.float64, device="cuda")
+    keep_dev = []
+
+    def burst(mean_first):
+        nonlocal t
+        for s_ in range(int(rng.randint(3, 11))):
+            t += 0.005
+            g, acc = ekf_script.imu_sample(irng, s_ + 1)
+            a.predict(t, g, acc); b.predict(t, g, acc)
+            if rng.rand() < 0.8:
+                a.normalize_quaternions(True); b.normalize_quaternions(True)
+        if mean_first:
+            a.predicted_mean_device(d_mean.data_ptr())
+            if rng.rand() < 0.7:
+                a.flush()
+
+    def meas(n, gross=False):
+        H, f, y = ekf_script.visual_measurement(rng, n, N, 40.0 if gross else 0.02)
+        return np.asfortranarray(H), np.ascontiguousarray(f), np.ascontiguousarray(y)
+
+    def oracle_visual(H, f, y, mode):
+        s_, c_ = b.visual_check(H, f, y, ekf_script.VISUAL_R) if mode != 1 else (0, 0.0)
+        if mode == 1 or (mode == 2 and s_ == 0):
+            b.visual_update(H, f, y, ekf_script.VISUAL_R)
+        return s_, c_
+
+    def compare(tag):
+        (ma, Pa), (mb, Pb) = a.download(), b.download()
+        assert np.abs(ma - mb).max() < C.TOL_M and ekf_script.rel_err(Pa, Pb) < C.TOL_P_REL, tag
+        assert a.pose_count() == b.pose_count(), tag
+
+    for step in range(30):
+        kind = rng.choice(["device_list", "host_list", "single", "structure", "clone"], p=[0.4, 0.2, 0.2, 0.15, 0.05])
+        burst(mean_first=rng.rand() < 0.6)
+        if kind in ("device_list", "host_list"):
+            nvis = int(rng.randint(2, 7))
+            with_aug = rng.rand() < 0.8
+            ops = (capi.EkfOp * (nvis + 2))()
+            exp, k = [], 0
+            for c in range(nvis):
+                H, f, y = meas(int(rng.choice([4, 8, 13, 20])), gross=rng.rand() < 0.25)
+                mode = 2 if c < 2 else 0
+                n_, l_ = H.shape
+                op = ops[k]
+                op.kind, op.n, op.l, op.mode, op.r, op.rmse_thr = capi.OP_VISUAL, n_, l_, mode, ekf_script.VISUAL_R, -1.0
+                if kind == "device_list":
+                    d = torch.from_numpy(np.concatenate([H.ravel(order="F"), f, y])).cuda(); keep_dev.append(d)
+                    op.H, op.f, op.y = d.data_ptr(), d.data_ptr() + 8 * n_ * l_, d.data_ptr() + 8 * (n_ * l_ + n_)
+                else:
+                    keep_dev += [H, f, y]
+                    op.H, op.f, op.y = H.ctypes.data, f.ctypes.data, y.ctypes.data
+                exp.append((k,) + oracle_visual(H, f, y, mode)); k += 1
+            if with_aug:
+                ops[k].kind = capi.OP_SYMMETRIZE; k += 1
+                ops[k].kind, ops[k].index = capi.OP_AUGMENT, -1; k += 1
+                b.symmetrize(); b.augment(-1)
+            torch.cuda.synchronize()
+            if kind == "device_list":
+                a.run_device(ops, k)
+                if rng.rand() < 0.5:
+                    st, chi2 = a.run_device_results(k)
+                else:
+                    st = None
+            else:
+                st, chi2, _ = a.run_host(ops, k)
+            if st is not None:
+                for i, s_, c_ in exp:
+                    assert st[i] == s_, (step, kind, i)
+                    assert abs(chi2[i] - c_) <= 1e-8 * max(1.0, abs(c_)), (step, kind, i)
+        elif kind == "single":
+            for c in range(int(rng.randint(1, 4))):
+                H, f, y = meas(int(rng.choice([4, 8, 20])), gross=rng.rand() < 0.3)
+                sa, ca = a.visual_check(H, f, y, ekf_script.VISUAL_R)
+                so, co = b.visual_check(H, f, y, ekf_script.VISUAL_R)
+                assert sa == so and abs(ca - co) <= 1e-8 * max(1.0, abs(co)), (step, c)
+                if so == 0 and rng.rand() < 0.7:                  # the speculative update is adopted ...
+                    a.visual_update(H, f, y, ekf_script.VISUAL_R); b.visual_update(H, f, y, ekf_script.VISUAL_R)
+        elif kind == "structure":
+            if a.pose_count() > 2 and rng.rand() < 0.5:
+                a.unaugment(); b.unaugment()
+            else:
+                a.symmetrize(); a.augment(-1); b.symmetrize(); b.augment(-1)
+        else:
+            ca = a.clone()
+            assert np.array_equal(ca.download()[0], a.download()[0])
+            ca.close()
+        if rng.rand() < 0.5:
+            compare(f"step {step} ({kind})")
+    compare("end")
+    torch.cuda.synchronize()
+    a.close(); b.close()
+
+
 def test_reference_catch2_suite_against_cuda_ekf():
     """The reference's OWN unit tests (test/ekf.cpp: chi-squared KAT, der_predict, tranformTo with test/data/P.csv,
     m.csv), compiled unmodified but linked against hybvio_b200/host/cuda_ekf.cpp instead of src/odometry/ekf.cpp
