@@ -107,7 +107,7 @@ def load():
     lib.hv_pyr_download_level_padded.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
     lib.hv_lk_track.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double]
     lib.hv_lk_track_device.argtypes = lib.hv_lk_track.argtypes
-    lib.hv_lk_track_device_on_stream.argtypes = [c_void_p, c_void_p] + list(lib.hv_lk_track.argtypes[1:])
+    lib.hv_lk_track_device_on_stream.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double]
     lib.hv_lk_track_batch_device.argtypes = [c_void_p, ctypes.POINTER(LkJob), c_int, c_int, c_double, c_double]
     lib.hv_ingest_create.argtypes = [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p)]
     lib.hv_ingest_destroy.argtypes = [c_void_p]

@@ -308,7 +308,7 @@ static int lk_check_pair(const char* who, hv_ctx* c, hv_pyr* a, hv_pyr* b)
     return HV_OK;
 }
 
-static int lk_track_batch_device_on(hv_ctx* c, cudaStream_t stream, const hv_lk_job* jobs, int njobs, int maxIter, double eps, double minEig)
+static int lk_track_batch_device_on(hv_ctx* c, cudaStream_t stream, const hv_lk_job* jobs, int njobs, int maxIter, double eps, double minEig, const float* initXY = nullptr)
 {
     if (!c || !jobs || njobs < 0) { hv_set_error("hv_lk_track_batch_device: invalid argument"); return HV_ERR_INVALID; }
     HV_CUDA(cudaSetDevice(c->device));
@@ -328,7 +328,7 @@ static int lk_track_batch_device_on(hv_ctx* c, cudaStream_t stream, const hv_lk_
             LkJob& d = L.jobs[i];
             d.prevIdx = j.prev->slot; d.nextIdx = j.next->slot; d.n = j.n; d.useInitial = j.use_initial;
             d.prevPts = (const float2*)j.d_prev_xy; d.nextPts = (float2*)j.d_next_xy;
-            d.status = j.d_status; d.trackStatus = j.d_track_status;
+            d.status = j.d_status; d.trackStatus = j.d_track_status; d.initPts = initXY && cnt == 1 ? (const float2*)initXY : nullptr;
         }
         L.njobs = cnt;
         lk_fill(L, c, maxLevel, maxIter, eps, minEig);
@@ -345,7 +345,7 @@ int hv_lk_track_batch_device(hv_ctx* c, const hv_lk_job* jobs, int njobs, int ma
 }
 
 static int lk_track_device_on(hv_ctx* c, cudaStream_t stream, hv_pyr* prev, hv_pyr* next, const float* dPrev, float* dNext, uint8_t* dStatus,
-                              int32_t* dTs, int n, int useInitial, int maxIter, double eps, double minEig)
+                              int32_t* dTs, int n, int useInitial, int maxIter, double eps, double minEig, const float* dInit = nullptr)
 {
     if (!c || n < 0) { hv_set_error("hv_lk_track_device: invalid argument"); return HV_ERR_INVALID; }
     if (n == 0) {                 // optical_flow.cpp:41-44: empty input, empty output (the pyramids are still validated)
@@ -354,17 +354,17 @@ static int lk_track_device_on(hv_ctx* c, cudaStream_t stream, hv_pyr* prev, hv_p
     }
     hv_lk_job j; j.prev = prev; j.next = next; j.d_prev_xy = dPrev; j.d_next_xy = dNext; j.d_status = dStatus;
     j.d_track_status = dTs; j.n = n; j.use_initial = useInitial;
-    return lk_track_batch_device_on(c, stream, &j, 1, maxIter, eps, minEig);
+    return lk_track_batch_device_on(c, stream, &j, 1, maxIter, eps, minEig, dInit);
 }
 int hv_lk_track_device(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* dPrev, float* dNext, uint8_t* dStatus,
                        int32_t* dTs, int n, int useInitial, int maxIter, double eps, double minEig)
 {
     return lk_track_device_on(c, c ? c->stream : nullptr, prev, next, dPrev, dNext, dStatus, dTs, n, useInitial, maxIter, eps, minEig);
 }
-int hv_lk_track_device_on_stream(hv_ctx* c, void* cudaStream, hv_pyr* prev, hv_pyr* next, const float* dPrev, float* dNext, uint8_t* dStatus,
-                                 int32_t* dTs, int n, int useInitial, int maxIter, double eps, double minEig)
+int hv_lk_track_device_on_stream(hv_ctx* c, void* cudaStream, hv_pyr* prev, hv_pyr* next, const float* dPrev, const float* dInit, float* dNext,
+                                 uint8_t* dStatus, int32_t* dTs, int n, int maxIter, double eps, double minEig)
 {
-    return lk_track_device_on(c, (cudaStream_t)cudaStream, prev, next, dPrev, dNext, dStatus, dTs, n, useInitial, maxIter, eps, minEig);
+    return lk_track_device_on(c, (cudaStream_t)cudaStream, prev, next, dPrev, dNext, dStatus, dTs, n, dInit ? 1 : 0, maxIter, eps, minEig, dInit);
 }
 
 int hv_lk_track(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* prevXY, float* nextXY, uint8_t* status,
@@ -390,7 +390,7 @@ int hv_lk_track(hv_ctx* c, hv_pyr* prev, hv_pyr* next, const float* prevXY, floa
         LkJob& d = L.jobs[0];
         d.prevIdx = prev->slot; d.nextIdx = next->slot; d.n = n; d.useInitial = useInitial;
         d.prevPts = (const float2*)(hd + oPrev); d.nextPts = (float2*)(hd + oNext);
-        d.status = hd + oSt; d.trackStatus = (int32_t*)(hd + oTs);
+        d.status = hd + oSt; d.trackStatus = (int32_t*)(hd + oTs); d.initPts = nullptr;
         L.njobs = 1;
         lk_fill(L, c, HV_MAX_LEVELS, maxIter, eps, minEig);
         volatile unsigned* flag = (volatile unsigned*)(hs + c->stageBytes);

@@ -47,6 +47,7 @@ struct LkJob {
     float2* nextPts;            // device; in: initial guess (if useInitial), out: end point
     uint8_t* status;            // device; OpenCV status 1 = ok, 0 = failed
     int32_t* trackStatus;       // device, optional; tracker::Feature::Status (src/tracker/track.hpp:9-20)
+    const float2* initPts;      // device, optional: the initial guess lives here instead of in nextPts (which is then only written)
 };
 
 struct LkLaunch {

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32) hv_lk_kernel(LkLaunch L
     const int col = min(lane, WIN);            // lanes above WIN duplicate the last column (results unused)
 
     const float2 prevPt = job.prevPts[f];
-    float2 outPt = job.useInitial ? job.nextPts[f] : prevPt;
+    float2 outPt = job.useInitial ? (job.initPts ? job.initPts[f] : job.nextPts[f]) : prevPt;
     int status = 1;
 
     __shared__ __align__(16) uint8_t s_region[LK_WARPS_PER_CTA][LK_REG_H * LK_REG_W];
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(NW * 32) hv_lk_cta_kernel(LkLaunch L)
     const int nr = max(0, min(RPW, WIN - r0));              // rows owned (the last warp may own fewer)
 
     const float2 prevPt = job.prevPts[f];
-    float2 outPt = job.useInitial ? job.nextPts[f] : prevPt;
+    float2 outPt = job.useInitial ? (job.initPts ? job.initPts[f] : job.nextPts[f]) : prevPt;
     int status = 1;
     int Ipat[RPW], dIpat[RPW];
 

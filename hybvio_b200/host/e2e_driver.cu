@@ -140,10 +140,10 @@ int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
         if (rc == HV_OK) rc = hv_ekf_predicted_mean_device(ekf, d_mean);       // ... its mean part first: all the flow predictor reads ...
         if (rc == HV_OK) rc = hv_ekf_flush(ekf);                               // ... the full launch (covariance) on the library's own stream
         if (rc != HV_OK) break;
-        cudaMemcpyAsync(d_next, f.d_init_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToDevice, sb);     // (the predictor's output)
         cudaStreamWaitEvent(sb, evPyr, 0);                                     // issued a whole frame of filter work ago: has fired
-        rc = hv_lk_track_device_on_stream(trk, sb, p[0], cur[0], d_points, d_next, d_status, d_ts, n, 1, 20, 0.03, 1e-3);
-        if (rc == HV_OK && f.right) rc = hv_lk_track_device_on_stream(trk, sb, cur[0], cur[1], d_next, d_next2, d_status, d_ts, n, 0, 20, 0.03, 1e-3);
+        // (f.d_init_xy: the predictor's output, read where it is)
+        rc = hv_lk_track_device_on_stream(trk, sb, p[0], cur[0], d_points, f.d_init_xy, d_next, d_status, d_ts, n, 20, 0.03, 1e-3);
+        if (rc == HV_OK && f.right) rc = hv_lk_track_device_on_stream(trk, sb, cur[0], cur[1], d_next, nullptr, d_next2, d_status, d_ts, n, 20, 0.03, 1e-3);
         if (rc != HV_OK) break;
         cudaEventRecord(evLk, sb);
         rc = hv_ekf_run_device(ekf, f.ops + f.nimu, f.nops - f.nimu);         // joins the covariance launch, then the visual updates

@@ -102,9 +102,11 @@ int hv_lk_track_device(hv_ctx* ctx, hv_pyr* prev, hv_pyr* next, const float* d_p
 /* The same launch on a stream of the CALLER instead of the context's own (cuda_stream: a cudaStream_t of the same device). For pipelines
  * that keep the tracker and the filter on ONE stream, so that the optical flow of a frame, its visual updates and the next propagation
  * follow each other without cross-stream events, while the pyramid builds keep the context's stream. The caller orders the call
- * behind the builds of both pyramids (an event recorded on hv_ctx_stream(ctx)) and the next build of either pyramid behind this call. */
-int hv_lk_track_device_on_stream(hv_ctx* ctx, void* cuda_stream, hv_pyr* prev, hv_pyr* next, const float* d_prev_xy, float* d_next_xy,
-                                 uint8_t* d_status, int32_t* d_track_status, int n, int use_initial, int max_iter, double eps, double min_eig);
+ * behind the builds of both pyramids (an event recorded on hv_ctx_stream(ctx)) and the next build of either pyramid behind this call.
+ * d_init_xy (n x 2, may be NULL = start at d_prev_xy): the predicted end points (OPTFLOW_USE_INITIAL_FLOW) are READ from there and the
+ * results written to d_next_xy -- a predictor's output buffer is used as it is, no copy into the result buffer first. */
+int hv_lk_track_device_on_stream(hv_ctx* ctx, void* cuda_stream, hv_pyr* prev, hv_pyr* next, const float* d_prev_xy, const float* d_init_xy,
+                                 float* d_next_xy, uint8_t* d_status, int32_t* d_track_status, int n, int max_iter, double eps, double min_eig);
 /* Several independent LK calls (e.g. one per stream) in one launch; device pointers. */
 typedef struct hv_lk_job {
     hv_pyr* prev; hv_pyr* next;
