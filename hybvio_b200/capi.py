@@ -256,6 +256,12 @@ class Context:
                                           1 if use_initial else 0, max_iter, eps, min_eig), "hv_lk_track_device")
 
 
+    def lk_track_device_on_stream(self, cuda_stream, prev, nxt, d_prev, d_init, d_next, d_status, d_ts, n, max_iter=20, eps=0.03, min_eig=1e-3):
+        """The same launch on a stream of the caller; d_init (or None): predicted end points, read from their own buffer."""
+        check(self.lib.hv_lk_track_device_on_stream(self.h, c_void_p(int(cuda_stream)), prev.h, nxt.h, _ptr(d_prev), _ptr(d_init), _ptr(d_next),
+                                                    _ptr(d_status), _ptr(d_ts), n, max_iter, eps, min_eig), "hv_lk_track_device_on_stream")
+
+
 def _stride0(im):
     if isinstance(im, np.ndarray):
         return im.strides[0]

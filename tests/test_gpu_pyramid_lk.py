@@ -205,4 +205,18 @@ def test_pyramid_from_device_frame_and_device_lk(hv, oracle_lk):
     hv.sync()
     n_host, st_host, ts_host = hv.lk_track(pl, pr, pts)
     assert np.array_equal(d_next.cpu().numpy(), n_host) and np.array_equal(d_ts.cpu().numpy(), ts_host)
+    # the same launch on a stream of the caller, with the initial guess in its own buffer: bit-identical to use_initial in place
+    init = (pts + np.array([1.5, -0.75], dtype=np.float32)).astype(np.float32)
+    d_init = torch.from_numpy(init).cuda()
+    d_a = d_init.clone(); d_b = torch.zeros_like(d_prev)
+    st2 = torch.zeros(150, dtype=torch.uint8, device="cuda"); ts2 = torch.zeros(150, dtype=torch.int32, device="cuda")
+    hv.lk_track_device(pl, pr, d_prev, d_a, d_st, d_ts, 150, True)
+    hv.sync()
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    hv.lk_track_device_on_stream(side.cuda_stream, pl, pr, d_prev, d_init, d_b, st2, ts2, 150)
+    hv.lk_track_device_on_stream(side.cuda_stream, pl, pr, d_prev, None, d_next, st2, ts2, 150)      # no guess: starts at the previous points
+    side.synchronize()
+    assert np.array_equal(d_a.cpu().numpy(), d_b.cpu().numpy()) and np.array_equal(d_init.cpu().numpy(), init)
+    assert np.array_equal(d_next.cpu().numpy(), n_host) and np.array_equal(ts2.cpu().numpy(), ts_host)
     pl.release(); pr.release()
