@@ -298,6 +298,7 @@ __device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int
 #pragma unroll
             for (int kt = 0; kt < 2; kt++) hv_dmma(c0, c1, linv[g8 * 8 + kt * 4 + t4], bf[kt]);
             const int col = 8 * ct + 2 * t4;
+            __syncwarp();                             // in place: every lane's loads of the tile precede any lane's store (racecheck, session W)
             if (g8 < nb) { if (col < ncols) T[(size_t)(r0 + g8) * W + col] = c0; if (col + 1 < ncols) T[(size_t)(r0 + g8) * W + col + 1] = c1; }
         }
         EK2_ELIM_MARK(1);
