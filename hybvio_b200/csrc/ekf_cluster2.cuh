@@ -171,6 +171,7 @@ __device__ __forceinline__ void ek2_dmma_chunk(int M, int Nn, int K, int MT, int
 #pragma unroll
         for (int q = 0; q < NI; q++) hv_dmma(c0[q], c1[q], a0[q], b0[q]);
     }
+    __syncwarp();                                     // (a product in place: lanes with clamped indices have read what other lanes store)
 #pragma unroll
     for (int q = 0; q < NI; q++)
         if (row[q] < M && col[q] < Nn) store(row[q], col[q], c0[q], c1[q]);
@@ -332,6 +333,7 @@ __device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int
                 double c0 = crow[min(coli, ncols - 1)], c1 = crow[min(coli + 1, ncols - 1)];
                 hv_dmma(c0, c1, k0v ? -x0 : 0.0, x0);
                 hv_dmma(c0, c1, k1v ? -x1 : 0.0, x1);
+                __syncwarp();                         // lanes past the last row read CLAMPED elements that other lanes store (values unused)
                 if (rowi < n) { if (coli < ncols) crow[coli] = c0; if (coli + 1 < ncols) crow[coli + 1] = c1; }
             } else if (worker) {
                 int mt = first, nt, idx = min(lo, total - 1);
@@ -352,6 +354,7 @@ __device__ __forceinline__ bool ek2_block_eliminate(double* T, int W, int n, int
                     const double b0 = rowk0[bn], b1 = rowk1[bn];                       // B[k][nn] = U_j[k][8 nt + nn]
                     hv_dmma(c0, c1, a0, b0);
                     hv_dmma(c0, c1, a1, b1);
+                    __syncwarp();
                     if (rowi < n) { if (coli < ncols) crow[coli] = c0; if (coli + 1 < ncols) crow[coli + 1] = c1; }
                     if (++nt == CT) { mt++; nt = mt; }
                 }
