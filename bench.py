@@ -831,7 +831,8 @@ def run_ours(args):
         dom = max((k for k in shares if k.startswith(domfam)), key=lambda k: shares[k])
         traffic = None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same launch from the committed ncu --set full capture
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))
+            name = "r02_ncu_full_summary.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_ncu_full_summary.json")) else "r01_ncu_full_summary.json"
+            prof = json.load(open(os.path.join(ROOT, "profiles", name)))
             key = "check+update n=84" if "n=84" in dom else "augment" if "augment" in dom else None
             traffic = next((int(e["dram_bytes"]) for e in prof["kernels"] if key and key in e["launch"]), None)
         except Exception:
