@@ -480,7 +480,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     __shared__ double s_linv[EK2_LINV_DOUBLES];
     __shared__ int s_bad;
     __shared__ __align__(16) double s_m[EK2_MAXN];
-    __shared__ __align__(8) unsigned long long s_bar[2];      // [0] staging (two arrivals: H, then P block + mean), [1] Z gather
+    __shared__ __align__(8) unsigned long long s_bar[4];      // [0] staging (two arrivals: H, then P block + mean), [1] Z gather, [2] / [3] S exchange
     const int c = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, nwarps = EK2_NT / 32;
     const int N = a.b.N, n = a.n, l = a.l;
@@ -513,7 +513,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     // side aligned); otherwise the loops below do the same work.
     const bool bulk = (N & 1) == 0 && ((((size_t)P) | ((size_t)a.b.m) | ((size_t)a.b.cwork) | ((size_t)a.specP) | ((size_t)a.specM) | ((size_t)sm)) & 15) == 0;
     const bool bulkH = bulk && a.op == EKF_OP_DENSE && ((n * l) & 1) == 0 && (((size_t)a.H) & 15) == 0;
-    if (tid == 0) { ek2_bar_init(&s_bar[0], 2); ek2_bar_init(&s_bar[1], 1); }
+    if (tid == 0) { ek2_bar_init(&s_bar[0], 2); ek2_bar_init(&s_bar[1], 1); ek2_bar_init(&s_bar[2], 1); ek2_bar_init(&s_bar[3], 1); }
     if (bulk) __syncthreads();                        // the barriers exist before anybody waits on them
     // ---- the measurement matrix does not depend on earlier kernels: stage it before waiting for them
     const bool lateH = a.lateH != 0 && a.op == EKF_OP_DENSE;
@@ -550,14 +550,22 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     if (joseph) {
         const int drop = a.dropIdx;
         for (int i = tid; i < N; i += EK2_NT) { const int s = ek2_aug_src(i, drop); s_m[i] = s < 0 ? 0.0 : a.b.m[s]; }
+        // deferred maintainPositiveSemiDefinite (ekf.cpp:1059-1067): 0.5 (P + P') evaluated while the shift reads P. Two passes so that BOTH
+        // reads are coalesced: P(si, sj) with the row index running fastest, the mirror P(sj, si) with the column index of the block
+        // running fastest (one pass reading both had 8-byte loads a whole column apart: 3200 separate sectors per CTA)
         for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
             const int i = idx % N, j = J0 + idx / N;
             const int si = ek2_aug_src(i, drop), sj = ek2_aug_src(j, drop);
-            double v = (si < 0 || sj < 0) ? 0.0 : P[si + (size_t)sj * N];
-            // deferred maintainPositiveSemiDefinite (ekf.cpp:1059-1067): 0.5 (P + P') evaluated while the shift reads P
+            PB[i + (size_t)(idx / N) * LD] = (si < 0 || sj < 0) ? 0.0 : P[si + (size_t)sj * N];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
+            const int jj = idx % Bc, i = idx / Bc, j = J0 + jj;
+            const int si = ek2_aug_src(i, drop), sj = ek2_aug_src(j, drop);
+            double v = PB[i + (size_t)jj * LD];
             if (a.symFirst && si >= 0 && sj >= 0 && si != sj) v = 0.5 * (v + P[sj + (size_t)si * N]);
             if (i == j && i >= EKF_CAM && i < EKF_CAM + EKF_POSE) v += (i - EKF_CAM) < 3 ? a.augNoisePos : a.augNoiseOri;
-            PB[i + (size_t)(idx / N) * LD] = v;
+            PB[i + (size_t)jj * LD] = v;
         }
         if (bulk && tid == 0) ek2_bar_expect(&s_bar[0], 0);
     } else if (bulk) {
@@ -661,6 +669,7 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
                       });
     }
     EK2_PHASE(3);
+    if (bigS && bulk) ek2_fence_async_all();          // the partials are read by the neighbours' bulk copies
     cluster.sync();                                   // #1: every partial S is in place (and from here on shared memory is exposed)
     // ---- reduce S through distributed shared memory, fixed order r = 0 .. C-1 (+ R on the diagonal)
     {
@@ -673,6 +682,42 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
                     for (int r = 0; r < C; r++) s += cluster.map_shared_rank(RS, r)[i * n + ip];
                     if (i == ip) s += a.Rdiag;
                     T[(size_t)i * W + ip] = s;             // the own tableau is not read by anybody else
+                }
+            }
+            __syncthreads();
+        } else if (bigS && bulk && ETOT % (2 * C) == 0 && 2 * ETOT <= g.X) {
+            // Through L2 with bulk copies: the eight partial slices and, after the second barrier, the reduced S arrive in the region H
+            // occupied (dead since the partial product) by ONE round trip each, instead of one dependent load per entry and turn
+            const int E = ETOT / C, e0 = c * E;
+            double* SL = X + ETOT;                        // [C][E] partial slices
+            if (wrp == 0) {
+                if (lane == 0) ek2_bar_expect(&s_bar[2], (unsigned)(C * E * 8));
+                __syncwarp();
+                if (lane < C) ek2_bulk_g2s(SL + (size_t)lane * E, Spart + (size_t)lane * ETOT + e0, (unsigned)(E * 8), &s_bar[2]);
+            }
+            ek2_bar_wait(&s_bar[2], 0);
+            __syncthreads();
+            for (int q = tid; q < E; q += EK2_NT) {
+                const int e = e0 + q;
+                int i, ip; entry(e, i, ip);
+                double sacc = 0.0;
+                if (i < n && ip < n) {
+                    for (int r = 0; r < C; r++) sacc += SL[(size_t)r * E + q];
+                    if (i == ip) sacc += a.Rdiag;
+                }
+                Sred[e] = sacc;
+            }
+            ek2_fence_async_all();                        // the reduced slice is read by everybody's bulk copy
+            cluster.sync();                               // #2
+            if (tid == 0) { ek2_bar_expect(&s_bar[3], (unsigned)(ETOT * 8)); ek2_bulk_g2s(X, Sred, (unsigned)(ETOT * 8), &s_bar[3]); }
+            ek2_bar_wait(&s_bar[3], 0);
+            __syncthreads();
+            for (int tu = wrp; tu < ETOT / 64; tu += nwarps) {
+                int mt, nt; ek2_upper_tile(tu, mt, nt);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int q = lane + 32 * h, i = 8 * mt + (q >> 3), ip = 8 * nt + (q & 7);
+                    if (i < n && ip < n) T[(size_t)i * W + ip] = X[64 * tu + q];
                 }
             }
             __syncthreads();
