@@ -550,22 +550,16 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
     if (joseph) {
         const int drop = a.dropIdx;
         for (int i = tid; i < N; i += EK2_NT) { const int s = ek2_aug_src(i, drop); s_m[i] = s < 0 ? 0.0 : a.b.m[s]; }
-        // deferred maintainPositiveSemiDefinite (ekf.cpp:1059-1067): 0.5 (P + P') evaluated while the shift reads P. Two passes so that BOTH
-        // reads are coalesced: P(si, sj) with the row index running fastest, the mirror P(sj, si) with the column index of the block
-        // running fastest (one pass reading both had 8-byte loads a whole column apart: 3200 separate sectors per CTA)
         for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
             const int i = idx % N, j = J0 + idx / N;
             const int si = ek2_aug_src(i, drop), sj = ek2_aug_src(j, drop);
-            PB[i + (size_t)(idx / N) * LD] = (si < 0 || sj < 0) ? 0.0 : P[si + (size_t)sj * N];
-        }
-        __syncthreads();
-        for (int idx = tid; idx < N * Bc; idx += EK2_NT) {
-            const int jj = idx % Bc, i = idx / Bc, j = J0 + jj;
-            const int si = ek2_aug_src(i, drop), sj = ek2_aug_src(j, drop);
-            double v = PB[i + (size_t)jj * LD];
+            double v = (si < 0 || sj < 0) ? 0.0 : P[si + (size_t)sj * N];
+            // deferred maintainPositiveSemiDefinite (ekf.cpp:1059-1067): 0.5 (P + P') evaluated while the shift reads P (the mirror
+            // entries are a column apart each; reading them in a second, coalesced pass over the block was measured slower:
+            // 6.1 against 4.9 us for this phase, profiles/r02_ekf_phases_session_x.txt)
             if (a.symFirst && si >= 0 && sj >= 0 && si != sj) v = 0.5 * (v + P[sj + (size_t)si * N]);
             if (i == j && i >= EKF_CAM && i < EKF_CAM + EKF_POSE) v += (i - EKF_CAM) < 3 ? a.augNoisePos : a.augNoiseOri;
-            PB[i + (size_t)jj * LD] = v;
+            PB[i + (size_t)(idx / N) * LD] = v;
         }
         if (bulk && tid == 0) ek2_bar_expect(&s_bar[0], 0);
     } else if (bulk) {
@@ -685,9 +679,10 @@ __device__ __forceinline__ void ek2_body(EkfUpdateArgs& a, double* sm, Cluster c
                 }
             }
             __syncthreads();
-        } else if (bigS && bulk && ETOT % (2 * C) == 0 && 2 * ETOT <= g.X) {
+        } else if (bigS && bulk && ETOT >= 2048 && ETOT % (2 * C) == 0 && 2 * ETOT <= g.X) {
             // Through L2 with bulk copies: the eight partial slices and, after the second barrier, the reduced S arrive in the region H
             // occupied (dead since the partial product) by ONE round trip each, instead of one dependent load per entry and turn
+            // (n = 84: 5.4 -> 4.4 us; below ~57 rows the barriers of the copies cost more than they save: n = 40 measured 2.8 -> 3.6 us)
             const int E = ETOT / C, e0 = c * E;
             double* SL = X + ETOT;                        // [C][E] partial slices
             if (wrp == 0) {
