@@ -123,7 +123,10 @@ int hv_dev_run(hv_ctx* trk, hv_ctx* ekf_ctx, hv_pyr** pyr, hv_ekf* ekf, const fl
     cudaEventCreateWithFlags(&evPyr, cudaEventDisableTiming); cudaEventCreateWithFlags(&evLk, cudaEventDisableTiming);
     hv_ctx_sync(trk); hv_ctx_sync(ekf_ctx);
     double* d_mean = nullptr;
-    if (cudaMalloc(&d_mean, 20 * sizeof(double)) != cudaSuccess) return HV_ERR_OOM;
+    if (cudaMalloc(&d_mean, 20 * sizeof(double)) != cudaSuccess) {
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(evLk); cudaEventDestroy(evPyr);
+        return HV_ERR_OOM;
+    }
     cudaEventRecord(e0, sb);
     cudaEventRecord(evLk, sb);
     int rc = HV_OK, lastOps = 0;

@@ -208,6 +208,10 @@ int hv_ekf_flush(hv_ekf* ekf);
  * (src/odometry/backend.cpp:547-600 reads ekf->position() / orientation() and the pose trail, which predict() does not change), so that
  * the tracker can start while the covariance is still being propagated. Bit-identical to what the full launch leaves in the state. */
 int hv_ekf_predicted_mean_device(hv_ekf* ekf, double* d_mean20);
+/* After this call the queued FULL launch (hv_ekf_flush, or whatever issues the queue next) goes to a stream of the library instead of the
+ * context's stream, and the next call that touches the filter waits for it there: work the caller puts on the context's stream in between
+ * without touching the filter -- the optical flow of a pipeline that keeps tracker and filter on one stream -- does not queue behind the
+ * covariance propagation. (Not in throughput mode, HV_EKF_NO_PDL=1.) */
 int hv_ekf_set_imu_batching(hv_ekf* ekf, int max_samples);
 
 /* The fixed-H updates (ekf.cpp:573-677); rate limits and early-outs as in the reference. Asynchronous. */

@@ -116,6 +116,10 @@ def test_bookkeeping_and_error_codes(cuda):
     H = np.random.RandomState(0).normal(0, 0.1, (8, 27))
     assert e.visual_check(H, np.zeros(8), np.ones(8) * 100, -1.0)[0] == 0
     assert e.visual_check(H, np.zeros(8), np.ones(8) * 100, 0.05, rmse_thr=1.0)[0] == 2
+    with pytest.raises(capi.HvError):
+        e.run_device_results(3)                 # no device list has run: nothing to report
+    st, chi2 = e.run_device_results(0)
+    assert len(st) == 0
     e.close()
 
 
