@@ -173,6 +173,7 @@ def _bind_ekf(lib):
     lib.hv_ekf_set_imu_batching.argtypes = [c_void_p, c_int]
     lib.hv_ekf_run_device.argtypes = [c_void_p, ctypes.POINTER(EkfOp), c_int]
     lib.hv_ekf_predicted_mean_device.argtypes = [c_void_p, c_void_p]
+    lib.hv_ekf_predicted_mean.argtypes = [c_void_p, c_void_p]
     lib.hv_ekf_run_device_results.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double)]
     lib.hv_ekf_run_host.argtypes = [c_void_p, ctypes.POINTER(EkfOp), c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double), c_void_p]
     lib.hv_ekf_normalize_quaternions.argtypes = [c_void_p, c_int]
@@ -460,6 +461,12 @@ class Ekf:
     def predicted_mean_device(self, d_ptr):
         """Mean part of the queued IMU samples into 20 doubles of DEVICE memory (own small launch; the full predict stays queued)."""
         check(self.lib.hv_ekf_predicted_mean_device(self.h, c_void_p(int(d_ptr))), "hv_ekf_predicted_mean_device")
+
+    def predicted_mean(self):
+        """The 20 inertial states the queued IMU samples lead to (host array); the full predict stays queued."""
+        m = np.zeros(20)
+        check(self.lib.hv_ekf_predicted_mean(self.h, _ptr(m)), "hv_ekf_predicted_mean")
+        return m
 
     def run_device_results(self, nops):
         """(vu_status, chi2) arrays of the last run_device list (entries of non-VISUAL ops: -1 / nan); waits for the list."""

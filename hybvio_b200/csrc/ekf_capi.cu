@@ -50,6 +50,7 @@ struct hv_ekf {
     double* cworkSide = nullptr;            // exchange areas and result words of the clusters on the side stream
     double* resSide = nullptr;
     double* d_opres = nullptr;              // hv_ekf_run_device: result words per op of the list (4 doubles each, HV_RUN_MAX_OPS)
+    double* d_mean20 = nullptr;             // hv_ekf_predicted_mean: device scratch
     std::vector<unsigned char> lastVisual;  // per op of the last hv_ekf_run_device list: 1 = VISUAL (has result words)
     double hostTimes[4] = {0, 0, 0, 0};     // last hv_ekf_run_host list: {issue, wait, total} in us, number of ops (hv_ekf_debug_host_times)
     // host bookkeeping, exactly the members of EKFImplementation (ekf.cpp:145-151)
@@ -136,6 +137,7 @@ static int ekf_check(const hv_ekf* e, const char* who)
 
 extern "C" { static int flush_pending(hv_ekf* e); }
 static int join_side(hv_ekf* e);
+extern "C" { static int staging_acquire(hv_ekf* e); }
 // EKF_ENTER_LAZY: entry points that only extend the deferred queue; EKF_ENTER: everything else issues the queue first
 #define EKF_ENTER_LAZY(e, who)                         \
     do { int rc_ = ekf_check(e, who); if (rc_ != HV_OK) return rc_; HV_CUDA(cudaSetDevice((e)->ctx->device)); } while (0)
@@ -215,7 +217,7 @@ static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
     const size_t cworkD = (size_t)(EKF_MAX_BATCH + 1) * 10 * NN;       // one exchange area per cluster of a check batch (+ its augmentation)
     e->inDoubles = (size_t)EKF_MAX_BATCH * (NN + 2 * N);
     const size_t resD = (size_t)EKF_RES_STRIDE * (EKF_MAX_BATCH + 1);
-    const size_t total = N + NN + NN + workD + 2 * cworkD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + 2 * resD + e->inDoubles + N + 4 * HV_RUN_MAX_OPS;
+    const size_t total = N + NN + NN + workD + 2 * cworkD + EKF_SMALL_MAXN * EKF_SMALL_MAXL + 144 + 400 + 2 * resD + e->inDoubles + N + 4 * HV_RUN_MAX_OPS + 32;
     cudaError_t err = cudaMalloc(&e->d_block, total * sizeof(double));
     if (err != cudaSuccess) { delete e; hv_set_error("hv_ekf_create: cudaMalloc failed: %s", cudaGetErrorString(err)); return HV_ERR_OOM; }
     cudaMemsetAsync(e->d_block, 0, total * sizeof(double), c->stream);
@@ -224,7 +226,8 @@ static int ekf_alloc(hv_ctx* c, const hv_ekf_params* prm, hv_ekf** out)
     e->b.Hs = p; p += EKF_SMALL_MAXN * EKF_SMALL_MAXL; e->b.Q = p; p += 144; e->b.dydx = p; p += 400; e->b.res = p; p += EKF_RES_STRIDE * (EKF_MAX_BATCH + 1);
     e->d_in = p; p += e->inDoubles;
     e->m2 = p; p += N;
-    e->cworkSide = p; p += cworkD; e->resSide = p; p += resD; e->d_opres = p;
+    e->cworkSide = p; p += cworkD; e->resSide = p; p += resD; e->d_opres = p; p += 4 * HV_RUN_MAX_OPS;
+    e->d_mean20 = p;
     e->b.N = e->N; e->b.trail = e->trail; e->b.mapDim = e->mapDim;
     err = cudaMallocHost(&e->h_pin, (e->inDoubles + N + 8 + EKF_RES_STRIDE * EKF_MAX_BATCH) * sizeof(double));
     if (err != cudaSuccess) { cudaFree(e->d_block); delete e; hv_set_error("hv_ekf_create: cudaMallocHost failed"); return HV_ERR_OOM; }
@@ -543,6 +546,21 @@ int hv_ekf_predicted_mean_device(hv_ekf* e, double* dMean20)
     HV_CUDA(ekf_launch_predict(a, s));
     e->ctx->launches++;
     e->meanIssued = true;
+    return HV_OK;
+}
+
+int hv_ekf_predicted_mean(hv_ekf* e, double* mean20)
+{
+    EKF_ENTER_LAZY(e, "hv_ekf_predicted_mean");
+    if (!mean20) { hv_set_error("hv_ekf_predicted_mean: NULL output"); return HV_ERR_INVALID; }
+    int rc = staging_acquire(e);
+    if (rc != HV_OK) return rc;
+    rc = hv_ekf_predicted_mean_device(e, e->d_mean20);
+    if (rc != HV_OK) return rc;
+    double* hout = e->h_pin;
+    HV_CUDA(cudaMemcpyAsync(hout, e->d_mean20, sizeof(double) * EKF_INER, cudaMemcpyDeviceToHost, e->ctx->stream));
+    HV_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    memcpy(mean20, hout, sizeof(double) * EKF_INER);
     return HV_OK;
 }
 

@@ -57,6 +57,7 @@ int hv_adapter_e2e_run(int width, int height, int maxTracks, int maxLevel, int t
                                                                                            const_cast<uint8_t*>(p)));
     };
     clk::time_point t0 = clk::now();
+    double predictorSink = 0.0;
     for (int k = 0; k < nframes; k++) {
         if (k == warmup) { t0 = clk::now(); nCheck = nInlier = nUpdate = 0; }
         const hv_adapter_frame& fr = frames[k];
@@ -64,6 +65,12 @@ int hv_adapter_e2e_run(int width, int height, int maxTracks, int maxLevel, int t
             const double* u = fr.imu + 7 * s;
             ekf->predict(u[0], Eigen::Vector3d(u[1], u[2], u[3]), Eigen::Vector3d(u[4], u[5], u[6]));
             ekf->normalizeQuaternions(true);
+        }
+        // the flow predictor reads the propagated pose and the newest pose of the trail before the optical flow (backend.cpp:547-600)
+        {
+            const Eigen::Vector3d pp = ekf->position(), hp = ekf->historyPosition(0);
+            const Eigen::Vector4d po = ekf->orientation(), ho = ekf->historyOrientation(0);
+            predictorSink += pp[0] + po[0] + hp[0] + ho[0];
         }
         auto pyrL = factory->compute(image(fr.left));
         std::shared_ptr<tracker::ImagePyramid> pyrR;
@@ -97,6 +104,7 @@ int hv_adapter_e2e_run(int width, int height, int maxTracks, int maxLevel, int t
     }
     if (wall_ms) *wall_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
     if (counts) { counts[0] = nCheck; counts[1] = nInlier; counts[2] = nUpdate; }
+    if (pose_out && !(predictorSink == predictorSink)) pose_out[0] = predictorSink;      // (keeps the reads; NaN propagates)
     return 0;
 }
 }

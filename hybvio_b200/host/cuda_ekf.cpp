@@ -35,7 +35,7 @@ struct CudaEKF : public EKF {
     const double noiseScale;
     mutable Eigen::VectorXd m;          // host mirrors
     mutable Eigen::MatrixXd P;
-    mutable bool mStale = true, PStale = true;
+    mutable bool mStale = true, PStale = true, inertialOnly = false;   // inertialOnly: the mirror is stale in its 20 inertial states only
 
     explicit CudaEKF(const Parameters& p)
         : parameters(p), camPoseCount(p.odometry.cameraTrailLength), hybridMapDim(p.odometry.hybridMapSize * MAP_POINT_DIM),
@@ -56,18 +56,29 @@ struct CudaEKF : public EKF {
     }
     CudaEKF(const CudaEKF& o)
         : EKF(o), parameters(o.parameters), camPoseCount(o.camPoseCount), hybridMapDim(o.hybridMapDim), stateDim(o.stateDim),
-          noiseScale(o.noiseScale), m(o.m), P(o.P), mStale(o.mStale), PStale(o.PStale) {
+          noiseScale(o.noiseScale), m(o.m), P(o.P), mStale(o.mStale), PStale(o.PStale), inertialOnly(o.inertialOnly) {
         HV(hv_ekf_clone(o.h, &h));
     }
     ~CudaEKF() override { hv_ekf_destroy(h); }
     std::unique_ptr<EKF> clone() const final { return std::unique_ptr<EKF>(new CudaEKF(*this)); }
 
-    void touched() { mStale = true; PStale = true; }
-    const Eigen::VectorXd& mean() const { if (mStale) { HV(hv_ekf_download(h, m.data(), nullptr)); mStale = false; } return m; }
+    void touched() { mStale = true; inertialOnly = false; PStale = true; }
+    // predict() and normalizeQuaternions(true) change the 20 inertial states only: behind a burst of them the mirror is refreshed from the
+    // mean launch of the queued burst (hv_ekf_predicted_mean: ~5 us + 160 bytes) instead of the full launch and the whole mean -- what
+    // the flow predictor's position() / orientation() reads cost (backend.cpp:547-600)
+    void predicted() { if (!mStale) inertialOnly = true; mStale = true; PStale = true; }
+    const Eigen::VectorXd& mean() const {
+        if (mStale) {
+            if (inertialOnly) HV(hv_ekf_predicted_mean(h, m.data()));
+            else HV(hv_ekf_download(h, m.data(), nullptr));
+            mStale = false; inertialOnly = false;
+        }
+        return m;
+    }
     const Eigen::MatrixXd& cov() const { if (PStale) { HV(hv_ekf_download(h, nullptr, P.data())); PStale = false; } return P; }
 
     void initializeOrientation(const Eigen::Vector3d& xa) final { HV(hv_ekf_initialize_orientation(h, xa.data())); touched(); }
-    void predict(double t, const Eigen::Vector3d& xg, const Eigen::Vector3d& xa) final { HV(hv_ekf_predict(h, t, xg.data(), xa.data())); touched(); }
+    void predict(double t, const Eigen::Vector3d& xg, const Eigen::Vector3d& xa) final { HV(hv_ekf_predict(h, t, xg.data(), xa.data())); predicted(); }
     Eigen::Vector3d position() const final { return mean().segment(POS, 3); }
     Eigen::Vector3d velocity() const final { return mean().segment(VEL, 3); }
     Eigen::Vector4d orientation() const final { return mean().segment(ORI, 4); }
@@ -122,14 +133,17 @@ struct CudaEKF : public EKF {
 
     void conditionOnLastPose() final { HV(hv_ekf_condition_on_last_pose(h)); touched(); }
     void lockBiases() final { HV(hv_ekf_lock_biases(h)); touched(); }
-    void normalizeQuaternions(bool onlyCurrent) final { HV(hv_ekf_normalize_quaternions(h, onlyCurrent ? 1 : 0)); mStale = true; }
+    void normalizeQuaternions(bool onlyCurrent) final {
+        HV(hv_ekf_normalize_quaternions(h, onlyCurrent ? 1 : 0));
+        if (onlyCurrent) { if (!mStale) inertialOnly = true; mStale = true; } else { mStale = true; inertialOnly = false; }
+    }
     void setFirstSampleTime(double t) final { HV(hv_ekf_set_first_sample_time(h, t)); }
     bool isPositiveSemiDefinite() final {   // "Expensive, use only for debugging" (ekf.cpp:1043-1057)
         Eigen::SelfAdjointEigenSolver<Eigen::MatrixXd> es(cov());
         return es.info() == Eigen::Success && es.eigenvalues().minCoeff() >= 0.0;
     }
     void maintainPositiveSemiDefinite() final { HV(hv_ekf_symmetrize(h)); PStale = true; }
-    void setState(const Eigen::VectorXd& m_) final { HV(hv_ekf_upload(h, m_.data(), nullptr)); mStale = true; }
+    void setState(const Eigen::VectorXd& m_) final { HV(hv_ekf_upload(h, m_.data(), nullptr)); mStale = true; inertialOnly = false; }
     void setStateCovariance(const Eigen::MatrixXd& P_) final { HV(hv_ekf_upload(h, nullptr, P_.data())); PStale = true; }
     void setProcessNoise(const Eigen::MatrixXd& Q_) final { Eigen::Matrix<double, Q_DIM, Q_DIM> q = Q_; HV(hv_ekf_set_process_noise(h, q.data())); }
     double getPlatformTime() const final { return hv_ekf_platform_time(h); }

@@ -208,6 +208,9 @@ int hv_ekf_flush(hv_ekf* ekf);
  * (src/odometry/backend.cpp:547-600 reads ekf->position() / orientation() and the pose trail, which predict() does not change), so that
  * the tracker can start while the covariance is still being propagated. Bit-identical to what the full launch leaves in the state. */
 int hv_ekf_predicted_mean_device(hv_ekf* ekf, double* d_mean20);
+/* The same into host memory (launch, 160-byte read-back, one synchronisation): what odometry::EKF::position() / orientation() / velocity()
+ * cost behind a burst of predict() calls -- the flow predictor's reads -- instead of the full launch plus a read-back of the whole mean. */
+int hv_ekf_predicted_mean(hv_ekf* ekf, double* mean20);
 /* After this call the queued FULL launch (hv_ekf_flush, or whatever issues the queue next) goes to a stream of the library instead of the
  * context's stream, and the next call that touches the filter waits for it there: work the caller puts on the context's stream in between
  * without touching the filter -- the optical flow of a pipeline that keeps tracker and filter on one stream -- does not queue behind the

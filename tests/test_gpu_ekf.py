@@ -268,6 +268,7 @@ def test_predicted_mean_launch_matches_full_predict(cuda):
         a.predicted_mean_device(d.data_ptr())
         torch.cuda.synchronize()
         pred = d.cpu().numpy().copy()
+        assert np.array_equal(a.predicted_mean(), pred)          # host variant (what the adapter's position() / orientation() use)
         if burst == 2:
             a.flush()                           # the full launch goes to the covariance stream; the download below joins it
         m1, P1 = a.download()                   # issues the queued full launch (or waits for it)
